@@ -1,0 +1,1 @@
+// TEST INFRASTRUCTURE: placeholder; the declarations the reference needs live in boost/graph/adjacency_list.hpp.
