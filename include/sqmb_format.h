@@ -1,5 +1,5 @@
-// TEST INFRASTRUCTURE (oracle side).  Not part of the shipped product.
-//
+// SQMB = an uncompressed, memory-mappable stand-in for a coordinate-sorted BAM: the alignment-level
+// input format of the host packer (squid_b200/csrc/host) and of the test oracle's BamReader shim.
 // "SQMB" = an uncompressed, memory-mappable stand-in for a coordinate-sorted BAM.
 // It carries exactly the BamAlignment members the reference reads on the
 // segment-graph path (BamTools row), so the reference's own sources can be

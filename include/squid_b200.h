@@ -1,0 +1,155 @@
+/*
+ * squid_b200 — C ABI of the B200-native segment-graph construction path of SQUID.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer; its seam is four
+ * member functions of SegmentGraph_t, called once per run from the constructor and main():
+ *     BuildNode_STAR            src/SegmentGraph.h:77   (def. src/SegmentGraph.cpp:192)
+ *     BuildEdges                src/SegmentGraph.h:79   (def. src/SegmentGraph.cpp:1932)
+ *     ExactBPConcordantSupport  src/SegmentGraph.h:104  (def. src/SegmentGraph.cpp:3083)
+ *     SegmentGraph_t(graphfile) src/SegmentGraph.h:71   (node reload, def. src/SegmentGraph.cpp:126)
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the
+ * binding a SQUID maintainer adds to call them.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success
+ * or a negative SQG_E* code and never throws; a context is used by one host thread at a time;
+ * input arrays are caller-owned HOST memory unless a function says DEVICE, and are not modified;
+ * output arrays returned through `T**` are library-owned pinned host buffers that stay valid
+ * until the next call of the same function on the same context or sqg_destroy().  There is no
+ * CPU fallback: without a CUDA device sqg_create() fails with SQG_ENODEVICE.
+ */
+#ifndef SQUID_B200_H
+#define SQUID_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQG_OK 0
+#define SQG_EINVAL (-1)     /* bad argument / malformed batch (unsorted, RefID out of range, ...) */
+#define SQG_ENODEVICE (-2)  /* no usable CUDA device */
+#define SQG_ECUDA (-3)      /* CUDA runtime error, see sqg_last_error() */
+#define SQG_ESTATE (-4)     /* call order violated (e.g. build_edges before nodes exist) */
+#define SQG_EUNSUPPORTED (-5) /* input the reference itself handles with undefined behaviour, or BWA mode */
+#define SQG_ENOMEM (-6)
+
+typedef struct sqg_ctx sqg_ctx;
+
+/* The reference's Config globals that gate the path (src/Config.cpp:14-37). */
+typedef struct sqg_config {
+    int32_t using_star;        /* UsingSTAR        Config.cpp:18  (only 1 is implemented) */
+    int32_t max_lowphred_len;  /* Max_LowPhred_Len Config.cpp:20  (-pl) */
+    int32_t min_mapq;          /* Min_MapQual      Config.cpp:22, 221-222 (-mq; STAR default 255) */
+    int32_t concord_dist_pos;  /* Concord_Dist_Pos Config.cpp:24  (-dp) */
+    int32_t concord_dist_idx;  /* Concord_Dist_Idx Config.cpp:25  (-di) */
+    int32_t read_len;          /* ReadLen          Config.cpp:14, set by BuildChimericSBamRecord ReadRec.cpp:378-379 */
+} sqg_config;
+
+/* aux bits of a record */
+#define SQG_AUX_XA 1u        /* record.HasTag("XA")                       SegmentGraph.cpp:297 */
+#define SQG_AUX_IH_GT1 2u    /* IH tag present with value > 1             SegmentGraph.cpp:298-302 */
+#define SQG_AUX_CHIMNAME 8u  /* record.Name is in ChimName                SegmentGraph.cpp:302 */
+
+/*
+ * Struct-of-arrays batch of decoded alignment records, sorted by (ref_id, pos).
+ * One record = one BAM alignment line.  Blocks are the gap-free aligned blocks that
+ * ReadRec_t::ReadRec_t (src/ReadRec.cpp:46-87) derives from the CIGAR, in CIGAR order, with
+ * read_pos already strand-flipped (ReadRec.cpp:74-75) and poly-A/T blocks removed (ReadRec.cpp:62-72).
+ *   per record (32 B): ref_id, pos, mate_ref_id, mate_pos, end_pos (= GetEndPosition()),
+ *                      flag (BAM FLAG), total_len (ReadRec.cpp:16-18), lowphred_run (longest run of
+ *                      qualities below the -pm threshold, ReadRec.cpp:19-38), mapq, aux, blk_off
+ *   per block  (12 B): ref_pos, match_ref, read_pos, match_read
+ */
+typedef struct sqg_batch {
+    int64_t n_rec, n_blk;
+    const int32_t *ref_id, *pos, *mate_ref_id, *mate_pos, *end_pos;
+    const uint16_t *flag, *total_len, *lowphred_run;
+    const uint8_t *mapq, *aux;
+    const uint32_t *blk_off; /* n_rec + 1 entries */
+    const int32_t *blk_ref_pos, *blk_match_ref;
+    const uint16_t *blk_read_pos, *blk_match_read;
+} sqg_batch;
+
+/*
+ * Chimeric reads after the host loader (twin of BuildChimericSBamRecord, src/ReadRec.cpp:329-413):
+ * read i owns blocks [read_off[i], read_off[i+1]); the first n_first[i] of them are FirstRead, the
+ * rest SecondMate, each list sorted by read position.  Block arrays are IN/OUT for
+ * sqg_build_edges (LocateRead trims them in place, src/SegmentGraph.cpp:1229-1248).
+ */
+typedef struct sqg_chimeric {
+    int64_t n_reads, n_blk;
+    const uint32_t *read_off;  /* n_reads + 1 */
+    const uint16_t *n_first;
+    const int32_t *first_total_len, *second_total_len;
+    const uint8_t *first_lowphred, *second_lowphred; /* 0/1 */
+    const uint8_t *multi_filter;                      /* ReadRec_t::MultiFilter (always 0 in STAR mode) */
+    int32_t *blk_ref_id, *blk_ref_pos, *blk_read_pos, *blk_match_ref, *blk_match_read;
+    uint8_t *blk_is_reverse;
+} sqg_chimeric;
+
+/* Creates a context on CUDA device `device`.  ref_len[n_ref] = RefLength (ReadRec.cpp:274-279). */
+int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int32_t n_ref, int32_t device);
+void sqg_destroy(sqg_ctx *ctx);
+const char *sqg_last_error(const sqg_ctx *ctx);
+
+/*
+ * Replaces the three BamReader passes over the concordant BAM (SegmentGraph.cpp:293-296,
+ * 1570-1577, 3126-3129): the batch is copied to HBM once and stays resident for all phases.
+ * `first_record_index` is the global index of record 0 of this batch in the whole sorted stream
+ * (0 on a single GPU; the shard offset when the stream is range-sharded).
+ */
+int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *batch, int64_t first_record_index);
+/* Same, but the arrays of `batch` are DEVICE pointers that the caller keeps alive until sqg_destroy(). */
+int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *batch, int64_t first_record_index);
+
+/* Replaces the Chimrecord argument of BuildNode_STAR/BuildEdges (SegmentGraph.cpp:192, 1932). */
+int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *chim);
+
+/*
+ * Replaces SegmentGraph_t::BuildNode_STAR (SegmentGraph.cpp:192-831).
+ * Outputs n_nodes segments tiling every chromosome, and per node three (count, sum of MatchRef)
+ * pairs kept separate as the reference accumulates them: [0] discordant blocks (:773-779),
+ * [1] ReadsMain (:784-801), [2] ReadsOther (:806-823); count3/sumlen3 are [3][n_nodes] int32
+ * (the reference's accumulators are `int`).  `reads_other_nonempty` tells the host twin whether
+ * to perform the AvgDepth division (:804, :824).
+ */
+int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
+                    int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty);
+
+/* Replaces SegmentGraph_t(string graphfile)'s node reload (SegmentGraph.cpp:126-157): installs a node
+ * table (must tile the genome) so that edges/coverage can run on a stored graph. */
+int sqg_set_nodes(sqg_ctx *ctx, const int32_t *chr, const int32_t *pos, const int32_t *len, int64_t n_nodes);
+
+/*
+ * Replaces SegmentGraph_t::BuildEdges up to UpdateNodeLink (SegmentGraph.cpp:1932-1959):
+ * RawEdgesChim + RawEdgesOther + sort + run-length sum + drop Weight<=0.
+ * heads[i] bit0 = Head1, bit1 = Head2.  Chimeric blocks loaded by sqg_load_chimeric are trimmed
+ * in place (written back into the caller's sqg_chimeric arrays passed here).
+ */
+int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges,
+                    sqg_chimeric *chim_inout);
+
+/*
+ * Replaces the BAM pass of SegmentGraph_t::ExactBPConcordantSupport (SegmentGraph.cpp:3124-3166):
+ * (bp_chr, bp_pos)[n_bp] sorted by (chr, pos) as at :3109; cov_out[n_bp] = Coverages.
+ */
+int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, int64_t n_bp, int32_t *cov_out);
+
+/*
+ * Multi-GPU.  A range shard computes partial results; these expose them as DEVICE
+ * buffers so that the caller can run the NCCL exchange and hand the merged table back.
+ */
+int sqg_edges_device_table(sqg_ctx *ctx, uint64_t **d_keys, int32_t **d_weights, int64_t *n);
+int sqg_merge_edge_tables(sqg_ctx *ctx, const uint64_t *d_keys, const int32_t *d_weights, int64_t n,
+                          int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges);
+
+/* Device time in ms of the named phase/kernel of the most recent call ("classify", "seed", "depth_edges",
+ * "edge_sort", "coverage", ...), measured with CUDA events on the context's stream; <0 if unknown. */
+float sqg_phase_ms(const sqg_ctx *ctx, const char *name);
+/* Number of kernel launches issued by this context so far. */
+int64_t sqg_launch_count(const sqg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

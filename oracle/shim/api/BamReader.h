@@ -7,7 +7,7 @@
 #include <string>
 #include <vector>
 #include "BamAlignment.h"
-#include "../sqmb_format.h"
+#include "sqmb_format.h"
 namespace BamTools {
 struct SamSequence {
     std::string Name, Length;

@@ -1,0 +1,185 @@
+// Host twin of BuildChimericSBamRecord and the SoA packer.  See chimeric.h.
+#include "chimeric.h"
+
+#include <algorithm>
+#include <thread>
+
+namespace sqh {
+
+Alignment alignment_at(const SqmbView &v, uint64_t r) {
+    Alignment a;
+    a.ref_id = v.ref_id[r]; a.pos = v.pos[r]; a.mate_ref_id = v.mate_ref_id[r]; a.mate_pos = v.mate_pos[r];
+    a.flag = v.flag[r]; a.mapq = v.mapq[r];
+    a.tag_xa = v.aux[r] & 1; a.tag_ih = v.aux[r] & 2; a.ih_value = v.ih[r];
+    a.cigar = v.cigar + v.cigar_off[r]; a.n_cigar = v.cigar_off[r + 1] - v.cigar_off[r];
+    if (v.seq_off[r] >= 0) {
+        const uint8_t *b = v.blob + v.seq_off[r];
+        uint32_t l;
+        memcpy(&l, b, 4);
+        a.l_seq = l; a.seq = (const char *)b + 4; a.qual = (const char *)b + 4 + l;
+    } else {
+        a.synth_lowrun = v.lowrun[r]; a.synth_polya = v.polya[r];
+    }
+    return a;
+}
+
+std::string name_at(const SqmbView &v, uint64_t r) {
+    std::string s = "q" + std::to_string(v.name_id[r]);
+    if (v.aux[r] & 4) s += (v.flag[r] & 0x80) ? "/2" : "/1";
+    return s;
+}
+
+// src/ReadRec.cpp:329-413
+void load_chimeric(const SqmbView &chim, HostConfig &cfg, std::vector<Read> &out) {
+    std::vector<Read> recs;
+    std::vector<int> sample;  // first five totals (ReadRec.cpp:336, 347-348)
+    Decoded d;
+    for (uint64_t r = 0; r < chim.n_rec; r++) {
+        Alignment a = alignment_at(chim, r);
+        if (!a.is_mapped() || a.is_dup()) continue;  // :344
+        decode_alignment(a, cfg, d);
+        Read rd;
+        rd.qname = name_at(chim, r);
+        if (rd.qname.size() >= 2) {  // :12-13
+            const std::string tail = rd.qname.substr(rd.qname.size() - 2);
+            if (tail == "/1" || tail == "/2") rd.qname.resize(rd.qname.size() - 2);
+        }
+        const bool low = d.lowphred_run > cfg.max_lowphred_len;
+        if (a.is_first()) { rd.first_total = d.total_len; rd.first_low = low; rd.first = d.blocks; }
+        else { rd.second_total = d.total_len; rd.second_low = low; rd.second = d.blocks; }
+        if (sample.size() < 5) sample.push_back(std::max(rd.first_total, rd.second_total));
+        recs.push_back(std::move(rd));
+    }
+    // group by Qname: same unstable std::sort on the same sequence with the same ordering as the
+    // reference (:354) so that equal-name records merge in the same order
+    std::sort(recs.begin(), recs.end(), [](const Read &x, const Read &y) { return x.qname < y.qname; });
+    std::vector<Read> merged;
+    merged.reserve(recs.size());
+    for (Read &r : recs) {
+        if (merged.empty() || r.qname != merged.back().qname) { merged.push_back(std::move(r)); continue; }
+        Read &m = merged.back();  // :359-372
+        if (m.first_total == 0 && r.first_total != 0) { m.first_total = r.first_total; m.first_low = r.first_low; }
+        if (m.second_total == 0 && r.second_total != 0) { m.second_total = r.second_total; m.second_low = r.second_low; }
+        m.first.insert(m.first.end(), r.first.begin(), r.first.end());
+        m.second.insert(m.second.end(), r.second.begin(), r.second.end());
+    }
+    for (Read &r : merged) r.sort_by_read_pos();
+    if (!sample.empty()) {  // :378-379
+        std::sort(sample.begin(), sample.end());
+        cfg.read_len = sample[sample.size() / 2];
+    }
+    std::sort(merged.begin(), merged.end(), Read::front_smaller);  // :382
+    // PCR duplicates: same first-mate front position and Equal() to an already kept read (:388-409)
+    out.clear();
+    for (Read &r : merged) {
+        bool dup = false;
+        if (!out.empty() && !r.first.empty() && !out.back().first.empty() &&
+            r.first.front().ref_id == out.back().first.front().ref_id && r.first.front().ref_pos == out.back().first.front().ref_pos) {
+            for (size_t k = out.size(); k-- > 0;) {
+                const Read &o = out[k];
+                if (o.first.empty() || o.first.front().ref_id != r.first.front().ref_id || o.first.front().ref_pos != r.first.front().ref_pos) break;
+                if (Read::equal(r, o)) { dup = true; break; }
+            }
+        }
+        if (!dup) out.push_back(std::move(r));
+    }
+}
+
+sqg_batch PackedBatch::view() const {
+    sqg_batch b;
+    b.n_rec = (int64_t)ref_id.size(); b.n_blk = (int64_t)blk_ref_pos.size();
+    b.ref_id = ref_id.data(); b.pos = pos.data(); b.mate_ref_id = mate_ref_id.data(); b.mate_pos = mate_pos.data(); b.end_pos = end_pos.data();
+    b.flag = flag.data(); b.total_len = total_len.data(); b.lowphred_run = lowphred_run.data();
+    b.mapq = mapq.data(); b.aux = aux.data(); b.blk_off = blk_off.data();
+    b.blk_ref_pos = blk_ref_pos.data(); b.blk_match_ref = blk_match_ref.data();
+    b.blk_read_pos = blk_read_pos.data(); b.blk_match_read = blk_match_read.data();
+    return b;
+}
+
+int pack_concordant(const SqmbView &conc, const HostConfig &cfg, const std::unordered_set<std::string> &chim_names, PackedBatch &out, std::string &err) {
+    const uint64_t n = conc.n_rec;
+    out.ref_id.assign(conc.ref_id, conc.ref_id + n); out.pos.assign(conc.pos, conc.pos + n);
+    out.mate_ref_id.assign(conc.mate_ref_id, conc.mate_ref_id + n); out.mate_pos.assign(conc.mate_pos, conc.mate_pos + n);
+    out.flag.assign(conc.flag, conc.flag + n); out.mapq.assign(conc.mapq, conc.mapq + n);
+    out.end_pos.resize(n); out.total_len.resize(n); out.lowphred_run.resize(n); out.aux.resize(n);
+    out.blk_off.assign(n + 1, 0);
+    // pass 1 (parallel over record ranges): per-record summaries and block counts
+    const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<std::vector<Block>> tblocks(nt);
+    std::vector<std::string> terr(nt);
+    auto work = [&](unsigned t) {
+        const uint64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        Decoded d;
+        std::vector<Block> &acc = tblocks[t];
+        for (uint64_t r = lo; r < hi; r++) {
+            Alignment a = alignment_at(conc, r);
+            decode_alignment(a, cfg, d);
+            if (d.blocks.size() > 16) { terr[t] = "record " + std::to_string(r) + " has more than 16 aligned blocks"; return; }
+            out.end_pos[r] = a.end_pos();
+            out.total_len[r] = (uint16_t)std::min(d.total_len, 65535);
+            out.lowphred_run[r] = (uint16_t)std::min(d.lowphred_run, 65535);
+            uint8_t aux = 0;
+            if (a.tag_xa) aux |= SQG_AUX_XA;
+            if (a.tag_ih && a.ih_value > 1) aux |= SQG_AUX_IH_GT1;
+            if (!chim_names.empty() && chim_names.count(name_at(conc, r))) aux |= SQG_AUX_CHIMNAME;
+            out.aux[r] = aux;
+            out.blk_off[r + 1] = (uint32_t)d.blocks.size();
+            acc.insert(acc.end(), d.blocks.begin(), d.blocks.end());
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+    for (unsigned t = 0; t < nt; t++) if (!terr[t].empty()) { err = terr[t]; return SQG_EUNSUPPORTED; }
+    for (uint64_t r = 0; r < n; r++) out.blk_off[r + 1] += out.blk_off[r];
+    const size_t nb = out.blk_off[n];
+    out.blk_ref_pos.resize(nb); out.blk_match_ref.resize(nb); out.blk_read_pos.resize(nb); out.blk_match_read.resize(nb);
+    size_t o = 0;
+    for (unsigned t = 0; t < nt; t++)
+        for (const Block &b : tblocks[t]) {
+            out.blk_ref_pos[o] = b.ref_pos; out.blk_match_ref[o] = b.match_ref;
+            out.blk_read_pos[o] = (uint16_t)b.read_pos; out.blk_match_read[o] = (uint16_t)b.match_read;
+            o++;
+        }
+    return SQG_OK;
+}
+
+sqg_chimeric PackedChimeric::view() {
+    sqg_chimeric c;
+    c.n_reads = (int64_t)n_first.size(); c.n_blk = (int64_t)blk_ref_id.size();
+    c.read_off = read_off.data(); c.n_first = n_first.data();
+    c.first_total_len = first_total.data(); c.second_total_len = second_total.data();
+    c.first_lowphred = first_low.data(); c.second_lowphred = second_low.data(); c.multi_filter = multi_filter.data();
+    c.blk_ref_id = blk_ref_id.data(); c.blk_ref_pos = blk_ref_pos.data(); c.blk_read_pos = blk_read_pos.data();
+    c.blk_match_ref = blk_match_ref.data(); c.blk_match_read = blk_match_read.data(); c.blk_is_reverse = blk_is_reverse.data();
+    return c;
+}
+
+void PackedChimeric::from_reads(const std::vector<Read> &reads) {
+    *this = PackedChimeric();
+    read_off.push_back(0);
+    for (const Read &r : reads) {
+        n_first.push_back((uint16_t)r.first.size());
+        first_total.push_back(r.first_total); second_total.push_back(r.second_total);
+        first_low.push_back(r.first_low); second_low.push_back(r.second_low); multi_filter.push_back(r.multi_filter);
+        for (int m = 0; m < 2; m++)
+            for (const Block &b : (m ? r.second : r.first)) {
+                blk_ref_id.push_back(b.ref_id); blk_ref_pos.push_back(b.ref_pos); blk_read_pos.push_back(b.read_pos);
+                blk_match_ref.push_back(b.match_ref); blk_match_read.push_back(b.match_read); blk_is_reverse.push_back(b.is_reverse);
+            }
+        read_off.push_back((uint32_t)blk_ref_id.size());
+    }
+}
+
+void PackedChimeric::to_reads(std::vector<Read> &reads) const {
+    for (size_t i = 0; i < reads.size(); i++) {
+        size_t o = read_off[i];
+        for (int m = 0; m < 2; m++)
+            for (Block &b : (m ? reads[i].second : reads[i].first)) {
+                b.ref_pos = blk_ref_pos[o]; b.read_pos = blk_read_pos[o]; b.match_ref = blk_match_ref[o]; b.match_read = blk_match_read[o];
+                o++;
+            }
+    }
+}
+
+}  // namespace sqh

@@ -1,0 +1,437 @@
+// Seed-segment state machine of BuildNode_STAR, restated event-driven.
+//
+// The reference (SegmentGraph.cpp:296-701) steps through every concordant alignment and keeps
+// per-record state.  All of that state is either (a) a pure function of the sorted discordant
+// blocks (the discordant groups and their right ends), (b) a prefix scan over the record stream
+// (otherrightmost, the duplicate filter), or (c) only observable when a discordant group is
+// processed.  So the stream itself is handled by data-parallel kernels (classify, scans,
+// compaction of the few "coverage gap" records) and this machine runs once per discordant GROUP:
+//   1. apply, lazily, what the records since the previous group did to the machine state
+//      (close a pending segment at the first 0-coverage record, clear or trim the cluster windows);
+//   2. run the per-group segmentation rules literally (SegmentGraph.cpp:353-612).
+// ConcordantCluster / PartialAlignCluster are not materialised: they are index windows over the
+// record stream (class bits CLS_CONC / CLS_PART); ConcordRest is a set, queried from a small
+// position-sorted table of candidate blocks.
+#ifndef SQ_SEED_CUH
+#define SQ_SEED_CUH
+#include "sq_common.cuh"
+
+namespace sq {
+
+struct DiscBlock {  // bamdiscordant element (+1 zeroed sentinel at the end)
+    int32_t chr, pos, len;
+    int32_t rev;
+};
+struct Group {      // discordant group [ds,de) with its chained right end (:341-348)
+    int32_t ds, de, chr, right;
+};
+struct SeedNode {
+    int32_t chr, pos, len;
+};
+struct RestBlock {  // ConcordRest candidate: non-first block of a concordant record, sorted by (chr,pos)
+    int32_t chr, pos, end, rec;
+};
+
+struct SeedInputs {
+    DevBatch b;
+    const uint8_t *cls;
+    const uint64_t *other_excl;     // per record: otherChr/otherrightmost before the record ((chr+1)<<32|pos)
+    const int32_t *gap_rec; int32_t n_gap;  // kept records preceded by a concordant-coverage gap, ascending
+    const int32_t *pc_rec; int32_t n_pc;    // records with CLS_PART, ascending
+    const DiscBlock *D; int32_t nD;
+    const Group *G; int32_t nG;
+    const int64_t *trigger;         // per group: first kept record past its right end, or n_rec
+    const int32_t *Pchr, *Ppos; int32_t nP;  // PartAlignPos sorted
+    const RestBlock *rest; int32_t n_rest;
+    int32_t read_len;
+};
+
+struct SeedState {
+    int64_t offCC;   // record-index cursor of the ConcordantCluster window
+    int32_t offPC;   // cursor into pc_rec
+    int32_t markedStart, markedChr;
+    bool have_back;  int32_t backChr, backEnd;
+    int32_t n_out;
+};
+
+struct SeedMachine {
+    SeedInputs in;
+    SeedState st;
+    SeedNode *out; int32_t out_cap;
+    int32_t *margin; int32_t margin_cap;
+    int32_t error;  // 1: margin overflow, 2: output overflow
+
+    SQ_HD bool isCC(int64_t r) const { return (in.cls[r] & (CLS_CONC | CLS_PART)) == CLS_CONC; }
+    SQ_HD int64_t nextCC(int64_t x, int64_t lim) const { while (x < lim && !isCC(x)) x++; return x < lim ? x : lim; }
+    SQ_HD int32_t e_chr(int64_t r) const { return in.b.ref_id[r]; }
+    SQ_HD int32_t e_pos(int64_t r) const { return in.b.blk_ref_pos[in.b.blk_off[r]]; }
+    SQ_HD int32_t e_len(int64_t r) const { return in.b.blk_match_ref[in.b.blk_off[r]]; }
+    SQ_HD int32_t e_readpos(int64_t r) const { return in.b.blk_read_pos[in.b.blk_off[r]]; }
+    SQ_HD bool e_rev(int64_t r) const { return flag_rev(in.b.flag[r]); }
+
+    SQ_HD void push_node(int32_t chr, int32_t pos, int32_t len) {
+        if (st.n_out >= out_cap) { error = 2; return; }
+        out[st.n_out].chr = chr; out[st.n_out].pos = pos; out[st.n_out].len = len;
+        st.n_out++;
+        st.have_back = true; st.backChr = chr; st.backEnd = pos + len;
+    }
+    SQ_HD void set_back_end(int32_t e) {  // vNodes.back().Length += e - Position - Length
+        out[st.n_out - 1].len += e - st.backEnd;
+        st.backEnd = e;
+    }
+    SQ_HD void push_margin(int32_t &n, int32_t v) {
+        if (n >= margin_cap) { error = 1; return; }
+        margin[n++] = v;
+    }
+    SQ_HD void sort_margins(int32_t n) {  // plain heapsort: values only, so any correct sort agrees with std::sort
+        int32_t *a = margin;
+        for (int32_t s = n / 2 - 1; s >= 0; s--) sift(a, s, n);
+        for (int32_t e = n - 1; e > 0; e--) { int32_t t = a[0]; a[0] = a[e]; a[e] = t; sift(a, 0, e); }
+    }
+    SQ_HD static void sift(int32_t *a, int32_t s, int32_t n) {
+        for (;;) {
+            int32_t c = 2 * s + 1;
+            if (c >= n) return;
+            if (c + 1 < n && a[c + 1] > a[c]) c++;
+            if (a[s] >= a[c]) return;
+            int32_t t = a[s]; a[s] = a[c]; a[c] = t; s = c;
+        }
+    }
+
+    SQ_HD void init() {
+        st.offCC = 0; st.offPC = 0; st.markedStart = -1; st.markedChr = -1;
+        st.have_back = false; st.backChr = -1; st.backEnd = 0; st.n_out = 0; error = 0;
+    }
+
+    // (curChr, currightmost) and the 0-coverage test of :616-620 for kept record r while group g is pending
+    SQ_HD bool is0(int64_t r, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, int32_t *curChr, int32_t *curRight) const {
+        const uint64_t ok = in.other_excl[r];
+        const int32_t oChr = (int32_t)(ok >> 32) - 1, oRight = (int32_t)(uint32_t)ok;
+        const int32_t cr = (dChr > oChr || (dChr == oChr && dRight > oRight)) ? dRight : oRight;
+        const int32_t cc = dChr > oChr ? dChr : oChr;
+        *curChr = cc; *curRight = cr;
+        const int32_t rl = in.read_len;
+        return (in.b.ref_id[r] != cc || in.b.pos[r] > cr + rl) && (cc < sChr || (cc == sChr && cr + rl < sPos));
+    }
+
+    // Lazy replay of steps :616-646 for the kept records in [r_lo, r_hi) while group g is pending.
+    // (sChr,sPos) = start of the pending group (or the zero sentinel once all groups are done).
+    SQ_HD void replay_between(int64_t r_lo, int64_t r_hi, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, bool do_trim) {
+        if (r_hi <= r_lo) return;
+        // gap records inside [r_lo, r_hi)
+        int32_t a = 0, bnd = in.n_gap;
+        { int32_t lo = 0, hi = in.n_gap; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.gap_rec[m] < r_lo) lo = m + 1; else hi = m; } a = lo; }
+        { int32_t lo = a, hi = in.n_gap; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.gap_rec[m] < r_hi) lo = m + 1; else hi = m; } bnd = lo; }
+        int32_t cc, cr;
+        int32_t f = -1, z = -1;
+        for (int32_t k = a; k < bnd; k++) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, &cc, &cr)) { f = k; break; }
+        if (f >= 0) {
+            if (st.markedStart != -1) {  // :621-630
+                if (cc == st.markedChr && cr > st.markedStart && cr - st.markedStart < kSeedThresh * 20 && st.have_back && st.markedStart == st.backEnd)
+                    set_back_end(st.backEnd + (cr - st.markedStart));
+                else if (cc == st.markedChr && cr > st.markedStart && cr - st.markedStart >= kSeedThresh * 20)
+                    push_node(st.markedChr, st.markedStart, cr - st.markedStart);
+                st.markedStart = -1; st.markedChr = -1;
+            }
+            if (!do_trim) return;
+            for (int32_t k = bnd - 1; k >= f; k--) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, &cc, &cr)) { z = k; break; }
+            const int64_t zr = in.gap_rec[z];
+            st.offCC = zr;  // :633-636 at record z: both windows emptied; z's own block is pushed afterwards
+            { int32_t lo = 0, hi = in.n_pc; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.pc_rec[m] < zr) lo = m + 1; else hi = m; } st.offPC = lo; }
+            r_lo = zr + 1;
+        }
+        if (!do_trim) return;
+        // :637-646 for the kept records in [r_lo, r_hi): a prefix skip whose predicate is that of the LAST kept record
+        int64_t last = r_hi - 1;
+        while (last >= r_lo && !(in.cls[last] & CLS_KEEP)) last--;
+        if (last < r_lo) return;
+        const int32_t lchr = in.b.ref_id[last];
+        // entries visible to that record are those pushed before it, i.e. from records < last
+        int64_t x = st.offCC;
+        for (;;) {
+            x = nextCC(x, last);
+            if (x >= last) { x = last; break; }
+            const int32_t c = e_chr(x);
+            if (c != lchr || c < sChr || (st.have_back && c == st.backChr && e_pos(x) < st.backEnd)) { x++; continue; }
+            break;
+        }
+        if (x > st.offCC) st.offCC = x;
+        int32_t szp;
+        { int32_t lo = 0, hi = in.n_pc; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.pc_rec[m] < last) lo = m + 1; else hi = m; } szp = lo; }
+        int32_t y = st.offPC;
+        while (y < szp) {
+            const int64_t r = in.pc_rec[y];
+            const int32_t c = e_chr(r);
+            if (c != lchr || c < sChr || (st.have_back && c == st.backChr && e_pos(r) < st.backEnd)) { y++; continue; }
+            break;
+        }
+        if (y > st.offPC) st.offPC = y;
+    }
+
+    // ConcordRest coverage at `brk` for group with start sPos on chromosome chrG, records before rg (:471-473)
+    SQ_HD int32_t rest_coverage(int32_t chrG, int32_t sPos, int32_t brk, int64_t rg) const {
+        const int32_t lo_pos = sPos - in.read_len;
+        int32_t lo = 0, hi = in.n_rest;
+        while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
+        int32_t cnt = 0;
+        for (int32_t k = lo; k < in.n_rest; k++) {
+            const RestBlock &e = in.rest[k];
+            if (e.chr != chrG || e.pos >= brk - kSeedThresh) break;
+            if (e.rec < rg && e.end >= brk + kSeedThresh) cnt++;
+        }
+        return cnt;
+    }
+
+    // Lines :353-612 for group g, reached at trigger record rg.
+    SQ_HD void process_group(int32_t g, int64_t rg) {
+        const int32_t thresh = kSeedThresh, RL = in.read_len;
+        const Group grp = in.G[g];
+        int32_t ds = grp.ds; const int32_t de = grp.de, chrG = grp.chr, nextright = grp.right;
+        const DiscBlock *D = in.D;
+        const int32_t recChr = in.b.ref_id[rg], recPos = in.b.pos[rg];
+        int32_t curEndPos = 0, curStartPos = 0, disStartPos = -1, disEndPos = -1, disCount = -1;
+        bool isClusternSplit = false;
+        if (st.markedStart != -1 && chrG != st.markedChr) { st.markedChr = -1; st.markedStart = -1; }
+        int32_t szPC;
+        { int32_t lo = 0, hi = in.n_pc; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.pc_rec[m] < rg) lo = m + 1; else hi = m; } szPC = lo; }
+        // :365-368 skip cluster entries of earlier chromosomes
+        {
+            int64_t lo = 0, hi = rg;
+            while (lo < hi) { int64_t m = (lo + hi) >> 1; if (in.b.ref_id[m] < chrG) lo = m + 1; else hi = m; }
+            // NB records with ref_id -1 are never cluster entries; the stream is sorted so this is a plain lower bound
+            if (lo > st.offCC) st.offCC = lo;
+            st.offCC = nextCC(st.offCC, rg);
+            while (st.offPC < szPC && e_chr(in.pc_rec[st.offPC]) < chrG) st.offPC++;
+        }
+        // :369-372 whole window stale?
+        if (st.offCC < rg) {
+            int64_t lb = rg - 1;
+            while (!isCC(lb)) lb--;
+            if (D[ds].pos > e_pos(lb) + e_len(lb) + RL) st.offCC = rg;
+        }
+        if (st.offPC < szPC) {
+            const int64_t lb = in.pc_rec[szPC - 1];
+            if (D[ds].pos > e_pos(lb) + e_len(lb) + RL) st.offPC = szPC;
+        }
+        // :375-385
+        curStartPos = D[ds].pos;
+        {
+            const bool hc = st.offCC < rg, hp = st.offPC < szPC;
+            int64_t t = -1;
+            if (hc && hp) {
+                const int64_t a = st.offCC, bq = in.pc_rec[st.offPC];
+                const bool a_lt = e_chr(a) != e_chr(bq) ? e_chr(a) < e_chr(bq) : e_pos(a) < e_pos(bq);
+                t = a_lt ? a : bq;
+            } else if (hc) t = st.offCC;
+            else if (hp) t = in.pc_rec[st.offPC];
+            if (t >= 0 && (e_chr(t) < chrG || (e_chr(t) == chrG && e_pos(t) < D[ds].pos))) curStartPos = e_pos(t);
+        }
+        if (st.markedStart > curStartPos) curStartPos = st.markedStart;
+        // :392-393 PartAlignPos window of this group
+        int32_t ps, pe;
+        {
+            const int32_t v = D[ds].pos - RL;
+            int32_t lo = 0, hi = in.nP;
+            while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.Pchr[m] < chrG || (in.Pchr[m] == chrG && in.Ppos[m] < v)) lo = m + 1; else hi = m; }
+            ps = lo;
+            for (pe = ps; pe < in.nP && in.Pchr[pe] == chrG && in.Ppos[pe] < nextright + RL; pe++) {}
+        }
+        while (ds != de) {
+            if (ds != 0 && D[ds].chr != D[ds - 1].chr && st.offCC >= rg && st.offPC >= szPC) curStartPos = D[ds].pos;
+            isClusternSplit = false;
+            int32_t nM = 0;
+            int32_t dc;
+            for (dc = ds; dc != de; dc++) {
+                push_margin(nM, D[dc].pos); push_margin(nM, D[dc].pos + D[dc].len);
+                if (D[dc].pos + D[dc].len > curEndPos) curEndPos = D[dc].pos + D[dc].len;
+                if (dc + 1 != de && D[dc + 1].pos > D[dc].pos + D[dc].len) break;
+            }
+            disStartPos = curStartPos > D[ds].pos ? curStartPos : D[ds].pos;
+            disEndPos = curEndPos;
+            disCount = dc - ds;
+            if (dc != de)
+                for (dc++; dc != de && D[dc].pos < curEndPos + thresh; dc++) { push_margin(nM, D[dc].pos); push_margin(nM, D[dc].pos + D[dc].len); }
+            for (int32_t pc = ps; pc != pe && in.Ppos[pc] < curEndPos + thresh; pc++) push_margin(nM, in.Ppos[pc]);
+            const int32_t m0 = D[ds].pos;  // MarginPositions.front() while still unsorted
+            for (int32_t i = st.offPC; i < szPC; i++) {  // :420-434
+                const int64_t r = in.pc_rec[i];
+                if (e_chr(r) != chrG) continue;
+                const int32_t p0 = e_pos(r), p1 = p0 + e_len(r);
+                const bool rv = e_rev(r);
+                if (e_readpos(r) > 15 && p0 > m0 - thresh && p0 < curEndPos + thresh) {
+                    if (rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
+                    else if (!rv) push_margin(nM, p0);
+                } else {
+                    if (rv && p0 > m0 - thresh && p0 < curEndPos + thresh) push_margin(nM, p0);
+                    else if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
+                }
+            }
+            if (error) return;
+            sort_margins(nM);
+            int32_t lastCurser = -1, lastSupport = 0;
+            for (int32_t ib = 0; ib < nM;) {
+                const int32_t brk = margin[ib];
+                if (st.have_back && st.backChr == chrG && brk - st.backEnd < thresh * 20) { ib++; continue; }
+                int32_t sr = 0, pl = 0, pr = 0;
+                for (int32_t k = 0; k < nM && margin[k] < brk + thresh; k++) {
+                    const int32_t d = brk - margin[k];
+                    if ((d < 0 ? -d : d) < thresh) sr++;
+                }
+                for (int32_t k = ds; k != de; k++) {
+                    const int32_t e1 = D[k].pos + D[k].len;
+                    if (e1 < brk && e1 > brk - RL && !D[k].rev) pl++;
+                    else if (D[k].pos > brk && D[k].pos < brk + RL && D[k].rev) pr++;
+                }
+                if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
+                    int32_t coverage = 0;
+                    for (int64_t r = st.offCC; r < rg; r++) {
+                        if (!isCC(r) || e_chr(r) != chrG) continue;
+                        const int32_t p0 = e_pos(r);
+                        if (p0 + e_len(r) >= brk + thresh && p0 < brk - thresh) coverage++;
+                    }
+                    for (int32_t k = ds; k != de; k++)
+                        if (D[k].chr == chrG && D[k].pos + D[k].len >= brk + thresh && D[k].pos < brk - thresh) coverage++;
+                    for (int32_t i = st.offPC; i < szPC; i++) {
+                        const int64_t r = in.pc_rec[i];
+                        if (e_chr(r) != chrG) continue;
+                        const int32_t p0 = e_pos(r);
+                        if (p0 + e_len(r) >= brk + thresh && p0 < brk - thresh) coverage++;
+                    }
+                    int32_t rest = coverage - sr; if (rest < 0) rest = 0;
+                    if (sr > rest + 2) {
+                        coverage += rest_coverage(chrG, in.D[grp.ds].pos, brk, rg);
+                        rest = coverage - sr; if (rest < 0) rest = 0;
+                    }
+                    if (sr > rest + 2) {
+                        const int32_t sup = sr + (pl > pr ? pl : pr);
+                        if (lastCurser == -1 && brk - curStartPos < thresh * 20) {
+                            st.markedStart = curStartPos; st.markedChr = chrG;
+                        } else if ((lastCurser == -1 || brk - lastCurser < thresh * 20) && sup > lastSupport) {
+                            lastCurser = brk; lastSupport = sup;
+                        } else if (brk - lastCurser >= thresh * 20) {
+                            isClusternSplit = true;
+                            if (D[ds].pos - curStartPos > thresh * 20 && lastCurser - D[ds].pos > thresh * 20) {
+                                push_node(chrG, curStartPos, D[ds].pos - curStartPos);
+                                curStartPos = D[ds].pos;
+                            }
+                            push_node(chrG, curStartPos, lastCurser - curStartPos);
+                            curStartPos = lastCurser; curEndPos = lastCurser;
+                            st.markedStart = lastCurser; st.markedChr = chrG;
+                            lastCurser = brk;
+                        }
+                    }
+                }
+                int32_t j = ib;
+                while (j < nM && margin[j] == brk) j++;
+                if (j < nM) ib = j; else break;
+            }
+            if (lastCurser != -1 && (!isClusternSplit || st.backEnd != lastCurser)) {  // :505-516
+                isClusternSplit = true;
+                if (D[ds].pos - curStartPos > thresh * 20 && lastCurser - D[ds].pos > thresh * 20) {
+                    push_node(chrG, curStartPos, D[ds].pos - curStartPos);
+                    curStartPos = D[ds].pos;
+                }
+                push_node(chrG, curStartPos, lastCurser - curStartPos);
+                curStartPos = lastCurser; curEndPos = lastCurser;
+                st.markedStart = lastCurser; st.markedChr = chrG;
+            }
+            // :518-527 dense discordant group without a clear break: the whole span is one segment
+            if (disStartPos != -1 && !isClusternSplit &&
+                (disCount > 5 || (int64_t)disCount * RL > 4 * (int64_t)(disEndPos - disStartPos))) {
+                const int32_t lastChr = D[de - 1].chr;
+                if (st.have_back && st.backChr == lastChr && disEndPos - st.backEnd < thresh * 20) set_back_end(disEndPos);
+                else push_node(lastChr, disStartPos, disEndPos - disStartPos);
+                curStartPos = disEndPos; curEndPos = disEndPos;
+                st.markedStart = disEndPos; st.markedChr = chrG;
+            }
+            // :529-532
+            while (st.offCC < rg && e_chr(st.offCC) < chrG) st.offCC = nextCC(st.offCC + 1, rg);
+            while (st.offPC < szPC && e_chr(in.pc_rec[st.offPC]) < chrG) st.offPC++;
+            for (dc = ds; dc != de && D[dc].pos + D[dc].len <= curEndPos; dc++) {}
+            // :536-567 walk the windows up to the end of the last inserted segment, tracking the 0-coverage position
+            int32_t concord0pos = curStartPos;
+            do {
+                bool f1 = false, f2 = false;
+                if (st.offCC < rg) {
+                    const int64_t r = st.offCC;
+                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
+                    f1 = true;
+                    if (c > chrG) f1 = false;
+                    if (dc != in.nD && c == D[dc].chr && p1 + RL >= D[dc].pos) f1 = false;
+                    if (st.have_back && (c > st.backChr || (c == st.backChr && p0 >= st.backEnd))) f1 = false;
+                    if (f1) { if (p1 > concord0pos) concord0pos = p1; st.offCC = nextCC(r + 1, rg); }
+                }
+                if (st.offPC < szPC) {
+                    const int64_t r = in.pc_rec[st.offPC];
+                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
+                    f2 = true;
+                    if (c > chrG) f2 = false;
+                    if (dc != in.nD && c == D[dc].chr && p1 + RL >= D[dc].pos) f2 = false;
+                    if (st.have_back && (c > st.backChr || (c == st.backChr && p0 >= st.backEnd))) f2 = false;
+                    if (f2) { if (p1 > concord0pos) concord0pos = p1; st.offPC++; }
+                }
+                if (!f1 && !f2) break;
+            } while (st.offCC < rg || st.offPC < szPC);
+            // :570-601 extend the last segment to the next 0-coverage position if the stream already shows one
+            do {
+                const bool ccEmpty = !(st.offCC < rg), pcEmpty = !(st.offPC < szPC);
+                if (st.markedStart != -1 && (recChr > st.markedChr || recPos > concord0pos + RL) &&
+                    (ccEmpty || e_chr(st.offCC) != st.markedChr || e_pos(st.offCC) > concord0pos + RL) &&
+                    (pcEmpty || e_chr(in.pc_rec[st.offPC]) != st.markedChr || e_pos(in.pc_rec[st.offPC]) > concord0pos)) {
+                    if (concord0pos > st.markedStart && concord0pos < st.markedStart + thresh * 20 && st.have_back && st.backChr == st.markedChr)
+                        set_back_end(concord0pos);
+                    else if (concord0pos > st.markedStart)
+                        push_node(st.markedChr, st.markedStart, concord0pos - st.markedStart);
+                    curStartPos = concord0pos;
+                    st.markedChr = -1; st.markedStart = -1;
+                    break;
+                }
+                bool f1 = false, f2 = false;
+                if (!ccEmpty) {
+                    const int64_t r = st.offCC;
+                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
+                    if (dc == in.nD || c < D[dc].chr || (c == D[dc].chr && p1 + RL < D[dc].pos)) f1 = true;
+                    if (f1) { if (p1 > concord0pos) concord0pos = p1; st.offCC = nextCC(r + 1, rg); }
+                }
+                if (!pcEmpty) {
+                    const int64_t r = in.pc_rec[st.offPC];
+                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
+                    if (dc == in.nD || c < D[dc].chr || (c == D[dc].chr && p1 + RL < D[dc].pos)) f2 = true;
+                    if (f2) { if (p1 > concord0pos) concord0pos = p1; st.offPC++; }
+                }
+                if (!f1 && !f2) break;
+            } while (st.offCC < rg || st.offPC < szPC);
+            ds = dc;
+            if (error) return;
+        }
+    }
+
+    // Whole stream, one island: every group in order.  Returns the index of the first group that was
+    // never reached by the stream (== nG when all were processed).
+    SQ_HD int32_t run_all(int64_t first_kept, int64_t n_rec) {
+        init();
+        int32_t dChr = 0, dRight = 0;
+        int64_t r_prev = first_kept;
+        int32_t g = 0;
+        for (; g < in.nG; g++) {
+            const int64_t rg = in.trigger[g];
+            const Group grp = in.G[g];
+            if (rg >= n_rec) break;
+            replay_between(r_prev, rg, dChr, dRight, grp.chr, in.D[grp.ds].pos, true);
+            process_group(g, rg);
+            if (error) return g;
+            dChr = grp.chr; dRight = grp.right;
+            r_prev = rg;
+        }
+        if (g < in.nG) {  // the stream ended before group g: only the pending-segment close-out can still fire
+            const Group grp = in.G[g];
+            replay_between(r_prev, n_rec, dChr, dRight, grp.chr, in.D[grp.ds].pos, false);
+        }
+        // after the last group the reference compares against the element one past the end of
+        // bamdiscordant (zero sentinel): the 0-coverage test can never hold there, nothing to do.
+        return g;
+    }
+};
+
+}  // namespace sq
+#endif

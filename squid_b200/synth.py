@@ -114,7 +114,7 @@ def _table(ref_len, ref_id, pos, mate_ref_id, mate_pos, flag, name_id, cigar_off
     return t
 
 
-def _pairs_from_transcripts(rng, tx: Transcriptome, gene: np.ndarray, name_base: int, clip_frac: float):
+def _pairs_from_transcripts(rng, tx: Transcriptome, gene: np.ndarray, name_base: int, clip_frac: float, min_block: int = 4):
     """FR proper pairs sampled from transcripts: two records per pair (left = forward, right = reverse)."""
     n = gene.shape[0]
     ins = np.minimum(rng.integers(150, 401, size=n), tx.g_tlen[gene])
@@ -141,6 +141,14 @@ def _pairs_from_transcripts(rng, tx: Transcriptome, gene: np.ndarray, name_base:
     roff, rcig = _cigars_from_blocks(rn, rgs, rgl, rcl, rcr)
     left = _table(tx.ref_len, chr_, lpos, chr_, rpos, lflag, names, loff, lcig)
     right = _table(tx.ref_len, chr_, rpos, chr_, lpos, rflag, names, roff, rcig)
+    if min_block > 1:
+        # Pairs with an aligned block shorter than `min_block` are dropped.  Blocks of <= 3 bp make the
+        # reference's per-segment Support depend on the tie order of an unstable std::sort
+        # (SegmentGraph.cpp:781; DESIGN.md "known divergence"), so the default parity workload avoids them.
+        big = np.int64(1 << 40)
+        ok = (np.where(lgl > 0, lgl, big).min(axis=1) >= min_block) & (np.where(rgl > 0, rgl, big).min(axis=1) >= min_block)
+        keep = np.flatnonzero(ok)
+        left, right = left.take(keep), right.take(keep)
     return left, right
 
 
@@ -153,7 +161,7 @@ def _simple_cigar(n, lclip, m, rclip):
 
 
 def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.005, n_genes: int | None = None,
-              fusion_support: float = 20.0, clip_frac: float = 0.02, adversarial: bool = True):
+              fusion_support: float = 20.0, clip_frac: float = 0.02, adversarial: bool = True, min_block: int = 4):
     """Returns (concordant AlnTable sorted by coordinate, chimeric AlnTable, info dict)."""
     ref_len = np.asarray(GRCH38_LEN if ref_len is None else ref_len, dtype=np.int64)
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -162,8 +170,8 @@ def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.0
     tx = Transcriptome(rng, ref_len, n_genes)
     p = tx.g_expr / tx.g_expr.sum()
     gene = rng.choice(n_genes, size=n_pairs, p=p)
-    left, right = _pairs_from_transcripts(rng, tx, gene, 0, clip_frac)
-    n = n_pairs
+    left, right = _pairs_from_transcripts(rng, tx, gene, 0, clip_frac, min_block)
+    n = left.n
     parts = []
     if adversarial and n >= 50:
         # per-record decorations exercising the gate / low-phred / poly-A / duplicate rules
@@ -197,7 +205,8 @@ def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.0
         # long same-chromosome fragments (> -dp) and cross-chromosome pairs living in the concordant file
         m = max(4, n // 1000)
         g2 = rng.choice(n_genes, size=m, p=p)
-        l2, r2 = _pairs_from_transcripts(rng, tx, g2, 600_000_000, 0.0)
+        l2, r2 = _pairs_from_transcripts(rng, tx, g2, 600_000_000, 0.0, min_block)
+        m = l2.n
         far = rng.integers(60_000, 900_000, size=m)
         newpos = np.minimum(l2.pos.astype(np.int64) + far, ref_len[l2.ref_id] - 200)
         off, cig = _simple_cigar(m, np.zeros(m), np.full(m, READ_LEN), np.zeros(m))
@@ -294,12 +303,12 @@ def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.0
     if adversarial and n_chim:
         m = max(2, n_chim // 20)
         g3 = rng.choice(n_genes, size=m, p=p)
-        l3, r3 = _pairs_from_transcripts(rng, tx, g3, name_ctr, 1.0)  # every pair has one clipped mate
+        l3, r3 = _pairs_from_transcripts(rng, tx, g3, name_ctr, 1.0, 1)  # every pair has one clipped mate
         name_ctr += m
         chim_tabs += [l3, r3]
         m = max(2, n_chim // 40)
         g4 = rng.choice(n_genes, size=m, p=p)
-        l4, r4 = _pairs_from_transcripts(rng, tx, g4, name_ctr, 0.0)
+        l4, r4 = _pairs_from_transcripts(rng, tx, g4, name_ctr, 0.0, 1)
         name_ctr += m
         # move the right mate > 750 kb away on the same chromosome, keep FR orientation
         np4 = np.minimum(r4.pos.astype(np.int64) + 800_000, ref_len[r4.ref_id] - 2000)
@@ -322,7 +331,8 @@ def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.0
         if pick.size:
             m = pick.size
             g5 = rng.choice(n_genes, size=m, p=p)
-            l5, r5 = _pairs_from_transcripts(rng, tx, g5, 0, 0.0)
+            l5, r5 = _pairs_from_transcripts(rng, tx, g5, 0, 0.0, min_block)
+            pick = pick[: l5.n]; m = l5.n
             l5.name_id = pick.copy(); r5.name_id = pick.copy()
             sfx = rng.random(m) < 0.5
             l5.aux[sfx] |= sqmb.AUX_NAME_SUFFIX; r5.aux[sfx] |= sqmb.AUX_NAME_SUFFIX
