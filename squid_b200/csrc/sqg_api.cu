@@ -1,0 +1,961 @@
+// squid_b200 C ABI implementation: kernels for sm_100a + orchestration.  See include/squid_b200.h.
+//
+// Phase structure:
+//   load      : batch -> HBM once, stays resident for the three phases
+//   classify  : gate + duplicate filter + concordance class + otherrightmost scan  (phase-1 stream pass)
+//   seed      : discordant-group state machine over the compacted gap/partial lists -> seed segments
+//   tile      : normalise + tile the genome -> segment table
+//   depth_edges: per-segment depth + read-to-segment assignment + raw edges        (phase-2 stream pass)
+//   edge_sort : radix sort by packed key + run-length reduce
+//   coverage  : breakpoint coverage with the reference's indBP lag                 (phase-3 stream pass)
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "sq_classify.cuh"
+#include "sq_depth_cover.cuh"
+#include "sq_locate.cuh"
+#include "sq_seed.cuh"
+#include "sqg_ctx.cuh"
+
+using namespace sq;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return SQG_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+#define LAUNCH(kernel, grid, block, ...)                                                           \
+    do {                                                                                           \
+        kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                                  \
+        ctx->launches++;                                                                           \
+        CK(cudaGetLastError());                                                                    \
+    } while (0)
+
+static constexpr int kThreads = 256;
+static inline unsigned blocks_for(int64_t n, int threads = kThreads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+static int phase_begin(sqg_ctx *ctx, const char *name) {
+    PhaseTimer &t = ctx->timers[name];
+    if (!t.a) { CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); }
+    t.done = false;
+    CK(cudaEventRecord(t.a, ctx->stream));
+    return SQG_OK;
+}
+static int phase_end(sqg_ctx *ctx, const char *name) {
+    PhaseTimer &t = ctx->timers[name];
+    CK(cudaEventRecord(t.b, ctx->stream));
+    t.done = true;
+    return SQG_OK;
+}
+#define PHASE_BEGIN(name) do { int rc_ = phase_begin(ctx, name); if (rc_) return rc_; } while (0)
+#define PHASE_END(name) do { int rc_ = phase_end(ctx, name); if (rc_) return rc_; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// functors / kernels: classify
+// ------------------------------------------------------------------------------------------------
+struct GateIdxOp {
+    DevBatch b; int32_t min_mapq;
+    __device__ int32_t operator()(int32_t r) const {
+        return record_gate(b.flag[r], b.mapq[r], b.aux[r], b.ref_id[r], min_mapq) ? r : -1;
+    }
+};
+struct MaxI32 { __device__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; } };
+struct MaxU64 { __device__ uint64_t operator()(uint64_t a, uint64_t b) const { return a > b ? a : b; } };
+struct MinI64 { __device__ int64_t operator()(int64_t a, int64_t b) const { return a < b ? a : b; } };
+
+__global__ void k_validate(DevBatch b, int32_t n_ref, int32_t *flags) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec) return;
+    int bad = 0;
+    const int32_t rid = b.ref_id[r];
+    if (rid >= n_ref || rid < -1) bad |= 1;
+    if (rid < 0 && flag_mapped(b.flag[r])) bad |= 2;
+    if (b.blk_off[r + 1] < b.blk_off[r] || b.blk_off[r + 1] - b.blk_off[r] > (uint32_t)kMaxBlocks) bad |= 4;
+    if (r + 1 < b.n_rec) {
+        const int32_t rid2 = b.ref_id[r + 1];
+        const uint64_t k1 = rid < 0 ? ~0ull : (((uint64_t)(uint32_t)rid << 32) | (uint32_t)b.pos[r]);
+        const uint64_t k2 = rid2 < 0 ? ~0ull : (((uint64_t)(uint32_t)rid2 << 32) | (uint32_t)b.pos[r + 1]);
+        if (k2 < k1) bad |= 8;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+__global__ void k_classify(DevBatch b, Params p, const int32_t *lastpass, uint8_t *cls, uint64_t *other_key) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec) return;
+    const int64_t prev = r > 0 ? lastpass[r - 1] : -1;
+    const ClassifyOut o = classify_record(b, p, r, prev);
+    cls[r] = o.cls;
+    other_key[r] = o.other_key;
+}
+
+struct IsGapOp {
+    DevBatch b; const uint8_t *cls; const uint64_t *other; int32_t read_len;
+    __device__ bool operator()(int32_t r) const {
+        if (!(cls[r] & CLS_KEEP)) return false;
+        const uint64_t k = other[r];
+        const int32_t oc = (int32_t)(k >> 32) - 1, orr = (int32_t)(uint32_t)k;
+        return b.ref_id[r] != oc || b.pos[r] > orr + read_len;
+    }
+};
+struct IsPartOp {
+    const uint8_t *cls;
+    __device__ bool operator()(int32_t r) const { return cls[r] & CLS_PART; }
+};
+struct FirstKeptOp {
+    const uint8_t *cls; int64_t n;
+    __device__ int64_t operator()(int32_t r) const { return (cls[r] & CLS_KEEP) ? (int64_t)r : n; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels: node building
+// ------------------------------------------------------------------------------------------------
+__global__ void k_triggers(DevBatch b, const uint8_t *cls, const Group *G, int32_t nG, int64_t *trig) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nG) return;
+    const Group grp = G[g];
+    int64_t lo = 0, hi = b.n_rec;
+    while (lo < hi) {  // first record past (chr, right) of the group (:353)
+        const int64_t m = (lo + hi) >> 1;
+        const int32_t rid = b.ref_id[m];
+        const bool past = rid < 0 || grp.chr < rid || (grp.chr == rid && grp.right < b.pos[m]);
+        if (!past) lo = m + 1; else hi = m;
+    }
+    while (lo < b.n_rec && !(cls[lo] & CLS_KEEP)) lo++;
+    trig[g] = lo;
+}
+
+// ConcordRest candidates: non-first blocks of concordant records that start inside
+// [group start - ReadLen, group right + ReadLen) of some discordant group (:690-699, :387, :471-473)
+__global__ void k_rest_collect(DevBatch b, const uint8_t *cls, const Group *G, const DiscBlock *D, int32_t nG, int32_t read_len,
+                               RestBlock *out, uint64_t *out_key, int64_t cap, int64_t *counter) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec) return;
+    if (!(cls[r] & CLS_CONC) || !(b.flag[r] & 0xC0)) return;
+    const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
+    if (e - o < 2) return;
+    const int32_t c = b.ref_id[r];
+    for (uint32_t k = o + 1; k < e; k++) {
+        const int32_t q = b.blk_ref_pos[k];
+        int32_t lo = 0, hi = nG;  // last group with (chr, start - RL) <= (c, q)
+        while (lo < hi) {
+            const int32_t m = (lo + hi) >> 1;
+            const Group g = G[m];
+            const int32_t s = D[g.ds].pos - read_len;
+            if (g.chr < c || (g.chr == c && s <= q)) lo = m + 1; else hi = m;
+        }
+        const int32_t gi = lo - 1;
+        if (gi < 0) continue;
+        const Group g = G[gi];
+        if (g.chr != c || q >= g.right + read_len) continue;
+        const int64_t slot = (int64_t)atomicAdd((unsigned long long *)counter, 1ull);
+        if (slot < cap) {
+            out[slot] = RestBlock{c, q, q + b.blk_match_ref[k], (int32_t)r};
+            out_key[slot] = ((uint64_t)(uint32_t)c << 32) | (uint32_t)q;
+        }
+    }
+}
+
+__global__ void k_seed_single(SeedInputs in, SeedNode *out, int32_t out_cap, int32_t *margin, int32_t margin_cap,
+                              int64_t first_kept, int64_t n_rec, SeedState *st_out, int32_t *g_done, int32_t *err) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    SeedMachine sm;
+    sm.in = in; sm.out = out; sm.out_cap = out_cap; sm.margin = margin; sm.margin_cap = margin_cap;
+    const int32_t g = sm.run_all(first_kept, n_rec);
+    *st_out = sm.st;
+    *g_done = g;
+    *err = sm.error;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: depth
+// ------------------------------------------------------------------------------------------------
+__global__ void k_depth_disc(NodeTable nt, const DiscBlock *D, int32_t nD, int32_t *cnt, int32_t *sum) {
+    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nD) return;
+    const DiscBlock d = D[k];
+    if (d.chr < 0 || d.chr >= nt.n_ref) return;
+    const int32_t c0 = nt.chr_first[d.chr], c1 = nt.chr_first[d.chr + 1];
+    const int32_t j = upper_bound_i32(nt.pos, c0, c1, d.pos) - 1;  // segment whose turn consumes this block (:774)
+    if (j >= c0 && d.pos >= nt.pos[j] && d.pos + d.len <= nt.end[j]) { atomicAdd(&cnt[j], 1); atomicAdd(&sum[j], d.len); }
+}
+
+// ReadsMain targets (to be max-scanned) + ReadsOther counted directly (no sort needed: DESIGN.md)
+__global__ void k_depth_targets(DevBatch b, const uint8_t *cls, NodeTable nt, int64_t r_break, int32_t *target,
+                                int32_t *cnt_other, int32_t *sum_other, int32_t *other_nonempty) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec) return;
+    int32_t m = -1;
+    if (r < r_break && (cls[r] & CLS_HASBLK)) {
+        const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
+        const int32_t c = b.ref_id[r];
+        m = depth_target(nt, c, b.blk_ref_pos[o], b.blk_match_ref[o]);
+        if (e - o > 1) *other_nonempty = 1;
+        for (uint32_t k = o + 1; k < e; k++) {
+            const int32_t s = b.blk_ref_pos[k], l = b.blk_match_ref[k];
+            const int32_t m2 = depth_target(nt, c, s, l);
+            if (m2 != kNoNode && depth_contained(nt, m2, c, s, l)) { atomicAdd(&cnt_other[m2], 1); atomicAdd(&sum_other[m2], l); }
+        }
+    }
+    target[r] = m;
+}
+__global__ void k_depth_main_count(DevBatch b, const uint8_t *cls, NodeTable nt, int64_t r_break, const int32_t *cursor,
+                                   int32_t *cnt_main, int32_t *sum_main) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec || r >= r_break || !(cls[r] & CLS_HASBLK)) return;
+    const int32_t c = cursor[r];
+    if (c == kNoNode || c < 0 || c >= nt.n) return;
+    const uint32_t o = b.blk_off[r];
+    const int32_t s = b.blk_ref_pos[o], l = b.blk_match_ref[o];
+    if (depth_contained(nt, c, b.ref_id[r], s, l)) { atomicAdd(&cnt_main[c], 1); atomicAdd(&sum_main[c], l); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: assignment + raw edges
+// ------------------------------------------------------------------------------------------------
+struct EdgeSink {
+    uint64_t *keys; int64_t cap; unsigned long long *counter;
+    __device__ void operator()(uint64_t k) {
+        const unsigned long long slot = atomicAdd(counter, 1ull);
+        if ((int64_t)slot < cap) keys[slot] = k;
+    }
+};
+struct EdgeSinkSerial {  // single-thread fix-up kernels
+    uint64_t *keys; int64_t cap; unsigned long long *counter;
+    __device__ void operator()(uint64_t k) {
+        const unsigned long long slot = (*counter)++;
+        if ((int64_t)slot < cap) keys[slot] = k;
+    }
+};
+
+// res0 codes: >= 0 segment of the read's first block; -1 located nowhere; -2 read does not touch the hint; -3 hint-sensitive
+__device__ __forceinline__ bool conc_builds_edges(const DevBatch &b, const Params &p, int64_t r) {  // whetherbuildedge (:1601-1605)
+    const uint32_t o = b.blk_off[r], nb = b.blk_off[r + 1] - o;
+    if (nb == 0 || !has_mate_block(b.flag[r], b.mate_ref_id[r])) return true;
+    int32_t front_rp = 0x7fffffff;
+    for (uint32_t k = 0; k < nb; k++) { const int32_t rp = b.blk_read_pos[o + k]; if (rp < front_rp) front_rp = rp; }
+    return front_rp <= 15 || (int32_t)b.lowphred_run[r] > p.max_lowphred_len;
+}
+__device__ __forceinline__ void conc_load_read(const DevBatch &b, int64_t r, ReadView &rv, bool &is_first) {
+    is_first = flag_first(b.flag[r]);
+    Blk *own = is_first ? rv.F : rv.S;
+    Blk *oth = is_first ? rv.S : rv.F;
+    const int no = load_sorted_blocks(b, r, own);
+    int nm = 0;
+    if (has_mate_block(b.flag[r], b.mate_ref_id[r])) {
+        Blk x;
+        x.ref_id = b.mate_ref_id[r]; x.ref_pos = b.mate_pos[r]; x.read_pos = 0; x.match_ref = kMateBlockLen; x.match_read = kMateBlockLen;
+        x.rev = flag_mate_rev(b.flag[r]);
+        oth[nm++] = x;
+    }
+    if (is_first) { rv.nF = no; rv.nS = nm; rv.first_total = b.total_len[r]; rv.second_total = 0; }
+    else { rv.nS = no; rv.nF = nm; rv.second_total = b.total_len[r]; rv.first_total = 0; }
+}
+
+__global__ void k_conc_edges(DevBatch b, const uint8_t *cls, Params p, NodeTable nt, int32_t *res0, EdgeSink sink) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec) return;
+    int32_t out = -2;
+    if ((cls[r] & CLS_KEEP) && conc_builds_edges(b, p, r)) {
+        Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+        int32_t node[2 * kMaxBlocks + 2];
+        ReadView rv; rv.F = F; rv.S = S;
+        bool is_first;
+        conc_load_read(b, r, rv, is_first);
+        if (rv.nF + rv.nS > 0) {
+            if (read_edges(nt, p, rv, MODE_OTHER, is_first, false, 0, node, sink)) out = node[0];
+            else out = -3;
+        }
+    }
+    res0[r] = out;
+}
+__global__ void k_conc_fixup(DevBatch b, Params p, NodeTable nt, int32_t *res0, const int32_t *sens, int32_t n_sens, EdgeSinkSerial sink) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int32_t i = 0; i < n_sens; i++) {
+        const int64_t r = sens[i];
+        int32_t hint = 0;  // firstfrontindex starts at 0 (:1568)
+        for (int64_t q = r - 1; q >= 0; q--) if (res0[q] >= 0) { hint = res0[q]; break; }
+        Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+        int32_t node[2 * kMaxBlocks + 2];
+        ReadView rv; rv.F = F; rv.S = S;
+        bool is_first;
+        conc_load_read(b, r, rv, is_first);
+        read_edges(nt, p, rv, MODE_OTHER, is_first, true, hint, node, sink);
+        res0[r] = node[0];
+    }
+}
+
+struct ChimDev {
+    int64_t n_reads;
+    const uint32_t *read_off; const uint16_t *n_first;
+    const int32_t *first_total, *second_total;
+    int32_t *ref_id, *ref_pos, *read_pos, *match_ref, *match_read;
+    const uint8_t *rev;
+};
+__device__ __forceinline__ void chim_load_read(const ChimDev &c, int64_t i, ReadView &rv) {
+    const uint32_t o = c.read_off[i], e = c.read_off[i + 1], nf = c.n_first[i];
+    rv.nF = 0; rv.nS = 0;
+    for (uint32_t k = o; k < e; k++) {
+        Blk x;
+        x.ref_id = c.ref_id[k]; x.ref_pos = c.ref_pos[k]; x.match_ref = c.match_ref[k]; x.read_pos = c.read_pos[k]; x.match_read = c.match_read[k]; x.rev = c.rev[k];
+        if (k - o < nf) { if (rv.nF < kMaxBlocks) rv.F[rv.nF++] = x; } else { if (rv.nS < kMaxBlocks) rv.S[rv.nS++] = x; }
+    }
+    rv.first_total = c.first_total[i]; rv.second_total = c.second_total[i];
+}
+__device__ __forceinline__ void chim_store_read(const ChimDev &c, int64_t i, const ReadView &rv) {
+    uint32_t k = c.read_off[i];
+    for (int m = 0; m < 2; m++)
+        for (int q = 0; q < (m ? rv.nS : rv.nF); q++, k++) {
+            const Blk &x = m ? rv.S[q] : rv.F[q];
+            c.ref_pos[k] = x.ref_pos; c.match_ref[k] = x.match_ref; c.read_pos[k] = x.read_pos; c.match_read[k] = x.match_read;
+        }
+}
+__global__ void k_chim_edges(ChimDev c, Params p, NodeTable nt, int32_t *res0, EdgeSink sink) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= c.n_reads) return;
+    Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+    int32_t node[2 * kMaxBlocks + 2];
+    ReadView rv; rv.F = F; rv.S = S;
+    chim_load_read(c, i, rv);
+    int32_t out = -2;
+    if (rv.nF + rv.nS > 0) {
+        if (read_edges(nt, p, rv, MODE_CHIM, true, false, 0, node, sink)) { out = node[0]; chim_store_read(c, i, rv); }
+        else out = -3;
+    }
+    res0[i] = out;
+}
+__global__ void k_chim_fixup(ChimDev c, Params p, NodeTable nt, int32_t *res0, EdgeSinkSerial sink) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int32_t hint = 0;
+    for (int64_t i = 0; i < c.n_reads; i++) {
+        if (res0[i] == -3) {
+            Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+            int32_t node[2 * kMaxBlocks + 2];
+            ReadView rv; rv.F = F; rv.S = S;
+            chim_load_read(c, i, rv);
+            read_edges(nt, p, rv, MODE_CHIM, true, true, hint, node, sink);
+            chim_store_read(c, i, rv);
+            res0[i] = node[0];
+        }
+        if (res0[i] >= 0) hint = res0[i];
+    }
+}
+struct IsSensOp {
+    const int32_t *res0;
+    __device__ bool operator()(int32_t r) const { return res0[r] == -3; }
+};
+__global__ void k_unpack_edges(const uint64_t *keys, const int32_t *counts, int64_t n, int32_t *ind1, int32_t *ind2, uint8_t *heads, int32_t *w) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t a, c; bool h1, h2;
+    edge_unpack(keys[i], a, h1, c, h2);
+    ind1[i] = a; ind2[i] = c; heads[i] = (uint8_t)((h1 ? 1 : 0) | (h2 ? 2 : 0)); w[i] = counts[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: breakpoint coverage
+// ------------------------------------------------------------------------------------------------
+struct CoverKeyOp {
+    DevBatch b; const uint8_t *cls;
+    __device__ uint64_t operator()(int32_t r) const {
+        const uint16_t f = b.flag[r];
+        const int32_t rid = b.ref_id[r], pos = b.pos[r], mrid = b.mate_ref_id[r], mpos = b.mate_pos[r];
+        if (!cover_qualifies(cls[r], f, rid, pos, mrid, mpos)) return 0;
+        return chrpos_key(rid, cover_start(f, rid, pos, mrid, mpos));
+    }
+};
+__global__ void k_cov_r0(const uint64_t *M, int64_t n, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, uint64_t *bpkey, int64_t *r0) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    bpkey[k] = chrpos_key(bp_chr[k], bp_pos[k]);
+    const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
+    r0[k] = upper_bound_u64(M, 0, n, T);  // first record whose running-max key exceeds T
+}
+// the reference advances indBP by at most one per qualifying record (:3157-3158): t[k] = record at which indBP leaves k
+__global__ void k_cov_chain(DevBatch b, const uint8_t *cls, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist,
+                            const int64_t *r0, int64_t *t) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    CoverKeyOp key{b, cls};
+    int64_t tp = -1;
+    const int64_t n = b.n_rec;
+    for (int64_t k = 0; k < K; k++) {
+        int64_t c;
+        if (r0[k] > tp) c = r0[k];
+        else {
+            const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
+            c = tp + 1;
+            while (c < n && !(key((int32_t)c) > T)) c++;
+        }
+        t[k] = c;
+        tp = c < n ? c : n;
+    }
+}
+__global__ void k_cov_count(DevBatch b, const uint8_t *cls, const uint64_t *bpkey, const int64_t *t, int64_t K, int32_t *cov) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec) return;
+    CoverKeyOp key{b, cls};
+    const uint64_t ks = key((int32_t)r);
+    if (!ks) return;
+    const uint64_t ke = chrpos_key(b.ref_id[r], b.end_pos[r]);
+    for (int64_t k = lower_bound_u64(bpkey, 0, K, ks); k < K && bpkey[k] < ke; k++)
+        if (r < t[k]) atomicAdd(&cov[k], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// API
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int32_t n_ref, int32_t device) {
+    if (!out || !cfg || !ref_len || n_ref <= 0) return SQG_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SQG_ENODEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return SQG_ENODEVICE;
+    sqg_ctx *ctx = new (std::nothrow) sqg_ctx();
+    if (!ctx) return SQG_ENOMEM;
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
+    ctx->params.min_mapq = cfg->min_mapq; ctx->params.max_lowphred_len = cfg->max_lowphred_len;
+    ctx->params.concord_dist_pos = cfg->concord_dist_pos; ctx->params.concord_dist_idx = cfg->concord_dist_idx;
+    ctx->params.read_len = cfg->read_len; ctx->params.n_ref = n_ref;
+    ctx->ref_len.assign(ref_len, ref_len + n_ref);
+    *out = ctx;
+    if (!cfg->using_star) { ctx->err = "BWA mode (BuildNode_BWA / RawEdges) is not implemented"; return SQG_EUNSUPPORTED; }
+    if (cfg->read_len <= 0) { ctx->err = "read_len must be > 0"; return SQG_EINVAL; }
+    return SQG_OK;
+}
+
+void sqg_destroy(sqg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    // DBuf/HBuf members are plain pointers: release explicitly
+    ctx->o_ref_id.release(); ctx->o_pos.release(); ctx->o_mate_ref_id.release(); ctx->o_mate_pos.release(); ctx->o_end_pos.release();
+    ctx->o_blk_ref_pos.release(); ctx->o_blk_match_ref.release(); ctx->o_flag.release(); ctx->o_total_len.release(); ctx->o_lowphred_run.release();
+    ctx->o_blk_read_pos.release(); ctx->o_blk_match_read.release(); ctx->o_mapq.release(); ctx->o_aux.release(); ctx->o_blk_off.release();
+    ctx->d_cls.release(); ctx->d_other.release(); ctx->d_scratch32.release(); ctx->d_gap.release(); ctx->d_pc.release(); ctx->d_temp.release();
+    ctx->d_counters.release(); ctx->h_counters.release();
+    ctx->d_disc.release(); ctx->d_groups.release(); ctx->d_pchr.release(); ctx->d_ppos.release(); ctx->dc_read_off.release(); ctx->dc_n_first.release();
+    ctx->dc_first_total.release(); ctx->dc_second_total.release(); ctx->dc_ref_id.release(); ctx->dc_ref_pos.release(); ctx->dc_read_pos.release();
+    ctx->dc_match_ref.release(); ctx->dc_match_read.release(); ctx->dc_res0.release(); ctx->dc_rev.release();
+    ctx->d_trigger.release(); ctx->d_rest.release(); ctx->d_rest2.release(); ctx->d_restkey.release(); ctx->d_restkey2.release();
+    ctx->d_seeds.release(); ctx->d_margin.release(); ctx->d_seedstate.release();
+    ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
+    ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
+    ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
+    ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
+    ctx->h_chr.release(); ctx->h_pos.release(); ctx->h_len.release(); ctx->h_cnt3.release(); ctx->h_sum3.release(); ctx->h_ind1.release(); ctx->h_ind2.release();
+    ctx->h_w.release(); ctx->h_chimblk.release(); ctx->h_heads.release(); ctx->h_seeds.release();
+    for (auto &kv : ctx->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *sqg_last_error(const sqg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+float sqg_phase_ms(const sqg_ctx *ctx, const char *name) {
+    if (!ctx || !name) return -1.f;
+    auto it = ctx->timers.find(name);
+    if (it == ctx->timers.end() || !it->second.done) return -1.f;
+    if (cudaEventSynchronize(it->second.b) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) return -1.f;
+    return ms;
+}
+int64_t sqg_launch_count(const sqg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+static int validate_batch(sqg_ctx *ctx) {
+    CK(ctx->d_counters.ensure(16));
+    CK(ctx->h_counters.ensure(16));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int64_t), ctx->stream));
+    if (ctx->batch.n_rec > 0) LAUNCH(k_validate, blocks_for(ctx->batch.n_rec), kThreads, ctx->batch, ctx->params.n_ref, (int32_t *)ctx->d_counters.p);
+    CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int32_t flags = *(int32_t *)ctx->h_counters.p;
+    if (flags & 1) FAIL(SQG_EINVAL, "record with ref_id outside [-1, n_ref)");
+    if (flags & 2) FAIL(SQG_EUNSUPPORTED, "mapped record with ref_id -1");
+    if (flags & 4) FAIL(SQG_EUNSUPPORTED, "record with more than 16 aligned blocks or a decreasing blk_off");
+    if (flags & 8) FAIL(SQG_EINVAL, "batch is not sorted by (ref_id, pos)");
+    return SQG_OK;
+}
+
+extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t first_record_index) {
+    if (!ctx || !hb || hb->n_rec < 0 || hb->n_blk < 0) return SQG_EINVAL;
+    if (hb->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
+    CK(cudaSetDevice(ctx->device));
+    PHASE_BEGIN("h2d");
+    const size_t n = (size_t)hb->n_rec, nb = (size_t)hb->n_blk;
+#define UP(buf, src, cnt)                                                                                       \
+    do {                                                                                                        \
+        CK(ctx->buf.ensure((cnt) ? (cnt) : 1));                                                                 \
+        if (cnt) CK(cudaMemcpyAsync(ctx->buf.p, hb->src, (cnt) * sizeof(*hb->src), cudaMemcpyHostToDevice, ctx->stream)); \
+    } while (0)
+    UP(o_ref_id, ref_id, n); UP(o_pos, pos, n); UP(o_mate_ref_id, mate_ref_id, n); UP(o_mate_pos, mate_pos, n); UP(o_end_pos, end_pos, n);
+    UP(o_flag, flag, n); UP(o_total_len, total_len, n); UP(o_lowphred_run, lowphred_run, n); UP(o_mapq, mapq, n); UP(o_aux, aux, n);
+    UP(o_blk_off, blk_off, n + 1);
+    UP(o_blk_ref_pos, blk_ref_pos, nb); UP(o_blk_match_ref, blk_match_ref, nb); UP(o_blk_read_pos, blk_read_pos, nb); UP(o_blk_match_read, blk_match_read, nb);
+#undef UP
+    DevBatch &b = ctx->batch;
+    b.n_rec = hb->n_rec; b.n_blk = hb->n_blk;
+    b.ref_id = ctx->o_ref_id.p; b.pos = ctx->o_pos.p; b.mate_ref_id = ctx->o_mate_ref_id.p; b.mate_pos = ctx->o_mate_pos.p; b.end_pos = ctx->o_end_pos.p;
+    b.flag = ctx->o_flag.p; b.total_len = ctx->o_total_len.p; b.lowphred_run = ctx->o_lowphred_run.p; b.mapq = ctx->o_mapq.p; b.aux = ctx->o_aux.p;
+    b.blk_off = ctx->o_blk_off.p; b.blk_ref_pos = ctx->o_blk_ref_pos.p; b.blk_match_ref = ctx->o_blk_match_ref.p;
+    b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
+    PHASE_END("h2d");
+    ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->first_record_index = first_record_index;
+    return validate_batch(ctx);
+}
+
+extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, int64_t first_record_index) {
+    if (!ctx || !db || db->n_rec < 0) return SQG_EINVAL;
+    if (db->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
+    CK(cudaSetDevice(ctx->device));
+    DevBatch &b = ctx->batch;
+    b.n_rec = db->n_rec; b.n_blk = db->n_blk;
+    b.ref_id = db->ref_id; b.pos = db->pos; b.mate_ref_id = db->mate_ref_id; b.mate_pos = db->mate_pos; b.end_pos = db->end_pos;
+    b.flag = db->flag; b.total_len = db->total_len; b.lowphred_run = db->lowphred_run; b.mapq = db->mapq; b.aux = db->aux;
+    b.blk_off = db->blk_off; b.blk_ref_pos = db->blk_ref_pos; b.blk_match_ref = db->blk_match_ref; b.blk_read_pos = db->blk_read_pos; b.blk_match_read = db->blk_match_read;
+    ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->first_record_index = first_record_index;
+    return validate_batch(ctx);
+}
+
+extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
+    if (!ctx || !c || c->n_reads < 0) return SQG_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < c->n_reads; i++) {
+        const uint32_t nb = c->read_off[i + 1] - c->read_off[i], nf = c->n_first[i];
+        if (nf > nb || nf > (uint32_t)kMaxBlocks || nb - nf > (uint32_t)kMaxBlocks) FAIL(SQG_EUNSUPPORTED, "chimeric read with more than 16 blocks in one mate");
+    }
+    sqh::chimeric_prepass(*c, ctx->params.n_ref, ctx->params.read_len, ctx->pre);
+    ctx->c_n_reads = c->n_reads; ctx->c_n_blk = c->n_blk;
+    const size_t nr = (size_t)c->n_reads, nb = (size_t)c->n_blk;
+    const size_t nD1 = ctx->pre.disc.size(), nG = ctx->pre.groups.size(), nP = ctx->pre.part_chr.size();
+#define UPV(buf, src, cnt)                                                                                     \
+    do {                                                                                                       \
+        CK(ctx->buf.ensure((cnt) ? (cnt) : 1));                                                                \
+        if (cnt) CK(cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream)); \
+    } while (0)
+    UPV(d_disc, ctx->pre.disc.data(), nD1); UPV(d_groups, ctx->pre.groups.data(), nG);
+    UPV(d_pchr, ctx->pre.part_chr.data(), nP); UPV(d_ppos, ctx->pre.part_pos.data(), nP);
+    UPV(dc_read_off, c->read_off, nr + 1); UPV(dc_n_first, c->n_first, nr);
+    UPV(dc_first_total, c->first_total_len, nr); UPV(dc_second_total, c->second_total_len, nr);
+    UPV(dc_ref_id, c->blk_ref_id, nb); UPV(dc_ref_pos, c->blk_ref_pos, nb); UPV(dc_read_pos, c->blk_read_pos, nb);
+    UPV(dc_match_ref, c->blk_match_ref, nb); UPV(dc_match_read, c->blk_match_read, nb); UPV(dc_rev, c->blk_is_reverse, nb);
+#undef UPV
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_chim = true;
+    return SQG_OK;
+}
+
+static int ensure_temp(sqg_ctx *ctx, size_t bytes) { CK(ctx->d_temp.ensure(bytes + 256)); return SQG_OK; }
+#define ENSURE_TEMP(bytes) do { int rc_ = ensure_temp(ctx, bytes); if (rc_) return rc_; } while (0)
+
+// classify stage: cls, other_excl, gap list, partial list, first kept record
+static int run_classify(sqg_ctx *ctx) {
+    if (ctx->classified) return SQG_OK;
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec;
+    PHASE_BEGIN("classify");
+    CK(ctx->d_cls.ensure(n + 1)); CK(ctx->d_other.ensure(n + 1)); CK(ctx->d_scratch32.ensure(n + 1));
+    CK(ctx->d_gap.ensure(n + 1)); CK(ctx->d_pc.ensure(n + 1));
+    CK(ctx->d_counters.ensure(16)); CK(ctx->h_counters.ensure(16));
+    ctx->n_gap = 0; ctx->n_pc = 0; ctx->first_kept = n;
+    if (n > 0) {
+        cub::CountingInputIterator<int32_t> cnt(0);
+        size_t tb = 0;
+        {   // last gate-passing record at or before r
+            cub::TransformInputIterator<int32_t, GateIdxOp, cub::CountingInputIterator<int32_t>> it(cnt, GateIdxOp{b, ctx->params.min_mapq});
+            CK(cub::DeviceScan::InclusiveScan(nullptr, tb, it, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, it, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
+            ctx->launches += 2;
+        }
+        LAUNCH(k_classify, blocks_for(n), kThreads, b, ctx->params, ctx->d_scratch32.p, ctx->d_cls.p, ctx->d_other.p);
+        {   // otherChr/otherrightmost before each record
+            CK(cub::DeviceScan::ExclusiveScan(nullptr, tb, ctx->d_other.p, ctx->d_other.p, MaxU64(), (uint64_t)(1ull << 32), (int)n, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceScan::ExclusiveScan(ctx->d_temp.p, tb, ctx->d_other.p, ctx->d_other.p, MaxU64(), (uint64_t)(1ull << 32), (int)n, ctx->stream));
+            ctx->launches += 2;
+        }
+        int32_t *d_nsel = (int32_t *)ctx->d_counters.p;
+        {
+            IsGapOp op{b, ctx->d_cls.p, ctx->d_other.p, ctx->params.read_len};
+            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_gap.p, d_nsel, (int)n, op, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_gap.p, d_nsel, (int)n, op, ctx->stream));
+            IsPartOp op2{ctx->d_cls.p};
+            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_pc.p, d_nsel + 1, (int)n, op2, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_pc.p, d_nsel + 1, (int)n, op2, ctx->stream));
+            cub::TransformInputIterator<int64_t, FirstKeptOp, cub::CountingInputIterator<int32_t>> fk(cnt, FirstKeptOp{ctx->d_cls.p, n});
+            CK(cub::DeviceReduce::Reduce(nullptr, tb, fk, ctx->d_counters.p + 2, (int)n, MinI64(), (int64_t)n, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceReduce::Reduce(ctx->d_temp.p, tb, fk, ctx->d_counters.p + 2, (int)n, MinI64(), (int64_t)n, ctx->stream));
+            ctx->launches += 6;
+        }
+        CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PHASE_END("classify");
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n > 0) {
+        const int32_t *sel = (const int32_t *)ctx->h_counters.p;
+        ctx->n_gap = sel[0]; ctx->n_pc = sel[1]; ctx->first_kept = ctx->h_counters.p[2];
+    }
+    ctx->classified = true;
+    return SQG_OK;
+}
+
+static int install_nodes(sqg_ctx *ctx) {  // from h_nchr/h_npos/h_nend
+    const int32_t N = (int32_t)ctx->h_nchr.size(), n_ref = ctx->params.n_ref;
+    ctx->h_chr_first.assign(n_ref + 1, N);
+    for (int32_t i = N - 1; i >= 0; i--) {
+        const int32_t c = ctx->h_nchr[i];
+        if (c < 0 || c >= n_ref) FAIL(SQG_EINVAL, "segment with chromosome outside [0, n_ref)");
+        ctx->h_chr_first[c] = i;
+    }
+    for (int32_t c = n_ref - 1; c >= 0; c--) if (ctx->h_chr_first[c] == N) ctx->h_chr_first[c] = ctx->h_chr_first[c + 1];
+    for (int32_t i = 0; i + 1 < N; i++) {
+        const bool same = ctx->h_nchr[i] == ctx->h_nchr[i + 1];
+        if (ctx->h_nchr[i] > ctx->h_nchr[i + 1] || (same && ctx->h_nend[i] != ctx->h_npos[i + 1])) FAIL(SQG_EINVAL, "segments must be sorted and tile each chromosome");
+    }
+    CK(ctx->d_nchr.ensure(N + 1)); CK(ctx->d_npos.ensure(N + 1)); CK(ctx->d_nend.ensure(N + 1)); CK(ctx->d_chr_first.ensure(n_ref + 2));
+    if (N) {
+        CK(cudaMemcpyAsync(ctx->d_nchr.p, ctx->h_nchr.data(), N * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_npos.p, ctx->h_npos.data(), N * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_nend.p, ctx->h_nend.data(), N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->d_chr_first.p, ctx->h_chr_first.data(), (n_ref + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nt.n = N; ctx->nt.n_ref = n_ref; ctx->nt.chr = ctx->d_nchr.p; ctx->nt.pos = ctx->d_npos.p; ctx->nt.end = ctx->d_nend.p; ctx->nt.chr_first = ctx->d_chr_first.p;
+    ctx->have_nodes = true; ctx->have_edge_table = false;
+    return SQG_OK;
+}
+
+extern "C" int sqg_set_nodes(sqg_ctx *ctx, const int32_t *chr, const int32_t *pos, const int32_t *len, int64_t n_nodes) {
+    if (!ctx || !chr || !pos || !len || n_nodes <= 0 || n_nodes > 0x7ffffff0ll) return SQG_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    ctx->h_nchr.assign(chr, chr + n_nodes); ctx->h_npos.assign(pos, pos + n_nodes); ctx->h_nend.resize(n_nodes);
+    for (int64_t i = 0; i < n_nodes; i++) ctx->h_nend[i] = pos[i] + len[i];
+    return install_nodes(ctx);
+}
+
+// seeds (device) -> normalised, genome-tiling segment table (SegmentGraph.cpp:19-38, 706-761)
+static int tile_genome(sqg_ctx *ctx, int32_t n_seeds) {
+    CK(ctx->h_seeds.ensure(n_seeds + 1));
+    if (n_seeds) CK(cudaMemcpyAsync(ctx->h_seeds.p, ctx->d_seeds.p, n_seeds * sizeof(SeedNode), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    SeedNode *s = ctx->h_seeds.p;
+    std::sort(s, s + n_seeds, [](const SeedNode &a, const SeedNode &c) { return a.chr != c.chr ? a.chr < c.chr : (a.pos != c.pos ? a.pos < c.pos : a.len < c.len); });
+    std::vector<SeedNode> norm;
+    norm.reserve(n_seeds);
+    for (int32_t i = 0; i < n_seeds; i++) {
+        if (norm.empty() || norm.back().chr != s[i].chr || norm.back().pos + norm.back().len <= s[i].pos) norm.push_back(s[i]);
+        else norm.back().len = std::max(norm.back().pos + norm.back().len, s[i].pos + s[i].len) - norm.back().pos;
+    }
+    ctx->h_nchr.clear(); ctx->h_npos.clear(); ctx->h_nend.clear();
+    size_t k = 0;
+    for (int32_t c = 0; c < ctx->params.n_ref; c++) {
+        int32_t cur = 0;
+        bool any = false;
+        for (; k < norm.size() && norm[k].chr == c; k++) {
+            int32_t st = norm[k].pos;
+            const int32_t en = norm[k].pos + norm[k].len;
+            if (norm[k].len <= 0 || en > ctx->ref_len[c]) FAIL(SQG_EUNSUPPORTED, "seed segment outside its chromosome (the reference asserts here, SegmentGraph.cpp:709)");
+            if (st - cur > 100) { ctx->h_nchr.push_back(c); ctx->h_npos.push_back(cur); ctx->h_nend.push_back(st); }
+            else st = cur;
+            ctx->h_nchr.push_back(c); ctx->h_npos.push_back(st); ctx->h_nend.push_back(en);
+            cur = en; any = true;
+        }
+        if (!any || cur != ctx->ref_len[c]) { ctx->h_nchr.push_back(c); ctx->h_npos.push_back(cur); ctx->h_nend.push_back(ctx->ref_len[c]); }
+    }
+    return install_nodes(ctx);
+}
+
+extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
+                               int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty) {
+    if (!ctx || !chr || !pos || !len || !n_nodes || !count3 || !sumlen3 || !reads_other_nonempty) return SQG_EINVAL;
+    if (!ctx->have_batch || !ctx->have_chim) FAIL(SQG_ESTATE, "load the concordant batch and the chimeric reads first");
+    CK(cudaSetDevice(ctx->device));
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec;
+    const int32_t nD = (int32_t)ctx->pre.disc.size() - 1, nG = (int32_t)ctx->pre.groups.size(), nP = (int32_t)ctx->pre.part_chr.size();
+    if (nD <= 0) FAIL(SQG_EUNSUPPORTED, "no discordant block in the chimeric reads: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
+    int rc = run_classify(ctx);
+    if (rc) return rc;
+
+    PHASE_BEGIN("seed");
+    CK(ctx->d_trigger.ensure(nG + 1));
+    LAUNCH(k_triggers, blocks_for(nG), kThreads, b, ctx->d_cls.p, ctx->d_groups.p, nG, ctx->d_trigger.p);
+    // ConcordRest candidates, sorted by (chr,pos)
+    int64_t rest_cap = std::max<int64_t>(1024, ctx->d_rest.cap);
+    int64_t n_rest = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(ctx->d_rest.ensure(rest_cap)); CK(ctx->d_rest2.ensure(rest_cap)); CK(ctx->d_restkey.ensure(rest_cap)); CK(ctx->d_restkey2.ensure(rest_cap));
+        CK(cudaMemsetAsync(ctx->d_counters.p + 4, 0, sizeof(int64_t), ctx->stream));
+        if (n > 0) LAUNCH(k_rest_collect, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->d_groups.p, ctx->d_disc.p, nG, ctx->params.read_len,
+                          ctx->d_rest.p, ctx->d_restkey.p, rest_cap, ctx->d_counters.p + 4);
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 4, ctx->d_counters.p + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_rest = ctx->h_counters.p[4];
+        if (n_rest <= rest_cap) break;
+        rest_cap = n_rest + 1024;
+    }
+    if (n_rest > 0) {
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, 64, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp.p, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, 64, ctx->stream));
+        ctx->launches += 4;
+    }
+    // the state machine
+    const int32_t out_cap = 4 * nD + 16;
+    const int32_t margin_cap = 4 * nD + 2 * nP + 2 * ctx->n_pc + 64;
+    CK(ctx->d_seeds.ensure(out_cap)); CK(ctx->d_margin.ensure(margin_cap)); CK(ctx->d_seedstate.ensure(1));
+    SeedInputs in;
+    in.b = b; in.cls = ctx->d_cls.p; in.other_excl = ctx->d_other.p;
+    in.gap_rec = ctx->d_gap.p; in.n_gap = ctx->n_gap; in.pc_rec = ctx->d_pc.p; in.n_pc = ctx->n_pc;
+    in.D = ctx->d_disc.p; in.nD = nD; in.G = ctx->d_groups.p; in.nG = nG; in.trigger = ctx->d_trigger.p;
+    in.Pchr = ctx->d_pchr.p; in.Ppos = ctx->d_ppos.p; in.nP = nP;
+    in.rest = ctx->d_rest2.p; in.n_rest = (int32_t)n_rest; in.read_len = ctx->params.read_len;
+    int32_t *d_gdone = (int32_t *)(ctx->d_counters.p + 6), *d_err = (int32_t *)(ctx->d_counters.p + 7);
+    LAUNCH(k_seed_single, 1, 1, in, ctx->d_seeds.p, out_cap, ctx->d_margin.p, margin_cap, ctx->first_kept, n, ctx->d_seedstate.p, d_gdone, d_err);
+    PHASE_END("seed");
+    SeedState st;
+    CK(cudaMemcpyAsync(&st, ctx->d_seedstate.p, sizeof(SeedState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters.p + 6, ctx->d_counters.p + 6, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int64_t> trig_last(1, n);
+    if (nG > 0) CK(cudaMemcpyAsync(trig_last.data(), ctx->d_trigger.p + (nG - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int32_t g_done = *(int32_t *)(ctx->h_counters.p + 6), serr = *(int32_t *)(ctx->h_counters.p + 7);
+    if (serr) FAIL(SQG_ENOMEM, serr == 1 ? "seed machine: margin scratch overflow" : "seed machine: output overflow");
+    if (st.n_out == 0) FAIL(SQG_EUNSUPPORTED, "no seed segment was produced: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
+
+    PHASE_BEGIN("tile");
+    rc = tile_genome(ctx, st.n_out);
+    if (rc) return rc;
+    PHASE_END("tile");
+
+    // break index of the depth streams (:338-339): the first kept record after the last group's trigger is still pushed
+    ctx->r_break = n;
+    if (g_done == nG) {
+        // find it on the device-side class bytes via a tiny host loop over a copied window
+        int64_t r = trig_last[0] + 1;
+        std::vector<uint8_t> win(4096);
+        bool found = false;
+        while (r < n && !found) {
+            const int64_t m = std::min<int64_t>(4096, n - r);
+            CK(cudaMemcpyAsync(win.data(), ctx->d_cls.p + r, m, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (int64_t k = 0; k < m; k++) if (win[k] & CLS_KEEP) { ctx->r_break = r + k + 1; found = true; break; }
+            r += m;
+        }
+    }
+    // depth
+    PHASE_BEGIN("depth");
+    const int32_t N = ctx->nt.n;
+    CK(ctx->d_cnt3.ensure(3 * (size_t)N + 4)); CK(ctx->d_sum3.ensure(3 * (size_t)N + 4));
+    CK(cudaMemsetAsync(ctx->d_cnt3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_sum3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
+    LAUNCH(k_depth_disc, blocks_for(nD), kThreads, ctx->nt, ctx->d_disc.p, nD, ctx->d_cnt3.p, ctx->d_sum3.p);
+    if (n > 0) {
+        int32_t *d_flag = ctx->d_cnt3.p + 3 * (size_t)N;
+        LAUNCH(k_depth_targets, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_scratch32.p,
+               ctx->d_cnt3.p + 2 * (size_t)N, ctx->d_sum3.p + 2 * (size_t)N, d_flag);
+        size_t tb = 0;
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_scratch32.p, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_scratch32.p, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
+        ctx->launches += 2;
+        LAUNCH(k_depth_main_count, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_scratch32.p,
+               ctx->d_cnt3.p + (size_t)N, ctx->d_sum3.p + (size_t)N);
+    }
+    PHASE_END("depth");
+    CK(ctx->h_chr.ensure(N)); CK(ctx->h_pos.ensure(N)); CK(ctx->h_len.ensure(N)); CK(ctx->h_cnt3.ensure(3 * (size_t)N + 4)); CK(ctx->h_sum3.ensure(3 * (size_t)N + 4));
+    CK(cudaMemcpyAsync(ctx->h_cnt3.p, ctx->d_cnt3.p, (3 * (size_t)N + 4) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_sum3.p, ctx->d_sum3.p, 3 * (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int32_t i = 0; i < N; i++) { ctx->h_chr.p[i] = ctx->h_nchr[i]; ctx->h_pos.p[i] = ctx->h_npos[i]; ctx->h_len.p[i] = ctx->h_nend[i] - ctx->h_npos[i]; }
+    *chr = ctx->h_chr.p; *pos = ctx->h_pos.p; *len = ctx->h_len.p; *n_nodes = N;
+    *count3 = ctx->h_cnt3.p; *sumlen3 = ctx->h_sum3.p;
+    *reads_other_nonempty = ctx->h_cnt3.p[3 * (size_t)N] != 0;
+    return SQG_OK;
+}
+
+// sort raw keys, run-length reduce, unpack
+static int reduce_edges(sqg_ctx *ctx, int64_t n_raw, const int32_t *d_weights_in) {
+    ctx->n_unique_edges = 0;
+    CK(ctx->d_ekeys2.ensure(n_raw + 1)); CK(ctx->d_ukeys.ensure(n_raw + 1)); CK(ctx->d_ecount.ensure(n_raw + 1));
+    if (n_raw > 0) {
+        size_t tb = 0;
+        if (!d_weights_in) {
+            CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, ctx->d_ekeys.p, ctx->d_ekeys2.p, (int)n_raw, 0, 64, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceRadixSort::SortKeys(ctx->d_temp.p, tb, ctx->d_ekeys.p, ctx->d_ekeys2.p, (int)n_raw, 0, 64, ctx->stream));
+            CK(cub::DeviceRunLengthEncode::Encode(nullptr, tb, ctx->d_ekeys2.p, ctx->d_ukeys.p, ctx->d_ecount.p, (int32_t *)(ctx->d_counters.p + 8), (int)n_raw, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceRunLengthEncode::Encode(ctx->d_temp.p, tb, ctx->d_ekeys2.p, ctx->d_ukeys.p, ctx->d_ecount.p, (int32_t *)(ctx->d_counters.p + 8), (int)n_raw, ctx->stream));
+        } else {
+            CK(ctx->d_sens.ensure(n_raw + 1));
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_ekeys.p, ctx->d_ekeys2.p, d_weights_in, ctx->d_sens.p, (int)n_raw, 0, 64, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp.p, tb, ctx->d_ekeys.p, ctx->d_ekeys2.p, d_weights_in, ctx->d_sens.p, (int)n_raw, 0, 64, ctx->stream));
+            CK(cub::DeviceReduce::ReduceByKey(nullptr, tb, ctx->d_ekeys2.p, ctx->d_ukeys.p, ctx->d_sens.p, ctx->d_ecount.p, (int32_t *)(ctx->d_counters.p + 8), cub::Sum(), (int)n_raw, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceReduce::ReduceByKey(ctx->d_temp.p, tb, ctx->d_ekeys2.p, ctx->d_ukeys.p, ctx->d_sens.p, ctx->d_ecount.p, (int32_t *)(ctx->d_counters.p + 8), cub::Sum(), (int)n_raw, ctx->stream));
+        }
+        ctx->launches += 5;
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 8, ctx->d_counters.p + 8, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->n_unique_edges = *(int32_t *)(ctx->h_counters.p + 8);
+    }
+    ctx->have_edge_table = true;
+    return SQG_OK;
+}
+
+static int export_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges) {
+    const int64_t m = ctx->n_unique_edges;
+    CK(ctx->d_e_ind1.ensure(m + 1)); CK(ctx->d_e_ind2.ensure(m + 1)); CK(ctx->d_e_w.ensure(m + 1)); CK(ctx->d_e_heads.ensure(m + 1));
+    CK(ctx->h_ind1.ensure(m + 1)); CK(ctx->h_ind2.ensure(m + 1)); CK(ctx->h_w.ensure(m + 1)); CK(ctx->h_heads.ensure(m + 1));
+    if (m > 0) {
+        LAUNCH(k_unpack_edges, blocks_for(m), kThreads, ctx->d_ukeys.p, ctx->d_ecount.p, m, ctx->d_e_ind1.p, ctx->d_e_ind2.p, ctx->d_e_heads.p, ctx->d_e_w.p);
+        CK(cudaMemcpyAsync(ctx->h_ind1.p, ctx->d_e_ind1.p, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_ind2.p, ctx->d_e_ind2.p, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_w.p, ctx->d_e_w.p, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_heads.p, ctx->d_e_heads.p, m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    // BuildEdges drops Weight <= 0 (:1953-1957): weights here are run lengths, always > 0
+    *ind1 = ctx->h_ind1.p; *ind2 = ctx->h_ind2.p; *heads = ctx->h_heads.p; *weight = ctx->h_w.p; *n_edges = m;
+    return SQG_OK;
+}
+
+extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges, sqg_chimeric *chim_inout) {
+    if (!ctx || !ind1 || !ind2 || !heads || !weight || !n_edges) return SQG_EINVAL;
+    if (!ctx->have_batch || !ctx->have_chim || !ctx->have_nodes) FAIL(SQG_ESTATE, "build_edges needs the concordant batch, the chimeric reads and a segment table");
+    if (chim_inout && (chim_inout->n_reads != ctx->c_n_reads || chim_inout->n_blk != ctx->c_n_blk)) FAIL(SQG_EINVAL, "chim_inout does not match the loaded chimeric reads");
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_classify(ctx);
+    if (rc) return rc;
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec;
+    ChimDev cd;
+    cd.n_reads = ctx->c_n_reads; cd.read_off = ctx->dc_read_off.p; cd.n_first = ctx->dc_n_first.p;
+    cd.first_total = ctx->dc_first_total.p; cd.second_total = ctx->dc_second_total.p;
+    cd.ref_id = ctx->dc_ref_id.p; cd.ref_pos = ctx->dc_ref_pos.p; cd.read_pos = ctx->dc_read_pos.p; cd.match_ref = ctx->dc_match_ref.p; cd.match_read = ctx->dc_match_read.p;
+    cd.rev = ctx->dc_rev.p;
+    int64_t cap = std::max<int64_t>((int64_t)ctx->d_ekeys.cap, n / 2 + 4 * ctx->c_n_blk + 2 * ctx->c_n_reads + 4096);
+    int64_t n_raw = 0;
+    CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1)); CK(ctx->d_sens.ensure(n + 1));
+    PHASE_BEGIN("depth_edges");
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(ctx->d_ekeys.ensure(cap));
+        cap = (int64_t)ctx->d_ekeys.cap;
+        unsigned long long *d_cnt = (unsigned long long *)(ctx->d_counters.p + 9);
+        CK(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t), ctx->stream));
+        EdgeSink sink{ctx->d_ekeys.p, cap, d_cnt};
+        EdgeSinkSerial ssink{ctx->d_ekeys.p, cap, d_cnt};
+        if (cd.n_reads > 0) {
+            LAUNCH(k_chim_edges, blocks_for(cd.n_reads), kThreads, cd, ctx->params, ctx->nt, ctx->dc_res0.p, sink);
+            LAUNCH(k_chim_fixup, 1, 1, cd, ctx->params, ctx->nt, ctx->dc_res0.p, ssink);
+        }
+        int32_t n_sens = 0;
+        if (n > 0) {
+            LAUNCH(k_conc_edges, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->params, ctx->nt, ctx->d_scratch32.p, sink);
+            cub::CountingInputIterator<int32_t> cnt(0);
+            IsSensOp op{ctx->d_scratch32.p};
+            size_t tb = 0;
+            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_sens.p, (int32_t *)(ctx->d_counters.p + 10), (int)n, op, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_sens.p, (int32_t *)(ctx->d_counters.p + 10), (int)n, op, ctx->stream));
+            ctx->launches += 2;
+            CK(cudaMemcpyAsync(ctx->h_counters.p + 10, ctx->d_counters.p + 10, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            n_sens = *(int32_t *)(ctx->h_counters.p + 10);
+            if (n_sens > 0) LAUNCH(k_conc_fixup, 1, 1, b, ctx->params, ctx->nt, ctx->d_scratch32.p, ctx->d_sens.p, n_sens, ssink);
+        }
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_raw = ctx->h_counters.p[9];
+        if (n_raw <= cap) break;
+        if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge buffer overflow");
+        cap = n_raw + 4096;  // rerun with room for everything (chimeric trims are idempotent)
+    }
+    PHASE_END("depth_edges");
+    PHASE_BEGIN("edge_sort");
+    rc = reduce_edges(ctx, n_raw, nullptr);
+    if (rc) return rc;
+    PHASE_END("edge_sort");
+    if (chim_inout && ctx->c_n_blk > 0) {  // LocateRead trimmed Chimrecord in place (:1229-1248)
+        const size_t nb = (size_t)ctx->c_n_blk;
+        CK(cudaMemcpyAsync(chim_inout->blk_ref_pos, ctx->dc_ref_pos.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(chim_inout->blk_read_pos, ctx->dc_read_pos.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(chim_inout->blk_match_ref, ctx->dc_match_ref.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(chim_inout->blk_match_read, ctx->dc_match_read.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return export_edges(ctx, ind1, ind2, heads, weight, n_edges);
+}
+
+extern "C" int sqg_edges_device_table(sqg_ctx *ctx, uint64_t **d_keys, int32_t **d_weights, int64_t *n) {
+    if (!ctx || !d_keys || !d_weights || !n) return SQG_EINVAL;
+    if (!ctx->have_edge_table) FAIL(SQG_ESTATE, "no edge table: call sqg_build_edges first");
+    *d_keys = ctx->d_ukeys.p; *d_weights = ctx->d_ecount.p; *n = ctx->n_unique_edges;
+    return SQG_OK;
+}
+
+extern "C" int sqg_merge_edge_tables(sqg_ctx *ctx, const uint64_t *d_keys, const int32_t *d_weights, int64_t n,
+                                     int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges) {
+    if (!ctx || n < 0 || !ind1 || !ind2 || !heads || !weight || !n_edges) return SQG_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    PHASE_BEGIN("edge_merge");
+    CK(ctx->d_ekeys.ensure(n + 1));
+    if (n > 0) CK(cudaMemcpyAsync(ctx->d_ekeys.p, d_keys, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    int rc = reduce_edges(ctx, n, d_weights);
+    if (rc) return rc;
+    PHASE_END("edge_merge");
+    return export_edges(ctx, ind1, ind2, heads, weight, n_edges);
+}
+
+extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t *cov_out) {
+    if (!ctx || K < 0 || (K > 0 && (!bp_chr || !bp_pos || !cov_out))) return SQG_EINVAL;
+    if (!ctx->have_batch) FAIL(SQG_ESTATE, "load the concordant batch first");
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t k = 0; k + 1 < K; k++)
+        if (bp_chr[k] > bp_chr[k + 1] || (bp_chr[k] == bp_chr[k + 1] && bp_pos[k] > bp_pos[k + 1])) FAIL(SQG_EINVAL, "breakpoints must be sorted by (chr, pos)");
+    if (K == 0) return SQG_OK;
+    int rc = run_classify(ctx);
+    if (rc) return rc;
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec;
+    PHASE_BEGIN("coverage");
+    CK(ctx->d_bpchr.ensure(K)); CK(ctx->d_bppos.ensure(K)); CK(ctx->d_bpkey.ensure(K)); CK(ctx->d_r0.ensure(K)); CK(ctx->d_t.ensure(K)); CK(ctx->d_cov.ensure(K));
+    CK(ctx->d_covM.ensure(n + 1));
+    CK(cudaMemcpyAsync(ctx->d_bpchr.p, bp_chr, K * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_bppos.p, bp_pos, K * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_cov.p, 0, K * 4, ctx->stream));
+    if (n > 0) {
+        cub::CountingInputIterator<int32_t> cnt(0);
+        cub::TransformInputIterator<uint64_t, CoverKeyOp, cub::CountingInputIterator<int32_t>> it(cnt, CoverKeyOp{b, ctx->d_cls.p});
+        size_t tb = 0;
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, it, ctx->d_covM.p, MaxU64(), (int)n, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, it, ctx->d_covM.p, MaxU64(), (int)n, ctx->stream));
+        ctx->launches += 2;
+    }
+    LAUNCH(k_cov_r0, blocks_for(K), kThreads, ctx->d_covM.p, n, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_bpkey.p, ctx->d_r0.p);
+    LAUNCH(k_cov_chain, 1, 1, b, ctx->d_cls.p, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
+    if (n > 0) LAUNCH(k_cov_count, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
+    PHASE_END("coverage");
+    CK(cudaMemcpyAsync(cov_out, ctx->d_cov.p, K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SQG_OK;
+}

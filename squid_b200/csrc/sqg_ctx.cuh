@@ -1,0 +1,132 @@
+// Context of the C ABI: owns the CUDA stream, the HBM-resident batches, the segment table and all
+// scratch.  One context per GPU per run (include/squid_b200.h).
+#ifndef SQG_CTX_CUH
+#define SQG_CTX_CUH
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "host/prepass.h"
+#include "sq_common.cuh"
+#include "sq_seed.cuh"
+#include "squid_b200.h"
+
+namespace sq {
+
+template <class T> struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T> struct HBuf {  // pinned host
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct PhaseTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool done = false;
+};
+
+}  // namespace sq
+
+struct sqg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    sq::Params params{};
+    std::vector<int32_t> ref_len;
+    int64_t launches = 0;
+    std::map<std::string, sq::PhaseTimer> timers;
+
+    // concordant batch
+    bool have_batch = false, batch_owned = false, classified = false;
+    int64_t first_record_index = 0;
+    sq::DevBatch batch;
+    sq::DBuf<int32_t> o_ref_id, o_pos, o_mate_ref_id, o_mate_pos, o_end_pos, o_blk_ref_pos, o_blk_match_ref;
+    sq::DBuf<uint16_t> o_flag, o_total_len, o_lowphred_run, o_blk_read_pos, o_blk_match_read;
+    sq::DBuf<uint8_t> o_mapq, o_aux;
+    sq::DBuf<uint32_t> o_blk_off;
+
+    // classify products
+    sq::DBuf<uint8_t> d_cls;
+    sq::DBuf<uint64_t> d_other;     // other_key, then its exclusive max-scan
+    sq::DBuf<int32_t> d_scratch32;  // lastpass / depth targets / res0
+    sq::DBuf<int32_t> d_gap, d_pc;
+    int32_t n_gap = 0, n_pc = 0;
+    int64_t first_kept = 0;
+    sq::DBuf<unsigned char> d_temp;  // CUB temp storage
+    sq::DBuf<int64_t> d_counters;    // small device counters
+    sq::HBuf<int64_t> h_counters;
+
+    // chimeric side
+    bool have_chim = false;
+    sqh::ChimPrepass pre;
+    std::vector<uint32_t> c_read_off;
+    std::vector<uint16_t> c_n_first;
+    std::vector<int32_t> c_first_total, c_second_total;
+    int64_t c_n_reads = 0, c_n_blk = 0;
+    sq::DBuf<sq::DiscBlock> d_disc;
+    sq::DBuf<sq::Group> d_groups;
+    sq::DBuf<int32_t> d_pchr, d_ppos;
+    sq::DBuf<uint32_t> dc_read_off;
+    sq::DBuf<uint16_t> dc_n_first;
+    sq::DBuf<int32_t> dc_first_total, dc_second_total, dc_ref_id, dc_ref_pos, dc_read_pos, dc_match_ref, dc_match_read, dc_res0;
+    sq::DBuf<uint8_t> dc_rev;
+
+    // node building
+    sq::DBuf<int64_t> d_trigger;
+    sq::DBuf<sq::RestBlock> d_rest, d_rest2;
+    sq::DBuf<uint64_t> d_restkey, d_restkey2;
+    sq::DBuf<sq::SeedNode> d_seeds;
+    sq::DBuf<int32_t> d_margin;
+    sq::DBuf<sq::SeedState> d_seedstate;
+    int64_t r_break = 0;
+
+    // segment table
+    bool have_nodes = false;
+    std::vector<int32_t> h_nchr, h_npos, h_nend, h_chr_first;
+    sq::DBuf<int32_t> d_nchr, d_npos, d_nend, d_chr_first;
+    sq::NodeTable nt;
+    sq::DBuf<int32_t> d_cnt3, d_sum3;
+
+    // edges
+    sq::DBuf<uint64_t> d_ekeys, d_ekeys2, d_ukeys;
+    sq::DBuf<int32_t> d_ecount, d_sens;
+    sq::DBuf<int32_t> d_e_ind1, d_e_ind2, d_e_w;
+    sq::DBuf<uint8_t> d_e_heads;
+    int64_t n_unique_edges = 0;
+    bool have_edge_table = false;
+
+    // coverage
+    sq::DBuf<uint64_t> d_bpkey, d_covM;
+    sq::DBuf<int64_t> d_r0, d_t;
+    sq::DBuf<int32_t> d_cov, d_bpchr, d_bppos;
+
+    // pinned outputs
+    sq::HBuf<int32_t> h_chr, h_pos, h_len, h_cnt3, h_sum3, h_ind1, h_ind2, h_w, h_chimblk;
+    sq::HBuf<uint8_t> h_heads;
+    sq::HBuf<sq::SeedNode> h_seeds;
+};
+#endif
