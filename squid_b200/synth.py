@@ -160,66 +160,12 @@ def _simple_cigar(n, lclip, m, rclip):
     return _cigars_from_blocks(nblk, gs, gl, lclip.astype(np.int64), rclip.astype(np.int64))
 
 
-def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.005, n_genes: int | None = None,
-              fusion_support: float = 20.0, clip_frac: float = 0.02, adversarial: bool = True, min_block: int = 4):
-    """Returns (concordant AlnTable sorted by coordinate, chimeric AlnTable, info dict)."""
-    ref_len = np.asarray(GRCH38_LEN if ref_len is None else ref_len, dtype=np.int64)
-    rng = np.random.Generator(np.random.PCG64(seed))
-    if n_genes is None:
-        n_genes = int(max(8, min(20000, n_pairs // 400)))
-    tx = Transcriptome(rng, ref_len, n_genes)
-    p = tx.g_expr / tx.g_expr.sum()
-    gene = rng.choice(n_genes, size=n_pairs, p=p)
-    left, right = _pairs_from_transcripts(rng, tx, gene, 0, clip_frac, min_block)
-    n = left.n
-    parts = []
-    if adversarial and n >= 50:
-        # per-record decorations exercising the gate / low-phred / poly-A / duplicate rules
-        for t in (left, right):
-            r = rng.random(n)
-            t.lowrun[r < 0.005] = 20
-            r = rng.random(n)
-            mm = r < 0.01
-            t.mapq[mm] = 3; t.aux[mm] |= sqmb.AUX_IH; t.ih[mm] = 2
-            r = rng.random(n)
-            t.aux[r < 0.002] |= sqmb.AUX_XA
-            r = rng.random(n)
-            t.flag[r < 0.002] |= sqmb.FLAG_DUP
-            r = rng.random(n)
-            t.polya[r < 0.002] = 1
-            r = rng.random(n)
-            t.aux[(r < 0.002) & ((t.aux & sqmb.AUX_IH) == 0)] |= sqmb.AUX_IH  # IH:1 is kept
-            t.ih[(t.aux & sqmb.AUX_IH != 0) & (t.ih == 0)] = 1
-        # exact consecutive duplicates (different names)
-        d = np.flatnonzero(rng.random(n) < 0.003)
-        if d.size:
-            dl, dr = left.take(d), right.take(d)
-            dl.name_id = (np.uint64(500_000_000) + np.arange(d.size).astype(np.uint64)); dr.name_id = dl.name_id.copy()
-            parts += [dl, dr]
-        # mate-unmapped singletons
-        s = rng.random(n) < 0.004
-        left.flag[s] = (left.flag[s] | sqmb.FLAG_MATE_UNMAPPED) & ~np.uint16(sqmb.FLAG_PROPER | sqmb.FLAG_MATE_REVERSE)
-        left.mate_pos[s] = left.pos[s]
-        keep_right = ~s
-        right = right.take(np.flatnonzero(keep_right))
-        # long same-chromosome fragments (> -dp) and cross-chromosome pairs living in the concordant file
-        m = max(4, n // 1000)
-        g2 = rng.choice(n_genes, size=m, p=p)
-        l2, r2 = _pairs_from_transcripts(rng, tx, g2, 600_000_000, 0.0, min_block)
-        m = l2.n
-        far = rng.integers(60_000, 900_000, size=m)
-        newpos = np.minimum(l2.pos.astype(np.int64) + far, ref_len[l2.ref_id] - 200)
-        off, cig = _simple_cigar(m, np.zeros(m), np.full(m, READ_LEN), np.zeros(m))
-        r2 = _table(ref_len, l2.ref_id, newpos, l2.ref_id, l2.pos, r2.flag & ~np.uint16(sqmb.FLAG_PROPER), l2.name_id, off, cig)
-        l2.mate_pos = r2.pos.copy(); l2.flag &= ~np.uint16(sqmb.FLAG_PROPER)
-        x = rng.random(m) < 0.3  # a third of them land on another chromosome
-        if len(ref_len) > 1:
-            oc = (r2.ref_id + 1 + rng.integers(0, len(ref_len) - 1, size=m)) % len(ref_len)
-            r2.ref_id = np.where(x, oc, r2.ref_id).astype(np.int32)
-            r2.pos = np.where(x, np.minimum(r2.pos, ref_len[r2.ref_id] - 200), r2.pos).astype(np.int32)
-            l2.mate_ref_id = r2.ref_id.copy(); l2.mate_pos = r2.pos.copy()
-        parts += [l2, r2]
-
+def make_chimeric(tx: Transcriptome, p: np.ndarray, n_pairs: int, seed: int, disc_frac: float, fusion_support: float = 20.0, adversarial: bool = True):
+    """Chimeric AlnTable: planted fusions (split reads + discordant pairs), uniform noise chimeras and (adversarial)
+    non-discordant chimeric reads that feed PartAlignPos / the 750 kb rule.  Own RNG stream (seed)."""
+    rng = np.random.Generator(np.random.PCG64([seed, 0xC41]))
+    ref_len = tx.ref_len
+    n_genes = tx.g_chr.shape[0]
     # ---- chimeric reads -------------------------------------------------------------------------
     n_chim = int(round(disc_frac * n_pairs))
     n_fus = max(1, int(round(0.9 * n_chim / fusion_support))) if n_chim > 0 else 0
@@ -323,6 +269,70 @@ def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.0
         chim = chim.take(rng.permutation(chim.n))
     else:
         chim = sqmb.empty(ref_len, 0)
+    return chim, fusions
+
+
+def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.005, n_genes: int | None = None,
+              fusion_support: float = 20.0, clip_frac: float = 0.02, adversarial: bool = True, min_block: int = 4):
+    """Returns (concordant AlnTable sorted by coordinate, chimeric AlnTable, info dict)."""
+    ref_len = np.asarray(GRCH38_LEN if ref_len is None else ref_len, dtype=np.int64)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if n_genes is None:
+        n_genes = int(max(8, min(20000, n_pairs // 400)))
+    tx = Transcriptome(rng, ref_len, n_genes)
+    p = tx.g_expr / tx.g_expr.sum()
+    gene = rng.choice(n_genes, size=n_pairs, p=p)
+    left, right = _pairs_from_transcripts(rng, tx, gene, 0, clip_frac, min_block)
+    n = left.n
+    parts = []
+    if adversarial and n >= 50:
+        # per-record decorations exercising the gate / low-phred / poly-A / duplicate rules
+        for t in (left, right):
+            r = rng.random(n)
+            t.lowrun[r < 0.005] = 20
+            r = rng.random(n)
+            mm = r < 0.01
+            t.mapq[mm] = 3; t.aux[mm] |= sqmb.AUX_IH; t.ih[mm] = 2
+            r = rng.random(n)
+            t.aux[r < 0.002] |= sqmb.AUX_XA
+            r = rng.random(n)
+            t.flag[r < 0.002] |= sqmb.FLAG_DUP
+            r = rng.random(n)
+            t.polya[r < 0.002] = 1
+            r = rng.random(n)
+            t.aux[(r < 0.002) & ((t.aux & sqmb.AUX_IH) == 0)] |= sqmb.AUX_IH  # IH:1 is kept
+            t.ih[(t.aux & sqmb.AUX_IH != 0) & (t.ih == 0)] = 1
+        # exact consecutive duplicates (different names)
+        d = np.flatnonzero(rng.random(n) < 0.003)
+        if d.size:
+            dl, dr = left.take(d), right.take(d)
+            dl.name_id = (np.uint64(500_000_000) + np.arange(d.size).astype(np.uint64)); dr.name_id = dl.name_id.copy()
+            parts += [dl, dr]
+        # mate-unmapped singletons
+        s = rng.random(n) < 0.004
+        left.flag[s] = (left.flag[s] | sqmb.FLAG_MATE_UNMAPPED) & ~np.uint16(sqmb.FLAG_PROPER | sqmb.FLAG_MATE_REVERSE)
+        left.mate_pos[s] = left.pos[s]
+        keep_right = ~s
+        right = right.take(np.flatnonzero(keep_right))
+        # long same-chromosome fragments (> -dp) and cross-chromosome pairs living in the concordant file
+        m = max(4, n // 1000)
+        g2 = rng.choice(n_genes, size=m, p=p)
+        l2, r2 = _pairs_from_transcripts(rng, tx, g2, 600_000_000, 0.0, min_block)
+        m = l2.n
+        far = rng.integers(60_000, 900_000, size=m)
+        newpos = np.minimum(l2.pos.astype(np.int64) + far, ref_len[l2.ref_id] - 200)
+        off, cig = _simple_cigar(m, np.zeros(m), np.full(m, READ_LEN), np.zeros(m))
+        r2 = _table(ref_len, l2.ref_id, newpos, l2.ref_id, l2.pos, r2.flag & ~np.uint16(sqmb.FLAG_PROPER), l2.name_id, off, cig)
+        l2.mate_pos = r2.pos.copy(); l2.flag &= ~np.uint16(sqmb.FLAG_PROPER)
+        x = rng.random(m) < 0.3  # a third of them land on another chromosome
+        if len(ref_len) > 1:
+            oc = (r2.ref_id + 1 + rng.integers(0, len(ref_len) - 1, size=m)) % len(ref_len)
+            r2.ref_id = np.where(x, oc, r2.ref_id).astype(np.int32)
+            r2.pos = np.where(x, np.minimum(r2.pos, ref_len[r2.ref_id] - 200), r2.pos).astype(np.int32)
+            l2.mate_ref_id = r2.ref_id.copy(); l2.mate_pos = r2.pos.copy()
+        parts += [l2, r2]
+
+    chim, fusions = make_chimeric(tx, p, n_pairs, seed, disc_frac, fusion_support, adversarial)
     # 1 % of chimeric names also occur in the concordant file (ChimName gate, SegmentGraph.cpp:302);
     # half of those carry a /1,/2 suffix there, which defeats the gate (SURVEY App. A-3)
     if chim.n and adversarial:
