@@ -52,12 +52,13 @@ SQ_HD bool is_concordant_pair(uint16_t f, int32_t rid, int32_t pos, int32_t mrid
 struct ClassifyOut {
     uint8_t cls;
     uint64_t other_key;  // (chr+1)<<32 | end of the CIGAR-first block when the record updates otherrightmost, else 0
+    int32_t first_len;   // length of the first kept block of a CLS_CONC record, else 0
 };
 
 // `prev` = index of the previous gate-passing record, or -1.
 SQ_HD ClassifyOut classify_record(const DevBatch &b, const Params &p, int64_t r, int64_t prev) {
     ClassifyOut o;
-    o.cls = 0; o.other_key = 0;
+    o.cls = 0; o.other_key = 0; o.first_len = 0;
     const uint16_t f = b.flag[r];
     const int32_t rid = b.ref_id[r];
     if (!record_gate(f, b.mapq[r], b.aux[r], rid, p.min_mapq)) return o;
@@ -68,8 +69,10 @@ SQ_HD ClassifyOut classify_record(const DevBatch &b, const Params &p, int64_t r,
     const uint32_t off = b.blk_off[r], nb = b.blk_off[r + 1] - off;
     if (nb == 0) return o;
     o.cls |= CLS_HASBLK;
+    if (b.blk_ref_pos[off] != b.pos[r]) o.cls |= CLS_DISPL;
     if (!is_concordant_pair(f, rid, b.pos[r], b.mate_ref_id[r], b.mate_pos[r])) return o;
     o.cls |= CLS_CONC;
+    o.first_len = b.blk_match_ref[off];
     const bool fm = flag_first(f), sm = flag_second(f);
     if (fm || sm) {
         o.other_key = ((uint64_t)(uint32_t)(rid + 1) << 32) | (uint32_t)(b.blk_ref_pos[off] + b.blk_match_ref[off]);

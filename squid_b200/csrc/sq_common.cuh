@@ -26,6 +26,7 @@ enum : uint8_t {
     CLS_CONC = 4,      // kept, proper FR pair within 750 kb (:651-654) and owns >= 1 block (:655)
     CLS_PART = 8,      // CLS_CONC and partially aligned (:668-683) => PartialAlignCluster, else ConcordantCluster
     CLS_HASBLK = 16,   // kept and owns >= 1 block (feeds ReadsMain, :320-333)
+    CLS_DISPL = 32,    // CLS_HASBLK and the first kept block does not start at the record position (leading block dropped)
 };
 
 // HBM-resident SoA batch (include/squid_b200.h: sqg_batch), device pointers.

@@ -1,4 +1,4 @@
-// Seed-segment state machine of BuildNode_STAR, restated event-driven.
+// Seed-segment state machine of BuildNode_STAR, restated event-driven and island-parallel.
 //
 // The reference (SegmentGraph.cpp:296-701) steps through every concordant alignment and keeps
 // per-record state.  All of that state is either (a) a pure function of the sorted discordant
@@ -10,8 +10,16 @@
 //      (close a pending segment at the first 0-coverage record, clear or trim the cluster windows);
 //   2. run the per-group segmentation rules literally (SegmentGraph.cpp:353-612).
 // ConcordantCluster / PartialAlignCluster are not materialised: they are index windows over the
-// record stream (class bits CLS_CONC / CLS_PART); ConcordRest is a set, queried from a small
-// position-sorted table of candidate blocks.
+// record stream (class bits CLS_CONC / CLS_PART).  Every "count the window entries that span x"
+// loop of the reference is answered from the sorted stream by binary search on position (entries
+// whose first kept block does not start at the record position are rare and kept in a side list).
+// ConcordRest is a set, queried from a small position-sorted table of candidate blocks.
+//
+// ISLANDS.  A 0-coverage record empties both windows and closes the pending segment
+// (:616-636); if it also lies more than ReadLen+70 bp left of the next group (or on another
+// chromosome) nothing of the earlier state can influence that group except (Chr, End) of the last
+// emitted segment, which is then known to be "far left".  Groups between two such cuts form an
+// island; islands run in parallel, each emitting a list of SeedOps that is stitched in order.
 #ifndef SQ_SEED_CUH
 #define SQ_SEED_CUH
 #include "sq_common.cuh"
@@ -28,9 +36,16 @@ struct Group {      // discordant group [ds,de) with its chained right end (:341
 struct SeedNode {
     int32_t chr, pos, len;
 };
+struct SeedOp {    // seed-segment emission of one island
+    int32_t kind;  // 0: push (chr,pos,len)
+                   // 1: the last segment emitted before this island, if on chr, gets End = pos+len; otherwise push (chr,pos,len)
+                   // 2: the current last segment gets End = pos
+    int32_t chr, pos, len;
+};
 struct RestBlock {  // ConcordRest candidate: non-first block of a concordant record, sorted by (chr,pos)
     int32_t chr, pos, end, rec;
 };
+constexpr int32_t kIslandSlack = 70;  // > thresh*20 + 2*thresh, see island_cut()
 
 struct SeedInputs {
     DevBatch b;
@@ -38,30 +53,38 @@ struct SeedInputs {
     const uint64_t *other_excl;     // per record: otherChr/otherrightmost before the record ((chr+1)<<32|pos)
     const int32_t *gap_rec; int32_t n_gap;  // kept records preceded by a concordant-coverage gap, ascending
     const int32_t *pc_rec; int32_t n_pc;    // records with CLS_PART, ascending
+    const int32_t *dp_rec; int32_t n_dp;    // CLS_CONC records whose first kept block does not start at the record position
+    int32_t lmax;                           // max first-block length over CLS_CONC records
+    int64_t n_rec;
     const DiscBlock *D; int32_t nD;
     const Group *G; int32_t nG;
     const int64_t *trigger;         // per group: first kept record past its right end, or n_rec
     const int32_t *Pchr, *Ppos; int32_t nP;  // PartAlignPos sorted
     const RestBlock *rest; int32_t n_rest;
     int32_t read_len;
+    int64_t first_kept;
 };
 
 struct SeedState {
     int64_t offCC;   // record-index cursor of the ConcordantCluster window
     int32_t offPC;   // cursor into pc_rec
     int32_t markedStart, markedChr;
-    bool have_back;  int32_t backChr, backEnd;
+    int32_t backChr, backEnd;
     int32_t n_out;
+    bool have_back;
+    bool back_inherited;  // the last segment belongs to an earlier island (far left of everything here)
 };
 
 struct SeedMachine {
     SeedInputs in;
     SeedState st;
-    SeedNode *out; int32_t out_cap;
+    SeedOp *out; int32_t out_cap;
     int32_t *margin; int32_t margin_cap;
     int32_t error;  // 1: margin overflow, 2: output overflow
 
+    // ---- entry accessors --------------------------------------------------------------------
     SQ_HD bool isCC(int64_t r) const { return (in.cls[r] & (CLS_CONC | CLS_PART)) == CLS_CONC; }
+    SQ_HD bool isDispl(int64_t r) const { return in.cls[r] & CLS_DISPL; }
     SQ_HD int64_t nextCC(int64_t x, int64_t lim) const { while (x < lim && !isCC(x)) x++; return x < lim ? x : lim; }
     SQ_HD int32_t e_chr(int64_t r) const { return in.b.ref_id[r]; }
     SQ_HD int32_t e_pos(int64_t r) const { return in.b.blk_ref_pos[in.b.blk_off[r]]; }
@@ -69,14 +92,45 @@ struct SeedMachine {
     SQ_HD int32_t e_readpos(int64_t r) const { return in.b.blk_read_pos[in.b.blk_off[r]]; }
     SQ_HD bool e_rev(int64_t r) const { return flag_rev(in.b.flag[r]); }
 
-    SQ_HD void push_node(int32_t chr, int32_t pos, int32_t len) {
+    // first record in [lo,hi) with (ref_id,pos) >= (c,x); unmapped records (ref_id -1) sort last
+    SQ_HD int64_t lb_pos(int64_t lo, int64_t hi, int32_t c, int32_t x) const {
+        while (lo < hi) {
+            const int64_t m = lo + ((hi - lo) >> 1);
+            const int32_t rc = in.b.ref_id[m];
+            const bool less = rc >= 0 && (rc < c || (rc == c && in.b.pos[m] < x));
+            if (less) lo = m + 1; else hi = m;
+        }
+        return lo;
+    }
+    SQ_HD int32_t lb_list(const int32_t *a, int32_t n, int64_t v) const {  // first i with a[i] >= v
+        int32_t lo = 0, hi = n;
+        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (a[m] < v) lo = m + 1; else hi = m; }
+        return lo;
+    }
+    // first index i in [lo,hi) of pc_rec whose record has (ref_id,pos) >= (c,x)
+    SQ_HD int32_t lb_pc_pos(int32_t lo, int32_t hi, int32_t c, int32_t x) const {
+        while (lo < hi) {
+            const int32_t m = (lo + hi) >> 1;
+            const int64_t r = in.pc_rec[m];
+            const int32_t rc = in.b.ref_id[r];
+            if (rc < c || (rc == c && in.b.pos[r] < x)) lo = m + 1; else hi = m;
+        }
+        return lo;
+    }
+
+    // ---- output ------------------------------------------------------------------------------
+    SQ_HD void emit(int32_t kind, int32_t chr, int32_t pos, int32_t len) {
         if (st.n_out >= out_cap) { error = 2; return; }
-        out[st.n_out].chr = chr; out[st.n_out].pos = pos; out[st.n_out].len = len;
+        out[st.n_out].kind = kind; out[st.n_out].chr = chr; out[st.n_out].pos = pos; out[st.n_out].len = len;
         st.n_out++;
-        st.have_back = true; st.backChr = chr; st.backEnd = pos + len;
+    }
+    SQ_HD void push_node(int32_t chr, int32_t pos, int32_t len) {
+        emit(0, chr, pos, len);
+        st.have_back = true; st.back_inherited = false; st.backChr = chr; st.backEnd = pos + len;
     }
     SQ_HD void set_back_end(int32_t e) {  // vNodes.back().Length += e - Position - Length
-        out[st.n_out - 1].len += e - st.backEnd;
+        if (st.n_out > 0 && out[st.n_out - 1].kind == 0) out[st.n_out - 1].len += e - st.backEnd;
+        else emit(2, st.backChr, e, 0);
         st.backEnd = e;
     }
     SQ_HD void push_margin(int32_t &n, int32_t v) {
@@ -98,12 +152,13 @@ struct SeedMachine {
         }
     }
 
-    SQ_HD void init() {
+    SQ_HD void init(bool inherited_back) {
         st.offCC = 0; st.offPC = 0; st.markedStart = -1; st.markedChr = -1;
-        st.have_back = false; st.backChr = -1; st.backEnd = 0; st.n_out = 0; error = 0;
+        st.have_back = inherited_back; st.back_inherited = inherited_back;
+        st.backChr = -2; st.backEnd = -(1 << 30); st.n_out = 0; error = 0;
     }
 
-    // (curChr, currightmost) and the 0-coverage test of :616-620 for kept record r while group g is pending
+    // (curChr, currightmost) and the 0-coverage test of :616-620 for kept record r while a group starting at (sChr,sPos) is pending
     SQ_HD bool is0(int64_t r, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, int32_t *curChr, int32_t *curRight) const {
         const uint64_t ok = in.other_excl[r];
         const int32_t oChr = (int32_t)(ok >> 32) - 1, oRight = (int32_t)(uint32_t)ok;
@@ -113,15 +168,63 @@ struct SeedMachine {
         const int32_t rl = in.read_len;
         return (in.b.ref_id[r] != cc || in.b.pos[r] > cr + rl) && (cc < sChr || (cc == sChr && cr + rl < sPos));
     }
+    // last 0-coverage record among the kept records of [r_lo, r_hi); -1 if none
+    SQ_HD int32_t last_is0(int64_t r_lo, int64_t r_hi, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, int32_t *cc, int32_t *cr) const {
+        if (r_hi <= r_lo) return -1;
+        const int32_t a = lb_list(in.gap_rec, in.n_gap, r_lo), bnd = lb_list(in.gap_rec, in.n_gap, r_hi);
+        for (int32_t k = bnd - 1; k >= a; k--) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, cc, cr)) return k;
+        return -1;
+    }
+    // May the machine be restarted at group g (g >= 1)?  Yes when the records between the triggers of g-1 and g
+    // contain a 0-coverage record z (windows emptied, pending segment closed) and every segment emitted so far
+    // ends at most currightmost(z)+3, i.e. more than 60 bp left of the leftmost position group g can look at
+    // (group start - ReadLen, from the PartAlignPos window) -- or lies on another chromosome.
+    SQ_HD bool island_cut(int32_t g) const {
+        const int64_t r_lo = in.trigger[g - 1], r_hi = in.trigger[g];
+        if (r_hi >= in.n_rec || r_hi <= r_lo) return false;
+        const Group gp = in.G[g - 1], gn = in.G[g];
+        int32_t cc, cr;
+        const int32_t z = last_is0(r_lo, r_hi, gp.chr, gp.right, gn.chr, in.D[gn.ds].pos, &cc, &cr);
+        if (z < 0) return false;
+        return cc != gn.chr || (int64_t)in.D[gn.ds].pos - cr > (int64_t)in.read_len + kIslandSlack;
+    }
 
-    // Lazy replay of steps :616-646 for the kept records in [r_lo, r_hi) while group g is pending.
-    // (sChr,sPos) = start of the pending group (or the zero sentinel once all groups are done).
+    // skip-prefix of the :637-646 trims: first entry index >= x (below `lim`) that is not skipped
+    SQ_HD int64_t trim_cc(int64_t x, int64_t lim, int32_t lchr, int32_t sChr) const {
+        if (x >= lim) return lim;
+        if (lchr < sChr) return lim;                     // every visible entry is on a chromosome before the pending group
+        int64_t y = lb_pos(x, lim, lchr, -(1 << 30));    // entries on earlier chromosomes
+        if (st.have_back && st.backChr == lchr) {
+            int64_t j = lb_pos(y, lim, lchr, st.backEnd);  // non-displaced entries left of the last segment's end
+            // a displaced entry (block start != record position) inside [y,j) that is not left of backEnd stops the skip
+            for (int32_t k = lb_list(in.dp_rec, in.n_dp, y); k < in.n_dp && in.dp_rec[k] < j; k++) {
+                const int64_t r = in.dp_rec[k];
+                if (isCC(r) && e_pos(r) >= st.backEnd) { j = r; break; }
+            }
+            // ... and displaced entries at/after j that ARE left of backEnd are skipped too
+            y = j;
+            for (;;) {
+                y = nextCC(y, lim);
+                if (y < lim && e_chr(y) == lchr && e_pos(y) < st.backEnd) { y++; continue; }
+                break;
+            }
+        }
+        return nextCC(y, lim);
+    }
+    SQ_HD int32_t trim_pc(int32_t x, int32_t lim, int32_t lchr, int32_t sChr) const {
+        while (x < lim) {
+            const int64_t r = in.pc_rec[x];
+            const int32_t c = e_chr(r);
+            if (c != lchr || c < sChr || (st.have_back && c == st.backChr && e_pos(r) < st.backEnd)) { x++; continue; }
+            break;
+        }
+        return x;
+    }
+
+    // Lazy replay of steps :616-646 for the kept records in [r_lo, r_hi) while the group starting at (sChr,sPos) is pending.
     SQ_HD void replay_between(int64_t r_lo, int64_t r_hi, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, bool do_trim) {
         if (r_hi <= r_lo) return;
-        // gap records inside [r_lo, r_hi)
-        int32_t a = 0, bnd = in.n_gap;
-        { int32_t lo = 0, hi = in.n_gap; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.gap_rec[m] < r_lo) lo = m + 1; else hi = m; } a = lo; }
-        { int32_t lo = a, hi = in.n_gap; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.gap_rec[m] < r_hi) lo = m + 1; else hi = m; } bnd = lo; }
+        const int32_t a = lb_list(in.gap_rec, in.n_gap, r_lo), bnd = lb_list(in.gap_rec, in.n_gap, r_hi);
         int32_t cc, cr;
         int32_t f = -1, z = -1;
         for (int32_t k = a; k < bnd; k++) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, &cc, &cr)) { f = k; break; }
@@ -137,7 +240,7 @@ struct SeedMachine {
             for (int32_t k = bnd - 1; k >= f; k--) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, &cc, &cr)) { z = k; break; }
             const int64_t zr = in.gap_rec[z];
             st.offCC = zr;  // :633-636 at record z: both windows emptied; z's own block is pushed afterwards
-            { int32_t lo = 0, hi = in.n_pc; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.pc_rec[m] < zr) lo = m + 1; else hi = m; } st.offPC = lo; }
+            st.offPC = lb_list(in.pc_rec, in.n_pc, zr);
             r_lo = zr + 1;
         }
         if (!do_trim) return;
@@ -147,28 +250,51 @@ struct SeedMachine {
         if (last < r_lo) return;
         const int32_t lchr = in.b.ref_id[last];
         // entries visible to that record are those pushed before it, i.e. from records < last
-        int64_t x = st.offCC;
-        for (;;) {
-            x = nextCC(x, last);
-            if (x >= last) { x = last; break; }
-            const int32_t c = e_chr(x);
-            if (c != lchr || c < sChr || (st.have_back && c == st.backChr && e_pos(x) < st.backEnd)) { x++; continue; }
-            break;
-        }
+        const int64_t x = trim_cc(st.offCC, last, lchr, sChr);
         if (x > st.offCC) st.offCC = x;
-        int32_t szp;
-        { int32_t lo = 0, hi = in.n_pc; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.pc_rec[m] < last) lo = m + 1; else hi = m; } szp = lo; }
-        int32_t y = st.offPC;
-        while (y < szp) {
-            const int64_t r = in.pc_rec[y];
-            const int32_t c = e_chr(r);
-            if (c != lchr || c < sChr || (st.have_back && c == st.backChr && e_pos(r) < st.backEnd)) { y++; continue; }
-            break;
-        }
+        const int32_t y = trim_pc(st.offPC, lb_list(in.pc_rec, in.n_pc, last), lchr, sChr);
         if (y > st.offPC) st.offPC = y;
     }
 
-    // ConcordRest coverage at `brk` for group with start sPos on chromosome chrG, records before rg (:471-473)
+    // number of ConcordantCluster + PartialAlignCluster window entries spanning brk +- thresh (:457-469)
+    SQ_HD int32_t window_coverage(int32_t chrG, int32_t brk, int64_t rg, int32_t szPC) const {
+        const int32_t thresh = kSeedThresh;
+        int32_t cov = 0;
+        // an entry spans iff pos < brk-thresh and pos+len >= brk+thresh, hence pos in [brk+thresh-lmax, brk-thresh)
+        const int32_t pmin = brk + thresh - in.lmax, pmax = brk - thresh;
+        if (st.offCC < rg) {
+            const int64_t lo = lb_pos(st.offCC, rg, chrG, pmin), hi = lb_pos(lo, rg, chrG, pmax);
+            for (int64_t r = lo; r < hi; r++)
+                if (isCC(r) && !isDispl(r) && in.b.ref_id[r] == chrG) {
+                    const int32_t p0 = e_pos(r);
+                    if (p0 + e_len(r) >= brk + thresh && p0 < pmax) cov++;
+                }
+        }
+        if (st.offPC < szPC) {
+            const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, pmin), hi = lb_pc_pos(lo, szPC, chrG, pmax);
+            for (int32_t i = lo; i < hi; i++) {
+                const int64_t r = in.pc_rec[i];
+                if (!isDispl(r) && in.b.ref_id[r] == chrG) {
+                    const int32_t p0 = e_pos(r);
+                    if (p0 + e_len(r) >= brk + thresh && p0 < pmax) cov++;
+                }
+            }
+        }
+        // displaced entries of either window
+        const int64_t w0 = st.offCC < rg ? st.offCC : rg;
+        const int64_t wp = st.offPC < szPC ? (int64_t)in.pc_rec[st.offPC] : rg;
+        for (int32_t k = lb_list(in.dp_rec, in.n_dp, w0 < wp ? w0 : wp); k < in.n_dp && in.dp_rec[k] < rg; k++) {
+            const int64_t r = in.dp_rec[k];
+            if (in.b.ref_id[r] != chrG) continue;
+            const bool part = in.cls[r] & CLS_PART;
+            if (part ? (r < wp) : (r < st.offCC)) continue;
+            const int32_t p0 = e_pos(r);
+            if (p0 + e_len(r) >= brk + thresh && p0 < pmax) cov++;
+        }
+        return cov;
+    }
+
+    // ConcordRest coverage at `brk` for the group starting at sPos on chromosome chrG, records before rg (:471-473)
     SQ_HD int32_t rest_coverage(int32_t chrG, int32_t sPos, int32_t brk, int64_t rg) const {
         const int32_t lo_pos = sPos - in.read_len;
         int32_t lo = 0, hi = in.n_rest;
@@ -182,6 +308,20 @@ struct SeedMachine {
         return cnt;
     }
 
+    SQ_HD void pc_margin(int64_t r, int32_t chrG, int32_t m0, int32_t curEndPos, int32_t &nM) {  // :420-434 for one entry
+        const int32_t thresh = kSeedThresh;
+        if (e_chr(r) != chrG) return;
+        const int32_t p0 = e_pos(r), p1 = p0 + e_len(r);
+        const bool rv = e_rev(r);
+        if (e_readpos(r) > 15 && p0 > m0 - thresh && p0 < curEndPos + thresh) {
+            if (rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
+            else if (!rv) push_margin(nM, p0);
+        } else {
+            if (rv && p0 > m0 - thresh && p0 < curEndPos + thresh) push_margin(nM, p0);
+            else if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
+        }
+    }
+
     // Lines :353-612 for group g, reached at trigger record rg.
     SQ_HD void process_group(int32_t g, int64_t rg) {
         const int32_t thresh = kSeedThresh, RL = in.read_len;
@@ -192,13 +332,10 @@ struct SeedMachine {
         int32_t curEndPos = 0, curStartPos = 0, disStartPos = -1, disEndPos = -1, disCount = -1;
         bool isClusternSplit = false;
         if (st.markedStart != -1 && chrG != st.markedChr) { st.markedChr = -1; st.markedStart = -1; }
-        int32_t szPC;
-        { int32_t lo = 0, hi = in.n_pc; while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.pc_rec[m] < rg) lo = m + 1; else hi = m; } szPC = lo; }
+        const int32_t szPC = lb_list(in.pc_rec, in.n_pc, rg);
         // :365-368 skip cluster entries of earlier chromosomes
         {
-            int64_t lo = 0, hi = rg;
-            while (lo < hi) { int64_t m = (lo + hi) >> 1; if (in.b.ref_id[m] < chrG) lo = m + 1; else hi = m; }
-            // NB records with ref_id -1 are never cluster entries; the stream is sorted so this is a plain lower bound
+            const int64_t lo = lb_pos(0, rg, chrG, -(1 << 30));
             if (lo > st.offCC) st.offCC = lo;
             st.offCC = nextCC(st.offCC, rg);
             while (st.offPC < szPC && e_chr(in.pc_rec[st.offPC]) < chrG) st.offPC++;
@@ -253,18 +390,12 @@ struct SeedMachine {
                 for (dc++; dc != de && D[dc].pos < curEndPos + thresh; dc++) { push_margin(nM, D[dc].pos); push_margin(nM, D[dc].pos + D[dc].len); }
             for (int32_t pc = ps; pc != pe && in.Ppos[pc] < curEndPos + thresh; pc++) push_margin(nM, in.Ppos[pc]);
             const int32_t m0 = D[ds].pos;  // MarginPositions.front() while still unsorted
-            for (int32_t i = st.offPC; i < szPC; i++) {  // :420-434
-                const int64_t r = in.pc_rec[i];
-                if (e_chr(r) != chrG) continue;
-                const int32_t p0 = e_pos(r), p1 = p0 + e_len(r);
-                const bool rv = e_rev(r);
-                if (e_readpos(r) > 15 && p0 > m0 - thresh && p0 < curEndPos + thresh) {
-                    if (rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
-                    else if (!rv) push_margin(nM, p0);
-                } else {
-                    if (rv && p0 > m0 - thresh && p0 < curEndPos + thresh) push_margin(nM, p0);
-                    else if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
-                }
+            if (st.offPC < szPC) {  // :420-434; an entry contributes only if its block start lies in (m0-thresh-lmax, curEndPos+thresh)
+                const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, m0 - thresh - in.lmax), hi = lb_pc_pos(lo, szPC, chrG, curEndPos + thresh);
+                for (int32_t i = lo; i < hi; i++) if (!isDispl(in.pc_rec[i])) pc_margin(in.pc_rec[i], chrG, m0, curEndPos, nM);
+                const int64_t wp = in.pc_rec[st.offPC];
+                for (int32_t k = lb_list(in.dp_rec, in.n_dp, wp); k < in.n_dp && in.dp_rec[k] < rg; k++)
+                    if (in.cls[in.dp_rec[k]] & CLS_PART) pc_margin(in.dp_rec[k], chrG, m0, curEndPos, nM);
             }
             if (error) return;
             sort_margins(nM);
@@ -273,9 +404,10 @@ struct SeedMachine {
                 const int32_t brk = margin[ib];
                 if (st.have_back && st.backChr == chrG && brk - st.backEnd < thresh * 20) { ib++; continue; }
                 int32_t sr = 0, pl = 0, pr = 0;
-                for (int32_t k = 0; k < nM && margin[k] < brk + thresh; k++) {
-                    const int32_t d = brk - margin[k];
-                    if ((d < 0 ? -d : d) < thresh) sr++;
+                {   // margins within +-thresh of brk (the array is sorted)
+                    int32_t k = ib;
+                    while (k > 0 && brk - margin[k - 1] < thresh) k--;
+                    for (; k < nM && margin[k] < brk + thresh; k++) sr++;
                 }
                 for (int32_t k = ds; k != de; k++) {
                     const int32_t e1 = D[k].pos + D[k].len;
@@ -283,20 +415,9 @@ struct SeedMachine {
                     else if (D[k].pos > brk && D[k].pos < brk + RL && D[k].rev) pr++;
                 }
                 if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
-                    int32_t coverage = 0;
-                    for (int64_t r = st.offCC; r < rg; r++) {
-                        if (!isCC(r) || e_chr(r) != chrG) continue;
-                        const int32_t p0 = e_pos(r);
-                        if (p0 + e_len(r) >= brk + thresh && p0 < brk - thresh) coverage++;
-                    }
+                    int32_t coverage = window_coverage(chrG, brk, rg, szPC);
                     for (int32_t k = ds; k != de; k++)
                         if (D[k].chr == chrG && D[k].pos + D[k].len >= brk + thresh && D[k].pos < brk - thresh) coverage++;
-                    for (int32_t i = st.offPC; i < szPC; i++) {
-                        const int64_t r = in.pc_rec[i];
-                        if (e_chr(r) != chrG) continue;
-                        const int32_t p0 = e_pos(r);
-                        if (p0 + e_len(r) >= brk + thresh && p0 < brk - thresh) coverage++;
-                    }
                     int32_t rest = coverage - sr; if (rest < 0) rest = 0;
                     if (sr > rest + 2) {
                         coverage += rest_coverage(chrG, in.D[grp.ds].pos, brk, rg);
@@ -378,7 +499,17 @@ struct SeedMachine {
                 if (st.markedStart != -1 && (recChr > st.markedChr || recPos > concord0pos + RL) &&
                     (ccEmpty || e_chr(st.offCC) != st.markedChr || e_pos(st.offCC) > concord0pos + RL) &&
                     (pcEmpty || e_chr(in.pc_rec[st.offPC]) != st.markedChr || e_pos(in.pc_rec[st.offPC]) > concord0pos)) {
-                    if (concord0pos > st.markedStart && concord0pos < st.markedStart + thresh * 20 && st.have_back && st.backChr == st.markedChr)
+                    if (st.back_inherited) {
+                        // the last segment was emitted by an earlier island: whether it is on markedChr (extend it) or
+                        // not (push a new one) is decided when the islands are stitched; both leave (markedChr, concord0pos)
+                        if (concord0pos > st.markedStart) {
+                            emit(1, st.markedChr, st.markedStart, concord0pos - st.markedStart);
+                            // kind 1 carries "extend only if < thresh*20" in the sign of len? no: the extend branch also needs
+                            // concord0pos < markedStart + thresh*20; encode it by kind: 1 = may extend, else plain push
+                            if (!(concord0pos < st.markedStart + thresh * 20)) out[st.n_out - 1].kind = 0;
+                            st.have_back = true; st.back_inherited = false; st.backChr = st.markedChr; st.backEnd = concord0pos;
+                        }
+                    } else if (concord0pos > st.markedStart && concord0pos < st.markedStart + thresh * 20 && st.have_back && st.backChr == st.markedChr)
                         set_back_end(concord0pos);
                     else if (concord0pos > st.markedStart)
                         push_node(st.markedChr, st.markedStart, concord0pos - st.markedStart);
@@ -406,32 +537,49 @@ struct SeedMachine {
         }
     }
 
-    // Whole stream, one island: every group in order.  Returns the index of the first group that was
-    // never reached by the stream (== nG when all were processed).
-    SQ_HD int32_t run_all(int64_t first_kept, int64_t n_rec) {
-        init();
+    // One island: groups [ga, gb).  `inherited_back`: some earlier island has emitted a segment.
+    // Returns the first group that was NOT processed (gb, or earlier if the stream ended first).
+    SQ_HD int32_t run_island(int32_t ga, int32_t gb, bool inherited_back) {
+        init(inherited_back);
         int32_t dChr = 0, dRight = 0;
-        int64_t r_prev = first_kept;
-        int32_t g = 0;
-        for (; g < in.nG; g++) {
+        int64_t r_prev = in.first_kept;
+        if (ga > 0) { dChr = in.G[ga - 1].chr; dRight = in.G[ga - 1].right; r_prev = in.trigger[ga - 1]; }
+        int32_t g = ga;
+        for (; g < gb; g++) {
             const int64_t rg = in.trigger[g];
             const Group grp = in.G[g];
-            if (rg >= n_rec) break;
+            if (rg >= in.n_rec) break;
             replay_between(r_prev, rg, dChr, dRight, grp.chr, in.D[grp.ds].pos, true);
             process_group(g, rg);
             if (error) return g;
             dChr = grp.chr; dRight = grp.right;
             r_prev = rg;
         }
-        if (g < in.nG) {  // the stream ended before group g: only the pending-segment close-out can still fire
+        // tail: a pending segment is closed by the first 0-coverage record that follows, while the next group
+        // (or, once the stream ends before it, still that group) is pending
+        if (g < in.nG) {
             const Group grp = in.G[g];
-            replay_between(r_prev, n_rec, dChr, dRight, grp.chr, in.D[grp.ds].pos, false);
+            const int64_t r_hi = in.trigger[g] < in.n_rec ? in.trigger[g] : in.n_rec;
+            replay_between(r_prev, r_hi, dChr, dRight, grp.chr, in.D[grp.ds].pos, false);
         }
-        // after the last group the reference compares against the element one past the end of
-        // bamdiscordant (zero sentinel): the 0-coverage test can never hold there, nothing to do.
+        // after the very last group the reference compares against the element one past the end of bamdiscordant
+        // (zero sentinel): the 0-coverage test can never hold there, nothing to do.
         return g;
     }
 };
+
+// Stitch island op lists (in island order) into the seed-segment list.  Host side (sizes are tiny).
+template <class Vec>
+inline void stitch_ops(const SeedOp *ops, int32_t n_ops, Vec &seeds) {
+    for (int32_t i = 0; i < n_ops; i++) {
+        const SeedOp &o = ops[i];
+        if (o.kind == 0) seeds.push_back(SeedNode{o.chr, o.pos, o.len});
+        else if (o.kind == 1) {
+            if (!seeds.empty() && seeds.back().chr == o.chr) seeds.back().len = o.pos + o.len - seeds.back().pos;
+            else seeds.push_back(SeedNode{o.chr, o.pos, o.len});
+        } else if (!seeds.empty()) seeds.back().len = o.pos - seeds.back().pos;
+    }
+}
 
 }  // namespace sq
 #endif

@@ -87,13 +87,18 @@ __global__ void k_validate(DevBatch b, int32_t n_ref, int32_t *flags) {
     if (bad) atomicOr(flags, bad);
 }
 
-__global__ void k_classify(DevBatch b, Params p, const int32_t *lastpass, uint8_t *cls, uint64_t *other_key) {
+__global__ void k_classify(DevBatch b, Params p, const int32_t *lastpass, uint8_t *cls, uint64_t *other_key, int32_t *lmax) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= b.n_rec) return;
-    const int64_t prev = r > 0 ? lastpass[r - 1] : -1;
-    const ClassifyOut o = classify_record(b, p, r, prev);
-    cls[r] = o.cls;
-    other_key[r] = o.other_key;
+    int32_t fl = 0;
+    if (r < b.n_rec) {
+        const int64_t prev = r > 0 ? lastpass[r - 1] : -1;
+        const ClassifyOut o = classify_record(b, p, r, prev);
+        cls[r] = o.cls;
+        other_key[r] = o.other_key;
+        fl = o.first_len;
+    }
+    fl = __reduce_max_sync(0xffffffffu, fl);
+    if ((threadIdx.x & 31) == 0 && fl > 0) atomicMax(lmax, fl);
 }
 
 struct IsGapOp {
@@ -108,6 +113,10 @@ struct IsGapOp {
 struct IsPartOp {
     const uint8_t *cls;
     __device__ bool operator()(int32_t r) const { return cls[r] & CLS_PART; }
+};
+struct IsDisplOp {
+    const uint8_t *cls;
+    __device__ bool operator()(int32_t r) const { return (cls[r] & (CLS_CONC | CLS_DISPL)) == (CLS_CONC | CLS_DISPL); }
 };
 struct FirstKeptOp {
     const uint8_t *cls; int64_t n;
@@ -163,15 +172,80 @@ __global__ void k_rest_collect(DevBatch b, const uint8_t *cls, const Group *G, c
     }
 }
 
-__global__ void k_seed_single(SeedInputs in, SeedNode *out, int32_t out_cap, int32_t *margin, int32_t margin_cap,
-                              int64_t first_kept, int64_t n_rec, SeedState *st_out, int32_t *g_done, int32_t *err) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// island cut flags: flag[g] = 1 when the seed machine may be restarted at group g
+__global__ void k_island_cuts(SeedInputs in, uint8_t *flag) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= in.nG) return;
     SeedMachine sm;
-    sm.in = in; sm.out = out; sm.out_cap = out_cap; sm.margin = margin; sm.margin_cap = margin_cap;
-    const int32_t g = sm.run_all(first_kept, n_rec);
-    *st_out = sm.st;
-    *g_done = g;
-    *err = sm.error;
+    sm.in = in;
+    flag[g] = (g == 0) ? 1 : (sm.island_cut(g) ? 1 : 0);
+}
+struct IsCutOp {
+    const uint8_t *flag;
+    __device__ bool operator()(int32_t g) const { return flag[g] != 0; }
+};
+// scratch each island needs: [2i] = op slots, [2i+1] = margin slots
+__global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n_isl, int32_t *cap_ops, int32_t *cap_mar) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_isl) return;
+    SeedMachine sm;
+    sm.in = in;
+    const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
+    const int32_t thresh = kSeedThresh, RL = in.read_len;
+    int32_t mmax = 0;
+    for (int32_t g = ga; g < gb; g++) {
+        const Group grp = in.G[g];
+        const int32_t s0 = in.D[grp.ds].pos;
+        int32_t m = 2 * (grp.de - grp.ds);
+        {   // PartAlignPos entries of the group (:392-393)
+            int32_t lo = 0, hi = in.nP;
+            while (lo < hi) { int32_t q = (lo + hi) >> 1; if (in.Pchr[q] < grp.chr || (in.Pchr[q] == grp.chr && in.Ppos[q] < s0 - RL)) lo = q + 1; else hi = q; }
+            int32_t lo2 = lo, hi2 = in.nP;
+            while (lo2 < hi2) { int32_t q = (lo2 + hi2) >> 1; if (in.Pchr[q] < grp.chr || (in.Pchr[q] == grp.chr && in.Ppos[q] < grp.right + RL)) lo2 = q + 1; else hi2 = q; }
+            m += lo2 - lo;
+        }
+        {   // PartialAlignCluster entries whose block start can land in the margin range (:420-434)
+            const int32_t lo = sm.lb_pc_pos(0, in.n_pc, grp.chr, s0 - thresh - in.lmax), hi = sm.lb_pc_pos(lo, in.n_pc, grp.chr, grp.right + thresh);
+            m += hi - lo;
+        }
+        if (m > mmax) mmax = m;
+    }
+    const int64_t r0 = ga > 0 ? in.trigger[ga - 1] : in.first_kept;
+    const int64_t r1 = in.trigger[gb - 1] < in.n_rec ? in.trigger[gb - 1] : in.n_rec;
+    const int32_t ndp = sm.lb_list(in.dp_rec, in.n_dp, r1) - sm.lb_list(in.dp_rec, in.n_dp, r0);
+    mmax += (ndp > 0 ? ndp : 0) + 16;
+    cap_ops[i] = 4 * (in.G[gb - 1].de - in.G[ga].ds) + 2 * mmax + 64;
+    cap_mar[i] = mmax;
+}
+// islands [i0, n_isl): one thread each.  i0 > 0 islands start with an inherited (far-left) last segment.
+// mode 0: sequential prefix, islands from 0 until one has emitted a segment (writes *n_prefix);  mode 1: islands >= *n_prefix in parallel
+__global__ void k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar, SeedOp *ops, int32_t *margin,
+                               int32_t *n_out, int32_t *g_done, int32_t *err, int32_t *n_prefix, int mode) {
+    SeedMachine sm;
+    sm.in = in;
+    if (mode == 0) {
+        if (blockIdx.x != 0 || threadIdx.x != 0) return;
+        int32_t i = 0;
+        for (; i < n_isl; i++) {
+            const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
+            sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
+            sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
+            g_done[i] = sm.run_island(ga, gb, false);
+            n_out[i] = sm.st.n_out;
+            if (sm.error) atomicMax(err, sm.error);
+            if (sm.st.n_out > 0) { i++; break; }
+        }
+        *n_prefix = i;
+        return;
+    }
+    const int32_t i = *n_prefix + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_isl) return;
+    const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
+    sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
+    sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
+    g_done[i] = sm.run_island(ga, gb, true);
+    n_out[i] = sm.st.n_out;
+    if (sm.error) atomicMax(err, sm.error);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -447,7 +521,9 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->dc_first_total.release(); ctx->dc_second_total.release(); ctx->dc_ref_id.release(); ctx->dc_ref_pos.release(); ctx->dc_read_pos.release();
     ctx->dc_match_ref.release(); ctx->dc_match_read.release(); ctx->dc_res0.release(); ctx->dc_rev.release();
     ctx->d_trigger.release(); ctx->d_rest.release(); ctx->d_rest2.release(); ctx->d_restkey.release(); ctx->d_restkey2.release();
-    ctx->d_seeds.release(); ctx->d_margin.release(); ctx->d_seedstate.release();
+    ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
+    ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
+    ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
@@ -567,9 +643,9 @@ static int run_classify(sqg_ctx *ctx) {
     const int64_t n = b.n_rec;
     PHASE_BEGIN("classify");
     CK(ctx->d_cls.ensure(n + 1)); CK(ctx->d_other.ensure(n + 1)); CK(ctx->d_scratch32.ensure(n + 1));
-    CK(ctx->d_gap.ensure(n + 1)); CK(ctx->d_pc.ensure(n + 1));
+    CK(ctx->d_gap.ensure(n + 1)); CK(ctx->d_pc.ensure(n + 1)); CK(ctx->d_dp.ensure(n + 1));
     CK(ctx->d_counters.ensure(16)); CK(ctx->h_counters.ensure(16));
-    ctx->n_gap = 0; ctx->n_pc = 0; ctx->first_kept = n;
+    ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n;
     if (n > 0) {
         cub::CountingInputIterator<int32_t> cnt(0);
         size_t tb = 0;
@@ -580,7 +656,8 @@ static int run_classify(sqg_ctx *ctx) {
             CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, it, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
             ctx->launches += 2;
         }
-        LAUNCH(k_classify, blocks_for(n), kThreads, b, ctx->params, ctx->d_scratch32.p, ctx->d_cls.p, ctx->d_other.p);
+        CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(int64_t), ctx->stream));
+        LAUNCH(k_classify, blocks_for(n), kThreads, b, ctx->params, ctx->d_scratch32.p, ctx->d_cls.p, ctx->d_other.p, (int32_t *)(ctx->d_counters.p + 3));
         {   // otherChr/otherrightmost before each record
             CK(cub::DeviceScan::ExclusiveScan(nullptr, tb, ctx->d_other.p, ctx->d_other.p, MaxU64(), (uint64_t)(1ull << 32), (int)n, ctx->stream));
             ENSURE_TEMP(tb);
@@ -597,6 +674,10 @@ static int run_classify(sqg_ctx *ctx) {
             CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_pc.p, d_nsel + 1, (int)n, op2, ctx->stream));
             ENSURE_TEMP(tb);
             CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_pc.p, d_nsel + 1, (int)n, op2, ctx->stream));
+            IsDisplOp op3{ctx->d_cls.p};
+            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_dp.p, d_nsel + 2, (int)n, op3, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_dp.p, d_nsel + 2, (int)n, op3, ctx->stream));
             cub::TransformInputIterator<int64_t, FirstKeptOp, cub::CountingInputIterator<int32_t>> fk(cnt, FirstKeptOp{ctx->d_cls.p, n});
             CK(cub::DeviceReduce::Reduce(nullptr, tb, fk, ctx->d_counters.p + 2, (int)n, MinI64(), (int64_t)n, ctx->stream));
             ENSURE_TEMP(tb);
@@ -609,7 +690,8 @@ static int run_classify(sqg_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (n > 0) {
         const int32_t *sel = (const int32_t *)ctx->h_counters.p;
-        ctx->n_gap = sel[0]; ctx->n_pc = sel[1]; ctx->first_kept = ctx->h_counters.p[2];
+        ctx->n_gap = sel[0]; ctx->n_pc = sel[1]; ctx->n_dp = sel[2]; ctx->first_kept = ctx->h_counters.p[2];
+        ctx->lmax = *(const int32_t *)(ctx->h_counters.p + 3);
     }
     ctx->classified = true;
     return SQG_OK;
@@ -650,11 +732,9 @@ extern "C" int sqg_set_nodes(sqg_ctx *ctx, const int32_t *chr, const int32_t *po
 }
 
 // seeds (device) -> normalised, genome-tiling segment table (SegmentGraph.cpp:19-38, 706-761)
-static int tile_genome(sqg_ctx *ctx, int32_t n_seeds) {
-    CK(ctx->h_seeds.ensure(n_seeds + 1));
-    if (n_seeds) CK(cudaMemcpyAsync(ctx->h_seeds.p, ctx->d_seeds.p, n_seeds * sizeof(SeedNode), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    SeedNode *s = ctx->h_seeds.p;
+static int tile_genome(sqg_ctx *ctx, std::vector<SeedNode> &seedv) {
+    const int32_t n_seeds = (int32_t)seedv.size();
+    SeedNode *s = seedv.data();
     std::sort(s, s + n_seeds, [](const SeedNode &a, const SeedNode &c) { return a.chr != c.chr ? a.chr < c.chr : (a.pos != c.pos ? a.pos < c.pos : a.len < c.len); });
     std::vector<SeedNode> norm;
     norm.reserve(n_seeds);
@@ -717,31 +797,80 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
         CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp.p, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, 64, ctx->stream));
         ctx->launches += 4;
     }
-    // the state machine
-    const int32_t out_cap = 4 * nD + 16;
-    const int32_t margin_cap = 4 * nD + 2 * nP + 2 * ctx->n_pc + 64;
-    CK(ctx->d_seeds.ensure(out_cap)); CK(ctx->d_margin.ensure(margin_cap)); CK(ctx->d_seedstate.ensure(1));
+    // the state machine, island-parallel
     SeedInputs in;
     in.b = b; in.cls = ctx->d_cls.p; in.other_excl = ctx->d_other.p;
     in.gap_rec = ctx->d_gap.p; in.n_gap = ctx->n_gap; in.pc_rec = ctx->d_pc.p; in.n_pc = ctx->n_pc;
+    in.dp_rec = ctx->d_dp.p; in.n_dp = ctx->n_dp; in.lmax = ctx->lmax; in.n_rec = n;
     in.D = ctx->d_disc.p; in.nD = nD; in.G = ctx->d_groups.p; in.nG = nG; in.trigger = ctx->d_trigger.p;
     in.Pchr = ctx->d_pchr.p; in.Ppos = ctx->d_ppos.p; in.nP = nP;
-    in.rest = ctx->d_rest2.p; in.n_rest = (int32_t)n_rest; in.read_len = ctx->params.read_len;
-    int32_t *d_gdone = (int32_t *)(ctx->d_counters.p + 6), *d_err = (int32_t *)(ctx->d_counters.p + 7);
-    LAUNCH(k_seed_single, 1, 1, in, ctx->d_seeds.p, out_cap, ctx->d_margin.p, margin_cap, ctx->first_kept, n, ctx->d_seedstate.p, d_gdone, d_err);
+    in.rest = ctx->d_rest2.p; in.n_rest = (int32_t)n_rest; in.read_len = ctx->params.read_len; in.first_kept = ctx->first_kept;
+    CK(ctx->d_cutflag.ensure(nG + 1)); CK(ctx->d_isl.ensure(nG + 2));
+    LAUNCH(k_island_cuts, blocks_for(nG, 64), 64, in, ctx->d_cutflag.p);
+    {
+        cub::CountingInputIterator<int32_t> cnt(0);
+        IsCutOp op{ctx->d_cutflag.p};
+        size_t tb = 0;
+        CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG, op, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG, op, ctx->stream));
+        ctx->launches += 2;
+    }
+    CK(cudaMemcpyAsync(ctx->h_counters.p + 5, ctx->d_counters.p + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int32_t n_isl = *(int32_t *)(ctx->h_counters.p + 5);
+    CK(ctx->d_cap_ops.ensure(n_isl + 2)); CK(ctx->d_cap_mar.ensure(n_isl + 2)); CK(ctx->d_off_ops.ensure(n_isl + 2)); CK(ctx->d_off_mar.ensure(n_isl + 2));
+    CK(ctx->d_isl_nout.ensure(n_isl + 1)); CK(ctx->d_isl_gdone.ensure(n_isl + 1));
+    CK(cudaMemsetAsync(ctx->d_cap_ops.p, 0, (n_isl + 2) * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->d_cap_mar.p, 0, (n_isl + 2) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_isl_nout.p, 0, (n_isl + 1) * 4, ctx->stream));
+    LAUNCH(k_island_caps, blocks_for(n_isl, 64), 64, in, ctx->d_isl.p, n_isl, ctx->d_cap_ops.p, ctx->d_cap_mar.p);
+    {
+        size_t tb = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_cap_ops.p, ctx->d_off_ops.p, n_isl + 1, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_temp.p, tb, ctx->d_cap_ops.p, ctx->d_off_ops.p, n_isl + 1, ctx->stream));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_temp.p, tb, ctx->d_cap_mar.p, ctx->d_off_mar.p, n_isl + 1, ctx->stream));
+        ctx->launches += 4;
+    }
+    int64_t tot[2];
+    CK(cudaMemcpyAsync(&tot[0], ctx->d_off_ops.p + n_isl, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&tot[1], ctx->d_off_mar.p + n_isl, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->d_ops.ensure(tot[0] + 1)); CK(ctx->d_margin.ensure(tot[1] + 1));
+    int32_t *d_err = (int32_t *)(ctx->d_counters.p + 7), *d_nprefix = (int32_t *)(ctx->d_counters.p + 6);
+    CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, 2 * sizeof(int64_t), ctx->stream));
+    LAUNCH(k_seed_islands, 1, 1, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
+           ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, d_nprefix, 0);
+    LAUNCH(k_seed_islands, blocks_for(n_isl, 32), 32, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
+           ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, d_nprefix, 1);
     PHASE_END("seed");
-    SeedState st;
-    CK(cudaMemcpyAsync(&st, ctx->d_seedstate.p, sizeof(SeedState), cudaMemcpyDeviceToHost, ctx->stream));
+    // stitch the island op lists in genome order (host: a few hundred thousand ops at most)
+    std::vector<int32_t> h_nout(n_isl), h_gdone(n_isl), h_isl(n_isl + 1);
+    std::vector<int64_t> h_off(n_isl + 1);
+    CK(cudaMemcpyAsync(h_nout.data(), ctx->d_isl_nout.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_gdone.data(), ctx->d_isl_gdone.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_isl.data(), ctx->d_isl.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_off.data(), ctx->d_off_ops.p, (n_isl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters.p + 6, ctx->d_counters.p + 6, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<int64_t> trig_last(1, n);
     if (nG > 0) CK(cudaMemcpyAsync(trig_last.data(), ctx->d_trigger.p + (nG - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx->h_ops.ensure(tot[0] + 1));
+    if (tot[0] > 0) CK(cudaMemcpyAsync(ctx->h_ops.p, ctx->d_ops.p, tot[0] * sizeof(SeedOp), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    const int32_t g_done = *(int32_t *)(ctx->h_counters.p + 6), serr = *(int32_t *)(ctx->h_counters.p + 7);
+    const int32_t serr = *(int32_t *)(ctx->h_counters.p + 7);
     if (serr) FAIL(SQG_ENOMEM, serr == 1 ? "seed machine: margin scratch overflow" : "seed machine: output overflow");
-    if (st.n_out == 0) FAIL(SQG_EUNSUPPORTED, "no seed segment was produced: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
+    h_isl[n_isl] = nG;
+    std::vector<SeedNode> seeds;
+    int32_t g_done = nG;
+    for (int32_t i = 0; i < n_isl; i++) {
+        stitch_ops(ctx->h_ops.p + h_off[i], h_nout[i], seeds);
+        if (h_gdone[i] < h_isl[i + 1]) { g_done = h_gdone[i]; break; }  // the stream ended before this group: nothing later is ever processed
+    }
+    if (seeds.empty()) FAIL(SQG_EUNSUPPORTED, "no seed segment was produced: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
+    ctx->n_islands = n_isl;
 
     PHASE_BEGIN("tile");
-    rc = tile_genome(ctx, st.n_out);
+    rc = tile_genome(ctx, seeds);
     if (rc) return rc;
     PHASE_END("tile");
 

@@ -73,8 +73,8 @@ struct sqg_ctx {
     sq::DBuf<uint8_t> d_cls;
     sq::DBuf<uint64_t> d_other;     // other_key, then its exclusive max-scan
     sq::DBuf<int32_t> d_scratch32;  // lastpass / depth targets / res0
-    sq::DBuf<int32_t> d_gap, d_pc;
-    int32_t n_gap = 0, n_pc = 0;
+    sq::DBuf<int32_t> d_gap, d_pc, d_dp;
+    int32_t n_gap = 0, n_pc = 0, n_dp = 0, lmax = 0, n_islands = 0;
     int64_t first_kept = 0;
     sq::DBuf<unsigned char> d_temp;  // CUB temp storage
     sq::DBuf<int64_t> d_counters;    // small device counters
@@ -99,7 +99,11 @@ struct sqg_ctx {
     sq::DBuf<int64_t> d_trigger;
     sq::DBuf<sq::RestBlock> d_rest, d_rest2;
     sq::DBuf<uint64_t> d_restkey, d_restkey2;
-    sq::DBuf<sq::SeedNode> d_seeds;
+    sq::DBuf<sq::SeedOp> d_ops;
+    sq::HBuf<sq::SeedOp> h_ops;
+    sq::DBuf<uint8_t> d_cutflag;
+    sq::DBuf<int32_t> d_isl, d_cap_ops, d_cap_mar, d_isl_nout, d_isl_gdone;
+    sq::DBuf<int64_t> d_off_ops, d_off_mar;
     sq::DBuf<int32_t> d_margin;
     sq::DBuf<sq::SeedState> d_seedstate;
     int64_t r_break = 0;

@@ -81,7 +81,8 @@ int main(int argc, char **argv) {
             if (o.cls & CLS_GATE) prev = r;
         }
     }
-    std::vector<int32_t> gap, pcrec;
+    std::vector<int32_t> gap, pcrec, dprec;
+    int32_t lmax = 0;
     int64_t first_kept = n;
     for (int64_t r = 0; r < n; r++) {
         if (!(cls[r] & CLS_KEEP)) continue;
@@ -89,6 +90,8 @@ int main(int argc, char **argv) {
         const int32_t oc = (int32_t)(other_excl[r] >> 32) - 1, orr = (int32_t)(uint32_t)other_excl[r];
         if (b.ref_id[r] != oc || b.pos[r] > orr + p.read_len) gap.push_back((int32_t)r);
         if (cls[r] & CLS_PART) pcrec.push_back((int32_t)r);
+        if ((cls[r] & CLS_CONC) && (cls[r] & CLS_DISPL)) dprec.push_back((int32_t)r);
+        if (cls[r] & CLS_CONC) lmax = std::max(lmax, b.blk_match_ref[b.blk_off[r]]);
     }
     const int32_t nD = (int32_t)pre.disc.size() - 1, nG = (int32_t)pre.groups.size();
     std::vector<int64_t> trig(nG);
@@ -127,12 +130,36 @@ int main(int argc, char **argv) {
     sm.in.Pchr = pre.part_chr.data(); sm.in.Ppos = pre.part_pos.data(); sm.in.nP = (int32_t)pre.part_chr.size();
     sm.in.rest = rest.data(); sm.in.n_rest = (int32_t)rest.size();
     sm.in.read_len = p.read_len;
-    std::vector<SeedNode> seeds(4 * (size_t)nD + 16);
+    sm.in.dp_rec = dprec.data(); sm.in.n_dp = (int32_t)dprec.size(); sm.in.lmax = lmax; sm.in.n_rec = n; sm.in.first_kept = first_kept;
     std::vector<int32_t> margin(4 * (size_t)nD + 2 * pre.part_chr.size() + 2 * pcrec.size() + 64);
-    sm.out = seeds.data(); sm.out_cap = (int32_t)seeds.size(); sm.margin = margin.data(); sm.margin_cap = (int32_t)margin.size();
-    const int32_t g_done = sm.run_all(first_kept, n);
-    if (sm.error) { fprintf(stderr, "seed machine error %d\n", sm.error); return 3; }
-    seeds.resize(sm.st.n_out);
+    sm.margin = margin.data(); sm.margin_cap = (int32_t)margin.size();
+    // islands: cut before group g when the machine provably restarts there
+    std::vector<int32_t> isl_start(1, 0);
+    const bool one_island = getenv("SQ_EMUL_ONE_ISLAND") != nullptr;
+    for (int32_t g = 1; g < nG && !one_island; g++) if (sm.island_cut(g)) isl_start.push_back(g);
+    const int32_t nI = (int32_t)isl_start.size();
+    isl_start.push_back(nG);
+    std::vector<std::vector<SeedOp>> ops(nI);
+    std::vector<int32_t> gdone(nI, 0);
+    auto run = [&](int32_t i, bool inherited) {
+        ops[i].assign(4 * (size_t)(pre.groups[isl_start[i + 1] - 1].de - pre.groups[isl_start[i]].ds) + 16, SeedOp{});
+        sm.out = ops[i].data(); sm.out_cap = (int32_t)ops[i].size();
+        gdone[i] = sm.run_island(isl_start[i], isl_start[i + 1], inherited);
+        if (sm.error) { fprintf(stderr, "seed machine error %d\n", sm.error); exit(3); }
+        ops[i].resize(sm.st.n_out);
+    };
+    // sequential prefix: until some island has emitted a segment the machine truly has no last segment
+    int32_t ip = 0;
+    for (; ip < nI; ip++) { run(ip, false); if (!ops[ip].empty()) { ip++; break; } }
+    // the rest is order independent: run it backwards to prove it
+    for (int32_t i = nI - 1; i >= ip; i--) run(i, true);
+    std::vector<SeedNode> seeds;
+    int32_t g_done = nG;
+    for (int32_t i = 0; i < nI; i++) {
+        stitch_ops(ops[i].data(), (int32_t)ops[i].size(), seeds);
+        if (gdone[i] < isl_start[i + 1]) { g_done = gdone[i]; break; }
+    }
+    fprintf(stderr, "emul: %d groups, %d islands, %zu seeds, lmax %d, %zu displaced\n", nG, nI, seeds.size(), lmax, dprec.size());
     {
         std::vector<int32_t> s;
         for (auto &x : seeds) { s.push_back(x.chr); s.push_back(x.pos); s.push_back(x.len); }
