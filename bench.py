@@ -222,6 +222,7 @@ def main():
             state["merged_edges"] = ne.value
         bc, bp = bps_from_graph(nodes, edges)
         cov = g.BPCoverage(bc, bp)
+        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback")}
         state.update(n_nodes=int(nodes.Chr.shape[0]), n_edges=int(edges.Ind1.shape[0]), n_bp=int(bc.shape[0]), cov_sum=int(cov.sum()),
                      d2h=int(nodes.Chr.nbytes * 3 + nodes.count3.nbytes * 2 + edges.Ind1.nbytes * 3 + edges.Ind1.shape[0] + cov.nbytes))
         return nodes, edges, cov
@@ -287,7 +288,7 @@ def main():
             "roofline": roof,
             "whole_path": {"alg_bytes_per_pair": b_alg_pair, "gpu_ms_in_kernels": total_gpu_ms,
                            "frac_of_hbm_roofline_wall": (b_alg_pair * P / sec) / 1e9 / peak, "frac_of_hbm_roofline_kernels": (b_alg_pair * P / (total_gpu_ms * 1e-3)) / 1e9 / peak if total_gpu_ms else None},
-            "phases_ms": phases, "phases_ms_e2e": phases_e2e,
+            "phases_ms": phases, "phases_ms_e2e": phases_e2e, "stats": state.get("stats"),
             "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches), "gen_s": t_gen,
         }
         print(json.dumps(out))

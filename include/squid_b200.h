@@ -148,6 +148,9 @@ int sqg_merge_edge_tables(sqg_ctx *ctx, const uint64_t *d_keys, const int32_t *d
 float sqg_phase_ms(const sqg_ctx *ctx, const char *name);
 /* Number of kernel launches issued by this context so far. */
 int64_t sqg_launch_count(const sqg_ctx *ctx);
+/* Counters of the most recent calls ("islands", "heavy_islands", "groups", "disc_blocks", "gap_records", "partial_records",
+ * "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "r_break"); -1 if unknown. */
+int64_t sqg_stat(const sqg_ctx *ctx, const char *name);
 
 #ifdef __cplusplus
 }

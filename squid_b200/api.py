@@ -63,7 +63,7 @@ CHIM_DTYPES = {
 EXPORTS = [
     "sqg_create", "sqg_destroy", "sqg_last_error", "sqg_load_concordant", "sqg_attach_concordant_device", "sqg_load_chimeric",
     "sqg_build_nodes", "sqg_set_nodes", "sqg_build_edges", "sqg_bp_coverage", "sqg_edges_device_table", "sqg_merge_edge_tables",
-    "sqg_phase_ms", "sqg_launch_count",
+    "sqg_phase_ms", "sqg_launch_count", "sqg_stat",
     "sqh_default_options", "sqh_open_case", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
     "sqh_case_n_ref", "sqh_case_ref_len", "sqh_case_blocks",
 ]
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.sqg_merge_edge_tables.argtypes = [_P, _P, _P, C.c_int64, pp(_P), pp(_P), pp(_P), pp(_P), pp(C.c_int64)]
     L.sqg_phase_ms.argtypes = [_P, C.c_char_p]; L.sqg_phase_ms.restype = C.c_float
     L.sqg_launch_count.argtypes = [_P]; L.sqg_launch_count.restype = C.c_int64
+    L.sqg_stat.argtypes = [_P, C.c_char_p]; L.sqg_stat.restype = C.c_int64
     L.sqh_default_options.argtypes = [pp(sqh_options)]; L.sqh_default_options.restype = None
     L.sqh_open_case.argtypes = [C.c_char_p, C.c_char_p, pp(sqh_options), pp(_P), C.c_char_p, C.c_int]
     L.sqh_close_case.argtypes = [_P]; L.sqh_close_case.restype = None
@@ -410,3 +411,6 @@ class SegmentGraph:
 
     def launch_count(self) -> int:
         return int(self.L.sqg_launch_count(self._h))
+
+    def stat(self, name: str) -> int:
+        return int(self.L.sqg_stat(self._h, name.encode()))

@@ -71,11 +71,79 @@ struct SeedState {
     int32_t markedStart, markedChr;
     int32_t backChr, backEnd;
     int32_t n_out;
+    int32_t last_kind;
     bool have_back;
     bool back_inherited;  // the last segment belongs to an earlier island (far left of everything here)
 };
 
-struct SeedMachine {
+// Cooperation policy: how many lanes step one island together.  All lanes keep identical scalar
+// state; only the marked loops are split across lanes and recombined with the reductions below.
+struct CoopSerial {  // one lane (CPU stepping harness, tiny islands)
+    static SQ_HD int lane() { return 0; }
+    static SQ_HD int size() { return 1; }
+    static SQ_HD int sum(int v) { return v; }
+    static SQ_HD int max(int v) { return v; }
+    static SQ_HD int min(int v) { return v; }
+    static SQ_HD int excl_prefix_max(int v, int identity) { (void)v; return identity; }
+    static SQ_HD void sync() {}
+};
+#if defined(__CUDACC__)
+struct CoopWarp {  // 32 lanes of one warp
+    static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int size() { return 32; }
+    static __device__ __forceinline__ int sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+    static __device__ __forceinline__ int max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+    static __device__ __forceinline__ int min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+    static __device__ __forceinline__ int excl_prefix_max(int v, int identity) {
+        const int l = threadIdx.x & 31;
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, d); if (l >= d && o > v) v = o; }
+        const int e = __shfl_up_sync(0xffffffffu, v, 1);
+        return l == 0 ? identity : e;
+    }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): for the few islands with huge windows
+    template <int OP> static __device__ __forceinline__ int reduce(int v, int identity) {
+        __shared__ int wv[32];
+        __shared__ int res;
+        v = OP == 0 ? __reduce_add_sync(0xffffffffu, v) : (OP == 1 ? __reduce_max_sync(0xffffffffu, v) : __reduce_min_sync(0xffffffffu, v));
+        if ((threadIdx.x & 31) == 0) wv[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int x = threadIdx.x < (blockDim.x >> 5) ? wv[threadIdx.x] : identity;
+            x = OP == 0 ? __reduce_add_sync(0xffffffffu, x) : (OP == 1 ? __reduce_max_sync(0xffffffffu, x) : __reduce_min_sync(0xffffffffu, x));
+            if (threadIdx.x == 0) res = x;
+        }
+        __syncthreads();
+        const int r = res;
+        __syncthreads();
+        return r;
+    }
+    static __device__ __forceinline__ int lane() { return threadIdx.x; }
+    static __device__ __forceinline__ int size() { return blockDim.x; }
+    static __device__ __forceinline__ int sum(int v) { return reduce<0>(v, 0); }
+    static __device__ __forceinline__ int max(int v) { return reduce<1>(v, -2147483647 - 1); }
+    static __device__ __forceinline__ int min(int v) { return reduce<2>(v, 2147483647); }
+    static __device__ __forceinline__ int excl_prefix_max(int v, int identity) {
+        __shared__ int wtot[32];
+        const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int incl = v;
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (l >= d && o > incl) incl = o; }
+        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (l == 0) excl = identity;
+        if (l == 31) wtot[w] = incl;
+        __syncthreads();
+        int base = identity;
+        for (int k = 0; k < w; k++) if (wtot[k] > base) base = wtot[k];
+        __syncthreads();
+        return excl > base ? excl : base;
+    }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+#endif
+
+template <class W>
+struct SeedMachineT {
     SeedInputs in;
     SeedState st;
     SeedOp *out; int32_t out_cap;
@@ -121,7 +189,8 @@ struct SeedMachine {
     // ---- output ------------------------------------------------------------------------------
     SQ_HD void emit(int32_t kind, int32_t chr, int32_t pos, int32_t len) {
         if (st.n_out >= out_cap) { error = 2; return; }
-        out[st.n_out].kind = kind; out[st.n_out].chr = chr; out[st.n_out].pos = pos; out[st.n_out].len = len;
+        if (W::lane() == 0) { out[st.n_out].kind = kind; out[st.n_out].chr = chr; out[st.n_out].pos = pos; out[st.n_out].len = len; }
+        st.last_kind = kind;
         st.n_out++;
     }
     SQ_HD void push_node(int32_t chr, int32_t pos, int32_t len) {
@@ -129,33 +198,42 @@ struct SeedMachine {
         st.have_back = true; st.back_inherited = false; st.backChr = chr; st.backEnd = pos + len;
     }
     SQ_HD void set_back_end(int32_t e) {  // vNodes.back().Length += e - Position - Length
-        if (st.n_out > 0 && out[st.n_out - 1].kind == 0) out[st.n_out - 1].len += e - st.backEnd;
+        if (st.n_out > 0 && st.last_kind == 0) { if (W::lane() == 0) out[st.n_out - 1].len += e - st.backEnd; }
         else emit(2, st.backChr, e, 0);
         st.backEnd = e;
     }
-    SQ_HD void push_margin(int32_t &n, int32_t v) {
+    SQ_HD void push_margin(int32_t &n, int32_t v) {  // uniform call: every lane counts, lane 0 stores
         if (n >= margin_cap) { error = 1; return; }
-        margin[n++] = v;
+        if (W::lane() == 0) margin[n] = v;
+        n++;
     }
-    SQ_HD void sort_margins(int32_t n) {  // plain heapsort: values only, so any correct sort agrees with std::sort
-        int32_t *a = margin;
-        for (int32_t s = n / 2 - 1; s >= 0; s--) sift(a, s, n);
-        for (int32_t e = n - 1; e > 0; e--) { int32_t t = a[0]; a[0] = a[e]; a[e] = t; sift(a, 0, e); }
-    }
-    SQ_HD static void sift(int32_t *a, int32_t s, int32_t n) {
-        for (;;) {
-            int32_t c = 2 * s + 1;
-            if (c >= n) return;
-            if (c + 1 < n && a[c + 1] > a[c]) c++;
-            if (a[s] >= a[c]) return;
-            int32_t t = a[s]; a[s] = a[c]; a[c] = t; s = c;
-        }
+    // values only, so any correct sort agrees with std::sort: bitonic network over the next power of two,
+    // compare-exchanges split across the lanes (the scratch is sized for the padding)
+    SQ_HD void sort_margins(int32_t n) {
+        int32_t m = 1;
+        while (m < n) m <<= 1;
+        if (m > margin_cap) { error = 1; return; }
+        W::sync();
+        for (int32_t i = n + W::lane(); i < m; i += W::size()) margin[i] = 0x7fffffff;
+        W::sync();
+        for (int32_t k = 2; k <= m; k <<= 1)
+            for (int32_t j = k >> 1; j > 0; j >>= 1) {
+                for (int32_t i = W::lane(); i < m; i += W::size()) {
+                    const int32_t l = i ^ j;
+                    if (l > i) {
+                        const int32_t a = margin[i], c = margin[l];
+                        const bool up = (i & k) == 0;
+                        if ((a > c) == up) { margin[i] = c; margin[l] = a; }
+                    }
+                }
+                W::sync();
+            }
     }
 
     SQ_HD void init(bool inherited_back) {
         st.offCC = 0; st.offPC = 0; st.markedStart = -1; st.markedChr = -1;
         st.have_back = inherited_back; st.back_inherited = inherited_back;
-        st.backChr = -2; st.backEnd = -(1 << 30); st.n_out = 0; error = 0;
+        st.backChr = -2; st.backEnd = -(1 << 30); st.n_out = 0; st.last_kind = -1; error = 0;
     }
 
     // (curChr, currightmost) and the 0-coverage test of :616-620 for kept record r while a group starting at (sChr,sPos) is pending
@@ -256,7 +334,7 @@ struct SeedMachine {
         if (y > st.offPC) st.offPC = y;
     }
 
-    // number of ConcordantCluster + PartialAlignCluster window entries spanning brk +- thresh (:457-469)
+    // number of ConcordantCluster + PartialAlignCluster window entries spanning brk +- thresh (:457-469); lanes split the ranges
     SQ_HD int32_t window_coverage(int32_t chrG, int32_t brk, int64_t rg, int32_t szPC) const {
         const int32_t thresh = kSeedThresh;
         int32_t cov = 0;
@@ -264,7 +342,7 @@ struct SeedMachine {
         const int32_t pmin = brk + thresh - in.lmax, pmax = brk - thresh;
         if (st.offCC < rg) {
             const int64_t lo = lb_pos(st.offCC, rg, chrG, pmin), hi = lb_pos(lo, rg, chrG, pmax);
-            for (int64_t r = lo; r < hi; r++)
+            for (int64_t r = lo + W::lane(); r < hi; r += W::size())
                 if (isCC(r) && !isDispl(r) && in.b.ref_id[r] == chrG) {
                     const int32_t p0 = e_pos(r);
                     if (p0 + e_len(r) >= brk + thresh && p0 < pmax) cov++;
@@ -272,7 +350,7 @@ struct SeedMachine {
         }
         if (st.offPC < szPC) {
             const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, pmin), hi = lb_pc_pos(lo, szPC, chrG, pmax);
-            for (int32_t i = lo; i < hi; i++) {
+            for (int32_t i = lo + W::lane(); i < hi; i += W::size()) {
                 const int64_t r = in.pc_rec[i];
                 if (!isDispl(r) && in.b.ref_id[r] == chrG) {
                     const int32_t p0 = e_pos(r);
@@ -283,7 +361,8 @@ struct SeedMachine {
         // displaced entries of either window
         const int64_t w0 = st.offCC < rg ? st.offCC : rg;
         const int64_t wp = st.offPC < szPC ? (int64_t)in.pc_rec[st.offPC] : rg;
-        for (int32_t k = lb_list(in.dp_rec, in.n_dp, w0 < wp ? w0 : wp); k < in.n_dp && in.dp_rec[k] < rg; k++) {
+        const int32_t k0 = lb_list(in.dp_rec, in.n_dp, w0 < wp ? w0 : wp), k1 = lb_list(in.dp_rec, in.n_dp, rg);
+        for (int32_t k = k0 + W::lane(); k < k1; k += W::size()) {
             const int64_t r = in.dp_rec[k];
             if (in.b.ref_id[r] != chrG) continue;
             const bool part = in.cls[r] & CLS_PART;
@@ -291,21 +370,22 @@ struct SeedMachine {
             const int32_t p0 = e_pos(r);
             if (p0 + e_len(r) >= brk + thresh && p0 < pmax) cov++;
         }
-        return cov;
+        return W::sum(cov);
     }
 
     // ConcordRest coverage at `brk` for the group starting at sPos on chromosome chrG, records before rg (:471-473)
     SQ_HD int32_t rest_coverage(int32_t chrG, int32_t sPos, int32_t brk, int64_t rg) const {
-        const int32_t lo_pos = sPos - in.read_len;
+        const int32_t lo_pos = sPos - in.read_len, hi_pos = brk - kSeedThresh;
         int32_t lo = 0, hi = in.n_rest;
         while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
+        int32_t lo2 = lo, hi2 = in.n_rest;
+        while (lo2 < hi2) { int32_t m = (lo2 + hi2) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < hi_pos)) lo2 = m + 1; else hi2 = m; }
         int32_t cnt = 0;
-        for (int32_t k = lo; k < in.n_rest; k++) {
+        for (int32_t k = lo + W::lane(); k < lo2; k += W::size()) {
             const RestBlock &e = in.rest[k];
-            if (e.chr != chrG || e.pos >= brk - kSeedThresh) break;
             if (e.rec < rg && e.end >= brk + kSeedThresh) cnt++;
         }
-        return cnt;
+        return W::sum(cnt);
     }
 
     SQ_HD void pc_margin(int64_t r, int32_t chrG, int32_t m0, int32_t curEndPos, int32_t &nM) {  // :420-434 for one entry
@@ -319,6 +399,144 @@ struct SeedMachine {
         } else {
             if (rv && p0 > m0 - thresh && p0 < curEndPos + thresh) push_margin(nM, p0);
             else if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
+        }
+    }
+
+    // flag1/flag2 of the two walks at :536-601 for an entry (c,p0,p1); dc = first discordant block not covered yet
+    SQ_HD bool walk_ok(bool first_walk, int32_t chrG, int32_t dc, int32_t c, int32_t p0, int32_t p1) const {
+        const DiscBlock *D = in.D;
+        const int32_t RL = in.read_len;
+        if (first_walk) {
+            if (c > chrG) return false;
+            if (dc != in.nD && c == D[dc].chr && p1 + RL >= D[dc].pos) return false;
+            if (st.have_back && (c > st.backChr || (c == st.backChr && p0 >= st.backEnd))) return false;
+            return true;
+        }
+        return dc == in.nD || c < D[dc].chr || (c == D[dc].chr && p1 + RL < D[dc].pos);
+    }
+    // Advance st.offCC over the maximal prefix of window entries that pass walk_ok; returns the largest end consumed.
+    SQ_HD int32_t consume_cc(int64_t rg, int32_t chrG, int32_t dc, bool first_walk) {
+        int32_t mx = -(1 << 30);
+        int64_t x = st.offCC;
+        while (x < rg) {
+            const int64_t r = x + W::lane();
+            const bool cc = r < rg && isCC(r);
+            bool ok = false;
+            int32_t p1 = -(1 << 30);
+            if (cc) { const int32_t p0 = e_pos(r); p1 = p0 + e_len(r); ok = walk_ok(first_walk, chrG, dc, e_chr(r), p0, p1); }
+            const int first_bad = W::min((cc && !ok) ? W::lane() : W::size());
+            const int32_t m = W::max((cc && ok && W::lane() < first_bad) ? p1 : -(1 << 30));
+            if (m > mx) mx = m;
+            if (first_bad < W::size()) { st.offCC = x + first_bad; return mx; }
+            x += W::size();
+        }
+        st.offCC = rg;
+        return mx;
+    }
+    SQ_HD int32_t consume_pc(int32_t szPC, int32_t chrG, int32_t dc, bool first_walk) {
+        int32_t mx = -(1 << 30);
+        int32_t x = st.offPC;
+        while (x < szPC) {
+            const int32_t i = x + W::lane();
+            const bool in_w = i < szPC;
+            bool ok = false;
+            int32_t p1 = -(1 << 30);
+            if (in_w) { const int64_t r = in.pc_rec[i]; const int32_t p0 = e_pos(r); p1 = p0 + e_len(r); ok = walk_ok(first_walk, chrG, dc, e_chr(r), p0, p1); }
+            const int first_bad = W::min((in_w && !ok) ? W::lane() : W::size());
+            const int32_t m = W::max((in_w && ok && W::lane() < first_bad) ? p1 : -(1 << 30));
+            if (m > mx) mx = m;
+            if (first_bad < W::size()) { st.offPC = x + first_bad; return mx; }
+            x += W::size();
+        }
+        st.offPC = szPC;
+        return mx;
+    }
+    // close-out of the pending segment at the 0-coverage position concord0pos (:572-580)
+    SQ_HD void close_marked(int32_t concord0pos, int32_t &curStartPos) {
+        const int32_t thresh = kSeedThresh;
+        if (st.back_inherited) {
+            // the last segment was emitted by an earlier island: whether it is on markedChr (extend it) or not (push a
+            // new one) is decided when the islands are stitched; either way the last segment becomes (markedChr, concord0pos)
+            if (concord0pos > st.markedStart) {
+                emit(concord0pos < st.markedStart + thresh * 20 ? 1 : 0, st.markedChr, st.markedStart, concord0pos - st.markedStart);
+                st.have_back = true; st.back_inherited = false; st.backChr = st.markedChr; st.backEnd = concord0pos;
+            }
+        } else if (concord0pos > st.markedStart && concord0pos < st.markedStart + thresh * 20 && st.have_back && st.backChr == st.markedChr)
+            set_back_end(concord0pos);
+        else if (concord0pos > st.markedStart)
+            push_node(st.markedChr, st.markedStart, concord0pos - st.markedStart);
+        curStartPos = concord0pos;
+        st.markedChr = -1; st.markedStart = -1;
+    }
+    // The loop at :570-601.  Every iteration first tests whether the stream shows a 0-coverage position right after
+    // concord0pos (then the pending segment is closed there), else consumes one entry of each window that is still more
+    // than ReadLen left of the next discordant block.  While the (sparse) PartialAlignCluster window still moves the
+    // iterations are stepped one by one; afterwards only the ConcordantCluster window advances and the iterations are
+    // evaluated a chunk at a time with a prefix maximum of the consumed ends.
+    SQ_HD void extend_to_zero_coverage(int64_t rg, int32_t szPC, int32_t dc, int32_t recChr, int32_t recPos, int32_t concord0pos, int32_t &curStartPos) {
+        const int32_t RL = in.read_len;
+        bool first = true;
+        for (;;) {  // phase 1: literal iterations while the PartialAlignCluster front is consumable
+            const bool ccEmpty = !(st.offCC < rg), pcEmpty = !(st.offPC < szPC);
+            if (!first && ccEmpty && pcEmpty) return;  // `while(... .size()!=offset ...)` fails
+            bool f2 = false;
+            int32_t pc_c = 0, pc_p0 = 0, pc_p1 = 0;
+            if (!pcEmpty) {
+                const int64_t r = in.pc_rec[st.offPC];
+                pc_c = e_chr(r); pc_p0 = e_pos(r); pc_p1 = pc_p0 + e_len(r);
+                f2 = walk_ok(false, 0, dc, pc_c, pc_p0, pc_p1);
+            }
+            if (!f2) break;  // the PartialAlignCluster front is stuck (or the window is empty) from now on
+            first = false;
+            int32_t cc_c = 0, cc_p0 = 0, cc_p1 = 0;
+            if (!ccEmpty) { cc_c = e_chr(st.offCC); cc_p0 = e_pos(st.offCC); cc_p1 = cc_p0 + e_len(st.offCC); }
+            if (st.markedStart != -1 && (recChr > st.markedChr || recPos > concord0pos + RL) &&
+                (ccEmpty || cc_c != st.markedChr || cc_p0 > concord0pos + RL) && (pc_c != st.markedChr || pc_p0 > concord0pos)) {
+                close_marked(concord0pos, curStartPos);
+                return;
+            }
+            if (!ccEmpty && walk_ok(false, 0, dc, cc_c, cc_p0, cc_p1)) { if (cc_p1 > concord0pos) concord0pos = cc_p1; st.offCC = nextCC(st.offCC + 1, rg); }
+            if (pc_p1 > concord0pos) concord0pos = pc_p1;
+            st.offPC++;
+        }
+        // phase 2: the PartialAlignCluster front is fixed
+        const bool pcEmpty = !(st.offPC < szPC);
+        int32_t pc_c = -1, pc_p0 = 0;
+        if (!pcEmpty) { pc_c = e_chr(in.pc_rec[st.offPC]); pc_p0 = e_pos(in.pc_rec[st.offPC]); }
+        const bool marked = st.markedStart != -1;
+        int64_t x = st.offCC;
+        for (;;) {
+            if (x >= rg) {  // ConcordantCluster window exhausted
+                st.offCC = rg;
+                if (!first && pcEmpty) return;
+                if (marked && (recChr > st.markedChr || recPos > concord0pos + RL) && (pcEmpty || pc_c != st.markedChr || pc_p0 > concord0pos))
+                    close_marked(concord0pos, curStartPos);
+                return;  // neither window can move
+            }
+            const int64_t r = x + W::lane();
+            const bool cc = r < rg && isCC(r);
+            int32_t c = 0, p0 = 0, p1 = -(1 << 30);
+            bool f1 = false;
+            if (cc) { c = e_chr(r); p0 = e_pos(r); p1 = p0 + e_len(r); f1 = walk_ok(false, 0, dc, c, p0, p1); }
+            // concord0pos seen by this lane's iteration = everything consumed by the lanes before it
+            int32_t mi = W::excl_prefix_max(cc ? p1 : -(1 << 30), -(1 << 30));
+            if (concord0pos > mi) mi = concord0pos;
+            const bool close_i = cc && marked && (recChr > st.markedChr || recPos > mi + RL) && (c != st.markedChr || p0 > mi + RL) &&
+                                 (pcEmpty || pc_c != st.markedChr || pc_p0 > mi);
+            const bool stop_i = cc && (close_i || !f1);
+            const int fs = W::min(stop_i ? W::lane() : W::size());
+            if (fs < W::size()) {
+                const int32_t m_at = W::max(W::lane() == fs ? mi : -(1 << 30));
+                const int32_t cl_at = W::max((W::lane() == fs && close_i) ? 1 : 0);
+                st.offCC = x + fs;
+                concord0pos = m_at;
+                if (cl_at) close_marked(concord0pos, curStartPos);
+                return;
+            }
+            const int32_t m = W::max(cc ? p1 : -(1 << 30));
+            if (m > concord0pos) concord0pos = m;
+            if (W::max(cc ? 1 : 0)) first = false;
+            x += W::size();
         }
     }
 
@@ -399,6 +617,7 @@ struct SeedMachine {
             }
             if (error) return;
             sort_margins(nM);
+            if (error) return;
             int32_t lastCurser = -1, lastSupport = 0;
             for (int32_t ib = 0; ib < nM;) {
                 const int32_t brk = margin[ib];
@@ -409,15 +628,18 @@ struct SeedMachine {
                     while (k > 0 && brk - margin[k - 1] < thresh) k--;
                     for (; k < nM && margin[k] < brk + thresh; k++) sr++;
                 }
-                for (int32_t k = ds; k != de; k++) {
+                for (int32_t k = ds + W::lane(); k < de; k += W::size()) {
                     const int32_t e1 = D[k].pos + D[k].len;
                     if (e1 < brk && e1 > brk - RL && !D[k].rev) pl++;
                     else if (D[k].pos > brk && D[k].pos < brk + RL && D[k].rev) pr++;
                 }
+                pl = W::sum(pl); pr = W::sum(pr);
                 if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
                     int32_t coverage = window_coverage(chrG, brk, rg, szPC);
-                    for (int32_t k = ds; k != de; k++)
-                        if (D[k].chr == chrG && D[k].pos + D[k].len >= brk + thresh && D[k].pos < brk - thresh) coverage++;
+                    int32_t dcov = 0;
+                    for (int32_t k = ds + W::lane(); k < de; k += W::size())
+                        if (D[k].chr == chrG && D[k].pos + D[k].len >= brk + thresh && D[k].pos < brk - thresh) dcov++;
+                    coverage += W::sum(dcov);
                     int32_t rest = coverage - sr; if (rest < 0) rest = 0;
                     if (sr > rest + 2) {
                         coverage += rest_coverage(chrG, in.D[grp.ds].pos, brk, rg);
@@ -469,69 +691,17 @@ struct SeedMachine {
             while (st.offCC < rg && e_chr(st.offCC) < chrG) st.offCC = nextCC(st.offCC + 1, rg);
             while (st.offPC < szPC && e_chr(in.pc_rec[st.offPC]) < chrG) st.offPC++;
             for (dc = ds; dc != de && D[dc].pos + D[dc].len <= curEndPos; dc++) {}
-            // :536-567 walk the windows up to the end of the last inserted segment, tracking the 0-coverage position
+            // :536-567 walk the windows up to the end of the last inserted segment, tracking the 0-coverage position.
+            // Each window gives up its maximal prefix of entries that lie left of the last segment's end and more than
+            // ReadLen left of the next discordant block; the two windows do not influence each other here.
             int32_t concord0pos = curStartPos;
-            do {
-                bool f1 = false, f2 = false;
-                if (st.offCC < rg) {
-                    const int64_t r = st.offCC;
-                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
-                    f1 = true;
-                    if (c > chrG) f1 = false;
-                    if (dc != in.nD && c == D[dc].chr && p1 + RL >= D[dc].pos) f1 = false;
-                    if (st.have_back && (c > st.backChr || (c == st.backChr && p0 >= st.backEnd))) f1 = false;
-                    if (f1) { if (p1 > concord0pos) concord0pos = p1; st.offCC = nextCC(r + 1, rg); }
-                }
-                if (st.offPC < szPC) {
-                    const int64_t r = in.pc_rec[st.offPC];
-                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
-                    f2 = true;
-                    if (c > chrG) f2 = false;
-                    if (dc != in.nD && c == D[dc].chr && p1 + RL >= D[dc].pos) f2 = false;
-                    if (st.have_back && (c > st.backChr || (c == st.backChr && p0 >= st.backEnd))) f2 = false;
-                    if (f2) { if (p1 > concord0pos) concord0pos = p1; st.offPC++; }
-                }
-                if (!f1 && !f2) break;
-            } while (st.offCC < rg || st.offPC < szPC);
+            {
+                const int32_t a = consume_cc(rg, chrG, dc, true), bq = consume_pc(szPC, chrG, dc, true);
+                if (a > concord0pos) concord0pos = a;
+                if (bq > concord0pos) concord0pos = bq;
+            }
             // :570-601 extend the last segment to the next 0-coverage position if the stream already shows one
-            do {
-                const bool ccEmpty = !(st.offCC < rg), pcEmpty = !(st.offPC < szPC);
-                if (st.markedStart != -1 && (recChr > st.markedChr || recPos > concord0pos + RL) &&
-                    (ccEmpty || e_chr(st.offCC) != st.markedChr || e_pos(st.offCC) > concord0pos + RL) &&
-                    (pcEmpty || e_chr(in.pc_rec[st.offPC]) != st.markedChr || e_pos(in.pc_rec[st.offPC]) > concord0pos)) {
-                    if (st.back_inherited) {
-                        // the last segment was emitted by an earlier island: whether it is on markedChr (extend it) or
-                        // not (push a new one) is decided when the islands are stitched; both leave (markedChr, concord0pos)
-                        if (concord0pos > st.markedStart) {
-                            emit(1, st.markedChr, st.markedStart, concord0pos - st.markedStart);
-                            // kind 1 carries "extend only if < thresh*20" in the sign of len? no: the extend branch also needs
-                            // concord0pos < markedStart + thresh*20; encode it by kind: 1 = may extend, else plain push
-                            if (!(concord0pos < st.markedStart + thresh * 20)) out[st.n_out - 1].kind = 0;
-                            st.have_back = true; st.back_inherited = false; st.backChr = st.markedChr; st.backEnd = concord0pos;
-                        }
-                    } else if (concord0pos > st.markedStart && concord0pos < st.markedStart + thresh * 20 && st.have_back && st.backChr == st.markedChr)
-                        set_back_end(concord0pos);
-                    else if (concord0pos > st.markedStart)
-                        push_node(st.markedChr, st.markedStart, concord0pos - st.markedStart);
-                    curStartPos = concord0pos;
-                    st.markedChr = -1; st.markedStart = -1;
-                    break;
-                }
-                bool f1 = false, f2 = false;
-                if (!ccEmpty) {
-                    const int64_t r = st.offCC;
-                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
-                    if (dc == in.nD || c < D[dc].chr || (c == D[dc].chr && p1 + RL < D[dc].pos)) f1 = true;
-                    if (f1) { if (p1 > concord0pos) concord0pos = p1; st.offCC = nextCC(r + 1, rg); }
-                }
-                if (!pcEmpty) {
-                    const int64_t r = in.pc_rec[st.offPC];
-                    const int32_t c = e_chr(r), p0 = e_pos(r), p1 = p0 + e_len(r);
-                    if (dc == in.nD || c < D[dc].chr || (c == D[dc].chr && p1 + RL < D[dc].pos)) f2 = true;
-                    if (f2) { if (p1 > concord0pos) concord0pos = p1; st.offPC++; }
-                }
-                if (!f1 && !f2) break;
-            } while (st.offCC < rg || st.offPC < szPC);
+            extend_to_zero_coverage(rg, szPC, dc, recChr, recPos, concord0pos, curStartPos);
             ds = dc;
             if (error) return;
         }
@@ -567,6 +737,8 @@ struct SeedMachine {
         return g;
     }
 };
+
+typedef SeedMachineT<CoopSerial> SeedMachine;
 
 // Stitch island op lists (in island order) into the seed-segment list.  Host side (sizes are tiny).
 template <class Vec>

@@ -68,6 +68,7 @@ struct GateIdxOp {
 };
 struct MaxI32 { __device__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; } };
 struct MaxU64 { __device__ uint64_t operator()(uint64_t a, uint64_t b) const { return a > b ? a : b; } };
+struct MaxI64 { __device__ int64_t operator()(int64_t a, int64_t b) const { return a > b ? a : b; } };
 struct MinI64 { __device__ int64_t operator()(int64_t a, int64_t b) const { return a < b ? a : b; } };
 
 __global__ void k_validate(DevBatch b, int32_t n_ref, int32_t *flags) {
@@ -185,7 +186,7 @@ struct IsCutOp {
     __device__ bool operator()(int32_t g) const { return flag[g] != 0; }
 };
 // scratch each island needs: [2i] = op slots, [2i+1] = margin slots
-__global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n_isl, int32_t *cap_ops, int32_t *cap_mar) {
+__global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n_isl, int32_t *cap_ops, int32_t *cap_mar, int32_t *span) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_isl) return;
     SeedMachine sm;
@@ -215,37 +216,53 @@ __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n
     const int32_t ndp = sm.lb_list(in.dp_rec, in.n_dp, r1) - sm.lb_list(in.dp_rec, in.n_dp, r0);
     mmax += (ndp > 0 ? ndp : 0) + 16;
     cap_ops[i] = 4 * (in.G[gb - 1].de - in.G[ga].ds) + 2 * mmax + 64;
-    cap_mar[i] = mmax;
+    int32_t pw = 1;
+    while (pw < mmax) pw <<= 1;  // sort_margins pads to a power of two
+    cap_mar[i] = pw;
+    span[i] = (int32_t)((r1 - r0) > 0x7fffffff ? 0x7fffffff : (r1 - r0));  // records the island may have to walk
 }
-// islands [i0, n_isl): one thread each.  i0 > 0 islands start with an inherited (far-left) last segment.
-// mode 0: sequential prefix, islands from 0 until one has emitted a segment (writes *n_prefix);  mode 1: islands >= *n_prefix in parallel
-__global__ void k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar, SeedOp *ops, int32_t *margin,
-                               int32_t *n_out, int32_t *g_done, int32_t *err, int32_t *n_prefix, int mode) {
-    SeedMachine sm;
+constexpr int kSeedBlock = 512;        // threads per block of the seed kernels
+constexpr int kHeavySpan = 1 << 14;    // islands spanning more records than this get a whole block instead of a warp
+struct IsHeavyOp {
+    const int32_t *span; const int32_t *n_prefix; bool want_heavy;
+    __device__ bool operator()(int32_t i) const { return i >= *n_prefix && ((span[i] > kHeavySpan) == want_heavy); }
+};
+template <class W>
+__device__ __forceinline__ void seed_one_island(const SeedInputs &in, int32_t i, bool inherited, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops,
+                                                const int64_t *off_mar, SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err, int32_t *n_out_ret) {
+    SeedMachineT<W> sm;
     sm.in = in;
-    if (mode == 0) {
-        if (blockIdx.x != 0 || threadIdx.x != 0) return;
-        int32_t i = 0;
-        for (; i < n_isl; i++) {
-            const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
-            sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
-            sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
-            g_done[i] = sm.run_island(ga, gb, false);
-            n_out[i] = sm.st.n_out;
-            if (sm.error) atomicMax(err, sm.error);
-            if (sm.st.n_out > 0) { i++; break; }
-        }
-        *n_prefix = i;
-        return;
-    }
-    const int32_t i = *n_prefix + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_isl) return;
     const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
     sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
     sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
-    g_done[i] = sm.run_island(ga, gb, true);
-    n_out[i] = sm.st.n_out;
-    if (sm.error) atomicMax(err, sm.error);
+    const int32_t gd = sm.run_island(ga, gb, inherited);
+    if (W::lane() == 0) { g_done[i] = gd; n_out[i] = sm.st.n_out; if (sm.error) atomicMax(err, sm.error); }
+    if (n_out_ret) *n_out_ret = sm.st.n_out;
+}
+// Sequential prefix (one block): islands from 0 until one has emitted a segment -- until then the machine truly has no
+// last segment.  Writes *n_prefix = number of islands consumed.
+__global__ void __launch_bounds__(kSeedBlock) k_seed_prefix(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar,
+                                                          SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err, int32_t *n_prefix) {
+    int32_t i = 0;
+    for (; i < n_isl; i++) {
+        int32_t emitted = 0;
+        seed_one_island<CoopBlock>(in, i, false, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, &emitted);
+        if (emitted > 0) { i++; break; }
+    }
+    if (threadIdx.x == 0) *n_prefix = i;
+}
+// All other islands in parallel, each starting from an inherited (far-left) last segment: blocks [0, n_heavy) take one
+// heavy island each (SeedMachineT<CoopBlock>), the remaining blocks take one light island per warp (SeedMachineT<CoopWarp>).
+__global__ void __launch_bounds__(kSeedBlock) k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar,
+                                                           SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err,
+                                                           const int32_t *heavy, int32_t n_heavy, const int32_t *light, int32_t n_light) {
+    if ((int32_t)blockIdx.x < n_heavy) {
+        seed_one_island<CoopBlock>(in, heavy[blockIdx.x], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr);
+        return;
+    }
+    const int32_t k = ((int32_t)blockIdx.x - n_heavy) * (kSeedBlock / 32) + (threadIdx.x >> 5);
+    if (k >= n_light) return;
+    seed_one_island<CoopWarp>(in, light[k], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -280,15 +297,25 @@ __global__ void k_depth_targets(DevBatch b, const uint8_t *cls, NodeTable nt, in
     }
     target[r] = m;
 }
+// one atomic per run of equal segments inside a warp (sorted input => long runs): int sums wrap like the reference's `int`
+__device__ __forceinline__ void warp_add_by_key(int32_t key, int32_t len, int32_t *cnt, int32_t *sum) {
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    const int32_t s = __reduce_add_sync(m, len);
+    if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(&cnt[key], __popc(m)); atomicAdd(&sum[key], s); }
+}
 __global__ void k_depth_main_count(DevBatch b, const uint8_t *cls, NodeTable nt, int64_t r_break, const int32_t *cursor,
                                    int32_t *cnt_main, int32_t *sum_main) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= b.n_rec || r >= r_break || !(cls[r] & CLS_HASBLK)) return;
-    const int32_t c = cursor[r];
-    if (c == kNoNode || c < 0 || c >= nt.n) return;
-    const uint32_t o = b.blk_off[r];
-    const int32_t s = b.blk_ref_pos[o], l = b.blk_match_ref[o];
-    if (depth_contained(nt, c, b.ref_id[r], s, l)) { atomicAdd(&cnt_main[c], 1); atomicAdd(&sum_main[c], l); }
+    int32_t key = -1, len = 0;
+    if (r < b.n_rec && r < r_break && (cls[r] & CLS_HASBLK)) {
+        const int32_t c = cursor[r];
+        if (c != kNoNode && c >= 0 && c < nt.n) {
+            const uint32_t o = b.blk_off[r];
+            const int32_t s = b.blk_ref_pos[o], l = b.blk_match_ref[o];
+            if (depth_contained(nt, c, b.ref_id[r], s, l)) { key = c; len = l; }
+        }
+    }
+    warp_add_by_key(key, len, cnt_main, sum_main);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -298,13 +325,6 @@ struct EdgeSink {
     uint64_t *keys; int64_t cap; unsigned long long *counter;
     __device__ void operator()(uint64_t k) {
         const unsigned long long slot = atomicAdd(counter, 1ull);
-        if ((int64_t)slot < cap) keys[slot] = k;
-    }
-};
-struct EdgeSinkSerial {  // single-thread fix-up kernels
-    uint64_t *keys; int64_t cap; unsigned long long *counter;
-    __device__ void operator()(uint64_t k) {
-        const unsigned long long slot = (*counter)++;
         if ((int64_t)slot < cap) keys[slot] = k;
     }
 };
@@ -350,20 +370,28 @@ __global__ void k_conc_edges(DevBatch b, const uint8_t *cls, Params p, NodeTable
     }
     res0[r] = out;
 }
-__global__ void k_conc_fixup(DevBatch b, Params p, NodeTable nt, int32_t *res0, const int32_t *sens, int32_t n_sens, EdgeSinkSerial sink) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    for (int32_t i = 0; i < n_sens; i++) {
-        const int64_t r = sens[i];
-        int32_t hint = 0;  // firstfrontindex starts at 0 (:1568)
-        for (int64_t q = r - 1; q >= 0; q--) if (res0[q] >= 0) { hint = res0[q]; break; }
-        Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
-        int32_t node[2 * kMaxBlocks + 2];
-        ReadView rv; rv.F = F; rv.S = S;
-        bool is_first;
-        conc_load_read(b, r, rv, is_first);
-        read_edges(nt, p, rv, MODE_OTHER, is_first, true, hint, node, sink);
-        res0[r] = node[0];
+// Hint-sensitive reads are replayed with the true hint = segment of the first block of the nearest earlier read that
+// set one (res0 >= 0).  A sensitive read whose nearest candidate is itself still unresolved waits for the next round;
+// chains of adjacent sensitive reads are short, so a couple of rounds resolve everything.
+__global__ void k_conc_fixup(DevBatch b, Params p, NodeTable nt, int32_t *res0, const int32_t *sens, int32_t n_sens, EdgeSink sink, int32_t *n_left) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sens) return;
+    const int64_t r = sens[i];
+    if (((volatile int32_t *)res0)[r] != -3) return;  // resolved in an earlier round
+    int32_t hint = 0;  // firstfrontindex starts at 0 (:1568)
+    for (int64_t q = r - 1; q >= 0; q--) {
+        const int32_t v = ((volatile int32_t *)res0)[q];
+        if (v >= 0) { hint = v; break; }
+        if (v == -3) { atomicAdd(n_left, 1); return; }
     }
+    Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+    int32_t node[2 * kMaxBlocks + 2];
+    ReadView rv; rv.F = F; rv.S = S;
+    bool is_first;
+    conc_load_read(b, r, rv, is_first);
+    read_edges(nt, p, rv, MODE_OTHER, is_first, true, hint, node, sink);
+    __threadfence();
+    ((volatile int32_t *)res0)[r] = node[0] >= 0 ? node[0] : -1;
 }
 
 struct ChimDev {
@@ -405,21 +433,25 @@ __global__ void k_chim_edges(ChimDev c, Params p, NodeTable nt, int32_t *res0, E
     }
     res0[i] = out;
 }
-__global__ void k_chim_fixup(ChimDev c, Params p, NodeTable nt, int32_t *res0, EdgeSinkSerial sink) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    int32_t hint = 0;
-    for (int64_t i = 0; i < c.n_reads; i++) {
-        if (res0[i] == -3) {
-            Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
-            int32_t node[2 * kMaxBlocks + 2];
-            ReadView rv; rv.F = F; rv.S = S;
-            chim_load_read(c, i, rv);
-            read_edges(nt, p, rv, MODE_CHIM, true, true, hint, node, sink);
-            chim_store_read(c, i, rv);
-            res0[i] = node[0];
-        }
-        if (res0[i] >= 0) hint = res0[i];
+__global__ void k_chim_fixup(ChimDev c, Params p, NodeTable nt, int32_t *res0, const int32_t *sens, int32_t n_sens, EdgeSink sink, int32_t *n_left) {
+    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_sens) return;
+    const int64_t i = sens[k];
+    if (((volatile int32_t *)res0)[i] != -3) return;
+    int32_t hint = 0;  // :1395
+    for (int64_t q = i - 1; q >= 0; q--) {
+        const int32_t v = ((volatile int32_t *)res0)[q];
+        if (v >= 0) { hint = v; break; }
+        if (v == -3) { atomicAdd(n_left, 1); return; }
     }
+    Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+    int32_t node[2 * kMaxBlocks + 2];
+    ReadView rv; rv.F = F; rv.S = S;
+    chim_load_read(c, i, rv);
+    read_edges(nt, p, rv, MODE_CHIM, true, true, hint, node, sink);
+    chim_store_read(c, i, rv);
+    __threadfence();
+    ((volatile int32_t *)res0)[i] = node[0] >= 0 ? node[0] : -1;
 }
 struct IsSensOp {
     const int32_t *res0;
@@ -445,41 +477,72 @@ struct CoverKeyOp {
         return chrpos_key(rid, cover_start(f, rid, pos, mrid, mpos));
     }
 };
-__global__ void k_cov_r0(const uint64_t *M, int64_t n, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, uint64_t *bpkey, int64_t *r0) {
+struct CoverQualOp {
+    DevBatch b; const uint8_t *cls;
+    __device__ bool operator()(int32_t r) const { return cover_qualifies(cls[r], b.flag[r], b.ref_id[r], b.pos[r], b.mate_ref_id[r], b.mate_pos[r]); }
+};
+// key of the i-th QUALIFYING record (rank space): the reference's indBP advances at most once per qualifying record
+struct CoverRankKeyOp {
+    DevBatch b; const int32_t *qidx;
+    __device__ uint64_t operator()(int32_t i) const {
+        const int32_t r = qidx[i];
+        return chrpos_key(b.ref_id[r], cover_start(b.flag[r], b.ref_id[r], b.pos[r], b.mate_ref_id[r], b.mate_pos[r]));
+    }
+};
+__global__ void k_cov_r0(const uint64_t *M, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, uint64_t *bpkey, int64_t *r0, int64_t *t) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= K) return;
     bpkey[k] = chrpos_key(bp_chr[k], bp_pos[k]);
     const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
-    r0[k] = upper_bound_u64(M, 0, n, T);  // first record whose running-max key exceeds T
+    const int64_t v = upper_bound_u64(M, 0, nq, T);  // first qualifying rank whose running-max key exceeds T
+    r0[k] = v;
+    t[k] = v - k;  // max-plus form of t[k] = max(r0[k], t[k-1]+1)
 }
-// the reference advances indBP by at most one per qualifying record (:3157-3158): t[k] = record at which indBP leaves k
-__global__ void k_cov_chain(DevBatch b, const uint8_t *cls, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist,
-                            const int64_t *r0, int64_t *t) {
+__global__ void k_cov_verify(CoverRankKeyOp key, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist,
+                             const int64_t *r0, int64_t *t, int32_t *fail) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int64_t c = t[k] + k;  // candidate rank
+    t[k] = c;
+    if (c != r0[k] && c < nq) {  // lag mode: the qualifying record right after t[k-1] must itself pass breakpoint k
+        const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
+        if (!(key((int32_t)c) > T)) *fail = 1;
+    }
+}
+// literal chain (:3157-3158), only when the verification above fails
+__global__ void k_cov_chain(CoverRankKeyOp key, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, const int64_t *r0, int64_t *t) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    CoverKeyOp key{b, cls};
     int64_t tp = -1;
-    const int64_t n = b.n_rec;
     for (int64_t k = 0; k < K; k++) {
         int64_t c;
         if (r0[k] > tp) c = r0[k];
         else {
             const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
             c = tp + 1;
-            while (c < n && !(key((int32_t)c) > T)) c++;
+            while (c < nq && !(key((int32_t)c) > T)) c++;
         }
         t[k] = c;
-        tp = c < n ? c : n;
+        tp = c < nq ? c : nq;
     }
 }
-__global__ void k_cov_count(DevBatch b, const uint8_t *cls, const uint64_t *bpkey, const int64_t *t, int64_t K, int32_t *cov) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= b.n_rec) return;
-    CoverKeyOp key{b, cls};
-    const uint64_t ks = key((int32_t)r);
-    if (!ks) return;
-    const uint64_t ke = chrpos_key(b.ref_id[r], b.end_pos[r]);
-    for (int64_t k = lower_bound_u64(bpkey, 0, K, ks); k < K && bpkey[k] < ke; k++)
-        if (r < t[k]) atomicAdd(&cov[k], 1);
+__global__ void k_cov_count(DevBatch b, const int32_t *qidx, int64_t nq, const uint64_t *bpkey, const int64_t *t, int64_t K, int32_t *cov) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = i < nq;
+    if (!valid) i = nq - 1;  // keep the whole warp in the aggregation loop
+    const int32_t r = qidx[i];
+    const int32_t rid = b.ref_id[r];
+    const uint64_t ks = chrpos_key(rid, cover_start(b.flag[r], rid, b.pos[r], b.mate_ref_id[r], b.mate_pos[r]));
+    const uint64_t ke = chrpos_key(rid, b.end_pos[r]);
+    // sorted input: neighbouring fragments cover the same breakpoints, so aggregate per warp before the atomic
+    int64_t k = lower_bound_u64(bpkey, 0, K, ks);
+    bool live = valid && k < K && bpkey[k] < ke;
+    const unsigned full = __activemask();
+    while (__any_sync(full, live)) {
+        const int32_t key = (live && i < t[k]) ? (int32_t)k : -1;
+        const unsigned m = __match_any_sync(full, key);
+        if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&cov[key], __popc(m));
+        if (live) { k++; live = k < K && bpkey[k] < ke; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -522,7 +585,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->dc_match_ref.release(); ctx->dc_match_read.release(); ctx->dc_res0.release(); ctx->dc_rev.release();
     ctx->d_trigger.release(); ctx->d_rest.release(); ctx->d_rest2.release(); ctx->d_restkey.release(); ctx->d_restkey2.release();
     ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
-    ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
+    ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
@@ -547,6 +610,23 @@ float sqg_phase_ms(const sqg_ctx *ctx, const char *name) {
     return ms;
 }
 int64_t sqg_launch_count(const sqg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
+    if (!ctx || !name) return -1;
+    const std::string n(name);
+    if (n == "islands") return ctx->n_islands;
+    if (n == "heavy_islands") return ctx->n_heavy;
+    if (n == "cov_chain_fallback") return ctx->cov_chain_fallback;
+    if (n == "gap_records") return ctx->n_gap;
+    if (n == "partial_records") return ctx->n_pc;
+    if (n == "displaced_records") return ctx->n_dp;
+    if (n == "lmax") return ctx->lmax;
+    if (n == "groups") return (int64_t)ctx->pre.groups.size();
+    if (n == "disc_blocks") return (int64_t)ctx->pre.disc.size() - 1;
+    if (n == "sensitive_reads") return ctx->n_sensitive;
+    if (n == "raw_edges") return ctx->n_raw_edges;
+    if (n == "r_break") return ctx->r_break;
+    return -1;
+}
 
 }  // extern "C"
 
@@ -823,7 +903,8 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     CK(ctx->d_isl_nout.ensure(n_isl + 1)); CK(ctx->d_isl_gdone.ensure(n_isl + 1));
     CK(cudaMemsetAsync(ctx->d_cap_ops.p, 0, (n_isl + 2) * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->d_cap_mar.p, 0, (n_isl + 2) * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_isl_nout.p, 0, (n_isl + 1) * 4, ctx->stream));
-    LAUNCH(k_island_caps, blocks_for(n_isl, 64), 64, in, ctx->d_isl.p, n_isl, ctx->d_cap_ops.p, ctx->d_cap_mar.p);
+    CK(ctx->d_span.ensure(n_isl + 2)); CK(ctx->d_heavy.ensure(n_isl + 2)); CK(ctx->d_light.ensure(n_isl + 2));
+    LAUNCH(k_island_caps, blocks_for(n_isl, 64), 64, in, ctx->d_isl.p, n_isl, ctx->d_cap_ops.p, ctx->d_cap_mar.p, ctx->d_span.p);
     {
         size_t tb = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_cap_ops.p, ctx->d_off_ops.p, n_isl + 1, ctx->stream));
@@ -839,10 +920,26 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     CK(ctx->d_ops.ensure(tot[0] + 1)); CK(ctx->d_margin.ensure(tot[1] + 1));
     int32_t *d_err = (int32_t *)(ctx->d_counters.p + 7), *d_nprefix = (int32_t *)(ctx->d_counters.p + 6);
     CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, 2 * sizeof(int64_t), ctx->stream));
-    LAUNCH(k_seed_islands, 1, 1, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
-           ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, d_nprefix, 0);
-    LAUNCH(k_seed_islands, blocks_for(n_isl, 32), 32, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
-           ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, d_nprefix, 1);
+    LAUNCH(k_seed_prefix, 1, kSeedBlock, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
+           ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, d_nprefix);
+    {
+        cub::CountingInputIterator<int32_t> cnt(0);
+        size_t tb = 0;
+        IsHeavyOp oh{ctx->d_span.p, d_nprefix, true}, ol{ctx->d_span.p, d_nprefix, false};
+        int32_t *d_nh = (int32_t *)(ctx->d_counters.p + 13);
+        CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_heavy.p, d_nh, n_isl, oh, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_heavy.p, d_nh, n_isl, oh, ctx->stream));
+        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_light.p, d_nh + 1, n_isl, ol, ctx->stream));
+        ctx->launches += 3;
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 13, ctx->d_counters.p + 13, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const int32_t n_heavy = ((int32_t *)(ctx->h_counters.p + 13))[0], n_light = ((int32_t *)(ctx->h_counters.p + 13))[1];
+    ctx->n_heavy = n_heavy;
+    if (n_heavy + n_light > 0)
+        LAUNCH(k_seed_islands, (unsigned)(n_heavy + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
+               ctx->d_ops.p, ctx->d_margin.p, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, ctx->d_heavy.p, n_heavy, ctx->d_light.p, n_light);
     PHASE_END("seed");
     // stitch the island op lists in genome order (host: a few hundred thousand ops at most)
     std::vector<int32_t> h_nout(n_isl), h_gdone(n_isl), h_isl(n_isl + 1);
@@ -984,7 +1081,7 @@ extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uin
     cd.rev = ctx->dc_rev.p;
     int64_t cap = std::max<int64_t>((int64_t)ctx->d_ekeys.cap, n / 2 + 4 * ctx->c_n_blk + 2 * ctx->c_n_reads + 4096);
     int64_t n_raw = 0;
-    CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1)); CK(ctx->d_sens.ensure(n + 1));
+    CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1)); CK(ctx->d_sens.ensure(std::max<int64_t>(n, ctx->c_n_reads) + 1));
     PHASE_BEGIN("depth_edges");
     for (int attempt = 0; attempt < 2; attempt++) {
         CK(ctx->d_ekeys.ensure(cap));
@@ -992,25 +1089,33 @@ extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uin
         unsigned long long *d_cnt = (unsigned long long *)(ctx->d_counters.p + 9);
         CK(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t), ctx->stream));
         EdgeSink sink{ctx->d_ekeys.p, cap, d_cnt};
-        EdgeSinkSerial ssink{ctx->d_ekeys.p, cap, d_cnt};
-        if (cd.n_reads > 0) {
-            LAUNCH(k_chim_edges, blocks_for(cd.n_reads), kThreads, cd, ctx->params, ctx->nt, ctx->dc_res0.p, sink);
-            LAUNCH(k_chim_fixup, 1, 1, cd, ctx->params, ctx->nt, ctx->dc_res0.p, ssink);
-        }
-        int32_t n_sens = 0;
-        if (n > 0) {
-            LAUNCH(k_conc_edges, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->params, ctx->nt, ctx->d_scratch32.p, sink);
-            cub::CountingInputIterator<int32_t> cnt(0);
-            IsSensOp op{ctx->d_scratch32.p};
+        int32_t *d_nsens = (int32_t *)(ctx->d_counters.p + 10), *d_left = (int32_t *)(ctx->d_counters.p + 11);
+        cub::CountingInputIterator<int32_t> cnt(0);
+        for (int stream_kind = 0; stream_kind < 2; stream_kind++) {  // 0: chimeric reads (RawEdgesChim), 1: concordant stream (RawEdgesOther)
+            const int64_t cnt_items = stream_kind == 0 ? cd.n_reads : n;
+            int32_t *res0 = stream_kind == 0 ? ctx->dc_res0.p : ctx->d_scratch32.p;
+            if (cnt_items <= 0) continue;
+            if (stream_kind == 0) LAUNCH(k_chim_edges, blocks_for(cnt_items), kThreads, cd, ctx->params, ctx->nt, res0, sink);
+            else LAUNCH(k_conc_edges, blocks_for(cnt_items), kThreads, b, ctx->d_cls.p, ctx->params, ctx->nt, res0, sink);
+            IsSensOp op{res0};
             size_t tb = 0;
-            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_sens.p, (int32_t *)(ctx->d_counters.p + 10), (int)n, op, ctx->stream));
+            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_sens.p, d_nsens, (int)cnt_items, op, ctx->stream));
             ENSURE_TEMP(tb);
-            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_sens.p, (int32_t *)(ctx->d_counters.p + 10), (int)n, op, ctx->stream));
+            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_sens.p, d_nsens, (int)cnt_items, op, ctx->stream));
             ctx->launches += 2;
             CK(cudaMemcpyAsync(ctx->h_counters.p + 10, ctx->d_counters.p + 10, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            n_sens = *(int32_t *)(ctx->h_counters.p + 10);
-            if (n_sens > 0) LAUNCH(k_conc_fixup, 1, 1, b, ctx->params, ctx->nt, ctx->d_scratch32.p, ctx->d_sens.p, n_sens, ssink);
+            const int32_t n_sens = *(int32_t *)(ctx->h_counters.p + 10);
+            ctx->n_sensitive = (stream_kind == 0 ? 0 : ctx->n_sensitive) + n_sens;
+            for (int round = 0; n_sens > 0; round++) {
+                if (round > n_sens + 1) FAIL(SQG_ECUDA, "hint fix-up did not converge");
+                CK(cudaMemsetAsync(d_left, 0, sizeof(int64_t), ctx->stream));
+                if (stream_kind == 0) LAUNCH(k_chim_fixup, blocks_for(n_sens, 64), 64, cd, ctx->params, ctx->nt, res0, ctx->d_sens.p, n_sens, sink, d_left);
+                else LAUNCH(k_conc_fixup, blocks_for(n_sens, 64), 64, b, ctx->params, ctx->nt, res0, ctx->d_sens.p, n_sens, sink, d_left);
+                CK(cudaMemcpyAsync(ctx->h_counters.p + 11, ctx->d_counters.p + 11, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                if (*(int32_t *)(ctx->h_counters.p + 11) == 0) break;
+            }
         }
         CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1019,6 +1124,7 @@ extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uin
         if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge buffer overflow");
         cap = n_raw + 4096;  // rerun with room for everything (chimeric trims are idempotent)
     }
+    ctx->n_raw_edges = n_raw;
     PHASE_END("depth_edges");
     PHASE_BEGIN("edge_sort");
     rc = reduce_edges(ctx, n_raw, nullptr);
@@ -1067,22 +1173,52 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
     const int64_t n = b.n_rec;
     PHASE_BEGIN("coverage");
     CK(ctx->d_bpchr.ensure(K)); CK(ctx->d_bppos.ensure(K)); CK(ctx->d_bpkey.ensure(K)); CK(ctx->d_r0.ensure(K)); CK(ctx->d_t.ensure(K)); CK(ctx->d_cov.ensure(K));
-    CK(ctx->d_covM.ensure(n + 1));
+    CK(ctx->d_sens.ensure(n + 1));
     CK(cudaMemcpyAsync(ctx->d_bpchr.p, bp_chr, K * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_bppos.p, bp_pos, K * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_cov.p, 0, K * 4, ctx->stream));
+    int64_t nq = 0;
+    int32_t *qidx = ctx->d_sens.p;  // qualifying records (right-hand mates that pass the gate, :3136-3142), ascending
     if (n > 0) {
         cub::CountingInputIterator<int32_t> cnt(0);
-        cub::TransformInputIterator<uint64_t, CoverKeyOp, cub::CountingInputIterator<int32_t>> it(cnt, CoverKeyOp{b, ctx->d_cls.p});
+        CoverQualOp qop{b, ctx->d_cls.p};
         size_t tb = 0;
-        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, it, ctx->d_covM.p, MaxU64(), (int)n, ctx->stream));
+        CK(cub::DeviceSelect::If(nullptr, tb, cnt, qidx, (int32_t *)(ctx->d_counters.p + 12), (int)n, qop, ctx->stream));
         ENSURE_TEMP(tb);
-        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, it, ctx->d_covM.p, MaxU64(), (int)n, ctx->stream));
+        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, qidx, (int32_t *)(ctx->d_counters.p + 12), (int)n, qop, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        nq = *(int32_t *)(ctx->h_counters.p + 12);
         ctx->launches += 2;
     }
-    LAUNCH(k_cov_r0, blocks_for(K), kThreads, ctx->d_covM.p, n, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_bpkey.p, ctx->d_r0.p);
-    LAUNCH(k_cov_chain, 1, 1, b, ctx->d_cls.p, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
-    if (n > 0) LAUNCH(k_cov_count, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
+    CK(ctx->d_covM.ensure(nq + 1));
+    CoverRankKeyOp kop{b, qidx};
+    if (nq > 0) {  // running maximum of the fragment-start keys in rank space
+        cub::CountingInputIterator<int32_t> cnt(0);
+        cub::TransformInputIterator<uint64_t, CoverRankKeyOp, cub::CountingInputIterator<int32_t>> it(cnt, kop);
+        size_t tb = 0;
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, it, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, it, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
+        ctx->launches += 2;
+    }
+    LAUNCH(k_cov_r0, blocks_for(K), kThreads, ctx->d_covM.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_bpkey.p, ctx->d_r0.p, ctx->d_t.p);
+    {   // t[k] = max(r0[k], t[k-1]+1) whenever the qualifying record right after t[k-1] passes breakpoint k (the common case):
+        // a max-plus prefix scan, verified in parallel; the literal one-step-per-record chain runs only if a candidate fails
+        size_t tb = 0;
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_t.p, ctx->d_t.p, MaxI64(), (int)K, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_t.p, ctx->d_t.p, MaxI64(), (int)K, ctx->stream));
+        ctx->launches += 2;
+        CK(cudaMemsetAsync(ctx->d_counters.p + 12, 0, sizeof(int64_t), ctx->stream));
+        LAUNCH(k_cov_verify, blocks_for(K), kThreads, kop, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (int32_t *)(ctx->d_counters.p + 12));
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->cov_chain_fallback = *(int32_t *)(ctx->h_counters.p + 12) != 0;
+        if (ctx->cov_chain_fallback)
+            LAUNCH(k_cov_chain, 1, 1, kop, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
+    }
+    if (nq > 0) LAUNCH(k_cov_count, blocks_for(nq), kThreads, b, qidx, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
     PHASE_END("coverage");
     CK(cudaMemcpyAsync(cov_out, ctx->d_cov.p, K * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

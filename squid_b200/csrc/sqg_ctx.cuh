@@ -102,7 +102,10 @@ struct sqg_ctx {
     sq::DBuf<sq::SeedOp> d_ops;
     sq::HBuf<sq::SeedOp> h_ops;
     sq::DBuf<uint8_t> d_cutflag;
-    sq::DBuf<int32_t> d_isl, d_cap_ops, d_cap_mar, d_isl_nout, d_isl_gdone;
+    sq::DBuf<int32_t> d_isl, d_cap_ops, d_cap_mar, d_isl_nout, d_isl_gdone, d_span, d_heavy, d_light;
+    int32_t n_heavy = 0;
+    bool cov_chain_fallback = false;
+    int64_t n_sensitive = 0, n_raw_edges = 0;
     sq::DBuf<int64_t> d_off_ops, d_off_mar;
     sq::DBuf<int32_t> d_margin;
     sq::DBuf<sq::SeedState> d_seedstate;
