@@ -102,7 +102,9 @@ int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *batch, int64_t first_reco
 /* Same, but the arrays of `batch` are DEVICE pointers that the caller keeps alive until sqg_destroy(). */
 int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *batch, int64_t first_record_index);
 
-/* Replaces the Chimrecord argument of BuildNode_STAR/BuildEdges (SegmentGraph.cpp:192, 1932). */
+/* Replaces the Chimrecord argument of BuildNode_STAR/BuildEdges (SegmentGraph.cpp:192, 1932).  The arrays of `chim` must
+ * stay valid and unmodified until sqg_build_nodes() or sqg_build_edges() has returned: the chimeric pre-pass
+ * (SegmentGraph.cpp:196-264) reads them on a host thread while the stream works on the concordant batch. */
 int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *chim);
 
 /*

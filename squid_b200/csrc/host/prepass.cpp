@@ -5,100 +5,105 @@
 
 namespace sqh {
 namespace {
-struct B {  // one chimeric block with the fields the pre-pass reads
-    int32_t chr, pos, rpos, mref, mread;
-    bool rev, first;
+// one chimeric read as index ranges over the flat block arrays of sqg_chimeric: FirstRead = [f0,f1), SecondMate = [f1,s1)
+struct View {
+    const sqg_chimeric &c;
+    uint32_t f0, f1, s1;
+    int32_t chr(uint32_t k) const { return c.blk_ref_id[k]; }
+    int32_t pos(uint32_t k) const { return c.blk_ref_pos[k]; }
+    int32_t rpos(uint32_t k) const { return c.blk_read_pos[k]; }
+    int32_t mref(uint32_t k) const { return c.blk_match_ref[k]; }
+    int32_t mread(uint32_t k) const { return c.blk_match_read[k]; }
+    bool rev(uint32_t k) const { return c.blk_is_reverse[k] != 0; }
 };
-struct R {
-    std::vector<B> F, S;
-    int32_t ft, st_;
-    bool fl, sl, mf;
-};
-bool end_disc(const std::vector<B> &v) {  // ReadRec.cpp:178-209
-    for (size_t i = 0; i + 1 < v.size(); i++) {
-        if (v[i].chr != v[i + 1].chr || v[i].rev != v[i + 1].rev) return true;
-        const bool a = v[i].pos < v[i + 1].pos, r = v[i].rpos < v[i + 1].rpos;
-        if (!v[i].rev && a != r) return true;
-        if (v[i].rev && a == r) return true;
+bool end_disc(const View &v, uint32_t a, uint32_t b) {  // ReadRec.cpp:178-209 on blocks [a,b)
+    for (uint32_t i = a; i + 1 < b; i++) {
+        if (v.chr(i) != v.chr(i + 1) || v.rev(i) != v.rev(i + 1)) return true;
+        const bool x = v.pos(i) < v.pos(i + 1), r = v.rpos(i) < v.rpos(i + 1);
+        if (!v.rev(i) && x != r) return true;
+        if (v.rev(i) && x == r) return true;
     }
     return false;
 }
-bool pair_disc(const R &r) {  // ReadRec.cpp:211-228 with needcheck=true
-    if (r.F.empty() || r.S.empty()) return false;
-    if (end_disc(r.F) || end_disc(r.S)) return true;
-    const B &ff = r.F.front(), &fb = r.F.back(), &sf = r.S.front(), &sb = r.S.back();
-    if (ff.chr != sb.chr || ff.rev == sb.rev) return true;
-    if (!ff.rev && ff.pos - ff.rpos > sb.pos - (r.st_ - sb.rpos - sb.mread)) return true;
-    if (!sf.rev && sf.pos - sf.rpos > fb.pos - (r.ft - fb.rpos - fb.mread)) return true;
+bool pair_disc(const View &v, int32_t ft, int32_t st_) {  // ReadRec.cpp:211-228 with needcheck=true
+    if (v.f0 == v.f1 || v.f1 == v.s1) return false;
+    if (end_disc(v, v.f0, v.f1) || end_disc(v, v.f1, v.s1)) return true;
+    const uint32_t ff = v.f0, fb = v.f1 - 1, sf = v.f1, sb = v.s1 - 1;
+    if (v.chr(ff) != v.chr(sb) || v.rev(ff) == v.rev(sb)) return true;
+    if (!v.rev(ff) && v.pos(ff) - v.rpos(ff) > v.pos(sb) - (st_ - v.rpos(sb) - v.mread(sb))) return true;
+    if (!v.rev(sf) && v.pos(sf) - v.rpos(sf) > v.pos(fb) - (ft - v.rpos(fb) - v.mread(fb))) return true;
     return false;
 }
-sq::DiscBlock as_disc(const B &b) { return sq::DiscBlock{b.chr, b.pos, b.mref, b.rev ? 1 : 0}; }
 }  // namespace
 
 void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out) {
     out = ChimPrepass();
-    struct DB { sq::DiscBlock d; int32_t rpos, mread; bool first; };
+    struct DB { uint64_t key; uint32_t k; };  // key = (RefID,RefPos) packed, k = block index
     std::vector<DB> dis;
+    dis.reserve((size_t)c.n_blk);
     std::vector<std::pair<int, int>> part((size_t)n_ref, std::make_pair(0, 0));  // resize()d then appended (:203-204)
-    auto push_dis = [&](const B &b) { dis.push_back(DB{as_disc(b), b.rpos, b.mread, b.first}); };
+    auto push_dis = [&](uint32_t k) { dis.push_back(DB{((uint64_t)(uint32_t)c.blk_ref_id[k] << 32) | (uint32_t)c.blk_ref_pos[k], k}); };
     for (int64_t i = 0; i < c.n_reads; i++) {
-        R r;
         const uint32_t o = c.read_off[i], e = c.read_off[i + 1], nf = c.n_first[i];
-        for (uint32_t k = o; k < e; k++) {
-            B b{c.blk_ref_id[k], c.blk_ref_pos[k], c.blk_read_pos[k], c.blk_match_ref[k], c.blk_match_read[k], c.blk_is_reverse[k] != 0, k - o < nf};
-            (k - o < nf ? r.F : r.S).push_back(b);
-        }
-        r.ft = c.first_total_len[i]; r.st_ = c.second_total_len[i];
-        r.fl = c.first_lowphred[i]; r.sl = c.second_lowphred[i]; r.mf = c.multi_filter[i];
-        const bool single = (r.F.empty() || r.S.empty()) && !r.mf;
-        if (end_disc(r.F) || end_disc(r.S) || single || pair_disc(r)) {  // :208-213
-            for (const B &b : r.F) push_dis(b);
-            for (const B &b : r.S) push_dis(b);
+        const View v{c, o, o + nf, e};
+        const int32_t ft = c.first_total_len[i], st_ = c.second_total_len[i];
+        const bool fl = c.first_lowphred[i], sl = c.second_lowphred[i], mf = c.multi_filter[i];
+        const bool fempty = v.f0 == v.f1, sempty = v.f1 == v.s1;
+        const bool single = (fempty || sempty) && !mf;
+        if (end_disc(v, v.f0, v.f1) || end_disc(v, v.f1, v.s1) || single || pair_disc(v, ft, st_)) {  // :208-213
+            for (uint32_t k = o; k < e; k++) push_dis(k);
             continue;
         }
         bool fin = false, sin = false;
         for (int m = 0; m < 2; m++) {  // blocks of one mate more than 750 kb apart (:217-239)
-            const std::vector<B> &v = m ? r.S : r.F;
-            int prev = -1;
-            for (int k = 0; k + 1 < (int)v.size(); k++)
-                if (std::abs(v[k].pos - v[k + 1].pos) > 750000) {
-                    if (prev != k) push_dis(v[k]);
-                    push_dis(v[k + 1]);
+            const uint32_t a = m ? v.f1 : v.f0, b = m ? v.s1 : v.f1;
+            int64_t prev = -1;
+            for (uint32_t k = a; k + 1 < b; k++)
+                if (std::abs(v.pos(k) - v.pos(k + 1)) > 750000) {
+                    if (prev != (int64_t)k) push_dis(k);
+                    push_dis(k + 1);
                     prev = k + 1;
-                    if (k + 1 == (int)v.size() - 1) (m ? sin : fin) = true;
+                    if (k + 1 == b - 1) (m ? sin : fin) = true;
                 }
         }
-        if (!r.F.empty() && !r.S.empty() && std::abs(r.F.back().pos - r.S.back().pos) > 750000) {  // :240-249
-            if (!fin) { push_dis(r.F.back()); fin = true; }
-            if (!sin) { push_dis(r.S.back()); sin = true; }
+        if (!fempty && !sempty && std::abs(v.pos(v.f1 - 1) - v.pos(v.s1 - 1)) > 750000) {  // :240-249
+            if (!fin) { push_dis(v.f1 - 1); fin = true; }
+            if (!sin) { push_dis(v.s1 - 1); sin = true; }
         }
         if (!fin && !sin) {  // soft-clipped ends of otherwise concordant chimeric reads (:250-259)
-            if (!r.F.empty() && r.F.front().rpos > 15 && !r.fl)
-                part.push_back({r.F[0].chr, r.F[0].rev ? r.F[0].pos + r.F[0].mref : r.F[0].pos});
-            if (!r.F.empty() && r.ft - r.F.back().rpos - r.F.back().mread > 15 && !r.fl)
-                part.push_back({r.F.back().chr, r.F.back().rev ? r.F.back().pos : r.F.back().pos + r.F.back().mref});
-            if (!r.S.empty() && r.S.front().rpos > 15 && !r.sl)
-                part.push_back({r.S[0].chr, r.S[0].rev ? r.S[0].pos + r.S[0].mref : r.S[0].pos});
-            if (!r.S.empty() && r.st_ - r.S.back().rpos - r.S.back().mread > 15 && !r.sl) {
-                // `!bamdiscordant.back().Same(SecondMate.back())` (:257); back() of an empty vector is UB in the
-                // reference, we read it as "not the same"
-                const B &sb = r.S.back();
-                bool same = false;
-                if (!dis.empty()) {
-                    const DB &l = dis.back();
-                    same = l.d.chr == sb.chr && l.d.pos == sb.pos && l.rpos == sb.rpos && l.mread == sb.mread && l.d.len == sb.mref &&
-                           (l.d.rev != 0) == sb.rev && l.first == sb.first;
+            if (!fempty && v.rpos(v.f0) > 15 && !fl) part.push_back({v.chr(v.f0), v.rev(v.f0) ? v.pos(v.f0) + v.mref(v.f0) : v.pos(v.f0)});
+            if (!fempty) { const uint32_t b = v.f1 - 1; if (ft - v.rpos(b) - v.mread(b) > 15 && !fl) part.push_back({v.chr(b), v.rev(b) ? v.pos(b) : v.pos(b) + v.mref(b)}); }
+            if (!sempty && v.rpos(v.f1) > 15 && !sl) part.push_back({v.chr(v.f1), v.rev(v.f1) ? v.pos(v.f1) + v.mref(v.f1) : v.pos(v.f1)});
+            if (!sempty) {
+                const uint32_t b = v.s1 - 1;
+                if (st_ - v.rpos(b) - v.mread(b) > 15 && !sl) {
+                    // `!bamdiscordant.back().Same(SecondMate.back())` (:257); back() of an empty vector is UB in the
+                    // reference, we read it as "not the same".  Same() compares every field incl. IsFirstRead.
+                    bool same = false;
+                    if (!dis.empty()) {
+                        const uint32_t l = dis.back().k;
+                        // which read does block l belong to? only its IsFirstRead matters: l is a SecondMate block iff it
+                        // lies at/after the first SecondMate block of its own read; find that read by binary search
+                        const uint32_t *ro = c.read_off;
+                        int64_t lo = 0, hi = c.n_reads;
+                        while (lo < hi) { const int64_t m2 = (lo + hi) >> 1; if (ro[m2 + 1] <= l) lo = m2 + 1; else hi = m2; }
+                        const bool l_first = l - ro[lo] < c.n_first[lo];
+                        same = v.chr(l) == v.chr(b) && v.pos(l) == v.pos(b) && v.rpos(l) == v.rpos(b) && v.mread(l) == v.mread(b) &&
+                               v.mref(l) == v.mref(b) && v.rev(l) == v.rev(b) && l_first == false;
+                    }
+                    if (!same) part.push_back({v.chr(b), v.rev(b) ? v.pos(b) : v.pos(b) + v.mref(b)});
                 }
-                if (!same) part.push_back({sb.chr, sb.rev ? sb.pos : sb.pos + sb.mref});
             }
         }
     }
     std::sort(part.begin(), part.end(), [](std::pair<int, int> a, std::pair<int, int> b) { return a.first == b.first ? a.second < b.second : a.first < b.first; });
-    // same unstable sort, same key, same sequence as :264 => same order among equal (RefID,RefPos)
-    std::sort(dis.begin(), dis.end(), [](const DB &a, const DB &b) { return a.d.chr != b.d.chr ? a.d.chr < b.d.chr : a.d.pos < b.d.pos; });
+    // Same unstable std::sort, same ordering relation, same input sequence as :264 => the same permutation, including
+    // the order among equal (RefID,RefPos) which the sub-cluster walk observes.  The packed key
+    // compares exactly like operator< of SingleBamRec_t (RefID, RefPos are non-negative here).
+    std::sort(dis.begin(), dis.end(), [](const DB &a, const DB &b) { return a.key < b.key; });
     for (auto &p : part) { out.part_chr.push_back(p.first); out.part_pos.push_back(p.second); }
     out.disc.reserve(dis.size() + 1);
-    for (const DB &d : dis) out.disc.push_back(d.d);
+    for (const DB &d : dis) out.disc.push_back(sq::DiscBlock{c.blk_ref_id[d.k], c.blk_ref_pos[d.k], c.blk_match_ref[d.k], c.blk_is_reverse[d.k] ? 1 : 0});
     const int32_t n = (int32_t)dis.size();
     out.disc.push_back(sq::DiscBlock{0, 0, 0, 0});
     for (int32_t s = 0; s < n;) {  // :341-348 chain while the next block starts within ReadLen of the running right end

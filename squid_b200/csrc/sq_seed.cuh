@@ -85,6 +85,8 @@ struct CoopSerial {  // one lane (CPU stepping harness, tiny islands)
     static SQ_HD int max(int v) { return v; }
     static SQ_HD int min(int v) { return v; }
     static SQ_HD int excl_prefix_max(int v, int identity) { (void)v; return identity; }
+    static SQ_HD int excl_prefix_sum(int v) { (void)v; return 0; }
+    static SQ_HD void add(int32_t *p, int32_t v) { *p += v; }
     static SQ_HD void sync() {}
 };
 #if defined(__CUDACC__)
@@ -100,6 +102,13 @@ struct CoopWarp {  // 32 lanes of one warp
         const int e = __shfl_up_sync(0xffffffffu, v, 1);
         return l == 0 ? identity : e;
     }
+    static __device__ __forceinline__ int excl_prefix_sum(int v) {
+        const int l = threadIdx.x & 31;
+        int incl = v;
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (l >= d) incl += o; }
+        return incl - v;
+    }
+    static __device__ __forceinline__ void add(int32_t *p, int32_t v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): for the few islands with huge windows
@@ -138,6 +147,19 @@ struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): 
         __syncthreads();
         return excl > base ? excl : base;
     }
+    static __device__ __forceinline__ int excl_prefix_sum(int v) {
+        __shared__ int wsum[32];
+        const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int incl = v;
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (l >= d) incl += o; }
+        if (l == 31) wsum[w] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int k = 0; k < w; k++) base += wsum[k];
+        __syncthreads();
+        return base + incl - v;
+    }
+    static __device__ __forceinline__ void add(int32_t *p, int32_t v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 #endif
@@ -202,8 +224,9 @@ struct SeedMachineT {
         else emit(2, st.backChr, e, 0);
         st.backEnd = e;
     }
+    SQ_HD int32_t mcap() const { return margin_cap / 6; }
     SQ_HD void push_margin(int32_t &n, int32_t v) {  // uniform call: every lane counts, lane 0 stores
-        if (n >= margin_cap) { error = 1; return; }
+        if (n + 1 >= mcap()) { error = 1; return; }
         if (W::lane() == 0) margin[n] = v;
         n++;
     }
@@ -212,7 +235,7 @@ struct SeedMachineT {
     SQ_HD void sort_margins(int32_t n) {
         int32_t m = 1;
         while (m < n) m <<= 1;
-        if (m > margin_cap) { error = 1; return; }
+        if (m > mcap()) { error = 1; return; }
         W::sync();
         for (int32_t i = n + W::lane(); i < m; i += W::size()) margin[i] = 0x7fffffff;
         W::sync();
@@ -400,6 +423,95 @@ struct SeedMachineT {
             if (rv && p0 > m0 - thresh && p0 < curEndPos + thresh) push_margin(nM, p0);
             else if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
         }
+    }
+
+    // ---- per-break tables ------------------------------------------------------------------------------------------
+    // For every entry of the sorted MarginPositions array the break loop (:440-504) needs srsupport, peleftfor,
+    // perightrev, the spanning coverage of the windows + discordant blocks, and the ConcordRest coverage.  None of them
+    // depends on what the loop emits, so they are tabulated up front: interval-shaped contributions go into difference
+    // arrays (two binary searches in the margin array each) that are prefix-summed, instead of rescanning the window
+    // for each candidate break.
+    SQ_HD int32_t m_upper(int32_t nM, int32_t v) const {  // first index with margin > v
+        int32_t lo = 0, hi = nM;
+        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (margin[m] <= v) lo = m + 1; else hi = m; }
+        return lo;
+    }
+    SQ_HD int32_t m_lower(int32_t nM, int32_t v) const {  // first index with margin >= v
+        int32_t lo = 0, hi = nM;
+        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (margin[m] < v) lo = m + 1; else hi = m; }
+        return lo;
+    }
+    SQ_HD void add_range(int32_t *diff, int32_t ja, int32_t jb) { if (ja < jb) { W::add(&diff[ja], 1); W::add(&diff[jb], -1); } }
+    // a block [p0,p1) spans break b iff p0 < b-thresh and p1 >= b+thresh  <=>  p0+thresh < b <= p1-thresh
+    SQ_HD void add_span(int32_t *diff, int32_t nM, int32_t p0, int32_t p1) { add_range(diff, m_upper(nM, p0 + kSeedThresh), m_upper(nM, p1 - kSeedThresh)); }
+    SQ_HD void scan_inplace(int32_t *a, int32_t n) {
+        W::sync();
+        int32_t carry = 0;
+        for (int32_t base = 0; base < n; base += W::size()) {
+            const int32_t i = base + W::lane();
+            const int32_t v = i < n ? a[i] : 0;
+            const int32_t ex = W::excl_prefix_sum(v);
+            if (i < n) a[i] = carry + ex + v;
+            carry += W::sum(v);
+        }
+        W::sync();
+    }
+    SQ_HD void tabulate_breaks(int32_t nM, int32_t ds, int32_t de, int32_t chrG, int32_t sPos, int64_t rg, int32_t szPC) {
+        const int32_t thresh = kSeedThresh, RL = in.read_len, cap = mcap();
+        int32_t *t_sr = margin + cap, *t_pl = margin + 2 * cap, *t_pr = margin + 3 * cap, *t_cov = margin + 4 * cap, *t_rest = margin + 5 * cap;
+        const DiscBlock *D = in.D;
+        W::sync();
+        for (int32_t i = W::lane(); i <= nM; i += W::size()) { t_pl[i] = 0; t_pr[i] = 0; t_cov[i] = 0; t_rest[i] = 0; }
+        for (int32_t i = W::lane(); i < nM; i += W::size()) {  // srsupport: margins within +-thresh (:445-448)
+            const int32_t brk = margin[i];
+            t_sr[i] = m_lower(nM, brk + thresh) - m_upper(nM, brk - thresh);
+        }
+        W::sync();
+        for (int32_t k = ds + W::lane(); k < de; k += W::size()) {
+            const int32_t p0 = D[k].pos, p1 = p0 + D[k].len;
+            if (!D[k].rev) add_range(t_pl, m_upper(nM, p1), m_lower(nM, p1 + RL));        // end < b < end+ReadLen   (:450)
+            else add_range(t_pr, m_upper(nM, p0 - RL), m_lower(nM, p0));                // pos-ReadLen < b < pos   (:452)
+            if (D[k].chr == chrG) add_span(t_cov, nM, p0, p1);                            // :462-464
+        }
+        const int32_t bmin = margin[0], bmax = margin[nM - 1];
+        const int32_t pmin = bmin + thresh - in.lmax, pmax = bmax - thresh;  // block starts that can span some break
+        if (st.offCC < rg) {  // ConcordantCluster window (:457-461)
+            const int64_t lo = lb_pos(st.offCC, rg, chrG, pmin), hi = lb_pos(lo, rg, chrG, pmax);
+            for (int64_t r = lo + W::lane(); r < hi; r += W::size())
+                if (isCC(r) && !isDispl(r) && in.b.ref_id[r] == chrG) { const int32_t p0 = e_pos(r); add_span(t_cov, nM, p0, p0 + e_len(r)); }
+        }
+        if (st.offPC < szPC) {  // PartialAlignCluster window (:465-469)
+            const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, pmin), hi = lb_pc_pos(lo, szPC, chrG, pmax);
+            for (int32_t i = lo + W::lane(); i < hi; i += W::size()) {
+                const int64_t r = in.pc_rec[i];
+                if (!isDispl(r) && in.b.ref_id[r] == chrG) { const int32_t p0 = e_pos(r); add_span(t_cov, nM, p0, p0 + e_len(r)); }
+            }
+        }
+        {   // displaced entries of either window
+            const int64_t w0 = st.offCC < rg ? st.offCC : rg;
+            const int64_t wp = st.offPC < szPC ? (int64_t)in.pc_rec[st.offPC] : rg;
+            const int32_t k0 = lb_list(in.dp_rec, in.n_dp, w0 < wp ? w0 : wp), k1 = lb_list(in.dp_rec, in.n_dp, rg);
+            for (int32_t k = k0 + W::lane(); k < k1; k += W::size()) {
+                const int64_t r = in.dp_rec[k];
+                if (in.b.ref_id[r] != chrG) continue;
+                const bool part = in.cls[r] & CLS_PART;
+                if (part ? (r < wp) : (r < st.offCC)) continue;
+                const int32_t p0 = e_pos(r);
+                add_span(t_cov, nM, p0, p0 + e_len(r));
+            }
+        }
+        {   // ConcordRest (:471-473): blocks of records before rg that start at/after group start - ReadLen
+            const int32_t lo_pos = sPos - RL;
+            int32_t lo = 0, hi = in.n_rest;
+            while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
+            int32_t lo2 = lo, hi2 = in.n_rest;
+            while (lo2 < hi2) { int32_t m = (lo2 + hi2) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < pmax)) lo2 = m + 1; else hi2 = m; }
+            for (int32_t k = lo + W::lane(); k < lo2; k += W::size()) {
+                const RestBlock &e = in.rest[k];
+                if (e.rec < rg) add_span(t_rest, nM, e.pos, e.end);
+            }
+        }
+        scan_inplace(t_pl, nM); scan_inplace(t_pr, nM); scan_inplace(t_cov, nM); scan_inplace(t_rest, nM);
     }
 
     // flag1/flag2 of the two walks at :536-601 for an entry (c,p0,p1); dc = first discordant block not covered yet
@@ -618,31 +730,18 @@ struct SeedMachineT {
             if (error) return;
             sort_margins(nM);
             if (error) return;
+            tabulate_breaks(nM, ds, de, chrG, in.D[grp.ds].pos, rg, szPC);
+            const int32_t *t_sr = margin + mcap(), *t_pl = margin + 2 * mcap(), *t_pr = margin + 3 * mcap(), *t_cov = margin + 4 * mcap(), *t_rest = margin + 5 * mcap();
             int32_t lastCurser = -1, lastSupport = 0;
             for (int32_t ib = 0; ib < nM;) {
                 const int32_t brk = margin[ib];
                 if (st.have_back && st.backChr == chrG && brk - st.backEnd < thresh * 20) { ib++; continue; }
-                int32_t sr = 0, pl = 0, pr = 0;
-                {   // margins within +-thresh of brk (the array is sorted)
-                    int32_t k = ib;
-                    while (k > 0 && brk - margin[k - 1] < thresh) k--;
-                    for (; k < nM && margin[k] < brk + thresh; k++) sr++;
-                }
-                for (int32_t k = ds + W::lane(); k < de; k += W::size()) {
-                    const int32_t e1 = D[k].pos + D[k].len;
-                    if (e1 < brk && e1 > brk - RL && !D[k].rev) pl++;
-                    else if (D[k].pos > brk && D[k].pos < brk + RL && D[k].rev) pr++;
-                }
-                pl = W::sum(pl); pr = W::sum(pr);
+                const int32_t sr = t_sr[ib], pl = t_pl[ib], pr = t_pr[ib];
                 if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
-                    int32_t coverage = window_coverage(chrG, brk, rg, szPC);
-                    int32_t dcov = 0;
-                    for (int32_t k = ds + W::lane(); k < de; k += W::size())
-                        if (D[k].chr == chrG && D[k].pos + D[k].len >= brk + thresh && D[k].pos < brk - thresh) dcov++;
-                    coverage += W::sum(dcov);
+                    int32_t coverage = t_cov[ib];
                     int32_t rest = coverage - sr; if (rest < 0) rest = 0;
                     if (sr > rest + 2) {
-                        coverage += rest_coverage(chrG, in.D[grp.ds].pos, brk, rg);
+                        coverage += t_rest[ib];
                         rest = coverage - sr; if (rest < 0) rest = 0;
                     }
                     if (sr > rest + 2) {

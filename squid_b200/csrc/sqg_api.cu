@@ -217,9 +217,16 @@ __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n
     mmax += (ndp > 0 ? ndp : 0) + 16;
     cap_ops[i] = 4 * (in.G[gb - 1].de - in.G[ga].ds) + 2 * mmax + 64;
     int32_t pw = 1;
-    while (pw < mmax) pw <<= 1;  // sort_margins pads to a power of two
-    cap_mar[i] = pw;
-    span[i] = (int32_t)((r1 - r0) > 0x7fffffff ? 0x7fffffff : (r1 - r0));  // records the island may have to walk
+    while (pw < mmax + 2) pw <<= 1;  // sort_margins pads to a power of two; + the five per-break tables
+    cap_mar[i] = 6 * pw;
+    int64_t w0 = r0;  // the windows were emptied at the last 0-coverage record before the island's first group
+    if (ga > 0) {
+        int32_t cc, cr;
+        const Group gp = in.G[ga - 1], gn = in.G[ga];
+        const int32_t z = sm.last_is0(in.trigger[ga - 1], in.trigger[ga] < in.n_rec ? in.trigger[ga] : in.n_rec, gp.chr, gp.right, gn.chr, in.D[gn.ds].pos, &cc, &cr);
+        if (z >= 0) w0 = in.gap_rec[z];
+    }
+    span[i] = (int32_t)((r1 - w0) > 0x7fffffff ? 0x7fffffff : (r1 - w0));  // records the island may have to walk
 }
 constexpr int kSeedBlock = 512;        // threads per block of the seed kernels
 constexpr int kHeavySpan = 1 << 14;    // islands spanning more records than this get a whole block instead of a warp
@@ -509,20 +516,42 @@ __global__ void k_cov_verify(CoverRankKeyOp key, int64_t nq, const int32_t *bp_c
         if (!(key((int32_t)c) > T)) *fail = 1;
     }
 }
-// literal chain (:3157-3158), only when the verification above fails
+// Literal chain (:3157-3158), used when the verification above fails: indBP advances by at most one per qualifying
+// record, so t[k] = first rank c > t[k-1] whose key passes breakpoint k.  One warp: the lanes prefetch r0/T of 32
+// breakpoints and a 32-wide window of record keys; the steps themselves run on shuffled registers.
 __global__ void k_cov_chain(CoverRankKeyOp key, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, const int64_t *r0, int64_t *t) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     int64_t tp = -1;
-    for (int64_t k = 0; k < K; k++) {
-        int64_t c;
-        if (r0[k] > tp) c = r0[k];
-        else {
-            const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
-            c = tp + 1;
-            while (c < nq && !(key((int32_t)c) > T)) c++;
+    int64_t wbase = -64;       // ranks [wbase, wbase+32) are held in wkey
+    uint64_t wkey = 0;
+    for (int64_t kb = 0; kb < K; kb += 32) {
+        const int64_t k = kb + lane;
+        const int64_t my_r0 = k < K ? r0[k] : nq;
+        const uint64_t my_T = k < K ? chrpos_key(bp_chr[k], bp_pos[k] + dist) : ~0ull;
+        int64_t my_t = 0;
+        const int cnt = (int)((K - kb) < 32 ? (K - kb) : 32);
+        for (int j = 0; j < cnt; j++) {
+            const int64_t r0j = __shfl_sync(0xffffffffu, my_r0, j);
+            const uint64_t Tj = __shfl_sync(0xffffffffu, my_T, j);
+            int64_t c;
+            if (r0j > tp) c = r0j;
+            else {
+                c = tp + 1;
+                while (c < nq) {
+                    if (c < wbase || c >= wbase + 32) {
+                        wbase = c;
+                        wkey = (c + lane < nq) ? key((int32_t)(c + lane)) : ~0ull;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, wbase + lane >= c && wkey > Tj);
+                    if (m) { c = wbase + (__ffs(m) - 1); break; }
+                    c = wbase + 32;
+                }
+            }
+            if (lane == j) my_t = c;
+            tp = c < nq ? c : nq;
         }
-        t[k] = c;
-        tp = c < nq ? c : nq;
+        if (k < K) t[k] = my_t;
     }
 }
 __global__ void k_cov_count(DevBatch b, const int32_t *qidx, int64_t nq, const uint64_t *bpkey, const int64_t *t, int64_t K, int32_t *cov) {
@@ -572,6 +601,7 @@ int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int
 
 void sqg_destroy(sqg_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->prepass_thread.joinable()) ctx->prepass_thread.join();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     // DBuf/HBuf members are plain pointers: release explicitly
@@ -630,14 +660,22 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
 
 }  // extern "C"
 
-static int validate_batch(sqg_ctx *ctx) {
-    CK(ctx->d_counters.ensure(16));
-    CK(ctx->h_counters.ensure(16));
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int64_t), ctx->stream));
-    if (ctx->batch.n_rec > 0) LAUNCH(k_validate, blocks_for(ctx->batch.n_rec), kThreads, ctx->batch, ctx->params.n_ref, (int32_t *)ctx->d_counters.p);
-    CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+// The validation kernel is enqueued at load time; its verdict is read at the first synchronisation of a later call
+// (or right away for pageable host input), so that the host->device copies overlap the host-side chimeric pre-pass.
+static int validate_enqueue(sqg_ctx *ctx) {
+    CK(ctx->d_counters.ensure(32));
+    CK(ctx->h_counters.ensure(32));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 32 * sizeof(int64_t), ctx->stream));
+    if (ctx->batch.n_rec > 0) LAUNCH(k_validate, blocks_for(ctx->batch.n_rec), kThreads, ctx->batch, ctx->params.n_ref, (int32_t *)(ctx->d_counters.p + 20));
+    CK(cudaMemcpyAsync(ctx->h_counters.p + 20, ctx->d_counters.p + 20, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->validated = false;
+    return SQG_OK;
+}
+static int validate_check(sqg_ctx *ctx) {
+    if (ctx->validated) return SQG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
-    const int32_t flags = *(int32_t *)ctx->h_counters.p;
+    ctx->validated = true;
+    const int32_t flags = *(int32_t *)(ctx->h_counters.p + 20);
     if (flags & 1) FAIL(SQG_EINVAL, "record with ref_id outside [-1, n_ref)");
     if (flags & 2) FAIL(SQG_EUNSUPPORTED, "mapped record with ref_id -1");
     if (flags & 4) FAIL(SQG_EUNSUPPORTED, "record with more than 16 aligned blocks or a decreasing blk_off");
@@ -669,7 +707,7 @@ extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t fi
     b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
     PHASE_END("h2d");
     ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->first_record_index = first_record_index;
-    return validate_batch(ctx);
+    return validate_enqueue(ctx);
 }
 
 extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, int64_t first_record_index) {
@@ -682,7 +720,7 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     b.flag = db->flag; b.total_len = db->total_len; b.lowphred_run = db->lowphred_run; b.mapq = db->mapq; b.aux = db->aux;
     b.blk_off = db->blk_off; b.blk_ref_pos = db->blk_ref_pos; b.blk_match_ref = db->blk_match_ref; b.blk_read_pos = db->blk_read_pos; b.blk_match_read = db->blk_match_read;
     ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->first_record_index = first_record_index;
-    return validate_batch(ctx);
+    return validate_enqueue(ctx);
 }
 
 extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
@@ -692,27 +730,40 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
         const uint32_t nb = c->read_off[i + 1] - c->read_off[i], nf = c->n_first[i];
         if (nf > nb || nf > (uint32_t)kMaxBlocks || nb - nf > (uint32_t)kMaxBlocks) FAIL(SQG_EUNSUPPORTED, "chimeric read with more than 16 blocks in one mate");
     }
-    sqh::chimeric_prepass(*c, ctx->params.n_ref, ctx->params.read_len, ctx->pre);
+    // The chimeric pre-pass (BuildNode_STAR part A, host std::sort for tie-order fidelity) runs on a host thread while the
+    // stream copies and classifies the concordant batch; it is joined in sqg_build_nodes / sqg_build_edges.
+    if (ctx->prepass_thread.joinable()) ctx->prepass_thread.join();
+    ctx->chim_view = *c;
+    ctx->prepass_thread = std::thread([ctx]() { sqh::chimeric_prepass(ctx->chim_view, ctx->params.n_ref, ctx->params.read_len, ctx->pre); });
+    ctx->prepass_uploaded = false;
     ctx->c_n_reads = c->n_reads; ctx->c_n_blk = c->n_blk;
     const size_t nr = (size_t)c->n_reads, nb = (size_t)c->n_blk;
-    const size_t nD1 = ctx->pre.disc.size(), nG = ctx->pre.groups.size(), nP = ctx->pre.part_chr.size();
 #define UPV(buf, src, cnt)                                                                                     \
     do {                                                                                                       \
         CK(ctx->buf.ensure((cnt) ? (cnt) : 1));                                                                \
         if (cnt) CK(cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream)); \
     } while (0)
-    UPV(d_disc, ctx->pre.disc.data(), nD1); UPV(d_groups, ctx->pre.groups.data(), nG);
-    UPV(d_pchr, ctx->pre.part_chr.data(), nP); UPV(d_ppos, ctx->pre.part_pos.data(), nP);
     UPV(dc_read_off, c->read_off, nr + 1); UPV(dc_n_first, c->n_first, nr);
     UPV(dc_first_total, c->first_total_len, nr); UPV(dc_second_total, c->second_total_len, nr);
     UPV(dc_ref_id, c->blk_ref_id, nb); UPV(dc_ref_pos, c->blk_ref_pos, nb); UPV(dc_read_pos, c->blk_read_pos, nb);
     UPV(dc_match_ref, c->blk_match_ref, nb); UPV(dc_match_read, c->blk_match_read, nb); UPV(dc_rev, c->blk_is_reverse, nb);
-#undef UPV
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_chim = true;
     return SQG_OK;
 }
 
+// join the host pre-pass and put its products (discordant blocks, groups, PartAlignPos) into HBM
+static int finish_prepass(sqg_ctx *ctx) {
+    if (ctx->prepass_thread.joinable()) ctx->prepass_thread.join();
+    if (ctx->prepass_uploaded) return SQG_OK;
+    const size_t nD1 = ctx->pre.disc.size(), nG = ctx->pre.groups.size(), nP = ctx->pre.part_chr.size();
+    UPV(d_disc, ctx->pre.disc.data(), nD1); UPV(d_groups, ctx->pre.groups.data(), nG);
+    UPV(d_pchr, ctx->pre.part_chr.data(), nP); UPV(d_ppos, ctx->pre.part_pos.data(), nP);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prepass_uploaded = true;
+    return SQG_OK;
+}
+#undef UPV
 static int ensure_temp(sqg_ctx *ctx, size_t bytes) { CK(ctx->d_temp.ensure(bytes + 256)); return SQG_OK; }
 #define ENSURE_TEMP(bytes) do { int rc_ = ensure_temp(ctx, bytes); if (rc_) return rc_; } while (0)
 
@@ -724,7 +775,7 @@ static int run_classify(sqg_ctx *ctx) {
     PHASE_BEGIN("classify");
     CK(ctx->d_cls.ensure(n + 1)); CK(ctx->d_other.ensure(n + 1)); CK(ctx->d_scratch32.ensure(n + 1));
     CK(ctx->d_gap.ensure(n + 1)); CK(ctx->d_pc.ensure(n + 1)); CK(ctx->d_dp.ensure(n + 1));
-    CK(ctx->d_counters.ensure(16)); CK(ctx->h_counters.ensure(16));
+    CK(ctx->d_counters.ensure(32)); CK(ctx->h_counters.ensure(32));
     ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n;
     if (n > 0) {
         cub::CountingInputIterator<int32_t> cnt(0);
@@ -767,6 +818,10 @@ static int run_classify(sqg_ctx *ctx) {
         CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     PHASE_END("classify");
+    {
+        const int rcv = validate_check(ctx);
+        if (rcv) return rcv;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     if (n > 0) {
         const int32_t *sel = (const int32_t *)ctx->h_counters.p;
@@ -848,10 +903,12 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     CK(cudaSetDevice(ctx->device));
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
-    const int32_t nD = (int32_t)ctx->pre.disc.size() - 1, nG = (int32_t)ctx->pre.groups.size(), nP = (int32_t)ctx->pre.part_chr.size();
-    if (nD <= 0) FAIL(SQG_EUNSUPPORTED, "no discordant block in the chimeric reads: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
     int rc = run_classify(ctx);
     if (rc) return rc;
+    rc = finish_prepass(ctx);
+    if (rc) return rc;
+    const int32_t nD = (int32_t)ctx->pre.disc.size() - 1, nG = (int32_t)ctx->pre.groups.size(), nP = (int32_t)ctx->pre.part_chr.size();
+    if (nD <= 0) FAIL(SQG_EUNSUPPORTED, "no discordant block in the chimeric reads: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
 
     PHASE_BEGIN("seed");
     CK(ctx->d_trigger.ensure(nG + 1));
@@ -1072,6 +1129,8 @@ extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uin
     CK(cudaSetDevice(ctx->device));
     int rc = run_classify(ctx);
     if (rc) return rc;
+    rc = finish_prepass(ctx);
+    if (rc) return rc;
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
     ChimDev cd;
@@ -1216,7 +1275,7 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->cov_chain_fallback = *(int32_t *)(ctx->h_counters.p + 12) != 0;
         if (ctx->cov_chain_fallback)
-            LAUNCH(k_cov_chain, 1, 1, kop, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
+            LAUNCH(k_cov_chain, 1, 32, kop, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
     }
     if (nq > 0) LAUNCH(k_cov_count, blocks_for(nq), kThreads, b, qidx, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
     PHASE_END("coverage");

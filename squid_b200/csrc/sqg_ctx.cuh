@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -81,8 +82,10 @@ struct sqg_ctx {
     sq::HBuf<int64_t> h_counters;
 
     // chimeric side
-    bool have_chim = false;
+    bool have_chim = false, validated = true, prepass_uploaded = false;
     sqh::ChimPrepass pre;
+    sqg_chimeric chim_view{};
+    std::thread prepass_thread;
     std::vector<uint32_t> c_read_off;
     std::vector<uint16_t> c_n_first;
     std::vector<int32_t> c_first_total, c_second_total;

@@ -131,7 +131,7 @@ int main(int argc, char **argv) {
     sm.in.rest = rest.data(); sm.in.n_rest = (int32_t)rest.size();
     sm.in.read_len = p.read_len;
     sm.in.dp_rec = dprec.data(); sm.in.n_dp = (int32_t)dprec.size(); sm.in.lmax = lmax; sm.in.n_rec = n; sm.in.first_kept = first_kept;
-    std::vector<int32_t> margin(2 * (4 * (size_t)nD + 2 * pre.part_chr.size() + 2 * pcrec.size() + 64));
+    std::vector<int32_t> margin(6 * 2 * (4 * (size_t)nD + 2 * pre.part_chr.size() + 2 * pcrec.size() + 64));
     sm.margin = margin.data(); sm.margin_cap = (int32_t)margin.size();
     // islands: cut before group g when the machine provably restarts there
     std::vector<int32_t> isl_start(1, 0);

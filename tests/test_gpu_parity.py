@@ -59,5 +59,8 @@ def test_errors_are_loud(tmp_path, built_lib):
         g.BuildEdges()  # nothing loaded
     bad = case.batch.slice(0, case.batch.n_rec)
     bad.a["pos"] = bad.a["pos"][::-1].copy()
-    with pytest.raises(api.SquidB200Error):
-        g.load_concordant(bad)  # unsorted
+    g.load_concordant(bad)  # unsorted: the validation kernel's verdict surfaces at the next synchronising call
+    g.load_chimeric(case.chimeric)
+    with pytest.raises(api.SquidB200Error) as ei:
+        g.BuildNode_STAR()
+    assert "sorted" in str(ei.value)
