@@ -67,6 +67,74 @@ def run(conc_sqmb: str, chim_sqmb: str, outdir: str, extra_args=(), timeout: flo
     return load_dumps(outdir)
 
 
+RESTATE_LIB = os.path.join(HERE, "liboracle.so")
+
+
+def build_restate() -> None:
+    """Compiles the CPU restatement (oracle/restate/squid_oracle.cpp -> oracle/liboracle.so)."""
+    src = os.path.join(HERE, "restate", "squid_oracle.cpp")
+    if os.path.exists(RESTATE_LIB) and os.path.getmtime(RESTATE_LIB) >= os.path.getmtime(src):
+        return
+    r = subprocess.run(["make", "-C", HERE, "restate"], capture_output=True, text=True)
+    if r.returncode != 0 or not os.path.exists(RESTATE_LIB):
+        raise RuntimeError("oracle restatement build failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+
+
+def run_restate(conc_sqmb: str, chim_sqmb: str, outdir: str, bps=None, opts=None, stop_after: int = 0) -> dict:
+    """Runs the CPU restatement; `bps` = sorted (chr,pos) int array for the coverage pass.  Same dump layout as run()."""
+    import ctypes as C
+    build_restate()
+    lib = C.CDLL(RESTATE_LIB)
+    lib.sqo_run.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    os.makedirs(outdir, exist_ok=True)
+    bf = None
+    if bps is not None:
+        bf = os.path.join(outdir, "bps_in.bin")
+        np.ascontiguousarray(bps, dtype=np.int32).reshape(-1, 2).tofile(bf)
+    o = (C.c_int * 6)(*(opts if opts is not None else (1, 10, 4, -1, 50000, 20)))
+    rc = lib.sqo_run(conc_sqmb.encode(), chim_sqmb.encode(), outdir.encode(), o, bf.encode() if bf else None, stop_after)
+    if rc != 0:
+        raise RuntimeError("sqo_run failed rc=%d" % rc)
+    d = load_dumps(outdir)
+    cp = os.path.join(outdir, "cov_i32.bin")
+    d["cov"] = np.fromfile(cp, dtype=np.int32) if os.path.exists(cp) else None
+    return d
+
+
+def breakpoints_of(d: dict) -> np.ndarray:
+    """The sorted BPs vector ExactBPConcordantSupport assembles (SegmentGraph.cpp:3091-3109) from a dump of the
+    reference harness (final graph + ExactBP map)."""
+    fn = d["final_nodes"].astype(np.int64)
+    xm = exactbp_map(d)
+    bps = []
+    for e in d["final_edges"]:
+        k = tuple(int(v) for v in e[:4])
+        if k in xm:
+            for b1, b2 in xm[k]:
+                bps.append((int(fn[k[0], 0]), b1)); bps.append((int(fn[k[1], 0]), b2))
+        else:
+            bps.append((int(fn[k[0], 0]), int(fn[k[0], 1] + (0 if k[2] else fn[k[0], 2]))))
+            bps.append((int(fn[k[1], 0]), int(fn[k[1], 1] + (0 if k[3] else fn[k[1], 2]))))
+    bps.sort()
+    return np.array(bps, dtype=np.int32).reshape(-1, 2)
+
+
+def support_from_cov(d: dict, bps: np.ndarray, cov: np.ndarray) -> dict:
+    """Maps a Coverages vector back to {edge: [(cov1,cov2)]} as SegmentGraph.cpp:3171-3211 does (lower_bound lookups)."""
+    fn = d["final_nodes"].astype(np.int64)
+    xm = exactbp_map(d)
+    key = bps[:, 0].astype(np.int64) * (1 << 32) + bps[:, 1].astype(np.int64)
+    look = lambda c, p: int(cov[np.searchsorted(key, int(c) * (1 << 32) + int(p))])
+    out = {}
+    for e in d["final_edges"]:
+        k = tuple(int(v) for v in e[:4])
+        if k in xm:
+            out[k] = [(look(fn[k[0], 0], b1), look(fn[k[1], 0], b2)) for b1, b2 in xm[k]]
+        else:
+            out[k] = [(look(fn[k[0], 0], fn[k[0], 1] + (0 if k[2] else fn[k[0], 2])), look(fn[k[1], 0], fn[k[1], 1] + (0 if k[3] else fn[k[1], 2])))]
+    return out
+
+
 def exactbp_map(d: dict) -> dict:
     m = {}
     for row in d["exactbp"]:

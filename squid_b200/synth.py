@@ -338,13 +338,15 @@ def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.0
     if chim.n and adversarial:
         un = np.unique(chim.name_id)
         pick = un[rng.random(un.shape[0]) < 0.01]
+        if pick.size < 2 and un.size >= 4:
+            pick = un[:: max(1, un.size // 4)][:4]  # small cases: still exercise the gate
         if pick.size:
             m = pick.size
             g5 = rng.choice(n_genes, size=m, p=p)
             l5, r5 = _pairs_from_transcripts(rng, tx, g5, 0, 0.0, min_block)
             pick = pick[: l5.n]; m = l5.n
             l5.name_id = pick.copy(); r5.name_id = pick.copy()
-            sfx = rng.random(m) < 0.5
+            sfx = (np.arange(m) % 2) == 1  # every other one carries the suffix
             l5.aux[sfx] |= sqmb.AUX_NAME_SUFFIX; r5.aux[sfx] |= sqmb.AUX_NAME_SUFFIX
             parts += [l5, r5]
     conc = sqmb.concat([left, right] + parts).sorted_by_coordinate()

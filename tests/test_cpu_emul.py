@@ -1,0 +1,43 @@
+"""The device-side rules (squid_b200/csrc/*.cuh, `SQ_HD`) stepped on the CPU by tests/emul and compared with the golden
+dumps: the event-driven seed machine with island cuts, the closed-form LocateRead with the hint fix-up, the depth
+cursor and the coverage chain are all exercised here without a GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyref
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def emul_bin():
+    out = os.path.join(ROOT, "tests", "emul", "_build", "emul")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    srcs = ["tests/emul/emul_main.cpp", "squid_b200/csrc/host/readrec.cpp", "squid_b200/csrc/host/chimeric.cpp", "squid_b200/csrc/host/prepass.cpp"]
+    cmd = ["g++", "-std=c++17", "-O2", "-I", "include", "-I", "squid_b200/csrc", "-o", out] + srcs + ["-lpthread"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return out
+
+
+@pytest.mark.parametrize("case", ["chr17_3k", "fourchr_6k"])
+@pytest.mark.parametrize("one_island", [False, True])
+def test_stepped_rules_match_golden(case, one_island, emul_bin, tmp_path):
+    g = pyref.load_dumps(os.path.join(GOLD, case, "ref"))
+    bps = pyref.breakpoints_of(g)
+    bps.tofile(str(tmp_path / "bps.bin"))
+    env = dict(os.environ)
+    if one_island:
+        env["SQ_EMUL_ONE_ISLAND"] = "1"
+    r = subprocess.run([emul_bin, os.path.join(GOLD, case, "conc.sqmb"), os.path.join(GOLD, case, "chim.sqmb"), str(tmp_path), str(tmp_path / "bps.bin")],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    me = pyref.load_dumps(str(tmp_path))
+    common.assert_same(g, me, ("nodes", "avgdepth", "edges", "chim_after_edges"))
+    cov = np.fromfile(str(tmp_path / "cov_i32.bin"), dtype=np.int32)
+    assert pyref.support_from_cov(g, bps, cov) == pyref.support_map(g)

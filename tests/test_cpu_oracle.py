@@ -1,0 +1,55 @@
+"""CPU tests of the oracle: the restatement (oracle/restate) must reproduce the committed golden dumps, which were
+produced by the reference's own sources (oracle/_ref; script: tests/golden/make_golden.py).  When oracle/_ref is
+present (development container / GPU box with the prebuilt binary) the goldens are re-derived and fresh fuzzed cases
+are compared as well."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyref
+from tests import common
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["chr17_3k", "fourchr_6k"]
+
+
+def _gold(case):
+    return pyref.load_dumps(os.path.join(GOLD, case, "ref"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_restatement_reproduces_golden(case, tmp_path):
+    g = _gold(case)
+    bps = pyref.breakpoints_of(g)
+    me = pyref.run_restate(os.path.join(GOLD, case, "conc.sqmb"), os.path.join(GOLD, case, "chim.sqmb"), str(tmp_path), bps=bps)
+    assert me["read_len"] == g["read_len"]
+    common.assert_same(g, me, ("chim_loaded", "chim_loaded_meta", "nodes", "avgdepth", "edges", "chim_after_edges"))
+    assert pyref.support_from_cov(g, bps, me["cov"]) == pyref.support_map(g)
+
+
+def test_restatement_decoder_kat(tmp_path):
+    g = pyref.load_dumps(os.path.join(GOLD, "kat_decode", "ref"))
+    me = pyref.run_restate(os.path.join(GOLD, "kat_decode", "conc.sqmb"), os.path.join(GOLD, "kat_decode", "chim.sqmb"), str(tmp_path), stop_after=1)
+    common.assert_same(g, me, ("chim_loaded", "chim_loaded_meta"))
+    assert me["read_len"] == g["read_len"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_reference_build_reproduces_golden(case, tmp_path, ref_oracle):
+    """The goldens are what oracle/_ref produces today (guards against stale fixtures)."""
+    g = _gold(case)
+    r = ref_oracle.run(os.path.join(GOLD, case, "conc.sqmb"), os.path.join(GOLD, case, "chim.sqmb"), str(tmp_path))
+    common.assert_same(g, r, ("chim_loaded", "nodes", "avgdepth", "edges", "chim_after_edges", "final_nodes", "final_edges", "exactbp", "support"))
+
+
+@pytest.mark.parametrize("seed,n,disc,ref_len", [(101, 4000, 0.05, None), (202, 20000, 0.01, [3000000, 2000000, 500000, 16569]), (303, 30000, 0.02, "grch38")])
+def test_restatement_matches_reference_on_fuzz(seed, n, disc, ref_len, tmp_path, ref_oracle):
+    from squid_b200 import synth
+    rl = synth.GRCH38_LEN if ref_len == "grch38" else ref_len
+    cp, hp, *_ = common.write_case(str(tmp_path), n, seed, disc, rl)
+    r = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    bps = pyref.breakpoints_of(r)
+    me = pyref.run_restate(cp, hp, str(tmp_path / "me"), bps=bps)
+    common.assert_same(r, me, ("chim_loaded", "nodes", "avgdepth", "edges", "chim_after_edges"))
+    assert pyref.support_from_cov(r, bps, me["cov"]) == pyref.support_map(r)
