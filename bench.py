@@ -180,6 +180,7 @@ def main():
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     R = int(batch["ref_id"].shape[0]); NB = int(batch["blk_ref_pos"].shape[0])
+    P_req, P = P, R // 2  # the generator drops pairs with <4-bp blocks: count what is really there
     n_bytes = synth_gpu.batch_bytes(batch)
     dstruct = synth_gpu.batch_struct(batch)
     host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in batch.items()}
@@ -282,7 +283,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
             "config": {"workload": "synthetic GRCh38-layout sorted alignment records, %d read pairs per GPU, ~0.5%% discordant (configs[1])" % P,
-                       "pairs_per_gpu": P, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": "range-shard x%d" % world,
+                       "pairs_per_gpu": P, "pairs_requested": P_req, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": "range-shard x%d" % world,
                        "l2": "inputs (%.1f GB) larger than L2" % (n_bytes / 1e9), "segments": state.get("n_nodes"), "edges": state.get("n_edges"), "breakpoints": state.get("n_bp")},
             "e2e": {"value": world * P / sec_e2e, "unit": "read pairs/s", "h2d_bytes_per_step": n_bytes + sum(v.nbytes for v in chim0.a.values()), "d2h_bytes_per_step": state.get("d2h", 0), "ms_per_step": 1e3 * sec_e2e},
             "roofline": roof,

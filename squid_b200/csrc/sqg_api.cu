@@ -505,7 +505,11 @@ __global__ void k_cov_r0(const uint64_t *M, int64_t nq, const int32_t *bp_chr, c
     r0[k] = v;
     t[k] = v - k;  // max-plus form of t[k] = max(r0[k], t[k-1]+1)
 }
-__global__ void k_cov_verify(CoverRankKeyOp key, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist,
+__global__ void k_cov_keys(CoverRankKeyOp key, int64_t nq, uint64_t *qkey) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nq) qkey[i] = key((int32_t)i);
+}
+__global__ void k_cov_verify(const uint64_t *qkey, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist,
                              const int64_t *r0, int64_t *t, int32_t *fail) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= K) return;
@@ -513,18 +517,20 @@ __global__ void k_cov_verify(CoverRankKeyOp key, int64_t nq, const int32_t *bp_c
     t[k] = c;
     if (c != r0[k] && c < nq) {  // lag mode: the qualifying record right after t[k-1] must itself pass breakpoint k
         const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
-        if (!(key((int32_t)c) > T)) *fail = 1;
+        if (!(qkey[c] > T)) *fail = 1;
     }
 }
 // Literal chain (:3157-3158), used when the verification above fails: indBP advances by at most one per qualifying
 // record, so t[k] = first rank c > t[k-1] whose key passes breakpoint k.  One warp: the lanes prefetch r0/T of 32
-// breakpoints and a 32-wide window of record keys; the steps themselves run on shuffled registers.
-__global__ void k_cov_chain(CoverRankKeyOp key, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, const int64_t *r0, int64_t *t) {
+// breakpoints and a 128-wide window of record keys; the steps themselves run on shuffled registers.
+__global__ void k_cov_chain(const uint64_t *qkey, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, const int64_t *r0, int64_t *t) {
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
+    constexpr int W = 4;       // keys per lane
     int64_t tp = -1;
-    int64_t wbase = -64;       // ranks [wbase, wbase+32) are held in wkey
-    uint64_t wkey = 0;
+    int64_t wbase = -1024;     // ranks [wbase, wbase + 32*W) are held in wkey[]
+    uint64_t wkey[W];
+    for (int q = 0; q < W; q++) wkey[q] = 0;
     for (int64_t kb = 0; kb < K; kb += 32) {
         const int64_t k = kb + lane;
         const int64_t my_r0 = k < K ? r0[k] : nq;
@@ -539,13 +545,19 @@ __global__ void k_cov_chain(CoverRankKeyOp key, int64_t nq, const int32_t *bp_ch
             else {
                 c = tp + 1;
                 while (c < nq) {
-                    if (c < wbase || c >= wbase + 32) {
+                    if (c < wbase || c >= wbase + 32 * W) {
                         wbase = c;
-                        wkey = (c + lane < nq) ? key((int32_t)(c + lane)) : ~0ull;
+#pragma unroll
+                        for (int q = 0; q < W; q++) { const int64_t rr = c + q * 32 + lane; wkey[q] = rr < nq ? qkey[rr] : ~0ull; }
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, wbase + lane >= c && wkey > Tj);
-                    if (m) { c = wbase + (__ffs(m) - 1); break; }
-                    c = wbase + 32;
+                    int64_t found = -1;
+#pragma unroll
+                    for (int q = 0; q < W; q++) {
+                        const unsigned m = __ballot_sync(0xffffffffu, wbase + q * 32 + lane >= c && wkey[q] > Tj);
+                        if (found < 0 && m) found = wbase + q * 32 + (__ffs(m) - 1);
+                    }
+                    if (found >= 0) { c = found; break; }
+                    c = wbase + 32 * W;
                 }
             }
             if (lane == j) my_t = c;
@@ -554,13 +566,13 @@ __global__ void k_cov_chain(CoverRankKeyOp key, int64_t nq, const int32_t *bp_ch
         if (k < K) t[k] = my_t;
     }
 }
-__global__ void k_cov_count(DevBatch b, const int32_t *qidx, int64_t nq, const uint64_t *bpkey, const int64_t *t, int64_t K, int32_t *cov) {
+__global__ void k_cov_count(DevBatch b, const int32_t *qidx, const uint64_t *qkey, int64_t nq, const uint64_t *bpkey, const int64_t *t, int64_t K, int32_t *cov) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool valid = i < nq;
     if (!valid) i = nq - 1;  // keep the whole warp in the aggregation loop
     const int32_t r = qidx[i];
     const int32_t rid = b.ref_id[r];
-    const uint64_t ks = chrpos_key(rid, cover_start(b.flag[r], rid, b.pos[r], b.mate_ref_id[r], b.mate_pos[r]));
+    const uint64_t ks = qkey[i];
     const uint64_t ke = chrpos_key(rid, b.end_pos[r]);
     // sorted input: neighbouring fragments cover the same breakpoints, so aggregate per warp before the atomic
     int64_t k = lower_bound_u64(bpkey, 0, K, ks);
@@ -620,7 +632,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
-    ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
+    ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
     ctx->h_chr.release(); ctx->h_pos.release(); ctx->h_len.release(); ctx->h_cnt3.release(); ctx->h_sum3.release(); ctx->h_ind1.release(); ctx->h_ind2.release();
     ctx->h_w.release(); ctx->h_chimblk.release(); ctx->h_heads.release(); ctx->h_seeds.release();
     for (auto &kv : ctx->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
@@ -1250,15 +1262,14 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
         nq = *(int32_t *)(ctx->h_counters.p + 12);
         ctx->launches += 2;
     }
-    CK(ctx->d_covM.ensure(nq + 1));
+    CK(ctx->d_covM.ensure(nq + 1)); CK(ctx->d_qkey.ensure(nq + 1));
     CoverRankKeyOp kop{b, qidx};
-    if (nq > 0) {  // running maximum of the fragment-start keys in rank space
-        cub::CountingInputIterator<int32_t> cnt(0);
-        cub::TransformInputIterator<uint64_t, CoverRankKeyOp, cub::CountingInputIterator<int32_t>> it(cnt, kop);
+    if (nq > 0) {  // fragment-start keys in rank space and their running maximum
+        LAUNCH(k_cov_keys, blocks_for(nq), kThreads, kop, nq, ctx->d_qkey.p);
         size_t tb = 0;
-        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, it, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_qkey.p, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
         ENSURE_TEMP(tb);
-        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, it, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
+        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_qkey.p, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
         ctx->launches += 2;
     }
     LAUNCH(k_cov_r0, blocks_for(K), kThreads, ctx->d_covM.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_bpkey.p, ctx->d_r0.p, ctx->d_t.p);
@@ -1270,14 +1281,14 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
         CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_t.p, ctx->d_t.p, MaxI64(), (int)K, ctx->stream));
         ctx->launches += 2;
         CK(cudaMemsetAsync(ctx->d_counters.p + 12, 0, sizeof(int64_t), ctx->stream));
-        LAUNCH(k_cov_verify, blocks_for(K), kThreads, kop, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (int32_t *)(ctx->d_counters.p + 12));
+        LAUNCH(k_cov_verify, blocks_for(K), kThreads, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (int32_t *)(ctx->d_counters.p + 12));
         CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->cov_chain_fallback = *(int32_t *)(ctx->h_counters.p + 12) != 0;
         if (ctx->cov_chain_fallback)
-            LAUNCH(k_cov_chain, 1, 32, kop, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
+            LAUNCH(k_cov_chain, 1, 32, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
     }
-    if (nq > 0) LAUNCH(k_cov_count, blocks_for(nq), kThreads, b, qidx, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
+    if (nq > 0) LAUNCH(k_cov_count, blocks_for(nq), kThreads, b, qidx, ctx->d_qkey.p, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
     PHASE_END("coverage");
     CK(cudaMemcpyAsync(cov_out, ctx->d_cov.p, K * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

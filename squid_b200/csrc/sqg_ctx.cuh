@@ -130,7 +130,7 @@ struct sqg_ctx {
     bool have_edge_table = false;
 
     // coverage
-    sq::DBuf<uint64_t> d_bpkey, d_covM;
+    sq::DBuf<uint64_t> d_bpkey, d_covM, d_qkey;
     sq::DBuf<int64_t> d_r0, d_t;
     sq::DBuf<int32_t> d_cov, d_bpchr, d_bppos;
 

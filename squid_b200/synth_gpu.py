@@ -33,8 +33,11 @@ def _map_interval(tx_t, a, b, max_blocks):
 
 
 def make_bench_batch(n_pairs: int, seed: int = 100, device: str = "cuda", ref_len=None, n_genes: int = 20000, max_blocks: int = 3,
-                     exon_len=(60, 1500)):
-    """Returns (dict of device tensors in sqg_batch layout, Transcriptome, expression probabilities)."""
+                     exon_len=(60, 1500), min_block: int = 4):
+    """Returns (dict of device tensors in sqg_batch layout, Transcriptome, expression probabilities).
+    Pairs with an aligned block shorter than `min_block` are dropped (as in synth.make_case: aligners do not emit 1-3 bp
+    overhangs by default, and such blocks make the reference's Support depend on an unstable sort), so the
+    batch holds slightly fewer than n_pairs pairs; use ref_id.shape[0] // 2."""
     ref_len = np.asarray(synth.GRCH38_LEN if ref_len is None else ref_len, dtype=np.int64)
     rng = np.random.Generator(np.random.PCG64(seed))
     tx = synth.Transcriptome(rng, ref_len, n_genes, exon_len=exon_len)
@@ -72,6 +75,18 @@ def make_bench_batch(n_pairs: int, seed: int = 100, device: str = "cuda", ref_le
     ln, lgs, lgl = _map_interval(tx_t, t0 + lcl, t0 + READ_LEN - lcr, max_blocks)
     rn, rgs, rgl = _map_interval(tx_t, t0 + ins - READ_LEN + rcl, t0 + ins - rcr, max_blocks)
     del t0, ins
+    if min_block > 1:
+        big = 1 << 30
+        ok = torch.ones_like(ln, dtype=torch.bool)
+        for j in range(max_blocks):
+            ok &= torch.where(ln > j, lgl[j], torch.full_like(lgl[j], big)) >= min_block
+            ok &= torch.where(rn > j, rgl[j], torch.full_like(rgl[j], big)) >= min_block
+        keep = torch.nonzero(ok).squeeze(1)
+        sel = lambda x: x[keep]
+        ln, rn, chr_, lcl, lcr, rcl, rcr, first_left = map(sel, (ln, rn, chr_, lcl, lcr, rcl, rcr, first_left))
+        lgs = [x[keep] for x in lgs]; lgl = [x[keep] for x in lgl]; rgs = [x[keep] for x in rgs]; rgl = [x[keep] for x in rgl]
+        n = int(keep.shape[0])
+        del ok, keep
     FP, FPR, FR, FMR, F1, F2 = 0x1, 0x2, 0x10, 0x20, 0x40, 0x80
     lflag = torch.where(first_left, FP | FPR | FMR | F1, FP | FPR | FMR | F2).to(torch.int32)
     rflag = torch.where(first_left, FP | FPR | FR | F2, FP | FPR | FR | F1).to(torch.int32)
