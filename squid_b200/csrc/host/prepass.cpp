@@ -2,6 +2,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <thread>
+#include <chrono>
+#include <cstdio>
 
 namespace sqh {
 namespace {
@@ -34,11 +37,89 @@ bool pair_disc(const View &v, int32_t ft, int32_t st_) {  // ReadRec.cpp:211-228
     if (!v.rev(sf) && v.pos(sf) - v.rpos(sf) > v.pos(fb) - (ft - v.rpos(fb) - v.mread(fb))) return true;
     return false;
 }
+
+// ---- std::sort, run on several threads -----------------------------------------------------------------------------
+// The order in which equal (RefID,RefPos) blocks leave the reference's `sort(bamdiscordant)` (SegmentGraph.cpp:264) is
+// observable, so the pre-pass must produce exactly libstdc++'s std::sort permutation.  std::sort
+// is introsort: quicksort partitions (median of first+1 / middle / last-1 moved to the front, unguarded Hoare partition
+// around it, recursion on the right part, loop on the left) down to ranges of 16, heap sort when the depth budget
+// 2*floor(log2 n) runs out, and a final insertion sort.  After a partition the two parts never interact again, so they can
+// be sorted by different threads without changing a single comparison; the final insertion pass is stable and never
+// moves an element across a partition boundary.  tests/test_cpu_host_twin.py checks this routine against std::sort.
+struct SortKey { uint64_t key; uint32_t k; };
+inline bool sk_lt(const SortKey &x, const SortKey &y) { return x.key < y.key; }
+void sort_loop(SortKey *first, SortKey *last, int depth, int fanout) {
+    std::vector<std::thread> kids;
+    while (last - first > 16) {
+        if (depth == 0) { std::partial_sort(first, last, last, sk_lt); break; }
+        --depth;
+        SortKey *mid = first + (last - first) / 2, *a = first + 1, *c = last - 1;
+        // median of (*a, *mid, *c) to *first
+        if (sk_lt(*a, *mid)) {
+            if (sk_lt(*mid, *c)) std::swap(*first, *mid);
+            else if (sk_lt(*a, *c)) std::swap(*first, *c);
+            else std::swap(*first, *a);
+        } else if (sk_lt(*a, *c)) std::swap(*first, *a);
+        else if (sk_lt(*mid, *c)) std::swap(*first, *c);
+        else std::swap(*first, *mid);
+        // unguarded partition of [first+1, last) around *first
+        SortKey *lo = first + 1, *hi = last;
+        for (;;) {
+            while (sk_lt(*lo, *first)) ++lo;
+            --hi;
+            while (sk_lt(*first, *hi)) --hi;
+            if (!(lo < hi)) break;
+            std::swap(*lo, *hi);
+            ++lo;
+        }
+        SortKey *cut = lo;
+        if (fanout > 0 && last - cut > 4096) {
+            --fanout;
+            kids.emplace_back(sort_loop, cut, last, depth, fanout);
+        } else sort_loop(cut, last, depth, 0);
+        last = cut;
+    }
+    for (std::thread &t : kids) t.join();
+}
+void sort_like_std(SortKey *first, SortKey *last, int fanout) {
+    if (first == last) return;
+    int lg = 0;
+    for (size_t n = (size_t)(last - first); n > 1; n >>= 1) lg++;
+    sort_loop(first, last, 2 * lg, fanout);
+    for (SortKey *i = first + 1; i < last; ++i) {  // final insertion sort
+        const SortKey v = *i;
+        SortKey *j = i;
+        while (j > first && sk_lt(v, *(j - 1))) { *j = *(j - 1); --j; }
+        *j = v;
+    }
+}
 }  // namespace
 
+// test hook: does sort_like_std reproduce std::sort's permutation (payload included) on n keys drawn from [0,range)?
+extern "C" int sqh_selftest_sort(int64_t n, uint64_t seed, uint64_t range, int pattern, int fanout) {
+    std::vector<SortKey> a((size_t)n), b;
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    for (int64_t i = 0; i < n; i++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        uint64_t v = range ? x % range : 0;
+        if (pattern == 1) v = (uint64_t)i / 3;                 // sorted with ties
+        else if (pattern == 2) v = (uint64_t)(n - i) / 3;      // reversed with ties
+        else if (pattern == 3) v = (uint64_t)std::min(i, n - 1 - i);  // organ pipe
+        a[(size_t)i] = SortKey{v, (uint32_t)i};
+    }
+    b = a;
+    std::sort(a.begin(), a.end(), sk_lt);
+    sort_like_std(b.data(), b.data() + b.size(), fanout);
+    for (size_t i = 0; i < a.size(); i++) if (a[i].key != b[i].key || a[i].k != b[i].k) return 0;
+    return 1;
+}
+
 void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out) {
+    const bool timing = getenv("SQH_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *w) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[prepass] %s %.1f ms\n", w, 1e3 * std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     out = ChimPrepass();
-    struct DB { uint64_t key; uint32_t k; };  // key = (RefID,RefPos) packed, k = block index
+    typedef SortKey DB;  // key = (RefID,RefPos) packed, k = block index
     std::vector<DB> dis;
     dis.reserve((size_t)c.n_blk);
     std::vector<std::pair<int, int>> part((size_t)n_ref, std::make_pair(0, 0));  // resize()d then appended (:203-204)
@@ -96,16 +177,31 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
             }
         }
     }
+    lap("reads");
     std::sort(part.begin(), part.end(), [](std::pair<int, int> a, std::pair<int, int> b) { return a.first == b.first ? a.second < b.second : a.first < b.first; });
     // Same unstable std::sort, same ordering relation, same input sequence as :264 => the same permutation, including
     // the order among equal (RefID,RefPos) which the sub-cluster walk observes.  The packed key
     // compares exactly like operator< of SingleBamRec_t (RefID, RefPos are non-negative here).
-    std::sort(dis.begin(), dis.end(), [](const DB &a, const DB &b) { return a.key < b.key; });
+    lap("part sort");
+    sort_like_std(dis.data(), dis.data() + dis.size(), 6);
+    lap("disc sort");
     for (auto &p : part) { out.part_chr.push_back(p.first); out.part_pos.push_back(p.second); }
-    out.disc.reserve(dis.size() + 1);
-    for (const DB &d : dis) out.disc.push_back(sq::DiscBlock{c.blk_ref_id[d.k], c.blk_ref_pos[d.k], c.blk_match_ref[d.k], c.blk_is_reverse[d.k] ? 1 : 0});
+    out.disc.resize(dis.size() + 1);
+    {   // gather the sorted blocks (random access into the caller's arrays): split across a few threads
+        const size_t nd = dis.size();
+        const unsigned nt = nd > (1u << 16) ? 8 : 1;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                for (size_t i = nd * t / nt; i < nd * (t + 1) / nt; i++) {
+                    const uint32_t k = dis[i].k;
+                    out.disc[i] = sq::DiscBlock{c.blk_ref_id[k], c.blk_ref_pos[k], c.blk_match_ref[k], c.blk_is_reverse[k] ? 1 : 0};
+                }
+            });
+        for (auto &x : th) x.join();
+    }
     const int32_t n = (int32_t)dis.size();
-    out.disc.push_back(sq::DiscBlock{0, 0, 0, 0});
+    out.disc[dis.size()] = sq::DiscBlock{0, 0, 0, 0};  // what *cend() reads
     for (int32_t s = 0; s < n;) {  // :341-348 chain while the next block starts within ReadLen of the running right end
         int32_t right = out.disc[s].pos + out.disc[s].len, e = s;
         for (; e < n && out.disc[e].chr == out.disc[s].chr && out.disc[e].pos < right + read_len; e++)
@@ -113,5 +209,6 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
         out.groups.push_back(sq::Group{s, e, out.disc[s].chr, right});
         s = e;
     }
+    lap("groups");
 }
 }  // namespace sqh

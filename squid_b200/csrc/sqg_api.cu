@@ -523,15 +523,37 @@ __global__ void k_cov_verify(const uint64_t *qkey, int64_t nq, const int32_t *bp
 // Literal chain (:3157-3158), used when the verification above fails: indBP advances by at most one per qualifying
 // record, so t[k] = first rank c > t[k-1] whose key passes breakpoint k.  One warp: the lanes prefetch r0/T of 32
 // breakpoints and a 128-wide window of record keys; the steps themselves run on shuffled registers.
-__global__ void k_cov_chain(const uint64_t *qkey, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t dist, const int64_t *r0, int64_t *t) {
-    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+// Chunked: the breakpoint list is cut where r0 jumps by more than kChainGap ranks; every chunk is replayed by its own warp
+// under the assumption that the chain has caught up at its first breakpoint (t = r0 there).  k_cov_chain_check verifies
+// that assumption (t of the previous breakpoint < r0 of the chunk's first); only if it fails somewhere is the whole list
+// replayed by one warp (chunk_start == nullptr).
+constexpr int64_t kChainGap = 4096;
+struct IsChainCutOp {
+    const int64_t *r0;
+    __device__ bool operator()(int32_t k) const { return k == 0 || r0[k] - r0[k - 1] > kChainGap; }
+};
+__global__ void k_cov_chain_check(const int32_t *chunk_start, int32_t n_chunks, const int64_t *r0, const int64_t *t, int32_t *fail) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= 0 || i >= n_chunks) return;
+    const int32_t k = chunk_start[i];
+    if (!(t[k - 1] < r0[k])) *fail = 1;
+}
+__global__ void k_cov_chain(const uint64_t *qkey, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K_all, int32_t dist, const int64_t *r0, int64_t *t,
+                            const int32_t *chunk_start, int32_t n_chunks) {
+    const int lane = threadIdx.x & 31;
     constexpr int W = 4;       // keys per lane
+    int64_t k_begin = 0, K = K_all;
+    if (chunk_start) {
+        const int32_t ci = (int32_t)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+        if (ci >= n_chunks) return;
+        k_begin = chunk_start[ci];
+        K = ci + 1 < n_chunks ? chunk_start[ci + 1] : K_all;
+    } else if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     int64_t tp = -1;
     int64_t wbase = -1024;     // ranks [wbase, wbase + 32*W) are held in wkey[]
     uint64_t wkey[W];
     for (int q = 0; q < W; q++) wkey[q] = 0;
-    for (int64_t kb = 0; kb < K; kb += 32) {
+    for (int64_t kb = k_begin; kb < K; kb += 32) {
         const int64_t k = kb + lane;
         const int64_t my_r0 = k < K ? r0[k] : nq;
         const uint64_t my_T = k < K ? chrpos_key(bp_chr[k], bp_pos[k] + dist) : ~0ull;
@@ -632,7 +654,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
-    ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
+    ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
     ctx->h_chr.release(); ctx->h_pos.release(); ctx->h_len.release(); ctx->h_cnt3.release(); ctx->h_sum3.release(); ctx->h_ind1.release(); ctx->h_ind2.release();
     ctx->h_w.release(); ctx->h_chimblk.release(); ctx->h_heads.release(); ctx->h_seeds.release();
     for (auto &kv : ctx->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
@@ -658,6 +680,7 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     if (n == "islands") return ctx->n_islands;
     if (n == "heavy_islands") return ctx->n_heavy;
     if (n == "cov_chain_fallback") return ctx->cov_chain_fallback;
+    if (n == "cov_chain_chunks") return ctx->cov_chain_chunks;
     if (n == "gap_records") return ctx->n_gap;
     if (n == "partial_records") return ctx->n_pc;
     if (n == "displaced_records") return ctx->n_dp;
@@ -800,7 +823,9 @@ static int run_classify(sqg_ctx *ctx) {
             ctx->launches += 2;
         }
         CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(int64_t), ctx->stream));
+        PHASE_BEGIN("k_classify");
         LAUNCH(k_classify, blocks_for(n), kThreads, b, ctx->params, ctx->d_scratch32.p, ctx->d_cls.p, ctx->d_other.p, (int32_t *)(ctx->d_counters.p + 3));
+        PHASE_END("k_classify");
         {   // otherChr/otherrightmost before each record
             CK(cub::DeviceScan::ExclusiveScan(nullptr, tb, ctx->d_other.p, ctx->d_other.p, MaxU64(), (uint64_t)(1ull << 32), (int)n, ctx->stream));
             ENSURE_TEMP(tb);
@@ -1064,8 +1089,10 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     LAUNCH(k_depth_disc, blocks_for(nD), kThreads, ctx->nt, ctx->d_disc.p, nD, ctx->d_cnt3.p, ctx->d_sum3.p);
     if (n > 0) {
         int32_t *d_flag = ctx->d_cnt3.p + 3 * (size_t)N;
+        PHASE_BEGIN("k_depth_targets");
         LAUNCH(k_depth_targets, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_scratch32.p,
                ctx->d_cnt3.p + 2 * (size_t)N, ctx->d_sum3.p + 2 * (size_t)N, d_flag);
+        PHASE_END("k_depth_targets");
         size_t tb = 0;
         CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_scratch32.p, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
         ENSURE_TEMP(tb);
@@ -1167,7 +1194,7 @@ extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uin
             int32_t *res0 = stream_kind == 0 ? ctx->dc_res0.p : ctx->d_scratch32.p;
             if (cnt_items <= 0) continue;
             if (stream_kind == 0) LAUNCH(k_chim_edges, blocks_for(cnt_items), kThreads, cd, ctx->params, ctx->nt, res0, sink);
-            else LAUNCH(k_conc_edges, blocks_for(cnt_items), kThreads, b, ctx->d_cls.p, ctx->params, ctx->nt, res0, sink);
+            else { PHASE_BEGIN("k_conc_edges"); LAUNCH(k_conc_edges, blocks_for(cnt_items), kThreads, b, ctx->d_cls.p, ctx->params, ctx->nt, res0, sink); PHASE_END("k_conc_edges"); }
             IsSensOp op{res0};
             size_t tb = 0;
             CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_sens.p, d_nsens, (int)cnt_items, op, ctx->stream));
@@ -1285,10 +1312,34 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
         CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->cov_chain_fallback = *(int32_t *)(ctx->h_counters.p + 12) != 0;
-        if (ctx->cov_chain_fallback)
-            LAUNCH(k_cov_chain, 1, 32, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p);
+        if (ctx->cov_chain_fallback) {
+            // literal chain, chunked at large jumps of r0 (one warp per chunk), validated; whole-list replay as a last resort
+            cub::CountingInputIterator<int32_t> cnt(0);
+            IsChainCutOp cop{ctx->d_r0.p};
+            CK(ctx->d_chunks.ensure(K + 1));
+            int32_t *chunks = ctx->d_chunks.p;
+            CK(cub::DeviceSelect::If(nullptr, tb, cnt, chunks, (int32_t *)(ctx->d_counters.p + 14), (int)K, cop, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, chunks, (int32_t *)(ctx->d_counters.p + 14), (int)K, cop, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_counters.p + 14, ctx->d_counters.p + 14, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const int32_t n_chunks = *(int32_t *)(ctx->h_counters.p + 14);
+            ctx->launches += 2;
+            LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, chunks, n_chunks);
+            CK(cudaMemsetAsync(ctx->d_counters.p + 12, 0, sizeof(int64_t), ctx->stream));
+            LAUNCH(k_cov_chain_check, blocks_for(n_chunks), kThreads, chunks, n_chunks, ctx->d_r0.p, ctx->d_t.p, (int32_t *)(ctx->d_counters.p + 12));
+            CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->cov_chain_chunks = n_chunks;
+            if (*(int32_t *)(ctx->h_counters.p + 12) != 0) {
+                ctx->cov_chain_chunks = 1;
+                LAUNCH(k_cov_chain, 1, 32, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (const int32_t *)nullptr, 0);
+            }
+        }
     }
+    PHASE_BEGIN("k_cov_count");
     if (nq > 0) LAUNCH(k_cov_count, blocks_for(nq), kThreads, b, qidx, ctx->d_qkey.p, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
+    PHASE_END("k_cov_count");
     PHASE_END("coverage");
     CK(cudaMemcpyAsync(cov_out, ctx->d_cov.p, K * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -107,3 +107,18 @@ def test_shard_plan_and_edge_merge():
     mk, mw = shard.merge_edge_tables([a, b2])
     i1, i2, h1, h2 = shard.unpack_edge_keys(mk)
     assert list(zip(i1, i2, h1.astype(int), h2.astype(int), mw)) == [(1, 2, 0, 1, 8), (1, 5, 1, 0, 6), (7, 9, 1, 1, 4)]
+
+
+def test_parallel_sort_reproduces_std_sort(built_lib):
+    """The chimeric pre-pass sorts with a multi-threaded restatement of libstdc++'s introsort; it must leave equal keys in
+    exactly std::sort's order (that order is observable, SURVEY.md App. A-11)."""
+    import ctypes as C
+    from squid_b200 import api
+    L = api.lib()
+    L.sqh_selftest_sort.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+    L.sqh_selftest_sort.restype = C.c_int
+    for n in (0, 1, 16, 17, 1000, 4097, 200000):
+        for rng in (1, 3, 100, 1 << 40):
+            for pat in range(4):
+                for fan in (0, 4):
+                    assert L.sqh_selftest_sort(n, n * 31 + rng + pat, rng, pat, fan) == 1, (n, rng, pat, fan)
