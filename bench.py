@@ -95,8 +95,8 @@ def bps_from_graph(nodes, edges, min_weight=5):
     p2 = nodes.Position[i2] + np.where(edges.Head2[keep], 0, nodes.Length[i2])
     c = np.concatenate([nodes.Chr[i1], nodes.Chr[i2]]).astype(np.int64)
     p = np.concatenate([p1, p2]).astype(np.int64)
-    o = np.lexsort((p, c))
-    return c[o].astype(np.int32), p[o].astype(np.int32)
+    key = np.sort((c << 32) | p)  # (chr, pos) ascending; positions are non-negative
+    return (key >> 32).astype(np.int32), (key & 0xffffffff).astype(np.int32)
 
 
 def reference_arm(args, rank, world):
@@ -201,15 +201,27 @@ def main():
     state = {}
 
     def step(resident: bool):
+        tl = state.setdefault("timeline", {})
+        t_ = [time.perf_counter()]
+
+        def lap(name):
+            t1 = time.perf_counter()
+            tl[name] = tl.get(name, 0.0) + 1e3 * (t1 - t_[0])
+            t_[0] = t1
         chim = api.ChimericReads(chim0.a)
+        lap("chim_copy")
         if resident:
             g.attach_concordant_device(dstruct, keepalive=batch)
         else:
             import ctypes as C0
             g._ck(g.L.sqg_load_concordant(g._h, C0.byref(hstruct), 0))
+        lap("load_concordant")
         g.load_chimeric(chim)
+        lap("load_chimeric")
         nodes = g.BuildNode_STAR()
+        lap("BuildNode_STAR")
         edges = g.BuildEdges()
+        lap("BuildEdges")
         if world > 1:  # exchange per-shard sparse edge tables, merge-reduce on the device
             import ctypes as C
             dk, dw, n = C.c_void_p(), C.c_void_p(), C.c_int64()
@@ -230,7 +242,9 @@ def main():
             g._ck(g.L.sqg_merge_edge_tables(g._h, allk.data_ptr(), allw.data_ptr(), int(allk.shape[0]), C.byref(i1), C.byref(i2), C.byref(hd), C.byref(w), C.byref(ne)))
             state["merged_edges"] = ne.value
         bc, bp = bps_from_graph(nodes, edges)
+        lap("bps_from_graph(host stand-in)")
         cov = g.BPCoverage(bc, bp)
+        lap("BPCoverage")
         state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback")}
         state.update(n_nodes=int(nodes.Chr.shape[0]), n_edges=int(edges.Ind1.shape[0]), n_bp=int(bc.shape[0]), cov_sum=int(cov.sum()),
                      d2h=int(nodes.Chr.nbytes * 3 + nodes.count3.nbytes * 2 + edges.Ind1.nbytes * 3 + edges.Ind1.shape[0] + cov.nbytes))
@@ -246,6 +260,7 @@ def main():
         for _ in range(warmup):
             step(resident)
         barrier()
+        state["timeline"] = {}
         l0 = g.launch_count()
         sampler = ClockSampler(local)
         sampler.start()
@@ -264,9 +279,11 @@ def main():
             tt = torch.tensor([sec], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             sec = float(tt.item())
+        state["timeline_ms"] = {k: v / steps for k, v in state["timeline"].items()}
         return sec, phases, clocks, (g.launch_count() - l0) // steps
 
     sec, phases, clocks, launches = timed(True, args.steps, args.warmup)
+    timeline = dict(state["timeline_ms"])
     sec_e2e, phases_e2e, _, _ = timed(False, max(1, min(args.steps, 3)), 1)
 
     # ---- roofline of the dominant stream phase --------------------------------------------------------------
@@ -302,7 +319,7 @@ def main():
             "roofline": roof,
             "whole_path": {"alg_bytes_per_pair": b_alg_pair, "gpu_ms_in_kernels": total_gpu_ms,
                            "frac_of_hbm_roofline_wall": (b_alg_pair * P / sec) / 1e9 / peak, "frac_of_hbm_roofline_kernels": (b_alg_pair * P / (total_gpu_ms * 1e-3)) / 1e9 / peak if total_gpu_ms else None},
-            "phases_ms": phases, "phases_ms_e2e": phases_e2e, "stats": state.get("stats"),
+            "phases_ms": phases, "host_timeline_ms": timeline, "phases_ms_e2e": phases_e2e, "stats": state.get("stats"),
             "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches), "gen_s": t_gen,
         }
         print(json.dumps(out))

@@ -38,6 +38,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("SQUID_NVCC_EXTRA", "").split()
     bdir = os.path.join(ROOT, "build")
     os.makedirs(bdir, exist_ok=True)
     objs = []
@@ -45,7 +46,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     for f in CU + CPP:
         o = os.path.join(bdir, f.replace("/", "_") + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-x", "cu"] if f.endswith(".cu") else []) + ["-c", os.path.join(CSRC, f), "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-x", "cu"] if f.endswith(".cu") else []) + ["-c", os.path.join(CSRC, f), "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -45,10 +45,16 @@ struct Params {
 };
 
 // Segment table: segments tile every chromosome; chr_first[c]..chr_first[c+1] are the segments of c.
+// bin_seg is a coarse position index over the tiling: for chromosome c, bin k (positions [k<<bin_shift, (k+1)<<bin_shift))
+// starts inside segment bin_seg[bin_off[c] + k].  Every "which segment holds position x" question of the path (LocateRead's
+// scans, the depth cursor, the spanning-block fallback) is then one table read plus a step or two along the tiling instead
+// of a binary search over the whole table.  With bin_seg == nullptr the lookups fall back to binary searches.
 struct NodeTable {
     int32_t n = 0, n_ref = 0;
     const int32_t *chr = nullptr, *pos = nullptr, *end = nullptr;  // end = Position + Length
     const int32_t *chr_first = nullptr;                            // n_ref + 1
+    const int32_t *bin_seg = nullptr, *bin_off = nullptr;          // bin_off: n_ref + 1
+    int32_t bin_shift = 12;
 };
 
 // An aligned block in registers/local memory (SingleBamRec_t).
@@ -88,6 +94,44 @@ SQ_HD int32_t upper_bound_i32(const int32_t *a, int32_t lo, int32_t hi, int32_t 
         if (a[mid] <= v) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// Segment of chromosome c (c0 = chr_first[c] <= result < c1 = chr_first[c+1], c1 > c0) that holds position x,
+// clamped to the first / last segment of the chromosome when x lies outside [0, chromosome length).
+SQ_HD int32_t seg_at(const NodeTable &nt, int32_t c, int32_t c0, int32_t c1, int32_t x) {
+    if (x < nt.pos[c0]) return c0;
+    if (x >= nt.end[c1 - 1]) return c1 - 1;
+    if (nt.bin_seg) {
+        const int32_t bo = nt.bin_off[c] + (x >> nt.bin_shift);
+        int32_t j = nt.bin_seg[bo];
+        if (nt.end[j] > x) return j;
+        int32_t hi = bo + 1 < nt.bin_off[c + 1] ? nt.bin_seg[bo + 1] : c1 - 1;  // segment holding the start of the next bin
+        if (hi - j <= 4) { do { j++; } while (nt.end[j] <= x); return j; }
+        return upper_bound_i32(nt.end, j + 1, hi + 1, x);
+    }
+    return upper_bound_i32(nt.end, c0, c1, x);
+}
+// value of bin k of chromosome c: the segment holding position k << bin_shift (the last segment of c at the chromosome end)
+SQ_HD int32_t bin_seg_value(const NodeTable &nt, int32_t c, int32_t k) {
+    const int32_t c0 = nt.chr_first[c], c1 = nt.chr_first[c + 1];
+    if (c1 <= c0) return c0;
+    const int32_t j = upper_bound_i32(nt.end, c0, c1, k << nt.bin_shift);
+    return j < c1 ? j : c1 - 1;
+}
+// first segment of c with End > v   (== upper_bound_i32(nt.end, c0, c1, v))
+SQ_HD int32_t seg_first_end_gt(const NodeTable &nt, int32_t c, int32_t c0, int32_t c1, int32_t v) {
+    if (c1 <= c0) return c0;
+    if (v >= nt.end[c1 - 1]) return c1;
+    return seg_at(nt, c, c0, c1, v);
+}
+// first segment of c with End >= v  (== lower_bound_i32(nt.end, c0, c1, v))
+SQ_HD int32_t seg_first_end_ge(const NodeTable &nt, int32_t c, int32_t c0, int32_t c1, int32_t v) {
+    return seg_first_end_gt(nt, c, c0, c1, v - 1);
+}
+// last segment of c with Position <= v, c0-1 if none  (== upper_bound_i32(nt.pos, c0, c1, v) - 1)
+SQ_HD int32_t seg_last_pos_le(const NodeTable &nt, int32_t c, int32_t c0, int32_t c1, int32_t v) {
+    if (c1 <= c0 || v < nt.pos[c0]) return c0 - 1;
+    return seg_at(nt, c, c0, c1, v);
 }
 
 // Own blocks of record r sorted by read position (SortbyReadPos: std::sort on <=16 elements is an

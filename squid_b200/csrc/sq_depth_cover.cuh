@@ -21,7 +21,7 @@ SQ_HD bool depth_contained(const NodeTable &nt, int32_t j, int32_t chr, int32_t 
 SQ_HD int32_t depth_target(const NodeTable &nt, int32_t chr, int32_t start, int32_t len) {
     if (chr < 0 || chr >= nt.n_ref) return kNoNode;
     const int32_t c0 = nt.chr_first[chr], c1 = nt.chr_first[chr + 1];
-    const int32_t n = upper_bound_i32(nt.end, c0, c1, start);  // first segment with End > start
+    const int32_t n = seg_first_end_gt(nt, chr, c0, c1, start);  // first segment with End > start
     if (len <= kSeedThresh) {
         for (int32_t j = (n - 3 > c0 ? n - 3 : c0); j < n; j++)
             if (depth_contained(nt, j, chr, start, len)) return j;

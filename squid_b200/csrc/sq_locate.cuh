@@ -56,8 +56,8 @@ SQ_HD int32_t locate_block(const NodeTable &nt, const Blk &b, Cursor &cur, bool 
     }
     const int32_t c0 = nt.chr_first[c], c1 = nt.chr_first[c + 1];
     // segments that fit: lo = first with End >= p+m-5, hi = last with Position <= p+5
-    const int32_t lo = lower_bound_i32(nt.end, c0, c1, b.ref_pos + b.match_ref - kLocateTol);
-    const int32_t hi = upper_bound_i32(nt.pos, c0, c1, b.ref_pos + kLocateTol) - 1;
+    const int32_t lo = seg_first_end_ge(nt, c, c0, c1, b.ref_pos + b.match_ref - kLocateTol);
+    const int32_t hi = seg_last_pos_le(nt, c, c0, c1, b.ref_pos + kLocateTol);
     if (cur.known) {
         const int32_t i = cur.idx;
         const bool forward = nt.chr[i] < c || (nt.chr[i] == c && nt.pos[i] <= b.ref_pos);  // :1214
@@ -128,7 +128,7 @@ SQ_HD bool read_pair_discordant_nocheck(const ReadView &rv) {  // IsPairDiscorda
 SQ_HD int32_t spanning_node(const NodeTable &nt, const Blk &b, bool ffi_known, int32_t ffi, bool *sensitive) {
     const int32_t c = b.ref_id;
     const int32_t c0 = nt.chr_first[c], c1 = nt.chr_first[c + 1];
-    int32_t n0 = upper_bound_i32(nt.pos, c0, c1, b.ref_pos) - 1;  // last segment with Position <= p
+    int32_t n0 = seg_last_pos_le(nt, c, c0, c1, b.ref_pos);  // last segment with Position <= p
     if (n0 < c0) n0 = c0;
     if (nt.pos[n0] == b.ref_pos && n0 - 1 >= c0) {
         if (!ffi_known) { *sensitive = true; return n0; }

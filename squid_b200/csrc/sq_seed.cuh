@@ -63,6 +63,7 @@ struct SeedInputs {
     const RestBlock *rest; int32_t n_rest;
     int32_t read_len;
     int64_t first_kept;
+    long long *prof_out = nullptr;  // SQ_SEED_PROF builds: 12 int64 per island
 };
 
 struct SeedState {
@@ -164,8 +165,17 @@ struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): 
 };
 #endif
 
+#if defined(SQ_SEED_PROF) && defined(__CUDA_ARCH__)
+#define SQ_PROF_T0() long long prof_t_ = clock64()
+#define SQ_PROF_ADD(k) do { const long long n_ = clock64(); prof[k] += n_ - prof_t_; prof_t_ = n_; } while (0)
+#else
+#define SQ_PROF_T0() do {} while (0)
+#define SQ_PROF_ADD(k) do {} while (0)
+#endif
+
 template <class W>
 struct SeedMachineT {
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     SeedInputs in;
     SeedState st;
     SeedOp *out; int32_t out_cap;
@@ -411,17 +421,37 @@ struct SeedMachineT {
         return W::sum(cnt);
     }
 
-    SQ_HD void pc_margin(int64_t r, int32_t chrG, int32_t m0, int32_t curEndPos, int32_t &nM) {  // :420-434 for one entry
+    // :420-434 for one PartialAlignCluster entry: the margin position it contributes, if any
+    SQ_HD bool pc_margin_value(int64_t r, int32_t chrG, int32_t m0, int32_t curEndPos, int32_t *v) const {
         const int32_t thresh = kSeedThresh;
-        if (e_chr(r) != chrG) return;
+        if (e_chr(r) != chrG) return false;
         const int32_t p0 = e_pos(r), p1 = p0 + e_len(r);
         const bool rv = e_rev(r);
         if (e_readpos(r) > 15 && p0 > m0 - thresh && p0 < curEndPos + thresh) {
-            if (rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
-            else if (!rv) push_margin(nM, p0);
-        } else {
-            if (rv && p0 > m0 - thresh && p0 < curEndPos + thresh) push_margin(nM, p0);
-            else if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) push_margin(nM, p1);
+            if (rv && p1 > m0 - thresh && p1 < curEndPos + thresh) { *v = p1; return true; }
+            if (!rv) { *v = p0; return true; }
+            return false;
+        }
+        if (rv && p0 > m0 - thresh && p0 < curEndPos + thresh) { *v = p0; return true; }
+        if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) { *v = p1; return true; }
+        return false;
+    }
+    // Lanes split the candidate list [lo,hi) of `list` (pc_rec or dp_rec indices); the margins are sorted afterwards, so
+    // only the multiset matters.  `want_displ`: take displaced PART entries (dp list) / non-displaced entries (pc list).
+    SQ_HD void pc_margins(const int32_t *list, int32_t lo, int32_t hi, bool from_dp, int32_t chrG, int32_t m0, int32_t curEndPos, int32_t &nM) {
+        for (int32_t base = lo; base < hi; base += W::size()) {
+            const int32_t i = base + W::lane();
+            int32_t v = 0;
+            bool has = false;
+            if (i < hi) {
+                const int64_t r = list[i];
+                const uint8_t c = in.cls[r];
+                if (from_dp ? (c & CLS_PART) != 0 : !(c & CLS_DISPL)) has = pc_margin_value(r, chrG, m0, curEndPos, &v);
+            }
+            const int32_t at = W::excl_prefix_sum(has ? 1 : 0), tot = W::sum(has ? 1 : 0);
+            if (nM + tot + 1 >= mcap()) { error = 1; return; }
+            if (has) margin[nM + at] = v;
+            nM += tot;
         }
     }
 
@@ -444,6 +474,42 @@ struct SeedMachineT {
     SQ_HD void add_range(int32_t *diff, int32_t ja, int32_t jb) { if (ja < jb) { W::add(&diff[ja], 1); W::add(&diff[jb], -1); } }
     // a block [p0,p1) spans break b iff p0 < b-thresh and p1 >= b+thresh  <=>  p0+thresh < b <= p1-thresh
     SQ_HD void add_span(int32_t *diff, int32_t nM, int32_t p0, int32_t p1) { add_range(diff, m_upper(nM, p0 + kSeedThresh), m_upper(nM, p1 - kSeedThresh)); }
+    // U independent searches stepped together (the loads of one step do not depend on each other)
+    template <int U>
+    SQ_HD void m_upper_n(int32_t nM, const int32_t *v, int32_t *res) const {
+        int32_t lo[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { lo[u] = 0; hi[u] = nM; }
+        for (int32_t span = nM; span > 0; span >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (lo[u] < hi[u]) { const int32_t m = (lo[u] + hi[u]) >> 1; if (margin[m] <= v[u]) lo[u] = m + 1; else hi[u] = m; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) res[u] = lo[u];
+    }
+    // add_span for the first kept blocks of up to U window records r0 + u*stride (u < U, r < hi) that satisfy `want`
+    // (class bits: value after masking with CONC|PART|DISPL), on chromosome chrG
+    template <int U>
+    SQ_HD void add_span_records(int32_t *diff, int32_t nM, int64_t r0, int64_t stride, int64_t hi, uint8_t want, int32_t chrG) {
+        uint8_t c[U]; uint32_t o[U]; int32_t rc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t r = r0 + u * stride;
+            const bool inr = r < hi;
+            c[u] = inr ? in.cls[r] : (uint8_t)0; o[u] = inr ? in.b.blk_off[r] : 0u; rc[u] = inr ? in.b.ref_id[r] : -1;
+        }
+        bool ok[U]; int32_t v[2 * U], j[2 * U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            ok[u] = (c[u] & (CLS_CONC | CLS_PART | CLS_DISPL)) == want && rc[u] == chrG;
+            const int32_t p0 = ok[u] ? in.b.blk_ref_pos[o[u]] : 0, l = ok[u] ? in.b.blk_match_ref[o[u]] : 0;
+            v[2 * u] = p0 + kSeedThresh; v[2 * u + 1] = p0 + l - kSeedThresh;
+        }
+        m_upper_n<2 * U>(nM, v, j);
+#pragma unroll
+        for (int u = 0; u < U; u++) if (ok[u]) add_range(diff, j[2 * u], j[2 * u + 1]);
+    }
     SQ_HD void scan_inplace(int32_t *a, int32_t n) {
         W::sync();
         int32_t carry = 0;
@@ -477,8 +543,9 @@ struct SeedMachineT {
         const int32_t pmin = bmin + thresh - in.lmax, pmax = bmax - thresh;  // block starts that can span some break
         if (st.offCC < rg) {  // ConcordantCluster window (:457-461)
             const int64_t lo = lb_pos(st.offCC, rg, chrG, pmin), hi = lb_pos(lo, rg, chrG, pmax);
-            for (int64_t r = lo + W::lane(); r < hi; r += W::size())
-                if (isCC(r) && !isDispl(r) && in.b.ref_id[r] == chrG) { const int32_t p0 = e_pos(r); add_span(t_cov, nM, p0, p0 + e_len(r)); }
+            constexpr int U = 4;
+            for (int64_t base = lo; base < hi; base += (int64_t)W::size() * U)
+                add_span_records<U>(t_cov, nM, base + W::lane(), W::size(), hi, CLS_CONC, chrG);
         }
         if (st.offPC < szPC) {  // PartialAlignCluster window (:465-469)
             const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, pmin), hi = lb_pc_pos(lo, szPC, chrG, pmax);
@@ -528,19 +595,40 @@ struct SeedMachineT {
     }
     // Advance st.offCC over the maximal prefix of window entries that pass walk_ok; returns the largest end consumed.
     SQ_HD int32_t consume_cc(int64_t rg, int32_t chrG, int32_t dc, bool first_walk) {
-        int32_t mx = -(1 << 30);
+        constexpr int U = 4;
+        const int32_t NEG = -(1 << 30);
+        const int chunk = W::size() * U;
+        int32_t mx = NEG;
         int64_t x = st.offCC;
         while (x < rg) {
-            const int64_t r = x + W::lane();
-            const bool cc = r < rg && isCC(r);
-            bool ok = false;
-            int32_t p1 = -(1 << 30);
-            if (cc) { const int32_t p0 = e_pos(r); p1 = p0 + e_len(r); ok = walk_ok(first_walk, chrG, dc, e_chr(r), p0, p1); }
-            const int first_bad = W::min((cc && !ok) ? W::lane() : W::size());
-            const int32_t m = W::max((cc && ok && W::lane() < first_bad) ? p1 : -(1 << 30));
+            uint8_t c[U]; uint32_t o[U]; int32_t rc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {  // entry index inside the chunk: u*size + lane (stream order)
+                const int64_t r = x + u * W::size() + W::lane();
+                const bool inr = r < rg;
+                c[u] = inr ? in.cls[r] : (uint8_t)0; o[u] = inr ? in.b.blk_off[r] : 0u; rc[u] = inr ? in.b.ref_id[r] : -1;
+            }
+            int32_t p1[U]; bool cc[U], ok[U];
+            int fb = chunk;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                cc[u] = (c[u] & (CLS_CONC | CLS_PART)) == CLS_CONC;
+                ok[u] = false; p1[u] = NEG;
+                if (cc[u]) {
+                    const int32_t p0 = in.b.blk_ref_pos[o[u]];
+                    p1[u] = p0 + in.b.blk_match_ref[o[u]];
+                    ok[u] = walk_ok(first_walk, chrG, dc, rc[u], p0, p1[u]);
+                    if (!ok[u] && u * W::size() + W::lane() < fb) fb = u * W::size() + W::lane();
+                }
+            }
+            const int first_bad = W::min(fb);
+            int32_t m = NEG;
+#pragma unroll
+            for (int u = 0; u < U; u++) if (cc[u] && ok[u] && u * W::size() + W::lane() < first_bad && p1[u] > m) m = p1[u];
+            m = W::max(m);
             if (m > mx) mx = m;
-            if (first_bad < W::size()) { st.offCC = x + first_bad; return mx; }
-            x += W::size();
+            if (first_bad < chunk) { st.offCC = x + first_bad; return mx; }
+            x += chunk;
         }
         st.offCC = rg;
         return mx;
@@ -655,6 +743,7 @@ struct SeedMachineT {
     // Lines :353-612 for group g, reached at trigger record rg.
     SQ_HD void process_group(int32_t g, int64_t rg) {
         const int32_t thresh = kSeedThresh, RL = in.read_len;
+        SQ_PROF_T0();
         const Group grp = in.G[g];
         int32_t ds = grp.ds; const int32_t de = grp.de, chrG = grp.chr, nextright = grp.right;
         const DiscBlock *D = in.D;
@@ -703,6 +792,7 @@ struct SeedMachineT {
             ps = lo;
             for (pe = ps; pe < in.nP && in.Pchr[pe] == chrG && in.Ppos[pe] < nextright + RL; pe++) {}
         }
+        SQ_PROF_ADD(1);
         while (ds != de) {
             if (ds != 0 && D[ds].chr != D[ds - 1].chr && st.offCC >= rg && st.offPC >= szPC) curStartPos = D[ds].pos;
             isClusternSplit = false;
@@ -722,15 +812,17 @@ struct SeedMachineT {
             const int32_t m0 = D[ds].pos;  // MarginPositions.front() while still unsorted
             if (st.offPC < szPC) {  // :420-434; an entry contributes only if its block start lies in (m0-thresh-lmax, curEndPos+thresh)
                 const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, m0 - thresh - in.lmax), hi = lb_pc_pos(lo, szPC, chrG, curEndPos + thresh);
-                for (int32_t i = lo; i < hi; i++) if (!isDispl(in.pc_rec[i])) pc_margin(in.pc_rec[i], chrG, m0, curEndPos, nM);
+                pc_margins(in.pc_rec, lo, hi, false, chrG, m0, curEndPos, nM);
                 const int64_t wp = in.pc_rec[st.offPC];
-                for (int32_t k = lb_list(in.dp_rec, in.n_dp, wp); k < in.n_dp && in.dp_rec[k] < rg; k++)
-                    if (in.cls[in.dp_rec[k]] & CLS_PART) pc_margin(in.dp_rec[k], chrG, m0, curEndPos, nM);
+                if (in.n_dp > 0 && !error) pc_margins(in.dp_rec, lb_list(in.dp_rec, in.n_dp, wp), lb_list(in.dp_rec, in.n_dp, rg), true, chrG, m0, curEndPos, nM);
             }
             if (error) return;
+            SQ_PROF_ADD(2);
             sort_margins(nM);
             if (error) return;
+            SQ_PROF_ADD(3);
             tabulate_breaks(nM, ds, de, chrG, in.D[grp.ds].pos, rg, szPC);
+            SQ_PROF_ADD(4);
             const int32_t *t_sr = margin + mcap(), *t_pl = margin + 2 * mcap(), *t_pr = margin + 3 * mcap(), *t_cov = margin + 4 * mcap(), *t_rest = margin + 5 * mcap();
             int32_t lastCurser = -1, lastSupport = 0;
             for (int32_t ib = 0; ib < nM;) {
@@ -786,6 +878,7 @@ struct SeedMachineT {
                 curStartPos = disEndPos; curEndPos = disEndPos;
                 st.markedStart = disEndPos; st.markedChr = chrG;
             }
+            SQ_PROF_ADD(5);
             // :529-532
             while (st.offCC < rg && e_chr(st.offCC) < chrG) st.offCC = nextCC(st.offCC + 1, rg);
             while (st.offPC < szPC && e_chr(in.pc_rec[st.offPC]) < chrG) st.offPC++;
@@ -799,8 +892,10 @@ struct SeedMachineT {
                 if (a > concord0pos) concord0pos = a;
                 if (bq > concord0pos) concord0pos = bq;
             }
+            SQ_PROF_ADD(6);
             // :570-601 extend the last segment to the next 0-coverage position if the stream already shows one
             extend_to_zero_coverage(rg, szPC, dc, recChr, recPos, concord0pos, curStartPos);
+            SQ_PROF_ADD(7);
             ds = dc;
             if (error) return;
         }
@@ -818,7 +913,7 @@ struct SeedMachineT {
             const int64_t rg = in.trigger[g];
             const Group grp = in.G[g];
             if (rg >= in.n_rec) break;
-            replay_between(r_prev, rg, dChr, dRight, grp.chr, in.D[grp.ds].pos, true);
+            { SQ_PROF_T0(); replay_between(r_prev, rg, dChr, dRight, grp.chr, in.D[grp.ds].pos, true); SQ_PROF_ADD(0); }
             process_group(g, rg);
             if (error) return g;
             dChr = grp.chr; dRight = grp.right;

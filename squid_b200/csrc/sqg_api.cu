@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sq_classify.cuh"
@@ -228,6 +229,10 @@ __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n
     }
     span[i] = (int32_t)((r1 - w0) > 0x7fffffff ? 0x7fffffff : (r1 - w0));  // records the island may have to walk
 }
+__global__ void k_gather_i32(const int32_t *src, const int32_t *idx, int32_t n, int32_t *out) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
 constexpr int kSeedBlock = 512;        // threads per block of the seed kernels
 constexpr int kHeavySpan = 1 << 14;    // islands spanning more records than this get a whole block instead of a warp
 struct IsHeavyOp {
@@ -242,7 +247,18 @@ __device__ __forceinline__ void seed_one_island(const SeedInputs &in, int32_t i,
     const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
     sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
     sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
+#ifdef SQ_SEED_PROF
+    long long t0_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0_));
+#endif
     const int32_t gd = sm.run_island(ga, gb, inherited);
+#ifdef SQ_SEED_PROF
+    if (W::lane() == 0 && in.prof_out) {
+        long long t1_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1_));
+        long long *q = in.prof_out + (int64_t)i * 12;
+        q[0] = t0_; q[1] = t1_; q[2] = gb - ga; q[3] = W::size();
+        for (int k = 0; k < 8; k++) q[4 + k] = sm.prof[k];
+    }
+#endif
     if (W::lane() == 0) { g_done[i] = gd; n_out[i] = sm.st.n_out; if (sm.error) atomicMax(err, sm.error); }
     if (n_out_ret) *n_out_ret = sm.st.n_out;
 }
@@ -260,7 +276,7 @@ __global__ void __launch_bounds__(kSeedBlock) k_seed_prefix(SeedInputs in, const
 }
 // All other islands in parallel, each starting from an inherited (far-left) last segment: blocks [0, n_heavy) take one
 // heavy island each (SeedMachineT<CoopBlock>), the remaining blocks take one light island per warp (SeedMachineT<CoopWarp>).
-__global__ void __launch_bounds__(kSeedBlock) k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar,
+__global__ void __launch_bounds__(kSeedBlock, 2) k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar,
                                                            SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err,
                                                            const int32_t *heavy, int32_t n_heavy, const int32_t *light, int32_t n_light) {
     if ((int32_t)blockIdx.x < n_heavy) {
@@ -273,6 +289,19 @@ __global__ void __launch_bounds__(kSeedBlock) k_seed_islands(SeedInputs in, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// kernels: segment table index
+// ------------------------------------------------------------------------------------------------
+// bin_seg[bin_off[c] + k] = segment of chromosome c holding position k << bin_shift (the last segment of c when that
+// position is the chromosome end itself)
+__global__ void k_build_bins(NodeTable nt, int32_t *bin_seg, int32_t n_bins) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bins) return;
+    int32_t lo = 0, hi = nt.n_ref;  // chromosome of bin i: last c with bin_off[c] <= i
+    while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (nt.bin_off[m + 1] <= i) lo = m + 1; else hi = m; }
+    bin_seg[i] = bin_seg_value(nt, lo, i - nt.bin_off[lo]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernels: depth
 // ------------------------------------------------------------------------------------------------
 __global__ void k_depth_disc(NodeTable nt, const DiscBlock *D, int32_t nD, int32_t *cnt, int32_t *sum) {
@@ -281,7 +310,7 @@ __global__ void k_depth_disc(NodeTable nt, const DiscBlock *D, int32_t nD, int32
     const DiscBlock d = D[k];
     if (d.chr < 0 || d.chr >= nt.n_ref) return;
     const int32_t c0 = nt.chr_first[d.chr], c1 = nt.chr_first[d.chr + 1];
-    const int32_t j = upper_bound_i32(nt.pos, c0, c1, d.pos) - 1;  // segment whose turn consumes this block (:774)
+    const int32_t j = seg_last_pos_le(nt, d.chr, c0, c1, d.pos);  // segment whose turn consumes this block (:774)
     if (j >= c0 && d.pos >= nt.pos[j] && d.pos + d.len <= nt.end[j]) { atomicAdd(&cnt[j], 1); atomicAdd(&sum[j], d.len); }
 }
 
@@ -651,7 +680,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
-    ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
+    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
@@ -889,8 +918,22 @@ static int install_nodes(sqg_ctx *ctx) {  // from h_nchr/h_npos/h_nend
         CK(cudaMemcpyAsync(ctx->d_nend.p, ctx->h_nend.data(), N * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaMemcpyAsync(ctx->d_chr_first.p, ctx->h_chr_first.data(), (n_ref + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->nt.n = N; ctx->nt.n_ref = n_ref; ctx->nt.chr = ctx->d_nchr.p; ctx->nt.pos = ctx->d_npos.p; ctx->nt.end = ctx->d_nend.p; ctx->nt.chr_first = ctx->d_chr_first.p;
+    {   // coarse position index over the tiling (sq_common.cuh: seg_at)
+        int64_t total = 0;
+        for (int32_t c = 0; c < n_ref; c++) total += ctx->ref_len[c] > 0 ? ctx->ref_len[c] : 0;
+        int32_t sh = 12;
+        while ((total >> sh) > (8ll << 20)) sh++;  // at most ~8M bins
+        ctx->h_bin_off.assign(n_ref + 1, 0);
+        for (int32_t c = 0; c < n_ref; c++) ctx->h_bin_off[c + 1] = ctx->h_bin_off[c] + ((ctx->ref_len[c] > 0 ? ctx->ref_len[c] : 0) >> sh) + 1;
+        const int32_t n_bins = ctx->h_bin_off[n_ref];
+        CK(ctx->d_bin_off.ensure(n_ref + 2)); CK(ctx->d_bin_seg.ensure(n_bins + 1));
+        CK(cudaMemcpyAsync(ctx->d_bin_off.p, ctx->h_bin_off.data(), (n_ref + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->nt.bin_off = ctx->d_bin_off.p; ctx->nt.bin_shift = sh; ctx->nt.bin_seg = nullptr;
+        LAUNCH(k_build_bins, blocks_for(n_bins), kThreads, ctx->nt, ctx->d_bin_seg.p, n_bins);
+        ctx->nt.bin_seg = ctx->d_bin_seg.p;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_nodes = true; ctx->have_edge_table = false;
     return SQG_OK;
 }
@@ -993,7 +1036,7 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     CK(cudaMemcpyAsync(ctx->h_counters.p + 5, ctx->d_counters.p + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int32_t n_isl = *(int32_t *)(ctx->h_counters.p + 5);
-    CK(ctx->d_cap_ops.ensure(n_isl + 2)); CK(ctx->d_cap_mar.ensure(n_isl + 2)); CK(ctx->d_off_ops.ensure(n_isl + 2)); CK(ctx->d_off_mar.ensure(n_isl + 2));
+    CK(ctx->d_cap_ops.ensure(2 * (size_t)n_isl + 4)); CK(ctx->d_cap_mar.ensure(n_isl + 2)); CK(ctx->d_off_ops.ensure(n_isl + 2)); CK(ctx->d_off_mar.ensure(n_isl + 2));
     CK(ctx->d_isl_nout.ensure(n_isl + 1)); CK(ctx->d_isl_gdone.ensure(n_isl + 1));
     CK(cudaMemsetAsync(ctx->d_cap_ops.p, 0, (n_isl + 2) * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->d_cap_mar.p, 0, (n_isl + 2) * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_isl_nout.p, 0, (n_isl + 1) * 4, ctx->stream));
@@ -1031,10 +1074,38 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     }
     const int32_t n_heavy = ((int32_t *)(ctx->h_counters.p + 13))[0], n_light = ((int32_t *)(ctx->h_counters.p + 13))[1];
     ctx->n_heavy = n_heavy;
-    if (n_heavy + n_light > 0)
-        LAUNCH(k_seed_islands, (unsigned)(n_heavy + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
+    if (n_heavy > 1) {  // longest islands first: the kernel's critical path is its largest island
+        // d_cap_ops is free again after the offset scans: sort scratch [keys | keys2]
+        int32_t *k1 = ctx->d_cap_ops.p, *k2 = ctx->d_cap_ops.p + n_heavy;
+        LAUNCH(k_gather_i32, blocks_for(n_heavy), kThreads, ctx->d_span.p, ctx->d_heavy.p, n_heavy, k1);
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, k1, k2, ctx->d_heavy.p, ctx->d_light.p + n_light, n_heavy, 0, 32, ctx->stream));
+        ENSURE_TEMP(tb);
+        CK(cub::DeviceRadixSort::SortPairsDescending(ctx->d_temp.p, tb, k1, k2, ctx->d_heavy.p, ctx->d_light.p + n_light, n_heavy, 0, 32, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_heavy.p, ctx->d_light.p + n_light, n_heavy * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->launches += 2;
+    }
+#ifdef SQ_SEED_PROF
+    long long *d_prof = nullptr;
+    if (getenv("SQG_SEED_PROF_OUT")) { cudaMalloc(&d_prof, (size_t)n_isl * 12 * 8); cudaMemset(d_prof, 0, (size_t)n_isl * 12 * 8); cudaDeviceSynchronize(); in.prof_out = d_prof; }
+#endif
+    if (n_heavy + n_light > 0) {
+        k_seed_islands<<<(unsigned)(n_heavy + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, 0, ctx->stream>>>(in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
                ctx->d_ops.p, ctx->d_margin.p, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, ctx->d_heavy.p, n_heavy, ctx->d_light.p, n_light);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
     PHASE_END("seed");
+#ifdef SQ_SEED_PROF
+    if (d_prof) {
+        cudaStreamSynchronize(ctx->stream);
+        std::vector<long long> hp((size_t)n_isl * 12); std::vector<int32_t> hs(n_isl);
+        cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost); cudaMemcpy(hs.data(), ctx->d_span.p, n_isl * 4, cudaMemcpyDeviceToHost);
+        FILE *f = fopen(getenv("SQG_SEED_PROF_OUT"), "wb");
+        if (f) { fwrite(&n_isl, 4, 1, f); fwrite(hs.data(), 4, n_isl, f); fwrite(hp.data(), 8, hp.size(), f); fclose(f); }
+        cudaFree(d_prof);
+    }
+#endif
     // stitch the island op lists in genome order (host: a few hundred thousand ops at most)
     std::vector<int32_t> h_nout(n_isl), h_gdone(n_isl), h_isl(n_isl + 1);
     std::vector<int64_t> h_off(n_isl + 1);

@@ -117,7 +117,8 @@ struct sqg_ctx {
     // segment table
     bool have_nodes = false;
     std::vector<int32_t> h_nchr, h_npos, h_nend, h_chr_first;
-    sq::DBuf<int32_t> d_nchr, d_npos, d_nend, d_chr_first;
+    sq::DBuf<int32_t> d_nchr, d_npos, d_nend, d_chr_first, d_bin_off, d_bin_seg;
+    std::vector<int32_t> h_bin_off;
     sq::NodeTable nt;
     sq::DBuf<int32_t> d_cnt3, d_sum3;
 

@@ -201,13 +201,24 @@ int main(int argc, char **argv) {
     for (int32_t c = n_ref - 1; c >= 0; c--) if (chr_first[c] == N && c + 1 <= n_ref) chr_first[c] = chr_first[c + 1];
     NodeTable nt;
     nt.n = N; nt.n_ref = n_ref; nt.chr = nchr.data(); nt.pos = npos.data(); nt.end = nend.data(); nt.chr_first = chr_first.data();
+    // coarse position index, as sqg_api.cu builds it (a small shift makes every branch of seg_at run on the test cases)
+    std::vector<int32_t> bin_off(n_ref + 1, 0), bin_seg;
+    nt.bin_shift = getenv("SQ_EMUL_BIN_SHIFT") ? atoi(getenv("SQ_EMUL_BIN_SHIFT")) : 12;
+    if (nt.bin_shift > 0) {
+        for (int32_t c = 0; c < n_ref; c++) bin_off[c + 1] = bin_off[c] + (conc.ref_len[c] >> nt.bin_shift) + 1;
+        bin_seg.resize(bin_off[n_ref]);
+        nt.bin_off = bin_off.data();
+        for (int32_t c = 0; c < n_ref; c++)
+            for (int32_t k = 0; k < bin_off[c + 1] - bin_off[c]; k++) bin_seg[bin_off[c] + k] = bin_seg_value(nt, c, k);
+        nt.bin_seg = bin_seg.data();
+    }
 
     // ---- depth ----
     std::vector<int32_t> cnt(3 * (size_t)N, 0), sum(3 * (size_t)N, 0);
     for (int32_t k = 0; k < nD; k++) {
         const DiscBlock &d = pre.disc[k];
         const int32_t c0 = chr_first[d.chr], c1 = chr_first[d.chr + 1];
-        int32_t j = upper_bound_i32(nt.pos, c0, c1, d.pos) - 1;
+        int32_t j = seg_last_pos_le(nt, d.chr, c0, c1, d.pos);
         if (j >= c0 && d.pos >= nt.pos[j] && d.pos + d.len <= nt.end[j]) { cnt[j]++; sum[j] += d.len; }
     }
     bool other_nonempty = false;

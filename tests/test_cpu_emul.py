@@ -26,12 +26,13 @@ def emul_bin():
 
 
 @pytest.mark.parametrize("case", ["chr17_3k", "fourchr_6k"])
-@pytest.mark.parametrize("one_island", [False, True])
-def test_stepped_rules_match_golden(case, one_island, emul_bin, tmp_path):
+@pytest.mark.parametrize("one_island,bin_shift", [(False, 12), (True, 12), (False, 4), (False, 0)])
+def test_stepped_rules_match_golden(case, one_island, bin_shift, emul_bin, tmp_path):
     g = pyref.load_dumps(os.path.join(GOLD, case, "ref"))
     bps = pyref.breakpoints_of(g)
     bps.tofile(str(tmp_path / "bps.bin"))
     env = dict(os.environ)
+    env["SQ_EMUL_BIN_SHIFT"] = str(bin_shift)  # segment-table position index: 0 = plain binary searches, 4 = many tiny bins
     if one_island:
         env["SQ_EMUL_ONE_ISLAND"] = "1"
     r = subprocess.run([emul_bin, os.path.join(GOLD, case, "conc.sqmb"), os.path.join(GOLD, case, "chim.sqmb"), str(tmp_path), str(tmp_path / "bps.bin")],
