@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <thread>
+#include <omp.h>
 #include <chrono>
 #include <cstdio>
 
@@ -43,27 +44,33 @@ bool pair_disc(const View &v, int32_t ft, int32_t st_) {  // ReadRec.cpp:211-228
 // observable, so the pre-pass must produce exactly libstdc++'s std::sort permutation.  std::sort
 // is introsort: quicksort partitions (median of first+1 / middle / last-1 moved to the front, unguarded Hoare partition
 // around it, recursion on the right part, loop on the left) down to ranges of 16, heap sort when the depth budget
-// 2*floor(log2 n) runs out, and a final insertion sort.  After a partition the two parts never interact again, so they can
-// be sorted by different threads without changing a single comparison; the final insertion pass is stable and never
-// moves an element across a partition boundary.  tests/test_cpu_host_twin.py checks this routine against std::sort.
+// 2*floor(log2 n) runs out, and a final insertion sort.  Two facts make it parallel without changing a single outcome:
+//   * after a partition the two parts never interact again (the final insertion pass is stable and never moves an element
+//     across a partition boundary), so they can be finished by different threads;
+//   * the Hoare partition itself has a closed form.  With L = positions (ascending) whose element is not < pivot and
+//     R = positions (descending) whose element is not > pivot, the loop swaps L[i] <-> R[i] for i < m, m = #{i : L[i] < R[i]},
+//     and returns L[m] if that lies left of R[m-1], else R[m-1]; every scan of the loop only ever looks at positions no
+//     earlier swap has touched.  So big ranges are partitioned by all threads together (collect L and R per chunk, pair
+//     them up, swap in parallel).
+// tests/test_cpu_host_twin.py checks this routine against std::sort (ties, sorted, reversed and organ-pipe inputs).
 struct SortKey { uint64_t key; uint32_t k; };
 inline bool sk_lt(const SortKey &x, const SortKey &y) { return x.key < y.key; }
-void sort_loop(SortKey *first, SortKey *last, int depth, int fanout) {
-    std::vector<std::thread> kids;
+inline void median_to_first(SortKey *first, SortKey *last) {  // std::__move_median_to_first(first, first+1, mid, last-1)
+    SortKey *mid = first + (last - first) / 2, *a = first + 1, *c = last - 1;
+    if (sk_lt(*a, *mid)) {
+        if (sk_lt(*mid, *c)) std::swap(*first, *mid);
+        else if (sk_lt(*a, *c)) std::swap(*first, *c);
+        else std::swap(*first, *a);
+    } else if (sk_lt(*a, *c)) std::swap(*first, *a);
+    else if (sk_lt(*mid, *c)) std::swap(*first, *c);
+    else std::swap(*first, *mid);
+}
+void sort_loop(SortKey *first, SortKey *last, int depth) {  // std::__introsort_loop
     while (last - first > 16) {
         if (depth == 0) { std::partial_sort(first, last, last, sk_lt); break; }
         --depth;
-        SortKey *mid = first + (last - first) / 2, *a = first + 1, *c = last - 1;
-        // median of (*a, *mid, *c) to *first
-        if (sk_lt(*a, *mid)) {
-            if (sk_lt(*mid, *c)) std::swap(*first, *mid);
-            else if (sk_lt(*a, *c)) std::swap(*first, *c);
-            else std::swap(*first, *a);
-        } else if (sk_lt(*a, *c)) std::swap(*first, *a);
-        else if (sk_lt(*mid, *c)) std::swap(*first, *c);
-        else std::swap(*first, *mid);
-        // unguarded partition of [first+1, last) around *first
-        SortKey *lo = first + 1, *hi = last;
+        median_to_first(first, last);
+        SortKey *lo = first + 1, *hi = last;  // std::__unguarded_partition(first+1, last, first)
         for (;;) {
             while (sk_lt(*lo, *first)) ++lo;
             --hi;
@@ -72,25 +79,77 @@ void sort_loop(SortKey *first, SortKey *last, int depth, int fanout) {
             std::swap(*lo, *hi);
             ++lo;
         }
-        SortKey *cut = lo;
-        if (fanout > 0 && last - cut > 4096) {
-            --fanout;
-            kids.emplace_back(sort_loop, cut, last, depth, fanout);
-        } else sort_loop(cut, last, depth, 0);
-        last = cut;
+        sort_loop(lo, last, depth);
+        last = lo;
     }
-    for (std::thread &t : kids) t.join();
 }
-void sort_like_std(SortKey *first, SortKey *last, int fanout) {
-    if (first == last) return;
-    int lg = 0;
-    for (size_t n = (size_t)(last - first); n > 1; n >>= 1) lg++;
-    sort_loop(first, last, 2 * lg, fanout);
-    for (SortKey *i = first + 1; i < last; ++i) {  // final insertion sort
+inline void insertion_sort(SortKey *first, SortKey *last) {  // what the final insertion pass does to one partition
+    for (SortKey *i = first + 1; i < last; ++i) {
         const SortKey v = *i;
         SortKey *j = i;
         while (j > first && sk_lt(v, *(j - 1))) { *j = *(j - 1); --j; }
         *j = v;
+    }
+}
+// Closed-form Hoare partition of [first+1, last) around *first, all threads together.  Returns the cut.
+SortKey *partition_parallel(SortKey *first, SortKey *last, int T, std::vector<uint32_t> &Lg, std::vector<uint32_t> &Rg) {
+    SortKey *base = first + 1;
+    const size_t n = (size_t)(last - base);
+    const SortKey piv = *first;
+    std::vector<size_t> cl((size_t)T + 1, 0), cr((size_t)T + 1, 0);
+    Lg.resize(n); Rg.resize(n);
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        const size_t a = n * (size_t)t / (size_t)T, b = n * (size_t)(t + 1) / (size_t)T;
+        size_t nl = 0, nr = 0;
+        for (size_t i = a; i < b; i++) { nl += !sk_lt(base[i], piv); nr += !sk_lt(piv, base[i]); }
+        cl[(size_t)t + 1] = nl; cr[(size_t)t + 1] = nr;
+#pragma omp barrier
+#pragma omp single
+        { for (int q = 0; q < T; q++) { cl[(size_t)q + 1] += cl[(size_t)q]; cr[(size_t)q + 1] += cr[(size_t)q]; } }
+        size_t wl = cl[(size_t)t], wr = cr[(size_t)t];
+        for (size_t i = a; i < b; i++) {
+            if (!sk_lt(base[i], piv)) Lg[wl++] = (uint32_t)i;
+            if (!sk_lt(piv, base[i])) Rg[wr++] = (uint32_t)i;   // ascending here; R[i] of the text is Rg[nR-1-i]
+        }
+    }
+    const size_t nL = cl[(size_t)T], nR = cr[(size_t)T];
+    // m = #{i : L[i] < R[i]}: the predicate is monotone in i
+    size_t lo = 0, hi = std::min(nL, nR);
+    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (Lg[mid] < Rg[nR - 1 - mid]) lo = mid + 1; else hi = mid; }
+    const size_t m = lo;
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (long long i = 0; i < (long long)m; i++) std::swap(base[Lg[(size_t)i]], base[Rg[nR - 1 - (size_t)i]]);
+    size_t cut;
+    if (m == 0) cut = Lg[0];
+    else cut = (m < nL && Lg[m] < Rg[nR - m]) ? Lg[m] : Rg[nR - m];  // R[m-1] = Rg[nR-m]
+    return base + cut;
+}
+void sort_like_std(SortKey *first, SortKey *last, int threads) {
+    if (first == last) return;
+    int lg = 0;
+    for (size_t n = (size_t)(last - first); n > 1; n >>= 1) lg++;
+    struct Range { SortKey *a, *b; int depth; };
+    const int T = std::max(1, std::min(threads, 32));
+    const ptrdiff_t kBig = 1 << 15;  // ranges above this are partitioned by all threads together
+    std::vector<Range> big, small;
+    big.push_back(Range{first, last, 2 * lg});
+    std::vector<uint32_t> Lg, Rg;
+    while (!big.empty()) {
+        Range r = big.back();
+        big.pop_back();
+        if (T == 1 || r.b - r.a <= kBig || r.depth == 0) { small.push_back(r); continue; }
+        median_to_first(r.a, r.b);
+        SortKey *cut = partition_parallel(r.a, r.b, T, Lg, Rg);
+        big.push_back(Range{r.a, cut, r.depth - 1});
+        big.push_back(Range{cut, r.b, r.depth - 1});
+    }
+    // the remaining partitions: sequential introsort loop + their share of the final insertion sort, one task each
+#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
+    for (long long i = 0; i < (long long)small.size(); i++) {
+        sort_loop(small[(size_t)i].a, small[(size_t)i].b, small[(size_t)i].depth);
+        insertion_sort(small[(size_t)i].a, small[(size_t)i].b);
     }
 }
 }  // namespace
@@ -109,9 +168,19 @@ extern "C" int sqh_selftest_sort(int64_t n, uint64_t seed, uint64_t range, int p
     }
     b = a;
     std::sort(a.begin(), a.end(), sk_lt);
-    sort_like_std(b.data(), b.data() + b.size(), fanout);
+    sort_like_std(b.data(), b.data() + b.size(), fanout == 0 ? 1 : (fanout < 0 ? omp_get_num_procs() : fanout));
     for (size_t i = 0; i < a.size(); i++) if (a[i].key != b[i].key || a[i].k != b[i].k) return 0;
     return 1;
+}
+
+// test hook: milliseconds sort_like_std needs for n random keys from [0,range) on `threads` threads
+extern "C" double sqh_time_sort(int64_t n, uint64_t seed, uint64_t range, int threads) {
+    std::vector<SortKey> a((size_t)n);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    for (int64_t i = 0; i < n; i++) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; a[(size_t)i] = SortKey{range ? x % range : 0, (uint32_t)i}; }
+    const auto t0 = std::chrono::steady_clock::now();
+    sort_like_std(a.data(), a.data() + a.size(), threads <= 0 ? omp_get_num_procs() : threads);
+    return 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out) {
@@ -120,61 +189,85 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     auto lap = [&](const char *w) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[prepass] %s %.1f ms\n", w, 1e3 * std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     out = ChimPrepass();
     typedef SortKey DB;  // key = (RefID,RefPos) packed, k = block index
-    std::vector<DB> dis;
-    dis.reserve((size_t)c.n_blk);
-    std::vector<std::pair<int, int>> part((size_t)n_ref, std::make_pair(0, 0));  // resize()d then appended (:203-204)
-    auto push_dis = [&](uint32_t k) { dis.push_back(DB{((uint64_t)(uint32_t)c.blk_ref_id[k] << 32) | (uint32_t)c.blk_ref_pos[k], k}); };
-    for (int64_t i = 0; i < c.n_reads; i++) {
-        const uint32_t o = c.read_off[i], e = c.read_off[i + 1], nf = c.n_first[i];
-        const View v{c, o, o + nf, e};
-        const int32_t ft = c.first_total_len[i], st_ = c.second_total_len[i];
-        const bool fl = c.first_lowphred[i], sl = c.second_lowphred[i], mf = c.multi_filter[i];
-        const bool fempty = v.f0 == v.f1, sempty = v.f1 == v.s1;
-        const bool single = (fempty || sempty) && !mf;
-        if (end_disc(v, v.f0, v.f1) || end_disc(v, v.f1, v.s1) || single || pair_disc(v, ft, st_)) {  // :208-213
-            for (uint32_t k = o; k < e; k++) push_dis(k);
-            continue;
-        }
-        bool fin = false, sin = false;
-        for (int m = 0; m < 2; m++) {  // blocks of one mate more than 750 kb apart (:217-239)
-            const uint32_t a = m ? v.f1 : v.f0, b = m ? v.s1 : v.f1;
-            int64_t prev = -1;
-            for (uint32_t k = a; k + 1 < b; k++)
-                if (std::abs(v.pos(k) - v.pos(k + 1)) > 750000) {
-                    if (prev != (int64_t)k) push_dis(k);
-                    push_dis(k + 1);
-                    prev = k + 1;
-                    if (k + 1 == b - 1) (m ? sin : fin) = true;
-                }
-        }
-        if (!fempty && !sempty && std::abs(v.pos(v.f1 - 1) - v.pos(v.s1 - 1)) > 750000) {  // :240-249
-            if (!fin) { push_dis(v.f1 - 1); fin = true; }
-            if (!sin) { push_dis(v.s1 - 1); sin = true; }
-        }
-        if (!fin && !sin) {  // soft-clipped ends of otherwise concordant chimeric reads (:250-259)
-            if (!fempty && v.rpos(v.f0) > 15 && !fl) part.push_back({v.chr(v.f0), v.rev(v.f0) ? v.pos(v.f0) + v.mref(v.f0) : v.pos(v.f0)});
-            if (!fempty) { const uint32_t b = v.f1 - 1; if (ft - v.rpos(b) - v.mread(b) > 15 && !fl) part.push_back({v.chr(b), v.rev(b) ? v.pos(b) : v.pos(b) + v.mref(b)}); }
-            if (!sempty && v.rpos(v.f1) > 15 && !sl) part.push_back({v.chr(v.f1), v.rev(v.f1) ? v.pos(v.f1) + v.mref(v.f1) : v.pos(v.f1)});
-            if (!sempty) {
-                const uint32_t b = v.s1 - 1;
-                if (st_ - v.rpos(b) - v.mread(b) > 15 && !sl) {
-                    // `!bamdiscordant.back().Same(SecondMate.back())` (:257); back() of an empty vector is UB in the
-                    // reference, we read it as "not the same".  Same() compares every field incl. IsFirstRead.
-                    bool same = false;
-                    if (!dis.empty()) {
-                        const uint32_t l = dis.back().k;
-                        // which read does block l belong to? only its IsFirstRead matters: l is a SecondMate block iff it
-                        // lies at/after the first SecondMate block of its own read; find that read by binary search
-                        const uint32_t *ro = c.read_off;
-                        int64_t lo = 0, hi = c.n_reads;
-                        while (lo < hi) { const int64_t m2 = (lo + hi) >> 1; if (ro[m2 + 1] <= l) lo = m2 + 1; else hi = m2; }
-                        const bool l_first = l - ro[lo] < c.n_first[lo];
-                        same = v.chr(l) == v.chr(b) && v.pos(l) == v.pos(b) && v.rpos(l) == v.rpos(b) && v.mread(l) == v.mread(b) &&
-                               v.mref(l) == v.mref(b) && v.rev(l) == v.rev(b) && l_first == false;
+    // The read loop (:206-262) is split into contiguous chunks of reads, one per thread; chunk results are concatenated in
+    // order.  The only coupling between reads is `bamdiscordant.back()` at :257: a chunk that has not pushed a discordant
+    // block yet defers that test until the chunks before it are known.
+    // half the cores: the caller's own thread spins on the GPU meanwhile, and an oversubscribed OpenMP team pays for every barrier
+    const int cores = std::max(1, omp_get_num_procs() / 2);
+    int T = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)cores, 16, c.n_reads / 4096 + 1}));
+    if (getenv("SQH_PREPASS_CHUNKS")) T = std::max(1, atoi(getenv("SQH_PREPASS_CHUNKS")));  // test hook: force the chunked path on small inputs
+    struct Chunk { std::vector<DB> dis; std::vector<std::pair<int, int>> part; std::vector<uint32_t> pend; };
+    std::vector<Chunk> chunks((size_t)T);
+    auto same_block = [&](uint32_t l, uint32_t b) {  // SingleBamRec_t::Same(): every field incl. IsFirstRead; b is a SecondMate block
+        const uint32_t *ro = c.read_off;
+        int64_t lo = 0, hi = c.n_reads;  // read owning block l
+        while (lo < hi) { const int64_t m2 = (lo + hi) >> 1; if (ro[m2 + 1] <= l) lo = m2 + 1; else hi = m2; }
+        const bool l_first = l - ro[lo] < c.n_first[lo];
+        return c.blk_ref_id[l] == c.blk_ref_id[b] && c.blk_ref_pos[l] == c.blk_ref_pos[b] && c.blk_read_pos[l] == c.blk_read_pos[b] &&
+               c.blk_match_read[l] == c.blk_match_read[b] && c.blk_match_ref[l] == c.blk_match_ref[b] &&
+               (c.blk_is_reverse[l] != 0) == (c.blk_is_reverse[b] != 0) && l_first == false;
+    };
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; t++) {
+        Chunk &ch = chunks[(size_t)t];
+        std::vector<DB> &dis = ch.dis;
+        std::vector<std::pair<int, int>> &part = ch.part;
+        auto push_dis = [&](uint32_t k) { dis.push_back(DB{((uint64_t)(uint32_t)c.blk_ref_id[k] << 32) | (uint32_t)c.blk_ref_pos[k], k}); };
+        const int64_t i0 = c.n_reads * t / T, i1 = c.n_reads * (t + 1) / T;
+        for (int64_t i = i0; i < i1; i++) {
+            const uint32_t o = c.read_off[i], e = c.read_off[i + 1], nf = c.n_first[i];
+            const View v{c, o, o + nf, e};
+            const int32_t ft = c.first_total_len[i], st_ = c.second_total_len[i];
+            const bool fl = c.first_lowphred[i], sl = c.second_lowphred[i], mf = c.multi_filter[i];
+            const bool fempty = v.f0 == v.f1, sempty = v.f1 == v.s1;
+            const bool single = (fempty || sempty) && !mf;
+            if (end_disc(v, v.f0, v.f1) || end_disc(v, v.f1, v.s1) || single || pair_disc(v, ft, st_)) {  // :208-213
+                for (uint32_t k = o; k < e; k++) push_dis(k);
+                continue;
+            }
+            bool fin = false, sin = false;
+            for (int m = 0; m < 2; m++) {  // blocks of one mate more than 750 kb apart (:217-239)
+                const uint32_t a = m ? v.f1 : v.f0, b = m ? v.s1 : v.f1;
+                int64_t prev = -1;
+                for (uint32_t k = a; k + 1 < b; k++)
+                    if (std::abs(v.pos(k) - v.pos(k + 1)) > 750000) {
+                        if (prev != (int64_t)k) push_dis(k);
+                        push_dis(k + 1);
+                        prev = k + 1;
+                        if (k + 1 == b - 1) (m ? sin : fin) = true;
                     }
-                    if (!same) part.push_back({v.chr(b), v.rev(b) ? v.pos(b) : v.pos(b) + v.mref(b)});
+            }
+            if (!fempty && !sempty && std::abs(v.pos(v.f1 - 1) - v.pos(v.s1 - 1)) > 750000) {  // :240-249
+                if (!fin) { push_dis(v.f1 - 1); fin = true; }
+                if (!sin) { push_dis(v.s1 - 1); sin = true; }
+            }
+            if (!fin && !sin) {  // soft-clipped ends of otherwise concordant chimeric reads (:250-259)
+                if (!fempty && v.rpos(v.f0) > 15 && !fl) part.push_back({v.chr(v.f0), v.rev(v.f0) ? v.pos(v.f0) + v.mref(v.f0) : v.pos(v.f0)});
+                if (!fempty) { const uint32_t b = v.f1 - 1; if (ft - v.rpos(b) - v.mread(b) > 15 && !fl) part.push_back({v.chr(b), v.rev(b) ? v.pos(b) : v.pos(b) + v.mref(b)}); }
+                if (!sempty && v.rpos(v.f1) > 15 && !sl) part.push_back({v.chr(v.f1), v.rev(v.f1) ? v.pos(v.f1) + v.mref(v.f1) : v.pos(v.f1)});
+                if (!sempty) {
+                    const uint32_t b = v.s1 - 1;
+                    if (st_ - v.rpos(b) - v.mread(b) > 15 && !sl) {
+                        // `!bamdiscordant.back().Same(SecondMate.back())` (:257); back() of an empty vector is UB in the
+                        // reference, we read it as "not the same".
+                        if (dis.empty()) ch.pend.push_back(b);  // decided when the earlier chunks are known
+                        else if (!same_block(dis.back().k, b)) part.push_back({v.chr(b), v.rev(b) ? v.pos(b) : v.pos(b) + v.mref(b)});
+                    }
                 }
             }
+        }
+    }
+    std::vector<DB> dis;
+    std::vector<std::pair<int, int>> part((size_t)n_ref, std::make_pair(0, 0));  // resize()d then appended (:203-204)
+    {
+        size_t nd = 0, np = part.size();
+        for (const Chunk &ch : chunks) { nd += ch.dis.size(); np += ch.part.size() + ch.pend.size(); }
+        dis.reserve(nd); part.reserve(np);
+        for (const Chunk &ch : chunks) {
+            for (uint32_t b : ch.pend)
+                if (dis.empty() || !same_block(dis.back().k, b)) part.push_back({c.blk_ref_id[b], c.blk_is_reverse[b] ? c.blk_ref_pos[b] : c.blk_ref_pos[b] + c.blk_match_ref[b]});
+            dis.insert(dis.end(), ch.dis.begin(), ch.dis.end());
+            part.insert(part.end(), ch.part.begin(), ch.part.end());
         }
     }
     lap("reads");
@@ -183,22 +276,18 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     // the order among equal (RefID,RefPos) which the sub-cluster walk observes.  The packed key
     // compares exactly like operator< of SingleBamRec_t (RefID, RefPos are non-negative here).
     lap("part sort");
-    sort_like_std(dis.data(), dis.data() + dis.size(), 6);
+    sort_like_std(dis.data(), dis.data() + dis.size(), std::min(cores, 16));
     lap("disc sort");
+    out.part_chr.reserve(part.size()); out.part_pos.reserve(part.size());
     for (auto &p : part) { out.part_chr.push_back(p.first); out.part_pos.push_back(p.second); }
     out.disc.resize(dis.size() + 1);
-    {   // gather the sorted blocks (random access into the caller's arrays): split across a few threads
-        const size_t nd = dis.size();
-        const unsigned nt = nd > (1u << 16) ? 8 : 1;
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++)
-            th.emplace_back([&, t]() {
-                for (size_t i = nd * t / nt; i < nd * (t + 1) / nt; i++) {
-                    const uint32_t k = dis[i].k;
-                    out.disc[i] = sq::DiscBlock{c.blk_ref_id[k], c.blk_ref_pos[k], c.blk_match_ref[k], c.blk_is_reverse[k] ? 1 : 0};
-                }
-            });
-        for (auto &x : th) x.join();
+    {   // gather the sorted blocks (random access into the caller's arrays)
+        const long long nd = (long long)dis.size();
+#pragma omp parallel for num_threads(std::min(cores, 16)) schedule(static)
+        for (long long i = 0; i < nd; i++) {
+            const uint32_t k = dis[(size_t)i].k;
+            out.disc[(size_t)i] = sq::DiscBlock{c.blk_ref_id[k], c.blk_ref_pos[k], c.blk_match_ref[k], c.blk_is_reverse[k] ? 1 : 0};
+        }
     }
     const int32_t n = (int32_t)dis.size();
     out.disc[dis.size()] = sq::DiscBlock{0, 0, 0, 0};  // what *cend() reads

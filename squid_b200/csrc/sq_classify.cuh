@@ -8,36 +8,56 @@
 namespace sq {
 
 // own(l) == [synthetic mate block of r]   (lists compared on RefID, RefPos, MatchRef; ReadRec.cpp:125)
-SQ_HD bool own_equals_mate_of(const DevBatch &b, int64_t l, int64_t r) {
+template <class B>
+SQ_HD bool own_equals_mate_of(const B &b, int64_t l, int64_t r) {
     const uint32_t ol = b.blk_off[l], nl = b.blk_off[l + 1] - ol;
     if (!has_mate_block(b.flag[r], b.mate_ref_id[r])) return nl == 0;
     return nl == 1 && b.ref_id[l] == b.mate_ref_id[r] && b.blk_ref_pos[ol] == b.mate_pos[r] && b.blk_match_ref[ol] == kMateBlockLen;
+}
+
+// Two block lists of the same length n > 1 (CIGAR order), each sorted by read position (SortbyReadPos: std::sort on <= 16
+// elements is an insertion sort, i.e. stable), compared on (RefPos, MatchRef).  Kept out of line and fed with plain pointers:
+// consecutive records with equal mate fields AND several blocks are rare, and the sort needs stack arrays.
+SQ_HD_NOINLINE bool sorted_blocks_equal(const int32_t *lp, const int32_t *lm, const uint16_t *lr, const int32_t *rp, const int32_t *rm, const uint16_t *rr, int n) {
+    int32_t xp[kMaxBlocks], xm[kMaxBlocks], xr[kMaxBlocks], yp[kMaxBlocks], ym[kMaxBlocks], yr[kMaxBlocks];
+    if (n > kMaxBlocks) n = kMaxBlocks;
+    for (int k = 0; k < n; k++) {
+        int j = k;
+        const int32_t q = lr[k];
+        while (j > 0 && q < xr[j - 1]) { xp[j] = xp[j - 1]; xm[j] = xm[j - 1]; xr[j] = xr[j - 1]; j--; }
+        xp[j] = lp[k]; xm[j] = lm[k]; xr[j] = q;
+        j = k;
+        const int32_t q2 = rr[k];
+        while (j > 0 && q2 < yr[j - 1]) { yp[j] = yp[j - 1]; ym[j] = ym[j - 1]; yr[j] = yr[j - 1]; j--; }
+        yp[j] = rp[k]; ym[j] = rm[k]; yr[j] = q2;
+    }
+    for (int k = 0; k < n; k++)
+        if (xp[k] != yp[k] || xm[k] != ym[k]) return false;
+    return true;
 }
 
 // ReadRec_t::Equal(lastreadrec, tmpreadrec) for two alignment records, each carrying its own
 // blocks (sorted by read position) plus the synthetic 15-bp mate block (SegmentGraph.cpp:305-315).
 // Equal = direct match or mate-swapped match; written out it does not depend on which record is
 // the first mate:  [own==own && mate==mate] || [own(l)==mate(r) && mate(l)==own(r)].
-SQ_HD bool records_equal(const DevBatch &b, int64_t l, int64_t r) {
+template <class B>
+SQ_HD bool records_equal(const B &b, int64_t l, int64_t r) {
     const uint32_t ol = b.blk_off[l], nl = b.blk_off[l + 1] - ol;
     const uint32_t orr = b.blk_off[r], nr = b.blk_off[r + 1] - orr;
     const bool ml = has_mate_block(b.flag[l], b.mate_ref_id[l]), mr = has_mate_block(b.flag[r], b.mate_ref_id[r]);
     bool direct = (nl == nr) && (ml == mr) && (b.ref_id[l] == b.ref_id[r] || nl == 0);
     if (direct && ml) direct = b.mate_ref_id[l] == b.mate_ref_id[r] && b.mate_pos[l] == b.mate_pos[r];
-    if (direct && nl > 0) {
-        // both lists are sorted by read position; same strand => same permutation of CIGAR order,
-        // different strand => compare through the sorted views
-        Blk x[kMaxBlocks], y[kMaxBlocks];
-        const int cx = load_sorted_blocks(b, l, x), cy = load_sorted_blocks(b, r, y);
-        for (int k = 0; k < cx && k < cy; k++)
-            if (x[k].ref_pos != y[k].ref_pos || x[k].match_ref != y[k].match_ref) { direct = false; break; }
-    }
+    if (direct && nl == 1) direct = b.blk_ref_pos[ol] == b.blk_ref_pos[orr] && b.blk_match_ref[ol] == b.blk_match_ref[orr];
+    else if (direct && nl > 1)
+        direct = sorted_blocks_equal(elem_ptr(b.blk_ref_pos, ol), elem_ptr(b.blk_match_ref, ol), elem_ptr(b.blk_read_pos, ol),
+                                     elem_ptr(b.blk_ref_pos, orr), elem_ptr(b.blk_match_ref, orr), elem_ptr(b.blk_read_pos, orr), (int)nl);
     if (direct) return true;
     return own_equals_mate_of(b, l, r) && own_equals_mate_of(b, r, l);
 }
 
 // Equal(default-constructed ReadRec_t, r): both lists of r empty.
-SQ_HD bool record_equals_empty(const DevBatch &b, int64_t r) {
+template <class B>
+SQ_HD bool record_equals_empty(const B &b, int64_t r) {
     return b.blk_off[r + 1] == b.blk_off[r] && !has_mate_block(b.flag[r], b.mate_ref_id[r]);
 }
 
@@ -56,7 +76,8 @@ struct ClassifyOut {
 };
 
 // `prev` = index of the previous gate-passing record, or -1.
-SQ_HD ClassifyOut classify_record(const DevBatch &b, const Params &p, int64_t r, int64_t prev) {
+template <class B>
+SQ_HD ClassifyOut classify_record(const B &b, const Params &p, int64_t r, int64_t prev) {
     ClassifyOut o;
     o.cls = 0; o.other_key = 0; o.first_len = 0;
     const uint16_t f = b.flag[r];

@@ -8,8 +8,10 @@
 
 #if defined(__CUDACC__)
 #define SQ_HD __host__ __device__ __forceinline__
+#define SQ_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define SQ_HD inline
+#define SQ_HD_NOINLINE inline
 #endif
 
 namespace sq {
@@ -38,6 +40,25 @@ struct DevBatch {
     const uint32_t *blk_off = nullptr;
     const int32_t *blk_ref_pos = nullptr, *blk_match_ref = nullptr;
     const uint16_t *blk_read_pos = nullptr, *blk_match_read = nullptr;
+};
+
+// The same batch seen through a tile staged in shared memory: arrays indexed by the GLOBAL record / block index, backed by
+// staging buffers that start at record `rec0` / block `blk0`.  The element rules are templates over the batch type, so the
+// very same code classifies from HBM (DevBatch) and from a staged tile (TileBatch).
+template <class T> struct OffPtr {
+    const T *p; uint32_t off;  // indices stay below 2^32 (records: 2^31 per context, blocks: uint32 offsets)
+    SQ_HD T operator[](int64_t i) const { return p[(uint32_t)i - off]; }
+};
+template <class T> SQ_HD const T *elem_ptr(const T *p, int64_t i) { return p + i; }
+template <class T> SQ_HD const T *elem_ptr(const OffPtr<T> &q, int64_t i) { return q.p + ((uint32_t)i - q.off); }
+struct TileBatch {
+    int64_t n_rec = 0, n_blk = 0;
+    OffPtr<int32_t> ref_id, pos, mate_ref_id, mate_pos, end_pos;
+    OffPtr<uint16_t> flag, total_len, lowphred_run;
+    OffPtr<uint8_t> mapq, aux;
+    OffPtr<uint32_t> blk_off;
+    OffPtr<int32_t> blk_ref_pos, blk_match_ref;
+    OffPtr<uint16_t> blk_read_pos, blk_match_read;
 };
 
 struct Params {
@@ -136,7 +157,8 @@ SQ_HD int32_t seg_last_pos_le(const NodeTable &nt, int32_t c, int32_t c0, int32_
 
 // Own blocks of record r sorted by read position (SortbyReadPos: std::sort on <=16 elements is an
 // insertion sort, i.e. stable).  Returns the count.
-SQ_HD int load_sorted_blocks(const DevBatch &b, int64_t r, Blk *out) {
+template <class B>
+SQ_HD int load_sorted_blocks(const B &b, int64_t r, Blk *out) {
     const uint32_t o = b.blk_off[r], n = b.blk_off[r + 1] - o;
     const int32_t rid = b.ref_id[r];
     const bool rev = flag_rev(b.flag[r]);

@@ -50,8 +50,8 @@ constexpr int32_t kIslandSlack = 70;  // > thresh*20 + 2*thresh, see island_cut(
 struct SeedInputs {
     DevBatch b;
     const uint8_t *cls;
-    const uint64_t *other_excl;     // per record: otherChr/otherrightmost before the record ((chr+1)<<32|pos)
     const int32_t *gap_rec; int32_t n_gap;  // kept records preceded by a concordant-coverage gap, ascending
+    const uint64_t *gap_other;      // per gap record: otherChr/otherrightmost before the record ((chr+1)<<32|pos)
     const int32_t *pc_rec; int32_t n_pc;    // records with CLS_PART, ascending
     const int32_t *dp_rec; int32_t n_dp;    // CLS_CONC records whose first kept block does not start at the record position
     int32_t lmax;                           // max first-block length over CLS_CONC records
@@ -269,9 +269,10 @@ struct SeedMachineT {
         st.backChr = -2; st.backEnd = -(1 << 30); st.n_out = 0; st.last_kind = -1; error = 0;
     }
 
-    // (curChr, currightmost) and the 0-coverage test of :616-620 for kept record r while a group starting at (sChr,sPos) is pending
-    SQ_HD bool is0(int64_t r, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, int32_t *curChr, int32_t *curRight) const {
-        const uint64_t ok = in.other_excl[r];
+    // (curChr, currightmost) and the 0-coverage test of :616-620 for gap record k while a group starting at (sChr,sPos) is pending
+    SQ_HD bool is0(int32_t k, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, int32_t *curChr, int32_t *curRight) const {
+        const int64_t r = in.gap_rec[k];
+        const uint64_t ok = in.gap_other[k];
         const int32_t oChr = (int32_t)(ok >> 32) - 1, oRight = (int32_t)(uint32_t)ok;
         const int32_t cr = (dChr > oChr || (dChr == oChr && dRight > oRight)) ? dRight : oRight;
         const int32_t cc = dChr > oChr ? dChr : oChr;
@@ -283,7 +284,7 @@ struct SeedMachineT {
     SQ_HD int32_t last_is0(int64_t r_lo, int64_t r_hi, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, int32_t *cc, int32_t *cr) const {
         if (r_hi <= r_lo) return -1;
         const int32_t a = lb_list(in.gap_rec, in.n_gap, r_lo), bnd = lb_list(in.gap_rec, in.n_gap, r_hi);
-        for (int32_t k = bnd - 1; k >= a; k--) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, cc, cr)) return k;
+        for (int32_t k = bnd - 1; k >= a; k--) if (is0(k, dChr, dRight, sChr, sPos, cc, cr)) return k;
         return -1;
     }
     // May the machine be restarted at group g (g >= 1)?  Yes when the records between the triggers of g-1 and g
@@ -338,7 +339,7 @@ struct SeedMachineT {
         const int32_t a = lb_list(in.gap_rec, in.n_gap, r_lo), bnd = lb_list(in.gap_rec, in.n_gap, r_hi);
         int32_t cc, cr;
         int32_t f = -1, z = -1;
-        for (int32_t k = a; k < bnd; k++) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, &cc, &cr)) { f = k; break; }
+        for (int32_t k = a; k < bnd; k++) if (is0(k, dChr, dRight, sChr, sPos, &cc, &cr)) { f = k; break; }
         if (f >= 0) {
             if (st.markedStart != -1) {  // :621-630
                 if (cc == st.markedChr && cr > st.markedStart && cr - st.markedStart < kSeedThresh * 20 && st.have_back && st.markedStart == st.backEnd)
@@ -348,7 +349,7 @@ struct SeedMachineT {
                 st.markedStart = -1; st.markedChr = -1;
             }
             if (!do_trim) return;
-            for (int32_t k = bnd - 1; k >= f; k--) if (is0(in.gap_rec[k], dChr, dRight, sChr, sPos, &cc, &cr)) { z = k; break; }
+            for (int32_t k = bnd - 1; k >= f; k--) if (is0(k, dChr, dRight, sChr, sPos, &cc, &cr)) { z = k; break; }
             const int64_t zr = in.gap_rec[z];
             st.offCC = zr;  // :633-636 at record z: both windows emptied; z's own block is pushed afterwards
             st.offPC = lb_list(in.pc_rec, in.n_pc, zr);

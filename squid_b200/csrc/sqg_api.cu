@@ -18,6 +18,7 @@
 #include "sq_classify.cuh"
 #include "sq_depth_cover.cuh"
 #include "sq_locate.cuh"
+#include "sq_phase1.cuh"
 #include "sq_seed.cuh"
 #include "sqg_ctx.cuh"
 
@@ -61,69 +62,10 @@ static int phase_end(sqg_ctx *ctx, const char *name) {
 // ------------------------------------------------------------------------------------------------
 // functors / kernels: classify
 // ------------------------------------------------------------------------------------------------
-struct GateIdxOp {
-    DevBatch b; int32_t min_mapq;
-    __device__ int32_t operator()(int32_t r) const {
-        return record_gate(b.flag[r], b.mapq[r], b.aux[r], b.ref_id[r], min_mapq) ? r : -1;
-    }
-};
 struct MaxI32 { __device__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; } };
 struct MaxU64 { __device__ uint64_t operator()(uint64_t a, uint64_t b) const { return a > b ? a : b; } };
 struct MaxI64 { __device__ int64_t operator()(int64_t a, int64_t b) const { return a > b ? a : b; } };
 struct MinI64 { __device__ int64_t operator()(int64_t a, int64_t b) const { return a < b ? a : b; } };
-
-__global__ void k_validate(DevBatch b, int32_t n_ref, int32_t *flags) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= b.n_rec) return;
-    int bad = 0;
-    const int32_t rid = b.ref_id[r];
-    if (rid >= n_ref || rid < -1) bad |= 1;
-    if (rid < 0 && flag_mapped(b.flag[r])) bad |= 2;
-    if (b.blk_off[r + 1] < b.blk_off[r] || b.blk_off[r + 1] - b.blk_off[r] > (uint32_t)kMaxBlocks) bad |= 4;
-    if (r + 1 < b.n_rec) {
-        const int32_t rid2 = b.ref_id[r + 1];
-        const uint64_t k1 = rid < 0 ? ~0ull : (((uint64_t)(uint32_t)rid << 32) | (uint32_t)b.pos[r]);
-        const uint64_t k2 = rid2 < 0 ? ~0ull : (((uint64_t)(uint32_t)rid2 << 32) | (uint32_t)b.pos[r + 1]);
-        if (k2 < k1) bad |= 8;
-    }
-    if (bad) atomicOr(flags, bad);
-}
-
-__global__ void k_classify(DevBatch b, Params p, const int32_t *lastpass, uint8_t *cls, uint64_t *other_key, int32_t *lmax) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int32_t fl = 0;
-    if (r < b.n_rec) {
-        const int64_t prev = r > 0 ? lastpass[r - 1] : -1;
-        const ClassifyOut o = classify_record(b, p, r, prev);
-        cls[r] = o.cls;
-        other_key[r] = o.other_key;
-        fl = o.first_len;
-    }
-    fl = __reduce_max_sync(0xffffffffu, fl);
-    if ((threadIdx.x & 31) == 0 && fl > 0) atomicMax(lmax, fl);
-}
-
-struct IsGapOp {
-    DevBatch b; const uint8_t *cls; const uint64_t *other; int32_t read_len;
-    __device__ bool operator()(int32_t r) const {
-        if (!(cls[r] & CLS_KEEP)) return false;
-        const uint64_t k = other[r];
-        const int32_t oc = (int32_t)(k >> 32) - 1, orr = (int32_t)(uint32_t)k;
-        return b.ref_id[r] != oc || b.pos[r] > orr + read_len;
-    }
-};
-struct IsPartOp {
-    const uint8_t *cls;
-    __device__ bool operator()(int32_t r) const { return cls[r] & CLS_PART; }
-};
-struct IsDisplOp {
-    const uint8_t *cls;
-    __device__ bool operator()(int32_t r) const { return (cls[r] & (CLS_CONC | CLS_DISPL)) == (CLS_CONC | CLS_DISPL); }
-};
-struct FirstKeptOp {
-    const uint8_t *cls; int64_t n;
-    __device__ int64_t operator()(int32_t r) const { return (cls[r] & CLS_KEEP) ? (int64_t)r : n; }
-};
 
 // ------------------------------------------------------------------------------------------------
 // kernels: node building
@@ -664,7 +606,7 @@ int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int
 
 void sqg_destroy(sqg_ctx *ctx) {
     if (!ctx) return;
-    if (ctx->prepass_thread.joinable()) ctx->prepass_thread.join();
+    ctx->prepass_worker.stop();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     // DBuf/HBuf members are plain pointers: release explicitly
@@ -680,7 +622,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
-    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
+    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
@@ -724,29 +666,6 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
 
 }  // extern "C"
 
-// The validation kernel is enqueued at load time; its verdict is read at the first synchronisation of a later call
-// (or right away for pageable host input), so that the host->device copies overlap the host-side chimeric pre-pass.
-static int validate_enqueue(sqg_ctx *ctx) {
-    CK(ctx->d_counters.ensure(32));
-    CK(ctx->h_counters.ensure(32));
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 32 * sizeof(int64_t), ctx->stream));
-    if (ctx->batch.n_rec > 0) LAUNCH(k_validate, blocks_for(ctx->batch.n_rec), kThreads, ctx->batch, ctx->params.n_ref, (int32_t *)(ctx->d_counters.p + 20));
-    CK(cudaMemcpyAsync(ctx->h_counters.p + 20, ctx->d_counters.p + 20, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->validated = false;
-    return SQG_OK;
-}
-static int validate_check(sqg_ctx *ctx) {
-    if (ctx->validated) return SQG_OK;
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->validated = true;
-    const int32_t flags = *(int32_t *)(ctx->h_counters.p + 20);
-    if (flags & 1) FAIL(SQG_EINVAL, "record with ref_id outside [-1, n_ref)");
-    if (flags & 2) FAIL(SQG_EUNSUPPORTED, "mapped record with ref_id -1");
-    if (flags & 4) FAIL(SQG_EUNSUPPORTED, "record with more than 16 aligned blocks or a decreasing blk_off");
-    if (flags & 8) FAIL(SQG_EINVAL, "batch is not sorted by (ref_id, pos)");
-    return SQG_OK;
-}
-
 extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t first_record_index) {
     if (!ctx || !hb || hb->n_rec < 0 || hb->n_blk < 0) return SQG_EINVAL;
     if (hb->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
@@ -771,7 +690,7 @@ extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t fi
     b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
     PHASE_END("h2d");
     ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->first_record_index = first_record_index;
-    return validate_enqueue(ctx);
+    return SQG_OK;
 }
 
 extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, int64_t first_record_index) {
@@ -784,7 +703,7 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     b.flag = db->flag; b.total_len = db->total_len; b.lowphred_run = db->lowphred_run; b.mapq = db->mapq; b.aux = db->aux;
     b.blk_off = db->blk_off; b.blk_ref_pos = db->blk_ref_pos; b.blk_match_ref = db->blk_match_ref; b.blk_read_pos = db->blk_read_pos; b.blk_match_read = db->blk_match_read;
     ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->first_record_index = first_record_index;
-    return validate_enqueue(ctx);
+    return SQG_OK;
 }
 
 extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
@@ -796,9 +715,9 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     }
     // The chimeric pre-pass (BuildNode_STAR part A, host std::sort for tie-order fidelity) runs on a host thread while the
     // stream copies and classifies the concordant batch; it is joined in sqg_build_nodes / sqg_build_edges.
-    if (ctx->prepass_thread.joinable()) ctx->prepass_thread.join();
+    ctx->prepass_worker.wait();
     ctx->chim_view = *c;
-    ctx->prepass_thread = std::thread([ctx]() { sqh::chimeric_prepass(ctx->chim_view, ctx->params.n_ref, ctx->params.read_len, ctx->pre); });
+    ctx->prepass_worker.submit([ctx]() { sqh::chimeric_prepass(ctx->chim_view, ctx->params.n_ref, ctx->params.read_len, ctx->pre); });
     ctx->prepass_uploaded = false;
     ctx->c_n_reads = c->n_reads; ctx->c_n_blk = c->n_blk;
     const size_t nr = (size_t)c->n_reads, nb = (size_t)c->n_blk;
@@ -818,7 +737,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
 
 // join the host pre-pass and put its products (discordant blocks, groups, PartAlignPos) into HBM
 static int finish_prepass(sqg_ctx *ctx) {
-    if (ctx->prepass_thread.joinable()) ctx->prepass_thread.join();
+    ctx->prepass_worker.wait();
     if (ctx->prepass_uploaded) return SQG_OK;
     const size_t nD1 = ctx->pre.disc.size(), nG = ctx->pre.groups.size(), nP = ctx->pre.part_chr.size();
     UPV(d_disc, ctx->pre.disc.data(), nD1); UPV(d_groups, ctx->pre.groups.data(), nG);
@@ -831,68 +750,103 @@ static int finish_prepass(sqg_ctx *ctx) {
 static int ensure_temp(sqg_ctx *ctx, size_t bytes) { CK(ctx->d_temp.ensure(bytes + 256)); return SQG_OK; }
 #define ENSURE_TEMP(bytes) do { int rc_ = ensure_temp(ctx, bytes); if (rc_) return rc_; } while (0)
 
-// classify stage: cls, other_excl, gap list, partial list, first kept record
+// look-back chains of a stream kernel: `n_chains` chains over `n_tiles` tiles; status words zeroed, ticket reset
+static int prepare_chains(sqg_ctx *ctx, int n_chains, int64_t n_tiles, Chain *out, int32_t **ticket) {
+    CK(ctx->d_chain64.ensure((size_t)n_chains * 4 * n_tiles + 8));
+    CK(ctx->d_chain32.ensure((size_t)n_chains * n_tiles + 8));
+    CK(cudaMemsetAsync(ctx->d_chain32.p, 0, ((size_t)n_chains * n_tiles + 8) * 4, ctx->stream));
+    for (int c = 0; c < n_chains; c++) {
+        out[c].status = ctx->d_chain32.p + (size_t)c * n_tiles;
+        uint64_t *q = ctx->d_chain64.p + (size_t)c * 4 * n_tiles;
+        out[c].agg_a = q; out[c].agg_b = q + n_tiles; out[c].inc_a = q + 2 * n_tiles; out[c].inc_b = q + 3 * n_tiles;
+    }
+    *ticket = (int32_t *)(ctx->d_chain32.p + (size_t)n_chains * n_tiles);
+    return SQG_OK;
+}
+static bool batch_bulk_ok(const DevBatch &b) {  // TMA bulk copies need 16-byte aligned sources
+    const void *ptrs[] = {b.ref_id, b.pos, b.mate_ref_id, b.mate_pos, b.end_pos, b.flag, b.total_len, b.lowphred_run, b.mapq, b.aux, b.blk_off,
+                          b.blk_ref_pos, b.blk_match_ref, b.blk_read_pos, b.blk_match_read};
+    for (const void *q : ptrs) if (((uintptr_t)q) & 15u) return false;
+    return true;
+}
+static constexpr size_t kTileSmemBytes = sizeof(TileStage) + 128;
+
+// classify stage (phase 1): class bytes, gap / partial / displaced lists, first kept record, lmax; validates the batch
 static int run_classify(sqg_ctx *ctx) {
     if (ctx->classified) return SQG_OK;
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
     PHASE_BEGIN("classify");
-    CK(ctx->d_cls.ensure(n + 1)); CK(ctx->d_other.ensure(n + 1)); CK(ctx->d_scratch32.ensure(n + 1));
-    CK(ctx->d_gap.ensure(n + 1)); CK(ctx->d_pc.ensure(n + 1)); CK(ctx->d_dp.ensure(n + 1));
+    CK(ctx->d_cls.ensure(n + 4)); CK(ctx->d_scratch32.ensure(n + 1));
     CK(ctx->d_counters.ensure(32)); CK(ctx->h_counters.ensure(32));
     ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n;
     if (n > 0) {
-        cub::CountingInputIterator<int32_t> cnt(0);
-        size_t tb = 0;
-        {   // last gate-passing record at or before r
-            cub::TransformInputIterator<int32_t, GateIdxOp, cub::CountingInputIterator<int32_t>> it(cnt, GateIdxOp{b, ctx->params.min_mapq});
-            CK(cub::DeviceScan::InclusiveScan(nullptr, tb, it, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
-            ENSURE_TEMP(tb);
-            CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, it, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
-            ctx->launches += 2;
+        const int64_t n_tiles = (n + kTile - 1) / kTile;
+        CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8));
+        int64_t cand_cap = std::max<int64_t>({(int64_t)ctx->d_cand_key.cap, n / 16, (int64_t)1 << 20});
+        int32_t n_cand = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            cand_cap = std::min<int64_t>(cand_cap, n + 1);
+            CK(ctx->d_cand_key.ensure(cand_cap));
+            P1Out o;
+            o.cls = ctx->d_cls.p; o.agg = ctx->d_tileagg.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
+            o.cand_rec = ctx->d_scratch32.p; o.cand_key = ctx->d_cand_key.p; o.cand_cap = (int32_t)cand_cap;
+            // counters: [0..1] totals n_gap, n_pc, n_dp (int32) | [2] first_kept | [3] lmax | [4] n_cand, ticket (int32) | [20] validation flags
+            CK(cudaMemsetAsync(ctx->d_counters.p, 0, 5 * sizeof(int64_t), ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_counters.p + 20, 0, sizeof(int64_t), ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_chain64.p, 0, n_tiles * sizeof(uint64_t), ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_counters.p + 2, &n, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+            int32_t *totals = (int32_t *)ctx->d_counters.p;
+            o.first_kept = (long long *)(ctx->d_counters.p + 2); o.lmax = (int32_t *)(ctx->d_counters.p + 3);
+            o.n_cand = (int32_t *)(ctx->d_counters.p + 4); o.ticket = o.n_cand + 1;
+            o.bad_flags = (int32_t *)(ctx->d_counters.p + 20);
+            {
+                BatchDesc hd; hd.b = b; hd.p = ctx->params;
+                CK(ctx->d_desc.ensure(sizeof(BatchDesc)));
+                CK(cudaMemcpyAsync(ctx->d_desc.p, &hd, sizeof(BatchDesc), cudaMemcpyHostToDevice, ctx->stream));  // pageable source: staged before the call returns
+                o.desc = (const BatchDesc *)ctx->d_desc.p;
+            }
+            CK(cudaFuncSetAttribute(k_classify_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            PHASE_BEGIN("k_classify");
+            k_classify_tiles<<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, ctx->params, o, batch_bulk_ok(b) ? 1 : 0);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            PHASE_END("k_classify");
+            LAUNCH(k_tile_scan, 1, 1024, ctx->d_tileagg.p, (int32_t)n_tiles, totals);
+            CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_counters.p + 20, ctx->d_counters.p + 20, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const int32_t flags = *(int32_t *)(ctx->h_counters.p + 20);
+            if (flags & 1) FAIL(SQG_EINVAL, "record with ref_id outside [-1, n_ref)");
+            if (flags & 2) FAIL(SQG_EUNSUPPORTED, "mapped record with ref_id -1");
+            if (flags & 4) FAIL(SQG_EUNSUPPORTED, "record with more than 16 aligned blocks or a decreasing blk_off");
+            if (flags & 8) FAIL(SQG_EINVAL, "batch is not sorted by (ref_id, pos)");
+            n_cand = *(int32_t *)(ctx->h_counters.p + 4);
+            if (!(flags & 16)) break;
+            if (attempt == 1) FAIL(SQG_ENOMEM, "coverage-gap candidate buffer overflow");
+            cand_cap = n + 1;  // every record can be a candidate at worst
         }
-        CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(int64_t), ctx->stream));
-        PHASE_BEGIN("k_classify");
-        LAUNCH(k_classify, blocks_for(n), kThreads, b, ctx->params, ctx->d_scratch32.p, ctx->d_cls.p, ctx->d_other.p, (int32_t *)(ctx->d_counters.p + 3));
-        PHASE_END("k_classify");
-        {   // otherChr/otherrightmost before each record
-            CK(cub::DeviceScan::ExclusiveScan(nullptr, tb, ctx->d_other.p, ctx->d_other.p, MaxU64(), (uint64_t)(1ull << 32), (int)n, ctx->stream));
-            ENSURE_TEMP(tb);
-            CK(cub::DeviceScan::ExclusiveScan(ctx->d_temp.p, tb, ctx->d_other.p, ctx->d_other.p, MaxU64(), (uint64_t)(1ull << 32), (int)n, ctx->stream));
-            ctx->launches += 2;
-        }
-        int32_t *d_nsel = (int32_t *)ctx->d_counters.p;
-        {
-            IsGapOp op{b, ctx->d_cls.p, ctx->d_other.p, ctx->params.read_len};
-            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_gap.p, d_nsel, (int)n, op, ctx->stream));
-            ENSURE_TEMP(tb);
-            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_gap.p, d_nsel, (int)n, op, ctx->stream));
-            IsPartOp op2{ctx->d_cls.p};
-            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_pc.p, d_nsel + 1, (int)n, op2, ctx->stream));
-            ENSURE_TEMP(tb);
-            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_pc.p, d_nsel + 1, (int)n, op2, ctx->stream));
-            IsDisplOp op3{ctx->d_cls.p};
-            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_dp.p, d_nsel + 2, (int)n, op3, ctx->stream));
-            ENSURE_TEMP(tb);
-            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_dp.p, d_nsel + 2, (int)n, op3, ctx->stream));
-            cub::TransformInputIterator<int64_t, FirstKeptOp, cub::CountingInputIterator<int32_t>> fk(cnt, FirstKeptOp{ctx->d_cls.p, n});
-            CK(cub::DeviceReduce::Reduce(nullptr, tb, fk, ctx->d_counters.p + 2, (int)n, MinI64(), (int64_t)n, ctx->stream));
-            ENSURE_TEMP(tb);
-            CK(cub::DeviceReduce::Reduce(ctx->d_temp.p, tb, fk, ctx->d_counters.p + 2, (int)n, MinI64(), (int64_t)n, ctx->stream));
-            ctx->launches += 6;
-        }
-        CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    PHASE_END("classify");
-    {
-        const int rcv = validate_check(ctx);
-        if (rcv) return rcv;
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (n > 0) {
         const int32_t *sel = (const int32_t *)ctx->h_counters.p;
-        ctx->n_gap = sel[0]; ctx->n_pc = sel[1]; ctx->n_dp = sel[2]; ctx->first_kept = ctx->h_counters.p[2];
+        ctx->n_pc = sel[1]; ctx->n_dp = sel[2]; ctx->first_kept = ctx->h_counters.p[2];
         ctx->lmax = *(const int32_t *)(ctx->h_counters.p + 3);
+        CK(ctx->d_gap.ensure((size_t)n_cand + 1)); CK(ctx->d_other.ensure((size_t)n_cand + 1));
+        CK(ctx->d_pc.ensure((size_t)ctx->n_pc + 1)); CK(ctx->d_dp.ensure((size_t)ctx->n_dp + 1));
+        if (n_cand > 0) {
+            LAUNCH(k_finish_gaps, blocks_for(n_cand), kThreads, b, ctx->d_tileagg.p, ctx->d_scratch32.p, ctx->d_cand_key.p, n_cand, ctx->params.read_len, (int32_t *)ctx->d_counters.p);
+            size_t tb = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_scratch32.p, ctx->d_gap.p, ctx->d_cand_key.p, ctx->d_other.p, n_cand, 0, 32, ctx->stream));
+            ENSURE_TEMP(tb);
+            CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp.p, tb, ctx->d_scratch32.p, ctx->d_gap.p, ctx->d_cand_key.p, ctx->d_other.p, n_cand, 0, 32, ctx->stream));
+            ctx->launches += 3;
+        }
+        if (ctx->n_pc + ctx->n_dp > 0) LAUNCH(k_compact_lists, (unsigned)n_tiles, kTileThreads, ctx->d_cls.p, n, ctx->d_tileagg.p, ctx->d_pc.p, ctx->d_dp.p);
+        CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PHASE_END("classify");
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->n_gap = sel[0];
+    } else {
+        PHASE_END("classify");
+        CK(ctx->d_gap.ensure(1)); CK(ctx->d_other.ensure(1)); CK(ctx->d_pc.ensure(1)); CK(ctx->d_dp.ensure(1));
     }
     ctx->classified = true;
     return SQG_OK;
@@ -1016,7 +970,7 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     }
     // the state machine, island-parallel
     SeedInputs in;
-    in.b = b; in.cls = ctx->d_cls.p; in.other_excl = ctx->d_other.p;
+    in.b = b; in.cls = ctx->d_cls.p; in.gap_other = ctx->d_other.p;
     in.gap_rec = ctx->d_gap.p; in.n_gap = ctx->n_gap; in.pc_rec = ctx->d_pc.p; in.n_pc = ctx->n_pc;
     in.dp_rec = ctx->d_dp.p; in.n_dp = ctx->n_dp; in.lmax = ctx->lmax; in.n_rec = n;
     in.D = ctx->d_disc.p; in.nD = nD; in.G = ctx->d_groups.p; in.nG = nG; in.trigger = ctx->d_trigger.p;

@@ -4,7 +4,10 @@
 #define SQG_CTX_CUH
 #include <cuda_runtime.h>
 
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
@@ -12,6 +15,7 @@
 #include "host/prepass.h"
 #include "sq_common.cuh"
 #include "sq_seed.cuh"
+#include "sq_phase1.cuh"
 #include "squid_b200.h"
 
 namespace sq {
@@ -45,6 +49,41 @@ template <class T> struct HBuf {  // pinned host
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// One persistent host thread that runs one job at a time.
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, busy = false, quit = false;
+    void submit(std::function<void()> f) {
+        wait();
+        std::unique_lock<std::mutex> lk(m);
+        if (!th.joinable()) th = std::thread([this]() { loop(); });
+        job = std::move(f); has_job = true; busy = true;
+        cv.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this]() { return !busy; }); }
+    void stop() {
+        wait();
+        { std::unique_lock<std::mutex> lk(m); quit = true; cv.notify_all(); }
+        if (th.joinable()) th.join();
+    }
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this]() { return has_job || quit; });
+                if (quit) return;
+                f = std::move(job); has_job = false;
+            }
+            f();
+            { std::unique_lock<std::mutex> lk(m); busy = false; cv.notify_all(); }
+        }
+    }
+};
+
 struct PhaseTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     bool done = false;
@@ -72,7 +111,12 @@ struct sqg_ctx {
 
     // classify products
     sq::DBuf<uint8_t> d_cls;
-    sq::DBuf<uint64_t> d_other;     // other_key, then its exclusive max-scan
+    sq::DBuf<uint64_t> d_other;     // running otherChr/otherrightmost key at each coverage-gap record
+    sq::DBuf<uint64_t> d_chain64;   // look-back chains of the stream kernels
+    sq::DBuf<uint32_t> d_chain32;
+    sq::DBuf<sq::TileAgg> d_tileagg;  // per-tile aggregates / exclusive prefixes of phase 1
+    sq::DBuf<unsigned char> d_desc;   // device copy of the batch descriptor
+    sq::DBuf<uint64_t> d_cand_key;    // coverage-gap candidates (their record indices live in d_scratch32)
     sq::DBuf<int32_t> d_scratch32;  // lastpass / depth targets / res0
     sq::DBuf<int32_t> d_gap, d_pc, d_dp;
     int32_t n_gap = 0, n_pc = 0, n_dp = 0, lmax = 0, n_islands = 0;
@@ -82,10 +126,10 @@ struct sqg_ctx {
     sq::HBuf<int64_t> h_counters;
 
     // chimeric side
-    bool have_chim = false, validated = true, prepass_uploaded = false;
+    bool have_chim = false, prepass_uploaded = false;
     sqh::ChimPrepass pre;
     sqg_chimeric chim_view{};
-    std::thread prepass_thread;
+    sq::Worker prepass_worker;  // persistent host thread of the chimeric pre-pass (keeps its OpenMP team alive between runs)
     std::vector<uint32_t> c_read_off;
     std::vector<uint16_t> c_n_first;
     std::vector<int32_t> c_first_total, c_second_total;

@@ -82,13 +82,14 @@ int main(int argc, char **argv) {
         }
     }
     std::vector<int32_t> gap, pcrec, dprec;
+    std::vector<uint64_t> gap_other;
     int32_t lmax = 0;
     int64_t first_kept = n;
     for (int64_t r = 0; r < n; r++) {
         if (!(cls[r] & CLS_KEEP)) continue;
         if (first_kept == n) first_kept = r;
         const int32_t oc = (int32_t)(other_excl[r] >> 32) - 1, orr = (int32_t)(uint32_t)other_excl[r];
-        if (b.ref_id[r] != oc || b.pos[r] > orr + p.read_len) gap.push_back((int32_t)r);
+        if (b.ref_id[r] != oc || b.pos[r] > orr + p.read_len) { gap.push_back((int32_t)r); gap_other.push_back(other_excl[r]); }
         if (cls[r] & CLS_PART) pcrec.push_back((int32_t)r);
         if ((cls[r] & CLS_CONC) && (cls[r] & CLS_DISPL)) dprec.push_back((int32_t)r);
         if (cls[r] & CLS_CONC) lmax = std::max(lmax, b.blk_match_ref[b.blk_off[r]]);
@@ -122,7 +123,7 @@ int main(int argc, char **argv) {
 
     // ---- seed machine ----
     SeedMachine sm;
-    sm.in.b = b; sm.in.cls = cls.data(); sm.in.other_excl = other_excl.data();
+    sm.in.b = b; sm.in.cls = cls.data(); sm.in.gap_other = gap_other.data();
     sm.in.gap_rec = gap.data(); sm.in.n_gap = (int32_t)gap.size();
     sm.in.pc_rec = pcrec.data(); sm.in.n_pc = (int32_t)pcrec.size();
     sm.in.D = pre.disc.data(); sm.in.nD = nD; sm.in.G = pre.groups.data(); sm.in.nG = nG;

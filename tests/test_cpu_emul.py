@@ -19,19 +19,20 @@ def emul_bin():
     out = os.path.join(ROOT, "tests", "emul", "_build", "emul")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     srcs = ["tests/emul/emul_main.cpp", "squid_b200/csrc/host/readrec.cpp", "squid_b200/csrc/host/chimeric.cpp", "squid_b200/csrc/host/prepass.cpp"]
-    cmd = ["g++", "-std=c++17", "-O2", "-I", "include", "-I", "squid_b200/csrc", "-o", out] + srcs + ["-lpthread"]
+    cmd = ["g++", "-std=c++17", "-O2", "-fopenmp", "-I", "include", "-I", "squid_b200/csrc", "-o", out] + srcs + ["-lpthread"]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return out
 
 
 @pytest.mark.parametrize("case", ["chr17_3k", "fourchr_6k"])
-@pytest.mark.parametrize("one_island,bin_shift", [(False, 12), (True, 12), (False, 4), (False, 0)])
-def test_stepped_rules_match_golden(case, one_island, bin_shift, emul_bin, tmp_path):
+@pytest.mark.parametrize("one_island,bin_shift,chunks", [(False, 12, 1), (True, 12, 1), (False, 4, 7), (False, 0, 64)])
+def test_stepped_rules_match_golden(case, one_island, bin_shift, chunks, emul_bin, tmp_path):
     g = pyref.load_dumps(os.path.join(GOLD, case, "ref"))
     bps = pyref.breakpoints_of(g)
     bps.tofile(str(tmp_path / "bps.bin"))
     env = dict(os.environ)
+    env["SQH_PREPASS_CHUNKS"] = str(chunks)    # chimeric pre-pass: read loop split into this many chunks
     env["SQ_EMUL_BIN_SHIFT"] = str(bin_shift)  # segment-table position index: 0 = plain binary searches, 4 = many tiny bins
     if one_island:
         env["SQ_EMUL_ONE_ISLAND"] = "1"

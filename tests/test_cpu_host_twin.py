@@ -117,8 +117,8 @@ def test_parallel_sort_reproduces_std_sort(built_lib):
     L = api.lib()
     L.sqh_selftest_sort.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
     L.sqh_selftest_sort.restype = C.c_int
-    for n in (0, 1, 16, 17, 1000, 4097, 200000):
+    for n in (0, 1, 16, 17, 1000, 4097, 40000, 200000, 1000003):
         for rng in (1, 3, 100, 1 << 40):
             for pat in range(4):
-                for fan in (0, 4):
+                for fan in (0, 3, 8):  # threads: 0 = the sequential introsort loop alone
                     assert L.sqh_selftest_sort(n, n * 31 + rng + pat, rng, pat, fan) == 1, (n, rng, pat, fan)
