@@ -268,7 +268,7 @@ def main():
         phases = {}
         for _ in range(steps):
             step(resident)
-            for ph in ("h2d", "classify", "seed", "tile", "depth", "depth_edges", "edge_sort", "coverage", "k_classify", "k_conc_edges", "k_depth_targets", "k_cov_count"):
+            for ph in ("h2d", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_cov_count"):
                 v = g.phase_ms(ph)
                 if v >= 0:
                     phases[ph] = phases.get(ph, 0.0) + v / steps
@@ -290,15 +290,15 @@ def main():
     K = NB / R
     # algorithmic bytes per launch of the stream kernels: phase 1 and phase 2 read the whole batch
     # (32 B/record + 12 B/block), phase 3 the 24-byte subset of the qualifying half
-    alg = {"k_classify": 32 * R + 12 * NB, "k_conc_edges": 32 * R + 12 * NB, "k_depth_targets": 32 * R + 12 * NB, "k_cov_count": 24 * R}
-    traffic = {"k_classify": 55.7, "k_conc_edges": 45.8, "k_depth_targets": 21.3, "k_cov_count": 13.7}  # ncu dram bytes per record (profiles/r1_ncu_full_*)
+    alg = {"k_classify": 32 * R + 12 * NB, "k_assign": 32 * R + 12 * NB, "k_cov_count": 24 * R}
+    traffic = {"k_classify": None, "k_assign": None, "k_cov_count": 13.7}  # ncu dram bytes per record (profiles/)
     peak, peak_src = measured_peak_gbs()
     stream = {k: v for k, v in phases.items() if k in alg}
     top = max(stream, key=stream.get) if stream else None
     roof = None
     if top:
         ach = alg[top] / (stream[top] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic[top] * R,
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic[top] * R if traffic.get(top) else None,
                 "peak_source": peak_src, "alg_bytes_per_launch": alg[top], "ms": stream[top],
                 "note": "dominant STREAM kernel; the latency-bound seed machine and coverage chain are listed in phases_ms",
                 "all_stream_kernels": {k: {"ms": v, "GBps": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak} for k, v in stream.items()}}

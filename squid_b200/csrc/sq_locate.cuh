@@ -201,5 +201,76 @@ SQ_HD bool read_edges(const NodeTable &nt, const Params &p, ReadView &rv, int mo
     return true;
 }
 
+// ---- the concordant stream (RawEdgesOther) ---------------------------------------------------------------------------
+// whetherbuildedge (:1601-1605)
+template <class B>
+SQ_HD bool conc_builds_edges(const B &b, const Params &p, int64_t r) {
+    const uint32_t o = b.blk_off[r], nb = b.blk_off[r + 1] - o;
+    if (nb == 0 || !has_mate_block(b.flag[r], b.mate_ref_id[r])) return true;
+    int32_t front_rp = 0x7fffffff;
+    for (uint32_t k = 0; k < nb; k++) { const int32_t rp = b.blk_read_pos[o + k]; if (rp < front_rp) front_rp = rp; }
+    return front_rp <= 15 || (int32_t)b.lowphred_run[r] > p.max_lowphred_len;
+}
+SQ_HD Blk mate_block_of(uint16_t flag, int32_t mate_ref_id, int32_t mate_pos) {  // the synthetic 15-bp mate block (:306-314, 1588-1596)
+    Blk x;
+    x.ref_id = mate_ref_id; x.ref_pos = mate_pos; x.read_pos = 0; x.match_ref = kMateBlockLen; x.match_read = kMateBlockLen;
+    x.rev = flag_mate_rev(flag);
+    return x;
+}
+template <class B>
+SQ_HD void conc_load_read(const B &b, int64_t r, ReadView &rv, bool &is_first) {
+    is_first = flag_first(b.flag[r]);
+    Blk *own = is_first ? rv.F : rv.S;
+    Blk *oth = is_first ? rv.S : rv.F;
+    const int no = load_sorted_blocks(b, r, own);
+    int nm = 0;
+    if (has_mate_block(b.flag[r], b.mate_ref_id[r])) oth[nm++] = mate_block_of(b.flag[r], b.mate_ref_id[r], b.mate_pos[r]);
+    if (is_first) { rv.nF = no; rv.nS = nm; rv.first_total = b.total_len[r]; rv.second_total = 0; }
+    else { rv.nS = no; rv.nF = nm; rv.second_total = b.total_len[r]; rv.first_total = 0; }
+}
+
+// read_edges(MODE_OTHER, hint unknown) for a record with at most ONE own block -- nine records out of ten -- with
+// everything in registers: the lists are [own] and [mate], so there are no split junctions and at most one pair edge.
+// Returns -3 when the read is hint-sensitive (nothing emitted), else tmpRead_Node[0] (>= -1).  n = #blocks must be > 0.
+template <class Emit>
+SQ_HD int32_t read_edges_single(const NodeTable &nt, const Params &p, bool has_own, Blk own, bool has_mate, Blk mate, bool is_first,
+                                int32_t own_total, Emit &emit) {
+    const bool hasF = is_first ? has_own : has_mate, hasS = is_first ? has_mate : has_own;
+    Blk A = hasF ? (is_first ? own : mate) : (is_first ? mate : own);  // first block in FirstRead-then-SecondMate order
+    Blk Bk = is_first ? mate : own;                                     // second one (when both lists are non-empty)
+    const bool two = hasF && hasS;
+    bool sensitive = false;
+    Cursor cur;
+    cur.idx = 0; cur.known = false;
+    const int32_t jA = locate_block(nt, A, cur, false, 0, &sensitive);
+    if (sensitive) return -3;
+    if (jA >= 0) trim_block(nt, jA, A);
+    int32_t jB = -1;
+    if (two) {
+        jB = locate_block(nt, Bk, cur, false, 0, &sensitive);
+        if (sensitive) return -3;
+        if (jB >= 0) trim_block(nt, jB, Bk);
+    }
+    const bool ffi_known = jA != -1;  // firstfrontindex after this read (:1608-1609); the incoming one is not known
+    const int32_t ffi = jA;
+    const bool spanA = jA == -1 && A.ref_id >= 0 && A.ref_id < nt.n_ref, spanB = two && jB == -1 && Bk.ref_id >= 0 && Bk.ref_id < nt.n_ref;
+    int32_t iA = 0, iB = 0;
+    if (spanA) { iA = spanning_node(nt, A, ffi_known, ffi, &sensitive); if (sensitive) return -3; }
+    if (spanB) { iB = spanning_node(nt, Bk, ffi_known, ffi, &sensitive); if (sensitive) return -3; }
+    if (spanA && iA + 1 < nt.n) emit(edge_key(iA, false, iA + 1, true));
+    if (spanB && iB + 1 < nt.n) emit(edge_key(iB, false, iB + 1, true));
+    if (is_first && two && jA != jB && jA != -1 && jB != -1) {  // pair edge; F = [A] (own), S = [Bk] (mate)
+        const uint64_t key = edge_key(jA, A.rev, jB, Bk.rev);
+        const bool disc = edge_is_discordant(nt, p, key);
+        bool pd;  // IsPairDiscordant(false) on the trimmed blocks, first_total = own_total, second_total = 0
+        if (A.ref_id != Bk.ref_id || A.rev == Bk.rev) pd = true;
+        else if (!A.rev && A.ref_pos - A.read_pos > Bk.ref_pos - (0 - Bk.read_pos - Bk.match_read)) pd = true;
+        else if (!Bk.rev && Bk.ref_pos - Bk.read_pos > A.ref_pos - (own_total - A.read_pos - A.match_read)) pd = true;
+        else pd = false;
+        if (pd == disc) emit(key);
+    }
+    return jA;
+}
+
 }  // namespace sq
 #endif

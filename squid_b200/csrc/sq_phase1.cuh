@@ -39,7 +39,6 @@ struct P1Out {
 };
 
 constexpr uint32_t kP1Fields = F_REF | F_POS | F_MREF | F_MPOS | F_FLAG | F_TLEN | F_LOWQ | F_MAPQ | F_AUX | F_BLOCKS;
-constexpr int kWarpsPerTile = kTileThreads / 32;
 
 // classification straight from HBM: records whose predecessor lies before the tile, tiles too dense to stage
 // (`desc` = device copy of the batch descriptor: taking the address of the kernel parameter would force a per-thread copy)

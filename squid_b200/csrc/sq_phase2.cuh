@@ -1,0 +1,315 @@
+// Phase 2 of the path in ONE pass over the record batch, once the segment table exists: per-segment depth of the
+// concordant stream (BuildNode_STAR part D, SegmentGraph.cpp:784-825) and read-to-segment assignment + raw edges of the
+// stream (RawEdgesOther, :1557-1696).  Tiles are staged with TMA bulk copies (sq_stream.cuh) and are independent.
+//   * Segment lookups go through the position index of the segment table (seg_at): one table read and a step or two.
+//   * Records with at most one aligned block (nine in ten) take a register-only path (read_edges_single); the others
+//     are collected per tile and run the generic read_edges densely packed, so a warp never drags 31 idle lanes through it.
+//   * Edges are not written one by one: every tile counts them in a small shared-memory hash table (keys repeat massively
+//     in sorted input) and flushes (key, count) pairs; the sort + reduce that follows sees ~1 % of the raw volume.
+//   * Depth: ReadsOther blocks are counted directly; ReadsMain needs the forward-only segment cursor = running maximum
+//     of the per-read target.  The tile counts with its LOCAL running maximum and records (first target, maximum);
+//     k_depth_fix corrects the few tiles whose incoming cursor was ahead of their first target.
+#ifndef SQ_PHASE2_CUH
+#define SQ_PHASE2_CUH
+#include "sq_depth_cover.cuh"
+#include "sq_locate.cuh"
+#include "sq_stream.cuh"
+
+namespace sq {
+
+struct PairSink {  // raw (edge key, weight) pairs
+    uint64_t *keys; int32_t *w; int64_t cap; unsigned long long *counter;
+    __device__ __forceinline__ void add(uint64_t k, int32_t weight) {
+        const unsigned long long slot = atomicAdd(counter, 1ull);
+        if ((int64_t)slot < cap) { keys[slot] = k; w[slot] = weight; }
+    }
+    __device__ __forceinline__ void operator()(uint64_t k) { add(k, 1); }
+};
+
+constexpr int kEdgeSlots = 256;      // shared-memory edge table of a tile
+constexpr int kDepthWin = 64;        // segments [base, base + 64) of a tile are counted in shared memory
+constexpr uint64_t kEmptyKey = ~0ull;
+
+struct TileEdgeTable {
+    unsigned long long keys[kEdgeSlots];
+    int32_t cnt[kEdgeSlots];
+    PairSink spill;
+    __device__ __forceinline__ void operator()(uint64_t k) {
+        uint32_t h = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 56);
+#pragma unroll 1
+        for (int probe = 0; probe < 8; probe++, h = (h + 1) & (kEdgeSlots - 1)) {
+            const unsigned long long old = atomicCAS(&keys[h], (unsigned long long)kEmptyKey, (unsigned long long)k);
+            if (old == kEmptyKey || old == k) { atomicAdd(&cnt[h], 1); return; }
+        }
+        spill.add(k, 1);
+    }
+};
+
+struct DepthTile {  // per tile, for k_depth_fix
+    int32_t first_target;  // target of the first counted read of the tile (INT32_MAX if none)
+    int32_t max_target;    // maximum target of the tile (-1 if none); after k_depth_scan: the cursor before the tile
+};
+struct P2Args {
+    const uint8_t *cls;
+    NodeTable nt;
+    Params p;
+    int64_t r_break;
+    int32_t do_depth, do_edges;
+    int32_t *cnt_main, *sum_main, *cnt_other, *sum_other, *other_nonempty;
+    DepthTile *dtile;
+    int32_t *res0;
+    PairSink sink;
+    int32_t *sens; int32_t *n_sens; int32_t sens_cap;
+};
+
+constexpr uint32_t kP2Fields = F_REF | F_MREF | F_MPOS | F_FLAG | F_TLEN | F_LOWQ | F_CLS | F_BLOCKS;
+
+// one shared-memory counter pair per segment of the window, else global; leaders of equal-key groups add for the group
+__device__ __forceinline__ void depth_add(int32_t seg, int32_t len, bool on, int32_t base, int32_t *s_cnt, int32_t *s_sum, int32_t *g_cnt, int32_t *g_sum) {
+    const unsigned act = __ballot_sync(0xffffffffu, on);
+    if (!on) return;
+    const unsigned m = __match_any_sync(act, seg);
+    const int32_t tot = __reduce_add_sync(m, len);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+        const uint32_t w = (uint32_t)(seg - base);
+        if (w < (uint32_t)kDepthWin) { atomicAdd(&s_cnt[w], __popc(m)); atomicAdd(&s_sum[w], tot); }
+        else { atomicAdd(&g_cnt[seg], __popc(m)); atomicAdd(&g_sum[seg], tot); }
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2Args a, int bulk_ok) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileStage &s = *reinterpret_cast<TileStage *>(smem_raw);
+    __shared__ TileEdgeTable s_edges;
+    __shared__ int32_t s_dcnt[2][kDepthWin], s_dsum[2][kDepthWin];
+    __shared__ uint16_t s_slow[kTile];
+    __shared__ int32_t s_cmax[kTileChunks];
+    __shared__ int32_t s_nslow, s_base, s_other, s_first;
+    int32_t *s_m = s.end_pos;   // per record: depth target of its first block (-1: not counted)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    const int64_t tile = blockIdx.x;
+    const StageTicket tk = stage_issue<kP2Fields>(s, b, a.cls, tile, bulk_ok != 0);
+    const TileInfo ti = tk.ti;
+    const int n = ti.n;
+    const int64_t rec0 = ti.rec0;
+    for (int i = tid; i < kEdgeSlots; i += kTileThreads) { s_edges.keys[i] = kEmptyKey; s_edges.cnt[i] = 0; }
+    for (int i = tid; i < 2 * kDepthWin; i += kTileThreads) { (&s_dcnt[0][0])[i] = 0; (&s_dsum[0][0])[i] = 0; }
+    if (tid == 0) { s_edges.spill = a.sink; s_nslow = 0; s_other = 0; s_first = 0x7fffffff; s_base = -(1 << 30); }
+    stage_wait<kP2Fields>(s, b, a.cls, tk);
+    const bool staged = ti.nb >= 0;
+    const TileBatch tb = tile_view(s, ti, b);
+    if (tid == 0 && a.do_depth) {  // window of segments counted in shared memory: starts one segment left of the tile's first block
+        for (int i = 0; i < n; i++) {
+            const uint32_t o0 = s.blk_off[i];
+            if (s.blk_off[i + 1] > o0 && s.ref_id[i] >= 0 && s.ref_id[i] < a.nt.n_ref) {
+                const int32_t c = s.ref_id[i], c0 = a.nt.chr_first[c], c1 = a.nt.chr_first[c + 1];
+                const int32_t st = staged ? tb.blk_ref_pos[o0] : b.blk_ref_pos[o0];
+                if (c1 > c0) s_base = seg_at(a.nt, c, c0, c1, st) - 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const int32_t base = s_base;
+
+    // ---- pass A: depth targets + ReadsOther; edges of the single-block records ------------------------------------
+#pragma unroll 1
+    for (int j = 0; j < kTileRPT; j++) {
+        const int i = j * kTileThreads + tid;
+        const int64_t r = rec0 + i;
+        const bool in = i < n;
+        const uint8_t c8 = in ? s.cls[i] : (uint8_t)0;
+        const uint32_t o0 = in ? s.blk_off[i] : 0u, nb = in ? s.blk_off[i + 1] - o0 : 0u;
+        const int32_t rid = in ? s.ref_id[i] : -1;
+        // depth
+        int32_t m = -1;
+        if (a.do_depth) {
+            const bool counted = in && r < a.r_break && (c8 & CLS_HASBLK);
+            int32_t st0 = 0, l0 = 0;
+            if (counted) {
+                st0 = staged ? tb.blk_ref_pos[o0] : b.blk_ref_pos[o0]; l0 = staged ? tb.blk_match_ref[o0] : b.blk_match_ref[o0];
+                m = depth_target(a.nt, rid, st0, l0);
+                if (nb > 1) s_other = 1;
+            }
+            const uint32_t nb_max = __reduce_max_sync(full, counted ? nb : 0u);
+            for (uint32_t k = 1; k < nb_max; k++) {  // ReadsOther: every block is counted in its own target segment
+                bool on = false;
+                int32_t m2 = 0, l = 0;
+                if (counted && k < nb) {
+                    const int32_t st = staged ? tb.blk_ref_pos[o0 + k] : b.blk_ref_pos[o0 + k];
+                    l = staged ? tb.blk_match_ref[o0 + k] : b.blk_match_ref[o0 + k];
+                    m2 = depth_target(a.nt, rid, st, l);
+                    on = m2 != kNoNode && depth_contained(a.nt, m2, rid, st, l);
+                }
+                depth_add(m2, l, on, base, s_dcnt[1], s_dsum[1], a.cnt_other, a.sum_other);
+            }
+            if (in) s_m[i] = m;
+            const int32_t cm = __reduce_max_sync(full, m);
+            const unsigned vm = __ballot_sync(full, m >= 0);
+            if (lane == 0) {
+                s_cmax[j * kWarpsPerTile + warp] = cm;
+                if (vm) atomicMin(&s_first, (j * kWarpsPerTile + warp) * 32 + __ffs(vm) - 1);
+            }
+        }
+        // edges
+        if (a.do_edges) {
+            int32_t out = -2;
+            if (in && (c8 & CLS_KEEP)) {
+                if (nb <= 1 && staged) {
+                    const uint16_t f = s.flag[i];
+                    const bool has_mate = has_mate_block(f, s.mate_ref_id[i]);
+                    bool builds = true;
+                    Blk own;
+                    own.ref_id = rid; own.rev = flag_rev(f); own.ref_pos = 0; own.match_ref = 0; own.read_pos = 0; own.match_read = 0;
+                    if (nb == 1) {
+                        own.ref_pos = tb.blk_ref_pos[o0]; own.match_ref = tb.blk_match_ref[o0]; own.read_pos = tb.blk_read_pos[o0]; own.match_read = tb.blk_match_read[o0];
+                        if (has_mate) builds = own.read_pos <= 15 || (int32_t)s.lowphred_run[i] > a.p.max_lowphred_len;
+                    }
+                    if (builds && (nb == 1 || has_mate))
+                        out = read_edges_single(a.nt, a.p, nb == 1, own, has_mate, mate_block_of(f, s.mate_ref_id[i], s.mate_pos[i]), flag_first(f), (int32_t)s.total_len[i], s_edges);
+                } else {
+                    out = -4;  // generic path below
+                    s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)i;
+                }
+            }
+            if (in && out != -4) {
+                a.res0[r] = out;
+                if (out == -3) { const int32_t q = atomicAdd(a.n_sens, 1); if (q < a.sens_cap) a.sens[q] = (int32_t)r; }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- pass B: the multi-block records, densely packed, through the generic rules --------------------------------
+    if (a.do_edges) {
+        const int ns = s_nslow;
+#pragma unroll 1
+        for (int q = tid; q < ns; q += kTileThreads) {
+            const int i = s_slow[q];
+            const int64_t r = rec0 + i;
+            int32_t out = -2;
+            if (staged ? conc_builds_edges(tb, a.p, r) : conc_builds_edges(b, a.p, r)) {
+                Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+                int32_t node[2 * kMaxBlocks + 2];
+                ReadView rv; rv.F = F; rv.S = S;
+                bool is_first;
+                if (staged) conc_load_read(tb, r, rv, is_first); else conc_load_read(b, r, rv, is_first);
+                if (rv.nF + rv.nS > 0) out = read_edges(a.nt, a.p, rv, MODE_OTHER, is_first, false, 0, node, s_edges) ? node[0] : -3;
+            }
+            a.res0[r] = out;
+            if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
+        }
+    }
+    // ---- ReadsMain with the tile-local cursor -----------------------------------------------------------------------
+    if (a.do_depth) {
+        if (warp == 0) {
+            int32_t inc = lane < kTileChunks ? s_cmax[lane] : -1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(full, inc, d); if (lane >= d && u > inc) inc = u; }
+            const int32_t tot = __shfl_sync(full, inc, 31);
+            int32_t exc = __shfl_up_sync(full, inc, 1);
+            if (lane == 0) exc = -1;
+            if (lane < kTileChunks) s_cmax[lane] = exc;
+            if (lane == 0) {
+                DepthTile d; d.max_target = tot; d.first_target = s_first < kTile ? s_m[s_first] : 0x7fffffff;
+                a.dtile[tile] = d;
+                if (s_other) *a.other_nonempty = 1;
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int j = 0; j < kTileRPT; j++) {
+            const int i = j * kTileThreads + tid;
+            const int32_t m = i < n ? s_m[i] : -1;
+            int32_t v = m;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(full, v, d); if (lane >= d && u > v) v = u; }
+            const int32_t e = s_cmax[j * kWarpsPerTile + warp];
+            if (e > v) v = e;  // cursor at this read: running maximum of the targets so far in the tile
+            bool on = false;
+            int32_t l0 = 0;
+            if (m >= 0 && v != kNoNode && v < a.nt.n) {
+                const uint32_t o0 = s.blk_off[i];
+                const int32_t st0 = staged ? tb.blk_ref_pos[o0] : b.blk_ref_pos[o0];
+                l0 = staged ? tb.blk_match_ref[o0] : b.blk_match_ref[o0];
+                on = depth_contained(a.nt, v, s.ref_id[i], st0, l0);
+            }
+            depth_add(v, l0, on, base, s_dcnt[0], s_dsum[0], a.cnt_main, a.sum_main);
+        }
+    }
+    __syncthreads();
+    // ---- flush the tile's tables --------------------------------------------------------------------------------------
+    if (a.do_depth) {
+        for (int w = tid; w < kDepthWin; w += kTileThreads) {
+            const int32_t seg = base + w;
+            if (s_dcnt[0][w]) { atomicAdd(&a.cnt_main[seg], s_dcnt[0][w]); atomicAdd(&a.sum_main[seg], s_dsum[0][w]); }
+            if (s_dcnt[1][w]) { atomicAdd(&a.cnt_other[seg], s_dcnt[1][w]); atomicAdd(&a.sum_other[seg], s_dsum[1][w]); }
+        }
+    }
+    if (a.do_edges) {  // one reservation in the raw pair list per tile
+        int mine = 0;
+        for (int h = tid; h < kEdgeSlots; h += kTileThreads) mine += s_edges.cnt[h] != 0;
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(full, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) s_cmax[warp] = inc;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < kWarpsPerTile; w++) { const int c = s_cmax[w]; s_cmax[w] = tot; tot += c; }
+            s_nslow = tot;
+            if (tot > 0) { const unsigned long long at = atomicAdd(a.sink.counter, (unsigned long long)tot); s_cmax[kWarpsPerTile] = (int32_t)(at & 0x7fffffffu); s_cmax[kWarpsPerTile + 1] = (int32_t)(at >> 31); }
+        }
+        __syncthreads();
+        if (s_nslow > 0) {
+            long long at = ((long long)s_cmax[kWarpsPerTile + 1] << 31) + s_cmax[kWarpsPerTile] + s_cmax[warp] + inc - mine;
+            for (int h = tid; h < kEdgeSlots; h += kTileThreads)
+                if (s_edges.cnt[h]) { if (at < a.sink.cap) { a.sink.keys[at] = (uint64_t)s_edges.keys[h]; a.sink.w[at] = s_edges.cnt[h]; } at++; }
+        }
+    }
+}
+
+// exclusive running maximum of the per-tile maximum targets (one block); tiles with no counted read pass the cursor on
+__global__ void __launch_bounds__(1024) k_depth_scan(DepthTile *dt, int32_t n_tiles) {
+    __shared__ int32_t s_mx[1024];
+    const int tid = threadIdx.x;
+    const int per = (n_tiles + 1023) / 1024;
+    const int lo = tid * per < n_tiles ? tid * per : n_tiles, hi = (tid + 1) * per < n_tiles ? (tid + 1) * per : n_tiles;
+    int32_t mx = -1;
+    for (int t = lo; t < hi; t++) if (dt[t].max_target > mx) mx = dt[t].max_target;
+    s_mx[tid] = mx;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        int32_t v = -1;
+        if (tid >= d) v = s_mx[tid - d];
+        __syncthreads();
+        if (tid >= d && v > s_mx[tid]) s_mx[tid] = v;
+        __syncthreads();
+    }
+    mx = tid ? s_mx[tid - 1] : -1;
+    for (int t = lo; t < hi; t++) { const int32_t own = dt[t].max_target; dt[t].max_target = mx; if (own > mx) mx = own; }
+}
+
+// Tiles whose incoming cursor is ahead of their first target counted some reads against the wrong segment: redo those
+// reads literally (one thread per such tile; sorted input makes them rare).
+__global__ void k_depth_fix(DevBatch b, const uint8_t *cls, NodeTable nt, int64_t r_break, const DepthTile *dt, int32_t n_tiles, int32_t *cnt_main, int32_t *sum_main) {
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int32_t carry = dt[t].max_target;
+    if (carry < 0 || dt[t].first_target == 0x7fffffff || carry <= dt[t].first_target) return;
+    int32_t loc = -1;
+    const int64_t r0 = (int64_t)t * kTile, r1 = r0 + kTile < b.n_rec ? r0 + kTile : b.n_rec;
+    for (int64_t r = r0; r < r1 && r < r_break; r++) {
+        if (!(cls[r] & CLS_HASBLK)) continue;
+        const uint32_t o = b.blk_off[r];
+        const int32_t c = b.ref_id[r], st = b.blk_ref_pos[o], l = b.blk_match_ref[o];
+        const int32_t m = depth_target(nt, c, st, l);
+        if (m > loc) loc = m;
+        if (loc >= carry) break;  // from here on the local cursor was the true one
+        if (loc != kNoNode && loc >= 0 && loc < nt.n && depth_contained(nt, loc, c, st, l)) { atomicAdd(&cnt_main[loc], -1); atomicAdd(&sum_main[loc], -l); }
+        if (carry != kNoNode && carry < nt.n && depth_contained(nt, carry, c, st, l)) { atomicAdd(&cnt_main[carry], 1); atomicAdd(&sum_main[carry], l); }
+    }
+}
+
+}  // namespace sq
+#endif

@@ -16,6 +16,7 @@ namespace sq {
 constexpr int kTile = 512;           // records per tile
 constexpr int kTileThreads = 128;    // threads per tile (kTile / kTileThreads records each, striped); 8 tiles resident per SM
 constexpr int kTileRPT = kTile / kTileThreads;
+constexpr int kWarpsPerTile = kTileThreads / 32;
 constexpr int kTileChunks = kTile / 32;  // 32-record chunks: chunk c = records [32c, 32c+32) of the tile
 constexpr int kTileBlkCap = 768;     // staged blocks per tile (K <= 1.48 with the 8-element alignment slack); denser tiles read HBM directly
 

@@ -19,6 +19,7 @@
 #include "sq_depth_cover.cuh"
 #include "sq_locate.cuh"
 #include "sq_phase1.cuh"
+#include "sq_phase2.cuh"
 #include "sq_seed.cuh"
 #include "sqg_ctx.cuh"
 
@@ -256,122 +257,10 @@ __global__ void k_depth_disc(NodeTable nt, const DiscBlock *D, int32_t nD, int32
     if (j >= c0 && d.pos >= nt.pos[j] && d.pos + d.len <= nt.end[j]) { atomicAdd(&cnt[j], 1); atomicAdd(&sum[j], d.len); }
 }
 
-// ReadsMain targets (to be max-scanned) + ReadsOther counted directly (no sort needed: DESIGN.md)
-__global__ void k_depth_targets(DevBatch b, const uint8_t *cls, NodeTable nt, int64_t r_break, int32_t *target,
-                                int32_t *cnt_other, int32_t *sum_other, int32_t *other_nonempty) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= b.n_rec) return;
-    int32_t m = -1;
-    if (r < r_break && (cls[r] & CLS_HASBLK)) {
-        const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
-        const int32_t c = b.ref_id[r];
-        m = depth_target(nt, c, b.blk_ref_pos[o], b.blk_match_ref[o]);
-        if (e - o > 1) *other_nonempty = 1;
-        for (uint32_t k = o + 1; k < e; k++) {
-            const int32_t s = b.blk_ref_pos[k], l = b.blk_match_ref[k];
-            const int32_t m2 = depth_target(nt, c, s, l);
-            if (m2 != kNoNode && depth_contained(nt, m2, c, s, l)) { atomicAdd(&cnt_other[m2], 1); atomicAdd(&sum_other[m2], l); }
-        }
-    }
-    target[r] = m;
-}
-// one atomic per run of equal segments inside a warp (sorted input => long runs): int sums wrap like the reference's `int`
-__device__ __forceinline__ void warp_add_by_key(int32_t key, int32_t len, int32_t *cnt, int32_t *sum) {
-    const unsigned m = __match_any_sync(0xffffffffu, key);
-    const int32_t s = __reduce_add_sync(m, len);
-    if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(&cnt[key], __popc(m)); atomicAdd(&sum[key], s); }
-}
-__global__ void k_depth_main_count(DevBatch b, const uint8_t *cls, NodeTable nt, int64_t r_break, const int32_t *cursor,
-                                   int32_t *cnt_main, int32_t *sum_main) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int32_t key = -1, len = 0;
-    if (r < b.n_rec && r < r_break && (cls[r] & CLS_HASBLK)) {
-        const int32_t c = cursor[r];
-        if (c != kNoNode && c >= 0 && c < nt.n) {
-            const uint32_t o = b.blk_off[r];
-            const int32_t s = b.blk_ref_pos[o], l = b.blk_match_ref[o];
-            if (depth_contained(nt, c, b.ref_id[r], s, l)) { key = c; len = l; }
-        }
-    }
-    warp_add_by_key(key, len, cnt_main, sum_main);
-}
-
 // ------------------------------------------------------------------------------------------------
 // kernels: assignment + raw edges
 // ------------------------------------------------------------------------------------------------
-struct EdgeSink {
-    uint64_t *keys; int64_t cap; unsigned long long *counter;
-    __device__ void operator()(uint64_t k) {
-        const unsigned long long slot = atomicAdd(counter, 1ull);
-        if ((int64_t)slot < cap) keys[slot] = k;
-    }
-};
-
 // res0 codes: >= 0 segment of the read's first block; -1 located nowhere; -2 read does not touch the hint; -3 hint-sensitive
-__device__ __forceinline__ bool conc_builds_edges(const DevBatch &b, const Params &p, int64_t r) {  // whetherbuildedge (:1601-1605)
-    const uint32_t o = b.blk_off[r], nb = b.blk_off[r + 1] - o;
-    if (nb == 0 || !has_mate_block(b.flag[r], b.mate_ref_id[r])) return true;
-    int32_t front_rp = 0x7fffffff;
-    for (uint32_t k = 0; k < nb; k++) { const int32_t rp = b.blk_read_pos[o + k]; if (rp < front_rp) front_rp = rp; }
-    return front_rp <= 15 || (int32_t)b.lowphred_run[r] > p.max_lowphred_len;
-}
-__device__ __forceinline__ void conc_load_read(const DevBatch &b, int64_t r, ReadView &rv, bool &is_first) {
-    is_first = flag_first(b.flag[r]);
-    Blk *own = is_first ? rv.F : rv.S;
-    Blk *oth = is_first ? rv.S : rv.F;
-    const int no = load_sorted_blocks(b, r, own);
-    int nm = 0;
-    if (has_mate_block(b.flag[r], b.mate_ref_id[r])) {
-        Blk x;
-        x.ref_id = b.mate_ref_id[r]; x.ref_pos = b.mate_pos[r]; x.read_pos = 0; x.match_ref = kMateBlockLen; x.match_read = kMateBlockLen;
-        x.rev = flag_mate_rev(b.flag[r]);
-        oth[nm++] = x;
-    }
-    if (is_first) { rv.nF = no; rv.nS = nm; rv.first_total = b.total_len[r]; rv.second_total = 0; }
-    else { rv.nS = no; rv.nF = nm; rv.second_total = b.total_len[r]; rv.first_total = 0; }
-}
-
-__global__ void k_conc_edges(DevBatch b, const uint8_t *cls, Params p, NodeTable nt, int32_t *res0, EdgeSink sink) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= b.n_rec) return;
-    int32_t out = -2;
-    if ((cls[r] & CLS_KEEP) && conc_builds_edges(b, p, r)) {
-        Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
-        int32_t node[2 * kMaxBlocks + 2];
-        ReadView rv; rv.F = F; rv.S = S;
-        bool is_first;
-        conc_load_read(b, r, rv, is_first);
-        if (rv.nF + rv.nS > 0) {
-            if (read_edges(nt, p, rv, MODE_OTHER, is_first, false, 0, node, sink)) out = node[0];
-            else out = -3;
-        }
-    }
-    res0[r] = out;
-}
-// Hint-sensitive reads are replayed with the true hint = segment of the first block of the nearest earlier read that
-// set one (res0 >= 0).  A sensitive read whose nearest candidate is itself still unresolved waits for the next round;
-// chains of adjacent sensitive reads are short, so a couple of rounds resolve everything.
-__global__ void k_conc_fixup(DevBatch b, Params p, NodeTable nt, int32_t *res0, const int32_t *sens, int32_t n_sens, EdgeSink sink, int32_t *n_left) {
-    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_sens) return;
-    const int64_t r = sens[i];
-    if (((volatile int32_t *)res0)[r] != -3) return;  // resolved in an earlier round
-    int32_t hint = 0;  // firstfrontindex starts at 0 (:1568)
-    for (int64_t q = r - 1; q >= 0; q--) {
-        const int32_t v = ((volatile int32_t *)res0)[q];
-        if (v >= 0) { hint = v; break; }
-        if (v == -3) { atomicAdd(n_left, 1); return; }
-    }
-    Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
-    int32_t node[2 * kMaxBlocks + 2];
-    ReadView rv; rv.F = F; rv.S = S;
-    bool is_first;
-    conc_load_read(b, r, rv, is_first);
-    read_edges(nt, p, rv, MODE_OTHER, is_first, true, hint, node, sink);
-    __threadfence();
-    ((volatile int32_t *)res0)[r] = node[0] >= 0 ? node[0] : -1;
-}
-
 struct ChimDev {
     int64_t n_reads;
     const uint32_t *read_off; const uint16_t *n_first;
@@ -397,7 +286,7 @@ __device__ __forceinline__ void chim_store_read(const ChimDev &c, int64_t i, con
             c.ref_pos[k] = x.ref_pos; c.match_ref[k] = x.match_ref; c.read_pos[k] = x.read_pos; c.match_read[k] = x.match_read;
         }
 }
-__global__ void k_chim_edges(ChimDev c, Params p, NodeTable nt, int32_t *res0, EdgeSink sink) {
+__global__ void k_chim_edges(ChimDev c, Params p, NodeTable nt, int32_t *res0, PairSink sink, int32_t *sens, int32_t *n_sens) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= c.n_reads) return;
     Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
@@ -407,34 +296,51 @@ __global__ void k_chim_edges(ChimDev c, Params p, NodeTable nt, int32_t *res0, E
     int32_t out = -2;
     if (rv.nF + rv.nS > 0) {
         if (read_edges(nt, p, rv, MODE_CHIM, true, false, 0, node, sink)) { out = node[0]; chim_store_read(c, i, rv); }
-        else out = -3;
+        else { out = -3; sens[atomicAdd(n_sens, 1)] = (int32_t)i; }  // sens holds n_reads entries
     }
     res0[i] = out;
 }
-__global__ void k_chim_fixup(ChimDev c, Params p, NodeTable nt, int32_t *res0, const int32_t *sens, int32_t n_sens, EdgeSink sink, int32_t *n_left) {
-    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_sens) return;
-    const int64_t i = sens[k];
-    if (((volatile int32_t *)res0)[i] != -3) return;
-    int32_t hint = 0;  // :1395
-    for (int64_t q = i - 1; q >= 0; q--) {
-        const int32_t v = ((volatile int32_t *)res0)[q];
-        if (v >= 0) { hint = v; break; }
-        if (v == -3) { atomicAdd(n_left, 1); return; }
+// Hint-sensitive reads are replayed with the true hint = segment of the first block of the nearest earlier read that
+// located one (res0 >= 0), in stream order.  A run of sensitive reads with no located read in between is a chain: its first
+// read (the head) knows its hint from the untouched part of res0, and the head's thread replays the whole chain in order.
+__global__ void k_fix_heads(const int32_t *res0, const int32_t *sens, const int32_t *n_sens, int32_t cap, int32_t *head_hint) {
+    const int32_t n = *n_sens < cap ? *n_sens : cap;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int32_t hint = 0;  // firstfrontindex starts at 0 (:1395, :1568)
+        for (int64_t q = (int64_t)sens[i] - 1; q >= 0; q--) {
+            const int32_t v = res0[q];
+            if (v >= 0) { hint = v; break; }
+            if (v == -3) { hint = -1; break; }  // not a head
+        }
+        head_hint[i] = hint;
     }
-    Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
-    int32_t node[2 * kMaxBlocks + 2];
-    ReadView rv; rv.F = F; rv.S = S;
-    chim_load_read(c, i, rv);
-    read_edges(nt, p, rv, MODE_CHIM, true, true, hint, node, sink);
-    chim_store_read(c, i, rv);
-    __threadfence();
-    ((volatile int32_t *)res0)[i] = node[0] >= 0 ? node[0] : -1;
 }
-struct IsSensOp {
-    const int32_t *res0;
-    __device__ bool operator()(int32_t r) const { return res0[r] == -3; }
-};
+template <bool CHIM>
+__global__ void k_fix_chains(DevBatch b, ChimDev c, Params p, NodeTable nt, int32_t *res0, int64_t n_items, const int32_t *sens, const int32_t *n_sens, int32_t cap,
+                             const int32_t *head_hint, PairSink sink) {
+    const int32_t n = *n_sens < cap ? *n_sens : cap;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int32_t hint = head_hint[i];
+        if (hint < 0) continue;
+        int64_t q = sens[i];
+        for (;;) {
+            Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+            int32_t node[2 * kMaxBlocks + 2];
+            ReadView rv; rv.F = F; rv.S = S;
+            bool is_first = true;
+            if (CHIM) chim_load_read(c, q, rv); else conc_load_read(b, q, rv, is_first);
+            read_edges(nt, p, rv, CHIM ? MODE_CHIM : MODE_OTHER, is_first, true, hint, node, sink);
+            if (CHIM) chim_store_read(c, q, rv);
+            res0[q] = node[0] >= 0 ? node[0] : -1;
+            if (node[0] >= 0) hint = node[0];
+            int64_t q2 = q + 1;
+            int32_t v = -2;
+            while (q2 < n_items && (v = res0[q2]) < 0 && v != -3) q2++;
+            if (q2 >= n_items || v != -3) break;  // the next read that matters located on its own: the chain ends
+            q = q2;
+        }
+    }
+}
 __global__ void k_unpack_edges(const uint64_t *keys, const int32_t *counts, int64_t n, int32_t *ind1, int32_t *ind2, uint8_t *heads, int32_t *w) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -623,7 +529,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
-    ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
+    ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
     ctx->h_chr.release(); ctx->h_pos.release(); ctx->h_len.release(); ctx->h_cnt3.release(); ctx->h_sum3.release(); ctx->h_ind1.release(); ctx->h_ind2.release();
@@ -689,7 +595,7 @@ extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t fi
     b.blk_off = ctx->o_blk_off.p; b.blk_ref_pos = ctx->o_blk_ref_pos.p; b.blk_match_ref = ctx->o_blk_match_ref.p;
     b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
     PHASE_END("h2d");
-    ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->first_record_index = first_record_index;
+    ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
     return SQG_OK;
 }
 
@@ -702,7 +608,7 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     b.ref_id = db->ref_id; b.pos = db->pos; b.mate_ref_id = db->mate_ref_id; b.mate_pos = db->mate_pos; b.end_pos = db->end_pos;
     b.flag = db->flag; b.total_len = db->total_len; b.lowphred_run = db->lowphred_run; b.mapq = db->mapq; b.aux = db->aux;
     b.blk_off = db->blk_off; b.blk_ref_pos = db->blk_ref_pos; b.blk_match_ref = db->blk_match_ref; b.blk_read_pos = db->blk_read_pos; b.blk_match_read = db->blk_match_read;
-    ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->first_record_index = first_record_index;
+    ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
     return SQG_OK;
 }
 
@@ -731,7 +637,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     UPV(dc_ref_id, c->blk_ref_id, nb); UPV(dc_ref_pos, c->blk_ref_pos, nb); UPV(dc_read_pos, c->blk_read_pos, nb);
     UPV(dc_match_ref, c->blk_match_ref, nb); UPV(dc_match_read, c->blk_match_read, nb); UPV(dc_rev, c->blk_is_reverse, nb);
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->have_chim = true;
+    ctx->have_chim = true; ctx->have_edge_table = false;
     return SQG_OK;
 }
 
@@ -930,6 +836,93 @@ static int tile_genome(sqg_ctx *ctx, std::vector<SeedNode> &seedv) {
     return install_nodes(ctx);
 }
 
+static int reduce_edges(sqg_ctx *ctx, int64_t n_raw, const int32_t *d_weights_in);
+
+// Phase 2 (sq_phase2.cuh): one pass over the batch for the depth numerators (do_depth) and the raw edges of the chimeric
+// reads + the concordant stream (do_edges); then the hint fix-up chains and the sort + reduce of the (key, count) pairs.
+static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec;
+    const int32_t N = ctx->nt.n;
+    const int32_t nD = (int32_t)ctx->pre.disc.size() - 1;
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    ChimDev cd;
+    cd.n_reads = ctx->c_n_reads; cd.read_off = ctx->dc_read_off.p; cd.n_first = ctx->dc_n_first.p;
+    cd.first_total = ctx->dc_first_total.p; cd.second_total = ctx->dc_second_total.p;
+    cd.ref_id = ctx->dc_ref_id.p; cd.ref_pos = ctx->dc_ref_pos.p; cd.read_pos = ctx->dc_read_pos.p; cd.match_ref = ctx->dc_match_ref.p; cd.match_read = ctx->dc_match_read.p;
+    cd.rev = ctx->dc_rev.p;
+    if (do_depth) { CK(ctx->d_cnt3.ensure(3 * (size_t)N + 4)); CK(ctx->d_sum3.ensure(3 * (size_t)N + 4)); CK(ctx->d_dtile.ensure(n_tiles + 1)); }
+    int64_t cap = std::max<int64_t>({(int64_t)ctx->d_ekeys.cap, n / 8 + 4 * ctx->c_n_blk + 2 * ctx->c_n_reads + 4096, (int64_t)1 << 20});
+    int64_t sens_cap = std::max<int64_t>({(int64_t)ctx->d_sens.cap, n / 64 + 4096, ctx->c_n_reads + 1});
+    CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1));
+    int64_t n_raw = 0;
+    PHASE_BEGIN(do_depth ? "depth_edges" : "edges_only");
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (do_edges) { CK(ctx->d_ekeys.ensure(cap)); CK(ctx->d_ew.ensure(cap)); CK(ctx->d_sens.ensure(sens_cap)); CK(ctx->d_head.ensure(sens_cap)); }
+        cap = do_edges ? (int64_t)std::min(ctx->d_ekeys.cap, ctx->d_ew.cap) : 0;
+        sens_cap = do_edges ? (int64_t)std::min(ctx->d_sens.cap, ctx->d_head.cap) : 0;
+        // counters: [9] raw pairs | [10] sensitive concordant reads, sensitive chimeric reads (int32 each)
+        CK(cudaMemsetAsync(ctx->d_counters.p + 9, 0, 2 * sizeof(int64_t), ctx->stream));
+        unsigned long long *d_cnt = (unsigned long long *)(ctx->d_counters.p + 9);
+        int32_t *d_nsens = (int32_t *)(ctx->d_counters.p + 10);
+        PairSink sink{ctx->d_ekeys.p, ctx->d_ew.p, cap, d_cnt};
+        if (do_depth) {
+            CK(cudaMemsetAsync(ctx->d_cnt3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_sum3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
+            if (nD > 0) LAUNCH(k_depth_disc, blocks_for(nD), kThreads, ctx->nt, ctx->d_disc.p, nD, ctx->d_cnt3.p, ctx->d_sum3.p);
+        }
+        if (do_edges && cd.n_reads > 0) {  // RawEdgesChim: chimeric reads, their sensitive ones replayed in chains
+            // (the chimeric sensitive list lives behind the concordant one)
+            int32_t *csens = ctx->d_sens.p + (sens_cap - ctx->c_n_reads - 1), *chead = ctx->d_head.p + (sens_cap - ctx->c_n_reads - 1);
+            LAUNCH(k_chim_edges, blocks_for(cd.n_reads), kThreads, cd, ctx->params, ctx->nt, ctx->dc_res0.p, sink, csens, d_nsens + 1);
+            LAUNCH(k_fix_heads, 64, 128, ctx->dc_res0.p, csens, d_nsens + 1, (int32_t)ctx->c_n_reads, chead);
+            LAUNCH(k_fix_chains<true>, 64, 128, b, cd, ctx->params, ctx->nt, ctx->dc_res0.p, cd.n_reads, csens, d_nsens + 1, (int32_t)ctx->c_n_reads, chead, sink);
+        }
+        const int32_t conc_sens_cap = (int32_t)std::max<int64_t>(0, sens_cap - ctx->c_n_reads - 1);
+        if (n > 0) {
+            P2Args a;
+            a.cls = ctx->d_cls.p; a.nt = ctx->nt; a.p = ctx->params; a.r_break = ctx->r_break; a.do_depth = do_depth; a.do_edges = do_edges;
+            a.cnt_main = ctx->d_cnt3.p + (size_t)N; a.sum_main = ctx->d_sum3.p + (size_t)N;
+            a.cnt_other = ctx->d_cnt3.p + 2 * (size_t)N; a.sum_other = ctx->d_sum3.p + 2 * (size_t)N;
+            a.other_nonempty = do_depth ? ctx->d_cnt3.p + 3 * (size_t)N : nullptr;
+            a.dtile = ctx->d_dtile.p; a.res0 = ctx->d_scratch32.p; a.sink = sink;
+            a.sens = ctx->d_sens.p; a.n_sens = d_nsens; a.sens_cap = conc_sens_cap;
+            CK(cudaFuncSetAttribute(k_assign_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            PHASE_BEGIN("k_assign");
+            k_assign_tiles<<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            PHASE_END("k_assign");
+            if (do_depth) {
+                LAUNCH(k_depth_scan, 1, 1024, ctx->d_dtile.p, (int32_t)n_tiles);
+                LAUNCH(k_depth_fix, blocks_for(n_tiles), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_dtile.p, (int32_t)n_tiles, a.cnt_main, a.sum_main);
+            }
+            if (do_edges) {
+                LAUNCH(k_fix_heads, 256, 128, ctx->d_scratch32.p, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p);
+                LAUNCH(k_fix_chains<false>, 256, 128, b, cd, ctx->params, ctx->nt, ctx->d_scratch32.p, n, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, sink);
+            }
+        }
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_raw = ctx->h_counters.p[9];
+        const int32_t ns_conc = ((int32_t *)(ctx->h_counters.p + 10))[0], ns_chim = ((int32_t *)(ctx->h_counters.p + 10))[1];
+        ctx->n_sensitive = (int64_t)ns_conc + ns_chim;
+        if (!do_edges || (n_raw <= cap && ns_conc <= conc_sens_cap)) break;
+        if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge / sensitive read buffer overflow");
+        cap = std::max(cap, n_raw + 4096);  // rerun with room for everything (chimeric trims are idempotent, counters are reset)
+        sens_cap = std::max<int64_t>(sens_cap, (int64_t)ns_conc + ctx->c_n_reads + 4096);
+    }
+    PHASE_END(do_depth ? "depth_edges" : "edges_only");
+    if (do_edges) {
+        ctx->n_raw_edges = n_raw;
+        PHASE_BEGIN("edge_sort");
+        const int rc = reduce_edges(ctx, n_raw, ctx->d_ew.p);
+        if (rc) return rc;
+        PHASE_END("edge_sort");
+    }
+    return SQG_OK;
+}
+
 extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
                                int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty) {
     if (!ctx || !chr || !pos || !len || !n_nodes || !count3 || !sumlen3 || !reads_other_nonempty) return SQG_EINVAL;
@@ -1105,28 +1098,10 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
             r += m;
         }
     }
-    // depth
-    PHASE_BEGIN("depth");
+    // phase 2 in one pass: per-segment depth and, eagerly, the assignment + raw edges sqg_build_edges will ask for
     const int32_t N = ctx->nt.n;
-    CK(ctx->d_cnt3.ensure(3 * (size_t)N + 4)); CK(ctx->d_sum3.ensure(3 * (size_t)N + 4));
-    CK(cudaMemsetAsync(ctx->d_cnt3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_sum3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
-    LAUNCH(k_depth_disc, blocks_for(nD), kThreads, ctx->nt, ctx->d_disc.p, nD, ctx->d_cnt3.p, ctx->d_sum3.p);
-    if (n > 0) {
-        int32_t *d_flag = ctx->d_cnt3.p + 3 * (size_t)N;
-        PHASE_BEGIN("k_depth_targets");
-        LAUNCH(k_depth_targets, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_scratch32.p,
-               ctx->d_cnt3.p + 2 * (size_t)N, ctx->d_sum3.p + 2 * (size_t)N, d_flag);
-        PHASE_END("k_depth_targets");
-        size_t tb = 0;
-        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_scratch32.p, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
-        ENSURE_TEMP(tb);
-        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_scratch32.p, ctx->d_scratch32.p, MaxI32(), (int)n, ctx->stream));
-        ctx->launches += 2;
-        LAUNCH(k_depth_main_count, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_scratch32.p,
-               ctx->d_cnt3.p + (size_t)N, ctx->d_sum3.p + (size_t)N);
-    }
-    PHASE_END("depth");
+    rc = run_assign(ctx, true, true);
+    if (rc) return rc;
     CK(ctx->h_chr.ensure(N)); CK(ctx->h_pos.ensure(N)); CK(ctx->h_len.ensure(N)); CK(ctx->h_cnt3.ensure(3 * (size_t)N + 4)); CK(ctx->h_sum3.ensure(3 * (size_t)N + 4));
     CK(cudaMemcpyAsync(ctx->h_cnt3.p, ctx->d_cnt3.p, (3 * (size_t)N + 4) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_sum3.p, ctx->d_sum3.p, 3 * (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1195,64 +1170,10 @@ extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uin
     if (rc) return rc;
     rc = finish_prepass(ctx);
     if (rc) return rc;
-    const DevBatch &b = ctx->batch;
-    const int64_t n = b.n_rec;
-    ChimDev cd;
-    cd.n_reads = ctx->c_n_reads; cd.read_off = ctx->dc_read_off.p; cd.n_first = ctx->dc_n_first.p;
-    cd.first_total = ctx->dc_first_total.p; cd.second_total = ctx->dc_second_total.p;
-    cd.ref_id = ctx->dc_ref_id.p; cd.ref_pos = ctx->dc_ref_pos.p; cd.read_pos = ctx->dc_read_pos.p; cd.match_ref = ctx->dc_match_ref.p; cd.match_read = ctx->dc_match_read.p;
-    cd.rev = ctx->dc_rev.p;
-    int64_t cap = std::max<int64_t>((int64_t)ctx->d_ekeys.cap, n / 2 + 4 * ctx->c_n_blk + 2 * ctx->c_n_reads + 4096);
-    int64_t n_raw = 0;
-    CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1)); CK(ctx->d_sens.ensure(std::max<int64_t>(n, ctx->c_n_reads) + 1));
-    PHASE_BEGIN("depth_edges");
-    for (int attempt = 0; attempt < 2; attempt++) {
-        CK(ctx->d_ekeys.ensure(cap));
-        cap = (int64_t)ctx->d_ekeys.cap;
-        unsigned long long *d_cnt = (unsigned long long *)(ctx->d_counters.p + 9);
-        CK(cudaMemsetAsync(d_cnt, 0, sizeof(int64_t), ctx->stream));
-        EdgeSink sink{ctx->d_ekeys.p, cap, d_cnt};
-        int32_t *d_nsens = (int32_t *)(ctx->d_counters.p + 10), *d_left = (int32_t *)(ctx->d_counters.p + 11);
-        cub::CountingInputIterator<int32_t> cnt(0);
-        for (int stream_kind = 0; stream_kind < 2; stream_kind++) {  // 0: chimeric reads (RawEdgesChim), 1: concordant stream (RawEdgesOther)
-            const int64_t cnt_items = stream_kind == 0 ? cd.n_reads : n;
-            int32_t *res0 = stream_kind == 0 ? ctx->dc_res0.p : ctx->d_scratch32.p;
-            if (cnt_items <= 0) continue;
-            if (stream_kind == 0) LAUNCH(k_chim_edges, blocks_for(cnt_items), kThreads, cd, ctx->params, ctx->nt, res0, sink);
-            else { PHASE_BEGIN("k_conc_edges"); LAUNCH(k_conc_edges, blocks_for(cnt_items), kThreads, b, ctx->d_cls.p, ctx->params, ctx->nt, res0, sink); PHASE_END("k_conc_edges"); }
-            IsSensOp op{res0};
-            size_t tb = 0;
-            CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_sens.p, d_nsens, (int)cnt_items, op, ctx->stream));
-            ENSURE_TEMP(tb);
-            CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_sens.p, d_nsens, (int)cnt_items, op, ctx->stream));
-            ctx->launches += 2;
-            CK(cudaMemcpyAsync(ctx->h_counters.p + 10, ctx->d_counters.p + 10, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            const int32_t n_sens = *(int32_t *)(ctx->h_counters.p + 10);
-            ctx->n_sensitive = (stream_kind == 0 ? 0 : ctx->n_sensitive) + n_sens;
-            for (int round = 0; n_sens > 0; round++) {
-                if (round > n_sens + 1) FAIL(SQG_ECUDA, "hint fix-up did not converge");
-                CK(cudaMemsetAsync(d_left, 0, sizeof(int64_t), ctx->stream));
-                if (stream_kind == 0) LAUNCH(k_chim_fixup, blocks_for(n_sens, 64), 64, cd, ctx->params, ctx->nt, res0, ctx->d_sens.p, n_sens, sink, d_left);
-                else LAUNCH(k_conc_fixup, blocks_for(n_sens, 64), 64, b, ctx->params, ctx->nt, res0, ctx->d_sens.p, n_sens, sink, d_left);
-                CK(cudaMemcpyAsync(ctx->h_counters.p + 11, ctx->d_counters.p + 11, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                if (*(int32_t *)(ctx->h_counters.p + 11) == 0) break;
-            }
-        }
-        CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        n_raw = ctx->h_counters.p[9];
-        if (n_raw <= cap) break;
-        if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge buffer overflow");
-        cap = n_raw + 4096;  // rerun with room for everything (chimeric trims are idempotent)
+    if (!ctx->have_edge_table) {  // sqg_build_nodes computes the table eagerly; sqg_set_nodes invalidates it
+        rc = run_assign(ctx, false, true);
+        if (rc) return rc;
     }
-    ctx->n_raw_edges = n_raw;
-    PHASE_END("depth_edges");
-    PHASE_BEGIN("edge_sort");
-    rc = reduce_edges(ctx, n_raw, nullptr);
-    if (rc) return rc;
-    PHASE_END("edge_sort");
     if (chim_inout && ctx->c_n_blk > 0) {  // LocateRead trimmed Chimrecord in place (:1229-1248)
         const size_t nb = (size_t)ctx->c_n_blk;
         CK(cudaMemcpyAsync(chim_inout->blk_ref_pos, ctx->dc_ref_pos.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -16,6 +16,7 @@
 #include "sq_common.cuh"
 #include "sq_seed.cuh"
 #include "sq_phase1.cuh"
+#include "sq_phase2.cuh"
 #include "squid_b200.h"
 
 namespace sq {
@@ -168,7 +169,8 @@ struct sqg_ctx {
 
     // edges
     sq::DBuf<uint64_t> d_ekeys, d_ekeys2, d_ukeys;
-    sq::DBuf<int32_t> d_ecount, d_sens;
+    sq::DBuf<int32_t> d_ecount, d_sens, d_head, d_ew;
+    sq::DBuf<sq::DepthTile> d_dtile;
     sq::DBuf<int32_t> d_e_ind1, d_e_ind2, d_e_w;
     sq::DBuf<uint8_t> d_e_heads;
     int64_t n_unique_edges = 0;

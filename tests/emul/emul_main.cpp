@@ -277,6 +277,14 @@ int main(int argc, char **argv) {
             if (rv.nF + rv.nS == 0) continue;
             std::vector<uint64_t> tmp;
             EdgeVec e2{&tmp};
+            const int n_own = is_first ? rv.nF : rv.nS, n_mate = is_first ? rv.nS : rv.nF;
+            if (mode == MODE_OTHER && n_own <= 1 && !getenv("SQ_EMUL_NO_FAST_EDGES")) {  // the register fast path of the stream kernel
+                const Blk own = n_own ? (is_first ? rv.F[0] : rv.S[0]) : Blk{}, mate = n_mate ? (is_first ? rv.S[0] : rv.F[0]) : Blk{};
+                const int32_t r0 = read_edges_single(nt, p, n_own > 0, own, n_mate > 0, mate, is_first, is_first ? rv.first_total : rv.second_total, e2);
+                if (r0 != -3) { keys.insert(keys.end(), tmp.begin(), tmp.end()); res0[i] = r0; }
+                else sens[i] = 1;
+                continue;
+            }
             if (read_edges(nt, p, rv, mode, is_first, false, 0, node, e2)) {
                 keys.insert(keys.end(), tmp.begin(), tmp.end());
                 res0[i] = node[0];

@@ -36,6 +36,7 @@ def test_stepped_rules_match_golden(case, one_island, bin_shift, chunks, emul_bi
     env["SQ_EMUL_BIN_SHIFT"] = str(bin_shift)  # segment-table position index: 0 = plain binary searches, 4 = many tiny bins
     if one_island:
         env["SQ_EMUL_ONE_ISLAND"] = "1"
+        env["SQ_EMUL_NO_FAST_EDGES"] = "1"  # this variant runs every read through the generic read_edges
     r = subprocess.run([emul_bin, os.path.join(GOLD, case, "conc.sqmb"), os.path.join(GOLD, case, "chim.sqmb"), str(tmp_path), str(tmp_path / "bps.bin")],
                        capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
