@@ -55,6 +55,13 @@ SQ_HD int32_t locate_block(const NodeTable &nt, const Blk &b, Cursor &cur, bool 
         return -1;
     }
     const int32_t c0 = nt.chr_first[c], c1 = nt.chr_first[c + 1];
+    if (!cur.known && c1 > c0 && b.match_ref > kLocateTol) {
+        // the common case in closed form: the block lies inside the segment s that holds its start, clear of both ends
+        // by more than the tolerance.  Then s is the only segment it fits (lo == hi == s below) and no scan can miss it.
+        const int32_t s = seg_at(nt, c, c0, c1, b.ref_pos);
+        const int32_t q = nt.pos[s], e = nt.end[s];
+        if (q <= b.ref_pos && b.ref_pos + kLocateTol < e && b.ref_pos + b.match_ref - kLocateTol <= e) { cur.known = true; cur.idx = s; return s; }
+    }
     // segments that fit: lo = first with End >= p+m-5, hi = last with Position <= p+5
     const int32_t lo = seg_first_end_ge(nt, c, c0, c1, b.ref_pos + b.match_ref - kLocateTol);
     const int32_t hi = seg_last_pos_le(nt, c, c0, c1, b.ref_pos + kLocateTol);

@@ -13,6 +13,7 @@
 #define SQ_PHASE2_CUH
 #include "sq_depth_cover.cuh"
 #include "sq_locate.cuh"
+#include "sq_phase1.cuh"
 #include "sq_stream.cuh"
 
 namespace sq {
@@ -60,6 +61,7 @@ struct P2Args {
     int32_t *res0;
     PairSink sink;
     int32_t *sens; int32_t *n_sens; int32_t sens_cap;
+    const BatchDesc *desc; const NodeTable *nt_dev;  // device copies for the out-of-line generic path
 };
 
 constexpr uint32_t kP2Fields = F_REF | F_MREF | F_MPOS | F_FLAG | F_TLEN | F_LOWQ | F_CLS | F_BLOCKS;
@@ -77,6 +79,22 @@ __device__ __forceinline__ void depth_add(int32_t seg, int32_t len, bool on, int
     }
 }
 
+// RawEdgesOther for a record with several aligned blocks: the generic rules, read straight from HBM (the tile's bytes are
+// still in L2) and kept out of line so that the hot single-block path stays small.  Returns the res0 code.
+__device__ __noinline__ int32_t conc_edges_generic(const BatchDesc *desc, const NodeTable *ntp, int64_t r, TileEdgeTable *edges) {
+    const DevBatch &b = desc->b;
+    const Params &p = desc->p;
+    const NodeTable nt = *ntp;
+    if (!conc_builds_edges(b, p, r)) return -2;
+    Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
+    int32_t node[2 * kMaxBlocks + 2];
+    ReadView rv; rv.F = F; rv.S = S;
+    bool is_first;
+    conc_load_read(b, r, rv, is_first);
+    if (rv.nF + rv.nS == 0) return -2;
+    return read_edges(nt, p, rv, MODE_OTHER, is_first, false, 0, node, *edges) ? node[0] : -3;
+}
+
 __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2Args a, int bulk_ok) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileStage &s = *reinterpret_cast<TileStage *>(smem_raw);
@@ -84,8 +102,9 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     __shared__ int32_t s_dcnt[2][kDepthWin], s_dsum[2][kDepthWin];
     __shared__ uint16_t s_slow[kTile];
     __shared__ int32_t s_cmax[kTileChunks];
-    __shared__ int32_t s_nslow, s_base, s_other, s_first;
+    __shared__ int32_t s_nslow, s_base, s_other, s_first, s_seg[4];
     int32_t *s_m = s.end_pos;   // per record: depth target of its first block (-1: not counted)
+    uint8_t *s_cont = s.mapq;   // per record: first block contained in that target
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
     const int64_t tile = blockIdx.x;
@@ -99,19 +118,29 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     stage_wait<kP2Fields>(s, b, a.cls, tk);
     const bool staged = ti.nb >= 0;
     const TileBatch tb = tile_view(s, ti, b);
-    if (tid == 0 && a.do_depth) {  // window of segments counted in shared memory: starts one segment left of the tile's first block
+    if (tid == 0) {
+        // The segment that holds the tile's first block: sorted input keeps most of the tile (usually all of it) inside this
+        // one segment, so it is looked up once and every block of the tile is first tested against it.  The window of
+        // segments counted in shared memory starts one segment to its left.
+        s_seg[0] = -1; s_seg[1] = 0; s_seg[2] = 0; s_seg[3] = 0;
         for (int i = 0; i < n; i++) {
             const uint32_t o0 = s.blk_off[i];
             if (s.blk_off[i + 1] > o0 && s.ref_id[i] >= 0 && s.ref_id[i] < a.nt.n_ref) {
                 const int32_t c = s.ref_id[i], c0 = a.nt.chr_first[c], c1 = a.nt.chr_first[c + 1];
                 const int32_t st = staged ? tb.blk_ref_pos[o0] : b.blk_ref_pos[o0];
-                if (c1 > c0) s_base = seg_at(a.nt, c, c0, c1, st) - 1;
+                if (c1 > c0) {
+                    const int32_t sg = seg_at(a.nt, c, c0, c1, st);
+                    s_base = sg - 1;
+                    s_seg[0] = c; s_seg[1] = sg; s_seg[2] = a.nt.pos[sg]; s_seg[3] = a.nt.end[sg];
+                }
                 break;
             }
         }
     }
     __syncthreads();
     const int32_t base = s_base;
+    const int32_t wc = s_seg[0], ws = s_seg[1], wq = s_seg[2], we = s_seg[3];  // wc == -1: no such segment
+    const NodeTable &nt = a.nt;
 
     // ---- pass A: depth targets + ReadsOther; edges of the single-block records ------------------------------------
 #pragma unroll 1
@@ -127,9 +156,11 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
         if (a.do_depth) {
             const bool counted = in && r < a.r_break && (c8 & CLS_HASBLK);
             int32_t st0 = 0, l0 = 0;
+            bool cont = false;
             if (counted) {
                 st0 = staged ? tb.blk_ref_pos[o0] : b.blk_ref_pos[o0]; l0 = staged ? tb.blk_match_ref[o0] : b.blk_match_ref[o0];
-                m = depth_target(a.nt, rid, st0, l0);
+                if (rid == wc && wq <= st0 && st0 < we && l0 > kSeedThresh) { m = ws; cont = st0 + l0 <= we + kSeedThresh; }  // depth_target / depth_contained in the tile's segment
+                else { m = depth_target(nt, rid, st0, l0); cont = m != kNoNode && depth_contained(nt, m, rid, st0, l0); }
                 if (nb > 1) s_other = 1;
             }
             const uint32_t nb_max = __reduce_max_sync(full, counted ? nb : 0u);
@@ -139,12 +170,16 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
                 if (counted && k < nb) {
                     const int32_t st = staged ? tb.blk_ref_pos[o0 + k] : b.blk_ref_pos[o0 + k];
                     l = staged ? tb.blk_match_ref[o0 + k] : b.blk_match_ref[o0 + k];
-                    m2 = depth_target(a.nt, rid, st, l);
-                    on = m2 != kNoNode && depth_contained(a.nt, m2, rid, st, l);
+                    if (rid == wc && wq <= st && st < we && l > kSeedThresh) { m2 = ws; on = st + l <= we + kSeedThresh; }
+                    else { m2 = depth_target(nt, rid, st, l); on = m2 != kNoNode && depth_contained(nt, m2, rid, st, l); }
                 }
                 depth_add(m2, l, on, base, s_dcnt[1], s_dsum[1], a.cnt_other, a.sum_other);
             }
-            if (in) s_m[i] = m;
+            if (in) {
+                s_m[i] = m;
+                // is the block contained (+-3) in its own target?  (pass B only looks again when the cursor is elsewhere)
+                s_cont[i] = cont ? 1 : 0;
+            }
             const int32_t cm = __reduce_max_sync(full, m);
             const unsigned vm = __ballot_sync(full, m >= 0);
             if (lane == 0) {
@@ -166,8 +201,12 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
                         own.ref_pos = tb.blk_ref_pos[o0]; own.match_ref = tb.blk_match_ref[o0]; own.read_pos = tb.blk_read_pos[o0]; own.match_read = tb.blk_match_read[o0];
                         if (has_mate) builds = own.read_pos <= 15 || (int32_t)s.lowphred_run[i] > a.p.max_lowphred_len;
                     }
-                    if (builds && (nb == 1 || has_mate))
-                        out = read_edges_single(a.nt, a.p, nb == 1, own, has_mate, mate_block_of(f, s.mate_ref_id[i], s.mate_pos[i]), flag_first(f), (int32_t)s.total_len[i], s_edges);
+                    // both blocks well inside the tile's segment: each locates there whatever the scan order, nothing to emit
+                    const bool own_in = nb == 0 || (rid == wc && own.match_ref > kLocateTol && wq <= own.ref_pos && own.ref_pos + kLocateTol < we && own.ref_pos + own.match_ref - kLocateTol <= we);
+                    const bool mate_in = !has_mate || (s.mate_ref_id[i] == wc && wq <= s.mate_pos[i] && s.mate_pos[i] + kLocateTol < we && s.mate_pos[i] + kMateBlockLen - kLocateTol <= we);
+                    if (builds && (nb == 1 || has_mate) && own_in && mate_in) out = ws;
+                    else if (builds && (nb == 1 || has_mate))
+                        out = read_edges_single(nt, a.p, nb == 1, own, has_mate, mate_block_of(f, s.mate_ref_id[i], s.mate_pos[i]), flag_first(f), (int32_t)s.total_len[i], s_edges);
                 } else {
                     out = -4;  // generic path below
                     s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)i;
@@ -187,15 +226,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
         for (int q = tid; q < ns; q += kTileThreads) {
             const int i = s_slow[q];
             const int64_t r = rec0 + i;
-            int32_t out = -2;
-            if (staged ? conc_builds_edges(tb, a.p, r) : conc_builds_edges(b, a.p, r)) {
-                Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
-                int32_t node[2 * kMaxBlocks + 2];
-                ReadView rv; rv.F = F; rv.S = S;
-                bool is_first;
-                if (staged) conc_load_read(tb, r, rv, is_first); else conc_load_read(b, r, rv, is_first);
-                if (rv.nF + rv.nS > 0) out = read_edges(a.nt, a.p, rv, MODE_OTHER, is_first, false, 0, node, s_edges) ? node[0] : -3;
-            }
+            const int32_t out = conc_edges_generic(a.desc, a.nt_dev, r, &s_edges);
             a.res0[r] = out;
             if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
         }
@@ -228,11 +259,11 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
             if (e > v) v = e;  // cursor at this read: running maximum of the targets so far in the tile
             bool on = false;
             int32_t l0 = 0;
-            if (m >= 0 && v != kNoNode && v < a.nt.n) {
+            if (m >= 0 && v != kNoNode && v < nt.n) {
                 const uint32_t o0 = s.blk_off[i];
-                const int32_t st0 = staged ? tb.blk_ref_pos[o0] : b.blk_ref_pos[o0];
                 l0 = staged ? tb.blk_match_ref[o0] : b.blk_match_ref[o0];
-                on = depth_contained(a.nt, v, s.ref_id[i], st0, l0);
+                if (v == m) on = s_cont[i] != 0;
+                else on = depth_contained(nt, v, s.ref_id[i], staged ? tb.blk_ref_pos[o0] : b.blk_ref_pos[o0], l0);
             }
             depth_add(v, l0, on, base, s_dcnt[0], s_dsum[0], a.cnt_main, a.sum_main);
         }

@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -887,6 +888,13 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             a.other_nonempty = do_depth ? ctx->d_cnt3.p + 3 * (size_t)N : nullptr;
             a.dtile = ctx->d_dtile.p; a.res0 = ctx->d_scratch32.p; a.sink = sink;
             a.sens = ctx->d_sens.p; a.n_sens = d_nsens; a.sens_cap = conc_sens_cap;
+            {
+                struct { BatchDesc d; NodeTable nt; } hd;
+                hd.d.b = b; hd.d.p = ctx->params; hd.nt = ctx->nt;
+                CK(ctx->d_desc.ensure(sizeof(hd)));
+                CK(cudaMemcpyAsync(ctx->d_desc.p, &hd, sizeof(hd), cudaMemcpyHostToDevice, ctx->stream));
+                a.desc = (const BatchDesc *)ctx->d_desc.p; a.nt_dev = (const NodeTable *)(ctx->d_desc.p + offsetof(decltype(hd), nt));
+            }
             CK(cudaFuncSetAttribute(k_assign_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
             PHASE_BEGIN("k_assign");
             k_assign_tiles<<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
