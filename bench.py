@@ -268,7 +268,7 @@ def main():
         phases = {}
         for _ in range(steps):
             step(resident)
-            for ph in ("h2d", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_cov_count"):
+            for ph in ("h2d", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_cov_compact", "k_cov_count"):
                 v = g.phase_ms(ph)
                 if v >= 0:
                     phases[ph] = phases.get(ph, 0.0) + v / steps
@@ -290,8 +290,8 @@ def main():
     K = NB / R
     # algorithmic bytes per launch of the stream kernels: phase 1 and phase 2 read the whole batch
     # (32 B/record + 12 B/block), phase 3 the 24-byte subset of the qualifying half
-    alg = {"k_classify": 32 * R + 12 * NB, "k_assign": 32 * R + 12 * NB, "k_cov_count": 24 * R}
-    traffic = {"k_classify": None, "k_assign": None, "k_cov_count": 13.7}  # ncu dram bytes per record (profiles/)
+    alg = {"k_classify": 32 * R + 12 * NB, "k_assign": 32 * R + 12 * NB, "k_cov_compact": 24 * R}
+    traffic = {"k_classify": None, "k_assign": None, "k_cov_compact": None}  # ncu dram bytes per record (profiles/)
     peak, peak_src = measured_peak_gbs()
     stream = {k: v for k, v in phases.items() if k in alg}
     top = max(stream, key=stream.get) if stream else None

@@ -132,7 +132,7 @@ void sort_like_std(SortKey *first, SortKey *last, int threads) {
     for (size_t n = (size_t)(last - first); n > 1; n >>= 1) lg++;
     struct Range { SortKey *a, *b; int depth; };
     const int T = std::max(1, std::min(threads, 32));
-    const ptrdiff_t kBig = 1 << 15;  // ranges above this are partitioned by all threads together
+    const ptrdiff_t kBig = 1 << 14;  // ranges above this are partitioned by all threads together
     std::vector<Range> big, small;
     big.push_back(Range{first, last, 2 * lg});
     std::vector<uint32_t> Lg, Rg;
@@ -146,7 +146,9 @@ void sort_like_std(SortKey *first, SortKey *last, int threads) {
         big.push_back(Range{cut, r.b, r.depth - 1});
     }
     // the remaining partitions: sequential introsort loop + their share of the final insertion sort, one task each
-#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
+    // (no barriers inside: this loop may use every core even while the caller's thread spins on the GPU)
+    std::sort(small.begin(), small.end(), [](const Range &x, const Range &y) { return x.b - x.a > y.b - y.a; });  // largest first
+#pragma omp parallel for num_threads(std::min(2 * T, 32)) schedule(dynamic, 1)
     for (long long i = 0; i < (long long)small.size(); i++) {
         sort_loop(small[(size_t)i].a, small[(size_t)i].b, small[(size_t)i].depth);
         insertion_sort(small[(size_t)i].a, small[(size_t)i].b);
@@ -291,12 +293,62 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     }
     const int32_t n = (int32_t)dis.size();
     out.disc[dis.size()] = sq::DiscBlock{0, 0, 0, 0};  // what *cend() reads
-    for (int32_t s = 0; s < n;) {  // :341-348 chain while the next block starts within ReadLen of the running right end
-        int32_t right = out.disc[s].pos + out.disc[s].len, e = s;
-        for (; e < n && out.disc[e].chr == out.disc[s].chr && out.disc[e].pos < right + read_len; e++)
-            right = std::max(right, out.disc[e].pos + out.disc[e].len);
-        out.groups.push_back(sq::Group{s, e, out.disc[s].chr, right});
-        s = e;
+    // :341-348 chain while the next block starts within ReadLen of the running right end.  In sorted order the running right
+    // end of a group equals the maximum end over ALL earlier blocks of the chromosome (the previous group ended more than
+    // ReadLen left of this one), so block e opens a group iff it is the first of its chromosome or starts at/after that
+    // prefix maximum + ReadLen: a prefix maximum per chunk of blocks, chunks in parallel.
+    {
+        int TG = n > (1 << 16) ? std::min(cores, 16) : 1;
+        if (getenv("SQH_PREPASS_CHUNKS")) TG = std::max(1, std::min(n, atoi(getenv("SQH_PREPASS_CHUNKS"))));  // test hook
+        struct Tail { int32_t chr, mx; bool any; };
+        std::vector<Tail> tail((size_t)TG);
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> brk((size_t)TG);  // (block index that opens a group, right end of the group before it)
+#pragma omp parallel num_threads(TG)
+        {
+            const int t = omp_get_thread_num();
+            const int32_t a = (int32_t)((int64_t)n * t / TG), b = (int32_t)((int64_t)n * (t + 1) / TG);
+            Tail tl{-1, 0, false};  // last chromosome of the chunk and the maximum end seen on it inside the chunk
+            for (int32_t e = a; e < b; e++) {
+                const sq::DiscBlock &d = out.disc[(size_t)e];
+                if (!tl.any || d.chr != tl.chr) { tl.chr = d.chr; tl.mx = d.pos + d.len; tl.any = true; }
+                else tl.mx = std::max(tl.mx, d.pos + d.len);
+            }
+            tail[(size_t)t] = tl;
+#pragma omp barrier
+            // carry into this chunk: maximum end over the earlier chunks on the chromosome they end with
+            int32_t cchr = -1, cmx = 0;
+            bool cany = false;
+            for (int q = 0; q < t; q++) {
+                const Tail &x = tail[(size_t)q];
+                if (!x.any) continue;
+                if (cany && x.chr == cchr) {
+                    // the chunk may hold earlier chromosomes too; its tail maximum is about its LAST chromosome only, which
+                    // equals cchr here, so the maxima combine
+                    cmx = std::max(cmx, x.mx);
+                    // ... unless the chunk changed chromosome and came back (impossible in sorted order)
+                } else { cchr = x.chr; cmx = x.mx; cany = true; }
+            }
+            int32_t rchr = cchr, rmx = cmx;
+            bool rany = cany;
+            for (int32_t e = a; e < b; e++) {
+                const sq::DiscBlock &d = out.disc[(size_t)e];
+                const bool opens = !rany || d.chr != rchr || d.pos >= rmx + read_len;
+                if (opens) brk[(size_t)t].push_back({e, rany ? rmx : 0});
+                if (!rany || d.chr != rchr) { rchr = d.chr; rmx = d.pos + d.len; rany = true; }
+                else rmx = std::max(rmx, d.pos + d.len);
+            }
+            if (t == TG - 1) tail[(size_t)t] = Tail{rchr, rmx, rany};  // the true running state at the end of the list
+        }
+        size_t ng = 0;
+        for (auto &v : brk) ng += v.size();
+        out.groups.reserve(ng);
+        int32_t prev_start = -1;
+        for (auto &v : brk)
+            for (auto &pr : v) {
+                if (prev_start >= 0) out.groups.push_back(sq::Group{prev_start, pr.first, out.disc[(size_t)prev_start].chr, pr.second});
+                prev_start = pr.first;
+            }
+        if (prev_start >= 0) out.groups.push_back(sq::Group{prev_start, n, out.disc[(size_t)prev_start].chr, tail[(size_t)TG - 1].mx});
     }
     lap("groups");
 }

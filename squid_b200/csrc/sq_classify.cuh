@@ -96,6 +96,7 @@ SQ_HD ClassifyOut classify_record(const B &b, const Params &p, int64_t r, int64_
     o.first_len = b.blk_match_ref[off];
     const bool fm = flag_first(f), sm = flag_second(f);
     if (fm || sm) {
+        if (nb > 1) o.cls |= CLS_REST;
         o.other_key = ((uint64_t)(uint32_t)(rid + 1) << 32) | (uint32_t)(b.blk_ref_pos[off] + b.blk_match_ref[off]);
         // partial alignment: > 15 unaligned bases at either end of the read and no low-phred run (:668-683)
         const bool low = (int32_t)b.lowphred_run[r] > p.max_lowphred_len;

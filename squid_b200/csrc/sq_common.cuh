@@ -29,6 +29,7 @@ enum : uint8_t {
     CLS_PART = 8,      // CLS_CONC and partially aligned (:668-683) => PartialAlignCluster, else ConcordantCluster
     CLS_HASBLK = 16,   // kept and owns >= 1 block (feeds ReadsMain, :320-333)
     CLS_DISPL = 32,    // CLS_HASBLK and the first kept block does not start at the record position (leading block dropped)
+    CLS_REST = 64,     // CLS_CONC with a mate flag and >= 2 blocks: its later blocks feed ConcordRest (:690-699)
 };
 
 // HBM-resident SoA batch (include/squid_b200.h: sqg_batch), device pointers.

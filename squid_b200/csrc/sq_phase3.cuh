@@ -1,0 +1,181 @@
+// Phase 3 of the path: concordant fragments covering each breakpoint (the BAM pass of ExactBPConcordantSupport,
+// SegmentGraph.cpp:3124-3166), two passes:
+//   k_cov_compact : ONE pass over the record fields the rule needs (23 B/record): the qualifying records -- right-hand
+//                   mates that pass the gate (:3136-3142) -- are compacted in stream order into (fragment start key,
+//                   fragment end) pairs.  Rank offsets and the running maximum of the start keys cross tiles through one
+//                   decoupled look-back chain; both are kept per tile, which is all the indBP threshold search needs.
+//   k_cov_count   : one pass over the compacted pairs (12 B each).  A block first intersects the position range of its
+//                   fragments with the sorted breakpoint list; most blocks see no breakpoint at all and stop there, the
+//                   others count against the few breakpoints in range from shared memory.
+#ifndef SQ_PHASE3_CUH
+#define SQ_PHASE3_CUH
+#include "sq_depth_cover.cuh"
+#include "sq_stream.cuh"
+
+namespace sq {
+
+struct CovTile {
+    int64_t rank0;       // qualifying records before the tile
+    uint64_t incmax;     // running maximum of the start keys up to and including the tile
+};
+
+constexpr int kCovTile = 2048, kCovThreads = 256, kCovRPT = kCovTile / kCovThreads, kCovWarps = kCovThreads / 32, kCovChunks = kCovTile / 32;
+__global__ void __launch_bounds__(kCovThreads) k_cov_compact(DevBatch b, const uint8_t *cls, Chain chain, int32_t *ticket, int32_t n_tiles,
+                                                              uint64_t *qkey, int32_t *qend, CovTile *tiles, int64_t *nq_out) {
+    __shared__ int s_tile;
+    __shared__ int32_t s_cnt[kCovChunks];
+    __shared__ unsigned long long s_max[kCovWarps];
+    __shared__ long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int64_t rec0 = (int64_t)tile * kCovTile;
+    uint64_t key[kCovRPT]; int32_t endp[kCovRPT]; unsigned qm[kCovRPT];
+    uint64_t mx = 0;
+#pragma unroll
+    for (int j = 0; j < kCovRPT; j++) {
+        const int64_t r = rec0 + j * kCovThreads + tid;
+        bool q = false;
+        key[j] = 0; endp[j] = 0;
+        if (r < b.n_rec) {
+            const uint16_t f = b.flag[r];
+            const int32_t rid = b.ref_id[r], pos = b.pos[r], mrid = b.mate_ref_id[r], mpos = b.mate_pos[r];
+            q = cover_qualifies(cls[r], f, rid, pos, mrid, mpos);
+            if (q) { key[j] = chrpos_key(rid, cover_start(f, rid, pos, mrid, mpos)); endp[j] = b.end_pos[r]; if (key[j] > mx) mx = key[j]; }
+        }
+        qm[j] = __ballot_sync(full, q);
+        if (lane == 0) s_cnt[j * kCovWarps + warp] = __popc(qm[j]);
+    }
+    mx = warp_max_u64(mx);
+    if (lane == 0) s_max[warp] = mx;
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the kCovChunks (= 64) chunk counts: two consecutive chunks per lane
+        const int32_t v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1];
+        int32_t inc = v0 + v1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(full, inc, d); if (lane >= d) inc += u; }
+        const int32_t tot = __shfl_sync(full, inc, 31);
+        s_cnt[2 * lane] = inc - v0 - v1; s_cnt[2 * lane + 1] = inc - v1;
+        uint64_t tm = 0;
+#pragma unroll
+        for (int k = 0; k < kCovWarps; k++) if (s_max[k] > tm) tm = s_max[k];
+        uint64_t xa, xb;
+        chain_scan(chain, tile, tm, (uint64_t)(uint32_t)tot, &xa, &xb);
+        if (lane == 0) {
+            s_base = (long long)xb;
+            CovTile t; t.rank0 = (int64_t)xb; t.incmax = xa > tm ? xa : tm;
+            tiles[tile] = t;
+            if (tile == n_tiles - 1) *nq_out = (int64_t)xb + tot;
+        }
+    }
+    __syncthreads();
+    const int64_t base = s_base;
+#pragma unroll
+    for (int j = 0; j < kCovRPT; j++)
+        if (qm[j] & (1u << lane)) {
+            const int64_t at = base + s_cnt[j * kCovWarps + warp] + __popc(qm[j] & ((1u << lane) - 1u));
+            qkey[at] = key[j]; qend[at] = endp[j];
+        }
+}
+
+// r0[k] = first qualifying rank whose running-maximum start key exceeds (chr, pos + dist) of breakpoint k (nq if none);
+// also the breakpoint keys and the max-plus form t[k] = r0[k] - k.
+__global__ void k_cov_r0_tiles(const uint64_t *qkey, const CovTile *tiles, int32_t n_tiles, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K,
+                               int32_t dist, uint64_t *bpkey, int64_t *r0, int64_t *t) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    bpkey[k] = chrpos_key(bp_chr[k], bp_pos[k]);
+    const uint64_t T = chrpos_key(bp_chr[k], bp_pos[k] + dist);
+    int32_t lo = 0, hi = n_tiles;  // first tile whose inclusive maximum exceeds T
+    while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (tiles[m].incmax <= T) lo = m + 1; else hi = m; }
+    int64_t v = nq;
+    if (lo < n_tiles) {
+        uint64_t run = lo > 0 ? tiles[lo - 1].incmax : 0ull;
+        const int64_t a = tiles[lo].rank0, e = lo + 1 < n_tiles ? tiles[lo + 1].rank0 : nq;
+        for (int64_t i = a; i < e; i++) { const uint64_t q = qkey[i]; if (q > run) run = q; if (run > T) { v = i; break; } }
+    }
+    r0[k] = v;
+    t[k] = v - k;
+}
+
+constexpr int kCovRanks = 1024;   // ranks per block of k_cov_count
+constexpr int kCovWin = 256;      // breakpoints a block counts in shared memory
+__global__ void __launch_bounds__(256) k_cov_count_tiles(const uint64_t *qkey, const int32_t *qend, int64_t nq, const uint64_t *bpkey, const int64_t *t, int64_t K, int32_t *cov) {
+    __shared__ unsigned long long s_lo[8], s_hi[8];
+    __shared__ unsigned long long s_bp[kCovWin];
+    __shared__ long long s_t[kCovWin];
+    __shared__ int32_t s_c[kCovWin];
+    __shared__ long long s_ka, s_kb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    const int64_t i0 = (int64_t)blockIdx.x * kCovRanks;
+    uint64_t ks[4], ke[4];
+    uint64_t mn = ~0ull, mxe = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int64_t i = i0 + j * 256 + tid;
+        ks[j] = ~0ull; ke[j] = 0;
+        if (i < nq) {
+            ks[j] = qkey[i];
+            ke[j] = (ks[j] & 0xffffffff00000000ull) | (uint32_t)qend[i];
+            if (ks[j] < mn) mn = ks[j];
+            if (ke[j] > mxe) mxe = ke[j];
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const uint64_t o = __shfl_xor_sync(full, mn, d); if (o < mn) mn = o; }
+    mxe = warp_max_u64(mxe);
+    if (lane == 0) { s_lo[warp] = mn; s_hi[warp] = mxe; }
+    __syncthreads();
+    if (warp < 2) {  // warp 0: first breakpoint at/after the leftmost fragment start; warp 1: ... the rightmost fragment end
+        uint64_t a = ~0ull, e = 0;
+        for (int w = 0; w < 8; w++) { if (s_lo[w] < a) a = s_lo[w]; if (s_hi[w] > e) e = s_hi[w]; }
+        const uint64_t v = warp == 0 ? a : e;
+        int64_t lo = 0, hi = K;  // 32-way search: 4 dependent probes instead of 18
+        while (hi - lo > 0) {
+            const int64_t step = (hi - lo + 32) / 33;
+            const int64_t p = lo + (int64_t)(lane + 1) * step - 1;  // probes lo+step-1, lo+2step-1, ...
+            const bool less = p < hi && bpkey[p] < v;
+            const unsigned m = __ballot_sync(full, less);
+            const int c = __popc(m);  // probes below v form a prefix
+            const int64_t nlo = lo + (int64_t)c * step;
+            const int64_t nhi = c < 32 ? (lo + (int64_t)(c + 1) * step - 1 < hi ? lo + (int64_t)(c + 1) * step - 1 : hi) : hi;
+            lo = nlo < hi ? nlo : hi; hi = nhi;
+        }
+        if (lane == 0) { if (warp == 0) s_ka = lo; else s_kb = lo; }
+    }
+    __syncthreads();
+    const int64_t ka = s_ka, kb = s_kb;
+    if (ka >= kb) return;  // no breakpoint under any fragment of the block
+    if (kb - ka <= kCovWin) {
+        const int nw = (int)(kb - ka);
+        for (int w = tid; w < nw; w += 256) { s_bp[w] = bpkey[ka + w]; s_t[w] = t[ka + w]; s_c[w] = 0; }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t i = i0 + j * 256 + tid;
+            for (int w = 0; w < nw; w++) {
+                const unsigned long long bp = s_bp[w];
+                const bool hit = ks[j] <= bp && bp < ke[j] && i < s_t[w];
+                const unsigned m = __ballot_sync(full, hit);
+                if (lane == 0 && m) atomicAdd(&s_c[w], __popc(m));
+            }
+        }
+        __syncthreads();
+        for (int w = tid; w < nw; w += 256) if (s_c[w]) atomicAdd(&cov[ka + w], s_c[w]);
+    } else {  // a very dense breakpoint region: every fragment searches the list itself
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t i = i0 + j * 256 + tid;
+            if (i >= nq) continue;
+            for (int64_t k = lower_bound_u64(bpkey, ka, kb, ks[j]); k < kb && bpkey[k] < ke[j]; k++)
+                if (i < t[k]) atomicAdd(&cov[k], 1);
+        }
+    }
+}
+
+}  // namespace sq
+#endif

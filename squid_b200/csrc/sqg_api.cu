@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@
 #include "sq_locate.cuh"
 #include "sq_phase1.cuh"
 #include "sq_phase2.cuh"
+#include "sq_phase3.cuh"
 #include "sq_seed.cuh"
 #include "sqg_ctx.cuh"
 
@@ -42,6 +44,16 @@ using namespace sq;
         CK(cudaGetLastError());                                                                    \
     } while (0)
 
+struct HostLap {  // SQG_TIMING=1: wall-clock laps of the host side of a call, to stderr
+    bool on; std::chrono::steady_clock::time_point t0;
+    HostLap() : on(getenv("SQG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void operator()(const char *what) {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sqg] %-28s %8.3f ms\n", what, 1e3 * std::chrono::duration<double>(t - t0).count());
+        t0 = t;
+    }
+};
 static constexpr int kThreads = 256;
 static inline unsigned blocks_for(int64_t n, int threads = kThreads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
@@ -93,9 +105,8 @@ __global__ void k_rest_collect(DevBatch b, const uint8_t *cls, const Group *G, c
                                RestBlock *out, uint64_t *out_key, int64_t cap, int64_t *counter) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= b.n_rec) return;
-    if (!(cls[r] & CLS_CONC) || !(b.flag[r] & 0xC0)) return;
+    if (!(cls[r] & CLS_REST)) return;  // CLS_CONC, a mate flag, >= 2 blocks
     const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
-    if (e - o < 2) return;
     const int32_t c = b.ref_id[r];
     for (uint32_t k = o + 1; k < e; k++) {
         const int32_t q = b.blk_ref_pos[k];
@@ -530,7 +541,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
-    ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
+    ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
     ctx->h_chr.release(); ctx->h_pos.release(); ctx->h_len.release(); ctx->h_cnt3.release(); ctx->h_sum3.release(); ctx->h_ind1.release(); ctx->h_ind2.release();
@@ -596,7 +607,7 @@ extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t fi
     b.blk_off = ctx->o_blk_off.p; b.blk_ref_pos = ctx->o_blk_ref_pos.p; b.blk_match_ref = ctx->o_blk_match_ref.p;
     b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
     PHASE_END("h2d");
-    ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
+    ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
     return SQG_OK;
 }
 
@@ -609,7 +620,7 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     b.ref_id = db->ref_id; b.pos = db->pos; b.mate_ref_id = db->mate_ref_id; b.mate_pos = db->mate_pos; b.end_pos = db->end_pos;
     b.flag = db->flag; b.total_len = db->total_len; b.lowphred_run = db->lowphred_run; b.mapq = db->mapq; b.aux = db->aux;
     b.blk_off = db->blk_off; b.blk_ref_pos = db->blk_ref_pos; b.blk_match_ref = db->blk_match_ref; b.blk_read_pos = db->blk_read_pos; b.blk_match_read = db->blk_match_read;
-    ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
+    ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
     return SQG_OK;
 }
 
@@ -837,6 +848,30 @@ static int tile_genome(sqg_ctx *ctx, std::vector<SeedNode> &seedv) {
     return install_nodes(ctx);
 }
 
+// Phase 3, first pass (sq_phase3.cuh: k_cov_compact): enqueued as soon as the class bytes exist -- it does not depend on the
+// segment table, so sqg_build_nodes runs it while the host still waits for the chimeric pre-pass.  The count lands in
+// h_counters[15] once the stream has been synchronised.
+static int run_cov_compact(sqg_ctx *ctx) {
+    if (ctx->cov_compacted) return SQG_OK;
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec;
+    const int64_t n_tiles = (n + kCovTile - 1) / kCovTile;
+    if (n > 0) {
+        Chain ch[1];
+        int32_t *ticket = nullptr;
+        int rc = prepare_chains(ctx, 1, n_tiles, ch, &ticket);
+        if (rc) return rc;
+        CK(ctx->d_qkey.ensure(n + 1)); CK(ctx->d_qend.ensure(n + 1)); CK(ctx->d_covtile.ensure(n_tiles + 1));
+        CK(cudaMemsetAsync(ctx->d_counters.p + 15, 0, sizeof(int64_t), ctx->stream));
+        PHASE_BEGIN("k_cov_compact");
+        LAUNCH(k_cov_compact, (unsigned)n_tiles, kCovThreads, b, ctx->d_cls.p, ch[0], ticket, (int32_t)n_tiles, ctx->d_qkey.p, ctx->d_qend.p, ctx->d_covtile.p, ctx->d_counters.p + 15);
+        PHASE_END("k_cov_compact");
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 15, ctx->d_counters.p + 15, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    } else { CK(ctx->d_qkey.ensure(1)); CK(ctx->d_qend.ensure(1)); CK(ctx->d_covtile.ensure(1)); }
+    ctx->cov_compacted = true;
+    return SQG_OK;
+}
+
 static int reduce_edges(sqg_ctx *ctx, int64_t n_raw, const int32_t *d_weights_in);
 
 // Phase 2 (sq_phase2.cuh): one pass over the batch for the depth numerators (do_depth) and the raw edges of the chimeric
@@ -938,10 +973,15 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     CK(cudaSetDevice(ctx->device));
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
+    HostLap lap;
     int rc = run_classify(ctx);
+    if (rc) return rc;
+    lap("classify");
+    rc = run_cov_compact(ctx);  // independent of the segment table: overlaps the wait for the chimeric pre-pass
     if (rc) return rc;
     rc = finish_prepass(ctx);
     if (rc) return rc;
+    lap("wait for pre-pass + upload");
     const int32_t nD = (int32_t)ctx->pre.disc.size() - 1, nG = (int32_t)ctx->pre.groups.size(), nP = (int32_t)ctx->pre.part_chr.size();
     if (nD <= 0) FAIL(SQG_EUNSUPPORTED, "no discordant block in the chimeric reads: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
 
@@ -964,9 +1004,11 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     }
     if (n_rest > 0) {
         size_t tb = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, 64, ctx->stream));
+        int key_bits = 33;  // (chr << 32 | pos): only the bits a chromosome index can set
+        while (key_bits < 64 && (1ll << (key_bits - 32)) < (long long)ctx->params.n_ref) key_bits++;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, key_bits, ctx->stream));
         ENSURE_TEMP(tb);
-        CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp.p, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, 64, ctx->stream));
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp.p, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, key_bits, ctx->stream));
         ctx->launches += 4;
     }
     // the state machine, island-parallel
@@ -1051,6 +1093,7 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
         CK(cudaGetLastError());
     }
     PHASE_END("seed");
+    lap("seed: enqueue");
 #ifdef SQ_SEED_PROF
     if (d_prof) {
         cudaStreamSynchronize(ctx->stream);
@@ -1086,6 +1129,7 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     if (seeds.empty()) FAIL(SQG_EUNSUPPORTED, "no seed segment was produced: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
     ctx->n_islands = n_isl;
 
+    lap("seed: wait + stitch");
     PHASE_BEGIN("tile");
     rc = tile_genome(ctx, seeds);
     if (rc) return rc;
@@ -1106,10 +1150,12 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
             r += m;
         }
     }
+    lap("tile + r_break");
     // phase 2 in one pass: per-segment depth and, eagerly, the assignment + raw edges sqg_build_edges will ask for
     const int32_t N = ctx->nt.n;
     rc = run_assign(ctx, true, true);
     if (rc) return rc;
+    lap("assign + edge reduce");
     CK(ctx->h_chr.ensure(N)); CK(ctx->h_pos.ensure(N)); CK(ctx->h_len.ensure(N)); CK(ctx->h_cnt3.ensure(3 * (size_t)N + 4)); CK(ctx->h_sum3.ensure(3 * (size_t)N + 4));
     CK(cudaMemcpyAsync(ctx->h_cnt3.p, ctx->d_cnt3.p, (3 * (size_t)N + 4) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_sum3.p, ctx->d_sum3.p, 3 * (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1118,6 +1164,7 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     *chr = ctx->h_chr.p; *pos = ctx->h_pos.p; *len = ctx->h_len.p; *n_nodes = N;
     *count3 = ctx->h_cnt3.p; *sumlen3 = ctx->h_sum3.p;
     *reads_other_nonempty = ctx->h_cnt3.p[3 * (size_t)N] != 0;
+    lap("outputs");
     return SQG_OK;
 }
 
@@ -1225,35 +1272,17 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
     const int64_t n = b.n_rec;
     PHASE_BEGIN("coverage");
     CK(ctx->d_bpchr.ensure(K)); CK(ctx->d_bppos.ensure(K)); CK(ctx->d_bpkey.ensure(K)); CK(ctx->d_r0.ensure(K)); CK(ctx->d_t.ensure(K)); CK(ctx->d_cov.ensure(K));
-    CK(ctx->d_sens.ensure(n + 1));
     CK(cudaMemcpyAsync(ctx->d_bpchr.p, bp_chr, K * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_bppos.p, bp_pos, K * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_cov.p, 0, K * 4, ctx->stream));
-    int64_t nq = 0;
-    int32_t *qidx = ctx->d_sens.p;  // qualifying records (right-hand mates that pass the gate, :3136-3142), ascending
-    if (n > 0) {
-        cub::CountingInputIterator<int32_t> cnt(0);
-        CoverQualOp qop{b, ctx->d_cls.p};
-        size_t tb = 0;
-        CK(cub::DeviceSelect::If(nullptr, tb, cnt, qidx, (int32_t *)(ctx->d_counters.p + 12), (int)n, qop, ctx->stream));
-        ENSURE_TEMP(tb);
-        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, qidx, (int32_t *)(ctx->d_counters.p + 12), (int)n, qop, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        nq = *(int32_t *)(ctx->h_counters.p + 12);
-        ctx->launches += 2;
-    }
-    CK(ctx->d_covM.ensure(nq + 1)); CK(ctx->d_qkey.ensure(nq + 1));
-    CoverRankKeyOp kop{b, qidx};
-    if (nq > 0) {  // fragment-start keys in rank space and their running maximum
-        LAUNCH(k_cov_keys, blocks_for(nq), kThreads, kop, nq, ctx->d_qkey.p);
-        size_t tb = 0;
-        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_qkey.p, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
-        ENSURE_TEMP(tb);
-        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_qkey.p, ctx->d_covM.p, MaxU64(), (int)nq, ctx->stream));
-        ctx->launches += 2;
-    }
-    LAUNCH(k_cov_r0, blocks_for(K), kThreads, ctx->d_covM.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_bpkey.p, ctx->d_r0.p, ctx->d_t.p);
+    // qualifying records compacted in stream order (done already if sqg_build_nodes ran: it only needs the class bytes)
+    rc = run_cov_compact(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t n_tiles = (n + kCovTile - 1) / kCovTile;
+    const int64_t nq = n > 0 ? ctx->h_counters.p[15] : 0;
+    LAUNCH(k_cov_r0_tiles, blocks_for(K), kThreads, ctx->d_qkey.p, ctx->d_covtile.p, (int32_t)(n > 0 ? n_tiles : 0), nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos,
+           ctx->d_bpkey.p, ctx->d_r0.p, ctx->d_t.p);
     {   // t[k] = max(r0[k], t[k-1]+1) whenever the qualifying record right after t[k-1] passes breakpoint k (the common case):
         // a max-plus prefix scan, verified in parallel; the literal one-step-per-record chain runs only if a candidate fails
         size_t tb = 0;
@@ -1292,7 +1321,7 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
         }
     }
     PHASE_BEGIN("k_cov_count");
-    if (nq > 0) LAUNCH(k_cov_count, blocks_for(nq), kThreads, b, qidx, ctx->d_qkey.p, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
+    if (nq > 0) LAUNCH(k_cov_count_tiles, blocks_for(nq, kCovRanks), 256, ctx->d_qkey.p, ctx->d_qend.p, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
     PHASE_END("k_cov_count");
     PHASE_END("coverage");
     CK(cudaMemcpyAsync(cov_out, ctx->d_cov.p, K * 4, cudaMemcpyDeviceToHost, ctx->stream));

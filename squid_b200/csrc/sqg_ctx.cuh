@@ -17,6 +17,7 @@
 #include "sq_seed.cuh"
 #include "sq_phase1.cuh"
 #include "sq_phase2.cuh"
+#include "sq_phase3.cuh"
 #include "squid_b200.h"
 
 namespace sq {
@@ -102,7 +103,7 @@ struct sqg_ctx {
     std::map<std::string, sq::PhaseTimer> timers;
 
     // concordant batch
-    bool have_batch = false, batch_owned = false, classified = false;
+    bool have_batch = false, batch_owned = false, classified = false, cov_compacted = false;
     int64_t first_record_index = 0;
     sq::DevBatch batch;
     sq::DBuf<int32_t> o_ref_id, o_pos, o_mate_ref_id, o_mate_pos, o_end_pos, o_blk_ref_pos, o_blk_match_ref;
@@ -181,7 +182,8 @@ struct sqg_ctx {
     sq::DBuf<int32_t> d_chunks;
     int32_t cov_chain_chunks = 0;
     sq::DBuf<int64_t> d_r0, d_t;
-    sq::DBuf<int32_t> d_cov, d_bpchr, d_bppos;
+    sq::DBuf<int32_t> d_cov, d_bpchr, d_bppos, d_qend;
+    sq::DBuf<sq::CovTile> d_covtile;
 
     // pinned outputs
     sq::HBuf<int32_t> h_chr, h_pos, h_len, h_cnt3, h_sum3, h_ind1, h_ind2, h_w, h_chimblk;
