@@ -132,7 +132,7 @@ void sort_like_std(SortKey *first, SortKey *last, int threads) {
     for (size_t n = (size_t)(last - first); n > 1; n >>= 1) lg++;
     struct Range { SortKey *a, *b; int depth; };
     const int T = std::max(1, std::min(threads, 32));
-    const ptrdiff_t kBig = 1 << 14;  // ranges above this are partitioned by all threads together
+    const ptrdiff_t kBig = 1 << 15;  // ranges above this are partitioned by all threads together
     std::vector<Range> big, small;
     big.push_back(Range{first, last, 2 * lg});
     std::vector<uint32_t> Lg, Rg;
@@ -148,7 +148,7 @@ void sort_like_std(SortKey *first, SortKey *last, int threads) {
     // the remaining partitions: sequential introsort loop + their share of the final insertion sort, one task each
     // (no barriers inside: this loop may use every core even while the caller's thread spins on the GPU)
     std::sort(small.begin(), small.end(), [](const Range &x, const Range &y) { return x.b - x.a > y.b - y.a; });  // largest first
-#pragma omp parallel for num_threads(std::min(2 * T, 32)) schedule(dynamic, 1)
+#pragma omp parallel for num_threads(std::max(T, std::min(2 * T, omp_get_num_procs()))) schedule(dynamic, 1)
     for (long long i = 0; i < (long long)small.size(); i++) {
         sort_loop(small[(size_t)i].a, small[(size_t)i].b, small[(size_t)i].depth);
         insertion_sort(small[(size_t)i].a, small[(size_t)i].b);

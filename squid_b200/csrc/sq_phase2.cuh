@@ -95,6 +95,7 @@ __device__ __noinline__ int32_t conc_edges_generic(const BatchDesc *desc, const 
     return read_edges(nt, p, rv, MODE_OTHER, is_first, false, 0, node, *edges) ? node[0] : -3;
 }
 
+template <bool DO_DEPTH, bool DO_EDGES>
 __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2Args a, int bulk_ok) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileStage &s = *reinterpret_cast<TileStage *>(smem_raw);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
         const int32_t rid = in ? s.ref_id[i] : -1;
         // depth
         int32_t m = -1;
-        if (a.do_depth) {
+        if (DO_DEPTH) {
             const bool counted = in && r < a.r_break && (c8 & CLS_HASBLK);
             int32_t st0 = 0, l0 = 0;
             bool cont = false;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
             }
         }
         // edges
-        if (a.do_edges) {
+        if (DO_EDGES) {
             int32_t out = -2;
             if (in && (c8 & CLS_KEEP)) {
                 if (nb <= 1 && staged) {
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     }
     __syncthreads();
     // ---- pass B: the multi-block records, densely packed, through the generic rules --------------------------------
-    if (a.do_edges) {
+    if (DO_EDGES) {
         const int ns = s_nslow;
 #pragma unroll 1
         for (int q = tid; q < ns; q += kTileThreads) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
         }
     }
     // ---- ReadsMain with the tile-local cursor -----------------------------------------------------------------------
-    if (a.do_depth) {
+    if (DO_DEPTH) {
         if (warp == 0) {
             int32_t inc = lane < kTileChunks ? s_cmax[lane] : -1;
 #pragma unroll
@@ -270,14 +271,14 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     }
     __syncthreads();
     // ---- flush the tile's tables --------------------------------------------------------------------------------------
-    if (a.do_depth) {
+    if (DO_DEPTH) {
         for (int w = tid; w < kDepthWin; w += kTileThreads) {
             const int32_t seg = base + w;
             if (s_dcnt[0][w]) { atomicAdd(&a.cnt_main[seg], s_dcnt[0][w]); atomicAdd(&a.sum_main[seg], s_dsum[0][w]); }
             if (s_dcnt[1][w]) { atomicAdd(&a.cnt_other[seg], s_dcnt[1][w]); atomicAdd(&a.sum_other[seg], s_dsum[1][w]); }
         }
     }
-    if (a.do_edges) {  // one reservation in the raw pair list per tile
+    if (DO_EDGES) {  // one reservation in the raw pair list per tile
         int mine = 0;
         for (int h = tid; h < kEdgeSlots; h += kTileThreads) mine += s_edges.cnt[h] != 0;
         int inc = mine;

@@ -930,11 +930,23 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
                 CK(cudaMemcpyAsync(ctx->d_desc.p, &hd, sizeof(hd), cudaMemcpyHostToDevice, ctx->stream));
                 a.desc = (const BatchDesc *)ctx->d_desc.p; a.nt_dev = (const NodeTable *)(ctx->d_desc.p + offsetof(decltype(hd), nt));
             }
-            CK(cudaFuncSetAttribute(k_assign_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            // two launches of the same tile kernel, one per job: each half is small enough for the instruction cache, and
+            // reading the batch twice is cheap next to that
+            CK(cudaFuncSetAttribute(k_assign_tiles<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            CK(cudaFuncSetAttribute(k_assign_tiles<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
             PHASE_BEGIN("k_assign");
-            k_assign_tiles<<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
-            ctx->launches++;
-            CK(cudaGetLastError());
+            if (do_depth) {
+                PHASE_BEGIN("k_assign_depth");
+                k_assign_tiles<true, false><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
+                ctx->launches++;
+                CK(cudaGetLastError());
+                PHASE_END("k_assign_depth");
+            }
+            if (do_edges) {
+                k_assign_tiles<false, true><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
+                ctx->launches++;
+                CK(cudaGetLastError());
+            }
             PHASE_END("k_assign");
             if (do_depth) {
                 LAUNCH(k_depth_scan, 1, 1024, ctx->d_dtile.p, (int32_t)n_tiles);
