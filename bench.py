@@ -208,8 +208,14 @@ def main():
             t1 = time.perf_counter()
             tl[name] = tl.get(name, 0.0) + 1e3 * (t1 - t_[0])
             t_[0] = t1
-        chim = api.ChimericReads(chim0.a)
-        lap("chim_copy")
+        # sqg_build_edges trims the chimeric blocks in place (LocateRead, :1229-1248): restore the four mutable arrays
+        chim = state.get("chim")
+        if chim is None:
+            chim = state["chim"] = api.ChimericReads(chim0.a)
+        else:
+            for k in ("blk_ref_pos", "blk_read_pos", "blk_match_ref", "blk_match_read"):
+                np.copyto(chim.a[k], chim0.a[k])
+        lap("chim_restore")
         if resident:
             g.attach_concordant_device(dstruct, keepalive=batch)
         else:
@@ -245,7 +251,7 @@ def main():
         lap("bps_from_graph(host stand-in)")
         cov = g.BPCoverage(bc, bp)
         lap("BPCoverage")
-        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback")}
+        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "edges_single_path", "edges_generic_path")}
         state.update(n_nodes=int(nodes.Chr.shape[0]), n_edges=int(edges.Ind1.shape[0]), n_bp=int(bc.shape[0]), cov_sum=int(cov.sum()),
                      d2h=int(nodes.Chr.nbytes * 3 + nodes.count3.nbytes * 2 + edges.Ind1.nbytes * 3 + edges.Ind1.shape[0] + cov.nbytes))
         return nodes, edges, cov
@@ -268,7 +274,7 @@ def main():
         phases = {}
         for _ in range(steps):
             step(resident)
-            for ph in ("h2d", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_assign_depth", "k_cov_compact", "k_cov_count"):
+            for ph in ("h2d", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_assign_depth", "k_assign_edges", "k_edges_generic", "k_cov_compact", "k_cov_count"):
                 v = g.phase_ms(ph)
                 if v >= 0:
                     phases[ph] = phases.get(ph, 0.0) + v / steps
@@ -290,8 +296,11 @@ def main():
     K = NB / R
     # algorithmic bytes per launch of the stream kernels: phase 1 and phase 2 read the whole batch
     # (32 B/record + 12 B/block), phase 3 the 24-byte subset of the qualifying half
-    alg = {"k_classify": 32 * R + 12 * NB, "k_assign": 32 * R + 12 * NB, "k_cov_compact": 24 * R}
-    traffic = {"k_classify": None, "k_assign": None, "k_cov_compact": None}  # ncu dram bytes per record (profiles/)
+    # (k_assign_depth and k_assign_edges are two launches of the tile kernel, each over the whole batch; phase 3 is the compaction
+    # pass over the 24-byte subset plus the 12-byte pass over the compacted pairs)
+    alg = {"k_classify": 32 * R + 12 * NB, "k_assign_depth": 32 * R + 12 * NB, "k_assign_edges": 32 * R + 12 * NB, "k_cov_compact": 24 * R}
+    # dram__bytes_read + dram__bytes_write per record from the ncu --set full capture (profiles/r1_ncu_summary_20Mpairs.txt)
+    traffic = {"k_classify": 42.8, "k_assign_depth": 36.2, "k_assign_edges": 44.3, "k_cov_compact": 28.4}
     peak, peak_src = measured_peak_gbs()
     stream = {k: v for k, v in phases.items() if k in alg}
     top = max(stream, key=stream.get) if stream else None
@@ -300,7 +309,7 @@ def main():
         ach = alg[top] / (stream[top] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic[top] * R if traffic.get(top) else None,
                 "peak_source": peak_src, "alg_bytes_per_launch": alg[top], "ms": stream[top],
-                "note": "dominant STREAM kernel; the latency-bound seed machine and coverage chain are listed in phases_ms",
+                "note": "dominant STREAM kernel of the step; the latency-bound seed machine is listed in phases_ms",
                 "all_stream_kernels": {k: {"ms": v, "GBps": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak} for k, v in stream.items()}}
     b_alg_pair = (2 * (32 * R + 12 * NB) + 24 * R) / P
     total_gpu_ms = sum(v for k, v in phases.items() if not k.startswith("k_"))

@@ -234,33 +234,41 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     }
 }
 
-// Exclusive scan of the tile aggregates, in place (one block): okmax -> maximum over earlier tiles, n_pc / n_dp -> offsets.
-// totals[1] = #partial, totals[2] = #displaced.
+// Exclusive scan of the tile aggregates, in place (one block of 32 warps): okmax -> maximum over earlier tiles, n_pc / n_dp ->
+// offsets.  Every warp owns a contiguous run of tiles and walks it 32 tiles at a time (coalesced), first to reduce the run,
+// then -- with the carry of the runs before it -- to scan it.  totals[1] = #partial, totals[2] = #displaced.
 __global__ void __launch_bounds__(1024) k_tile_scan(TileAgg *agg, int32_t n_tiles, int32_t *totals) {
-    __shared__ uint64_t s_ok[1024];
-    __shared__ uint32_t s_pc[1024], s_dp[1024];
-    const int tid = threadIdx.x;
-    const int per = (n_tiles + 1023) / 1024;
-    const int lo = tid * per < n_tiles ? tid * per : n_tiles, hi = (tid + 1) * per < n_tiles ? (tid + 1) * per : n_tiles;
+    __shared__ uint64_t s_ok[32];
+    __shared__ uint32_t s_pc[32], s_dp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const int per = ((n_tiles + 31) / 32 + 31) / 32 * 32;  // tiles per warp, a multiple of 32
+    const int lo = warp * per < n_tiles ? warp * per : n_tiles, hi = (warp + 1) * per < n_tiles ? (warp + 1) * per : n_tiles;
     uint64_t ok = 0; uint32_t pc = 0, dp = 0;
-    for (int t = lo; t < hi; t++) { const TileAgg g = agg[t]; if (g.okmax > ok) ok = g.okmax; pc += g.n_pc; dp += g.n_dp; }
-    s_ok[tid] = ok; s_pc[tid] = pc; s_dp[tid] = dp;
+    for (int t = lo + lane; t < hi; t += 32) { const TileAgg g = agg[t]; if (g.okmax > ok) ok = g.okmax; pc += g.n_pc; dp += g.n_dp; }
+    ok = warp_max_u64(ok); pc = __reduce_add_sync(full, pc); dp = __reduce_add_sync(full, dp);
+    if (lane == 0) { s_ok[warp] = ok; s_pc[warp] = pc; s_dp[warp] = dp; }
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {  // inclusive Hillis-Steele over the 1024 thread totals
-        uint64_t a = 0; uint32_t x = 0, y = 0;
-        if (tid >= d) { a = s_ok[tid - d]; x = s_pc[tid - d]; y = s_dp[tid - d]; }
-        __syncthreads();
-        if (tid >= d) { if (a > s_ok[tid]) s_ok[tid] = a; s_pc[tid] += x; s_dp[tid] += y; }
-        __syncthreads();
-    }
-    if (tid == 1023) { totals[1] = (int32_t)s_pc[1023]; totals[2] = (int32_t)s_dp[1023]; }
-    ok = tid ? s_ok[tid - 1] : 0ull; pc = tid ? s_pc[tid - 1] : 0u; dp = tid ? s_dp[tid - 1] : 0u;
-    for (int t = lo; t < hi; t++) {
-        const TileAgg g = agg[t];
-        TileAgg e; e.okmax = ok; e.n_pc = pc; e.n_dp = dp;
-        agg[t] = e;
-        if (g.okmax > ok) ok = g.okmax;
-        pc += g.n_pc; dp += g.n_dp;
+    ok = 0; pc = 0; dp = 0;  // carry into this warp's run
+    for (int w = 0; w < warp; w++) { if (s_ok[w] > ok) ok = s_ok[w]; pc += s_pc[w]; dp += s_dp[w]; }
+    if (threadIdx.x == 1023) { totals[1] = (int32_t)(pc + s_pc[31]); totals[2] = (int32_t)(dp + s_dp[31]); }
+    for (int base = lo; base < hi; base += 32) {
+        const int t = base + lane;
+        TileAgg g; g.okmax = 0; g.n_pc = 0; g.n_dp = 0;
+        if (t < hi) g = agg[t];
+        uint64_t iok = g.okmax; uint32_t ipc = g.n_pc, idp = g.n_dp;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t a = __shfl_up_sync(full, iok, d);
+            const uint32_t x = __shfl_up_sync(full, ipc, d), y = __shfl_up_sync(full, idp, d);
+            if (lane >= d) { if (a > iok) iok = a; ipc += x; idp += y; }
+        }
+        uint64_t eok = __shfl_up_sync(full, iok, 1); uint32_t epc = __shfl_up_sync(full, ipc, 1), edp = __shfl_up_sync(full, idp, 1);
+        if (lane == 0) { eok = 0; epc = 0; edp = 0; }
+        if (t < hi) { TileAgg e; e.okmax = eok > ok ? eok : ok; e.n_pc = pc + epc; e.n_dp = dp + edp; agg[t] = e; }
+        const uint64_t tok = __shfl_sync(full, iok, 31);
+        if (tok > ok) ok = tok;
+        pc += __shfl_sync(full, ipc, 31); dp += __shfl_sync(full, idp, 31);
     }
 }
 

@@ -62,6 +62,8 @@ struct P2Args {
     PairSink sink;
     int32_t *sens; int32_t *n_sens; int32_t sens_cap;
     const BatchDesc *desc; const NodeTable *nt_dev;  // device copies for the out-of-line generic path
+    unsigned long long *path_counts;  // [0] records through read_edges_single, [1] through the generic read_edges (statistics)
+    int32_t *slow_list; int32_t *n_slow; int32_t slow_cap;  // records left to k_edges_generic
 };
 
 constexpr uint32_t kP2Fields = F_REF | F_MREF | F_MPOS | F_FLAG | F_TLEN | F_LOWQ | F_CLS | F_BLOCKS;
@@ -101,9 +103,9 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     TileStage &s = *reinterpret_cast<TileStage *>(smem_raw);
     __shared__ TileEdgeTable s_edges;
     __shared__ int32_t s_dcnt[2][kDepthWin], s_dsum[2][kDepthWin];
-    __shared__ uint16_t s_slow[kTile];
+    __shared__ uint16_t s_slow[kTile], s_mid[kTile];
     __shared__ int32_t s_cmax[kTileChunks];
-    __shared__ int32_t s_nslow, s_base, s_other, s_first, s_seg[4];
+    __shared__ int32_t s_nslow, s_nmid, s_base, s_other, s_first, s_seg[4];
     int32_t *s_m = s.end_pos;   // per record: depth target of its first block (-1: not counted)
     uint8_t *s_cont = s.mapq;   // per record: first block contained in that target
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     const int64_t rec0 = ti.rec0;
     for (int i = tid; i < kEdgeSlots; i += kTileThreads) { s_edges.keys[i] = kEmptyKey; s_edges.cnt[i] = 0; }
     for (int i = tid; i < 2 * kDepthWin; i += kTileThreads) { (&s_dcnt[0][0])[i] = 0; (&s_dsum[0][0])[i] = 0; }
-    if (tid == 0) { s_edges.spill = a.sink; s_nslow = 0; s_other = 0; s_first = 0x7fffffff; s_base = -(1 << 30); }
+    if (tid == 0) { s_edges.spill = a.sink; s_nslow = 0; s_nmid = 0; s_other = 0; s_first = 0x7fffffff; s_base = -(1 << 30); }
     stage_wait<kP2Fields>(s, b, a.cls, tk);
     const bool staged = ti.nb >= 0;
     const TileBatch tb = tile_view(s, ti, b);
@@ -206,8 +208,23 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
                     const bool own_in = nb == 0 || (rid == wc && own.match_ref > kLocateTol && wq <= own.ref_pos && own.ref_pos + kLocateTol < we && own.ref_pos + own.match_ref - kLocateTol <= we);
                     const bool mate_in = !has_mate || (s.mate_ref_id[i] == wc && wq <= s.mate_pos[i] && s.mate_pos[i] + kLocateTol < we && s.mate_pos[i] + kMateBlockLen - kLocateTol <= we);
                     if (builds && (nb == 1 || has_mate) && own_in && mate_in) out = ws;
-                    else if (builds && (nb == 1 || has_mate))
-                        out = read_edges_single(nt, a.p, nb == 1, own, has_mate, mate_block_of(f, s.mate_ref_id[i], s.mate_pos[i]), flag_first(f), (int32_t)s.total_len[i], s_edges);
+                    else if (builds && (nb == 1 || has_mate)) { out = -4; s_mid[atomicAdd(&s_nmid, 1)] = (uint16_t)i; }  // pass B1
+                } else if (staged && rid == wc) {
+                    // several blocks: if every one of them (and the mate block) lies well inside the tile's segment, each locates
+                    // there -- the first by the closed form, the others because they fit the cursor -- and no rule emits anything
+                    const uint16_t f = s.flag[i];
+                    const bool has_mate = has_mate_block(f, s.mate_ref_id[i]);
+                    bool all_in = !has_mate || (s.mate_ref_id[i] == wc && wq <= s.mate_pos[i] && s.mate_pos[i] + kLocateTol < we && s.mate_pos[i] + kMateBlockLen - kLocateTol <= we);
+                    int32_t front_rp = 0x7fffffff;
+                    for (uint32_t k = 0; k < nb; k++) {
+                        const int32_t p0 = tb.blk_ref_pos[o0 + k], m0 = tb.blk_match_ref[o0 + k], rp = tb.blk_read_pos[o0 + k];
+                        all_in = all_in && m0 > kLocateTol && wq <= p0 && p0 + kLocateTol < we && p0 + m0 - kLocateTol <= we;
+                        if (rp < front_rp) front_rp = rp;
+                    }
+                    const bool builds = !has_mate || front_rp <= 15 || (int32_t)s.lowphred_run[i] > a.p.max_lowphred_len;  // :1601-1605
+                    if (!builds) out = -2;
+                    else if (all_in) out = ws;
+                    else { out = -4; s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)i; }
                 } else {
                     out = -4;  // generic path below
                     s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)i;
@@ -220,16 +237,34 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
         }
     }
     __syncthreads();
-    // ---- pass B: the multi-block records, densely packed, through the generic rules --------------------------------
+    // ---- pass B1: single-block records that left the tile's segment, densely packed ---------------------------------
     if (DO_EDGES) {
-        const int ns = s_nslow;
+        const int nm = s_nmid;
 #pragma unroll 1
-        for (int q = tid; q < ns; q += kTileThreads) {
-            const int i = s_slow[q];
+        for (int q = tid; q < nm; q += kTileThreads) {
+            const int i = s_mid[q];
             const int64_t r = rec0 + i;
-            const int32_t out = conc_edges_generic(a.desc, a.nt_dev, r, &s_edges);
+            const uint16_t f = s.flag[i];
+            const uint32_t o0 = s.blk_off[i], nb = s.blk_off[i + 1] - o0;
+            Blk own;
+            own.ref_id = s.ref_id[i]; own.rev = flag_rev(f); own.ref_pos = 0; own.match_ref = 0; own.read_pos = 0; own.match_read = 0;
+            if (nb == 1) { own.ref_pos = tb.blk_ref_pos[o0]; own.match_ref = tb.blk_match_ref[o0]; own.read_pos = tb.blk_read_pos[o0]; own.match_read = tb.blk_match_read[o0]; }
+            const int32_t out = read_edges_single(nt, a.p, nb == 1, own, has_mate_block(f, s.mate_ref_id[i]), mate_block_of(f, s.mate_ref_id[i], s.mate_pos[i]), flag_first(f),
+                                                  (int32_t)s.total_len[i], s_edges);
             a.res0[r] = out;
             if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
+        }
+    }
+    // ---- the multi-block records that left the tile's segment go to k_edges_generic (one dense kernel over all of them) ----
+    if (DO_EDGES) {
+        __shared__ int32_t s_slow_base;
+        const int ns = s_nslow;
+        if (tid == 0 && ns > 0) s_slow_base = atomicAdd(a.n_slow, ns);
+        __syncthreads();
+        if (ns > 0) {
+            const int32_t base_q = s_slow_base;
+            for (int q = tid; q < ns; q += kTileThreads)
+                if (base_q + q < a.slow_cap) a.slow_list[base_q + q] = (int32_t)(rec0 + s_slow[q]);
         }
     }
     // ---- ReadsMain with the tile-local cursor -----------------------------------------------------------------------
@@ -278,6 +313,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
             if (s_dcnt[1][w]) { atomicAdd(&a.cnt_other[seg], s_dcnt[1][w]); atomicAdd(&a.sum_other[seg], s_dsum[1][w]); }
         }
     }
+    if (DO_EDGES && tid == 0 && a.path_counts) { atomicAdd(a.path_counts, (unsigned long long)s_nmid); atomicAdd(a.path_counts + 1, (unsigned long long)s_nslow); }
     if (DO_EDGES) {  // one reservation in the raw pair list per tile
         int mine = 0;
         for (int h = tid; h < kEdgeSlots; h += kTileThreads) mine += s_edges.cnt[h] != 0;
@@ -301,25 +337,72 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     }
 }
 
-// exclusive running maximum of the per-tile maximum targets (one block); tiles with no counted read pass the cursor on
-__global__ void __launch_bounds__(1024) k_depth_scan(DepthTile *dt, int32_t n_tiles) {
-    __shared__ int32_t s_mx[1024];
-    const int tid = threadIdx.x;
-    const int per = (n_tiles + 1023) / 1024;
-    const int lo = tid * per < n_tiles ? tid * per : n_tiles, hi = (tid + 1) * per < n_tiles ? (tid + 1) * per : n_tiles;
-    int32_t mx = -1;
-    for (int t = lo; t < hi; t++) if (dt[t].max_target > mx) mx = dt[t].max_target;
-    s_mx[tid] = mx;
+// The records k_assign_tiles left over (several aligned blocks, not all inside one segment): the generic rules, one record
+// per thread, every lane busy.  Edges are counted in a per-block table like in the tile kernel.
+__global__ void __launch_bounds__(128) k_edges_generic(P2Args a) {
+    __shared__ TileEdgeTable s_edges;
+    __shared__ int32_t s_tot, s_woff[4];
+    __shared__ unsigned long long s_at;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kEdgeSlots; i += 128) { s_edges.keys[i] = kEmptyKey; s_edges.cnt[i] = 0; }
+    if (tid == 0) s_edges.spill = a.sink;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        int32_t v = -1;
-        if (tid >= d) v = s_mx[tid - d];
-        __syncthreads();
-        if (tid >= d && v > s_mx[tid]) s_mx[tid] = v;
-        __syncthreads();
+    const int32_t n = *a.n_slow < a.slow_cap ? *a.n_slow : a.slow_cap;
+    for (int32_t q = blockIdx.x * 128 + tid; q < n; q += gridDim.x * 128) {
+        const int64_t r = a.slow_list[q];
+        const int32_t out = conc_edges_generic(a.desc, a.nt_dev, r, &s_edges);
+        a.res0[r] = out;
+        if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
     }
-    mx = tid ? s_mx[tid - 1] : -1;
-    for (int t = lo; t < hi; t++) { const int32_t own = dt[t].max_target; dt[t].max_target = mx; if (own > mx) mx = own; }
+    __syncthreads();
+    int mine = 0;
+    for (int h = tid; h < kEdgeSlots; h += 128) mine += s_edges.cnt[h] != 0;
+    int inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    if (lane == 31) s_woff[warp] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < 4; w++) { const int c = s_woff[w]; s_woff[w] = tot; tot += c; }
+        s_tot = tot;
+        if (tot > 0) s_at = atomicAdd(a.sink.counter, (unsigned long long)tot);
+    }
+    __syncthreads();
+    if (s_tot > 0) {
+        long long at = (long long)s_at + s_woff[warp] + inc - mine;
+        for (int h = tid; h < kEdgeSlots; h += 128)
+            if (s_edges.cnt[h]) { if (at < a.sink.cap) { a.sink.keys[at] = (uint64_t)s_edges.keys[h]; a.sink.w[at] = s_edges.cnt[h]; } at++; }
+    }
+}
+
+// exclusive running maximum of the per-tile maximum targets (one block of 32 warps, each walking a contiguous run of tiles
+// 32 at a time); tiles with no counted read pass the cursor on
+__global__ void __launch_bounds__(1024) k_depth_scan(DepthTile *dt, int32_t n_tiles) {
+    __shared__ int32_t s_mx[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const int per = ((n_tiles + 31) / 32 + 31) / 32 * 32;
+    const int lo = warp * per < n_tiles ? warp * per : n_tiles, hi = (warp + 1) * per < n_tiles ? (warp + 1) * per : n_tiles;
+    int32_t mx = -1;
+    for (int t = lo + lane; t < hi; t += 32) { const int32_t v = dt[t].max_target; if (v > mx) mx = v; }
+    mx = __reduce_max_sync(full, mx);
+    if (lane == 0) s_mx[warp] = mx;
+    __syncthreads();
+    mx = -1;
+    for (int w = 0; w < warp; w++) if (s_mx[w] > mx) mx = s_mx[w];
+    for (int base = lo; base < hi; base += 32) {
+        const int t = base + lane;
+        const int32_t own = t < hi ? dt[t].max_target : -1;
+        int32_t inc = own;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(full, inc, d); if (lane >= d && u > inc) inc = u; }
+        int32_t exc = __shfl_up_sync(full, inc, 1);
+        if (lane == 0) exc = -1;
+        if (t < hi) dt[t].max_target = exc > mx ? exc : mx;
+        const int32_t tot = __shfl_sync(full, inc, 31);
+        if (tot > mx) mx = tot;
+    }
 }
 
 // Tiles whose incoming cursor is ahead of their first target counted some reads against the wrong segment: redo those

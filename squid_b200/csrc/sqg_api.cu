@@ -541,7 +541,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
-    ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
+    ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_slow.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
     ctx->h_chr.release(); ctx->h_pos.release(); ctx->h_len.release(); ctx->h_cnt3.release(); ctx->h_sum3.release(); ctx->h_ind1.release(); ctx->h_ind2.release();
@@ -579,6 +579,8 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     if (n == "sensitive_reads") return ctx->n_sensitive;
     if (n == "raw_edges") return ctx->n_raw_edges;
     if (n == "r_break") return ctx->r_break;
+    if (n == "edges_single_path") return ctx->h_counters.p ? ctx->h_counters.p[16] : -1;
+    if (n == "edges_generic_path") return ctx->h_counters.p ? ctx->h_counters.p[17] : -1;
     return -1;
 }
 
@@ -794,8 +796,8 @@ static int install_nodes(sqg_ctx *ctx) {  // from h_nchr/h_npos/h_nend
     {   // coarse position index over the tiling (sq_common.cuh: seg_at)
         int64_t total = 0;
         for (int32_t c = 0; c < n_ref; c++) total += ctx->ref_len[c] > 0 ? ctx->ref_len[c] : 0;
-        int32_t sh = 12;
-        while ((total >> sh) > (8ll << 20)) sh++;  // at most ~8M bins
+        int32_t sh = 9;  // 512-bp bins: reads pile up exactly where segments are dense (fusion genes), so the bins must be fine
+        while ((total >> sh) > (16ll << 20)) sh++;  // at most ~16M bins (64 MB, L2-resident where it is hot)
         ctx->h_bin_off.assign(n_ref + 1, 0);
         for (int32_t c = 0; c < n_ref; c++) ctx->h_bin_off[c + 1] = ctx->h_bin_off[c] + ((ctx->ref_len[c] > 0 ? ctx->ref_len[c] : 0) >> sh) + 1;
         const int32_t n_bins = ctx->h_bin_off[n_ref];
@@ -890,6 +892,7 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
     if (do_depth) { CK(ctx->d_cnt3.ensure(3 * (size_t)N + 4)); CK(ctx->d_sum3.ensure(3 * (size_t)N + 4)); CK(ctx->d_dtile.ensure(n_tiles + 1)); }
     int64_t cap = std::max<int64_t>({(int64_t)ctx->d_ekeys.cap, n / 8 + 4 * ctx->c_n_blk + 2 * ctx->c_n_reads + 4096, (int64_t)1 << 20});
     int64_t sens_cap = std::max<int64_t>({(int64_t)ctx->d_sens.cap, n / 64 + 4096, ctx->c_n_reads + 1});
+    int64_t slow_cap = std::max<int64_t>({(int64_t)ctx->d_slow.cap, n / 8 + 4096});
     CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1));
     int64_t n_raw = 0;
     PHASE_BEGIN(do_depth ? "depth_edges" : "edges_only");
@@ -923,6 +926,10 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             a.other_nonempty = do_depth ? ctx->d_cnt3.p + 3 * (size_t)N : nullptr;
             a.dtile = ctx->d_dtile.p; a.res0 = ctx->d_scratch32.p; a.sink = sink;
             a.sens = ctx->d_sens.p; a.n_sens = d_nsens; a.sens_cap = conc_sens_cap;
+            a.path_counts = (unsigned long long *)(ctx->d_counters.p + 16);
+            CK(cudaMemsetAsync(ctx->d_counters.p + 16, 0, 3 * sizeof(int64_t), ctx->stream));
+            CK(ctx->d_slow.ensure(slow_cap));
+            a.slow_list = ctx->d_slow.p; a.n_slow = (int32_t *)(ctx->d_counters.p + 18); a.slow_cap = (int32_t)std::min<int64_t>(ctx->d_slow.cap, 0x7fffffff);
             {
                 struct { BatchDesc d; NodeTable nt; } hd;
                 hd.d.b = b; hd.d.p = ctx->params; hd.nt = ctx->nt;
@@ -943,9 +950,14 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
                 PHASE_END("k_assign_depth");
             }
             if (do_edges) {
+                PHASE_BEGIN("k_assign_edges");
                 k_assign_tiles<false, true><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
                 ctx->launches++;
                 CK(cudaGetLastError());
+                PHASE_END("k_assign_edges");
+                PHASE_BEGIN("k_edges_generic");
+                LAUNCH(k_edges_generic, 148 * 16, 128, a);
+                PHASE_END("k_edges_generic");
             }
             PHASE_END("k_assign");
             if (do_depth) {
@@ -958,11 +970,14 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             }
         }
         CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 16, ctx->d_counters.p + 16, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         n_raw = ctx->h_counters.p[9];
         const int32_t ns_conc = ((int32_t *)(ctx->h_counters.p + 10))[0], ns_chim = ((int32_t *)(ctx->h_counters.p + 10))[1];
         ctx->n_sensitive = (int64_t)ns_conc + ns_chim;
-        if (!do_edges || (n_raw <= cap && ns_conc <= conc_sens_cap)) break;
+        const int64_t n_slow = *(int32_t *)(ctx->h_counters.p + 18);
+        if (!do_edges || (n_raw <= cap && ns_conc <= conc_sens_cap && n_slow <= slow_cap)) break;
+        slow_cap = std::max(slow_cap, n_slow + 4096);
         if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge / sensitive read buffer overflow");
         cap = std::max(cap, n_raw + 4096);  // rerun with room for everything (chimeric trims are idempotent, counters are reset)
         sens_cap = std::max<int64_t>(sens_cap, (int64_t)ns_conc + ctx->c_n_reads + 4096);

@@ -170,7 +170,7 @@ struct sqg_ctx {
 
     // edges
     sq::DBuf<uint64_t> d_ekeys, d_ekeys2, d_ukeys;
-    sq::DBuf<int32_t> d_ecount, d_sens, d_head, d_ew;
+    sq::DBuf<int32_t> d_ecount, d_sens, d_head, d_ew, d_slow;
     sq::DBuf<sq::DepthTile> d_dtile;
     sq::DBuf<int32_t> d_e_ind1, d_e_ind2, d_e_w;
     sq::DBuf<uint8_t> d_e_heads;
