@@ -312,7 +312,8 @@ def main():
                 "note": "dominant STREAM kernel of the step; the latency-bound seed machine is listed in phases_ms",
                 "all_stream_kernels": {k: {"ms": v, "GBps": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak} for k, v in stream.items()}}
     b_alg_pair = (2 * (32 * R + 12 * NB) + 24 * R) / P
-    total_gpu_ms = sum(v for k, v in phases.items() if not k.startswith("k_"))
+    # phases are disjoint stream intervals; the eager coverage compaction runs between "classify" and "seed"
+    total_gpu_ms = sum(v for k, v in phases.items() if not k.startswith("k_")) + phases.get("k_cov_compact", 0.0)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg()
