@@ -273,13 +273,15 @@ def make_chimeric(tx: Transcriptome, p: np.ndarray, n_pairs: int, seed: int, dis
 
 
 def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.005, n_genes: int | None = None,
-              fusion_support: float = 20.0, clip_frac: float = 0.02, adversarial: bool = True, min_block: int = 4):
-    """Returns (concordant AlnTable sorted by coordinate, chimeric AlnTable, info dict)."""
+              fusion_support: float = 20.0, clip_frac: float = 0.02, adversarial: bool = True, min_block: int = 4,
+              exon_len=(100, 1500), intron_len=(200, 20000)):
+    """Returns (concordant AlnTable sorted by coordinate, chimeric AlnTable, info dict).  Short exons make every read span
+    several of them (many aligned blocks per record)."""
     ref_len = np.asarray(GRCH38_LEN if ref_len is None else ref_len, dtype=np.int64)
     rng = np.random.Generator(np.random.PCG64(seed))
     if n_genes is None:
         n_genes = int(max(8, min(20000, n_pairs // 400)))
-    tx = Transcriptome(rng, ref_len, n_genes)
+    tx = Transcriptome(rng, ref_len, n_genes, exon_len=exon_len, intron_len=intron_len)
     p = tx.g_expr / tx.g_expr.sum()
     gene = rng.choice(n_genes, size=n_pairs, p=p)
     left, right = _pairs_from_transcripts(rng, tx, gene, 0, clip_frac, min_block)

@@ -66,3 +66,86 @@ def test_errors_are_loud(tmp_path, built_lib):
     with pytest.raises(api.SquidB200Error) as ei:
         g.BuildNode_STAR()
     assert "sorted" in str(ei.value)
+
+
+def test_many_blocks_per_record(tmp_path, built_lib, ref_oracle):
+    """Short exons: ~3 aligned blocks per record, so most tiles hold more blocks than the staging buffer takes and run the
+    HBM path of the tile kernels; nearly every read goes through the generic multi-block rules."""
+    from oracle import pyref
+    cp, hp, conc, chim, info = common.write_case(str(tmp_path), 60000, 77, 0.02, [3000000, 2000000, 500000, 16569], n_genes=30, exon_len=(20, 170), intron_len=(60, 400))
+    ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    got = common.run_cuda(cp, hp, do_cov_with=ref)
+    b = got["case"].batch
+    assert b.n_blk > 1.5 * b.n_rec  # dense enough that tiles overflow the staging buffer
+    common.assert_same(ref, got)
+    assert got["support"] == pyref.support_map(ref)
+
+
+def test_unaligned_device_batch(tmp_path, built_lib, ref_oracle):
+    """A caller-owned device batch whose arrays start at odd offsets: no TMA bulk copies, the tiles are staged with plain
+    loads.  Same answers."""
+    import torch
+    from oracle import pyref
+    from squid_b200 import api
+    cp, hp, *_ = common.write_case(str(tmp_path), 30000, 41, 0.02)
+    ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    case = api.HostCase(cp, hp)
+    keep, st = {}, api.sqg_batch()
+    st.n_rec, st.n_blk = case.batch.n_rec, case.batch.n_blk
+    for k, a in case.batch.a.items():
+        t = torch.zeros(a.shape[0] + 3, dtype=getattr(torch, {"uint16": "int16", "uint32": "int32"}.get(a.dtype.name, a.dtype.name)), device="cuda")
+        v = t[1:1 + a.shape[0]]  # one element off the allocation's alignment
+        v.copy_(torch.from_numpy(a.view({"uint16": "int16", "uint32": "int32"}.get(a.dtype.name, a.dtype.name))))
+        keep[k] = t
+        setattr(st, k, v.data_ptr())
+        assert v.data_ptr() % 16 != 0
+    g = api.SegmentGraph(case.config, case.ref_len)
+    g.attach_concordant_device(st, keepalive=keep)
+    g.load_chimeric(case.chimeric)
+    nodes = g.BuildNode_STAR()
+    edges = g.BuildEdges()
+    got = {"nodes": np.stack([nodes.Chr, nodes.Position, nodes.Length, nodes.Support], axis=1).astype(np.int32), "avgdepth": nodes.AvgDepth,
+           "edges": edges.table(), "chim_after_edges": case.chimeric.block_table()}
+    common.assert_same(ref, got)
+    sup = g.ExactBPConcordantSupport(ref["final_nodes"], ref["final_edges"], pyref.exactbp_map(ref))
+    assert sup == pyref.support_map(ref)
+
+
+def test_degenerate_batches(tmp_path, built_lib):
+    """Ragged inputs: an empty concordant batch, a batch that is not a multiple of the tile size, unsorted input."""
+    from squid_b200 import api
+    cp, hp, *_ = common.write_case(str(tmp_path), 3000, 13, 0.05)
+    case = api.HostCase(cp, hp)
+    # 1. batch sizes around tile boundaries (512 records per tile): two contexts agree, and agree with the full batch on the prefix
+    n = case.batch.n_rec
+
+    def run(cut):
+        g = api.SegmentGraph(case.config, case.ref_len)
+        g.load_concordant(case.batch.slice(0, cut)); g.load_chimeric(api.ChimericReads(case.chimeric.a))
+        try:
+            nd = g.BuildNode_STAR(); ed = g.BuildEdges()
+        except api.SquidB200Error as e:  # a stream that ends before the first group triggers: undefined in the reference, reported here
+            assert e.code == api.SQG_EUNSUPPORTED
+            return None
+        return nd.Position.copy(), nd.Support.copy(), ed.table().copy()
+    for cut in (n, n - 1, (n // 512) * 512, (n // 512) * 512 + 1, (n // 512) * 512 - 1, 1025, 512, 511):
+        a, b2 = run(cut), run(cut)
+        assert (a is None) == (b2 is None)
+        if a is not None:
+            assert all(np.array_equal(x, y) for x, y in zip(a, b2))
+    # 2. no concordant record at all: the chimeric reads alone still give a graph
+    g = api.SegmentGraph(case.config, case.ref_len)
+    g.load_concordant(case.batch.slice(0, 0)); g.load_chimeric(api.ChimericReads(case.chimeric.a))
+    try:
+        n0 = g.BuildNode_STAR()
+        assert n0.Chr.shape[0] >= len(case.ref_len)
+    except api.SquidB200Error as e:  # BuildNode_STAR is undefined when nothing triggers a group; that must be reported, not crash
+        assert e.code in (api.SQG_EUNSUPPORTED, api.SQG_ESTATE)
+    # 3. unsorted input is refused
+    bad = case.batch.slice(0, case.batch.n_rec)
+    bad.a["pos"][10], bad.a["pos"][11] = bad.a["pos"][11] + 5, bad.a["pos"][10]
+    if bad.a["ref_id"][10] == bad.a["ref_id"][11]:
+        g = api.SegmentGraph(case.config, case.ref_len)
+        g.load_concordant(bad); g.load_chimeric(api.ChimericReads(case.chimeric.a))
+        with pytest.raises(api.SquidB200Error):
+            g.BuildNode_STAR()
