@@ -127,6 +127,9 @@ int sqg_set_nodes(sqg_ctx *ctx, const int32_t *chr, const int32_t *pos, const in
  * RawEdgesChim + RawEdgesOther + sort + run-length sum + drop Weight<=0.
  * heads[i] bit0 = Head1, bit1 = Head2.  Chimeric blocks loaded by sqg_load_chimeric are trimmed
  * in place (written back into the caller's sqg_chimeric arrays passed here).
+ * sqg_build_nodes() already runs the assignment pass (it shares its staging with the depth pass) and
+ * caches the edge table of the segments it produced; this call then only copies it out.  After
+ * sqg_set_nodes() the table is recomputed for the injected segments.
  */
 int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges,
                     sqg_chimeric *chim_inout);
@@ -145,13 +148,15 @@ int sqg_edges_device_table(sqg_ctx *ctx, uint64_t **d_keys, int32_t **d_weights,
 int sqg_merge_edge_tables(sqg_ctx *ctx, const uint64_t *d_keys, const int32_t *d_weights, int64_t n,
                           int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges);
 
-/* Device time in ms of the named phase/kernel of the most recent call ("classify", "seed", "depth_edges",
- * "edge_sort", "coverage", ...), measured with CUDA events on the context's stream; <0 if unknown. */
+/* Device time in ms of the named phase/kernel of the most recent call ("classify", "seed", "tile", "depth_edges",
+ * "edge_sort", "coverage"; kernels: "k_classify", "k_cov_compact", "k_assign_depth", "k_assign_edges", "k_edges_generic",
+ * "k_cov_count"), measured with CUDA events on the context's stream; <0 if unknown. */
 float sqg_phase_ms(const sqg_ctx *ctx, const char *name);
 /* Number of kernel launches issued by this context so far. */
 int64_t sqg_launch_count(const sqg_ctx *ctx);
 /* Counters of the most recent calls ("islands", "heavy_islands", "groups", "disc_blocks", "gap_records", "partial_records",
- * "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "r_break"); -1 if unknown. */
+ * "displaced_records", "lmax", "sensitive_reads", "raw_edges" (= (key, count) pairs before the reduce), "cov_chain_fallback",
+ * "r_break", "edges_single_path", "edges_generic_path"); -1 if unknown. */
 int64_t sqg_stat(const sqg_ctx *ctx, const char *name);
 
 #ifdef __cplusplus

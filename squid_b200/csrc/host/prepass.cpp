@@ -92,38 +92,57 @@ inline void insertion_sort(SortKey *first, SortKey *last) {  // what the final i
     }
 }
 // Closed-form Hoare partition of [first+1, last) around *first, all threads together.  Returns the cut.
+// One scan: thread t writes the positions of its chunk [a_t, b_t) that belong to L / R into Lg / Rg starting at a_t (a chunk
+// cannot hold more of them than it has elements); rank i of the whole list lives at Lg[a_t + i - cl[t]] for the t with
+// cl[t] <= i < cl[t+1].
+struct Ranked {  // access by rank to the per-chunk position lists
+    const std::vector<uint32_t> &g; const std::vector<size_t> &cum, &start; int T;
+    int chunk_of(size_t i) const { int lo = 0, hi = T - 1; while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (cum[(size_t)m] <= i) lo = m; else hi = m - 1; } return lo; }
+    uint32_t at(size_t i) const { const int t = chunk_of(i); return g[start[(size_t)t] + (i - cum[(size_t)t])]; }
+};
 SortKey *partition_parallel(SortKey *first, SortKey *last, int T, std::vector<uint32_t> &Lg, std::vector<uint32_t> &Rg) {
     SortKey *base = first + 1;
     const size_t n = (size_t)(last - base);
     const SortKey piv = *first;
-    std::vector<size_t> cl((size_t)T + 1, 0), cr((size_t)T + 1, 0);
-    Lg.resize(n); Rg.resize(n);
+    std::vector<size_t> cl((size_t)T + 1, 0), cr((size_t)T + 1, 0), st((size_t)T + 1, 0);
+    if (Lg.size() < n) { Lg.resize(n); Rg.resize(n); }
+    for (int t = 0; t <= T; t++) st[(size_t)t] = n * (size_t)t / (size_t)T;
 #pragma omp parallel num_threads(T)
     {
         const int t = omp_get_thread_num();
-        const size_t a = n * (size_t)t / (size_t)T, b = n * (size_t)(t + 1) / (size_t)T;
-        size_t nl = 0, nr = 0;
-        for (size_t i = a; i < b; i++) { nl += !sk_lt(base[i], piv); nr += !sk_lt(piv, base[i]); }
-        cl[(size_t)t + 1] = nl; cr[(size_t)t + 1] = nr;
-#pragma omp barrier
-#pragma omp single
-        { for (int q = 0; q < T; q++) { cl[(size_t)q + 1] += cl[(size_t)q]; cr[(size_t)q + 1] += cr[(size_t)q]; } }
-        size_t wl = cl[(size_t)t], wr = cr[(size_t)t];
+        const size_t a = st[(size_t)t], b = st[(size_t)t + 1];
+        size_t wl = a, wr = a;
         for (size_t i = a; i < b; i++) {
-            if (!sk_lt(base[i], piv)) Lg[wl++] = (uint32_t)i;
-            if (!sk_lt(piv, base[i])) Rg[wr++] = (uint32_t)i;   // ascending here; R[i] of the text is Rg[nR-1-i]
+            const uint64_t k = base[i].key;
+            if (!(k < piv.key)) Lg[wl++] = (uint32_t)i;
+            if (!(piv.key < k)) Rg[wr++] = (uint32_t)i;   // ascending here; R[i] of the text is rank nR-1-i
         }
+        cl[(size_t)t + 1] = wl - a; cr[(size_t)t + 1] = wr - a;
     }
+    for (int q = 0; q < T; q++) { cl[(size_t)q + 1] += cl[(size_t)q]; cr[(size_t)q + 1] += cr[(size_t)q]; }
     const size_t nL = cl[(size_t)T], nR = cr[(size_t)T];
+    const Ranked L{Lg, cl, st, T}, R{Rg, cr, st, T};
     // m = #{i : L[i] < R[i]}: the predicate is monotone in i
     size_t lo = 0, hi = std::min(nL, nR);
-    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (Lg[mid] < Rg[nR - 1 - mid]) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (L.at(mid) < R.at(nR - 1 - mid)) lo = mid + 1; else hi = mid; }
     const size_t m = lo;
-#pragma omp parallel for num_threads(T) schedule(static)
-    for (long long i = 0; i < (long long)m; i++) std::swap(base[Lg[(size_t)i]], base[Rg[nR - 1 - (size_t)i]]);
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        const size_t i0 = m * (size_t)t / (size_t)T, i1 = m * (size_t)(t + 1) / (size_t)T;
+        if (i0 < i1) {
+            int tl = L.chunk_of(i0), tr = R.chunk_of(nR - 1 - i0);  // walk the chunks instead of searching per element
+            for (size_t i = i0; i < i1; i++) {
+                while (cl[(size_t)tl + 1] <= i) tl++;
+                const size_t j = nR - 1 - i;
+                while (cr[(size_t)tr] > j) tr--;
+                std::swap(base[Lg[st[(size_t)tl] + (i - cl[(size_t)tl])]], base[Rg[st[(size_t)tr] + (j - cr[(size_t)tr])]]);
+            }
+        }
+    }
     size_t cut;
-    if (m == 0) cut = Lg[0];
-    else cut = (m < nL && Lg[m] < Rg[nR - m]) ? Lg[m] : Rg[nR - m];  // R[m-1] = Rg[nR-m]
+    if (m == 0) cut = L.at(0);
+    else cut = (m < nL && L.at(m) < R.at(nR - m)) ? L.at(m) : R.at(nR - m);  // R[m-1] is ascending rank nR-m
     return base + cut;
 }
 void sort_like_std(SortKey *first, SortKey *last, int threads) {

@@ -121,4 +121,6 @@ def test_parallel_sort_reproduces_std_sort(built_lib):
         for rng in (1, 3, 100, 1 << 40):
             for pat in range(4):
                 for fan in (0, 3, 8):  # threads: 0 = the sequential introsort loop alone
+                    if n > 500000 and (fan != 8 or rng not in (3, 1 << 40)):
+                        continue  # the largest size only on the fully parallel path
                     assert L.sqh_selftest_sort(n, n * 31 + rng + pat, rng, pat, fan) == 1, (n, rng, pat, fan)
