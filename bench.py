@@ -258,7 +258,7 @@ def main():
         lap("breakpoints (cached host stand-in)")
         cov = g.BPCoverage(bc, bp)
         lap("BPCoverage")
-        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "edges_single_path", "edges_generic_path")}
+        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "edges_single_path", "edges_generic_path")}
         state.update(n_nodes=int(nodes.Chr.shape[0]), n_edges=int(edges.Ind1.shape[0]), n_bp=int(bc.shape[0]), cov_sum=int(cov.sum()),
                      d2h=int(nodes.Chr.nbytes * 3 + nodes.count3.nbytes * 2 + edges.Ind1.nbytes * 3 + edges.Ind1.shape[0] + cov.nbytes))
         return nodes, edges, cov

@@ -27,6 +27,7 @@ struct TileAgg {   // per tile: aggregate, then (after k_tile_scan) exclusive pr
 };
 struct P1Out {
     uint8_t *cls;
+    uint16_t *first_len;      // per record: length of the first kept block of a CLS_CONC record (65535 = too long for 16 bits), else 0
     TileAgg *agg;             // n_tiles
     uint64_t *gate_word;      // n_tiles, zeroed: one-word chain of "1 + index of the last gate-passing record"
     int32_t *cand_rec; uint64_t *cand_key; int32_t *n_cand; int32_t cand_cap;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     __shared__ long long s_prev_carry;
     __shared__ int32_t s_bad, s_lmax, s_minkeep;
     int32_t *s_end = s.end_pos;               // per record: end of the first block if the record updates otherrightmost, else 0
+    uint16_t *s_flen = s.total_len;           // per record: first_len (a record's total_len is only read by its own thread, before)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
     if (tid == 0) { s_tile = atomicAdd(o.ticket, 1); s_bad = 0; s_lmax = 0; s_minkeep = kTile; }
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     for (int j = 0; j < kTileRPT; j++) {
         const int i = j * kTileThreads + tid;
         uint8_t c = 0;
-        int32_t key_end = 0;
+        int32_t key_end = 0, co_len = 0;
         if (i < n && usable && ((s_gate[i >> 5] >> (i & 31)) & 1u)) {
             int word = i >> 5;
             uint32_t m = s_gate[word] & ((1u << (i & 31)) - 1u);
@@ -150,9 +152,10 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
             const int64_t r = rec0 + i;
             const ClassifyOut co = (staged && prev >= rec0) ? classify_record(tb, p, r, prev) : classify_from_hbm(o.desc, r, prev);
             c = co.cls; key_end = (int32_t)(uint32_t)co.other_key;  // (other_key >> 32) - 1 == ref_id of the record
+            co_len = co.first_len;
             if (co.first_len > flen_max) flen_max = co.first_len;
         }
-        if (i < n) { s.cls[i] = c; s_end[i] = key_end; }
+        if (i < n) { s.cls[i] = c; s_end[i] = key_end; s_flen[i] = (uint16_t)(co_len < 65535 ? co_len : 65535); }
         const int chunk = j * kWarpsPerTile + warp;
         npc += __popc(__ballot_sync(full, (c & CLS_PART) != 0));
         ndp += __popc(__ballot_sync(full, (c & (CLS_CONC | CLS_DISPL)) == (CLS_CONC | CLS_DISPL)));
@@ -223,9 +226,11 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
         TileAgg g; g.okmax = run; g.n_pc = (uint32_t)s_pc[0]; g.n_dp = (uint32_t)s_dp[0];
         o.agg[tile] = g;
     }
-    // class bytes out, 4 at a time (rec0 is a multiple of kTile)
-    if (4 * tid + 3 < n) *reinterpret_cast<uint32_t *>(o.cls + rec0 + 4 * tid) = *reinterpret_cast<const uint32_t *>(&s.cls[4 * tid]);
-    else for (int i = 4 * tid; i < n; i++) o.cls[rec0 + i] = s.cls[i];
+    // class bytes and first-block lengths out, 4 records at a time (rec0 is a multiple of kTile)
+    if (4 * tid + 3 < n) {
+        *reinterpret_cast<uint32_t *>(o.cls + rec0 + 4 * tid) = *reinterpret_cast<const uint32_t *>(&s.cls[4 * tid]);
+        *reinterpret_cast<uint2 *>(o.first_len + rec0 + 4 * tid) = *reinterpret_cast<const uint2 *>(&s_flen[4 * tid]);
+    } else for (int i = 4 * tid; i < n; i++) { o.cls[rec0 + i] = s.cls[i]; o.first_len[rec0 + i] = s_flen[i]; }
     __syncthreads();
     if (tid == 0) {
         if (s_lmax > 0) atomicMax(o.lmax, s_lmax);

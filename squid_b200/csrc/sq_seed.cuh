@@ -50,6 +50,7 @@ constexpr int32_t kIslandSlack = 70;  // > thresh*20 + 2*thresh, see island_cut(
 struct SeedInputs {
     DevBatch b;
     const uint8_t *cls;
+    const uint16_t *first_len;      // per CLS_CONC record: length of its first kept block (65535: look at the block arrays)
     const int32_t *gap_rec; int32_t n_gap;  // kept records preceded by a concordant-coverage gap, ascending
     const uint64_t *gap_other;      // per gap record: otherChr/otherrightmost before the record ((chr+1)<<32|pos)
     const int32_t *pc_rec; int32_t n_pc;    // records with CLS_PART, ascending
@@ -88,6 +89,7 @@ struct CoopSerial {  // one lane (CPU stepping harness, tiny islands)
     static SQ_HD int excl_prefix_max(int v, int identity) { (void)v; return identity; }
     static SQ_HD int excl_prefix_sum(int v) { (void)v; return 0; }
     static SQ_HD void add(int32_t *p, int32_t v) { *p += v; }
+    static SQ_HD void add_range(int32_t *diff, int32_t ja, int32_t jb, bool on) { if (on && ja < jb) { diff[ja] += 1; diff[jb] -= 1; } }
     static SQ_HD void sync() {}
 };
 #if defined(__CUDACC__)
@@ -110,6 +112,18 @@ struct CoopWarp {  // 32 lanes of one warp
         return incl - v;
     }
     static __device__ __forceinline__ void add(int32_t *p, int32_t v) { atomicAdd(p, v); }
+    // +1 at diff[ja], -1 at diff[jb] for the lanes with `on` (called by every lane of the warp): sorted input makes
+    // neighbouring lanes hit the same two cells, so one lane per distinct index adds for its whole group
+    static __device__ __forceinline__ void add_range(int32_t *diff, int32_t ja, int32_t jb, bool on) {
+        on = on && ja < jb;
+        const unsigned act = __ballot_sync(0xffffffffu, on);
+        if (!on) return;
+        const int l = threadIdx.x & 31;
+        unsigned m = __match_any_sync(act, ja);
+        if (l == __ffs(m) - 1) atomicAdd(&diff[ja], __popc(m));
+        m = __match_any_sync(act, jb);
+        if (l == __ffs(m) - 1) atomicAdd(&diff[jb], -__popc(m));
+    }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): for the few islands with huge windows
@@ -161,6 +175,18 @@ struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): 
         return base + incl - v;
     }
     static __device__ __forceinline__ void add(int32_t *p, int32_t v) { atomicAdd(p, v); }
+    // +1 at diff[ja], -1 at diff[jb] for the lanes with `on` (called by every lane of the warp): sorted input makes
+    // neighbouring lanes hit the same two cells, so one lane per distinct index adds for its whole group
+    static __device__ __forceinline__ void add_range(int32_t *diff, int32_t ja, int32_t jb, bool on) {
+        on = on && ja < jb;
+        const unsigned act = __ballot_sync(0xffffffffu, on);
+        if (!on) return;
+        const int l = threadIdx.x & 31;
+        unsigned m = __match_any_sync(act, ja);
+        if (l == __ffs(m) - 1) atomicAdd(&diff[ja], __popc(m));
+        m = __match_any_sync(act, jb);
+        if (l == __ffs(m) - 1) atomicAdd(&diff[jb], -__popc(m));
+    }
     static __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 #endif
@@ -180,6 +206,8 @@ struct SeedMachineT {
     SeedState st;
     SeedOp *out; int32_t out_cap;
     int32_t *margin; int32_t margin_cap;
+    int32_t *msearch = nullptr; int32_t msearch_cap = 0;  // fast (shared) memory for a copy of the sorted margins, if the caller has some
+    const int32_t *ms = nullptr;                          // what the searches read: that copy, or margin itself
     int32_t error;  // 1: margin overflow, 2: output overflow
 
     // ---- entry accessors --------------------------------------------------------------------
@@ -187,8 +215,10 @@ struct SeedMachineT {
     SQ_HD bool isDispl(int64_t r) const { return in.cls[r] & CLS_DISPL; }
     SQ_HD int64_t nextCC(int64_t x, int64_t lim) const { while (x < lim && !isCC(x)) x++; return x < lim ? x : lim; }
     SQ_HD int32_t e_chr(int64_t r) const { return in.b.ref_id[r]; }
-    SQ_HD int32_t e_pos(int64_t r) const { return in.b.blk_ref_pos[in.b.blk_off[r]]; }
-    SQ_HD int32_t e_len(int64_t r) const { return in.b.blk_match_ref[in.b.blk_off[r]]; }
+    // the first kept block of a window entry (a CLS_CONC record): its start is the record position unless the record is
+    // displaced, its length sits in the side array phase 1 wrote -- two independent loads instead of blk_off -> block
+    SQ_HD int32_t e_pos(int64_t r) const { return (in.cls[r] & CLS_DISPL) ? in.b.blk_ref_pos[in.b.blk_off[r]] : in.b.pos[r]; }
+    SQ_HD int32_t e_len(int64_t r) const { const uint32_t l = in.first_len[r]; return l != 65535u ? (int32_t)l : in.b.blk_match_ref[in.b.blk_off[r]]; }
     SQ_HD int32_t e_readpos(int64_t r) const { return in.b.blk_read_pos[in.b.blk_off[r]]; }
     SQ_HD bool e_rev(int64_t r) const { return flag_rev(in.b.flag[r]); }
 
@@ -464,12 +494,12 @@ struct SeedMachineT {
     // for each candidate break.
     SQ_HD int32_t m_upper(int32_t nM, int32_t v) const {  // first index with margin > v
         int32_t lo = 0, hi = nM;
-        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (margin[m] <= v) lo = m + 1; else hi = m; }
+        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (ms[m] <= v) lo = m + 1; else hi = m; }
         return lo;
     }
     SQ_HD int32_t m_lower(int32_t nM, int32_t v) const {  // first index with margin >= v
         int32_t lo = 0, hi = nM;
-        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (margin[m] < v) lo = m + 1; else hi = m; }
+        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (ms[m] < v) lo = m + 1; else hi = m; }
         return lo;
     }
     SQ_HD void add_range(int32_t *diff, int32_t ja, int32_t jb) { if (ja < jb) { W::add(&diff[ja], 1); W::add(&diff[jb], -1); } }
@@ -484,7 +514,7 @@ struct SeedMachineT {
         for (int32_t span = nM; span > 0; span >>= 1) {
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if (lo[u] < hi[u]) { const int32_t m = (lo[u] + hi[u]) >> 1; if (margin[m] <= v[u]) lo[u] = m + 1; else hi[u] = m; }
+                if (lo[u] < hi[u]) { const int32_t m = (lo[u] + hi[u]) >> 1; if (ms[m] <= v[u]) lo[u] = m + 1; else hi[u] = m; }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) res[u] = lo[u];
@@ -493,23 +523,25 @@ struct SeedMachineT {
     // (class bits: value after masking with CONC|PART|DISPL), on chromosome chrG
     template <int U>
     SQ_HD void add_span_records(int32_t *diff, int32_t nM, int64_t r0, int64_t stride, int64_t hi, uint8_t want, int32_t chrG) {
-        uint8_t c[U]; uint32_t o[U]; int32_t rc[U];
+        uint8_t c[U]; uint32_t fl[U]; int32_t rc[U], ps[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
+        for (int u = 0; u < U; u++) {  // all loads of all records independent of each other (`want` excludes displaced records)
             const int64_t r = r0 + u * stride;
             const bool inr = r < hi;
-            c[u] = inr ? in.cls[r] : (uint8_t)0; o[u] = inr ? in.b.blk_off[r] : 0u; rc[u] = inr ? in.b.ref_id[r] : -1;
+            c[u] = inr ? in.cls[r] : (uint8_t)0; fl[u] = inr ? in.first_len[r] : 0u; rc[u] = inr ? in.b.ref_id[r] : -1; ps[u] = inr ? in.b.pos[r] : 0;
         }
         bool ok[U]; int32_t v[2 * U], j[2 * U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             ok[u] = (c[u] & (CLS_CONC | CLS_PART | CLS_DISPL)) == want && rc[u] == chrG;
-            const int32_t p0 = ok[u] ? in.b.blk_ref_pos[o[u]] : 0, l = ok[u] ? in.b.blk_match_ref[o[u]] : 0;
+            const int32_t p0 = ps[u];
+            int32_t l = (int32_t)fl[u];
+            if (ok[u] && fl[u] == 65535u) l = in.b.blk_match_ref[in.b.blk_off[r0 + u * stride]];
             v[2 * u] = p0 + kSeedThresh; v[2 * u + 1] = p0 + l - kSeedThresh;
         }
         m_upper_n<2 * U>(nM, v, j);
 #pragma unroll
-        for (int u = 0; u < U; u++) if (ok[u]) add_range(diff, j[2 * u], j[2 * u + 1]);
+        for (int u = 0; u < U; u++) W::add_range(diff, j[2 * u], j[2 * u + 1], ok[u]);
     }
     SQ_HD void scan_inplace(int32_t *a, int32_t n) {
         W::sync();
@@ -530,7 +562,7 @@ struct SeedMachineT {
         W::sync();
         for (int32_t i = W::lane(); i <= nM; i += W::size()) { t_pl[i] = 0; t_pr[i] = 0; t_cov[i] = 0; t_rest[i] = 0; }
         for (int32_t i = W::lane(); i < nM; i += W::size()) {  // srsupport: margins within +-thresh (:445-448)
-            const int32_t brk = margin[i];
+            const int32_t brk = ms[i];
             t_sr[i] = m_lower(nM, brk + thresh) - m_upper(nM, brk - thresh);
         }
         W::sync();
@@ -540,7 +572,7 @@ struct SeedMachineT {
             else add_range(t_pr, m_upper(nM, p0 - RL), m_lower(nM, p0));                // pos-ReadLen < b < pos   (:452)
             if (D[k].chr == chrG) add_span(t_cov, nM, p0, p1);                            // :462-464
         }
-        const int32_t bmin = margin[0], bmax = margin[nM - 1];
+        const int32_t bmin = ms[0], bmax = ms[nM - 1];
         const int32_t pmin = bmin + thresh - in.lmax, pmax = bmax - thresh;  // block starts that can span some break
         if (st.offCC < rg) {  // ConcordantCluster window (:457-461)
             const int64_t lo = lb_pos(st.offCC, rg, chrG, pmin), hi = lb_pos(lo, rg, chrG, pmax);
@@ -550,9 +582,15 @@ struct SeedMachineT {
         }
         if (st.offPC < szPC) {  // PartialAlignCluster window (:465-469)
             const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, pmin), hi = lb_pc_pos(lo, szPC, chrG, pmax);
-            for (int32_t i = lo + W::lane(); i < hi; i += W::size()) {
-                const int64_t r = in.pc_rec[i];
-                if (!isDispl(r) && in.b.ref_id[r] == chrG) { const int32_t p0 = e_pos(r); add_span(t_cov, nM, p0, p0 + e_len(r)); }
+            for (int32_t base = lo; base < hi; base += W::size()) {
+                const int32_t i = base + W::lane();
+                bool on = false;
+                int32_t ja = 0, jb = 0;
+                if (i < hi) {
+                    const int64_t r = in.pc_rec[i];
+                    if (!isDispl(r) && in.b.ref_id[r] == chrG) { on = true; const int32_t p0 = e_pos(r); ja = m_upper(nM, p0 + kSeedThresh); jb = m_upper(nM, p0 + e_len(r) - kSeedThresh); }
+                }
+                W::add_range(t_cov, ja, jb, on);
             }
         }
         {   // displaced entries of either window
@@ -574,9 +612,15 @@ struct SeedMachineT {
             while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
             int32_t lo2 = lo, hi2 = in.n_rest;
             while (lo2 < hi2) { int32_t m = (lo2 + hi2) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < pmax)) lo2 = m + 1; else hi2 = m; }
-            for (int32_t k = lo + W::lane(); k < lo2; k += W::size()) {
-                const RestBlock &e = in.rest[k];
-                if (e.rec < rg) add_span(t_rest, nM, e.pos, e.end);
+            for (int32_t base = lo; base < lo2; base += W::size()) {
+                const int32_t k = base + W::lane();
+                bool on = false;
+                int32_t ja = 0, jb = 0;
+                if (k < lo2) {
+                    const RestBlock e = in.rest[k];
+                    if (e.rec < rg) { on = true; ja = m_upper(nM, e.pos + kSeedThresh); jb = m_upper(nM, e.end - kSeedThresh); }
+                }
+                W::add_range(t_rest, ja, jb, on);
             }
         }
         scan_inplace(t_pl, nM); scan_inplace(t_pr, nM); scan_inplace(t_cov, nM); scan_inplace(t_rest, nM);
@@ -602,12 +646,12 @@ struct SeedMachineT {
         int32_t mx = NEG;
         int64_t x = st.offCC;
         while (x < rg) {
-            uint8_t c[U]; uint32_t o[U]; int32_t rc[U];
+            uint8_t c[U]; uint32_t fl[U]; int32_t rc[U], ps[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {  // entry index inside the chunk: u*size + lane (stream order)
                 const int64_t r = x + u * W::size() + W::lane();
                 const bool inr = r < rg;
-                c[u] = inr ? in.cls[r] : (uint8_t)0; o[u] = inr ? in.b.blk_off[r] : 0u; rc[u] = inr ? in.b.ref_id[r] : -1;
+                c[u] = inr ? in.cls[r] : (uint8_t)0; fl[u] = inr ? in.first_len[r] : 0u; rc[u] = inr ? in.b.ref_id[r] : -1; ps[u] = inr ? in.b.pos[r] : 0;
             }
             int32_t p1[U]; bool cc[U], ok[U];
             int fb = chunk;
@@ -616,8 +660,10 @@ struct SeedMachineT {
                 cc[u] = (c[u] & (CLS_CONC | CLS_PART)) == CLS_CONC;
                 ok[u] = false; p1[u] = NEG;
                 if (cc[u]) {
-                    const int32_t p0 = in.b.blk_ref_pos[o[u]];
-                    p1[u] = p0 + in.b.blk_match_ref[o[u]];
+                    const int64_t r = x + u * W::size() + W::lane();
+                    const bool plain = !(c[u] & CLS_DISPL) && fl[u] != 65535u;  // else: through the block arrays
+                    const int32_t p0 = plain ? ps[u] : e_pos(r);
+                    p1[u] = p0 + (plain ? (int32_t)fl[u] : e_len(r));
                     ok[u] = walk_ok(first_walk, chrG, dc, rc[u], p0, p1[u]);
                     if (!ok[u] && u * W::size() + W::lane() < fb) fb = u * W::size() + W::lane();
                 }
@@ -821,13 +867,19 @@ struct SeedMachineT {
             SQ_PROF_ADD(2);
             sort_margins(nM);
             if (error) return;
+            ms = margin;
+            if (nM <= msearch_cap) {  // the sorted margins are searched twice per window entry: keep them close
+                for (int32_t i = W::lane(); i < nM; i += W::size()) msearch[i] = margin[i];
+                W::sync();
+                ms = msearch;
+            }
             SQ_PROF_ADD(3);
             tabulate_breaks(nM, ds, de, chrG, in.D[grp.ds].pos, rg, szPC);
             SQ_PROF_ADD(4);
             const int32_t *t_sr = margin + mcap(), *t_pl = margin + 2 * mcap(), *t_pr = margin + 3 * mcap(), *t_cov = margin + 4 * mcap(), *t_rest = margin + 5 * mcap();
             int32_t lastCurser = -1, lastSupport = 0;
             for (int32_t ib = 0; ib < nM;) {
-                const int32_t brk = margin[ib];
+                const int32_t brk = ms[ib];
                 if (st.have_back && st.backChr == chrG && brk - st.backEnd < thresh * 20) { ib++; continue; }
                 const int32_t sr = t_sr[ib], pl = t_pl[ib], pr = t_pr[ib];
                 if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
@@ -857,7 +909,7 @@ struct SeedMachineT {
                     }
                 }
                 int32_t j = ib;
-                while (j < nM && margin[j] == brk) j++;
+                while (j < nM && ms[j] == brk) j++;
                 if (j < nM) ib = j; else break;
             }
             if (lastCurser != -1 && (!isClusternSplit || st.backEnd != lastCurser)) {  // :505-516

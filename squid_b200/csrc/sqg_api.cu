@@ -8,6 +8,7 @@
 //   depth_edges: per-segment depth + read-to-segment assignment + raw edges        (phase-2 stream pass)
 //   edge_sort : radix sort by packed key + run-length reduce
 //   coverage  : breakpoint coverage with the reference's indBP lag                 (phase-3 stream pass)
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -189,19 +190,26 @@ __global__ void k_gather_i32(const int32_t *src, const int32_t *idx, int32_t n, 
     if (i < n) out[i] = src[idx[i]];
 }
 constexpr int kSeedBlock = 512;        // threads per block of the seed kernels
-constexpr int kHeavySpan = 1 << 14;    // islands spanning more records than this get a whole block instead of a warp
+constexpr int kHeavySpan = 1 << 14;
+// Islands spanning more records than this would get a thread-block cluster (k_seed_giants).  Measured on the benchmark the
+// cluster policy is correct (GPU tests force it with SQG_GIANT_SPAN) but not yet faster than one 512-thread block: 11 islands of
+// 0.4-0.9 M records took 16 ms in clusters of 8 against 11 ms in single blocks (cluster barriers inside the chunked window
+// walks, 8x redundant scalar control).  Off by default until the walks are restructured around fewer barriers.
+constexpr int kGiantSpan = 0x7fffffff;
+constexpr int32_t kSeedMarginSmem = 8192;  // ints of shared memory per block for the sorted margins (32 KB)    // islands spanning more records than this get a whole block instead of a warp
 struct IsHeavyOp {
     const int32_t *span; const int32_t *n_prefix; bool want_heavy;
     __device__ bool operator()(int32_t i) const { return i >= *n_prefix && ((span[i] > kHeavySpan) == want_heavy); }
 };
 template <class W>
 __device__ __forceinline__ void seed_one_island(const SeedInputs &in, int32_t i, bool inherited, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops,
-                                                const int64_t *off_mar, SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err, int32_t *n_out_ret) {
+                                                const int64_t *off_mar, SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err, int32_t *n_out_ret, int32_t *fast, int32_t fast_cap) {
     SeedMachineT<W> sm;
     sm.in = in;
     const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
     sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
     sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
+    sm.msearch = fast; sm.msearch_cap = fast_cap;
 #ifdef SQ_SEED_PROF
     long long t0_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0_));
 #endif
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(kSeedBlock) k_seed_prefix(SeedInputs in, const
     int32_t i = 0;
     for (; i < n_isl; i++) {
         int32_t emitted = 0;
-        seed_one_island<CoopBlock>(in, i, false, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, &emitted);
+        seed_one_island<CoopBlock>(in, i, false, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, &emitted, nullptr, 0);
         if (emitted > 0) { i++; break; }
     }
     if (threadIdx.x == 0) *n_prefix = i;
@@ -234,13 +242,61 @@ __global__ void __launch_bounds__(kSeedBlock) k_seed_prefix(SeedInputs in, const
 __global__ void __launch_bounds__(kSeedBlock, 2) k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar,
                                                            SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err,
                                                            const int32_t *heavy, int32_t n_heavy, const int32_t *light, int32_t n_light) {
+    __shared__ int32_t s_margins[kSeedMarginSmem];  // sorted margins of the island being processed (whole block, or one slice per warp)
     if ((int32_t)blockIdx.x < n_heavy) {
-        seed_one_island<CoopBlock>(in, heavy[blockIdx.x], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr);
+        seed_one_island<CoopBlock>(in, heavy[blockIdx.x], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr, s_margins, kSeedMarginSmem);
         return;
     }
     const int32_t k = ((int32_t)blockIdx.x - n_heavy) * (kSeedBlock / 32) + (threadIdx.x >> 5);
     if (k >= n_light) return;
-    seed_one_island<CoopWarp>(in, light[k], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr);
+    constexpr int32_t per_warp = kSeedMarginSmem / (kSeedBlock / 32);
+    seed_one_island<CoopWarp>(in, light[k], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr, s_margins + (threadIdx.x >> 5) * per_warp, per_warp);
+}
+
+// A thread-block cluster stepping ONE island together: the few islands that span hundreds of thousands of records (highly
+// expressed genes) are bound by what a single SM can issue, so their window scans are spread over kGiantCluster SMs.  Same
+// contract as CoopBlock: every thread keeps identical scalar state; partial results cross CTAs through distributed shared
+// memory, and W::sync() is a cluster barrier (release/acquire at cluster scope, which also orders the scratch in HBM).
+namespace cg = cooperative_groups;
+constexpr int kGiantCluster = 8;
+struct CoopCluster {
+    template <int OP> static __device__ __forceinline__ int combine(int a, int b) { return OP == 0 ? a + b : (OP == 1 ? (a > b ? a : b) : (a < b ? a : b)); }
+    // value of every CTA -> all CTAs; `upto_self`: combine only the CTAs ranked before this one
+    template <int OP> static __device__ __forceinline__ int exchange(int block_value, int identity, bool before_self) {
+        __shared__ int slot;
+        cg::cluster_group cl = cg::this_cluster();
+        if (threadIdx.x == 0) slot = block_value;
+        cl.sync();
+        int r = identity;
+        const int n = before_self ? (int)cl.block_rank() : (int)cl.num_blocks();
+        for (int k = 0; k < n; k++) r = combine<OP>(r, *cl.map_shared_rank(&slot, k));
+        cl.sync();
+        return r;
+    }
+    static __device__ __forceinline__ int lane() { return (int)cg::this_cluster().block_rank() * blockDim.x + threadIdx.x; }
+    static __device__ __forceinline__ int size() { return (int)cg::this_cluster().num_blocks() * blockDim.x; }
+    static __device__ __forceinline__ int sum(int v) { return exchange<0>(CoopBlock::sum(v), 0, false); }
+    static __device__ __forceinline__ int max(int v) { return exchange<1>(CoopBlock::max(v), -2147483647 - 1, false); }
+    static __device__ __forceinline__ int min(int v) { return exchange<2>(CoopBlock::min(v), 2147483647, false); }
+    static __device__ __forceinline__ int excl_prefix_max(int v, int identity) {
+        const int e = CoopBlock::excl_prefix_max(v, identity), t = CoopBlock::max(v);
+        const int base = exchange<1>(t, identity, true);
+        return e > base ? e : base;
+    }
+    static __device__ __forceinline__ int excl_prefix_sum(int v) {
+        const int e = CoopBlock::excl_prefix_sum(v), t = CoopBlock::sum(v);
+        return exchange<0>(t, 0, true) + e;
+    }
+    static __device__ __forceinline__ void add(int32_t *p, int32_t v) { atomicAdd(p, v); }
+    static __device__ __forceinline__ void add_range(int32_t *diff, int32_t ja, int32_t jb, bool on) { CoopBlock::add_range(diff, ja, jb, on); }
+    static __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+};
+__global__ void __cluster_dims__(kGiantCluster, 1, 1) __launch_bounds__(kSeedBlock, 2)
+k_seed_giants(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar, SeedOp *ops, int32_t *margin, int32_t *n_out,
+              int32_t *g_done, int32_t *err, const int32_t *giant, int32_t n_giant) {
+    const int32_t gi = (int32_t)blockIdx.x / kGiantCluster;
+    if (gi >= n_giant) return;
+    seed_one_island<CoopCluster>(in, giant[gi], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,6 +568,10 @@ int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int
     if (!ctx) return SQG_ENOMEM;
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the cluster kernel must get its SMs before the block kernel fills them
+    if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
     ctx->params.min_mapq = cfg->min_mapq; ctx->params.max_lowphred_len = cfg->max_lowphred_len;
     ctx->params.concord_dist_pos = cfg->concord_dist_pos; ctx->params.concord_dist_idx = cfg->concord_dist_idx;
     ctx->params.read_len = cfg->read_len; ctx->params.n_ref = n_ref;
@@ -540,7 +600,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
-    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
+    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_slow.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
@@ -548,6 +608,9 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->h_w.release(); ctx->h_chimblk.release(); ctx->h_heads.release(); ctx->h_seeds.release();
     for (auto &kv : ctx->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
     cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 
@@ -568,6 +631,7 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     const std::string n(name);
     if (n == "islands") return ctx->n_islands;
     if (n == "heavy_islands") return ctx->n_heavy;
+    if (n == "giant_islands") return ctx->n_giant;
     if (n == "cov_chain_fallback") return ctx->cov_chain_fallback;
     if (n == "cov_chain_chunks") return ctx->cov_chain_chunks;
     if (n == "gap_records") return ctx->n_gap;
@@ -697,7 +761,7 @@ static int run_classify(sqg_ctx *ctx) {
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
     PHASE_BEGIN("classify");
-    CK(ctx->d_cls.ensure(n + 4)); CK(ctx->d_scratch32.ensure(n + 1));
+    CK(ctx->d_cls.ensure(n + 4)); CK(ctx->d_flen.ensure(n + 4)); CK(ctx->d_scratch32.ensure(n + 1));
     CK(ctx->d_counters.ensure(32)); CK(ctx->h_counters.ensure(32));
     ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n;
     if (n > 0) {
@@ -709,7 +773,7 @@ static int run_classify(sqg_ctx *ctx) {
             cand_cap = std::min<int64_t>(cand_cap, n + 1);
             CK(ctx->d_cand_key.ensure(cand_cap));
             P1Out o;
-            o.cls = ctx->d_cls.p; o.agg = ctx->d_tileagg.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
+            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
             o.cand_rec = ctx->d_scratch32.p; o.cand_key = ctx->d_cand_key.p; o.cand_cap = (int32_t)cand_cap;
             // counters: [0..1] totals n_gap, n_pc, n_dp (int32) | [2] first_kept | [3] lmax | [4] n_cand, ticket (int32) | [20] validation flags
             CK(cudaMemsetAsync(ctx->d_counters.p, 0, 5 * sizeof(int64_t), ctx->stream));
@@ -1040,7 +1104,7 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     }
     // the state machine, island-parallel
     SeedInputs in;
-    in.b = b; in.cls = ctx->d_cls.p; in.gap_other = ctx->d_other.p;
+    in.b = b; in.cls = ctx->d_cls.p; in.first_len = ctx->d_flen.p; in.gap_other = ctx->d_other.p;
     in.gap_rec = ctx->d_gap.p; in.n_gap = ctx->n_gap; in.pc_rec = ctx->d_pc.p; in.n_pc = ctx->n_pc;
     in.dp_rec = ctx->d_dp.p; in.n_dp = ctx->n_dp; in.lmax = ctx->lmax; in.n_rec = n;
     in.D = ctx->d_disc.p; in.nD = nD; in.G = ctx->d_groups.p; in.nG = nG; in.trigger = ctx->d_trigger.p;
@@ -1113,12 +1177,35 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     long long *d_prof = nullptr;
     if (getenv("SQG_SEED_PROF_OUT")) { cudaMalloc(&d_prof, (size_t)n_isl * 12 * 8); cudaMemset(d_prof, 0, (size_t)n_isl * 12 * 8); cudaDeviceSynchronize(); in.prof_out = d_prof; }
 #endif
-    if (n_heavy + n_light > 0) {
-        k_seed_islands<<<(unsigned)(n_heavy + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, 0, ctx->stream>>>(in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
-               ctx->d_ops.p, ctx->d_margin.p, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, ctx->d_heavy.p, n_heavy, ctx->d_light.p, n_light);
+    // the longest islands (sorted first) go to thread-block clusters on a second stream, concurrently with the rest
+    int32_t n_giant = 0;
+    if (n_heavy > 0) {
+        int32_t hs[64];
+        const int32_t m = std::min(n_heavy, 64);
+        if (n_heavy > 1) {  // (a single block-sized island stays with the block kernel)
+            CK(cudaMemcpyAsync(hs, ctx->d_cap_ops.p + n_heavy, m * 4, cudaMemcpyDeviceToHost, ctx->stream));  // spans, longest first
+            CK(cudaStreamSynchronize(ctx->stream));
+            const int64_t giant_span = getenv("SQG_GIANT_SPAN") ? atoll(getenv("SQG_GIANT_SPAN")) : (int64_t)kGiantSpan;  // env: test hook
+            while (n_giant < m && hs[n_giant] > giant_span) n_giant++;
+        }
+    }
+    ctx->n_giant = n_giant;
+    if (n_giant > 0) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        k_seed_giants<<<(unsigned)(n_giant * kGiantCluster), kSeedBlock, 0, ctx->stream2>>>(in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
+                                                                                         ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, ctx->d_heavy.p, n_giant);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    }
+    if (n_heavy - n_giant + n_light > 0) {
+        k_seed_islands<<<(unsigned)(n_heavy - n_giant + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, 0, ctx->stream>>>(in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
+               ctx->d_ops.p, ctx->d_margin.p, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, ctx->d_heavy.p + n_giant, n_heavy - n_giant, ctx->d_light.p, n_light);
         ctx->launches++;
         CK(cudaGetLastError());
     }
+    if (n_giant > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     PHASE_END("seed");
     lap("seed: enqueue");
 #ifdef SQ_SEED_PROF

@@ -95,7 +95,8 @@ struct PhaseTimer {
 
 struct sqg_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the cluster kernel of the seed machine, forked / joined with events
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     sq::Params params{};
     std::vector<int32_t> ref_len;
@@ -113,6 +114,7 @@ struct sqg_ctx {
 
     // classify products
     sq::DBuf<uint8_t> d_cls;
+    sq::DBuf<uint16_t> d_flen;      // first-block length of every CLS_CONC record (seed machine windows)
     sq::DBuf<uint64_t> d_other;     // running otherChr/otherrightmost key at each coverage-gap record
     sq::DBuf<uint64_t> d_chain64;   // look-back chains of the stream kernels
     sq::DBuf<uint32_t> d_chain32;
@@ -152,7 +154,7 @@ struct sqg_ctx {
     sq::HBuf<sq::SeedOp> h_ops;
     sq::DBuf<uint8_t> d_cutflag;
     sq::DBuf<int32_t> d_isl, d_cap_ops, d_cap_mar, d_isl_nout, d_isl_gdone, d_span, d_heavy, d_light;
-    int32_t n_heavy = 0;
+    int32_t n_heavy = 0, n_giant = 0;
     bool cov_chain_fallback = false;
     int64_t n_sensitive = 0, n_raw_edges = 0;
     sq::DBuf<int64_t> d_off_ops, d_off_mar;

@@ -69,6 +69,7 @@ int main(int argc, char **argv) {
 
     // ---- classify + scans ----
     std::vector<uint8_t> cls(n);
+    std::vector<uint16_t> first_len(n, 0);
     std::vector<uint64_t> other_excl(n);
     {
         int64_t prev = -1;
@@ -76,6 +77,7 @@ int main(int argc, char **argv) {
         for (int64_t r = 0; r < n; r++) {
             ClassifyOut o = classify_record(b, p, r, prev);
             cls[r] = o.cls;
+            first_len[r] = (uint16_t)(o.first_len < 65535 ? o.first_len : 65535);
             other_excl[r] = run;
             if (o.other_key > run) run = o.other_key;
             if (o.cls & CLS_GATE) prev = r;
@@ -123,7 +125,7 @@ int main(int argc, char **argv) {
 
     // ---- seed machine ----
     SeedMachine sm;
-    sm.in.b = b; sm.in.cls = cls.data(); sm.in.gap_other = gap_other.data();
+    sm.in.b = b; sm.in.cls = cls.data(); sm.in.first_len = first_len.data(); sm.in.gap_other = gap_other.data();
     sm.in.gap_rec = gap.data(); sm.in.n_gap = (int32_t)gap.size();
     sm.in.pc_rec = pcrec.data(); sm.in.n_pc = (int32_t)pcrec.size();
     sm.in.D = pre.disc.data(); sm.in.nD = nD; sm.in.G = pre.groups.data(); sm.in.nG = nG;

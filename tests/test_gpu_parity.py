@@ -25,6 +25,8 @@ def test_hot_path_matches_reference(tmp_path, built_lib, ref_oracle, monkeypatch
     from squid_b200 import synth
     if seed in (17, 1003):  # force the chunked (multi-threaded) read loop of the chimeric pre-pass on a small input
         monkeypatch.setenv("SQH_PREPASS_CHUNKS", "13")
+    if seed in (1020, 1022):  # every block-sized island through the thread-block-cluster policy of the seed machine
+        monkeypatch.setenv("SQG_GIANT_SPAN", "1000")
     rl = synth.GRCH38_LEN if ref_len == "grch38" else ref_len
     cp, hp, conc, chim, info = common.write_case(str(tmp_path), n_pairs, seed, disc, rl, **kw)
     ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
@@ -34,6 +36,8 @@ def test_hot_path_matches_reference(tmp_path, built_lib, ref_oracle, monkeypatch
     assert got["support"] == pyref.support_map(ref)
     g = got["graph"]
     assert g.launch_count() > 0
+    if seed == 1020:
+        assert g.stat("giant_islands") > 0
     for ph in ("classify", "seed", "depth_edges", "edge_sort", "coverage"):
         assert g.phase_ms(ph) >= 0.0
 
