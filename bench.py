@@ -171,7 +171,12 @@ def main():
     build.build(verbose=False)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    real_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout: keep stdout clean for the one JSON line
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     P = args.pairs
@@ -233,17 +238,22 @@ def main():
             dk, dw, n = C.c_void_p(), C.c_void_p(), C.c_int64()
             g._ck(g.L.sqg_edges_device_table(g._h, C.byref(dk), C.byref(dw), C.byref(n)))
             m = n.value
-            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([m], dtype=torch.int64, device=dev))
-            mx = int(max(int(s.item()) for s in sizes))
-            keys = torch.zeros(mx, dtype=torch.int64, device=dev); ws = torch.zeros(mx, dtype=torch.int32, device=dev)
+            # one tiny all_reduce for the padded size, one all_gather of [count | keys | weights] per rank
+            mx_t = torch.tensor([m], dtype=torch.int64, device=dev)
+            dist.all_reduce(mx_t, op=dist.ReduceOp.MAX)
+            mx = int(mx_t.item())
+            buf = torch.zeros(1 + 2 * mx, dtype=torch.int64, device=dev)
+            buf[0] = m
             if m:
-                keys[:m] = _dev_view(dk.value, m, torch.int64, dev)
-                ws[:m] = _dev_view(dw.value, m, torch.int32, dev)
-            gk = [torch.empty_like(keys) for _ in range(world)]; gw = [torch.empty_like(ws) for _ in range(world)]
-            dist.all_gather(gk, keys); dist.all_gather(gw, ws)
+                buf[1:1 + m] = _dev_view(dk.value, m, torch.int64, dev)
+                buf[1 + mx:1 + mx + m] = _dev_view(dw.value, m, torch.int32, dev).to(torch.int64)
+            allb = torch.empty(world * (1 + 2 * mx), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allb, buf)
+            allb = allb.view(world, 1 + 2 * mx)
+            cnts = allb[:, 0].tolist()
             # node indices are shard-local in this weak-scaling run; the merge-reduce cost is what is exercised
-            allk = torch.cat([gk[r][: int(sizes[r].item())] for r in range(world)]); allw = torch.cat([gw[r][: int(sizes[r].item())] for r in range(world)])
+            allk = torch.cat([allb[r, 1:1 + int(cnts[r])] for r in range(world)]); allw = torch.cat([allb[r, 1 + mx:1 + mx + int(cnts[r])] for r in range(world)]).to(torch.int32)
+            torch.cuda.current_stream().synchronize()  # the library works on its own stream
             i1, i2, hd, w, ne = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
             g._ck(g.L.sqg_merge_edge_tables(g._h, allk.data_ptr(), allw.data_ptr(), int(allk.shape[0]), C.byref(i1), C.byref(i2), C.byref(hd), C.byref(w), C.byref(ne)))
             state["merged_edges"] = ne.value
@@ -255,7 +265,7 @@ def main():
             state["bps"] = bps_from_graph(nodes, edges)
             state["bps_standin_ms"] = 1e3 * (time.perf_counter() - t_b)
         bc, bp = state["bps"]
-        lap("breakpoints (cached host stand-in)")
+        lap("edge exchange + breakpoints (cached host stand-in)" if world > 1 else "breakpoints (cached host stand-in)")
         cov = g.BPCoverage(bc, bp)
         lap("BPCoverage")
         state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "edges_single_path", "edges_generic_path")}
@@ -299,6 +309,8 @@ def main():
 
     sec, phases, clocks, launches = timed(True, args.steps, args.warmup)
     timeline = dict(state["timeline_ms"])
+    if world > 1:
+        print("[rank %d] resident step %.1f ms; host timeline %s" % (rank, 1e3 * sec, {k: round(v, 1) for k, v in timeline.items()}), file=sys.stderr, flush=True)
     sec_e2e, phases_e2e, _, _ = timed(False, max(1, min(args.steps, 3)), 1)
 
     # ---- roofline of the dominant stream phase --------------------------------------------------------------
@@ -342,7 +354,10 @@ def main():
             "phases_ms": phases, "host_timeline_ms": timeline, "bps_standin_ms_outside_timed_region": state.get("bps_standin_ms"), "phases_ms_e2e": phases_e2e, "stats": state.get("stats"),
             "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches), "gen_s": t_gen,
         }
-        print(json.dumps(out))
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
     g.close()
     if world > 1:
         dist.destroy_process_group()

@@ -477,24 +477,35 @@ struct IsChainCutOp {
     const int64_t *r0;
     __device__ bool operator()(int32_t k) const { return k == 0 || r0[k] - r0[k - 1] > kChainGap; }
 };
-__global__ void k_cov_chain_check(const int32_t *chunk_start, int32_t n_chunks, const int64_t *r0, const int64_t *t, int32_t *fail) {
+// A chunk was replayed with some incoming t (`used`, -1 = "the chain has caught up": irrelevant).  Given the current t of
+// its predecessor it needed `need` = t[k-1] if that reaches r0 of the chunk's first breakpoint, else -1.  Chunks whose used
+// and needed carries differ are flagged for another replay; *n_redo counts them.
+__global__ void k_cov_chain_check(const int32_t *chunk_start, int32_t n_chunks, const int64_t *r0, const int64_t *t, const int64_t *used, int64_t *need, int32_t *n_redo) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= 0 || i >= n_chunks) return;
-    const int32_t k = chunk_start[i];
-    if (!(t[k - 1] < r0[k])) *fail = 1;
+    if (i >= n_chunks) return;
+    int64_t nd = -1;
+    if (i > 0) { const int32_t k = chunk_start[i]; if (!(t[k - 1] < r0[k])) nd = t[k - 1]; }
+    need[i] = nd;
+    if (nd != used[i]) atomicAdd(n_redo, 1);
 }
 __global__ void k_cov_chain(const uint64_t *qkey, int64_t nq, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K_all, int32_t dist, const int64_t *r0, int64_t *t,
-                            const int32_t *chunk_start, int32_t n_chunks) {
+                            const int32_t *chunk_start, int32_t n_chunks, int64_t *used, const int64_t *need) {
     const int lane = threadIdx.x & 31;
     constexpr int W = 4;       // keys per lane
     int64_t k_begin = 0, K = K_all;
+    int64_t tp = -1;
     if (chunk_start) {
         const int32_t ci = (int32_t)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
         if (ci >= n_chunks) return;
+        if (need) {  // a re-run: only the chunks whose incoming t changed, starting from it
+            if (need[ci] == used[ci]) return;
+            tp = need[ci];
+        }
+        __syncwarp();
+        if (lane == 0) used[ci] = tp;
         k_begin = chunk_start[ci];
         K = ci + 1 < n_chunks ? chunk_start[ci + 1] : K_all;
     } else if (blockIdx.x != 0 || threadIdx.x >= 32) return;
-    int64_t tp = -1;
     int64_t wbase = -1024;     // ranks [wbase, wbase + 32*W) are held in wkey[]
     uint64_t wkey[W];
     for (int q = 0; q < W; q++) wkey[q] = 0;
@@ -601,7 +612,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
-    ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_slow.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
+    ctx->d_chain_used.release(); ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_slow.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
     ctx->h_chr.release(); ctx->h_pos.release(); ctx->h_len.release(); ctx->h_cnt3.release(); ctx->h_sum3.release(); ctx->h_ind1.release(); ctx->h_ind2.release();
@@ -1422,15 +1433,26 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
             CK(cudaStreamSynchronize(ctx->stream));
             const int32_t n_chunks = *(int32_t *)(ctx->h_counters.p + 14);
             ctx->launches += 2;
-            LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, chunks, n_chunks);
-            CK(cudaMemsetAsync(ctx->d_counters.p + 12, 0, sizeof(int64_t), ctx->stream));
-            LAUNCH(k_cov_chain_check, blocks_for(n_chunks), kThreads, chunks, n_chunks, ctx->d_r0.p, ctx->d_t.p, (int32_t *)(ctx->d_counters.p + 12));
-            CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(ctx->d_chain_used.ensure(2 * (size_t)n_chunks + 2));
+            int64_t *used = ctx->d_chain_used.p, *need = ctx->d_chain_used.p + n_chunks + 1;
+            LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, chunks, n_chunks,
+                   used, (const int64_t *)nullptr);
+            // chunks whose predecessor's chain runs into them are replayed from its t; a few rounds settle runs of such chunks
             ctx->cov_chain_chunks = n_chunks;
-            if (*(int32_t *)(ctx->h_counters.p + 12) != 0) {
+            bool settled = false;
+            for (int round = 0; round < 16 && !settled; round++) {
+                CK(cudaMemsetAsync(ctx->d_counters.p + 12, 0, sizeof(int64_t), ctx->stream));
+                LAUNCH(k_cov_chain_check, blocks_for(n_chunks), kThreads, chunks, n_chunks, ctx->d_r0.p, ctx->d_t.p, used, need, (int32_t *)(ctx->d_counters.p + 12));
+                CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                if (*(int32_t *)(ctx->h_counters.p + 12) == 0) { settled = true; break; }
+                LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, chunks, n_chunks,
+                       used, (const int64_t *)need);
+            }
+            if (!settled) {  // a lagging chain through very many chunks: literal replay of the whole list by one warp
                 ctx->cov_chain_chunks = 1;
-                LAUNCH(k_cov_chain, 1, 32, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (const int32_t *)nullptr, 0);
+                LAUNCH(k_cov_chain, 1, 32, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (const int32_t *)nullptr, 0,
+                       (int64_t *)nullptr, (const int64_t *)nullptr);
             }
         }
     }

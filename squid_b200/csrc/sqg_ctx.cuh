@@ -183,7 +183,7 @@ struct sqg_ctx {
     sq::DBuf<uint64_t> d_bpkey, d_covM, d_qkey;
     sq::DBuf<int32_t> d_chunks;
     int32_t cov_chain_chunks = 0;
-    sq::DBuf<int64_t> d_r0, d_t;
+    sq::DBuf<int64_t> d_r0, d_t, d_chain_used;
     sq::DBuf<int32_t> d_cov, d_bpchr, d_bppos, d_qend;
     sq::DBuf<sq::CovTile> d_covtile;
 

@@ -153,3 +153,39 @@ def test_degenerate_batches(tmp_path, built_lib):
         g.load_concordant(bad); g.load_chimeric(api.ChimericReads(case.chimeric.a))
         with pytest.raises(api.SquidB200Error):
             g.BuildNode_STAR()
+
+
+def test_dense_breakpoints_lagging_chain(tmp_path, built_lib):
+    """Tens of thousands of breakpoints packed into expressed regions: indBP lags far behind the stream (one breakpoint per
+    qualifying record, SegmentGraph.cpp:3157-3158), so the max-plus shortcut fails and the chunked literal chain has to repair
+    chunks that run into each other.  Checked against the literal chain of the CPU stepping harness."""
+    import os
+    import subprocess
+    from squid_b200 import api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    emul = os.path.join(root, "tests", "emul", "_build", "emul_gpu_test")
+    os.makedirs(os.path.dirname(emul), exist_ok=True)
+    srcs = ["tests/emul/emul_main.cpp", "squid_b200/csrc/host/readrec.cpp", "squid_b200/csrc/host/chimeric.cpp", "squid_b200/csrc/host/prepass.cpp"]
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", "-I", "include", "-I", "squid_b200/csrc", "-o", emul] + srcs + ["-lpthread"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    cp, hp, *_ = common.write_case(str(tmp_path), 60000, 23, 0.02, [3000000, 2000000, 500000, 16569], n_genes=40)
+    case = api.HostCase(cp, hp)
+    a = case.batch.a
+    keys = np.unique((a["ref_id"].astype(np.int64) << 32) | a["pos"].astype(np.int64))
+    keys = keys[keys >= 0]
+    # every distinct record position, plus runs of consecutive positions behind each of them: very dense lists
+    dense = np.unique(np.concatenate([keys, keys + 1, keys + 2, keys + 37]))
+    bp = np.stack([(dense >> 32).astype(np.int32), (dense & 0xffffffff).astype(np.int32)], axis=1)
+    bp = bp[bp[:, 1] < np.asarray(case.ref_len)[bp[:, 0]]]
+    assert bp.shape[0] > 20000
+    bp.astype(np.int32).tofile(str(tmp_path / "bps.bin"))
+    out = tmp_path / "emul"
+    out.mkdir()
+    r = subprocess.run([emul, cp, hp, str(out), str(tmp_path / "bps.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = np.fromfile(str(out / "cov_i32.bin"), dtype=np.int32)
+    g = api.SegmentGraph(case.config, case.ref_len)
+    g.load_concordant(case.batch); g.load_chimeric(case.chimeric)
+    got = g.BPCoverage(bp[:, 0], bp[:, 1])
+    assert g.stat("cov_chain_fallback") == 1  # the shortcut must have failed, else this test does not test the chain
+    assert np.array_equal(got, want)
