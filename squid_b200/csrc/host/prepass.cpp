@@ -214,9 +214,9 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     // order.  The only coupling between reads is `bamdiscordant.back()` at :257: a chunk that has not pushed a discordant
     // block yet defers that test until the chunks before it are known.
     const int local_ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;  // one process per GPU shares the host
-    // a lone process takes half the cores (its own thread spins on the GPU; an oversubscribed OpenMP team pays for every
-    // barrier); several processes split them, one core each left to the spinning threads
-    const int cores = local_ranks == 1 ? std::max(1, omp_get_num_procs() / 2) : std::max(2, omp_get_num_procs() / local_ranks - 1);
+    // half the cores, split between the processes of the node: the calling threads spin on their GPUs meanwhile (and NCCL has
+    // its own), and an oversubscribed OpenMP team pays for every barrier
+    const int cores = std::max(local_ranks == 1 ? 1 : 2, omp_get_num_procs() / 2 / local_ranks);
     int T = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)cores, 16, c.n_reads / 4096 + 1}));
     if (getenv("SQH_PREPASS_CHUNKS")) T = std::max(1, atoi(getenv("SQH_PREPASS_CHUNKS")));  // test hook: force the chunked path on small inputs
     struct Chunk { std::vector<DB> dis; std::vector<std::pair<int, int>> part; std::vector<uint32_t> pend; };
