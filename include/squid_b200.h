@@ -143,10 +143,58 @@ int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, 
 /*
  * Multi-GPU.  A range shard computes partial results; these expose them as DEVICE
  * buffers so that the caller can run the NCCL exchange and hand the merged table back.
+ * (sqg_merge_edge_tables replaces the context's own table with the merged one.)
  */
 int sqg_edges_device_table(sqg_ctx *ctx, uint64_t **d_keys, int32_t **d_weights, int64_t *n);
 int sqg_merge_edge_tables(sqg_ctx *ctx, const uint64_t *d_keys, const int32_t *d_weights, int64_t n,
                           int32_t **ind1, int32_t **ind2, uint8_t **heads, int32_t **weight, int64_t *n_edges);
+
+/*
+ * Exact range sharding of ONE sorted stream over several contexts / GPUs.  The reference has no such notion: its
+ * three BamReader passes (SegmentGraph.cpp:293-296, 1570-1577, 3126-3129) walk the whole file on one thread.  Here the caller
+ * cuts the stream with sqg_plan_shards(), gives every context its record range (sqg_load_concordant) and ALL chimeric reads
+ * (sqg_load_chimeric), and runs the stages below, exchanging the small per-shard results between them (NCCL / torch.distributed
+ * all_gather when the contexts live in different processes; squid_b200/sharded.py is that driver).  The combined outputs are
+ * bit-identical to the single-context calls above.
+ *
+ *   sqg_plan_shards   cuts[0..n_planned] (cuts[0] = 0, cuts[n_planned] = n_rec); shard i owns records [cuts[i], cuts[i+1]).
+ *                     Cuts are placed at coverage gaps clear of every discordant group, where BuildNode_STAR's windows are
+ *                     empty and its pending segment closed (:616-636); n_planned < n_shards when the stream has too few.
+ *                     All arrays of `batch` are HOST pointers.
+ *   sqg_set_shard     declares the context shard `index` of `count` (before the stages).  Shard 0 owns the edges of the chimeric
+ *                     reads and the discordant-block depth.
+ *   sqg_shard_seeds   stage 1 = BuildNode_STAR up to the seed segments (:296-701) on this shard: *ops = n_ops x 4 int32
+ *                     (kind, chr, pos, len) emission ops, library-owned.  prior_emission: has an earlier shard emitted an op?
+ *                     (shards run with 1 speculatively; the caller repeats the stage with 0 for a shard whose predecessors all
+ *                     came back empty -- until a segment exists the reference behaves differently, :545, :558).
+ *   sqg_shard_build   stage 2 = the ops of ALL shards, concatenated in shard order -> segment table (:19-38, 706-761), this
+ *                     shard's depth numerators (:765-826; add the count3 / sumlen3 / reads_other_nonempty of all shards) and its
+ *                     edge table (sqg_edges_device_table -> all_gather -> sqg_merge_edge_tables).
+ *   sqg_shard_hint_state / sqg_shard_redo_edges
+ *                     LocateRead's running hint (firstfrontindex, :1568, 1612-1614) crosses shard boundaries: out_hint = the
+ *                     value this shard leaves (-1: it located no read), lead_sensitive = some read of this shard depended on
+ *                     the incoming value.  A shard with lead_sensitive whose true incoming hint (out_hint of the nearest
+ *                     earlier shard that has one) is not the one it ran with repeats its edge pass with it.
+ *   sqg_shard_cov_*   ExactBPConcordantSupport's BAM pass (:3124-3166).  begin: uploads the sorted breakpoints; *nq = this
+ *                     shard's qualifying records (rank offsets = exclusive sums over the shards), *n_pass = breakpoints some
+ *                     record of this shard passes.  chain: indBP enters this shard at breakpoint k_in; *k_out = first
+ *                     breakpoint it leaves unresolved (= k_in of the next shard; run speculatively with k_in = max n_pass of
+ *                     the earlier shards and repeat where k_out of the predecessor differs).  owned_t: writes rank_offset + t
+ *                     for [k_in, k_out) into t_global[n_bp].  count: this shard's share of Coverages given the complete
+ *                     t_global (unresolved breakpoints = total number of qualifying records); sum the shares.
+ */
+int sqg_plan_shards(const sqg_batch *batch, const sqg_chimeric *chim, const sqg_config *cfg, int32_t n_ref, int32_t n_shards,
+                    int64_t *cuts, int32_t *n_planned);
+int sqg_set_shard(sqg_ctx *ctx, int32_t index, int32_t count);
+int sqg_shard_seeds(sqg_ctx *ctx, int32_t prior_emission, const int32_t **ops, int64_t *n_ops);
+int sqg_shard_build(sqg_ctx *ctx, const int32_t *ops_all, int64_t n_ops_all, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
+                    int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty);
+int sqg_shard_hint_state(sqg_ctx *ctx, int32_t *lead_sensitive, int32_t *out_hint);
+int sqg_shard_redo_edges(sqg_ctx *ctx, int32_t init_hint);
+int sqg_shard_cov_begin(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, int64_t n_bp, int64_t *nq, int64_t *n_pass);
+int sqg_shard_cov_chain(sqg_ctx *ctx, int64_t k_in, int64_t *k_out);
+int sqg_shard_cov_owned_t(sqg_ctx *ctx, int64_t rank_offset, int64_t k_in, int64_t k_out, int64_t *t_global);
+int sqg_shard_cov_count(sqg_ctx *ctx, int64_t rank_offset, const int64_t *t_global, int32_t *cov_partial);
 
 /* Device time in ms of the named phase/kernel of the most recent call ("classify", "seed", "tile", "depth_edges",
  * "edge_sort", "coverage"; kernels: "k_classify", "k_cov_compact", "k_assign_depth", "k_assign_edges", "k_edges_generic",

@@ -64,6 +64,8 @@ EXPORTS = [
     "sqg_create", "sqg_destroy", "sqg_last_error", "sqg_load_concordant", "sqg_attach_concordant_device", "sqg_load_chimeric",
     "sqg_build_nodes", "sqg_set_nodes", "sqg_build_edges", "sqg_bp_coverage", "sqg_edges_device_table", "sqg_merge_edge_tables",
     "sqg_phase_ms", "sqg_launch_count", "sqg_stat",
+    "sqg_plan_shards", "sqg_set_shard", "sqg_shard_seeds", "sqg_shard_build", "sqg_shard_hint_state", "sqg_shard_redo_edges",
+    "sqg_shard_cov_begin", "sqg_shard_cov_chain", "sqg_shard_cov_owned_t", "sqg_shard_cov_count",
     "sqh_default_options", "sqh_open_case", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
     "sqh_case_n_ref", "sqh_case_ref_len", "sqh_case_blocks",
 ]
@@ -98,6 +100,16 @@ def lib() -> C.CDLL:
     L.sqg_phase_ms.argtypes = [_P, C.c_char_p]; L.sqg_phase_ms.restype = C.c_float
     L.sqg_launch_count.argtypes = [_P]; L.sqg_launch_count.restype = C.c_int64
     L.sqg_stat.argtypes = [_P, C.c_char_p]; L.sqg_stat.restype = C.c_int64
+    L.sqg_plan_shards.argtypes = [pp(sqg_batch), pp(sqg_chimeric), pp(sqg_config), C.c_int32, C.c_int32, _P, pp(C.c_int32)]
+    L.sqg_set_shard.argtypes = [_P, C.c_int32, C.c_int32]
+    L.sqg_shard_seeds.argtypes = [_P, C.c_int32, pp(_P), pp(C.c_int64)]
+    L.sqg_shard_build.argtypes = [_P, _P, C.c_int64, pp(_P), pp(_P), pp(_P), pp(C.c_int64), pp(_P), pp(_P), pp(C.c_int32)]
+    L.sqg_shard_hint_state.argtypes = [_P, pp(C.c_int32), pp(C.c_int32)]
+    L.sqg_shard_redo_edges.argtypes = [_P, C.c_int32]
+    L.sqg_shard_cov_begin.argtypes = [_P, _P, _P, C.c_int64, pp(C.c_int64), pp(C.c_int64)]
+    L.sqg_shard_cov_chain.argtypes = [_P, C.c_int64, pp(C.c_int64)]
+    L.sqg_shard_cov_owned_t.argtypes = [_P, C.c_int64, C.c_int64, C.c_int64, _P]
+    L.sqg_shard_cov_count.argtypes = [_P, C.c_int64, _P, _P]
     L.sqh_default_options.argtypes = [pp(sqh_options)]; L.sqh_default_options.restype = None
     L.sqh_open_case.argtypes = [C.c_char_p, C.c_char_p, pp(sqh_options), pp(_P), C.c_char_p, C.c_int]
     L.sqh_close_case.argtypes = [_P]; L.sqh_close_case.restype = None
@@ -352,6 +364,57 @@ class SegmentGraph:
         self.vNodes = Nodes(_np_from(chr_, N, np.int32), _np_from(pos, N, np.int32), length, support.astype(np.int32), depth, count3, sum3)
         return self.vNodes
 
+    # -- range shards of one stream (include/squid_b200.h "Exact range sharding"; driver: squid_b200/sharded.py) ---------
+    def set_shard(self, index: int, count: int):
+        self._ck(self.L.sqg_set_shard(self._h, index, count))
+
+    def shard_seeds(self, prior_emission: bool) -> np.ndarray:
+        """Stage 1: this shard's seed ops, rows (kind, chr, pos, len)."""
+        ops, n = _P(), C.c_int64()
+        self._ck(self.L.sqg_shard_seeds(self._h, int(prior_emission), C.byref(ops), C.byref(n)))
+        return _np_from(ops, 4 * n.value, np.int32).reshape(-1, 4)
+
+    def shard_build(self, ops_all: np.ndarray):
+        """Stage 2: ops of all shards -> (Chr, Position, Length, count3[3,N], sumlen3[3,N], reads_other_nonempty) with this
+        shard's partial depth numerators."""
+        ops = np.ascontiguousarray(ops_all, np.int32).reshape(-1, 4)
+        chr_, pos, ln, c3, s3 = _P(), _P(), _P(), _P(), _P()
+        n, other = C.c_int64(), C.c_int32()
+        self._ck(self.L.sqg_shard_build(self._h, ops.ctypes.data, int(ops.shape[0]), C.byref(chr_), C.byref(pos), C.byref(ln), C.byref(n),
+                                        C.byref(c3), C.byref(s3), C.byref(other)))
+        N = n.value
+        return (_np_from(chr_, N, np.int32), _np_from(pos, N, np.int32), _np_from(ln, N, np.int32),
+                _np_from(c3, 3 * N, np.int32).reshape(3, N), _np_from(s3, 3 * N, np.int32).reshape(3, N), int(other.value))
+
+    def shard_hint_state(self):
+        lead, out = C.c_int32(), C.c_int32()
+        self._ck(self.L.sqg_shard_hint_state(self._h, C.byref(lead), C.byref(out)))
+        return bool(lead.value), int(out.value)
+
+    def shard_redo_edges(self, init_hint: int):
+        self._ck(self.L.sqg_shard_redo_edges(self._h, int(init_hint)))
+
+    def shard_cov_begin(self, bp_chr, bp_pos):
+        self._bp = (np.ascontiguousarray(bp_chr, np.int32), np.ascontiguousarray(bp_pos, np.int32))
+        nq, npass = C.c_int64(), C.c_int64()
+        self._ck(self.L.sqg_shard_cov_begin(self._h, self._bp[0].ctypes.data, self._bp[1].ctypes.data, int(self._bp[0].shape[0]), C.byref(nq), C.byref(npass)))
+        return int(nq.value), int(npass.value)
+
+    def shard_cov_chain(self, k_in: int) -> int:
+        k_out = C.c_int64()
+        self._ck(self.L.sqg_shard_cov_chain(self._h, int(k_in), C.byref(k_out)))
+        return int(k_out.value)
+
+    def shard_cov_owned_t(self, rank_offset: int, k_in: int, k_out: int, t_global: np.ndarray):
+        assert t_global.dtype == np.int64 and t_global.flags.c_contiguous
+        self._ck(self.L.sqg_shard_cov_owned_t(self._h, int(rank_offset), int(k_in), int(k_out), t_global.ctypes.data))
+
+    def shard_cov_count(self, rank_offset: int, t_global: np.ndarray) -> np.ndarray:
+        t = np.ascontiguousarray(t_global, np.int64)
+        out = np.zeros(t.shape[0], np.int32)
+        self._ck(self.L.sqg_shard_cov_count(self._h, int(rank_offset), t.ctypes.data, out.ctypes.data))
+        return out
+
     def set_nodes(self, Chr, Position, Length):
         c = np.ascontiguousarray(Chr, np.int32); p = np.ascontiguousarray(Position, np.int32); l = np.ascontiguousarray(Length, np.int32)
         self._ck(self.L.sqg_set_nodes(self._h, c.ctypes.data, p.ctypes.data, l.ctypes.data, int(c.shape[0])))
@@ -414,3 +477,15 @@ class SegmentGraph:
 
     def stat(self, name: str) -> int:
         return int(self.L.sqg_stat(self._h, name.encode()))
+
+
+def plan_shards(batch: RecordBatch, chim: ChimericReads, config: Config, n_ref: int, n_shards: int):
+    """sqg_plan_shards: clean cuts of the sorted stream.  Returns [c_0 = 0, ..., c_m = n_rec] with m <= n_shards."""
+    L = lib()
+    bs, cs, cfg = batch.as_struct(), chim.as_struct(), config.as_struct()
+    cuts = np.zeros(n_shards + 1, np.int64)
+    m = C.c_int32()
+    rc = L.sqg_plan_shards(C.byref(bs), C.byref(cs), C.byref(cfg), int(n_ref), int(n_shards), cuts.ctypes.data, C.byref(m))
+    if rc != 0:
+        raise SquidB200Error(rc, "sqg_plan_shards failed")
+    return [int(x) for x in cuts[: m.value + 1]]

@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
 
 // Exclusive scan of the tile aggregates, in place (one block of 32 warps): okmax -> maximum over earlier tiles, n_pc / n_dp ->
 // offsets.  Every warp owns a contiguous run of tiles and walks it 32 tiles at a time (coalesced), first to reduce the run,
-// then -- with the carry of the runs before it -- to scan it.  totals[1] = #partial, totals[2] = #displaced.
-__global__ void __launch_bounds__(1024) k_tile_scan(TileAgg *agg, int32_t n_tiles, int32_t *totals) {
+// then -- with the carry of the runs before it -- to scan it.  totals[1] = #partial, totals[2] = #displaced, *ok_total = the
+// maximum over all tiles.
+__global__ void __launch_bounds__(1024) k_tile_scan(TileAgg *agg, int32_t n_tiles, int32_t *totals, uint64_t *ok_total) {
     __shared__ uint64_t s_ok[32];
     __shared__ uint32_t s_pc[32], s_dp[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(TileAgg *agg, int32_t n_tile
         if (tok > ok) ok = tok;
         pc += __shfl_sync(full, ipc, 31); dp += __shfl_sync(full, idp, 31);
     }
+    if (threadIdx.x == 1023 && ok_total) *ok_total = ok;  // otherChr/otherrightmost after the last record (range shards: sq_seed.cuh end_other)
 }
 
 // Candidate -> gap decision with the true running maximum; non-gaps get the key INT32_MAX so that a sort by record index

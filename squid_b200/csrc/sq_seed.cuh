@@ -65,6 +65,11 @@ struct SeedInputs {
     int32_t read_len;
     int64_t first_kept;
     long long *prof_out = nullptr;  // SQ_SEED_PROF builds: 12 int64 per island
+    // range shard of one genome: groups before g_lo belong to earlier shards; when a later shard follows, the record right
+    // after this batch is a 0-coverage record for the pending group (the shard planner guarantees it, sqg_plan_shards)
+    int32_t g_lo = 0;
+    bool has_next = false;
+    uint64_t end_other = 0;         // otherChr/otherrightmost after the last record of the batch
 };
 
 struct SeedState {
@@ -363,6 +368,16 @@ struct SeedMachineT {
         return x;
     }
 
+    // :621-630 at a 0-coverage record whose (curChr, currightmost) is (cc, cr)
+    SQ_HD void close_marked_gap(int32_t cc, int32_t cr) {
+        if (st.markedStart == -1) return;
+        if (cc == st.markedChr && cr > st.markedStart && cr - st.markedStart < kSeedThresh * 20 && st.have_back && st.markedStart == st.backEnd)
+            set_back_end(st.backEnd + (cr - st.markedStart));
+        else if (cc == st.markedChr && cr > st.markedStart && cr - st.markedStart >= kSeedThresh * 20)
+            push_node(st.markedChr, st.markedStart, cr - st.markedStart);
+        st.markedStart = -1; st.markedChr = -1;
+    }
+
     // Lazy replay of steps :616-646 for the kept records in [r_lo, r_hi) while the group starting at (sChr,sPos) is pending.
     SQ_HD void replay_between(int64_t r_lo, int64_t r_hi, int32_t dChr, int32_t dRight, int32_t sChr, int32_t sPos, bool do_trim) {
         if (r_hi <= r_lo) return;
@@ -371,13 +386,7 @@ struct SeedMachineT {
         int32_t f = -1, z = -1;
         for (int32_t k = a; k < bnd; k++) if (is0(k, dChr, dRight, sChr, sPos, &cc, &cr)) { f = k; break; }
         if (f >= 0) {
-            if (st.markedStart != -1) {  // :621-630
-                if (cc == st.markedChr && cr > st.markedStart && cr - st.markedStart < kSeedThresh * 20 && st.have_back && st.markedStart == st.backEnd)
-                    set_back_end(st.backEnd + (cr - st.markedStart));
-                else if (cc == st.markedChr && cr > st.markedStart && cr - st.markedStart >= kSeedThresh * 20)
-                    push_node(st.markedChr, st.markedStart, cr - st.markedStart);
-                st.markedStart = -1; st.markedChr = -1;
-            }
+            close_marked_gap(cc, cr);
             if (!do_trim) return;
             for (int32_t k = bnd - 1; k >= f; k--) if (is0(k, dChr, dRight, sChr, sPos, &cc, &cr)) { z = k; break; }
             const int64_t zr = in.gap_rec[z];
@@ -978,6 +987,15 @@ struct SeedMachineT {
             const Group grp = in.G[g];
             const int64_t r_hi = in.trigger[g] < in.n_rec ? in.trigger[g] : in.n_rec;
             replay_between(r_prev, r_hi, dChr, dRight, grp.chr, in.D[grp.ds].pos, false);
+            if (in.has_next && in.trigger[g] >= in.n_rec && st.markedStart != -1) {
+                // range shard: the pending segment is closed by the first record of the next shard, a 0-coverage record
+                // whose (curChr, currightmost) is the maximum of the last group's right end and the batch's final other key
+                const uint64_t e = in.end_other < (1ull << 32) ? (1ull << 32) : in.end_other;
+                const int32_t oChr = (int32_t)(e >> 32) - 1, oRight = (int32_t)(uint32_t)e;
+                const int32_t cr = (dChr > oChr || (dChr == oChr && dRight > oRight)) ? dRight : oRight;
+                const int32_t cc = dChr > oChr ? dChr : oChr;
+                close_marked_gap(cc, cr);
+            }
         }
         // after the very last group the reference compares against the element one past the end of bamdiscordant
         // (zero sentinel): the 0-coverage test can never hold there, nothing to do.

@@ -136,7 +136,7 @@ __global__ void k_island_cuts(SeedInputs in, uint8_t *flag) {
     if (g >= in.nG) return;
     SeedMachine sm;
     sm.in = in;
-    flag[g] = (g == 0) ? 1 : (sm.island_cut(g) ? 1 : 0);
+    flag[g] = (g == in.g_lo) ? 1 : (g < in.g_lo ? 0 : (sm.island_cut(g) ? 1 : 0));  // groups before g_lo belong to earlier shards
 }
 struct IsCutOp {
     const uint8_t *flag;
@@ -371,17 +371,27 @@ __global__ void k_chim_edges(ChimDev c, Params p, NodeTable nt, int32_t *res0, P
 // Hint-sensitive reads are replayed with the true hint = segment of the first block of the nearest earlier read that
 // located one (res0 >= 0), in stream order.  A run of sensitive reads with no located read in between is a chain: its first
 // read (the head) knows its hint from the untouched part of res0, and the head's thread replays the whole chain in order.
-__global__ void k_fix_heads(const int32_t *res0, const int32_t *sens, const int32_t *n_sens, int32_t cap, int32_t *head_hint) {
+// `init_hint`: firstfrontindex before the first read (0 at the start of the stream, :1395, :1568; a range shard gets the
+// value its predecessor left); *used_init is set when some chain had to start from it.
+__global__ void k_fix_heads(const int32_t *res0, const int32_t *sens, const int32_t *n_sens, int32_t cap, int32_t *head_hint, int32_t init_hint, int32_t *used_init) {
     const int32_t n = *n_sens < cap ? *n_sens : cap;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int32_t hint = 0;  // firstfrontindex starts at 0 (:1395, :1568)
+        int32_t hint = init_hint;
+        bool from_init = true;
         for (int64_t q = (int64_t)sens[i] - 1; q >= 0; q--) {
             const int32_t v = res0[q];
-            if (v >= 0) { hint = v; break; }
-            if (v == -3) { hint = -1; break; }  // not a head
+            if (v >= 0) { hint = v; from_init = false; break; }
+            if (v == -3) { hint = -1; from_init = false; break; }  // not a head
         }
         head_hint[i] = hint;
+        if (from_init && used_init) *used_init = 1;
     }
+}
+// firstfrontindex after the last read of the batch: res0 of the last read that located its first block (-1: none)
+__global__ void k_last_located(const int32_t *res0, int64_t n, int32_t *out) {
+    int32_t v = -1;
+    for (int64_t q = n - 1; q >= 0; q--) if (res0[q] >= 0) { v = res0[q]; break; }
+    *out = v;
 }
 template <bool CHIM>
 __global__ void k_fix_chains(DevBatch b, ChimDev c, Params p, NodeTable nt, int32_t *res0, int64_t n_items, const int32_t *sens, const int32_t *n_sens, int32_t cap,
@@ -774,7 +784,7 @@ static int run_classify(sqg_ctx *ctx) {
     PHASE_BEGIN("classify");
     CK(ctx->d_cls.ensure(n + 4)); CK(ctx->d_flen.ensure(n + 4)); CK(ctx->d_scratch32.ensure(n + 1));
     CK(ctx->d_counters.ensure(32)); CK(ctx->h_counters.ensure(32));
-    ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n;
+    ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n; ctx->end_other = 0;
     if (n > 0) {
         const int64_t n_tiles = (n + kTile - 1) / kTile;
         CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8));
@@ -807,9 +817,9 @@ static int run_classify(sqg_ctx *ctx) {
             ctx->launches++;
             CK(cudaGetLastError());
             PHASE_END("k_classify");
-            LAUNCH(k_tile_scan, 1, 1024, ctx->d_tileagg.p, (int32_t)n_tiles, totals);
+            LAUNCH(k_tile_scan, 1, 1024, ctx->d_tileagg.p, (int32_t)n_tiles, totals, (uint64_t *)(ctx->d_counters.p + 21));
             CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->h_counters.p + 20, ctx->d_counters.p + 20, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_counters.p + 20, ctx->d_counters.p + 20, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             const int32_t flags = *(int32_t *)(ctx->h_counters.p + 20);
             if (flags & 1) FAIL(SQG_EINVAL, "record with ref_id outside [-1, n_ref)");
@@ -824,6 +834,7 @@ static int run_classify(sqg_ctx *ctx) {
         const int32_t *sel = (const int32_t *)ctx->h_counters.p;
         ctx->n_pc = sel[1]; ctx->n_dp = sel[2]; ctx->first_kept = ctx->h_counters.p[2];
         ctx->lmax = *(const int32_t *)(ctx->h_counters.p + 3);
+        ctx->end_other = (uint64_t)ctx->h_counters.p[21];
         CK(ctx->d_gap.ensure((size_t)n_cand + 1)); CK(ctx->d_other.ensure((size_t)n_cand + 1));
         CK(ctx->d_pc.ensure((size_t)ctx->n_pc + 1)); CK(ctx->d_dp.ensure((size_t)ctx->n_dp + 1));
         if (n_cand > 0) {
@@ -983,13 +994,14 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
         if (do_depth) {
             CK(cudaMemsetAsync(ctx->d_cnt3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
             CK(cudaMemsetAsync(ctx->d_sum3.p, 0, (3 * (size_t)N + 4) * 4, ctx->stream));
-            if (nD > 0) LAUNCH(k_depth_disc, blocks_for(nD), kThreads, ctx->nt, ctx->d_disc.p, nD, ctx->d_cnt3.p, ctx->d_sum3.p);
+            if (nD > 0 && ctx->shard_index == 0) LAUNCH(k_depth_disc, blocks_for(nD), kThreads, ctx->nt, ctx->d_disc.p, nD, ctx->d_cnt3.p, ctx->d_sum3.p);
         }
-        if (do_edges && cd.n_reads > 0) {  // RawEdgesChim: chimeric reads, their sensitive ones replayed in chains
+        CK(cudaMemsetAsync(ctx->d_counters.p + 22, 0, 2 * sizeof(int64_t), ctx->stream));  // [22] used_init flag | [23] out hint
+        if (do_edges && cd.n_reads > 0 && ctx->shard_index == 0) {  // (range shards: the chimeric reads are replicated, shard 0 owns their edges)  // RawEdgesChim: chimeric reads, their sensitive ones replayed in chains
             // (the chimeric sensitive list lives behind the concordant one)
             int32_t *csens = ctx->d_sens.p + (sens_cap - ctx->c_n_reads - 1), *chead = ctx->d_head.p + (sens_cap - ctx->c_n_reads - 1);
             LAUNCH(k_chim_edges, blocks_for(cd.n_reads), kThreads, cd, ctx->params, ctx->nt, ctx->dc_res0.p, sink, csens, d_nsens + 1);
-            LAUNCH(k_fix_heads, 64, 128, ctx->dc_res0.p, csens, d_nsens + 1, (int32_t)ctx->c_n_reads, chead);
+            LAUNCH(k_fix_heads, 64, 128, ctx->dc_res0.p, csens, d_nsens + 1, (int32_t)ctx->c_n_reads, chead, 0, (int32_t *)nullptr);
             LAUNCH(k_fix_chains<true>, 64, 128, b, cd, ctx->params, ctx->nt, ctx->dc_res0.p, cd.n_reads, csens, d_nsens + 1, (int32_t)ctx->c_n_reads, chead, sink);
         }
         const int32_t conc_sens_cap = (int32_t)std::max<int64_t>(0, sens_cap - ctx->c_n_reads - 1);
@@ -1040,13 +1052,17 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
                 LAUNCH(k_depth_fix, blocks_for(n_tiles), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_dtile.p, (int32_t)n_tiles, a.cnt_main, a.sum_main);
             }
             if (do_edges) {
-                LAUNCH(k_fix_heads, 256, 128, ctx->d_scratch32.p, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p);
+                LAUNCH(k_fix_heads, 256, 128, ctx->d_scratch32.p, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, ctx->shard_init_hint, (int32_t *)(ctx->d_counters.p + 22));
                 LAUNCH(k_fix_chains<false>, 256, 128, b, cd, ctx->params, ctx->nt, ctx->d_scratch32.p, n, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, sink);
+                if (ctx->shard_count > 1) LAUNCH(k_last_located, 1, 1, ctx->d_scratch32.p, n, (int32_t *)(ctx->d_counters.p + 23));
             }
         }
         CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_counters.p + 16, ctx->d_counters.p + 16, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 22, ctx->d_counters.p + 22, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        ctx->shard_lead_sensitive = *(int32_t *)(ctx->h_counters.p + 22) != 0;
+        ctx->shard_out_hint = (ctx->shard_count > 1 && do_edges && n > 0) ? *(int32_t *)(ctx->h_counters.p + 23) : -1;
         n_raw = ctx->h_counters.p[9];
         const int32_t ns_conc = ((int32_t *)(ctx->h_counters.p + 10))[0], ns_chim = ((int32_t *)(ctx->h_counters.p + 10))[1];
         ctx->n_sensitive = (int64_t)ns_conc + ns_chim;
@@ -1068,14 +1084,12 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
     return SQG_OK;
 }
 
-extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
-                               int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty) {
-    if (!ctx || !chr || !pos || !len || !n_nodes || !count3 || !sumlen3 || !reads_other_nonempty) return SQG_EINVAL;
-    if (!ctx->have_batch || !ctx->have_chim) FAIL(SQG_ESTATE, "load the concordant batch and the chimeric reads first");
-    CK(cudaSetDevice(ctx->device));
+// BuildNode_STAR up to the seed segments: classification, the chimeric pre-pass, the island-parallel state machine.
+// Leaves this batch's seed ops (island order) in ctx->shard_ops; a range shard owns the groups from shard_g_lo on.
+static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
-    HostLap lap;
+    ctx->shard_seeded = false;
     int rc = run_classify(ctx);
     if (rc) return rc;
     lap("classify");
@@ -1121,15 +1135,35 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     in.D = ctx->d_disc.p; in.nD = nD; in.G = ctx->d_groups.p; in.nG = nG; in.trigger = ctx->d_trigger.p;
     in.Pchr = ctx->d_pchr.p; in.Ppos = ctx->d_ppos.p; in.nP = nP;
     in.rest = ctx->d_rest2.p; in.n_rest = (int32_t)n_rest; in.read_len = ctx->params.read_len; in.first_kept = ctx->first_kept;
+    // range shard (sqg_set_shard): the groups whose right end lies left of this batch's first kept record were triggered in
+    // an earlier shard; when another shard follows, the pending segment of the last island is closed at the batch end
+    int32_t g_lo = 0;
+    if (ctx->shard_index > 0) {
+        g_lo = nG;
+        if (ctx->first_kept < n) {
+            int32_t rp[2];
+            CK(cudaMemcpyAsync(&rp[0], b.ref_id + ctx->first_kept, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&rp[1], b.pos + ctx->first_kept, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            g_lo = 0;
+            while (g_lo < nG) {
+                const Group &gg = ctx->pre.groups[g_lo];
+                if (rp[0] < 0 || gg.chr < rp[0] || (gg.chr == rp[0] && gg.right < rp[1])) g_lo++; else break;
+            }
+        }
+    }
+    ctx->shard_g_lo = g_lo;
+    in.g_lo = g_lo; in.has_next = ctx->shard_index + 1 < ctx->shard_count; in.end_other = ctx->end_other;
     CK(ctx->d_cutflag.ensure(nG + 1)); CK(ctx->d_isl.ensure(nG + 2));
     LAUNCH(k_island_cuts, blocks_for(nG, 64), 64, in, ctx->d_cutflag.p);
-    {
-        cub::CountingInputIterator<int32_t> cnt(0);
+    CK(cudaMemsetAsync(ctx->d_counters.p + 5, 0, sizeof(int64_t), ctx->stream));
+    if (nG - g_lo > 0) {
+        cub::CountingInputIterator<int32_t> cnt(g_lo);
         IsCutOp op{ctx->d_cutflag.p};
         size_t tb = 0;
-        CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG, op, ctx->stream));
+        CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG - g_lo, op, ctx->stream));
         ENSURE_TEMP(tb);
-        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG, op, ctx->stream));
+        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG - g_lo, op, ctx->stream));
         ctx->launches += 2;
     }
     CK(cudaMemcpyAsync(ctx->h_counters.p + 5, ctx->d_counters.p + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1156,9 +1190,12 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     CK(ctx->d_ops.ensure(tot[0] + 1)); CK(ctx->d_margin.ensure(tot[1] + 1));
     int32_t *d_err = (int32_t *)(ctx->d_counters.p + 7), *d_nprefix = (int32_t *)(ctx->d_counters.p + 6);
     CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, 2 * sizeof(int64_t), ctx->stream));
-    LAUNCH(k_seed_prefix, 1, kSeedBlock, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
-           ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, d_nprefix);
-    {
+    // (a shard that follows one with an emitted segment starts with an inherited last segment: no sequential prefix)
+    if (!(ctx->shard_index > 0 && ctx->shard_prior_emission) && n_isl > 0)
+        LAUNCH(k_seed_prefix, 1, kSeedBlock, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
+               ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, d_nprefix);
+    CK(cudaMemsetAsync(ctx->d_counters.p + 13, 0, sizeof(int64_t), ctx->stream));
+    if (n_isl > 0) {
         cub::CountingInputIterator<int32_t> cnt(0);
         size_t tb = 0;
         IsHeavyOp oh{ctx->d_span.p, d_nprefix, true}, ol{ctx->d_span.p, d_nprefix, false};
@@ -1168,9 +1205,9 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
         CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_heavy.p, d_nh, n_isl, oh, ctx->stream));
         CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_light.p, d_nh + 1, n_isl, ol, ctx->stream));
         ctx->launches += 3;
-        CK(cudaMemcpyAsync(ctx->h_counters.p + 13, ctx->d_counters.p + 13, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
     }
+    CK(cudaMemcpyAsync(ctx->h_counters.p + 13, ctx->d_counters.p + 13, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     const int32_t n_heavy = ((int32_t *)(ctx->h_counters.p + 13))[0], n_light = ((int32_t *)(ctx->h_counters.p + 13))[1];
     ctx->n_heavy = n_heavy;
     if (n_heavy > 1) {  // longest islands first: the kernel's critical path is its largest island
@@ -1229,12 +1266,14 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
         cudaFree(d_prof);
     }
 #endif
-    // stitch the island op lists in genome order (host: a few hundred thousand ops at most)
-    std::vector<int32_t> h_nout(n_isl), h_gdone(n_isl), h_isl(n_isl + 1);
+    // this batch's op lists in island order (host: a few hundred thousand ops at most)
+    std::vector<int32_t> h_nout(n_isl + 1), h_gdone(n_isl + 1), h_isl(n_isl + 1);
     std::vector<int64_t> h_off(n_isl + 1);
-    CK(cudaMemcpyAsync(h_nout.data(), ctx->d_isl_nout.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_gdone.data(), ctx->d_isl_gdone.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_isl.data(), ctx->d_isl.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_isl > 0) {
+        CK(cudaMemcpyAsync(h_nout.data(), ctx->d_isl_nout.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_gdone.data(), ctx->d_isl_gdone.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_isl.data(), ctx->d_isl.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaMemcpyAsync(h_off.data(), ctx->d_off_ops.p, (n_isl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters.p + 6, ctx->d_counters.p + 6, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<int64_t> trig_last(1, n);
@@ -1245,26 +1284,39 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     const int32_t serr = *(int32_t *)(ctx->h_counters.p + 7);
     if (serr) FAIL(SQG_ENOMEM, serr == 1 ? "seed machine: margin scratch overflow" : "seed machine: output overflow");
     h_isl[n_isl] = nG;
-    std::vector<SeedNode> seeds;
+    ctx->shard_ops.clear();
     int32_t g_done = nG;
     for (int32_t i = 0; i < n_isl; i++) {
-        stitch_ops(ctx->h_ops.p + h_off[i], h_nout[i], seeds);
+        ctx->shard_ops.insert(ctx->shard_ops.end(), ctx->h_ops.p + h_off[i], ctx->h_ops.p + h_off[i] + h_nout[i]);
         if (h_gdone[i] < h_isl[i + 1]) { g_done = h_gdone[i]; break; }  // the stream ended before this group: nothing later is ever processed
     }
-    if (seeds.empty()) FAIL(SQG_EUNSUPPORTED, "no seed segment was produced: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
+    ctx->shard_g_done = g_done;
+    ctx->shard_trig_last = trig_last[0];
     ctx->n_islands = n_isl;
+    ctx->shard_seeded = true;
+    lap("seed: wait + ops");
+    return SQG_OK;
+}
 
-    lap("seed: wait + stitch");
+// The rest of BuildNode_STAR from the stitched seed segments: tiling, depth numerators, and (eagerly) the edge table.
+static int finish_stage(sqg_ctx *ctx, std::vector<SeedNode> &seeds, HostLap &lap, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
+                        int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty) {
+    const int64_t n = ctx->batch.n_rec;
+    const int32_t nG = (int32_t)ctx->pre.groups.size();
+    if (seeds.empty()) FAIL(SQG_EUNSUPPORTED, "no seed segment was produced: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
     PHASE_BEGIN("tile");
-    rc = tile_genome(ctx, seeds);
+    int rc = tile_genome(ctx, seeds);
     if (rc) return rc;
     PHASE_END("tile");
 
-    // break index of the depth streams (:338-339): the first kept record after the last group's trigger is still pushed
+    // break index of the depth streams (:338-339): the first kept record after the last group's trigger is still pushed.
+    // Range shards: the shard planner keeps two kept records of the owning shard behind every group, so the break falls
+    // into the shard that owns the last group; later shards contribute nothing to the depth streams.
     ctx->r_break = n;
-    if (g_done == nG) {
+    if (ctx->shard_index > 0 && ctx->shard_g_lo == nG) ctx->r_break = 0;
+    else if (ctx->shard_g_done == nG) {
         // find it on the device-side class bytes via a tiny host loop over a copied window
-        int64_t r = trig_last[0] + 1;
+        int64_t r = ctx->shard_trig_last + 1;
         std::vector<uint8_t> win(4096);
         bool found = false;
         while (r < n && !found) {
@@ -1291,6 +1343,64 @@ extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32
     *reads_other_nonempty = ctx->h_cnt3.p[3 * (size_t)N] != 0;
     lap("outputs");
     return SQG_OK;
+}
+
+extern "C" int sqg_build_nodes(sqg_ctx *ctx, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
+                               int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty) {
+    if (!ctx || !chr || !pos || !len || !n_nodes || !count3 || !sumlen3 || !reads_other_nonempty) return SQG_EINVAL;
+    if (!ctx->have_batch || !ctx->have_chim) FAIL(SQG_ESTATE, "load the concordant batch and the chimeric reads first");
+    if (ctx->shard_count > 1) FAIL(SQG_ESTATE, "this context is a range shard: use sqg_shard_seeds / sqg_shard_build");
+    CK(cudaSetDevice(ctx->device));
+    HostLap lap;
+    int rc = seed_stage(ctx, lap);
+    if (rc) return rc;
+    std::vector<SeedNode> seeds;
+    stitch_ops(ctx->shard_ops.data(), (int32_t)ctx->shard_ops.size(), seeds);
+    return finish_stage(ctx, seeds, lap, chr, pos, len, n_nodes, count3, sumlen3, reads_other_nonempty);
+}
+
+// ---- range shards of one genome --------------------------------------------------------------------
+extern "C" int sqg_set_shard(sqg_ctx *ctx, int32_t index, int32_t count) {
+    if (!ctx || count < 1 || index < 0 || index >= count) return SQG_EINVAL;
+    ctx->shard_index = index; ctx->shard_count = count; ctx->shard_prior_emission = index > 0; ctx->shard_init_hint = 0;
+    ctx->shard_seeded = false; ctx->have_edge_table = false;
+    return SQG_OK;
+}
+extern "C" int sqg_shard_seeds(sqg_ctx *ctx, int32_t prior_emission, const int32_t **ops, int64_t *n_ops) {
+    if (!ctx || !ops || !n_ops) return SQG_EINVAL;
+    if (!ctx->have_batch || !ctx->have_chim) FAIL(SQG_ESTATE, "load the concordant batch and the chimeric reads first");
+    CK(cudaSetDevice(ctx->device));
+    ctx->shard_prior_emission = ctx->shard_index > 0 && prior_emission != 0;
+    HostLap lap;
+    int rc = seed_stage(ctx, lap);
+    if (rc) return rc;
+    static_assert(sizeof(SeedOp) == 16, "SeedOp crosses the C ABI as 4 x int32");
+    *ops = (const int32_t *)ctx->shard_ops.data(); *n_ops = (int64_t)ctx->shard_ops.size();
+    return SQG_OK;
+}
+extern "C" int sqg_shard_build(sqg_ctx *ctx, const int32_t *ops_all, int64_t n_ops_all, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
+                               int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty) {
+    if (!ctx || (n_ops_all > 0 && !ops_all) || n_ops_all < 0 || n_ops_all > 0x7fffffff || !chr || !pos || !len || !n_nodes || !count3 || !sumlen3 || !reads_other_nonempty) return SQG_EINVAL;
+    if (!ctx->shard_seeded) FAIL(SQG_ESTATE, "sqg_shard_seeds must run first");
+    CK(cudaSetDevice(ctx->device));
+    HostLap lap;
+    std::vector<SeedNode> seeds;
+    stitch_ops((const SeedOp *)ops_all, (int32_t)n_ops_all, seeds);
+    ctx->shard_init_hint = 0;
+    return finish_stage(ctx, seeds, lap, chr, pos, len, n_nodes, count3, sumlen3, reads_other_nonempty);
+}
+extern "C" int sqg_shard_hint_state(sqg_ctx *ctx, int32_t *lead_sensitive, int32_t *out_hint) {
+    if (!ctx || !lead_sensitive || !out_hint) return SQG_EINVAL;
+    if (!ctx->have_edge_table) FAIL(SQG_ESTATE, "no edge table yet");
+    *lead_sensitive = ctx->shard_lead_sensitive; *out_hint = ctx->shard_out_hint;
+    return SQG_OK;
+}
+extern "C" int sqg_shard_redo_edges(sqg_ctx *ctx, int32_t init_hint) {
+    if (!ctx) return SQG_EINVAL;
+    if (!ctx->have_nodes || !ctx->shard_seeded) FAIL(SQG_ESTATE, "sqg_shard_build must run first");
+    CK(cudaSetDevice(ctx->device));
+    ctx->shard_init_hint = init_hint;
+    return run_assign(ctx, false, true);
 }
 
 // sort raw keys, run-length reduce, unpack
@@ -1384,46 +1494,53 @@ extern "C" int sqg_merge_edge_tables(sqg_ctx *ctx, const uint64_t *d_keys, const
     return export_edges(ctx, ind1, ind2, heads, weight, n_edges);
 }
 
-extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t *cov_out) {
-    if (!ctx || K < 0 || (K > 0 && (!bp_chr || !bp_pos || !cov_out))) return SQG_EINVAL;
+// ---- breakpoint coverage, staged: prepare (upload, compaction) -> chain (t of the breakpoints from k_begin on) -> count ----
+static int cov_prepare(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K) {
     if (!ctx->have_batch) FAIL(SQG_ESTATE, "load the concordant batch first");
     CK(cudaSetDevice(ctx->device));
     for (int64_t k = 0; k + 1 < K; k++)
         if (bp_chr[k] > bp_chr[k + 1] || (bp_chr[k] == bp_chr[k + 1] && bp_pos[k] > bp_pos[k + 1])) FAIL(SQG_EINVAL, "breakpoints must be sorted by (chr, pos)");
-    if (K == 0) return SQG_OK;
     int rc = run_classify(ctx);
     if (rc) return rc;
-    const DevBatch &b = ctx->batch;
-    const int64_t n = b.n_rec;
-    PHASE_BEGIN("coverage");
-    CK(ctx->d_bpchr.ensure(K)); CK(ctx->d_bppos.ensure(K)); CK(ctx->d_bpkey.ensure(K)); CK(ctx->d_r0.ensure(K)); CK(ctx->d_t.ensure(K)); CK(ctx->d_cov.ensure(K));
+    const int64_t n = ctx->batch.n_rec;
+    CK(ctx->d_bpchr.ensure(K + 1)); CK(ctx->d_bppos.ensure(K + 1)); CK(ctx->d_bpkey.ensure(K + 1)); CK(ctx->d_r0.ensure(K + 1)); CK(ctx->d_t.ensure(K + 1)); CK(ctx->d_cov.ensure(K + 1));
     CK(cudaMemcpyAsync(ctx->d_bpchr.p, bp_chr, K * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_bppos.p, bp_pos, K * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_cov.p, 0, K * 4, ctx->stream));
     // qualifying records compacted in stream order (done already if sqg_build_nodes ran: it only needs the class bytes)
     rc = run_cov_compact(ctx);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->cov_K = K;
+    ctx->cov_nq = n > 0 ? ctx->h_counters.p[15] : 0;
+    return SQG_OK;
+}
+
+// t[k] for k in [k_begin, K) from this batch's qualifying ranks alone, the chain starting fresh at breakpoint k_begin.
+// Values >= nq mean "not passed by any record of this batch" (everything from the first such breakpoint on is unresolved).
+static int cov_chain(sqg_ctx *ctx, int64_t k_begin) {
+    const int64_t n = ctx->batch.n_rec, nq = ctx->cov_nq, K = ctx->cov_K - k_begin;
+    if (K <= 0) return SQG_OK;
     const int64_t n_tiles = (n + kCovTile - 1) / kCovTile;
-    const int64_t nq = n > 0 ? ctx->h_counters.p[15] : 0;
-    LAUNCH(k_cov_r0_tiles, blocks_for(K), kThreads, ctx->d_qkey.p, ctx->d_covtile.p, (int32_t)(n > 0 ? n_tiles : 0), nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos,
-           ctx->d_bpkey.p, ctx->d_r0.p, ctx->d_t.p);
+    const int32_t *bpchr = ctx->d_bpchr.p + k_begin, *bppos = ctx->d_bppos.p + k_begin;
+    uint64_t *bpkey = ctx->d_bpkey.p + k_begin;
+    int64_t *r0 = ctx->d_r0.p + k_begin, *t = ctx->d_t.p + k_begin;
+    LAUNCH(k_cov_r0_tiles, blocks_for(K), kThreads, ctx->d_qkey.p, ctx->d_covtile.p, (int32_t)(n > 0 ? n_tiles : 0), nq, bpchr, bppos, K, ctx->params.concord_dist_pos, bpkey, r0, t);
     {   // t[k] = max(r0[k], t[k-1]+1) whenever the qualifying record right after t[k-1] passes breakpoint k (the common case):
         // a max-plus prefix scan, verified in parallel; the literal one-step-per-record chain runs only if a candidate fails
         size_t tb = 0;
-        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_t.p, ctx->d_t.p, MaxI64(), (int)K, ctx->stream));
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tb, t, t, MaxI64(), (int)K, ctx->stream));
         ENSURE_TEMP(tb);
-        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_t.p, ctx->d_t.p, MaxI64(), (int)K, ctx->stream));
+        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, t, t, MaxI64(), (int)K, ctx->stream));
         ctx->launches += 2;
         CK(cudaMemsetAsync(ctx->d_counters.p + 12, 0, sizeof(int64_t), ctx->stream));
-        LAUNCH(k_cov_verify, blocks_for(K), kThreads, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (int32_t *)(ctx->d_counters.p + 12));
+        LAUNCH(k_cov_verify, blocks_for(K), kThreads, ctx->d_qkey.p, nq, bpchr, bppos, K, ctx->params.concord_dist_pos, r0, t, (int32_t *)(ctx->d_counters.p + 12));
         CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->cov_chain_fallback = *(int32_t *)(ctx->h_counters.p + 12) != 0;
         if (ctx->cov_chain_fallback) {
             // literal chain, chunked at large jumps of r0 (one warp per chunk), validated; whole-list replay as a last resort
             cub::CountingInputIterator<int32_t> cnt(0);
-            IsChainCutOp cop{ctx->d_r0.p};
+            IsChainCutOp cop{r0};
             CK(ctx->d_chunks.ensure(K + 1));
             int32_t *chunks = ctx->d_chunks.p;
             CK(cub::DeviceSelect::If(nullptr, tb, cnt, chunks, (int32_t *)(ctx->d_counters.p + 14), (int)K, cop, ctx->stream));
@@ -1435,32 +1552,114 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
             ctx->launches += 2;
             CK(ctx->d_chain_used.ensure(2 * (size_t)n_chunks + 2));
             int64_t *used = ctx->d_chain_used.p, *need = ctx->d_chain_used.p + n_chunks + 1;
-            LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, chunks, n_chunks,
+            LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, bpchr, bppos, K, ctx->params.concord_dist_pos, r0, t, chunks, n_chunks,
                    used, (const int64_t *)nullptr);
             // chunks whose predecessor's chain runs into them are replayed from its t; a few rounds settle runs of such chunks
             ctx->cov_chain_chunks = n_chunks;
             bool settled = false;
             for (int round = 0; round < 16 && !settled; round++) {
                 CK(cudaMemsetAsync(ctx->d_counters.p + 12, 0, sizeof(int64_t), ctx->stream));
-                LAUNCH(k_cov_chain_check, blocks_for(n_chunks), kThreads, chunks, n_chunks, ctx->d_r0.p, ctx->d_t.p, used, need, (int32_t *)(ctx->d_counters.p + 12));
+                LAUNCH(k_cov_chain_check, blocks_for(n_chunks), kThreads, chunks, n_chunks, r0, t, used, need, (int32_t *)(ctx->d_counters.p + 12));
                 CK(cudaMemcpyAsync(ctx->h_counters.p + 12, ctx->d_counters.p + 12, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
                 if (*(int32_t *)(ctx->h_counters.p + 12) == 0) { settled = true; break; }
-                LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, chunks, n_chunks,
+                LAUNCH(k_cov_chain, blocks_for((int64_t)n_chunks * 32, 128), 128, ctx->d_qkey.p, nq, bpchr, bppos, K, ctx->params.concord_dist_pos, r0, t, chunks, n_chunks,
                        used, (const int64_t *)need);
             }
             if (!settled) {  // a lagging chain through very many chunks: literal replay of the whole list by one warp
                 ctx->cov_chain_chunks = 1;
-                LAUNCH(k_cov_chain, 1, 32, ctx->d_qkey.p, nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos, ctx->d_r0.p, ctx->d_t.p, (const int32_t *)nullptr, 0,
+                LAUNCH(k_cov_chain, 1, 32, ctx->d_qkey.p, nq, bpchr, bppos, K, ctx->params.concord_dist_pos, r0, t, (const int32_t *)nullptr, 0,
                        (int64_t *)nullptr, (const int64_t *)nullptr);
             }
         }
     }
+    return SQG_OK;
+}
+
+// Coverages[k] += #{qualifying rank i < t[k] : start_i <= pos_k < end_i} over this batch's ranks (t = ctx->d_t, local ranks)
+static int cov_count(sqg_ctx *ctx, int32_t *cov_out) {
+    const int64_t K = ctx->cov_K, nq = ctx->cov_nq;
+    CK(cudaMemsetAsync(ctx->d_cov.p, 0, K * 4, ctx->stream));
     PHASE_BEGIN("k_cov_count");
     if (nq > 0) LAUNCH(k_cov_count_tiles, blocks_for(nq, kCovRanks), 256, ctx->d_qkey.p, ctx->d_qend.p, nq, ctx->d_bpkey.p, ctx->d_t.p, K, ctx->d_cov.p);
     PHASE_END("k_cov_count");
-    PHASE_END("coverage");
     CK(cudaMemcpyAsync(cov_out, ctx->d_cov.p, K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return SQG_OK;
+}
+
+extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int32_t *cov_out) {
+    if (!ctx || K < 0 || (K > 0 && (!bp_chr || !bp_pos || !cov_out))) return SQG_EINVAL;
+    if (ctx->shard_count > 1) FAIL(SQG_ESTATE, "this context is a range shard: use sqg_shard_cov_*");
+    if (K == 0) { if (!ctx->have_batch) FAIL(SQG_ESTATE, "load the concordant batch first"); return SQG_OK; }
+    int rc = cov_prepare(ctx, bp_chr, bp_pos, K);
+    if (rc) return rc;
+    PHASE_BEGIN("coverage");
+    rc = cov_chain(ctx, 0);
+    if (rc) return rc;
+    rc = cov_count(ctx, cov_out);
+    if (rc) return rc;
+    PHASE_END("coverage");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SQG_OK;
+}
+
+// Range shards: the chain `indBP advances by at most one per qualifying record` (:3157-3158) runs through the shards in
+// order.  Every shard resolves the breakpoints [k_in, k_out) -- those whose t falls among its own qualifying ranks when the
+// chain enters the shard at breakpoint k_in -- and the caller hands k_out on as the next shard's k_in (shards may run
+// speculatively from a guessed k_in and repeat when the guess was wrong).  *n_pass = number of breakpoints that some record
+// of this shard passes at all, a guess-free upper bound of every later shard's k_in.
+extern "C" int sqg_shard_cov_begin(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_pos, int64_t K, int64_t *nq, int64_t *n_pass) {
+    if (!ctx || K < 0 || (K > 0 && (!bp_chr || !bp_pos)) || !nq || !n_pass) return SQG_EINVAL;
+    int rc = cov_prepare(ctx, bp_chr, bp_pos, K);
+    if (rc) return rc;
+    *nq = ctx->cov_nq; *n_pass = 0;
+    if (K == 0) return SQG_OK;
+    const int64_t n = ctx->batch.n_rec, n_tiles = (n + kCovTile - 1) / kCovTile;
+    LAUNCH(k_cov_r0_tiles, blocks_for(K), kThreads, ctx->d_qkey.p, ctx->d_covtile.p, (int32_t)(n > 0 ? n_tiles : 0), ctx->cov_nq, ctx->d_bpchr.p, ctx->d_bppos.p, K, ctx->params.concord_dist_pos,
+           ctx->d_bpkey.p, ctx->d_r0.p, ctx->d_t.p);
+    CK(ctx->h_t.ensure(K + 1));
+    CK(cudaMemcpyAsync(ctx->h_t.p, ctx->d_r0.p, K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int64_t lo = 0, hi = K;  // r0 is non-decreasing in k: first breakpoint no record of this shard passes
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (ctx->h_t.p[m] < ctx->cov_nq) lo = m + 1; else hi = m; }
+    *n_pass = lo;
+    return SQG_OK;
+}
+extern "C" int sqg_shard_cov_chain(sqg_ctx *ctx, int64_t k_in, int64_t *k_out) {
+    if (!ctx || !k_out || k_in < 0 || k_in > ctx->cov_K) return SQG_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t K = ctx->cov_K;
+    *k_out = k_in;
+    if (k_in == K) return SQG_OK;
+    int rc = cov_chain(ctx, k_in);
+    if (rc) return rc;
+    CK(ctx->h_t.ensure(K + 1));
+    CK(cudaMemcpyAsync(ctx->h_t.p + k_in, ctx->d_t.p + k_in, (K - k_in) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int64_t k = k_in;
+    while (k < K && ctx->h_t.p[k] < ctx->cov_nq) k++;
+    *k_out = k;
+    return SQG_OK;
+}
+// t_global[k] = rank_offset + t[k] for the breakpoints [k_in, k_out) of the last sqg_shard_cov_chain call; other entries untouched
+extern "C" int sqg_shard_cov_owned_t(sqg_ctx *ctx, int64_t rank_offset, int64_t k_in, int64_t k_out, int64_t *t_global) {
+    if (!ctx || !t_global || k_in < 0 || k_out < k_in || k_out > ctx->cov_K) return SQG_EINVAL;
+    for (int64_t k = k_in; k < k_out; k++) t_global[k] = rank_offset + ctx->h_t.p[k];
+    return SQG_OK;
+}
+// cov_partial[k] = this shard's share of Coverages[k] given the global t (unresolved breakpoints: t = total number of ranks)
+extern "C" int sqg_shard_cov_count(sqg_ctx *ctx, int64_t rank_offset, const int64_t *t_global, int32_t *cov_partial) {
+    if (!ctx || (ctx->cov_K > 0 && (!t_global || !cov_partial))) return SQG_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t K = ctx->cov_K, nq = ctx->cov_nq;
+    if (K == 0) return SQG_OK;
+    CK(ctx->h_t.ensure(K + 1));
+    for (int64_t k = 0; k < K; k++) { int64_t v = t_global[k] - rank_offset; ctx->h_t.p[k] = v < 0 ? 0 : (v > nq ? nq : v); }
+    CK(cudaMemcpyAsync(ctx->d_t.p, ctx->h_t.p, K * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PHASE_BEGIN("coverage");
+    int rc = cov_count(ctx, cov_partial);
+    if (rc) return rc;
+    PHASE_END("coverage");
     CK(cudaStreamSynchronize(ctx->stream));
     return SQG_OK;
 }

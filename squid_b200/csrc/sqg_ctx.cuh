@@ -125,6 +125,7 @@ struct sqg_ctx {
     sq::DBuf<int32_t> d_gap, d_pc, d_dp;
     int32_t n_gap = 0, n_pc = 0, n_dp = 0, lmax = 0, n_islands = 0;
     int64_t first_kept = 0;
+    uint64_t end_other = 0;      // otherChr/otherrightmost after the last record of the batch
     sq::DBuf<unsigned char> d_temp;  // CUB temp storage
     sq::DBuf<int64_t> d_counters;    // small device counters
     sq::HBuf<int64_t> h_counters;
@@ -161,6 +162,19 @@ struct sqg_ctx {
     sq::DBuf<int32_t> d_margin;
     sq::DBuf<sq::SeedState> d_seedstate;
     int64_t r_break = 0;
+
+    // range shard of one genome (sqg_set_shard): index 0 owns the chimeric edges and the discordant depth
+    int32_t shard_index = 0, shard_count = 1;
+    bool shard_prior_emission = false;   // some earlier shard has emitted a seed segment (k_seed_prefix is skipped)
+    int32_t shard_g_lo = 0;              // first discordant group this shard owns
+    int32_t shard_init_hint = 0;         // firstfrontindex at the shard's first read
+    int32_t shard_lead_sensitive = 0, shard_out_hint = -1;
+    bool shard_seeded = false;
+    std::vector<sq::SeedOp> shard_ops;   // this shard's seed ops, island order
+    int32_t shard_g_done = 0;
+    int64_t shard_trig_last = 0;
+    int64_t cov_K = 0, cov_nq = 0;       // staged coverage (sqg_shard_cov_*)
+    sq::HBuf<int64_t> h_t;
 
     // segment table
     bool have_nodes = false;

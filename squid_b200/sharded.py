@@ -1,0 +1,212 @@
+"""Exact range-sharded run of the segment-graph path over several contexts / GPUs (C ABI: "Exact range
+sharding" in include/squid_b200.h).  One sorted stream is cut at clean cuts (api.plan_shards), every shard runs the path on
+its own records, and the small per-shard results are exchanged between the stages:
+
+    stage                    exchanged                                   reference lines it reproduces
+    seeds                    seed ops (kind, chr, pos, len)              SegmentGraph.cpp:296-701
+    build                    depth numerators (sum), edge tables         :706-826, :1932-1959
+    hints                    LocateRead's firstfrontindex per boundary   :1568, :1612-1614
+    coverage                 rank counts, chain hand-over k, t, counts   :3124-3166
+
+The combined result is bit-identical to SegmentGraph on the whole stream.  `comm` hides where the shards live: LocalComm
+(every shard in this process, e.g. several contexts on one GPU -- used by the GPU tests) or DistComm (one shard per
+torch.distributed rank: NCCL on the GPUs, gloo in the CPU tests of this logic).  The exchange is written once, in terms of
+`comm.allgather(list of per-local-shard items) -> list of items of ALL shards in shard order`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import shard as _shard
+from .api import ChimericReads, Config, Edges, Nodes, RecordBatch, SegmentGraph, SquidB200Error, SQG_EUNSUPPORTED
+
+
+class LocalComm:
+    """All shards live in this process."""
+    rank, world = 0, 1
+
+    def allgather(self, items: list) -> list:
+        return list(items)
+
+
+class DistComm:
+    """One process per GPU (torch.distributed, backend nccl or gloo); every process may hold several consecutive shards."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allgather(self, items: list) -> list:
+        out = [None] * self.world
+        self.dist.all_gather_object(out, list(items), group=self.group)
+        return [x for sub in out for x in sub]
+
+
+# ---- the exchange logic, free of any device call (tested on CPU with gloo) --------------------------------------------------
+def first_wrong_prior(assumed, op_counts):
+    """Shards run stage 1 assuming `assumed[s]` = "an earlier shard has emitted a seed op".  Returns (s, truth) for the first
+    shard whose assumption is wrong given the op counts of the current runs, or None."""
+    seen = False
+    for s, n in enumerate(op_counts):
+        if assumed[s] != seen:
+            return s, seen
+        seen = seen or n > 0
+    return None
+
+
+def incoming_hints(states):
+    """states[s] = (lead_sensitive, out_hint).  firstfrontindex entering shard s = out_hint of the nearest earlier shard that
+    located a read, 0 at the start of the stream (SegmentGraph.cpp:1568)."""
+    inc, cur = [], 0
+    for lead, out in states:
+        inc.append(cur)
+        if out >= 0:
+            cur = out
+    return inc
+
+
+def chain_k_in_guess(n_pass):
+    """k_in[s] guess = number of breakpoints passed by some record of an earlier shard (exact unless indBP lags across the
+    boundary)."""
+    g, m = [], 0
+    for x in n_pass:
+        g.append(m)
+        m = max(m, x)
+    return g
+
+
+def merge_depth(parts):
+    """parts = [(count3, sumlen3, other_nonempty)] per shard -> sums in the reference's `int` arithmetic (wrap-around)."""
+    c = np.zeros_like(parts[0][0]); s = np.zeros_like(parts[0][1]); o = 0
+    with np.errstate(over="ignore"):
+        for pc, ps, po in parts:
+            c = (c + pc).astype(np.int32); s = (s + ps).astype(np.int32); o |= int(po)
+    return c, s, o
+
+
+class ShardedSegmentGraph:
+    """SegmentGraph over range shards.  `shard_ids` = the shards held by this process (all of them with LocalComm)."""
+
+    def __init__(self, config: Config, RefLength, n_shards: int, shard_ids, comm=None, devices=None):
+        self.comm = comm or LocalComm()
+        self.config, self.RefLength, self.n_shards = config, np.ascontiguousarray(RefLength, np.int32), int(n_shards)
+        self.ids = list(shard_ids)
+        devices = devices if devices is not None else [0] * len(self.ids)
+        self.g = [SegmentGraph(config, self.RefLength, device=d) for d in devices]
+        for g, sid in zip(self.g, self.ids):
+            g.set_shard(sid, self.n_shards)
+        self.vNodes = None
+        self.vEdges = None
+        self.Chimrecord = None
+        self.rounds = {"seeds": 0, "hints": 0, "chain": 0}
+
+    def close(self):
+        for g in self.g:
+            g.close()
+
+    def load(self, batches, chim_factory):
+        """batches[i] = RecordBatch of local shard i; chim_factory() -> a fresh ChimericReads (every shard gets all reads)."""
+        for g, b in zip(self.g, batches):
+            g.load_concordant(b)
+            g.load_chimeric(chim_factory())
+
+    # -- BuildNode_STAR ------------------------------------------------------------------------------------------------
+    def BuildNode_STAR(self) -> Nodes:
+        N = self.n_shards
+        assumed = [s > 0 for s in range(N)]
+        ops = [g.shard_seeds(assumed[sid]) for g, sid in zip(self.g, self.ids)]
+        while True:
+            self.rounds["seeds"] += 1
+            all_ops = self.comm.allgather(ops)
+            wrong = first_wrong_prior(assumed, [int(o.shape[0]) for o in all_ops])
+            if wrong is None:
+                break
+            s, truth = wrong
+            assumed[s] = truth
+            if s in self.ids:
+                i = self.ids.index(s)
+                ops[i] = self.g[i].shard_seeds(truth)
+        cat = np.concatenate(all_ops, axis=0) if all_ops else np.zeros((0, 4), np.int32)
+        parts, node = [], None
+        for g in self.g:
+            c, p, l, c3, s3, other = g.shard_build(cat)
+            node = (c, p, l)
+            parts.append((c3, s3, other))
+        count3, sum3, other = merge_depth(self.comm.allgather(parts))
+        self._fix_hints()
+        length = node[2]
+        support = count3[0] + count3[1] + (count3[2] if other else 0)  # as api.SegmentGraph.BuildNode_STAR
+        depth = sum3[0].astype(np.float64) + sum3[1].astype(np.float64)
+        if other:
+            depth = depth + sum3[2].astype(np.float64)
+            depth = 1.0 * depth / length
+        self.vNodes = Nodes(node[0], node[1], length, support.astype(np.int32), depth, count3, sum3)
+        return self.vNodes
+
+    def _fix_hints(self):
+        used = [0] * self.n_shards
+        while True:
+            self.rounds["hints"] += 1
+            states = self.comm.allgather([g.shard_hint_state() for g in self.g])
+            inc = incoming_hints(states)
+            redo = [s for s in range(self.n_shards) if states[s][0] and used[s] != inc[s]]
+            if not redo:
+                return
+            for s in redo:
+                used[s] = inc[s]
+                if s in self.ids:
+                    self.g[self.ids.index(s)].shard_redo_edges(inc[s])
+
+    # -- BuildEdges ----------------------------------------------------------------------------------------------------
+    def BuildEdges(self) -> Edges:
+        tabs, chim = [], None
+        for g, sid in zip(self.g, self.ids):
+            e = g.BuildEdges()
+            tabs.append((_shard.pack_edge_keys(e.Ind1, e.Ind2, e.Head1, e.Head2), e.Weight))
+            if sid == 0:
+                chim = g.Chimrecord  # trimmed in place by shard 0 (it owns the chimeric reads' LocateRead pass)
+        gathered = self.comm.allgather([(t, chim.a if (chim is not None and sid == 0) else None) for t, sid in zip(tabs, self.ids)])
+        keys, w = _shard.merge_edge_tables([t for t, _ in gathered])
+        i1, i2, h1, h2 = _shard.unpack_edge_keys(keys)
+        self.vEdges = Edges(i1, i2, h1, h2, w)
+        ca = next((a for _, a in gathered if a is not None), None)
+        self.Chimrecord = ChimericReads(ca) if ca is not None else None
+        return self.vEdges
+
+    # -- ExactBPConcordantSupport's BAM pass -----------------------------------------------------------------------------
+    def BPCoverage(self, bp_chr, bp_pos) -> np.ndarray:
+        K = int(np.asarray(bp_chr).shape[0])
+        if K == 0:
+            return np.zeros(0, np.int32)
+        info = self.comm.allgather([g.shard_cov_begin(bp_chr, bp_pos) for g in self.g])
+        nq = [x[0] for x in info]
+        off = np.concatenate([[0], np.cumsum(nq)]).astype(np.int64)
+        k_in = chain_k_in_guess([x[1] for x in info])
+        k_in[0] = 0
+        k_out = {sid: g.shard_cov_chain(k_in[sid]) for g, sid in zip(self.g, self.ids)}
+        while True:
+            self.rounds["chain"] += 1
+            outs = self.comm.allgather([k_out[sid] for sid in self.ids])
+            redo = [s for s in range(1, self.n_shards) if k_in[s] != outs[s - 1]]
+            if not redo:
+                break
+            s = redo[0]  # the hand-over is sequential: settle the first broken link, later ones may change with it
+            k_in[s] = outs[s - 1]
+            if s in self.ids:
+                k_out[s] = self.g[self.ids.index(s)].shard_cov_chain(k_in[s])
+        t = np.full(K, -1, np.int64)
+        for g, sid in zip(self.g, self.ids):
+            g.shard_cov_owned_t(int(off[sid]), k_in[sid], k_out[sid], t)
+        t = self._max_t(t)
+        t[t < 0] = int(off[-1])  # never passed: every qualifying record is tested against the breakpoint
+        parts = self.comm.allgather([g.shard_cov_count(int(off[sid]), t) for g, sid in zip(self.g, self.ids)])
+        cov = np.zeros(K, np.int32)
+        for p in parts:
+            cov += p
+        return cov
+
+    def _max_t(self, t_local: np.ndarray) -> np.ndarray:
+        """Every process filled the entries its shards own: elementwise max over processes."""
+        got = self.comm.allgather([t_local])
+        return np.max(np.stack(got, axis=0), axis=0)
