@@ -1,0 +1,70 @@
+"""Exact range sharding: one sorted stream cut at clean cuts (sqg_plan_shards), every shard on its own
+context, the per-shard results exchanged by squid_b200.sharded -- the combined segments, Support, AvgDepth, edges, trimmed
+chimeric blocks and breakpoint coverage must equal the reference build's on the WHOLE stream, bit for bit.  All shards run
+on cuda:0 here (LocalComm); the same driver runs one shard per rank over NCCL (tests/tools/dist_sharded.py)."""
+import numpy as np
+import pytest
+
+from tests import common
+from tests.tools import gpu_sharded_diag as diag
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n_pairs, seed, disc_frac, ref_len, kwargs, shard counts
+    (20000, 17, 0.02, None, {}, (2, 8)),
+    (30000, 31, 0.005, [3000000, 2000000, 500000, 16569], {"n_genes": 20}, (3,)),
+    (100000, 1003, 0.02, "grch38", {}, (2, 5)),
+    (150000, 2024, 0.05, "grch38", {"fusion_support": 10}, (4,)),
+]
+
+
+@pytest.mark.parametrize("n_pairs,seed,disc,ref_len,kw,shards", CASES)
+def test_sharded_matches_reference(tmp_path, built_lib, ref_oracle, n_pairs, seed, disc, ref_len, kw, shards):
+    from oracle import pyref
+    from squid_b200 import api, synth
+    rl = synth.GRCH38_LEN if ref_len == "grch38" else ref_len
+    cp, hp, *_ = common.write_case(str(tmp_path), n_pairs, seed, disc, rl, **kw)
+    ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    case = api.HostCase(cp, hp)
+    for ns in shards:
+        cuts = api.plan_shards(case.batch, case.chimeric, case.config, len(case.ref_len), ns)
+        assert len(cuts) - 1 >= 2, "the planner found no clean cut"
+        got = diag.run_sharded(case, cuts, ref)
+        common.assert_same(ref, got)
+        assert got["support"] == pyref.support_map(ref)
+        for g in got["sg"].g:
+            assert g.launch_count() > 0
+        got["sg"].close()
+
+
+def test_sharded_lagging_coverage_chain(tmp_path, built_lib):
+    """Dense breakpoints: indBP lags behind the stream and the chain crosses shard boundaries, so the speculative hand-over
+    (k_in guessed from the breakpoints earlier shards pass) is wrong and has to be repaired in rounds.  Sharded == single."""
+    from squid_b200 import api
+    cp, hp, *_ = common.write_case(str(tmp_path), 40000, 23, 0.02)
+    case = api.HostCase(cp, hp)
+    bp = diag.dense_bps(case)
+    g1 = api.SegmentGraph(case.config, case.ref_len)
+    g1.load_concordant(case.batch); g1.load_chimeric(api.ChimericReads(case.chimeric.a))
+    want = g1.BPCoverage(bp[:, 0], bp[:, 1])
+    cuts = api.plan_shards(case.batch, case.chimeric, case.config, len(case.ref_len), 4)
+    assert len(cuts) - 1 >= 3
+    got = diag.run_sharded(case, cuts, None, bp)
+    assert got["rounds"]["chain"] > 1  # the guess must have been wrong somewhere, else this test does not test the repair
+    assert np.array_equal(got["cov"], want)
+
+
+def test_shard_context_refuses_whole_stream_calls(tmp_path, built_lib):
+    from squid_b200 import api
+    cp, hp, *_ = common.write_case(str(tmp_path), 3000, 3, 0.05)
+    case = api.HostCase(cp, hp)
+    g = api.SegmentGraph(case.config, case.ref_len)
+    g.set_shard(1, 2)
+    g.load_concordant(case.batch); g.load_chimeric(case.chimeric)
+    with pytest.raises(api.SquidB200Error):
+        g.BuildNode_STAR()
+    with pytest.raises(api.SquidB200Error):
+        g.BPCoverage([0], [100])
+    with pytest.raises(api.SquidB200Error):
+        g.shard_build(np.zeros((0, 4), np.int32))  # stage order
