@@ -214,13 +214,12 @@ def main():
             tl[name] = tl.get(name, 0.0) + 1e3 * (t1 - t_[0])
             t_[0] = t1
         # sqg_build_edges trims the chimeric blocks in place (LocateRead, :1229-1248): restore the four mutable arrays
-        chim = state.get("chim")
-        if chim is None:
-            chim = state["chim"] = api.ChimericReads(chim0.a)
-        else:
-            for k in ("blk_ref_pos", "blk_read_pos", "blk_match_ref", "blk_match_read"):
-                np.copyto(chim.a[k], chim0.a[k])
-        lap("chim_restore")
+        # -- a caller that runs the path once never pays for that, so every step gets its own pristine copy, made before the
+        # timed region (chim_pool is refilled by timed() before each measurement)
+        pool = state.setdefault("chim_pool", [])
+        chim = pool.pop() if pool else api.ChimericReads(chim0.a)
+        state["chim"] = chim
+        lap("chim_input")
         if resident:
             g.attach_concordant_device(dstruct, keepalive=batch)
         else:
@@ -282,6 +281,7 @@ def main():
     def timed(resident: bool, steps: int, warmup: int):
         for _ in range(warmup):
             step(resident)
+        state["chim_pool"] = [api.ChimericReads(chim0.a) for _ in range(steps)]  # pristine inputs of the timed steps
         barrier()
         state["timeline"] = {}
         state["timed"] = True

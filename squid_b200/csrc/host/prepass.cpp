@@ -208,7 +208,9 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     const bool timing = getenv("SQH_TIMING") != nullptr;
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *w) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[prepass] %s %.1f ms\n", w, 1e3 * std::chrono::duration<double>(t - T0).count()); T0 = t; } };
-    out = ChimPrepass();
+    // buffers are reused from call to call (thread-local scratch, `out` keeps its capacity): at a few hundred thousand reads
+    // allocation, first-touch page faults and value-initialisation cost as much as the work itself
+    out.part_chr.clear(); out.part_pos.clear(); out.groups.clear();
     typedef SortKey DB;  // key = (RefID,RefPos) packed, k = block index
     // The read loop (:206-262) is split into contiguous chunks of reads, one per thread; chunk results are concatenated in
     // order.  The only coupling between reads is `bamdiscordant.back()` at :257: a chunk that has not pushed a discordant
@@ -216,11 +218,17 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     const int local_ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;  // one process per GPU shares the host
     // half the cores, split between the processes of the node: the calling threads spin on their GPUs meanwhile (and NCCL has
     // its own), and an oversubscribed OpenMP team pays for every barrier
-    const int cores = std::max(local_ranks == 1 ? 1 : 2, omp_get_num_procs() / 2 / local_ranks);
+    int cores = std::max(local_ranks == 1 ? 1 : 2, omp_get_num_procs() / 2 / local_ranks);
+    if (getenv("SQH_PREPASS_THREADS")) cores = std::max(1, atoi(getenv("SQH_PREPASS_THREADS")));  // tuning hook
     int T = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)cores, 16, c.n_reads / 4096 + 1}));
     if (getenv("SQH_PREPASS_CHUNKS")) T = std::max(1, atoi(getenv("SQH_PREPASS_CHUNKS")));  // test hook: force the chunked path on small inputs
     struct Chunk { std::vector<DB> dis; std::vector<std::pair<int, int>> part; std::vector<uint32_t> pend; };
-    std::vector<Chunk> chunks((size_t)T);
+    static thread_local std::vector<Chunk> tl_chunks;
+    static thread_local std::vector<DB> tl_dis;
+    std::vector<Chunk> &chunks = tl_chunks;  // (references: the OpenMP workers must see the caller's instances, not their own)
+    std::vector<DB> &dis = tl_dis;
+    if (chunks.size() < (size_t)T) chunks.resize((size_t)T);
+    for (Chunk &ch : chunks) { ch.dis.clear(); ch.part.clear(); ch.pend.clear(); }
     auto same_block = [&](uint32_t l, uint32_t b) {  // SingleBamRec_t::Same(): every field incl. IsFirstRead; b is a SecondMate block
         const uint32_t *ro = c.read_off;
         int64_t lo = 0, hi = c.n_reads;  // read owning block l
@@ -280,18 +288,25 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
             }
         }
     }
-    std::vector<DB> dis;
     std::vector<std::pair<int, int>> part((size_t)n_ref, std::make_pair(0, 0));  // resize()d then appended (:203-204)
     {
         size_t nd = 0, np = part.size();
-        for (const Chunk &ch : chunks) { nd += ch.dis.size(); np += ch.part.size() + ch.pend.size(); }
-        dis.reserve(nd); part.reserve(np);
-        for (const Chunk &ch : chunks) {
-            for (uint32_t b : ch.pend)
-                if (dis.empty() || !same_block(dis.back().k, b)) part.push_back({c.blk_ref_id[b], c.blk_is_reverse[b] ? c.blk_ref_pos[b] : c.blk_ref_pos[b] + c.blk_match_ref[b]});
-            dis.insert(dis.end(), ch.dis.begin(), ch.dis.end());
+        std::vector<size_t> off((size_t)T + 1, 0);
+        for (int t = 0; t < T; t++) { const Chunk &ch = chunks[(size_t)t]; off[(size_t)t + 1] = off[(size_t)t] + ch.dis.size(); np += ch.part.size() + ch.pend.size(); }
+        nd = off[(size_t)T];
+        if (dis.size() != nd) dis.resize(nd);
+        part.reserve(np);
+        for (int t = 0; t < T; t++) {
+            const Chunk &ch = chunks[(size_t)t];
+            for (uint32_t b : ch.pend) {  // `bamdiscordant.back()` as the earlier chunks left it
+                int q = t - 1;
+                while (q >= 0 && chunks[(size_t)q].dis.empty()) q--;
+                if (q < 0 || !same_block(chunks[(size_t)q].dis.back().k, b)) part.push_back({c.blk_ref_id[b], c.blk_is_reverse[b] ? c.blk_ref_pos[b] : c.blk_ref_pos[b] + c.blk_match_ref[b]});
+            }
             part.insert(part.end(), ch.part.begin(), ch.part.end());
         }
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+        for (int t = 0; t < T; t++) std::copy(chunks[(size_t)t].dis.begin(), chunks[(size_t)t].dis.end(), dis.begin() + (ptrdiff_t)off[(size_t)t]);
     }
     lap("reads");
     std::sort(part.begin(), part.end(), [](std::pair<int, int> a, std::pair<int, int> b) { return a.first == b.first ? a.second < b.second : a.first < b.first; });
@@ -303,7 +318,7 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     lap("disc sort");
     out.part_chr.reserve(part.size()); out.part_pos.reserve(part.size());
     for (auto &p : part) { out.part_chr.push_back(p.first); out.part_pos.push_back(p.second); }
-    out.disc.resize(dis.size() + 1);
+    if (out.disc.size() != dis.size() + 1) out.disc.resize(dis.size() + 1);
     {   // gather the sorted blocks (random access into the caller's arrays)
         const long long nd = (long long)dis.size();
 #pragma omp parallel for num_threads(std::min(cores, 16)) schedule(static)
@@ -374,3 +389,15 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     lap("groups");
 }
 }  // namespace sqh
+
+// test / tuning hook: milliseconds of the `iters`-th consecutive pre-pass of the same reads (buffers warm, as in a context)
+extern "C" double sqh_time_prepass(const sqg_chimeric *c, int32_t n_ref, int32_t read_len, int iters) {
+    sqh::ChimPrepass pre;
+    double ms = 0;
+    for (int i = 0; i < iters; i++) {
+        const auto t0 = std::chrono::steady_clock::now();
+        sqh::chimeric_prepass(*c, n_ref, read_len, pre);
+        ms = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return ms;
+}
