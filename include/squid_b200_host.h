@@ -5,8 +5,8 @@
  *                     (src/ReadRec.cpp:329-413) + the per-record ReadRec_t decode
  *                     (src/ReadRec.cpp:10-88) and tag / ChimName probes (src/SegmentGraph.cpp:297-302)
  *                     that the reference repeats inside each of its three BAM passes.
- * Inputs are SQMB files (include/sqmb_format.h), the uncompressed BAM stand-in used by the tests
- * and the benchmark; a BGZF/BAM front end is SURVEY.md §8(f) row 1 ("next").
+ * Inputs are BAM files (sqh_open_bam_case) or SQMB files (include/sqmb_format.h), the uncompressed BAM stand-in that
+ * also feeds the test oracle's BamReader shim.
  */
 #ifndef SQUID_B200_HOST_H
 #define SQUID_B200_HOST_H
@@ -25,6 +25,10 @@ typedef struct sqh_options {   /* src/Config.cpp:18-28 */
 } sqh_options;
 void sqh_default_options(sqh_options *o);
 int sqh_open_case(const char *concordant_sqmb, const char *chimeric_sqmb, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen);
+/* The same from coordinate-sorted BAM files (BGZF-compressed or plain): replaces BamTools' BamReader::Open / GetHeader /
+ * GetNextAlignment on the path (src/ReadRec.cpp:271-279, 340-343; src/SegmentGraph.cpp:293-296, 1570-1577, 3126-3129).
+ * The file is inflated on all cores and decoded once for all three phases. */
+int sqh_open_bam_case(const char *concordant_bam, const char *chimeric_bam, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen);
 void sqh_close_case(sqh_case *c);
 const sqg_batch *sqh_case_batch(const sqh_case *c);
 sqg_chimeric *sqh_case_chimeric(sqh_case *c);

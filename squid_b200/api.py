@@ -66,7 +66,7 @@ EXPORTS = [
     "sqg_phase_ms", "sqg_launch_count", "sqg_stat",
     "sqg_plan_shards", "sqg_set_shard", "sqg_shard_seeds", "sqg_shard_build", "sqg_shard_hint_state", "sqg_shard_redo_edges",
     "sqg_shard_cov_begin", "sqg_shard_cov_chain", "sqg_shard_cov_owned_t", "sqg_shard_cov_count",
-    "sqh_default_options", "sqh_open_case", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
+    "sqh_default_options", "sqh_open_case", "sqh_open_bam_case", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
     "sqh_case_n_ref", "sqh_case_ref_len", "sqh_case_blocks",
 ]
 
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
     L.sqg_shard_cov_count.argtypes = [_P, C.c_int64, _P, _P]
     L.sqh_default_options.argtypes = [pp(sqh_options)]; L.sqh_default_options.restype = None
     L.sqh_open_case.argtypes = [C.c_char_p, C.c_char_p, pp(sqh_options), pp(_P), C.c_char_p, C.c_int]
+    L.sqh_open_bam_case.argtypes = [C.c_char_p, C.c_char_p, pp(sqh_options), pp(_P), C.c_char_p, C.c_int]
     L.sqh_close_case.argtypes = [_P]; L.sqh_close_case.restype = None
     L.sqh_case_batch.argtypes = [_P]; L.sqh_case_batch.restype = pp(sqg_batch)
     L.sqh_case_chimeric.argtypes = [_P]; L.sqh_case_chimeric.restype = pp(sqg_chimeric)
@@ -223,7 +224,8 @@ class ChimericReads:
 class HostCase:
     """Host twin front end: SQMB files -> Chimrecord + packed concordant batch (sqh_open_case)."""
 
-    def __init__(self, concordant_sqmb: str, chimeric_sqmb: str, **opts):
+    def __init__(self, concordant_sqmb: str, chimeric_sqmb: str, bam: bool = False, **opts):
+        """bam=True: the two paths are coordinate-sorted BAM files (sqh_open_bam_case), else SQMB tables."""
         L = lib()
         o = sqh_options()
         L.sqh_default_options(C.byref(o))
@@ -231,7 +233,7 @@ class HostCase:
             setattr(o, k, v)
         h = _P()
         err = C.create_string_buffer(512)
-        rc = L.sqh_open_case(concordant_sqmb.encode(), chimeric_sqmb.encode(), C.byref(o), C.byref(h), err, 512)
+        rc = (L.sqh_open_bam_case if bam else L.sqh_open_case)(concordant_sqmb.encode(), chimeric_sqmb.encode(), C.byref(o), C.byref(h), err, 512)
         if rc != 0:
             raise SquidB200Error(rc, err.value.decode())
         self._h = h

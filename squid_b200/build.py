@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "squid_b200", "csrc")
 OUT = os.path.join(ROOT, "squid_b200", "libsquid_b200.so")
 CU = ["sqg_api.cu"]
-CPP = ["host/readrec.cpp", "host/chimeric.cpp", "host/prepass.cpp", "host/host_api.cpp", "host/plan.cpp"]
+CPP = ["host/readrec.cpp", "host/chimeric.cpp", "host/prepass.cpp", "host/host_api.cpp", "host/plan.cpp", "host/bam.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-Wno-deprecated-declarations",
               "-Wno-deprecated-declarations", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (f, out))
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-lpthread", "-lgomp"]
+    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-lpthread", "-lgomp", "-lz"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

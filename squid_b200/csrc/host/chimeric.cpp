@@ -29,17 +29,29 @@ std::string name_at(const SqmbView &v, uint64_t r) {
     return s;
 }
 
+AlnSource source_of(const SqmbView &v) {
+    AlnSource s;
+    s.n_rec = v.n_rec;
+    s.at = [&v](uint64_t r) { return alignment_at(v, r); };
+    s.name = [&v](uint64_t r) { return name_at(v, r); };
+    return s;
+}
+void load_chimeric(const SqmbView &chim, HostConfig &cfg, std::vector<Read> &out) { load_chimeric(source_of(chim), cfg, out); }
+int pack_concordant(const SqmbView &conc, const HostConfig &cfg, const std::unordered_set<std::string> &chim_names, PackedBatch &out, std::string &err) {
+    return pack_concordant(source_of(conc), cfg, chim_names, out, err);
+}
+
 // src/ReadRec.cpp:329-413
-void load_chimeric(const SqmbView &chim, HostConfig &cfg, std::vector<Read> &out) {
+void load_chimeric(const AlnSource &chim, HostConfig &cfg, std::vector<Read> &out) {
     std::vector<Read> recs;
     std::vector<int> sample;  // first five totals (ReadRec.cpp:336, 347-348)
     Decoded d;
     for (uint64_t r = 0; r < chim.n_rec; r++) {
-        Alignment a = alignment_at(chim, r);
+        Alignment a = chim.at(r);
         if (!a.is_mapped() || a.is_dup()) continue;  // :344
         decode_alignment(a, cfg, d);
         Read rd;
-        rd.qname = name_at(chim, r);
+        rd.qname = chim.name(r);
         if (rd.qname.size() >= 2) {  // :12-13
             const std::string tail = rd.qname.substr(rd.qname.size() - 2);
             if (tail == "/1" || tail == "/2") rd.qname.resize(rd.qname.size() - 2);
@@ -96,11 +108,9 @@ sqg_batch PackedBatch::view() const {
     return b;
 }
 
-int pack_concordant(const SqmbView &conc, const HostConfig &cfg, const std::unordered_set<std::string> &chim_names, PackedBatch &out, std::string &err) {
+int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::unordered_set<std::string> &chim_names, PackedBatch &out, std::string &err) {
     const uint64_t n = conc.n_rec;
-    out.ref_id.assign(conc.ref_id, conc.ref_id + n); out.pos.assign(conc.pos, conc.pos + n);
-    out.mate_ref_id.assign(conc.mate_ref_id, conc.mate_ref_id + n); out.mate_pos.assign(conc.mate_pos, conc.mate_pos + n);
-    out.flag.assign(conc.flag, conc.flag + n); out.mapq.assign(conc.mapq, conc.mapq + n);
+    out.ref_id.resize(n); out.pos.resize(n); out.mate_ref_id.resize(n); out.mate_pos.resize(n); out.flag.resize(n); out.mapq.resize(n);
     out.end_pos.resize(n); out.total_len.resize(n); out.lowphred_run.resize(n); out.aux.resize(n);
     out.blk_off.assign(n + 1, 0);
     // pass 1 (parallel over record ranges): per-record summaries and block counts
@@ -112,7 +122,9 @@ int pack_concordant(const SqmbView &conc, const HostConfig &cfg, const std::unor
         Decoded d;
         std::vector<Block> &acc = tblocks[t];
         for (uint64_t r = lo; r < hi; r++) {
-            Alignment a = alignment_at(conc, r);
+            Alignment a = conc.at(r);
+            out.ref_id[r] = a.ref_id; out.pos[r] = a.pos; out.mate_ref_id[r] = a.mate_ref_id; out.mate_pos[r] = a.mate_pos;
+            out.flag[r] = a.flag; out.mapq[r] = a.mapq;
             decode_alignment(a, cfg, d);
             if (d.blocks.size() > 16) { terr[t] = "record " + std::to_string(r) + " has more than 16 aligned blocks"; return; }
             out.end_pos[r] = a.end_pos();
@@ -121,7 +133,7 @@ int pack_concordant(const SqmbView &conc, const HostConfig &cfg, const std::unor
             uint8_t aux = 0;
             if (a.tag_xa) aux |= SQG_AUX_XA;
             if (a.tag_ih && a.ih_value > 1) aux |= SQG_AUX_IH_GT1;
-            if (!chim_names.empty() && chim_names.count(name_at(conc, r))) aux |= SQG_AUX_CHIMNAME;
+            if (!chim_names.empty() && chim_names.count(conc.name(r))) aux |= SQG_AUX_CHIMNAME;
             out.aux[r] = aux;
             out.blk_off[r + 1] = (uint32_t)d.blocks.size();
             acc.insert(acc.end(), d.blocks.begin(), d.blocks.end());

@@ -3,6 +3,7 @@
 #ifndef SQUID_B200_HOST_CHIMERIC_H
 #define SQUID_B200_HOST_CHIMERIC_H
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -14,6 +15,16 @@ namespace sqh {
 
 Alignment alignment_at(const SqmbView &v, uint64_t r);
 std::string name_at(const SqmbView &v, uint64_t r);
+
+// An alignment-level input (what BamReader::GetNextAlignment yields, in file order): SQMB tables and decoded BAM files
+// (host/bam.h) both present themselves through this.
+struct AlnSource {
+    uint64_t n_rec = 0;
+    std::function<Alignment(uint64_t)> at;
+    std::function<std::string(uint64_t)> name;   // BamAlignment::Name, raw
+};
+AlnSource source_of(const SqmbView &v);
+void load_chimeric(const AlnSource &chim, HostConfig &cfg, std::vector<Read> &out);
 
 // Chimrecord: reads grouped by Qname, mates merged, blocks sorted by read position, sorted by front
 // block, PCR duplicates removed; sets cfg.read_len (median of the first five totals).
@@ -34,6 +45,7 @@ struct PackedBatch {
 // suffix-stripped Qnames of Chimrecord; the gate compares the RAW record name against them
 // (SURVEY.md App. A-3), so a "/1" or "/2" suffixed name never matches.
 int pack_concordant(const SqmbView &conc, const HostConfig &cfg, const std::unordered_set<std::string> &chim_names, PackedBatch &out, std::string &err);
+int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::unordered_set<std::string> &chim_names, PackedBatch &out, std::string &err);
 
 // Owning storage behind a sqg_chimeric.
 struct PackedChimeric {

@@ -5,12 +5,14 @@
 #include <string>
 #include <unordered_set>
 
+#include "bam.h"
 #include "chimeric.h"
 #include "squid_b200_host.h"
 
 struct sqh_case {
     sqh::HostConfig cfg;
     SqmbView conc, chim;
+    sqh::BamTable bconc, bchim;
     std::vector<sqh::Read> reads;
     sqh::PackedBatch batch;
     sqh::PackedChimeric pchim;
@@ -26,7 +28,7 @@ void sqh_default_options(sqh_options *o) {
     o->phred33 = 1; o->max_lowphred_len = 10; o->min_phred = 4; o->min_mapq = -1; o->concord_dist_pos = 50000; o->concord_dist_idx = 20;
 }
 
-int sqh_open_case(const char *conc_path, const char *chim_path, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen) {
+static int open_case(bool bam, const char *conc_path, const char *chim_path, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen) {
     auto fail = [&](int code, const std::string &m) { if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", m.c_str()); return code; };
     if (!conc_path || !chim_path || !out) return fail(SQG_EINVAL, "null argument");
     *out = nullptr;
@@ -36,15 +38,25 @@ int sqh_open_case(const char *conc_path, const char *chim_path, const sqh_option
     if (opt) o = *opt; else sqh_default_options(&o);
     c->cfg.phred33 = o.phred33 != 0; c->cfg.max_lowphred_len = o.max_lowphred_len; c->cfg.min_phred = o.min_phred;
     c->cfg.min_mapq = o.min_mapq < 0 ? 255 : o.min_mapq; c->cfg.concord_dist_pos = o.concord_dist_pos; c->cfg.concord_dist_idx = o.concord_dist_idx;
-    if (!c->conc.open(conc_path)) { delete c; return fail(SQG_EINVAL, std::string("cannot open ") + conc_path); }
-    if (!c->chim.open(chim_path)) { delete c; return fail(SQG_EINVAL, std::string("cannot open ") + chim_path); }
-    c->ref_len.assign(c->conc.ref_len, c->conc.ref_len + c->conc.n_ref);
-    sqh::load_chimeric(c->chim, c->cfg, c->reads);
+    sqh::AlnSource sconc, schim;
+    if (bam) {  // BGZF/BAM front end (host/bam.h): BamReader::Open + GetHeader + GetNextAlignment of the reference
+        std::string e;
+        if (!c->bconc.open(conc_path, e)) { delete c; return fail(SQG_EINVAL, e); }
+        if (!c->bchim.open(chim_path, e)) { delete c; return fail(SQG_EINVAL, e); }
+        c->ref_len = c->bconc.ref_len;  // BuildRefName reads the header of the concordant BAM (ReadRec.cpp:267-283)
+        sconc = c->bconc.source(); schim = c->bchim.source();
+    } else {
+        if (!c->conc.open(conc_path)) { delete c; return fail(SQG_EINVAL, std::string("cannot open ") + conc_path); }
+        if (!c->chim.open(chim_path)) { delete c; return fail(SQG_EINVAL, std::string("cannot open ") + chim_path); }
+        c->ref_len.assign(c->conc.ref_len, c->conc.ref_len + c->conc.n_ref);
+        sconc = sqh::source_of(c->conc); schim = sqh::source_of(c->chim);
+    }
+    sqh::load_chimeric(schim, c->cfg, c->reads);
     std::unordered_set<std::string> names;
     names.insert("");  // ChimName is pre-sized with empty strings before the names are appended (SegmentGraph.cpp:196-198)
     for (const sqh::Read &r : c->reads) names.insert(r.qname);
     std::string err;
-    int rc = sqh::pack_concordant(c->conc, c->cfg, names, c->batch, err);
+    int rc = sqh::pack_concordant(sconc, c->cfg, names, c->batch, err);
     if (rc) { delete c; return fail(rc, err); }
     c->pchim.from_reads(c->reads);
     c->bview = c->batch.view();
@@ -54,6 +66,12 @@ int sqh_open_case(const char *conc_path, const char *chim_path, const sqh_option
     *out = c;
     return SQG_OK;
 }
+int sqh_open_case(const char *conc_path, const char *chim_path, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen) {
+    return open_case(false, conc_path, chim_path, opt, out, errbuf, errlen);
+}
+int sqh_open_bam_case(const char *conc_bam, const char *chim_bam, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen) {
+    return open_case(true, conc_bam, chim_bam, opt, out, errbuf, errlen);
+}
 void sqh_close_case(sqh_case *c) { delete c; }
 const sqg_batch *sqh_case_batch(const sqh_case *c) { return c ? &c->bview : nullptr; }
 sqg_chimeric *sqh_case_chimeric(sqh_case *c) { return c ? &c->cview : nullptr; }
@@ -61,7 +79,7 @@ const sqg_config *sqh_case_config(const sqh_case *c) { return c ? &c->gcfg : nul
 int32_t sqh_case_n_ref(const sqh_case *c) { return c ? (int32_t)c->ref_len.size() : 0; }
 const int32_t *sqh_case_ref_len(const sqh_case *c) { return c ? c->ref_len.data() : nullptr; }
 int32_t sqh_case_blocks(const sqh_case *c, int64_t r, int32_t *out4, int32_t max_blocks, int32_t *total_len, int32_t *lowphred_run) {
-    if (!c || r < 0 || (uint64_t)r >= c->conc.n_rec) return -1;
+    if (!c || r < 0 || (size_t)r + 1 >= c->batch.blk_off.size()) return -1;
     const uint32_t o = c->batch.blk_off[r], n = c->batch.blk_off[r + 1] - o;
     for (uint32_t k = 0; k < n && (int32_t)k < max_blocks; k++) {
         out4[4 * k] = c->batch.blk_ref_pos[o + k]; out4[4 * k + 1] = c->batch.blk_match_ref[o + k];

@@ -189,3 +189,21 @@ def test_dense_breakpoints_lagging_chain(tmp_path, built_lib):
     got = g.BPCoverage(bp[:, 0], bp[:, 1])
     assert g.stat("cov_chain_fallback") == 1  # the shortcut must have failed, else this test does not test the chain
     assert np.array_equal(got, want)
+
+
+def test_bam_input_matches_reference(tmp_path, built_lib, ref_oracle):
+    """The same case fed as real BGZF-compressed BAM files through the library's own BAM front end (sqh_open_bam_case)."""
+    from oracle import pyref
+    from squid_b200 import api, bamio
+    cp, hp, conc, chim, info = common.write_case(str(tmp_path), 8000, 19, 0.03)
+    ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    cb, hb = str(tmp_path / "conc.bam"), str(tmp_path / "chim.bam")
+    bamio.write_bam(cb, conc, block=8191); bamio.write_bam(hb, chim)
+    case = api.HostCase(cb, hb, bam=True)
+    g = api.SegmentGraph(case.config, case.ref_len)
+    nodes = g.BuildNode_STAR(case.chimeric, case.batch)
+    edges = g.BuildEdges()
+    got = {"nodes": np.stack([nodes.Chr, nodes.Position, nodes.Length, nodes.Support], axis=1).astype(np.int32), "avgdepth": nodes.AvgDepth,
+           "edges": edges.table(), "chim_after_edges": case.chimeric.block_table()}
+    common.assert_same(ref, got)
+    assert g.ExactBPConcordantSupport(ref["final_nodes"], ref["final_edges"], pyref.exactbp_map(ref)) == pyref.support_map(ref)
