@@ -88,8 +88,9 @@ def merge_depth(parts):
 class ShardedSegmentGraph:
     """SegmentGraph over range shards.  `shard_ids` = the shards held by this process (all of them with LocalComm)."""
 
-    def __init__(self, config: Config, RefLength, n_shards: int, shard_ids, comm=None, devices=None):
+    def __init__(self, config: Config, RefLength, n_shards: int, shard_ids, comm=None, devices=None, force_hint_redo: bool = False):
         self.comm = comm or LocalComm()
+        self.force_hint_redo = force_hint_redo  # test hook: every shard repeats its edge pass with its true incoming hint
         self.config, self.RefLength, self.n_shards = config, np.ascontiguousarray(RefLength, np.int32), int(n_shards)
         self.ids = list(shard_ids)
         devices = devices if devices is not None else [0] * len(self.ids)
@@ -150,7 +151,7 @@ class ShardedSegmentGraph:
             self.rounds["hints"] += 1
             states = self.comm.allgather([g.shard_hint_state() for g in self.g])
             inc = incoming_hints(states)
-            redo = [s for s in range(self.n_shards) if states[s][0] and used[s] != inc[s]]
+            redo = [s for s in range(self.n_shards) if (states[s][0] or self.force_hint_redo) and used[s] != inc[s]]
             if not redo:
                 return
             for s in redo:

@@ -55,6 +55,19 @@ def test_sharded_lagging_coverage_chain(tmp_path, built_lib):
     assert np.array_equal(got["cov"], want)
 
 
+def test_sharded_hint_handover_redo(tmp_path, built_lib, ref_oracle):
+    """Every shard behind the first repeats its edge pass with the firstfrontindex its predecessors really left (the path a
+    shard takes when one of its leading reads is hint-sensitive): same edges as the reference."""
+    from squid_b200 import api
+    cp, hp, *_ = common.write_case(str(tmp_path), 40000, 23, 0.02)
+    ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    case = api.HostCase(cp, hp)
+    cuts = api.plan_shards(case.batch, case.chimeric, case.config, len(case.ref_len), 4)
+    got = diag.run_sharded(case, cuts, ref, force_hint_redo=True)
+    assert got["rounds"]["hints"] > 1
+    common.assert_same(ref, got)
+
+
 def test_shard_context_refuses_whole_stream_calls(tmp_path, built_lib):
     from squid_b200 import api
     cp, hp, *_ = common.write_case(str(tmp_path), 3000, 3, 0.05)

@@ -22,9 +22,9 @@ CASES = [
 ]
 
 
-def run_sharded(case, cuts, ref=None, bps=None):
+def run_sharded(case, cuts, ref=None, bps=None, **kw):
     ns = len(cuts) - 1
-    sg = sharded.ShardedSegmentGraph(case.config, case.ref_len, ns, list(range(ns)))
+    sg = sharded.ShardedSegmentGraph(case.config, case.ref_len, ns, list(range(ns)), **kw)
     sg.load([case.batch.slice(cuts[i], cuts[i + 1]) for i in range(ns)], lambda: api.ChimericReads(case.chimeric.a))
     nodes = sg.BuildNode_STAR()
     edges = sg.BuildEdges()
