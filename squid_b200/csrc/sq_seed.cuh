@@ -68,6 +68,7 @@ struct SeedInputs {
     // range shard of one genome: groups before g_lo belong to earlier shards; when a later shard follows, the record right
     // after this batch is a 0-coverage record for the pending group (the shard planner guarantees it, sqg_plan_shards)
     int32_t g_lo = 0;
+    int32_t g_hi = 0;               // groups from g_hi on are never triggered by this batch (trigger == n_rec): islands cover [g_lo, g_hi)
     bool has_next = false;
     uint64_t end_other = 0;         // otherChr/otherrightmost after the last record of the batch
 };

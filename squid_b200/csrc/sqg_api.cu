@@ -136,7 +136,7 @@ __global__ void k_island_cuts(SeedInputs in, uint8_t *flag) {
     if (g >= in.nG) return;
     SeedMachine sm;
     sm.in = in;
-    flag[g] = (g == in.g_lo) ? 1 : (g < in.g_lo ? 0 : (sm.island_cut(g) ? 1 : 0));  // groups before g_lo belong to earlier shards
+    flag[g] = (g == in.g_lo) ? 1 : ((g < in.g_lo || g >= in.g_hi) ? 0 : (sm.island_cut(g) ? 1 : 0));  // groups before g_lo belong to earlier shards
 }
 struct IsCutOp {
     const uint8_t *flag;
@@ -148,7 +148,7 @@ __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n
     if (i >= n_isl) return;
     SeedMachine sm;
     sm.in = in;
-    const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
+    const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.g_hi;
     const int32_t thresh = kSeedThresh, RL = in.read_len;
     int32_t mmax = 0;
     for (int32_t g = ga; g < gb; g++) {
@@ -206,7 +206,7 @@ __device__ __forceinline__ void seed_one_island(const SeedInputs &in, int32_t i,
                                                 const int64_t *off_mar, SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err, int32_t *n_out_ret, int32_t *fast, int32_t fast_cap) {
     SeedMachineT<W> sm;
     sm.in = in;
-    const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.nG;
+    const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.g_hi;
     sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
     sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
     sm.msearch = fast; sm.msearch_cap = fast_cap;
@@ -1153,17 +1153,28 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
         }
     }
     ctx->shard_g_lo = g_lo;
+    // groups whose trigger lies behind the batch (trigger == n; triggers are non-decreasing along the groups) are never
+    // processed here: keep them out of the islands (they would all pile onto the last one)
+    int32_t g_hi = nG;
+    {
+        std::vector<int64_t> h_trig((size_t)nG);
+        CK(cudaMemcpyAsync(h_trig.data(), ctx->d_trigger.p, (size_t)nG * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        g_hi = (int32_t)(std::lower_bound(h_trig.begin(), h_trig.end(), n) - h_trig.begin());
+    }
+    if (g_hi < g_lo) g_hi = g_lo;
+    in.g_hi = g_hi;
     in.g_lo = g_lo; in.has_next = ctx->shard_index + 1 < ctx->shard_count; in.end_other = ctx->end_other;
     CK(ctx->d_cutflag.ensure(nG + 1)); CK(ctx->d_isl.ensure(nG + 2));
     LAUNCH(k_island_cuts, blocks_for(nG, 64), 64, in, ctx->d_cutflag.p);
     CK(cudaMemsetAsync(ctx->d_counters.p + 5, 0, sizeof(int64_t), ctx->stream));
-    if (nG - g_lo > 0) {
+    if (g_hi - g_lo > 0) {
         cub::CountingInputIterator<int32_t> cnt(g_lo);
         IsCutOp op{ctx->d_cutflag.p};
         size_t tb = 0;
-        CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG - g_lo, op, ctx->stream));
+        CK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), g_hi - g_lo, op, ctx->stream));
         ENSURE_TEMP(tb);
-        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), nG - g_lo, op, ctx->stream));
+        CK(cub::DeviceSelect::If(ctx->d_temp.p, tb, cnt, ctx->d_isl.p, (int32_t *)(ctx->d_counters.p + 5), g_hi - g_lo, op, ctx->stream));
         ctx->launches += 2;
     }
     CK(cudaMemcpyAsync(ctx->h_counters.p + 5, ctx->d_counters.p + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1283,9 +1294,9 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     CK(cudaStreamSynchronize(ctx->stream));
     const int32_t serr = *(int32_t *)(ctx->h_counters.p + 7);
     if (serr) FAIL(SQG_ENOMEM, serr == 1 ? "seed machine: margin scratch overflow" : "seed machine: output overflow");
-    h_isl[n_isl] = nG;
+    h_isl[n_isl] = g_hi;
     ctx->shard_ops.clear();
-    int32_t g_done = nG;
+    int32_t g_done = g_hi;  // (== nG exactly when every group was triggered by this batch)
     for (int32_t i = 0; i < n_isl; i++) {
         ctx->shard_ops.insert(ctx->shard_ops.end(), ctx->h_ops.p + h_off[i], ctx->h_ops.p + h_off[i] + h_nout[i]);
         if (h_gdone[i] < h_isl[i + 1]) { g_done = h_gdone[i]; break; }  // the stream ended before this group: nothing later is ever processed

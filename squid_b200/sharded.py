@@ -28,19 +28,66 @@ class LocalComm:
     def allgather(self, items: list) -> list:
         return list(items)
 
+    def allgather_arrays(self, arrays: list) -> list:
+        """One flat array per LOCAL shard -> the flat arrays of ALL shards, shard order."""
+        return [np.ascontiguousarray(a).ravel() for a in arrays]
 
-class DistComm:
-    """One process per GPU (torch.distributed, backend nccl or gloo); every process may hold several consecutive shards."""
+    def allreduce(self, a: np.ndarray, op: str) -> np.ndarray:
+        """Elementwise "sum" (two's-complement wrap-around, like the reference's int accumulators) or "max" over the
+        PROCESSES; the caller has already combined its local shards."""
+        return a
 
-    def __init__(self, group=None):
+
+class DistComm(LocalComm):
+    """One process per GPU (torch.distributed, backend nccl or gloo); every process holds the same number of consecutive
+    shards.  Arrays travel as tensors (on the GPU with NCCL: all_gather_into_tensor / all_reduce over NVLink); `allgather`
+    of arbitrary objects is kept for the rare large optional payloads (the trimmed chimeric blocks)."""
+
+    def __init__(self, group=None, device=None):
+        import torch
         import torch.distributed as dist
-        self.dist, self.group = dist, group
+        self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nccl = dist.get_backend(group) == "nccl"
+        self.dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu"))
 
     def allgather(self, items: list) -> list:
         out = [None] * self.world
         self.dist.all_gather_object(out, list(items), group=self.group)
         return [x for sub in out for x in sub]
+
+    def _t(self, a: np.ndarray):
+        view = {np.dtype(np.uint64): np.int64, np.dtype(np.uint32): np.int32, np.dtype(np.uint16): np.int16}.get(a.dtype)
+        return self.torch.from_numpy(a.view(view) if view else a)
+
+    def allgather_arrays(self, arrays: list) -> list:
+        torch = self.torch
+        flat = [np.ascontiguousarray(a).ravel() for a in arrays]
+        dt = flat[0].dtype
+        sizes = torch.tensor([f.shape[0] for f in flat], dtype=torch.int64, device=self.dev)
+        all_sizes = torch.empty(self.world * len(flat), dtype=torch.int64, device=self.dev)
+        self.dist.all_gather_into_tensor(all_sizes, sizes, group=self.group)
+        all_sizes = all_sizes.cpu().numpy().reshape(self.world, len(flat))
+        width = int(all_sizes.sum(axis=1).max())
+        mine = np.concatenate(flat) if flat else np.zeros(0, dt)
+        buf = torch.zeros(max(width, 1), dtype=self._t(mine[:0]).dtype, device=self.dev)
+        if mine.shape[0]:
+            buf[: mine.shape[0]] = self._t(mine).to(self.dev)
+        out = torch.empty(self.world * buf.shape[0], dtype=buf.dtype, device=self.dev)
+        self.dist.all_gather_into_tensor(out, buf, group=self.group)
+        out = out.cpu().numpy().reshape(self.world, buf.shape[0])
+        res = []
+        for r in range(self.world):
+            o = 0
+            for n in all_sizes[r]:
+                res.append(out[r, o:o + int(n)].view(dt).copy())
+                o += int(n)
+        return res
+
+    def allreduce(self, a: np.ndarray, op: str) -> np.ndarray:
+        t = self._t(np.ascontiguousarray(a)).to(self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX, group=self.group)
+        return t.cpu().numpy().view(a.dtype).reshape(a.shape)
 
 
 # ---- the exchange logic, free of any device call (tested on CPU with gloo) --------------------------------------------------
@@ -119,7 +166,7 @@ class ShardedSegmentGraph:
         ops = [g.shard_seeds(assumed[sid]) for g, sid in zip(self.g, self.ids)]
         while True:
             self.rounds["seeds"] += 1
-            all_ops = self.comm.allgather(ops)
+            all_ops = [o.reshape(-1, 4) for o in self.comm.allgather_arrays(ops)]
             wrong = first_wrong_prior(assumed, [int(o.shape[0]) for o in all_ops])
             if wrong is None:
                 break
@@ -134,7 +181,10 @@ class ShardedSegmentGraph:
             c, p, l, c3, s3, other = g.shard_build(cat)
             node = (c, p, l)
             parts.append((c3, s3, other))
-        count3, sum3, other = merge_depth(self.comm.allgather(parts))
+        count3, sum3, other = merge_depth(parts)  # the local shards; then across the processes, in one int32 vector
+        tot = self.comm.allreduce(np.concatenate([count3.ravel(), sum3.ravel(), np.array([other], np.int32)]).astype(np.int32), "sum")
+        nn = count3.size
+        count3, sum3, other = tot[:nn].reshape(count3.shape), tot[nn:2 * nn].reshape(sum3.shape), int(tot[2 * nn] != 0)
         self._fix_hints()
         length = node[2]
         support = count3[0] + count3[1] + (count3[2] if other else 0)  # as api.SegmentGraph.BuildNode_STAR
@@ -149,7 +199,8 @@ class ShardedSegmentGraph:
         used = [0] * self.n_shards
         while True:
             self.rounds["hints"] += 1
-            states = self.comm.allgather([g.shard_hint_state() for g in self.g])
+            st = self.comm.allgather_arrays([np.array(g.shard_hint_state(), np.int32) for g in self.g])
+            states = [(bool(x[0]), int(x[1])) for x in st]
             inc = incoming_hints(states)
             redo = [s for s in range(self.n_shards) if (states[s][0] or self.force_hint_redo) and used[s] != inc[s]]
             if not redo:
@@ -160,19 +211,23 @@ class ShardedSegmentGraph:
                     self.g[self.ids.index(s)].shard_redo_edges(inc[s])
 
     # -- BuildEdges ----------------------------------------------------------------------------------------------------
-    def BuildEdges(self) -> Edges:
-        tabs, chim = [], None
+    def BuildEdges(self, gather_chimeric: bool = True) -> Edges:
+        """gather_chimeric=False: the trimmed chimeric blocks stay with the process that holds shard 0."""
+        keys, ws, chim = [], [], None
         for g, sid in zip(self.g, self.ids):
             e = g.BuildEdges()
-            tabs.append((_shard.pack_edge_keys(e.Ind1, e.Ind2, e.Head1, e.Head2), e.Weight))
+            keys.append(_shard.pack_edge_keys(e.Ind1, e.Ind2, e.Head1, e.Head2)); ws.append(e.Weight)
             if sid == 0:
                 chim = g.Chimrecord  # trimmed in place by shard 0 (it owns the chimeric reads' LocateRead pass)
-        gathered = self.comm.allgather([(t, chim.a if (chim is not None and sid == 0) else None) for t, sid in zip(tabs, self.ids)])
-        keys, w = _shard.merge_edge_tables([t for t, _ in gathered])
-        i1, i2, h1, h2 = _shard.unpack_edge_keys(keys)
-        self.vEdges = Edges(i1, i2, h1, h2, w)
-        ca = next((a for _, a in gathered if a is not None), None)
-        self.Chimrecord = ChimericReads(ca) if ca is not None else None
+        all_k, all_w = self.comm.allgather_arrays(keys), self.comm.allgather_arrays(ws)
+        mk, mw = _shard.merge_edge_tables(list(zip(all_k, all_w)))
+        i1, i2, h1, h2 = _shard.unpack_edge_keys(mk)
+        self.vEdges = Edges(i1, i2, h1, h2, mw)
+        if gather_chimeric and self.comm.world > 1:
+            got = self.comm.allgather([chim.a if (chim is not None and sid == 0) else None for sid in self.ids])
+            ca = next((a for a in got if a is not None), None)
+            chim = ChimericReads(ca) if ca is not None else None
+        self.Chimrecord = chim
         return self.vEdges
 
     # -- ExactBPConcordantSupport's BAM pass -----------------------------------------------------------------------------
@@ -180,15 +235,15 @@ class ShardedSegmentGraph:
         K = int(np.asarray(bp_chr).shape[0])
         if K == 0:
             return np.zeros(0, np.int32)
-        info = self.comm.allgather([g.shard_cov_begin(bp_chr, bp_pos) for g in self.g])
-        nq = [x[0] for x in info]
+        info = self.comm.allgather_arrays([np.array(g.shard_cov_begin(bp_chr, bp_pos), np.int64) for g in self.g])
+        nq = [int(x[0]) for x in info]
         off = np.concatenate([[0], np.cumsum(nq)]).astype(np.int64)
-        k_in = chain_k_in_guess([x[1] for x in info])
+        k_in = chain_k_in_guess([int(x[1]) for x in info])
         k_in[0] = 0
         k_out = {sid: g.shard_cov_chain(k_in[sid]) for g, sid in zip(self.g, self.ids)}
         while True:
             self.rounds["chain"] += 1
-            outs = self.comm.allgather([k_out[sid] for sid in self.ids])
+            outs = [int(x[0]) for x in self.comm.allgather_arrays([np.array([k_out[sid]], np.int64) for sid in self.ids])]
             redo = [s for s in range(1, self.n_shards) if k_in[s] != outs[s - 1]]
             if not redo:
                 break
@@ -199,15 +254,9 @@ class ShardedSegmentGraph:
         t = np.full(K, -1, np.int64)
         for g, sid in zip(self.g, self.ids):
             g.shard_cov_owned_t(int(off[sid]), k_in[sid], k_out[sid], t)
-        t = self._max_t(t)
+        t = self.comm.allreduce(t, "max")  # every process filled the entries its shards own
         t[t < 0] = int(off[-1])  # never passed: every qualifying record is tested against the breakpoint
-        parts = self.comm.allgather([g.shard_cov_count(int(off[sid]), t) for g, sid in zip(self.g, self.ids)])
         cov = np.zeros(K, np.int32)
-        for p in parts:
-            cov += p
-        return cov
-
-    def _max_t(self, t_local: np.ndarray) -> np.ndarray:
-        """Every process filled the entries its shards own: elementwise max over processes."""
-        got = self.comm.allgather([t_local])
-        return np.max(np.stack(got, axis=0), axis=0)
+        for g, sid in zip(self.g, self.ids):
+            cov += g.shard_cov_count(int(off[sid]), t)
+        return self.comm.allreduce(cov, "sum")

@@ -95,11 +95,18 @@ def _worker(rank, world, port, out_dir):
         assumed[w[0]] = w[1]
         reran.append(w[0])
     assert reran == [1, 2] and assumed == [False, False, False, True]
-    # t of the breakpoints each rank's shards own, max-combined
+    # t of the breakpoints each rank's shards own, max-combined; depth numerators summed with int wrap-around
     t = np.full(6, -1, np.int64)
     t[3 * rank:3 * rank + 3] = 100 * rank + np.arange(3)
-    merged = np.max(np.stack(comm.allgather([t]), axis=0), axis=0)
-    assert merged.tolist() == [0, 1, 2, 100, 101, 102]
+    assert comm.allreduce(t, "max").tolist() == [0, 1, 2, 100, 101, 102]
+    big = np.array([2**31 - 1, 5], np.int32) if rank == 0 else np.array([1, 7], np.int32)
+    assert comm.allreduce(big, "sum").tolist() == [-2**31, 12]
+    # ragged arrays (edge keys are uint64 with the top bit in use), two per rank, back in shard order and dtype
+    mine = [np.arange(s + 1, dtype=np.uint64) + np.uint64(2**63 + 10 * s) for s in ids]
+    got = comm.allgather_arrays(mine)
+    assert [g.dtype for g in got] == [np.uint64] * (2 * world)
+    assert [g.tolist() for g in got] == [[2**63 + 10 * s + i for i in range(s + 1)] for s in range(2 * world)]
+    assert [g.shape[0] for g in comm.allgather_arrays([np.zeros(0, np.int32), np.zeros(rank, np.int32)])] == [0, 0, 0, 1]
     open(os.path.join(out_dir, "ok_%d" % rank), "w").write("ok")
     dist.barrier()
     dist.destroy_process_group()
