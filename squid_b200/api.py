@@ -63,7 +63,7 @@ CHIM_DTYPES = {
 EXPORTS = [
     "sqg_create", "sqg_destroy", "sqg_last_error", "sqg_load_concordant", "sqg_attach_concordant_device", "sqg_load_chimeric",
     "sqg_build_nodes", "sqg_set_nodes", "sqg_build_edges", "sqg_bp_coverage", "sqg_edges_device_table", "sqg_merge_edge_tables",
-    "sqg_phase_ms", "sqg_launch_count", "sqg_stat",
+    "sqg_phase_ms", "sqg_launch_count", "sqg_stat", "sqg_selftest_gpu_sort",
     "sqg_plan_shards", "sqg_set_shard", "sqg_shard_seeds", "sqg_shard_build", "sqg_shard_hint_state", "sqg_shard_redo_edges",
     "sqg_shard_cov_begin", "sqg_shard_cov_chain", "sqg_shard_cov_owned_t", "sqg_shard_cov_count",
     "sqh_default_options", "sqh_open_case", "sqh_open_bam_case", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",

@@ -53,7 +53,6 @@ bool pair_disc(const View &v, int32_t ft, int32_t st_) {  // ReadRec.cpp:211-228
 //     earlier swap has touched.  So big ranges are partitioned by all threads together (collect L and R per chunk, pair
 //     them up, swap in parallel).
 // tests/test_cpu_host_twin.py checks this routine against std::sort (ties, sorted, reversed and organ-pipe inputs).
-struct SortKey { uint64_t key; uint32_t k; };
 inline bool sk_lt(const SortKey &x, const SortKey &y) { return x.key < y.key; }
 inline void median_to_first(SortKey *first, SortKey *last) {  // std::__move_median_to_first(first, first+1, mid, last-1)
     SortKey *mid = first + (last - first) / 2, *a = first + 1, *c = last - 1;
@@ -204,7 +203,7 @@ extern "C" double sqh_time_sort(int64_t n, uint64_t seed, uint64_t range, int th
     return 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
-void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out) {
+void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out, const SortHook &sort_hook) {
     const bool timing = getenv("SQH_TIMING") != nullptr;
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *w) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[prepass] %s %.1f ms\n", w, 1e3 * std::chrono::duration<double>(t - T0).count()); T0 = t; } };
@@ -314,8 +313,12 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     // the order among equal (RefID,RefPos) which the sub-cluster walk observes.  The packed key
     // compares exactly like operator< of SingleBamRec_t (RefID, RefPos are non-negative here).
     lap("part sort");
-    sort_like_std(dis.data(), dis.data() + dis.size(), std::min(cores, 16));
-    lap("disc sort");
+    bool sorted = false;
+    if (sort_hook && dis.size() >= 2) {  // the device computes the same permutation and leaves the cores alone
+        sorted = sort_hook(dis.data(), dis.size());
+    }
+    if (!sorted) sort_like_std(dis.data(), dis.data() + dis.size(), std::min(cores, 16));
+    lap(sorted ? "disc sort (device)" : "disc sort");
     out.part_chr.reserve(part.size()); out.part_pos.reserve(part.size());
     for (auto &p : part) { out.part_chr.push_back(p.first); out.part_pos.push_back(p.second); }
     if (out.disc.size() != dis.size() + 1) out.disc.resize(dis.size() + 1);

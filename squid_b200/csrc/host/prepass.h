@@ -6,6 +6,7 @@
 #ifndef SQUID_B200_HOST_PREPASS_H
 #define SQUID_B200_HOST_PREPASS_H
 #include <cstdint>
+#include <functional>
 #include <vector>
 #include "squid_b200.h"
 #include "../sq_seed.cuh"
@@ -16,7 +17,12 @@ struct ChimPrepass {
     std::vector<int32_t> part_chr, part_pos;  // sorted PartAlignPos (incl. the n_ref leading (0,0) entries)
     std::vector<sq::Group> groups;
 };
+// element of the discordant-block sort: key = (RefID << 32 | RefPos), k = block index into the sqg_chimeric arrays
+struct SortKey { uint64_t key; uint32_t k; };
+// Optional replacement of the CPU sort: must leave a[0..n) in exactly std::sort's permutation (by key) and return true, or
+// return false with `a` untouched (the CPU twin then sorts).
+typedef std::function<bool(SortKey *a, size_t n)> SortHook;
 // `c` = chimeric reads as passed over the C ABI.
-void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out);
+void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out, const SortHook &sort_hook = SortHook());
 }  // namespace sqh
 #endif

@@ -25,6 +25,7 @@
 #include "sq_phase2.cuh"
 #include "sq_phase3.cuh"
 #include "sq_seed.cuh"
+#include "sq_gpusort.cuh"
 #include "sqg_ctx.cuh"
 
 using namespace sq;
@@ -630,6 +631,8 @@ void sqg_destroy(sqg_ctx *ctx) {
     for (auto &kv : ctx->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
     cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    ctx->d_gs_keys.release(); ctx->d_gs_idx.release(); ctx->d_gs_scratch.release(); ctx->h_gs_keys.release(); ctx->h_gs_idx.release(); ctx->h_t.release();
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
@@ -646,11 +649,12 @@ float sqg_phase_ms(const sqg_ctx *ctx, const char *name) {
     if (cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) return -1.f;
     return ms;
 }
-int64_t sqg_launch_count(const sqg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t sqg_launch_count(const sqg_ctx *ctx) { return ctx ? ctx->launches + ctx->gs_launches : 0; }
 int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     if (!ctx || !name) return -1;
     const std::string n(name);
     if (n == "islands") return ctx->n_islands;
+    if (n == "device_sort_status") return ctx->gs_last_status;  // 0: the pre-pass sort ran on the device; -100: on the cores
     if (n == "heavy_islands") return ctx->n_heavy;
     if (n == "giant_islands") return ctx->n_giant;
     if (n == "cov_chain_fallback") return ctx->cov_chain_fallback;
@@ -711,6 +715,72 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     return SQG_OK;
 }
 
+// The discordant-block sort of the chimeric pre-pass on the device (sq_gpusort.cuh): called on the pre-pass thread, works on
+// its own stream next to the classification kernels.  Leaves `a` untouched unless it returns true.
+static bool device_sort_hook(sqg_ctx *ctx, sqh::SortKey *a, size_t n) {
+    const size_t min_n = getenv("SQG_GPU_SORT_MIN") ? (size_t)atoll(getenv("SQG_GPU_SORT_MIN")) : (size_t)(1 << 15);
+    ctx->gs_last_status = -100;
+    if (n < min_n || n >= 0x7fffff00ull) return false;  // small sorts are faster on the cores than a round trip
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
+    if (!ctx->stream3 && cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (ctx->d_gs_keys.ensure(n) != cudaSuccess || ctx->d_gs_idx.ensure(n) != cudaSuccess || ctx->d_gs_scratch.ensure(gsort::bytes_needed(n)) != cudaSuccess ||
+        ctx->h_gs_keys.ensure(n) != cudaSuccess || ctx->h_gs_idx.ensure(n) != cudaSuccess) { cudaGetLastError(); return false; }
+    uint64_t *hk = ctx->h_gs_keys.p; uint32_t *hi = ctx->h_gs_idx.p;
+#pragma omp parallel for num_threads(4) schedule(static)
+    for (long long i = 0; i < (long long)n; i++) { hk[i] = a[i].key; hi[i] = a[i].k; }
+    if (cudaMemcpyAsync(ctx->d_gs_keys.p, hk, n * 8, cudaMemcpyHostToDevice, ctx->stream3) != cudaSuccess) return false;
+    if (cudaMemcpyAsync(ctx->d_gs_idx.p, hi, n * 4, cudaMemcpyHostToDevice, ctx->stream3) != cudaSuccess) return false;
+    const int rc = gsort::sort_like_std_device(ctx->d_gs_keys.p, ctx->d_gs_idx.p, n, ctx->d_gs_scratch.p, ctx->stream3, &ctx->gs_launches);
+    ctx->gs_last_status = rc;
+    if (rc != 0) { cudaGetLastError(); return false; }
+    if (cudaMemcpyAsync(hk, ctx->d_gs_keys.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream3) != cudaSuccess) return false;
+    if (cudaMemcpyAsync(hi, ctx->d_gs_idx.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream3) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(ctx->stream3) != cudaSuccess) return false;
+#pragma omp parallel for num_threads(4) schedule(static)
+    for (long long i = 0; i < (long long)n; i++) { a[i].key = hk[i]; a[i].k = hi[i]; }
+    return true;
+}
+
+// test hook: does the device sort reproduce std::sort's permutation (payload included) on n keys drawn from [0,range)?
+// 1 yes, 0 no, < 0 CUDA error, 2/3: the device sort declined (depth budget) -- patterns as sqh_selftest_sort
+extern "C" int sqg_selftest_gpu_sort(int32_t device, int64_t n, uint64_t seed, uint64_t range, int32_t pattern, float *ms_out) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    std::vector<sqh::SortKey> a((size_t)n);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    for (int64_t i = 0; i < n; i++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        uint64_t v = range ? x % range : 0;
+        if (pattern == 1) v = (uint64_t)i / 3;
+        else if (pattern == 2) v = (uint64_t)(n - i) / 3;
+        else if (pattern == 3) v = (uint64_t)std::min(i, n - 1 - i);
+        a[(size_t)i] = sqh::SortKey{v, (uint32_t)i};
+    }
+    std::vector<uint64_t> hk((size_t)n); std::vector<uint32_t> hi((size_t)n);
+    for (int64_t i = 0; i < n; i++) { hk[(size_t)i] = a[(size_t)i].key; hi[(size_t)i] = a[(size_t)i].k; }
+    std::sort(a.begin(), a.end(), [](const sqh::SortKey &p, const sqh::SortKey &q) { return p.key < q.key; });
+    uint64_t *dk = nullptr; uint32_t *di = nullptr; unsigned char *ds = nullptr;
+    cudaStream_t st;
+    int verdict = -1;
+    if (cudaStreamCreate(&st) != cudaSuccess) return -1;
+    if (cudaMalloc(&dk, (size_t)n * 8 + 8) == cudaSuccess && cudaMalloc(&di, (size_t)n * 4 + 4) == cudaSuccess && cudaMalloc(&ds, gsort::bytes_needed((size_t)n)) == cudaSuccess) {
+        cudaMemcpy(dk, hk.data(), (size_t)n * 8, cudaMemcpyHostToDevice); cudaMemcpy(di, hi.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        const int rc = gsort::sort_like_std_device(dk, di, (size_t)n, ds, st, nullptr);
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+        if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (rc != 0) verdict = rc;
+        else {
+            cudaMemcpy(hk.data(), dk, (size_t)n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(hi.data(), di, (size_t)n * 4, cudaMemcpyDeviceToHost);
+            verdict = cudaGetLastError() == cudaSuccess ? 1 : -2;
+            for (int64_t i = 0; verdict == 1 && i < n; i++) if (a[(size_t)i].key != hk[(size_t)i] || a[(size_t)i].k != hi[(size_t)i]) verdict = 0;
+        }
+    }
+    cudaFree(dk); cudaFree(di); cudaFree(ds); cudaStreamDestroy(st);
+    return verdict;
+}
+
 extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     if (!ctx || !c || c->n_reads < 0) return SQG_EINVAL;
     CK(cudaSetDevice(ctx->device));
@@ -722,7 +792,12 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     // stream copies and classifies the concordant batch; it is joined in sqg_build_nodes / sqg_build_edges.
     ctx->prepass_worker.wait();
     ctx->chim_view = *c;
-    ctx->prepass_worker.submit([ctx]() { sqh::chimeric_prepass(ctx->chim_view, ctx->params.n_ref, ctx->params.read_len, ctx->pre); });
+    ctx->prepass_worker.submit([ctx]() {
+        sqh::SortHook hook;
+        static const bool gpu_sort = !(getenv("SQG_GPU_SORT") && atoi(getenv("SQG_GPU_SORT")) == 0);
+        if (gpu_sort) hook = [ctx](sqh::SortKey *a, size_t n) { return device_sort_hook(ctx, a, n); };
+        sqh::chimeric_prepass(ctx->chim_view, ctx->params.n_ref, ctx->params.read_len, ctx->pre, hook);
+    });
     ctx->prepass_uploaded = false;
     ctx->c_n_reads = c->n_reads; ctx->c_n_blk = c->n_blk;
     const size_t nr = (size_t)c->n_reads, nb = (size_t)c->n_blk;

@@ -147,6 +147,16 @@ struct sqg_ctx {
     sq::DBuf<int32_t> dc_first_total, dc_second_total, dc_ref_id, dc_ref_pos, dc_read_pos, dc_match_ref, dc_match_read, dc_res0;
     sq::DBuf<uint8_t> dc_rev;
 
+    // std::sort's permutation of the discordant blocks on the device (sq_gpusort.cuh), driven by the pre-pass thread
+    cudaStream_t stream3 = nullptr;
+    sq::DBuf<uint64_t> d_gs_keys;
+    sq::DBuf<uint32_t> d_gs_idx;
+    sq::DBuf<unsigned char> d_gs_scratch;
+    sq::HBuf<uint64_t> h_gs_keys;
+    sq::HBuf<uint32_t> h_gs_idx;
+    int64_t gs_launches = 0;
+    int gs_last_status = -100;   // status of the most recent device sort (-100: not run)
+
     // node building
     sq::DBuf<int64_t> d_trigger;
     sq::DBuf<sq::RestBlock> d_rest, d_rest2;
