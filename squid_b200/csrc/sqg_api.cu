@@ -59,17 +59,22 @@ struct HostLap {  // SQG_TIMING=1: wall-clock laps of the host side of a call, t
 static constexpr int kThreads = 256;
 static inline unsigned blocks_for(int64_t n, int threads = kThreads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
-static int phase_begin(sqg_ctx *ctx, const char *name) {
+static int phase_begin(sqg_ctx *ctx, const char *name, cudaStream_t st = nullptr) {
     PhaseTimer &t = ctx->timers[name];
     if (!t.a) { CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); }
     t.done = false;
-    CK(cudaEventRecord(t.a, ctx->stream));
+    CK(cudaEventRecord(t.a, st ? st : ctx->stream));
     return SQG_OK;
 }
-static int phase_end(sqg_ctx *ctx, const char *name) {
+static int phase_end(sqg_ctx *ctx, const char *name, cudaStream_t st = nullptr) {
     PhaseTimer &t = ctx->timers[name];
-    CK(cudaEventRecord(t.b, ctx->stream));
+    CK(cudaEventRecord(t.b, st ? st : ctx->stream));
     t.done = true;
+    return SQG_OK;
+}
+// everything that rewrites what the coverage compaction reads (batch, class bytes, chain scratch) first waits for it
+static int cov_join(sqg_ctx *ctx) {
+    if (ctx->cov_pending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_cov_done, 0)); ctx->cov_pending = false; }
     return SQG_OK;
 }
 #define PHASE_BEGIN(name) do { int rc_ = phase_begin(ctx, name); if (rc_) return rc_; } while (0)
@@ -593,7 +598,10 @@ int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the cluster kernel must get its SMs before the block kernel fills them
     if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream_cov, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_cov_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_cov_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_chim, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
     ctx->params.min_mapq = cfg->min_mapq; ctx->params.max_lowphred_len = cfg->max_lowphred_len;
     ctx->params.concord_dist_pos = cfg->concord_dist_pos; ctx->params.concord_dist_idx = cfg->concord_dist_idx;
     ctx->params.read_len = cfg->read_len; ctx->params.n_ref = n_ref;
@@ -609,6 +617,8 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->prepass_worker.stop();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream_cov) cudaStreamSynchronize(ctx->stream_cov);
+    if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     // DBuf/HBuf members are plain pointers: release explicitly
     ctx->o_ref_id.release(); ctx->o_pos.release(); ctx->o_mate_ref_id.release(); ctx->o_mate_pos.release(); ctx->o_end_pos.release();
     ctx->o_blk_ref_pos.release(); ctx->o_blk_match_ref.release(); ctx->o_flag.release(); ctx->o_total_len.release(); ctx->o_lowphred_run.release();
@@ -633,6 +643,10 @@ void sqg_destroy(sqg_ctx *ctx) {
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     ctx->d_gs_keys.release(); ctx->d_gs_idx.release(); ctx->d_gs_scratch.release(); ctx->h_gs_keys.release(); ctx->h_gs_idx.release(); ctx->h_t.release();
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->ev_chim) cudaEventDestroy(ctx->ev_chim);
+    if (ctx->stream_cov) cudaStreamDestroy(ctx->stream_cov);
+    if (ctx->ev_cov_fork) cudaEventDestroy(ctx->ev_cov_fork);
+    if (ctx->ev_cov_done) cudaEventDestroy(ctx->ev_cov_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
@@ -679,6 +693,7 @@ extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t fi
     if (!ctx || !hb || hb->n_rec < 0 || hb->n_blk < 0) return SQG_EINVAL;
     if (hb->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
     CK(cudaSetDevice(ctx->device));
+    { const int rcj = cov_join(ctx); if (rcj) return rcj; }
     PHASE_BEGIN("h2d");
     const size_t n = (size_t)hb->n_rec, nb = (size_t)hb->n_blk;
 #define UP(buf, src, cnt)                                                                                       \
@@ -706,6 +721,7 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     if (!ctx || !db || db->n_rec < 0) return SQG_EINVAL;
     if (db->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->cov_pending) { CK(cudaStreamSynchronize(ctx->stream_cov)); ctx->cov_pending = false; }  // the previous batch's arrays belong to the caller again
     DevBatch &b = ctx->batch;
     b.n_rec = db->n_rec; b.n_blk = db->n_blk;
     b.ref_id = db->ref_id; b.pos = db->pos; b.mate_ref_id = db->mate_ref_id; b.mate_pos = db->mate_pos; b.end_pos = db->end_pos;
@@ -722,7 +738,7 @@ static bool device_sort_hook(sqg_ctx *ctx, sqh::SortKey *a, size_t n) {
     ctx->gs_last_status = -100;
     if (n < min_n || n >= 0x7fffff00ull) return false;  // small sorts are faster on the cores than a round trip
     if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
-    if (!ctx->stream3 && cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess) return false;
+    // (stream3 has the highest priority: its short kernels take the SM slots that the big stream kernels free, ahead of their own CTAs)
     if (ctx->d_gs_keys.ensure(n) != cudaSuccess || ctx->d_gs_idx.ensure(n) != cudaSuccess || ctx->d_gs_scratch.ensure(gsort::bytes_needed(n)) != cudaSuccess ||
         ctx->h_gs_keys.ensure(n) != cudaSuccess || ctx->h_gs_idx.ensure(n) != cudaSuccess) { cudaGetLastError(); return false; }
     uint64_t *hk = ctx->h_gs_keys.p; uint32_t *hi = ctx->h_gs_idx.p;
@@ -792,37 +808,55 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     // stream copies and classifies the concordant batch; it is joined in sqg_build_nodes / sqg_build_edges.
     ctx->prepass_worker.wait();
     ctx->chim_view = *c;
-    ctx->prepass_worker.submit([ctx]() {
+    ctx->prepass_uploaded = false;
+    ctx->c_n_reads = c->n_reads; ctx->c_n_blk = c->n_blk;
+    const size_t nr = (size_t)c->n_reads, nb = (size_t)c->n_blk;
+    CK(ctx->dc_read_off.ensure(nr + 1)); CK(ctx->dc_n_first.ensure(nr + 1)); CK(ctx->dc_first_total.ensure(nr + 1)); CK(ctx->dc_second_total.ensure(nr + 1));
+    CK(ctx->dc_ref_id.ensure(nb + 1)); CK(ctx->dc_ref_pos.ensure(nb + 1)); CK(ctx->dc_read_pos.ensure(nb + 1)); CK(ctx->dc_match_ref.ensure(nb + 1));
+    CK(ctx->dc_match_read.ensure(nb + 1)); CK(ctx->dc_rev.ensure(nb + 1));
+    // the previous edge pass may still read the device copies: the uploads are ordered behind everything enqueued so far
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
+    ctx->chim_upload_err = 0;
+    ctx->chim_upload_pending = true;
+    ctx->prepass_stage.store(0);
+    ctx->prepass_worker.submit([ctx, nr, nb]() {
         sqh::SortHook hook;
         static const bool gpu_sort = !(getenv("SQG_GPU_SORT") && atoi(getenv("SQG_GPU_SORT")) == 0);
         if (gpu_sort) hook = [ctx](sqh::SortKey *a, size_t n) { return device_sort_hook(ctx, a, n); };
         sqh::chimeric_prepass(ctx->chim_view, ctx->params.n_ref, ctx->params.read_len, ctx->pre, hook);
+        ctx->prepass_stage.store(1, std::memory_order_release);  // finish_prepass() may go on
+        // then the chimeric arrays themselves (needed by the edge pass only): from this thread, so that the caller's thread
+        // goes straight on to the classification
+        const sqg_chimeric &c = ctx->chim_view;
+        cudaError_t e = cudaSetDevice(ctx->device);
+#define UPW(buf, src, cnt) do { if (e == cudaSuccess && (cnt)) e = cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream3); } while (0)
+        UPW(dc_read_off, c.read_off, nr + 1); UPW(dc_n_first, c.n_first, nr);
+        UPW(dc_first_total, c.first_total_len, nr); UPW(dc_second_total, c.second_total_len, nr);
+        UPW(dc_ref_id, c.blk_ref_id, nb); UPW(dc_ref_pos, c.blk_ref_pos, nb); UPW(dc_read_pos, c.blk_read_pos, nb);
+        UPW(dc_match_ref, c.blk_match_ref, nb); UPW(dc_match_read, c.blk_match_read, nb); UPW(dc_rev, c.blk_is_reverse, nb);
+#undef UPW
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chim, ctx->stream3);
+        ctx->chim_upload_err = (int)e;
+        ctx->prepass_stage.store(2, std::memory_order_release);
     });
-    ctx->prepass_uploaded = false;
-    ctx->c_n_reads = c->n_reads; ctx->c_n_blk = c->n_blk;
-    const size_t nr = (size_t)c->n_reads, nb = (size_t)c->n_blk;
 #define UPV(buf, src, cnt)                                                                                     \
     do {                                                                                                       \
         CK(ctx->buf.ensure((cnt) ? (cnt) : 1));                                                                \
         if (cnt) CK(cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream)); \
     } while (0)
-    UPV(dc_read_off, c->read_off, nr + 1); UPV(dc_n_first, c->n_first, nr);
-    UPV(dc_first_total, c->first_total_len, nr); UPV(dc_second_total, c->second_total_len, nr);
-    UPV(dc_ref_id, c->blk_ref_id, nb); UPV(dc_ref_pos, c->blk_ref_pos, nb); UPV(dc_read_pos, c->blk_read_pos, nb);
-    UPV(dc_match_ref, c->blk_match_ref, nb); UPV(dc_match_read, c->blk_match_read, nb); UPV(dc_rev, c->blk_is_reverse, nb);
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_chim = true; ctx->have_edge_table = false;
     return SQG_OK;
 }
 
 // join the host pre-pass and put its products (discordant blocks, groups, PartAlignPos) into HBM
 static int finish_prepass(sqg_ctx *ctx) {
-    ctx->prepass_worker.wait();
+    while (ctx->prepass_stage.load(std::memory_order_acquire) < 1) std::this_thread::yield();  // the products; the thread may still be uploading
     if (ctx->prepass_uploaded) return SQG_OK;
     const size_t nD1 = ctx->pre.disc.size(), nG = ctx->pre.groups.size(), nP = ctx->pre.part_chr.size();
     UPV(d_disc, ctx->pre.disc.data(), nD1); UPV(d_groups, ctx->pre.groups.data(), nG);
     UPV(d_pchr, ctx->pre.part_chr.data(), nP); UPV(d_ppos, ctx->pre.part_pos.data(), nP);
-    CK(cudaStreamSynchronize(ctx->stream));
+    // (pageable sources: the copies are staged before cudaMemcpyAsync returns; no need to drain the stream here)
     ctx->prepass_uploaded = true;
     return SQG_OK;
 }
@@ -831,10 +865,10 @@ static int ensure_temp(sqg_ctx *ctx, size_t bytes) { CK(ctx->d_temp.ensure(bytes
 #define ENSURE_TEMP(bytes) do { int rc_ = ensure_temp(ctx, bytes); if (rc_) return rc_; } while (0)
 
 // look-back chains of a stream kernel: `n_chains` chains over `n_tiles` tiles; status words zeroed, ticket reset
-static int prepare_chains(sqg_ctx *ctx, int n_chains, int64_t n_tiles, Chain *out, int32_t **ticket) {
+static int prepare_chains(sqg_ctx *ctx, int n_chains, int64_t n_tiles, Chain *out, int32_t **ticket, cudaStream_t st) {
     CK(ctx->d_chain64.ensure((size_t)n_chains * 4 * n_tiles + 8));
     CK(ctx->d_chain32.ensure((size_t)n_chains * n_tiles + 8));
-    CK(cudaMemsetAsync(ctx->d_chain32.p, 0, ((size_t)n_chains * n_tiles + 8) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_chain32.p, 0, ((size_t)n_chains * n_tiles + 8) * 4, st));
     for (int c = 0; c < n_chains; c++) {
         out[c].status = ctx->d_chain32.p + (size_t)c * n_tiles;
         uint64_t *q = ctx->d_chain64.p + (size_t)c * 4 * n_tiles;
@@ -854,6 +888,7 @@ static constexpr size_t kTileSmemBytes = sizeof(TileStage) + 128;
 // classify stage (phase 1): class bytes, gap / partial / displaced lists, first kept record, lmax; validates the batch
 static int run_classify(sqg_ctx *ctx) {
     if (ctx->classified) return SQG_OK;
+    { const int rcj = cov_join(ctx); if (rcj) return rcj; }
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
     PHASE_BEGIN("classify");
@@ -1020,16 +1055,26 @@ static int run_cov_compact(sqg_ctx *ctx) {
     const int64_t n = b.n_rec;
     const int64_t n_tiles = (n + kCovTile - 1) / kCovTile;
     if (n > 0) {
+        // forked behind the classification: the seed machine (latency-bound, few resident warps) shares the SMs with it
+        cudaStream_t st = ctx->stream_cov;
+        CK(cudaEventRecord(ctx->ev_cov_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(st, ctx->ev_cov_fork, 0));
         Chain ch[1];
         int32_t *ticket = nullptr;
-        int rc = prepare_chains(ctx, 1, n_tiles, ch, &ticket);
+        CK(ctx->d_qkey.ensure(n + 1)); CK(ctx->d_qend.ensure(n + 1)); CK(ctx->d_covtile.ensure(n_tiles + 1));  // (allocation synchronises: before the launches)
+        int rc = prepare_chains(ctx, 1, n_tiles, ch, &ticket, st);
         if (rc) return rc;
-        CK(ctx->d_qkey.ensure(n + 1)); CK(ctx->d_qend.ensure(n + 1)); CK(ctx->d_covtile.ensure(n_tiles + 1));
-        CK(cudaMemsetAsync(ctx->d_counters.p + 15, 0, sizeof(int64_t), ctx->stream));
-        PHASE_BEGIN("k_cov_compact");
-        LAUNCH(k_cov_compact, (unsigned)n_tiles, kCovThreads, b, ctx->d_cls.p, ch[0], ticket, (int32_t)n_tiles, ctx->d_qkey.p, ctx->d_qend.p, ctx->d_covtile.p, ctx->d_counters.p + 15);
-        PHASE_END("k_cov_compact");
-        CK(cudaMemcpyAsync(ctx->h_counters.p + 15, ctx->d_counters.p + 15, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_counters.p + 15, 0, sizeof(int64_t), st));
+        rc = phase_begin(ctx, "k_cov_compact", st);
+        if (rc) return rc;
+        k_cov_compact<<<(unsigned)n_tiles, kCovThreads, 0, st>>>(b, ctx->d_cls.p, ch[0], ticket, (int32_t)n_tiles, ctx->d_qkey.p, ctx->d_qend.p, ctx->d_covtile.p, ctx->d_counters.p + 15);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        rc = phase_end(ctx, "k_cov_compact", st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 15, ctx->d_counters.p + 15, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_cov_done, st));
+        ctx->cov_pending = true;
     } else { CK(ctx->d_qkey.ensure(1)); CK(ctx->d_qend.ensure(1)); CK(ctx->d_covtile.ensure(1)); }
     ctx->cov_compacted = true;
     return SQG_OK;
@@ -1056,6 +1101,12 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
     int64_t slow_cap = std::max<int64_t>({(int64_t)ctx->d_slow.cap, n / 8 + 4096});
     CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1));
     int64_t n_raw = 0;
+    if (ctx->chim_upload_pending) {  // the chimeric arrays: uploaded by the pre-pass thread behind its own work
+        ctx->prepass_worker.wait();
+        if (ctx->chim_upload_err) { ctx->err = std::string("upload of the chimeric reads: ") + cudaGetErrorString((cudaError_t)ctx->chim_upload_err); return SQG_ECUDA; }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chim, 0));
+        ctx->chim_upload_pending = false;
+    }
     PHASE_BEGIN(do_depth ? "depth_edges" : "edges_only");
     for (int attempt = 0; attempt < 2; attempt++) {
         if (do_edges) { CK(ctx->d_ekeys.ensure(cap)); CK(ctx->d_ew.ensure(cap)); CK(ctx->d_sens.ensure(sens_cap)); CK(ctx->d_head.ensure(sens_cap)); }
@@ -1595,6 +1646,9 @@ static int cov_prepare(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_po
     // qualifying records compacted in stream order (done already if sqg_build_nodes ran: it only needs the class bytes)
     rc = run_cov_compact(ctx);
     if (rc) return rc;
+    rc = cov_join(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream_cov));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->cov_K = K;
     ctx->cov_nq = n > 0 ? ctx->h_counters.p[15] : 0;

@@ -97,6 +97,10 @@ struct sqg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the cluster kernel of the seed machine, forked / joined with events
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // the coverage compaction (phase 3, first pass) runs beside the seed machine on its own stream
+    cudaStream_t stream_cov = nullptr;
+    cudaEvent_t ev_cov_fork = nullptr, ev_cov_done = nullptr;
+    bool cov_pending = false;
     std::string err;
     sq::Params params{};
     std::vector<int32_t> ref_len;
@@ -149,6 +153,10 @@ struct sqg_ctx {
 
     // std::sort's permutation of the discordant blocks on the device (sq_gpusort.cuh), driven by the pre-pass thread
     cudaStream_t stream3 = nullptr;
+    cudaEvent_t ev_chim = nullptr;       // the chimeric arrays are in HBM (uploaded by the pre-pass thread behind its own work)
+    bool chim_upload_pending = false;
+    int chim_upload_err = 0;
+    std::atomic<int> prepass_stage{2};   // 0: pre-pass running, 1: its products are ready (uploads still going), 2: thread idle
     sq::DBuf<uint64_t> d_gs_keys;
     sq::DBuf<uint32_t> d_gs_idx;
     sq::DBuf<unsigned char> d_gs_scratch;
