@@ -11,8 +11,9 @@ synthetic sorted alignment records of the configs[1] shape (GRCh38 layout, ~0.5 
   roofline : dominant stream phase, algorithmic bytes (SURVEY.md §8d / DESIGN.md) / CUDA-event time / measured HBM peak
   cpu_baseline : the reference's own BuildNode_STAR/BuildEdges/ExactBPConcordantSupport (oracle/_ref, single thread)
                  on a bounded sample of the same generator
-N > 1: every rank owns an independent range shard of the stream (weak scaling), per-rank edge tables are exchanged with
-NCCL all_gather and merge-reduced on the device.
+N > 1: weak scaling over N independent streams of that shape, one per rank (a cohort of N samples): every rank runs the whole
+path on its own stream, the per-rank edge tables are exchanged with NCCL all_gather and merge-reduced on the device.  (ONE
+stream cut into exact range shards -- bit-identical results for every N -- is measured by bench_sharded.py)
 """
 from __future__ import annotations
 
@@ -344,7 +345,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
             "config": {"workload": "synthetic GRCh38-layout sorted alignment records, %d read pairs per GPU, ~0.5%% discordant (configs[1])" % P,
-                       "pairs_per_gpu": P, "pairs_requested": P_req, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": "range-shard x%d" % world,
+                       "pairs_per_gpu": P, "pairs_requested": P_req, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": "one independent stream per GPU x%d (exact range shards of one stream: bench_sharded.py)" % world,
                        "l2": "inputs (%.1f GB) larger than L2" % (n_bytes / 1e9), "segments": state.get("n_nodes"), "edges": state.get("n_edges"), "breakpoints": state.get("n_bp"),
                        "breakpoint_source": "host stand-in for the out-of-scope stages between BuildEdges and ExactBPConcordantSupport, computed in the warm-up steps"},
             "e2e": {"value": world * P / sec_e2e, "unit": "read pairs/s", "h2d_bytes_per_step": n_bytes + sum(v.nbytes for v in chim0.a.values()), "d2h_bytes_per_step": state.get("d2h", 0), "ms_per_step": 1e3 * sec_e2e},
