@@ -321,6 +321,11 @@ void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, Ch
     lap(sorted ? "disc sort (device)" : "disc sort");
     out.part_chr.reserve(part.size()); out.part_pos.reserve(part.size());
     for (auto &p : part) { out.part_chr.push_back(p.first); out.part_pos.push_back(p.second); }
+    if (out.disc.capacity() < dis.size() + 1) {
+        if (out.before_disc_realloc) out.before_disc_realloc();
+        out.disc.clear();
+        out.disc.reserve(dis.size() + 1 + dis.size() / 8);  // head room: the storage (and its page-lock) survives slightly larger inputs
+    }
     if (out.disc.size() != dis.size() + 1) out.disc.resize(dis.size() + 1);
     {   // gather the sorted blocks (random access into the caller's arrays)
         const long long nd = (long long)dis.size();

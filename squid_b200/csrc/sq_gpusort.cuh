@@ -115,11 +115,11 @@ __global__ void k_swap(uint64_t *keys, uint32_t *idx, uint32_t n, const Range *r
     swap_at(keys, idx, Lpos[base + i], Rpos[base + nR_in[r] - 1 - i]);
 }
 // children of every range: still-big ones are counted (cnt) for the next level, the others go to the leaf list
-__global__ void k_children_count(const Range *rg, const int32_t *n_rg, const uint32_t *cut_in, int32_t *cnt, Range *leaves, int32_t *n_leaves, int32_t *status) {
+__global__ void k_children_count(const Range *rg, const int32_t *n_rg, const uint32_t *cut_in, int32_t *cnt, int32_t cnt_len, Range *leaves, int32_t *n_leaves, int32_t *status) {
     const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const int32_t nr = *n_rg;
-    if (r > nr) return;
-    if (r == nr) { cnt[r] = 0; return; }
+    if (r >= cnt_len) return;
+    if (r >= nr) { cnt[r] = 0; return; }  // (the scan below runs over the whole array: the host does not know nr)
     const Range g = rg[r];
     const uint32_t cut = cut_in[r];
     const Range ch[2] = {Range{g.first, cut, g.depth - 1}, Range{cut, g.last, g.depth - 1}};
@@ -245,8 +245,12 @@ inline int sort_like_std_device(uint64_t *keys, uint32_t *idx, size_t n, unsigne
     int32_t *n_cur = s.counters, *n_nxt = s.counters + 1;
     int32_t n_active = h[0];
     const unsigned eb = (unsigned)((n + 1 + 255) / 256);
+    // The levels are enqueued back to back: every kernel reads the number of active ranges from device memory, so the host
+    // only looks (status, ranges left) every few levels instead of paying a round trip per level.
+    const int32_t R = (int32_t)max_ranges(n);
+    const unsigned rb = (unsigned)((R + 1 + 127) / 128);
+    const int kCheckEvery = 4;
     for (int level = 0; n_active > 0 && level < 4 * lg + 8; level++) {
-        const unsigned rb = (unsigned)((n_active + 1 + 127) / 128);
         k_median<<<rb, 128, 0, stream>>>(keys, idx, cur, n_cur);
         k_flags<<<eb, 256, 0, stream>>>(keys, (uint32_t)n, cur, n_cur, s.rid, s.flags);
         size_t tb = s.cub_bytes;
@@ -254,22 +258,26 @@ inline int sort_like_std_device(uint64_t *keys, uint32_t *idx, size_t n, unsigne
         k_scatter<<<eb, 256, 0, stream>>>((uint32_t)n, cur, s.rid, s.flags, s.scan, s.Lpos, s.Rpos);
         k_cut<<<rb, 128, 0, stream>>>(cur, n_cur, s.scan, s.Lpos, s.Rpos, s.m, s.cut, s.nR);
         k_swap<<<eb, 256, 0, stream>>>(keys, idx, (uint32_t)n, cur, s.rid, s.Lpos, s.Rpos, s.m, s.nR);
-        k_children_count<<<rb, 128, 0, stream>>>(cur, n_cur, s.cut, s.cnt, s.leaves, s.counters + 2, s.counters + 3);
+        k_children_count<<<rb, 128, 0, stream>>>(cur, n_cur, s.cut, s.cnt, R + 1, s.leaves, s.counters + 2, s.counters + 3);
         tb = s.cub_bytes;
-        GS_CK(cub::DeviceScan::ExclusiveSum(s.cub_temp, tb, s.cnt, s.off, n_active + 1, stream));
+        GS_CK(cub::DeviceScan::ExclusiveSum(s.cub_temp, tb, s.cnt, s.off, R + 1, stream));
         GS_CK(cudaMemsetAsync(n_nxt, 0, 4, stream));
         k_children_write<<<rb, 128, 0, stream>>>(cur, n_cur, s.cut, s.off, nxt, n_nxt);
         if (launches) *launches += 9;
-        GS_CK(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, stream));
-        GS_CK(cudaStreamSynchronize(stream));
-        if (h[3]) return h[3];
         Range *t = cur; cur = nxt; nxt = t;
         int32_t *tn = n_cur; n_cur = n_nxt; n_nxt = tn;
-        n_active = *(n_cur == s.counters ? &h[0] : &h[1]);
+        if ((level + 1) % kCheckEvery == 0) {
+            GS_CK(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, stream));
+            GS_CK(cudaStreamSynchronize(stream));
+            if (h[3]) return h[3];
+            n_active = *(n_cur == s.counters ? &h[0] : &h[1]);
+        }
     }
-    if (n_active > 0) return 2;
     GS_CK(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, stream));
     GS_CK(cudaStreamSynchronize(stream));
+    if (h[3]) return h[3];
+    n_active = *(n_cur == s.counters ? &h[0] : &h[1]);
+    if (n_active > 0) return 2;
     if (h[2] > 0) {
         k_leaves<<<(unsigned)(h[2] < 148 * 32 ? h[2] : 148 * 32), 32, 0, stream>>>(keys, idx, s.leaves, s.counters + 2, s.counters + 3);
         if (launches) *launches += 1;

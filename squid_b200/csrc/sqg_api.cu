@@ -601,7 +601,8 @@ int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream_cov, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_cov_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_cov_done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_chim, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
+        cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_chim, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
     ctx->params.min_mapq = cfg->min_mapq; ctx->params.max_lowphred_len = cfg->max_lowphred_len;
     ctx->params.concord_dist_pos = cfg->concord_dist_pos; ctx->params.concord_dist_idx = cfg->concord_dist_idx;
     ctx->params.read_len = cfg->read_len; ctx->params.n_ref = n_ref;
@@ -644,6 +645,8 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_gs_keys.release(); ctx->d_gs_idx.release(); ctx->d_gs_scratch.release(); ctx->h_gs_keys.release(); ctx->h_gs_idx.release(); ctx->h_t.release();
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->ev_chim) cudaEventDestroy(ctx->ev_chim);
+    if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
+    for (auto &pp : ctx->pre_pinned) if (pp.p) cudaHostUnregister(const_cast<void *>(pp.p));
     if (ctx->stream_cov) cudaStreamDestroy(ctx->stream_cov);
     if (ctx->ev_cov_fork) cudaEventDestroy(ctx->ev_cov_fork);
     if (ctx->ev_cov_done) cudaEventDestroy(ctx->ev_cov_done);
@@ -749,11 +752,11 @@ static bool device_sort_hook(sqg_ctx *ctx, sqh::SortKey *a, size_t n) {
     const int rc = gsort::sort_like_std_device(ctx->d_gs_keys.p, ctx->d_gs_idx.p, n, ctx->d_gs_scratch.p, ctx->stream3, &ctx->gs_launches);
     ctx->gs_last_status = rc;
     if (rc != 0) { cudaGetLastError(); return false; }
-    if (cudaMemcpyAsync(hk, ctx->d_gs_keys.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream3) != cudaSuccess) return false;
+    // only the permutation comes back: the pre-pass reads nothing but the block indices after the sort
     if (cudaMemcpyAsync(hi, ctx->d_gs_idx.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream3) != cudaSuccess) return false;
     if (cudaStreamSynchronize(ctx->stream3) != cudaSuccess) return false;
 #pragma omp parallel for num_threads(4) schedule(static)
-    for (long long i = 0; i < (long long)n; i++) { a[i].key = hk[i]; a[i].k = hi[i]; }
+    for (long long i = 0; i < (long long)n; i++) a[i].k = hi[i];
     return true;
 }
 
@@ -824,7 +827,35 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
         sqh::SortHook hook;
         static const bool gpu_sort = !(getenv("SQG_GPU_SORT") && atoi(getenv("SQG_GPU_SORT")) == 0);
         if (gpu_sort) hook = [ctx](sqh::SortKey *a, size_t n) { return device_sort_hook(ctx, a, n); };
+        ctx->pre.before_disc_realloc = [ctx]() {  // the page-lock must go before the storage does
+            sqg_ctx::Pinned &pp = ctx->pre_pinned[0];
+            if (pp.p) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream3); cudaHostUnregister(const_cast<void *>(pp.p)); pp.p = nullptr; pp.bytes = 0; }
+        };
         sqh::chimeric_prepass(ctx->chim_view, ctx->params.n_ref, ctx->params.read_len, ctx->pre, hook);
+        {   // its products go to HBM from here (DMA from the registered vectors), the caller's stream waits for ev_pre only
+            cudaError_t e = cudaSetDevice(ctx->device);
+            const size_t nD1 = ctx->pre.disc.size(), nG = ctx->pre.groups.size(), nP = ctx->pre.part_chr.size();
+            if (e == cudaSuccess) e = ctx->d_disc.ensure(nD1 ? nD1 : 1);
+            if (e == cudaSuccess) e = ctx->d_groups.ensure(nG ? nG : 1);
+            if (e == cudaSuccess) e = ctx->d_pchr.ensure(nP ? nP : 1);
+            if (e == cudaSuccess) e = ctx->d_ppos.ensure(nP ? nP : 1);
+            const void *src[4] = {ctx->pre.disc.data(), ctx->pre.groups.data(), ctx->pre.part_chr.data(), ctx->pre.part_pos.data()};
+            const size_t cap[4] = {ctx->pre.disc.capacity() * sizeof(DiscBlock), ctx->pre.groups.capacity() * sizeof(Group), ctx->pre.part_chr.capacity() * 4, ctx->pre.part_pos.capacity() * 4};
+            const size_t len[4] = {nD1 * sizeof(DiscBlock), nG * sizeof(Group), nP * 4, nP * 4};
+            void *dst[4] = {ctx->d_disc.p, ctx->d_groups.p, ctx->d_pchr.p, ctx->d_ppos.p};
+            for (int k = 0; k < 4 && e == cudaSuccess; k++) {
+                sqg_ctx::Pinned &pp = ctx->pre_pinned[k];
+                if (k == 0 && cap[k] >= (1u << 16) && (pp.p != src[k] || pp.bytes != cap[k])) {  // the big one; (re)register when the vector moved or grew
+                    if (pp.p) cudaHostUnregister(const_cast<void *>(pp.p));
+                    pp.p = nullptr; pp.bytes = 0;
+                    if (cudaHostRegister(const_cast<void *>(src[k]), cap[k], cudaHostRegisterDefault) == cudaSuccess) { pp.p = src[k]; pp.bytes = cap[k]; }
+                    else cudaGetLastError();  // not fatal: the copy is staged instead
+                }
+                if (len[k]) e = cudaMemcpyAsync(dst[k], src[k], len[k], cudaMemcpyHostToDevice, ctx->stream3);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pre, ctx->stream3);
+            ctx->pre_upload_err = (int)e;
+        }
         ctx->prepass_stage.store(1, std::memory_order_release);  // finish_prepass() may go on
         // then the chimeric arrays themselves (needed by the edge pass only): from this thread, so that the caller's thread
         // goes straight on to the classification
@@ -853,10 +884,8 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
 static int finish_prepass(sqg_ctx *ctx) {
     while (ctx->prepass_stage.load(std::memory_order_acquire) < 1) std::this_thread::yield();  // the products; the thread may still be uploading
     if (ctx->prepass_uploaded) return SQG_OK;
-    const size_t nD1 = ctx->pre.disc.size(), nG = ctx->pre.groups.size(), nP = ctx->pre.part_chr.size();
-    UPV(d_disc, ctx->pre.disc.data(), nD1); UPV(d_groups, ctx->pre.groups.data(), nG);
-    UPV(d_pchr, ctx->pre.part_chr.data(), nP); UPV(d_ppos, ctx->pre.part_pos.data(), nP);
-    // (pageable sources: the copies are staged before cudaMemcpyAsync returns; no need to drain the stream here)
+    if (ctx->pre_upload_err) { ctx->err = std::string("upload of the pre-pass products: ") + cudaGetErrorString((cudaError_t)ctx->pre_upload_err); return SQG_ECUDA; }
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));
     ctx->prepass_uploaded = true;
     return SQG_OK;
 }

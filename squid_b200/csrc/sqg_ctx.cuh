@@ -156,6 +156,10 @@ struct sqg_ctx {
     cudaEvent_t ev_chim = nullptr;       // the chimeric arrays are in HBM (uploaded by the pre-pass thread behind its own work)
     bool chim_upload_pending = false;
     int chim_upload_err = 0;
+    cudaEvent_t ev_pre = nullptr;        // the pre-pass products (discordant blocks, groups, PartAlignPos) are in HBM
+    int pre_upload_err = 0;
+    struct Pinned { const void *p = nullptr; size_t bytes = 0; };
+    Pinned pre_pinned[4];                // host vectors of `pre` registered for DMA (they keep their storage from step to step)
     std::atomic<int> prepass_stage{2};   // 0: pre-pass running, 1: its products are ready (uploads still going), 2: thread idle
     sq::DBuf<uint64_t> d_gs_keys;
     sq::DBuf<uint32_t> d_gs_idx;
