@@ -183,8 +183,9 @@ def main():
     P = args.pairs
     # ---- workload: generated on the device, sorted; chimeric reads through the host loader --------------------
     t0 = time.time()
-    batch, tx, prob = synth_gpu.make_bench_batch(P, seed=100 + rank, device=str(dev))
-    chim_tab, fusions = synth.make_chimeric(tx, prob, P, 100 + rank, DISC_FRAC, adversarial=False)
+    seed0 = int(os.environ.get("SQUID_BENCH_SEED", 100))  # (rank r of a multi-GPU run uses seed0 + r: its stream on one GPU = SQUID_BENCH_SEED=100+r)
+    batch, tx, prob = synth_gpu.make_bench_batch(P, seed=seed0 + rank, device=str(dev))
+    chim_tab, fusions = synth.make_chimeric(tx, prob, P, seed0 + rank, DISC_FRAC, adversarial=False)
     with tempfile.TemporaryDirectory() as d:
         sqmb.write_sqmb(d + "/chim.sqmb", chim_tab)
         sqmb.write_sqmb(d + "/conc.sqmb", sqmb.empty(synth.GRCH38_LEN, 0))
@@ -268,7 +269,7 @@ def main():
         lap("edge exchange + breakpoints (cached host stand-in)" if world > 1 else "breakpoints (cached host stand-in)")
         cov = g.BPCoverage(bc, bp)
         lap("BPCoverage")
-        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "edges_single_path", "edges_generic_path")}
+        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "cov_chain_chunks", "edges_single_path", "edges_generic_path")}
         state.update(n_nodes=int(nodes.Chr.shape[0]), n_edges=int(edges.Ind1.shape[0]), n_bp=int(bc.shape[0]), cov_sum=int(cov.sum()),
                      d2h=int(nodes.Chr.nbytes * 3 + nodes.count3.nbytes * 2 + edges.Ind1.nbytes * 3 + edges.Ind1.shape[0] + cov.nbytes))
         return nodes, edges, cov
@@ -331,7 +332,7 @@ def main():
         ach = alg[top] / (stream[top] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic[top] * R if traffic.get(top) else None,
                 "peak_source": peak_src, "alg_bytes_per_launch": alg[top], "ms": stream[top],
-                "note": "dominant STREAM kernel of the step; the latency-bound seed machine is listed in phases_ms",
+                "note": "dominant STREAM kernel of the step, timed live with CUDA events; k_classify shares the SMs with the chimeric pre-pass sort (own stream, highest priority), which costs it ~0.6 ms against its stand-alone 5.05 ms (profiles/r1_launches_100M_final.csv); the latency-bound seed machine is listed in phases_ms",
                 "all_stream_kernels": {k: {"ms": v, "GBps": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak} for k, v in stream.items()}}
     b_alg_pair = (2 * (32 * R + 12 * NB) + 24 * R) / P
     # phases are disjoint stream intervals; the eager coverage compaction runs between "classify" and "seed"

@@ -489,9 +489,11 @@ __global__ void k_cov_verify(const uint64_t *qkey, int64_t nq, const int32_t *bp
 // that assumption (t of the previous breakpoint < r0 of the chunk's first); only if it fails somewhere is the whole list
 // replayed by one warp (chunk_start == nullptr).
 constexpr int64_t kChainGap = 4096;
+// (also every 32nd breakpoint at which the max-plus candidate has caught up with r0, t == r0: long stretches without a big
+// jump of r0 would otherwise be one chunk, replayed by a single warp; the check / redo rounds make any cut set valid)
 struct IsChainCutOp {
-    const int64_t *r0;
-    __device__ bool operator()(int32_t k) const { return k == 0 || r0[k] - r0[k - 1] > kChainGap; }
+    const int64_t *r0, *t;
+    __device__ bool operator()(int32_t k) const { return k == 0 || r0[k] - r0[k - 1] > kChainGap || ((k & 31) == 0 && t[k] == r0[k]); }
 };
 // A chunk was replayed with some incoming t (`used`, -1 = "the chain has caught up": irrelevant).  Given the current t of
 // its predecessor it needed `need` = t[k-1] if that reaches r0 of the chunk's first breakpoint, else -1.  Chunks whose used
@@ -1709,7 +1711,7 @@ static int cov_chain(sqg_ctx *ctx, int64_t k_begin) {
         if (ctx->cov_chain_fallback) {
             // literal chain, chunked at large jumps of r0 (one warp per chunk), validated; whole-list replay as a last resort
             cub::CountingInputIterator<int32_t> cnt(0);
-            IsChainCutOp cop{r0};
+            IsChainCutOp cop{r0, t};
             CK(ctx->d_chunks.ensure(K + 1));
             int32_t *chunks = ctx->d_chunks.p;
             CK(cub::DeviceSelect::If(nullptr, tb, cnt, chunks, (int32_t *)(ctx->d_counters.p + 14), (int)K, cop, ctx->stream));
