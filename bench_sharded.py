@@ -87,7 +87,6 @@ def main():
         dist.barrier()
     cuts = json.load(open(shm + "/cuts.json"))
     mine = {k: np.load("%s/%d_%s.npy" % (shm, rank, k)) for k in api.BATCH_DTYPES}
-    tdt = {"uint16": torch.int16, "uint32": torch.int32}
     dbatch = {k: torch.from_numpy(v.view(np.int16) if v.dtype == np.uint16 else v.view(np.int32) if v.dtype == np.uint32 else v).to(dev) for k, v in mine.items()}
     R_mine = int(mine["ref_id"].shape[0])
     del mine

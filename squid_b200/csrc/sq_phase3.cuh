@@ -150,14 +150,35 @@ __global__ void __launch_bounds__(256) k_cov_count_tiles(const uint64_t *qkey, c
     __syncthreads();
     const int64_t ka = s_ka, kb = s_kb;
     if (ka >= kb) return;  // no breakpoint under any fragment of the block
-    if (kb - ka <= kCovWin) {
-        const int nw = (int)(kb - ka);
-        for (int w = tid; w < nw; w += 256) { s_bp[w] = bpkey[ka + w]; s_t[w] = t[ka + w]; s_c[w] = 0; }
+    // The breakpoints [ka, kb) under the block are counted kCovWin at a time in shared memory.  Every warp holds 32 consecutive
+    // ranks per slot j, whose fragments overlap almost the same few breakpoints: the warp walks only the breakpoints inside
+    // its own [leftmost start, rightmost end) and adds one ballot per breakpoint -- no global atomic per (fragment, breakpoint)
+    // pair, which serialises on the handful of breakpoints of a highly expressed gene.
+    uint64_t wmn[4], wmx[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint64_t a = ks[j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const uint64_t o = __shfl_xor_sync(full, a, d); if (o < a) a = o; }
+        wmn[j] = a; wmx[j] = warp_max_u64(ke[j]);
+    }
+    const int64_t nbp = kb - ka;
+    for (int64_t w0 = 0; w0 < nbp; w0 += kCovWin) {
+        const int nw = (int)((nbp - w0) < kCovWin ? (nbp - w0) : kCovWin);
+        __syncthreads();  // the previous window has been flushed
+        for (int w = tid; w < nw; w += 256) { s_bp[w] = bpkey[ka + w0 + w]; s_t[w] = t[ka + w0 + w]; s_c[w] = 0; }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            if (wmx[j] <= s_bp[0] || wmn[j] > s_bp[nw - 1]) continue;  // warp-uniform
+            int lo = 0, hi = nw;  // first breakpoint >= the warp's leftmost start
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (s_bp[m] < wmn[j]) lo = m + 1; else hi = m; }
+            const int wa = lo;
+            hi = nw;              // first breakpoint >= the warp's rightmost end
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (s_bp[m] < wmx[j]) lo = m + 1; else hi = m; }
+            const int wb = lo;
             const int64_t i = i0 + j * 256 + tid;
-            for (int w = 0; w < nw; w++) {
+            for (int w = wa; w < wb; w++) {
                 const unsigned long long bp = s_bp[w];
                 const bool hit = ks[j] <= bp && bp < ke[j] && i < s_t[w];
                 const unsigned m = __ballot_sync(full, hit);
@@ -165,15 +186,7 @@ __global__ void __launch_bounds__(256) k_cov_count_tiles(const uint64_t *qkey, c
             }
         }
         __syncthreads();
-        for (int w = tid; w < nw; w += 256) if (s_c[w]) atomicAdd(&cov[ka + w], s_c[w]);
-    } else {  // a very dense breakpoint region: every fragment searches the list itself
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int64_t i = i0 + j * 256 + tid;
-            if (i >= nq) continue;
-            for (int64_t k = lower_bound_u64(bpkey, ka, kb, ks[j]); k < kb && bpkey[k] < ke[j]; k++)
-                if (i < t[k]) atomicAdd(&cov[k], 1);
-        }
+        for (int w = tid; w < nw; w += 256) if (s_c[w]) atomicAdd(&cov[ka + w0 + w], s_c[w]);
     }
 }
 

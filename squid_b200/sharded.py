@@ -18,7 +18,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import shard as _shard
-from .api import ChimericReads, Config, Edges, Nodes, RecordBatch, SegmentGraph, SquidB200Error, SQG_EUNSUPPORTED
+from .api import ChimericReads, Config, Edges, Nodes, SegmentGraph
 
 
 class LocalComm:
