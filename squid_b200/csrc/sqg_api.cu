@@ -631,6 +631,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_disc.release(); ctx->d_groups.release(); ctx->d_pchr.release(); ctx->d_ppos.release(); ctx->dc_read_off.release(); ctx->dc_n_first.release();
     ctx->dc_first_total.release(); ctx->dc_second_total.release(); ctx->dc_ref_id.release(); ctx->dc_ref_pos.release(); ctx->dc_read_pos.release();
     ctx->dc_match_ref.release(); ctx->dc_match_read.release(); ctx->dc_res0.release(); ctx->dc_rev.release();
+    ctx->dc0_ref_pos.release(); ctx->dc0_read_pos.release(); ctx->dc0_match_ref.release(); ctx->dc0_match_read.release();
     ctx->d_trigger.release(); ctx->d_rest.release(); ctx->d_rest2.release(); ctx->d_restkey.release(); ctx->d_restkey2.release();
     ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
@@ -819,6 +820,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     CK(ctx->dc_read_off.ensure(nr + 1)); CK(ctx->dc_n_first.ensure(nr + 1)); CK(ctx->dc_first_total.ensure(nr + 1)); CK(ctx->dc_second_total.ensure(nr + 1));
     CK(ctx->dc_ref_id.ensure(nb + 1)); CK(ctx->dc_ref_pos.ensure(nb + 1)); CK(ctx->dc_read_pos.ensure(nb + 1)); CK(ctx->dc_match_ref.ensure(nb + 1));
     CK(ctx->dc_match_read.ensure(nb + 1)); CK(ctx->dc_rev.ensure(nb + 1));
+    CK(ctx->dc0_ref_pos.ensure(nb + 1)); CK(ctx->dc0_read_pos.ensure(nb + 1)); CK(ctx->dc0_match_ref.ensure(nb + 1)); CK(ctx->dc0_match_read.ensure(nb + 1));
     // the previous edge pass may still read the device copies: the uploads are ordered behind everything enqueued so far
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
@@ -866,8 +868,8 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
 #define UPW(buf, src, cnt) do { if (e == cudaSuccess && (cnt)) e = cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream3); } while (0)
         UPW(dc_read_off, c.read_off, nr + 1); UPW(dc_n_first, c.n_first, nr);
         UPW(dc_first_total, c.first_total_len, nr); UPW(dc_second_total, c.second_total_len, nr);
-        UPW(dc_ref_id, c.blk_ref_id, nb); UPW(dc_ref_pos, c.blk_ref_pos, nb); UPW(dc_read_pos, c.blk_read_pos, nb);
-        UPW(dc_match_ref, c.blk_match_ref, nb); UPW(dc_match_read, c.blk_match_read, nb); UPW(dc_rev, c.blk_is_reverse, nb);
+        UPW(dc_ref_id, c.blk_ref_id, nb); UPW(dc0_ref_pos, c.blk_ref_pos, nb); UPW(dc0_read_pos, c.blk_read_pos, nb);
+        UPW(dc0_match_ref, c.blk_match_ref, nb); UPW(dc0_match_read, c.blk_match_read, nb); UPW(dc_rev, c.blk_is_reverse, nb);
 #undef UPW
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chim, ctx->stream3);
         ctx->chim_upload_err = (int)e;
@@ -1154,6 +1156,13 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             if (nD > 0 && ctx->shard_index == 0) LAUNCH(k_depth_disc, blocks_for(nD), kThreads, ctx->nt, ctx->d_disc.p, nD, ctx->d_cnt3.p, ctx->d_sum3.p);
         }
         CK(cudaMemsetAsync(ctx->d_counters.p + 22, 0, 2 * sizeof(int64_t), ctx->stream));  // [22] used_init flag | [23] out hint
+        if (do_edges && ctx->c_n_blk > 0) {  // every pass trims the ORIGINAL blocks (a trimmed block can fit another segment)
+            const size_t nbb = (size_t)ctx->c_n_blk * 4;
+            CK(cudaMemcpyAsync(ctx->dc_ref_pos.p, ctx->dc0_ref_pos.p, nbb, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->dc_read_pos.p, ctx->dc0_read_pos.p, nbb, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->dc_match_ref.p, ctx->dc0_match_ref.p, nbb, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->dc_match_read.p, ctx->dc0_match_read.p, nbb, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         if (do_edges && cd.n_reads > 0 && ctx->shard_index == 0) {  // (range shards: the chimeric reads are replicated, shard 0 owns their edges)  // RawEdgesChim: chimeric reads, their sensitive ones replayed in chains
             // (the chimeric sensitive list lives behind the concordant one)
             int32_t *csens = ctx->d_sens.p + (sens_cap - ctx->c_n_reads - 1), *chead = ctx->d_head.p + (sens_cap - ctx->c_n_reads - 1);
@@ -1227,7 +1236,7 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
         if (!do_edges || (n_raw <= cap && ns_conc <= conc_sens_cap && n_slow <= slow_cap)) break;
         slow_cap = std::max(slow_cap, n_slow + 4096);
         if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge / sensitive read buffer overflow");
-        cap = std::max(cap, n_raw + 4096);  // rerun with room for everything (chimeric trims are idempotent, counters are reset)
+        cap = std::max(cap, n_raw + 4096);  // rerun with room for everything (counters are reset, the chimeric blocks restored from their pristine copies)
         sens_cap = std::max<int64_t>(sens_cap, (int64_t)ns_conc + ctx->c_n_reads + 4096);
     }
     PHASE_END(do_depth ? "depth_edges" : "edges_only");

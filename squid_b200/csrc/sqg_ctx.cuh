@@ -150,6 +150,9 @@ struct sqg_ctx {
     sq::DBuf<uint16_t> dc_n_first;
     sq::DBuf<int32_t> dc_first_total, dc_second_total, dc_ref_id, dc_ref_pos, dc_read_pos, dc_match_ref, dc_match_read, dc_res0;
     sq::DBuf<uint8_t> dc_rev;
+    // pristine copies of the four arrays LocateRead trims in place: every edge pass starts from them (a pass may run twice --
+    // buffer overflow, a shard's hint redo -- and a trimmed block can locate differently from the original one)
+    sq::DBuf<int32_t> dc0_ref_pos, dc0_read_pos, dc0_match_ref, dc0_match_read;
 
     // std::sort's permutation of the discordant blocks on the device (sq_gpusort.cuh), driven by the pre-pass thread
     cudaStream_t stream3 = nullptr;

@@ -16,6 +16,9 @@ CASES = [
     (100000, 1003, 0.02, "grch38", {}),
     (200000, 1022, 0.005, [30000000, 20000000, 5000000, 16569], {"n_genes": 300}),
     (400000, 1020, 0.05, "grch38", {"fusion_support": 10}),
+    # many multi-block records: the deferred-record list overflows and the edge pass runs twice; a chimeric block that the
+    # first pass trimmed to 1 bp at a 1-bp segment would fit another segment the second time (found by tests/tools/fuzz_sharded.py)
+    (60000, 418, 0.1, [30000000, 20000000, 5000000, 16569], {"fusion_support": 100, "exon_len": (20, 170), "intron_len": (60, 400)}),
 ]
 
 
