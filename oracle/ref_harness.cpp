@@ -101,6 +101,8 @@ static void dump_bpmap(const std::string &name, const map<Edge_t, vector<pair<in
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int main(int argc, char **argv) {
+    // BWA mode (src/main.cpp:31-36 with an empty -c): `--bwa`, the second path is ignored ("-"):
+    // one BAM carries concordant and discordant alignments; BuildNode_BWA + RawEdges run instead of the STAR functions.
     // usage: squid_ref <concordant.sqmb> <chimeric.sqmb> <outdir> [-mq N] [-pl N] [-pm N] [-pt 0|1] [-dp N] [-di N] [-w N] [-r X] [-a N] [--stop-after nodes|edges|filters]
     if (argc < 4) { fprintf(stderr, "usage: %s conc.sqmb chim.sqmb outdir [opts]\n", argv[0]); return 2; }
     std::string conc = argv[1], chim = argv[2];
@@ -108,11 +110,12 @@ int main(int argc, char **argv) {
     UsingSTAR = true;
     Min_MapQual = 255;  // Config.cpp:221-222 (STAR, no -mq)
     std::string stop = "";
-    bool quiet = false;
+    bool quiet = false, bwa = false, mq_given = false;
     for (int i = 4; i < argc; i++) {
         std::string a = argv[i];
         auto nxt = [&]() { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return std::string(argv[++i]); };
-        if (a == "-mq") Min_MapQual = (uint16_t)atoi(nxt().c_str());
+        if (a == "-mq") { Min_MapQual = (uint16_t)atoi(nxt().c_str()); mq_given = true; }
+        else if (a == "--bwa") bwa = true;
         else if (a == "-pl") Max_LowPhred_Len = (uint16_t)atoi(nxt().c_str());
         else if (a == "-pm") Min_Phred = (uint8_t)atoi(nxt().c_str());
         else if (a == "-pt") Phred_Type = atoi(nxt().c_str()) != 0;
@@ -125,6 +128,7 @@ int main(int argc, char **argv) {
         else if (a == "--quiet") quiet = true;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
+    if (bwa) { UsingSTAR = false; if (!mq_given) Min_MapQual = 1; }  // Config.cpp:22 default; 255 is the STAR override (:221-222)
     FILE *saved_stdout = nullptr;
     (void)saved_stdout;
     if (quiet) { if (!freopen("/dev/null", "w", stdout)) return 2; }
@@ -136,15 +140,16 @@ int main(int argc, char **argv) {
     if (RefLength.empty()) { fprintf(stderr, "cannot read %s\n", conc.c_str()); return 2; }
     SBamrecord_t Chimrecord;
     double t0 = now();
-    BuildChimericSBamRecord(Chimrecord, RefName, chim);
+    if (!bwa) BuildChimericSBamRecord(Chimrecord, RefName, chim);  // main.cpp:32-34: only with -c
     double t_chim = now() - t0;
     dump_chim("chim_loaded.bin", Chimrecord);
     { std::vector<int32_t> v{(int32_t)ReadLen}; dump_i32("readlen.bin", v); }
 
     SegmentGraph_t g;
     t0 = now();
-    g.BuildNode_STAR(RefLength, Chimrecord, conc);
+    if (bwa) g.BuildNode_BWA(RefLength, conc); else g.BuildNode_STAR(RefLength, Chimrecord, conc);  // SegmentGraph.cpp:105-108
     double t_nodes = now() - t0;
+    if (bwa) { std::vector<int32_t> v{(int32_t)ReadLen}; dump_i32("readlen.bin", v); }  // BuildNode_BWA infers ReadLen itself (:857-864)
     dump_nodes("nodes", g);
     double t_edges = 0, t_filters = 0, t_exactbp = 0, t_cov = 0;
     size_t n_final_nodes = 0, n_final_edges = 0;

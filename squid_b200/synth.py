@@ -354,3 +354,11 @@ def make_case(n_pairs: int, ref_len=None, seed: int = 17, disc_frac: float = 0.0
     conc = sqmb.concat([left, right] + parts).sorted_by_coordinate()
     info = {"n_pairs": n_pairs, "n_records": conc.n, "n_chim_records": chim.n, "fusions": fusions, "seed": seed}
     return conc, chim, info
+
+
+def make_bwa_case(n_pairs: int, **kw):
+    """BWA-style input (`squid --bwa -b all.bam`): ONE coordinate-sorted table that carries the
+    concordant alignments and the split / discordant ones of make_case together, as bwa mem writes them (the chimeric parts
+    keep their read names, which RawEdges joins on, SegmentGraph.cpp:1873-1926).  Returns (AlnTable, info)."""
+    conc, chim, info = make_case(n_pairs, **kw)
+    return sqmb.concat([conc, chim]).sorted_by_coordinate(), info

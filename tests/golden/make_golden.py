@@ -20,6 +20,12 @@ CASES = {
     "chr17_3k": dict(n_pairs=3000, seed=3, disc_frac=0.05, ref_len=synth.CHR17_LEN),
     "fourchr_6k": dict(n_pairs=6000, seed=11, disc_frac=0.03, ref_len=[3000000, 2000000, 500000, 16569], n_genes=12),
 }
+# BWA mode: one merged BAM, `squid_ref --bwa`.  Not implemented on the device yet (round 1 reports
+# SQG_EUNSUPPORTED for using_star = 0); the reference's outputs are pinned here so that the next round starts from a checker.
+BWA_CASES = {
+    "bwa_chr17_3k": dict(n_pairs=3000, seed=3, disc_frac=0.05, ref_len=synth.CHR17_LEN),
+    "bwa_fourchr_6k": dict(n_pairs=6000, seed=11, disc_frac=0.03, ref_len=[3000000, 2000000, 500000, 16569], n_genes=12),
+}
 KEEP = ["nodes_i32.bin", "nodes_f64.bin", "edges_i32.bin", "chim_loaded.bin", "chim_loaded.bin.meta", "chim_after_edges.bin", "final_nodes_i32.bin",
         "final_edges_i32.bin", "exactbp_i32.bin", "support_i32.bin", "readlen.bin"]
 
@@ -48,7 +54,26 @@ def kat_records():
     return recs
 
 
+def make_bwa():
+    pyref.build()
+    for name, kw in BWA_CASES.items():
+        d = os.path.join(HERE, name)
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+        kw = dict(kw)
+        tab, info = synth.make_bwa_case(kw.pop("n_pairs"), **kw)
+        sqmb.write_sqmb(d + "/all.sqmb", tab)
+        pyref.run(d + "/all.sqmb", "-", d + "/ref", extra_args=("--bwa",))
+        for f in os.listdir(d + "/ref"):
+            if f not in KEEP:
+                os.remove(os.path.join(d, "ref", f))
+        print(name, "records", tab.n)
+
+
 def main():
+    if "--bwa-only" in sys.argv:
+        return make_bwa()
+    make_bwa()
     pyref.build()
     for name, kw in CASES.items():
         d = os.path.join(HERE, name)
