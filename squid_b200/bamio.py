@@ -60,12 +60,19 @@ def _materialise(cig, polya: int, lowrun: int):
 
 
 def bam_bytes(t: sqmb.AlnTable) -> bytes:
+    return b"".join(bam_parts(t))
+
+
+def bam_parts(t: sqmb.AlnTable) -> list:
+    """[header bytes, record 0 bytes, record 1 bytes, ...] (each record with its block_size prefix)."""
+    parts = []
     out = bytearray()
     text = b"@HD\tVN:1.6\tSO:coordinate\n" + b"".join(b"@SQ\tSN:chr%d\tLN:%d\n" % (i, int(l)) for i, l in enumerate(t.ref_len))
     out += b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", int(t.ref_len.shape[0]))
     for i, l in enumerate(t.ref_len):
         nm = b"chr%d\0" % i
         out += struct.pack("<i", len(nm)) + nm + struct.pack("<i", int(l))
+    parts.append(bytes(out))
     coff = t.cigar_off.astype(np.int64)
     blob = t.blob.tobytes()
     for r in range(t.n):
@@ -96,8 +103,8 @@ def bam_bytes(t: sqmb.AlnTable) -> bytes:
         body = struct.pack("<iiBBHHHIiii", int(t.ref_id[r]), pos, len(name), int(t.mapq[r]), _reg2bin(max(pos, 0), max(pos, 0) + max(ref_span, 1)),
                            len(cig), int(t.flag[r]), lseq, int(t.mate_ref_id[r]), int(t.mate_pos[r]), 0)
         body += name + np.ascontiguousarray(cig, np.uint32).tobytes() + packed + phred + aux
-        out += struct.pack("<i", len(body)) + body
-    return bytes(out)
+        parts.append(struct.pack("<i", len(body)) + body)
+    return parts
 
 
 def bgzf_compress(data: bytes, block: int = 0xFF00, level: int = 6) -> bytes:
@@ -111,7 +118,40 @@ def bgzf_compress(data: bytes, block: int = 0xFF00, level: int = 6) -> bytes:
     return bytes(out) + _BGZF_EOF
 
 
-def write_bam(path: str, t: sqmb.AlnTable, block: int = 0xFF00, level: int = 6, compressed: bool = True) -> None:
-    raw = bam_bytes(t)
+def _member(chunk: bytes, level: int) -> bytes:
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    cd = c.compress(chunk) + c.flush()
+    return b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+
+
+def bgzf_compress_records(parts: list, block: int = 0xFF00, level: int = 6) -> bytes:
+    """As htslib writes BAM: the header is flushed on its own and no record straddles two BGZF members (bgzf_flush_try) unless
+    it is larger than a member."""
+    out = bytearray()
+    hdr = parts[0]
+    for o in range(0, len(hdr), block):
+        out += _member(hdr[o:o + block], level)
+    cur = bytearray()
+    for rec in parts[1:]:
+        if cur and len(cur) + len(rec) > block:
+            out += _member(bytes(cur), level)
+            cur = bytearray()
+        cur += rec
+        while len(cur) > block:  # an oversized record spills over
+            out += _member(bytes(cur[:block]), level)
+            cur = cur[block:]
+    if cur:
+        out += _member(bytes(cur), level)
+    return bytes(out) + _BGZF_EOF
+
+
+def write_bam(path: str, t: sqmb.AlnTable, block: int = 0xFF00, level: int = 6, compressed: bool = True, htslib_blocks: bool = False) -> None:
+    """htslib_blocks=True: BGZF members end at record boundaries (what samtools / aligners write); False: the stream is cut
+    every `block` bytes wherever that falls (records straddle members -- legal BGZF, and the harder case for a reader)."""
     with open(path, "wb") as f:
-        f.write(bgzf_compress(raw, block, level) if compressed else raw)
+        if not compressed:
+            f.write(bam_bytes(t))
+        elif htslib_blocks:
+            f.write(bgzf_compress_records(bam_parts(t), block, level))
+        else:
+            f.write(bgzf_compress(bam_bytes(t), block, level))

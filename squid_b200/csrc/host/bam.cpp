@@ -40,7 +40,7 @@ size_t aux_size(char t, const uint8_t *p, const uint8_t *end) {
 }
 }  // namespace
 
-bool bgzf_inflate_all(const uint8_t *d, size_t len, std::vector<uint8_t> &out, std::string &err, int threads) {
+bool bgzf_inflate_all(const uint8_t *d, size_t len, RawBuf<uint8_t> &out, std::string &err, int threads, std::vector<size_t> *member_off) {
     std::vector<Member> mem;
     size_t o = 0, total = 0;
     while (o < len) {
@@ -64,7 +64,12 @@ bool bgzf_inflate_all(const uint8_t *d, size_t len, std::vector<uint8_t> &out, s
         mem.push_back(m);
         o += msize;
     }
-    out.resize(total);
+    if (!out.resize(total)) { err = "out of memory"; return false; }
+    if (member_off) {
+        member_off->clear();
+        for (const Member &m : mem) if (m.isize) member_off->push_back(m.off);
+        member_off->push_back(total);
+    }
     const int T = threads > 0 ? threads : omp_get_num_procs();
     int bad = 0;
 #pragma omp parallel for num_threads(T) schedule(dynamic, 16)
@@ -99,11 +104,12 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
     ::close(fd);
     if (map == MAP_FAILED) { err = "cannot map " + path; return false; }
     const uint8_t *f = (const uint8_t *)map;
-    std::vector<uint8_t> raw;
+    RawBuf<uint8_t> raw;
+    std::vector<size_t> blocks;  // starts of the BGZF members in the inflated stream (+ its length)
     const uint8_t *b; size_t n;
     if (memcmp(f, "BAM\1", 4) == 0) { b = f; n = flen; }  // uncompressed BAM stream
     else {
-        if (!bgzf_inflate_all(f, flen, raw, err, threads)) { munmap(map, flen); return false; }
+        if (!bgzf_inflate_all(f, flen, raw, err, threads, &blocks)) { munmap(map, flen); return false; }
         b = raw.data(); n = raw.size();
     }
     lap("inflate");
@@ -124,30 +130,64 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
             ref_len.push_back(rdi32(b + o)); o += 4;
         }
         if (!hdr_ok) { err = "truncated BAM reference list"; break; }
-        // record boundaries (sequential hop over block_size), then the fields in parallel
-        std::vector<size_t> rec;
-        bool rec_ok = true;
-        while (o < n) {
-            if (o + 4 > n) { rec_ok = false; break; }
-            const int32_t bs = rdi32(b + o);
-            if (bs < 32 || o + 4 + (size_t)bs > n) { rec_ok = false; break; }
-            rec.push_back(o + 4);
-            o += 4 + (size_t)bs;
+        // Record boundaries.  htslib never lets a record straddle two BGZF members (bgzf_flush_try before every record), so in
+        // the files aligners and samtools write every member starts at a record boundary and the members can be walked
+        // independently.  That is an assumption about the writer, so it is PROVEN before it is used: the walk of member k
+        // (started at a true boundary) must end exactly where member k+1 starts -- by induction from the end of the header,
+        // which is a true boundary, every start is then a true boundary.  Any member that does not end there (records
+        // straddling members: other writers, tests/test_cpu_bam.py) sends the whole file down the sequential walk.
+        const int T = threads > 0 ? threads : omp_get_num_procs();
+        std::vector<size_t> seg;  // walk segments: [seg[k], seg[k+1])
+        seg.push_back(o);
+        for (size_t x : blocks) if (x > o && x < n) seg.push_back(x);
+        seg.push_back(n);
+        size_t S = seg.size() - 1;
+        struct Tot { size_t rec, name, cig, seq; };
+        std::vector<Tot> tot(S + 1, Tot{0, 0, 0, 0});
+        auto walk = [&](size_t a, size_t e, Tot &t, size_t *rec_out, uint64_t *no, uint64_t *co, uint64_t *so) -> bool {
+            size_t p = a;
+            while (p < e) {
+                if (p + 4 > e) return false;
+                const int32_t bs = rdi32(b + p);
+                if (bs < 32 || p + 4 + (size_t)bs > e) return false;
+                const uint8_t *q = b + p + 4;
+                const uint32_t l_name = q[8], n_cig = rd16(q + 12), l_seq = rd32(q + 16);
+                if (rec_out) { rec_out[t.rec] = p + 4; no[t.rec] = t.name; co[t.rec] = t.cig; so[t.rec] = t.seq; }
+                t.rec++; t.name += l_name ? l_name - 1 : 0; t.cig += n_cig; t.seq += l_seq;
+                p += 4 + (size_t)bs;
+            }
+            return true;
+        };
+        bool members_ok = S > 1;
+        if (members_ok) {
+            int fail = 0;
+#pragma omp parallel for num_threads(T) schedule(dynamic, 8)
+            for (long long k = 0; k < (long long)S; k++) { Tot t{0, 0, 0, 0}; if (!walk(seg[(size_t)k], seg[(size_t)k + 1], t, nullptr, nullptr, nullptr, nullptr)) fail = 1; tot[(size_t)k + 1] = t; }
+            members_ok = !fail;
         }
-        if (!rec_ok) { err = "truncated BAM alignment record"; break; }
-        lap("record boundaries");
-        const size_t R = rec.size();
+        if (!members_ok) {  // one sequential walk over the whole stream
+            seg.assign({o, n}); S = 1;
+            tot.assign(2, Tot{0, 0, 0, 0});
+            Tot t{0, 0, 0, 0};
+            if (!walk(o, n, t, nullptr, nullptr, nullptr, nullptr)) { err = "truncated BAM alignment record"; break; }
+            tot[1] = t;
+        }
+        for (size_t k = 1; k <= S; k++) { tot[k].rec += tot[k - 1].rec; tot[k].name += tot[k - 1].name; tot[k].cig += tot[k - 1].cig; tot[k].seq += tot[k - 1].seq; }
+        walked_per_member = members_ok;
+        lap(members_ok ? "record boundaries (per BGZF member)" : "record boundaries (sequential)");
+        const size_t R = tot[S].rec;
+        std::vector<size_t> rec(R);
         ref_id.resize(R); pos.resize(R); mate_ref_id.resize(R); mate_pos.resize(R); ih.assign(R, 0); flag.resize(R); mapq.resize(R); tags.assign(R, 0);
-        name_off.assign(R + 1, 0); cigar_off.assign(R + 1, 0); seq_off.assign(R + 1, 0);
-        for (size_t r = 0; r < R; r++) {
-            const uint8_t *p = b + rec[r];
-            const uint32_t l_name = p[8], n_cig = rd16(p + 12), l_seq = rd32(p + 16);
-            name_off[r + 1] = name_off[r] + (l_name ? l_name - 1 : 0);
-            cigar_off[r + 1] = cigar_off[r] + n_cig;
-            seq_off[r + 1] = seq_off[r] + l_seq;
+        name_off.resize(R + 1); cigar_off.resize(R + 1); seq_off.resize(R + 1);
+        name_off[R] = tot[S].name; cigar_off[R] = tot[S].cig; seq_off[R] = tot[S].seq;
+#pragma omp parallel for num_threads(T) schedule(dynamic, 8)
+        for (long long k = 0; k < (long long)S; k++) {
+            Tot t = tot[(size_t)k];
+            const size_t r0 = t.rec;
+            Tot local{0, t.name, t.cig, t.seq};
+            walk(seg[(size_t)k], seg[(size_t)k + 1], local, rec.data() + r0, name_off.data() + r0, cigar_off.data() + r0, seq_off.data() + r0);
         }
         if (!names.resize(name_off[R]) || !cigar.resize(cigar_off[R]) || !seq.resize(seq_off[R]) || !qual.resize(seq_off[R])) { err = "out of memory"; break; }
-        const int T = threads > 0 ? threads : omp_get_num_procs();
         int bad = 0;
         lap("offsets + allocation");
 #pragma omp parallel for num_threads(T) schedule(static)
@@ -205,6 +245,17 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
     return ok;
 }
 
+}  // namespace sqh
+// test hook: opens a BAM file with the front end; *n_rec = records, *per_member = 1 when the member-by-member walk was proven
+extern "C" int sqh_probe_bam(const char *path, int64_t *n_rec, int32_t *per_member) {
+    sqh::BamTable t;
+    std::string err;
+    if (!path || !t.open(path, err)) return -1;
+    if (n_rec) *n_rec = (int64_t)t.n_rec();
+    if (per_member) *per_member = t.walked_per_member ? 1 : 0;
+    return 0;
+}
+namespace sqh {
 AlnSource BamTable::source() const {
     AlnSource s;
     s.n_rec = n_rec();

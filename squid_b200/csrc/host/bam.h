@@ -41,6 +41,7 @@ struct BamTable {
     std::vector<uint64_t> name_off, cigar_off, seq_off;   // n + 1 entries each
     RawBuf<char> names, seq, qual;              // seq / qual as BamTools strings
     RawBuf<uint32_t> cigar;
+    bool walked_per_member = false;             // the record boundaries were found member by member (proven, see bam.cpp)
     uint64_t n_rec() const { return ref_id.size(); }
     // Reads a BGZF-compressed BAM (or an uncompressed BAM stream).  threads <= 0: all cores.
     bool open(const std::string &path, std::string &err, int threads = 0);
@@ -48,7 +49,8 @@ struct BamTable {
 };
 
 // inflate a whole BGZF file (concatenated gzip members with BSIZE) on `threads` threads
-bool bgzf_inflate_all(const uint8_t *data, size_t len, std::vector<uint8_t> &out, std::string &err, int threads);
+// (`member_off`, optional: offset of every member's data in `out`, plus the total as the last entry)
+bool bgzf_inflate_all(const uint8_t *data, size_t len, RawBuf<uint8_t> &out, std::string &err, int threads, std::vector<size_t> *member_off = nullptr);
 
 }  // namespace sqh
 #endif

@@ -19,15 +19,29 @@ def _same_case(a, b):
     assert a.config == b.config and np.array_equal(a.ref_len, b.ref_len)
 
 
-@pytest.mark.parametrize("block,compressed", [(0xFF00, True), (997, True), (0, False)])
-def test_bam_equals_sqmb(tmp_path, built_lib, block, compressed):
+def _probe(path):
+    import ctypes as C
+    from squid_b200 import api
+    L = api.lib()
+    L.sqh_probe_bam.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    n, pm = C.c_int64(), C.c_int32()
+    assert L.sqh_probe_bam(path.encode(), C.byref(n), C.byref(pm)) == 0
+    return n.value, bool(pm.value)
+
+
+@pytest.mark.parametrize("block,compressed,htslib", [(0xFF00, True, False), (997, True, False), (0, False, False), (0xFF00, True, True), (1500, True, True)])
+def test_bam_equals_sqmb(tmp_path, built_lib, block, compressed, htslib):
     from squid_b200 import api, bamio, synth
     cp, hp, conc, chim, info = common.write_case(str(tmp_path), 6000, 17, 0.05, synth.GRCH38_LEN)
     assert (conc.aux & 1).any() and (conc.aux & 2).any() and conc.lowrun.any()  # XA, IH and low-quality runs are exercised
     cb, hb = str(tmp_path / "conc.bam"), str(tmp_path / "chim.bam")
-    bamio.write_bam(cb, conc, block=block or 0xFF00, compressed=compressed)  # small blocks: records straddle BGZF members
-    bamio.write_bam(hb, chim, block=block or 0xFF00, compressed=compressed)
+    bamio.write_bam(cb, conc, block=block or 0xFF00, compressed=compressed, htslib_blocks=htslib)  # small blocks: records straddle BGZF members
+    bamio.write_bam(hb, chim, block=block or 0xFF00, compressed=compressed, htslib_blocks=htslib)
     _same_case(api.HostCase(cp, hp), api.HostCase(cb, hb, bam=True))
+    # members that end at record boundaries (htslib) are walked in parallel -- after that has been proven for the file; any
+    # other layout takes the sequential walk
+    n, per_member = _probe(cb)
+    assert n == conc.n and per_member == (compressed and htslib)
 
 
 def test_bam_known_answers(tmp_path, built_lib):
