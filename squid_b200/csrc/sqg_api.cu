@@ -875,11 +875,6 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
         ctx->chim_upload_err = (int)e;
         ctx->prepass_stage.store(2, std::memory_order_release);
     });
-#define UPV(buf, src, cnt)                                                                                     \
-    do {                                                                                                       \
-        CK(ctx->buf.ensure((cnt) ? (cnt) : 1));                                                                \
-        if (cnt) CK(cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream)); \
-    } while (0)
     ctx->have_chim = true; ctx->have_edge_table = false;
     return SQG_OK;
 }
@@ -893,7 +888,6 @@ static int finish_prepass(sqg_ctx *ctx) {
     ctx->prepass_uploaded = true;
     return SQG_OK;
 }
-#undef UPV
 static int ensure_temp(sqg_ctx *ctx, size_t bytes) { CK(ctx->d_temp.ensure(bytes + 256)); return SQG_OK; }
 #define ENSURE_TEMP(bytes) do { int rc_ = ensure_temp(ctx, bytes); if (rc_) return rc_; } while (0)
 
