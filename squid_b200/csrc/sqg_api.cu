@@ -831,6 +831,8 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
         sqh::SortHook hook;
         static const bool gpu_sort = !(getenv("SQG_GPU_SORT") && atoi(getenv("SQG_GPU_SORT")) == 0);
         if (gpu_sort) hook = [ctx](sqh::SortKey *a, size_t n) { return device_sort_hook(ctx, a, n); };
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream3);  // a previous job's DMA out of ctx->pre must be over before the vectors are rewritten
         ctx->pre.before_disc_realloc = [ctx]() {  // the page-lock must go before the storage does
             sqg_ctx::Pinned &pp = ctx->pre_pinned[0];
             if (pp.p) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream3); cudaHostUnregister(const_cast<void *>(pp.p)); pp.p = nullptr; pp.bytes = 0; }
