@@ -8,6 +8,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -210,8 +211,14 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
             memcpy(cigar.data() + cigar_off[r], q, 4ull * n_cig);
             q += 4ull * n_cig;
             static const char code[] = "=ACMGRSVTWYHKDBN";
+            static const std::array<uint16_t, 256> pair = [] {  // two bases per packed byte, as one little-endian store
+                std::array<uint16_t, 256> t{};
+                for (int v = 0; v < 256; v++) t[(size_t)v] = (uint16_t)((uint8_t)code[v >> 4] | ((uint16_t)(uint8_t)code[v & 15] << 8));
+                return t;
+            }();
             char *sq = seq.data() + seq_off[r], *ql = qual.data() + seq_off[r];
-            for (uint32_t k = 0; k < l_seq; k++) sq[k] = code[(q[k >> 1] >> ((k & 1) ? 0 : 4)) & 15];
+            for (uint32_t k = 0; k + 1 < l_seq; k += 2) { const uint16_t w = pair[q[k >> 1]]; memcpy(sq + k, &w, 2); }
+            if (l_seq & 1) sq[l_seq - 1] = code[q[l_seq >> 1] >> 4];
             q += (l_seq + 1) / 2;
             for (uint32_t k = 0; k < l_seq; k++) ql[k] = (char)(uint8_t)(q[k] + 33);
             q += l_seq;

@@ -54,6 +54,10 @@ def test_bam_known_answers(tmp_path, built_lib):
         dict(ref_id=0, pos=1300, cigar="30=5X30M35S", flag=F.FLAG_PAIRED | F.FLAG_SECOND | F.FLAG_REVERSE, mate_ref_id=0, mate_pos=100,
              seq="ACGT" * 25, qual="I" * 100, name_id=7, xa=True, ih=3, name_suffix=True),
         dict(ref_id=1, pos=5, cigar="100M", flag=F.FLAG_PAIRED | F.FLAG_FIRST, mate_ref_id=1, mate_pos=400, lowrun=12, polya=1, name_id=9, mapq=3),
+        # odd length: the last base sits alone in the high nibble of the last packed byte, and here it decides the poly-A rule
+        # (72 of 95 bases are A: 4*72 >= 3*95, dropped; with 71 it would be kept)
+        dict(ref_id=1, pos=900, cigar="95M", flag=F.FLAG_PAIRED | F.FLAG_FIRST, mate_ref_id=1, mate_pos=1400, seq="A" * 71 + "C" * 23 + "A", qual="I" * 95, name_id=11),
+        dict(ref_id=1, pos=950, cigar="95M", flag=F.FLAG_PAIRED | F.FLAG_FIRST, mate_ref_id=1, mate_pos=1400, seq="A" * 71 + "C" * 23 + "G", qual="I" * 95, name_id=12),
     ]
     t = F.from_records([5000, 3000], recs)
     ch = F.from_records([5000, 3000], [dict(ref_id=0, pos=10, cigar="60M40S", flag=F.FLAG_PAIRED | F.FLAG_FIRST, mate_ref_id=1, mate_pos=50, name_id=1),
@@ -68,7 +72,8 @@ def test_bam_known_answers(tmp_path, built_lib):
     assert blk.tolist() == [[100, 72, 15, 75]] and total == 105 and low == 13
     blk, total, low = b.blocks(1)
     assert blk.tolist() == [[1300, 65, 35, 65]] and total == 100  # reverse strand: read_pos = 100 - 0 - 65
-    assert b.batch.a["aux"].tolist() == [0, 3, 0]  # XA + IH>1 on record 1; the suffixed name never matches ChimName
+    assert b.batch.a["aux"].tolist() == [0, 3, 0, 0, 0]  # XA + IH>1 on record 1; the suffixed name never matches ChimName
+    assert b.blocks(3)[0].shape[0] == 0 and b.blocks(4)[0].tolist() == [[950, 95, 0, 95]]
     assert b.blocks(2)[0].shape[0] == 0 and b.blocks(2)[2] == 12  # poly-A block removed, 12 low qualities
 
 
