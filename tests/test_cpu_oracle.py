@@ -53,3 +53,19 @@ def test_restatement_matches_reference_on_fuzz(seed, n, disc, ref_len, tmp_path,
     me = pyref.run_restate(cp, hp, str(tmp_path / "me"), bps=bps)
     common.assert_same(r, me, ("chim_loaded", "nodes", "avgdepth", "edges", "chim_after_edges"))
     assert pyref.support_from_cov(r, bps, me["cov"]) == pyref.support_map(r)
+
+
+@pytest.mark.parametrize("opts,args", [
+    ((1, 25, 10, 3, 50000, 20), ["-mq", "3", "-pl", "25", "-pm", "10"]),
+    ((1, 5, 4, -1, 3000, 2), ["-dp", "3000", "-di", "2", "-pl", "5"]),
+])
+def test_restatement_matches_reference_with_options(opts, args, tmp_path, ref_oracle):
+    """The -mq / -pl / -pm / -dp / -di rules (Config.cpp:18-25) on both sides; the options must change the outputs."""
+    cp, hp, *_ = common.write_case(str(tmp_path), 20000, 47, 0.03)
+    base = ref_oracle.run(cp, hp, str(tmp_path / "ref0"))
+    r = ref_oracle.run(cp, hp, str(tmp_path / "ref"), extra_args=args)
+    assert not (np.array_equal(r["edges"], base["edges"]) and pyref.support_map(r) == pyref.support_map(base))
+    bps = pyref.breakpoints_of(r)
+    me = pyref.run_restate(cp, hp, str(tmp_path / "me"), bps=bps, opts=opts)
+    common.assert_same(r, me, ("chim_loaded", "nodes", "avgdepth", "edges", "chim_after_edges"))
+    assert pyref.support_from_cov(r, bps, me["cov"]) == pyref.support_map(r)

@@ -210,3 +210,26 @@ def test_bam_input_matches_reference(tmp_path, built_lib, ref_oracle):
            "edges": edges.table(), "chim_after_edges": case.chimeric.block_table()}
     common.assert_same(ref, got)
     assert g.ExactBPConcordantSupport(ref["final_nodes"], ref["final_edges"], pyref.exactbp_map(ref)) == pyref.support_map(ref)
+
+
+@pytest.mark.parametrize("opts,args", [
+    (dict(min_mapq=3, max_lowphred_len=25, min_phred=10), ["-mq", "3", "-pl", "25", "-pm", "10"]),
+    (dict(concord_dist_pos=3000, concord_dist_idx=2, max_lowphred_len=5), ["-dp", "3000", "-di", "2", "-pl", "5"]),
+])
+def test_non_default_parameters(tmp_path, built_lib, ref_oracle, opts, args):
+    """-mq / -pl / -pm gate and classify differently, -dp moves the point at which a breakpoint stops being counted
+    (SegmentGraph.cpp:3157): the same options on both sides, same answers."""
+    from oracle import pyref
+    from squid_b200 import api
+    cp, hp, *_ = common.write_case(str(tmp_path), 50000, 47, 0.03)
+    ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"), extra_args=args)
+    base = ref_oracle.run(cp, hp, str(tmp_path / "ref0"))
+    assert not (np.array_equal(ref["edges"], base["edges"]) and pyref.support_map(ref) == pyref.support_map(base)), "the options must change something"
+    case = api.HostCase(cp, hp, **opts)
+    g = api.SegmentGraph(case.config, case.ref_len)
+    nodes = g.BuildNode_STAR(case.chimeric, case.batch)
+    edges = g.BuildEdges()
+    got = {"nodes": np.stack([nodes.Chr, nodes.Position, nodes.Length, nodes.Support], axis=1).astype(np.int32), "avgdepth": nodes.AvgDepth,
+           "edges": edges.table(), "chim_after_edges": case.chimeric.block_table()}
+    common.assert_same(ref, got)
+    assert g.ExactBPConcordantSupport(ref["final_nodes"], ref["final_edges"], pyref.exactbp_map(ref)) == pyref.support_map(ref)
