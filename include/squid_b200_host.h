@@ -38,6 +38,35 @@ const int32_t *sqh_case_ref_len(const sqh_case *c);
 /* Known-answer access to the decoder: blocks of record r of the concordant table as
  * (ref_pos, match_ref, read_pos, match_read) rows; returns the block count. */
 int32_t sqh_case_blocks(const sqh_case *c, int64_t r, int32_t *out4, int32_t max_blocks, int32_t *total_len, int32_t *lowphred_run);
+
+/*
+ * Replaces SegmentGraph_t::ExactBreakpoint + CountTop (src/SegmentGraph.cpp:3019-3081, 51-102; SURVEY.md §8 row a17, host side).
+ * The chimeric reads -- as sqg_build_edges left them, i.e. already trimmed once -- are located on the FINAL graph
+ * (node_chr/pos/len[n_nodes]: the nodes after the host filters and compression, sorted, not necessarily tiling) with the
+ * literal hinted scan of LocateRead (:1207-1293), which trims them in place again; every discordant split junction adds a
+ * (bp1, bp2) pair to its edge and each edge keeps at most five representatives.
+ * *rows6 = n_rows x (Ind1, Ind2, Head1, Head2, bp1, bp2) in the order of the reference's map<Edge_t, vector<pair>> (edges by
+ * Edge_t::operator<, pairs in vector order); malloc'ed, release with sqh_free().
+ */
+int sqh_exact_breakpoint(const int32_t *node_chr, const int32_t *node_pos, const int32_t *node_len, int64_t n_nodes, sqg_chimeric *chim_inout,
+                         int32_t concord_dist_pos, int32_t concord_dist_idx, int32_t **rows6, int64_t *n_rows);
+void sqh_free(void *p);
+
+/*
+ * The two output formats of the path, byte for byte.
+ *   sqh_write_graph  = SegmentGraph_t::OutputGraph (src/SegmentGraph.cpp:3223-3234): <prefix>_graph.txt
+ *   sqh_write_bedpe  = DeMultiplyDisEdges (src/SegmentGraph.cpp:3012-3017) + WriteBEDPE (src/WriteIO.cpp:45-124): <prefix>_sv.txt.
+ *                      Edges in vEdges order (weights still multiplied by -r); components = the ordering the ILP stage produced
+ *                      (signed 1-based node ids, comp_off[n_comp + 1]); exactbp / support rows as sqh_exact_breakpoint returns
+ *                      them / as ExactBPConcordantSupport fills its map (SegmentGraph.cpp:3171-3211).
+ */
+int sqh_write_graph(const char *path, const int32_t *chr, const int32_t *pos, const int32_t *len, const int32_t *support, const double *avg_depth,
+                    const int32_t *label, int64_t n_nodes, const int32_t *ind1, const int32_t *ind2, const uint8_t *head1, const uint8_t *head2,
+                    const int32_t *weight, int64_t n_edges);
+int sqh_write_bedpe(const char *path, const char *const *ref_name, int32_t n_ref, const int32_t *chr, const int32_t *pos, const int32_t *len, int64_t n_nodes,
+                    const int32_t *ind1, const int32_t *ind2, const uint8_t *head1, const uint8_t *head2, const int32_t *weight, int64_t n_edges,
+                    const int64_t *comp_off, const int32_t *comp_nodes, int64_t n_comp, const int32_t *exactbp_rows6, int64_t n_exactbp,
+                    const int32_t *support_rows6, int64_t n_support, double discordant_ratio, int32_t concord_dist_pos, int32_t concord_dist_idx);
 #ifdef __cplusplus
 }
 #endif

@@ -110,7 +110,7 @@ int main(int argc, char **argv) {
     UsingSTAR = true;
     Min_MapQual = 255;  // Config.cpp:221-222 (STAR, no -mq)
     std::string stop = "";
-    bool quiet = false, bwa = false, mq_given = false;
+    bool quiet = false, bwa = false, mq_given = false, write_outputs = false;
     for (int i = 4; i < argc; i++) {
         std::string a = argv[i];
         auto nxt = [&]() { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return std::string(argv[++i]); };
@@ -126,6 +126,7 @@ int main(int argc, char **argv) {
         else if (a == "-a") MaxAllowedDegree = atoi(nxt().c_str());
         else if (a == "--stop-after") stop = nxt();
         else if (a == "--quiet") quiet = true;
+        else if (a == "--write-outputs") write_outputs = true;  // ref_graph.txt (OutputGraph) and ref_sv.txt (WriteBEDPE under a stand-in ordering)
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     if (bwa) { UsingSTAR = false; if (!mq_given) Min_MapQual = 1; }  // Config.cpp:22 default; 255 is the STAR override (:221-222)
@@ -185,6 +186,32 @@ int main(int argc, char **argv) {
                 g.ExactBPConcordantSupport(conc, Chimrecord, ExactBP, Support);
                 t_cov = now() - t0;
                 dump_bpmap("support_i32.bin", Support);
+                if (write_outputs) {
+                    // main.cpp:37-38, 61-62 without the GLPK ordering in between (out of scope, not installed): the component
+                    // ordering is a deterministic stand-in -- the nodes of every connected component in index order, every third
+                    // component reversed, orientations from a hash -- dumped so that the writer twin is fed the very same one.
+                    g.OutputGraph(outdir + "/ref_graph.txt");
+                    int n_lab = 0;
+                    for (size_t i = 0; i < g.Label.size(); i++) n_lab = std::max(n_lab, g.Label[i] + 1);
+                    vector<vector<int> > Components(n_lab);
+                    for (size_t i = 0; i < g.vNodes.size(); i++) {
+                        const bool neg = ((uint32_t)((uint32_t)i * 2654435761u) >> 7) & 1u;
+                        Components[g.Label[i]].push_back(neg ? -(int)(i + 1) : (int)(i + 1));
+                    }
+                    for (size_t c = 0; c < Components.size(); c += 3) std::reverse(Components[c].begin(), Components[c].end());
+                    {
+                        std::vector<int32_t> flat;
+                        flat.push_back((int32_t)Components.size());
+                        for (size_t c = 0; c < Components.size(); c++) { flat.push_back((int32_t)Components[c].size()); for (size_t j = 0; j < Components[c].size(); j++) flat.push_back(Components[c][j]); }
+                        dump_i32("components_i32.bin", flat);
+                    }
+                    vector<pair<int, int> > Node_NewChr; Node_NewChr.resize(g.vNodes.size());
+                    for (unsigned int i = 0; i < Components.size(); i++)
+                        for (unsigned int j = 0; j < Components[i].size(); j++) Node_NewChr[abs(Components[i][j]) - 1] = make_pair(i, j);
+                    dump_edges("edges_before_demultiply_i32.bin", g.vEdges);
+                    g.DeMultiplyDisEdges();
+                    WriteBEDPE(outdir + "/ref_sv.txt", g, Components, Node_NewChr, RefName, ExactBP, Support);
+                }
             }
         }
     }

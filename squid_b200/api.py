@@ -68,6 +68,7 @@ EXPORTS = [
     "sqg_shard_cov_begin", "sqg_shard_cov_chain", "sqg_shard_cov_owned_t", "sqg_shard_cov_count",
     "sqh_default_options", "sqh_open_case", "sqh_open_bam_case", "sqh_probe_bam", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
     "sqh_case_n_ref", "sqh_case_ref_len", "sqh_case_blocks",
+    "sqh_exact_breakpoint", "sqh_free", "sqh_write_graph", "sqh_write_bedpe",
 ]
 
 _lib = None
@@ -121,6 +122,11 @@ def lib() -> C.CDLL:
     L.sqh_case_ref_len.argtypes = [_P]; L.sqh_case_ref_len.restype = pp(C.c_int32)
     L.sqh_case_blocks.argtypes = [_P, C.c_int64, _P, C.c_int32, pp(C.c_int32), pp(C.c_int32)]
     L.sqh_case_blocks.restype = C.c_int32
+    L.sqh_exact_breakpoint.argtypes = [_P, _P, _P, C.c_int64, pp(sqg_chimeric), C.c_int32, C.c_int32, pp(_P), pp(C.c_int64)]
+    L.sqh_free.argtypes = [_P]; L.sqh_free.restype = None
+    L.sqh_write_graph.argtypes = [C.c_char_p, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int64]
+    L.sqh_write_bedpe.argtypes = [C.c_char_p, pp(C.c_char_p), C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64,
+                                  _P, C.c_int64, _P, C.c_int64, C.c_double, C.c_int32, C.c_int32]
     _lib = L
     return L
 
@@ -479,6 +485,62 @@ class SegmentGraph:
 
     def stat(self, name: str) -> int:
         return int(self.L.sqg_stat(self._h, name.encode()))
+
+
+def ExactBreakpoint(final_nodes: np.ndarray, Chimrecord: "ChimericReads", Concord_Dist_Pos: int = 50000, Concord_Dist_Idx: int = 20) -> np.ndarray:
+    """Twin of SegmentGraph_t::ExactBreakpoint + CountTop (SegmentGraph.cpp:3019-3081, 51-102), host side.  final_nodes rows
+    (Chr, Position, Length, ...); Chimrecord as BuildEdges left it (trimmed in place again here).  Returns rows
+    (Ind1, Ind2, Head1, Head2, bp1, bp2) in the order of the reference's map."""
+    L = lib()
+    fn = np.ascontiguousarray(np.asarray(final_nodes)[:, :3].T, np.int32)
+    cs = Chimrecord.as_struct()
+    rows, n = _P(), C.c_int64()
+    rc = L.sqh_exact_breakpoint(fn[0].ctypes.data, fn[1].ctypes.data, fn[2].ctypes.data, int(fn.shape[1]), C.byref(cs), int(Concord_Dist_Pos), int(Concord_Dist_Idx),
+                                C.byref(rows), C.byref(n))
+    if rc != 0:
+        raise SquidB200Error(rc, "sqh_exact_breakpoint failed")
+    out = _np_from(rows, 6 * n.value, np.int32).reshape(-1, 6)
+    L.sqh_free(rows)
+    return out
+
+
+def OutputGraph(path: str, nodes: np.ndarray, avg_depth: np.ndarray, label: np.ndarray, edges: np.ndarray):
+    """Twin of SegmentGraph_t::OutputGraph (SegmentGraph.cpp:3223-3234): <prefix>_graph.txt.  nodes rows (Chr, Position, Length,
+    Support), edges rows (Ind1, Ind2, Head1, Head2, Weight)."""
+    L = lib()
+    nd = np.ascontiguousarray(np.asarray(nodes)[:, :4].T, np.int32)
+    ad = np.ascontiguousarray(avg_depth, np.float64); lb = np.ascontiguousarray(label, np.int32)
+    ed = np.asarray(edges).reshape(-1, 5)
+    e = [np.ascontiguousarray(ed[:, 0], np.int32), np.ascontiguousarray(ed[:, 1], np.int32), np.ascontiguousarray(ed[:, 2], np.uint8), np.ascontiguousarray(ed[:, 3], np.uint8),
+         np.ascontiguousarray(ed[:, 4], np.int32)]
+    rc = L.sqh_write_graph(path.encode(), nd[0].ctypes.data, nd[1].ctypes.data, nd[2].ctypes.data, nd[3].ctypes.data, ad.ctypes.data, lb.ctypes.data, int(nd.shape[1]),
+                           e[0].ctypes.data, e[1].ctypes.data, e[2].ctypes.data, e[3].ctypes.data, e[4].ctypes.data, int(ed.shape[0]))
+    if rc != 0:
+        raise SquidB200Error(rc, "sqh_write_graph failed")
+
+
+def WriteBEDPE(path: str, ref_names, nodes: np.ndarray, edges: np.ndarray, components, exactbp_rows: np.ndarray, support_rows: np.ndarray,
+               DiscordantRatio: float = 8.0, Concord_Dist_Pos: int = 50000, Concord_Dist_Idx: int = 20):
+    """Twin of DeMultiplyDisEdges + WriteBEDPE (SegmentGraph.cpp:3012-3017; WriteIO.cpp:45-124): <prefix>_sv.txt.  edges rows
+    (Ind1, Ind2, Head1, Head2, Weight) in vEdges order with the weights still multiplied; components = list of lists of signed
+    1-based node ids (the ordering stage's output)."""
+    L = lib()
+    nd = np.ascontiguousarray(np.asarray(nodes)[:, :3].T, np.int32)
+    ed = np.asarray(edges).reshape(-1, 5)
+    e = [np.ascontiguousarray(ed[:, 0], np.int32), np.ascontiguousarray(ed[:, 1], np.int32), np.ascontiguousarray(ed[:, 2], np.uint8), np.ascontiguousarray(ed[:, 3], np.uint8),
+         np.ascontiguousarray(ed[:, 4], np.int32)]
+    off = np.zeros(len(components) + 1, np.int64)
+    for i, c in enumerate(components):
+        off[i + 1] = off[i] + len(c)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32) for c in components]) if len(components) else np.zeros(0, np.int32), np.int32)
+    xb = np.ascontiguousarray(exactbp_rows, np.int32).reshape(-1, 6); sp = np.ascontiguousarray(support_rows, np.int32).reshape(-1, 6)
+    names = (C.c_char_p * len(ref_names))(*[n.encode() for n in ref_names])
+    rc = L.sqh_write_bedpe(path.encode(), names, len(ref_names), nd[0].ctypes.data, nd[1].ctypes.data, nd[2].ctypes.data, int(nd.shape[1]),
+                           e[0].ctypes.data, e[1].ctypes.data, e[2].ctypes.data, e[3].ctypes.data, e[4].ctypes.data, int(ed.shape[0]),
+                           off.ctypes.data, flat.ctypes.data, len(components), xb.ctypes.data, int(xb.shape[0]), sp.ctypes.data, int(sp.shape[0]),
+                           float(DiscordantRatio), int(Concord_Dist_Pos), int(Concord_Dist_Idx))
+    if rc != 0:
+        raise SquidB200Error(rc, "sqh_write_bedpe failed (%d)" % rc)
 
 
 def plan_shards(batch: RecordBatch, chim: ChimericReads, config: Config, n_ref: int, n_shards: int):

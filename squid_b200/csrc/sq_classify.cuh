@@ -73,13 +73,16 @@ struct ClassifyOut {
     uint8_t cls;
     uint64_t other_key;  // (chr+1)<<32 | end of the CIGAR-first block when the record updates otherrightmost, else 0
     int32_t first_len;   // length of the first kept block of a CLS_CONC record, else 0
+    int32_t cc_end;      // end of the first kept block of a ConcordantCluster entry (CLS_CONC, not CLS_PART), else kNoCcEnd
 };
+constexpr int32_t kNoCcEnd = -(1 << 30);
+constexpr int32_t kCcWalkTile = 0x7fffffff;  // per-tile maximum of cc_end: "this tile holds several chromosomes, walk it"
 
 // `prev` = index of the previous gate-passing record, or -1.
 template <class B>
 SQ_HD ClassifyOut classify_record(const B &b, const Params &p, int64_t r, int64_t prev) {
     ClassifyOut o;
-    o.cls = 0; o.other_key = 0; o.first_len = 0;
+    o.cls = 0; o.other_key = 0; o.first_len = 0; o.cc_end = kNoCcEnd;
     const uint16_t f = b.flag[r];
     const int32_t rid = b.ref_id[r];
     if (!record_gate(f, b.mapq[r], b.aux[r], rid, p.min_mapq)) return o;
@@ -110,6 +113,7 @@ SQ_HD ClassifyOut classify_record(const B &b, const Params &p, int64_t r, int64_
             if (front_rp > 15 || (int32_t)b.total_len[r] - back_rp - back_mr > 15) o.cls |= CLS_PART;
         }
     }
+    if (!(o.cls & CLS_PART)) o.cc_end = b.blk_ref_pos[off] + b.blk_match_ref[off];
     return o;
 }
 

@@ -29,6 +29,7 @@ struct P1Out {
     uint8_t *cls;
     uint16_t *first_len;      // per record: length of the first kept block of a CLS_CONC record (65535 = too long for 16 bits), else 0
     TileAgg *agg;             // n_tiles
+    int32_t *ccmax;           // n_tiles: maximum end of the ConcordantCluster entries of the tile (kNoCcEnd: none; kCcWalkTile: several chromosomes)
     uint64_t *gate_word;      // n_tiles, zeroed: one-word chain of "1 + index of the last gate-passing record"
     int32_t *cand_rec; uint64_t *cand_key; int32_t *n_cand; int32_t cand_cap;
     int32_t *lmax;
@@ -66,12 +67,12 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     __shared__ int32_t s_cmax[kTileChunks];   // per chunk: max key end, then the exclusive maximum before the chunk
     __shared__ int32_t s_pc[kWarpsPerTile], s_dp[kWarpsPerTile];
     __shared__ long long s_prev_carry;
-    __shared__ int32_t s_bad, s_lmax, s_minkeep;
+    __shared__ int32_t s_bad, s_lmax, s_minkeep, s_ccmax;
     int32_t *s_end = s.end_pos;               // per record: end of the first block if the record updates otherrightmost, else 0
     uint16_t *s_flen = s.total_len;           // per record: first_len (a record's total_len is only read by its own thread, before)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
-    if (tid == 0) { s_tile = atomicAdd(o.ticket, 1); s_bad = 0; s_lmax = 0; s_minkeep = kTile; }
+    if (tid == 0) { s_tile = atomicAdd(o.ticket, 1); s_bad = 0; s_lmax = 0; s_minkeep = kTile; s_ccmax = kNoCcEnd; }
     __syncthreads();
     const int tile = s_tile;
     const StageTicket tk = stage_issue<kP1Fields>(s, b, nullptr, tile, bulk_ok != 0);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     // single-chromosome tiles (all but a handful) compare 32-bit block ends; the others are finished by one thread below
     const int32_t chr_tile = s.ref_id[0];
     const bool single_chr = chr_tile >= 0 && s.ref_id[n - 1] == chr_tile;
-    int32_t flen_max = 0, npc = 0, ndp = 0;
+    int32_t flen_max = 0, npc = 0, ndp = 0, cc_max = kNoCcEnd;
 #pragma unroll 1
     for (int j = 0; j < kTileRPT; j++) {
         const int i = j * kTileThreads + tid;
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
             c = co.cls; key_end = (int32_t)(uint32_t)co.other_key;  // (other_key >> 32) - 1 == ref_id of the record
             co_len = co.first_len;
             if (co.first_len > flen_max) flen_max = co.first_len;
+            if (co.cc_end > cc_max) cc_max = co.cc_end;
         }
         if (i < n) { s.cls[i] = c; s_end[i] = key_end; s_flen[i] = (uint16_t)(co_len < 65535 ? co_len : 65535); }
         const int chunk = j * kWarpsPerTile + warp;
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
         if (lane == 0) { s_cmax[chunk] = cm; if (km) atomicMin(&s_minkeep, chunk * 32 + __ffs(km) - 1); }
     }
     flen_max = __reduce_max_sync(full, flen_max);
-    if (lane == 0) { s_pc[warp] = npc; s_dp[warp] = ndp; if (flen_max > 0) atomicMax(&s_lmax, flen_max); }
+    cc_max = __reduce_max_sync(full, cc_max);
+    if (lane == 0) { s_pc[warp] = npc; s_dp[warp] = ndp; if (flen_max > 0) atomicMax(&s_lmax, flen_max); if (cc_max > kNoCcEnd) atomicMax(&s_ccmax, cc_max); }
     __syncthreads();
     if (warp == 0) {  // chunk maxima -> exclusive maximum before each chunk; the tile's aggregate
         int32_t inc = lane < kTileChunks ? s_cmax[lane] : 0;
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     } else for (int i = 4 * tid; i < n; i++) { o.cls[rec0 + i] = s.cls[i]; o.first_len[rec0 + i] = s_flen[i]; }
     __syncthreads();
     if (tid == 0) {
+        o.ccmax[tile] = single_chr ? s_ccmax : kCcWalkTile;
         if (s_lmax > 0) atomicMax(o.lmax, s_lmax);
         if (s_minkeep < kTile) atomicMin(o.first_kept, (long long)(rec0 + s_minkeep));
         if (s_bad) atomicOr(o.bad_flags, s_bad);

@@ -71,6 +71,9 @@ struct SeedInputs {
     int32_t g_hi = 0;               // groups from g_hi on are never triggered by this batch (trigger == n_rec): islands cover [g_lo, g_hi)
     bool has_next = false;
     uint64_t end_other = 0;         // otherChr/otherrightmost after the last record of the batch
+    const int32_t *ccmax = nullptr; int32_t cc_tile = 0;  // per tile of cc_tile records: maximum end of its ConcordantCluster entries (sq_classify.cuh)
+    int32_t dense_max_r = 0;        // > 0: sub-clusters whose margins span at most this many positions use position-indexed tables
+    bool dense_all = false;         // ... on every island (tests); default: only islands whose windows span > kHeavySpan records
 };
 
 struct SeedState {
@@ -97,6 +100,10 @@ struct CoopSerial {  // one lane (CPU stepping harness, tiny islands)
     static SQ_HD void add(int32_t *p, int32_t v) { *p += v; }
     static SQ_HD void add_range(int32_t *diff, int32_t ja, int32_t jb, bool on) { if (on && ja < jb) { diff[ja] += 1; diff[jb] -= 1; } }
     static SQ_HD void sync() {}
+    // unordered append: begin(cell, n) .. reserve(has, n, cell) per lane .. end(cell, n) leaves the new uniform count in n
+    static SQ_HD void begin_append(int32_t *cell, int32_t n) { (void)cell; (void)n; }
+    static SQ_HD int32_t reserve(bool has, int32_t &n, int32_t *cell) { (void)cell; const int32_t s = n; if (has) n++; return s; }
+    static SQ_HD void end_append(int32_t *cell, int32_t &n) { (void)cell; (void)n; }
 };
 #if defined(__CUDACC__)
 struct CoopWarp {  // 32 lanes of one warp
@@ -131,6 +138,15 @@ struct CoopWarp {  // 32 lanes of one warp
         if (l == __ffs(m) - 1) atomicAdd(&diff[jb], -__popc(m));
     }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
+    static __device__ __forceinline__ void begin_append(int32_t *cell, int32_t n) { (void)cell; (void)n; }
+    static __device__ __forceinline__ int32_t reserve(bool has, int32_t &n, int32_t *cell) {  // lanes in lockstep: slots from a ballot
+        (void)cell;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        const int32_t s = n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        n += __popc(m);
+        return s;
+    }
+    static __device__ __forceinline__ void end_append(int32_t *cell, int32_t &n) { (void)cell; (void)n; }
 };
 struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): for the few islands with huge windows
     template <int OP> static __device__ __forceinline__ int reduce(int v, int identity) {
@@ -194,6 +210,19 @@ struct CoopBlock {  // every thread of the block (blockDim.x a multiple of 32): 
         if (l == __ffs(m) - 1) atomicAdd(&diff[jb], -__popc(m));
     }
     static __device__ __forceinline__ void sync() { __syncthreads(); }
+    // unordered append through a counter cell in the island's scratch (one atomic per warp)
+    static __device__ __forceinline__ void begin_append(int32_t *cell, int32_t n) { __syncthreads(); if (threadIdx.x == 0) *cell = n; __syncthreads(); }
+    static __device__ __forceinline__ int32_t reserve(bool has, int32_t &n, int32_t *cell) {
+        (void)n;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (!m) return 0;
+        const int l = threadIdx.x & 31;
+        int32_t base = 0;
+        if (l == __ffs(m) - 1) base = atomicAdd(cell, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        return base + __popc(m & ((1u << l) - 1u));
+    }
+    static __device__ __forceinline__ void end_append(int32_t *cell, int32_t &n) { __syncthreads(); n = *(volatile int32_t *)cell; __syncthreads(); }
 };
 #endif
 
@@ -270,7 +299,19 @@ struct SeedMachineT {
         else emit(2, st.backChr, e, 0);
         st.backEnd = e;
     }
-    SQ_HD int32_t mcap() const { return margin_cap / 6; }
+    SQ_HD int32_t mcap() const { return (margin_cap - 8) / 6; }     // six regions + 8 reserved cells at the end of the scratch
+    SQ_HD int32_t *cell(int k) const { return margin + (margin_cap - 8) + k; }
+    bool use_dense = false;   // set per island by the caller (heavy islands; tests force it everywhere)
+    int32_t n_dense = 0, n_sparse = 0;  // sub-clusters tabulated by position / through the sorted margins (statistics)
+    // first index i in [lo,hi) with pred(i), else hi; the lanes split the range, the result is uniform
+    template <class F> SQ_HD int32_t find_first(int32_t lo, int32_t hi, F pred) const {
+        for (int32_t base = lo; base < hi; base += W::size()) {
+            const int32_t i = base + W::lane();
+            const int32_t m = W::min((i < hi && pred(i)) ? i : 0x7fffffff);
+            if (m != 0x7fffffff) return m;
+        }
+        return hi;
+    }
     SQ_HD void push_margin(int32_t &n, int32_t v) {  // uniform call: every lane counts, lane 0 stores
         if (n + 1 >= mcap()) { error = 1; return; }
         if (W::lane() == 0) margin[n] = v;
@@ -477,9 +518,13 @@ struct SeedMachineT {
         if (!rv && p1 > m0 - thresh && p1 < curEndPos + thresh) { *v = p1; return true; }
         return false;
     }
-    // Lanes split the candidate list [lo,hi) of `list` (pc_rec or dp_rec indices); the margins are sorted afterwards, so
-    // only the multiset matters.  `want_displ`: take displaced PART entries (dp list) / non-displaced entries (pc list).
+    // Lanes split the candidate list [lo,hi) of `list` (pc_rec or dp_rec indices); the margins are sorted (or histogrammed)
+    // afterwards, so only the multiset matters: unordered append.  `from_dp`: take displaced PART entries (dp list) /
+    // non-displaced entries (pc list).
     SQ_HD void pc_margins(const int32_t *list, int32_t lo, int32_t hi, bool from_dp, int32_t chrG, int32_t m0, int32_t curEndPos, int32_t &nM) {
+        if (hi <= lo) return;
+        const int32_t cap = mcap() - 1;
+        W::begin_append(cell(0), nM);
         for (int32_t base = lo; base < hi; base += W::size()) {
             const int32_t i = base + W::lane();
             int32_t v = 0;
@@ -489,11 +534,11 @@ struct SeedMachineT {
                 const uint8_t c = in.cls[r];
                 if (from_dp ? (c & CLS_PART) != 0 : !(c & CLS_DISPL)) has = pc_margin_value(r, chrG, m0, curEndPos, &v);
             }
-            const int32_t at = W::excl_prefix_sum(has ? 1 : 0), tot = W::sum(has ? 1 : 0);
-            if (nM + tot + 1 >= mcap()) { error = 1; return; }
-            if (has) margin[nM + at] = v;
-            nM += tot;
+            const int32_t at = W::reserve(has, nM, cell(0));
+            if (has && at < cap) margin[at] = v;
         }
+        W::end_append(cell(0), nM);
+        if (nM >= cap) error = 1;
     }
 
     // ---- per-break tables ------------------------------------------------------------------------------------------
@@ -636,6 +681,143 @@ struct SeedMachineT {
         scan_inplace(t_pl, nM); scan_inplace(t_pr, nM); scan_inplace(t_cov, nM); scan_inplace(t_rest, nM);
     }
 
+    // ---- the same tables indexed by POSITION -----------------------------------------------------------------------
+    // When the margins of a sub-cluster span a modest position range [P_lo, P_lo + R) -- the rule for every island that sits in
+    // a highly expressed gene, where the windows hold hundreds of thousands of records and the margins thousands of partial-
+    // alignment ends -- nothing needs the sorted margin array: H[x] counts the margins at position x, the interval-shaped
+    // contributions are +1/-1 at clamped position offsets (no binary searches), one prefix sum per table turns them into
+    // values, and the candidate breaks (the positions that pass the support and coverage tests of :455-475, none of which
+    // depends on what the break loop emits) are compacted in increasing order for the short sequential pass.
+    SQ_HD int32_t didx(int32_t x, int32_t P_lo, int32_t R) const { const int32_t i = x - P_lo; return i < 0 ? 0 : (i > R ? R : i); }
+    // returns the number of candidate breaks; CAND = (position, support) pairs
+    SQ_HD int32_t tabulate_dense(int32_t nM, int32_t P_lo, int32_t R, int32_t ds, int32_t de, int32_t chrG, int32_t sPos, int64_t rg, int32_t szPC, int32_t *CAND) {
+        const int32_t thresh = kSeedThresh, RL = in.read_len;
+        int32_t *H = margin + mcap(), *PL = H + (R + 2), *PR = PL + (R + 2), *COV = PR + (R + 2), *REST = COV + (R + 2);
+        const DiscBlock *D = in.D;
+        W::sync();
+        for (int32_t i = W::lane(); i < 5 * (R + 2); i += W::size()) H[i] = 0;
+        W::sync();
+        for (int32_t i = W::lane(); i < nM; i += W::size()) W::add(&H[margin[i] - P_lo], 1);
+        for (int32_t k = ds + W::lane(); k < de; k += W::size()) {
+            const int32_t p0 = D[k].pos, p1 = p0 + D[k].len;
+            if (!D[k].rev) add_range(PL, didx(p1 + 1, P_lo, R), didx(p1 + RL, P_lo, R));            // end < b < end+ReadLen   (:450)
+            else add_range(PR, didx(p0 - RL + 1, P_lo, R), didx(p0, P_lo, R));                      // pos-ReadLen < b < pos   (:452)
+            if (D[k].chr == chrG) add_range(COV, didx(p0 + thresh + 1, P_lo, R), didx(p1 - thresh + 1, P_lo, R));   // :462-464
+        }
+        const int32_t bmin = P_lo, bmax = P_lo + R - 1;
+        const int32_t pmin = bmin + thresh - in.lmax, pmax = bmax - thresh;  // block starts that can span some break
+        if (st.offCC < rg) {  // ConcordantCluster window (:457-461); every record of [lo,hi) lies on chrG (sorted stream, rg is the group's trigger)
+            const int64_t lo = lb_pos(st.offCC, rg, chrG, pmin), hi = lb_pos(lo, rg, chrG, pmax);
+            constexpr int U = 8;
+            for (int64_t base = lo; base < hi; base += (int64_t)W::size() * U) {
+                uint8_t c[U]; uint32_t fl[U]; int32_t ps_[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int64_t r = base + (int64_t)u * W::size() + W::lane();
+                    const bool inr = r < hi;
+                    c[u] = inr ? in.cls[r] : (uint8_t)0; fl[u] = inr ? in.first_len[r] : 0u; ps_[u] = inr ? in.b.pos[r] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const bool ok = (c[u] & (CLS_CONC | CLS_PART | CLS_DISPL)) == CLS_CONC;
+                    int32_t l = (int32_t)fl[u];
+                    if (ok && fl[u] == 65535u) l = in.b.blk_match_ref[in.b.blk_off[base + (int64_t)u * W::size() + W::lane()]];
+                    W::add_range(COV, didx(ps_[u] + thresh + 1, P_lo, R), didx(ps_[u] + l - thresh + 1, P_lo, R), ok);
+                }
+            }
+        }
+        if (st.offPC < szPC) {  // PartialAlignCluster window (:465-469)
+            const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, pmin), hi = lb_pc_pos(lo, szPC, chrG, pmax);
+            for (int32_t base = lo; base < hi; base += W::size()) {
+                const int32_t i = base + W::lane();
+                bool on = false;
+                int32_t ja = 0, jb = 0;
+                if (i < hi) {
+                    const int64_t r = in.pc_rec[i];
+                    if (!isDispl(r) && in.b.ref_id[r] == chrG) { on = true; const int32_t p0 = e_pos(r); ja = didx(p0 + thresh + 1, P_lo, R); jb = didx(p0 + e_len(r) - thresh + 1, P_lo, R); }
+                }
+                W::add_range(COV, ja, jb, on);
+            }
+        }
+        {   // displaced entries of either window
+            const int64_t w0 = st.offCC < rg ? st.offCC : rg;
+            const int64_t wp = st.offPC < szPC ? (int64_t)in.pc_rec[st.offPC] : rg;
+            const int32_t k0 = lb_list(in.dp_rec, in.n_dp, w0 < wp ? w0 : wp), k1 = lb_list(in.dp_rec, in.n_dp, rg);
+            for (int32_t k = k0 + W::lane(); k < k1; k += W::size()) {
+                const int64_t r = in.dp_rec[k];
+                if (in.b.ref_id[r] != chrG) continue;
+                const bool part = in.cls[r] & CLS_PART;
+                if (part ? (r < wp) : (r < st.offCC)) continue;
+                const int32_t p0 = e_pos(r);
+                add_range(COV, didx(p0 + thresh + 1, P_lo, R), didx(p0 + e_len(r) - thresh + 1, P_lo, R));
+            }
+        }
+        {   // ConcordRest (:471-473): blocks of records before rg that start at/after group start - ReadLen
+            const int32_t lo_pos = sPos - RL;
+            int32_t lo = 0, hi = in.n_rest;
+            while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
+            int32_t lo2 = lo, hi2 = in.n_rest;
+            while (lo2 < hi2) { int32_t m = (lo2 + hi2) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < pmax)) lo2 = m + 1; else hi2 = m; }
+            for (int32_t base = lo; base < lo2; base += W::size()) {
+                const int32_t k = base + W::lane();
+                bool on = false;
+                int32_t ja = 0, jb = 0;
+                if (k < lo2) {
+                    const RestBlock e = in.rest[k];
+                    if (e.rec < rg) { on = true; ja = didx(e.pos + thresh + 1, P_lo, R); jb = didx(e.end - thresh + 1, P_lo, R); }
+                }
+                W::add_range(REST, ja, jb, on);
+            }
+        }
+        scan_inplace(PL, R); scan_inplace(PR, R); scan_inplace(COV, R); scan_inplace(REST, R);
+        // candidate breaks, in increasing position
+        int32_t nC = 0;
+        for (int32_t base = 0; base < R; base += W::size()) {
+            const int32_t i = base + W::lane();
+            bool is = false;
+            int32_t sup = 0;
+            if (i < R && H[i] > 0) {
+                int32_t sr = 0;  // margins within +-thresh (:445-448)
+                for (int32_t d = -(thresh - 1); d <= thresh - 1; d++) { const int32_t q = i + d; if (q >= 0 && q < R) sr += H[q]; }
+                const int32_t pl = PL[i], pr = PR[i];
+                if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
+                    int32_t coverage = COV[i];
+                    int32_t rest = coverage - sr; if (rest < 0) rest = 0;
+                    if (sr > rest + 2) { coverage += REST[i]; rest = coverage - sr; if (rest < 0) rest = 0; }
+                    if (sr > rest + 2) { is = true; sup = sr + (pl > pr ? pl : pr); }
+                }
+            }
+            const int32_t tot = W::sum(is ? 1 : 0);
+            if (tot == 0) continue;
+            const int32_t at = nC + W::excl_prefix_sum(is ? 1 : 0);
+            if (is) { CAND[2 * at] = P_lo + i; CAND[2 * at + 1] = sup; }
+            nC += tot;
+        }
+        W::sync();
+        return nC;
+    }
+
+    struct BreakCtx { int32_t lastCurser, lastSupport, curStartPos, curEndPos; bool isClusternSplit; };
+    // :476-497 for a break position that passed the support and coverage tests
+    SQ_HD void accept_break(int32_t brk, int32_t sup, int32_t chrG, int32_t dpos, BreakCtx &c) {
+        const int32_t thresh = kSeedThresh;
+        if (c.lastCurser == -1 && brk - c.curStartPos < thresh * 20) {
+            st.markedStart = c.curStartPos; st.markedChr = chrG;
+        } else if ((c.lastCurser == -1 || brk - c.lastCurser < thresh * 20) && sup > c.lastSupport) {
+            c.lastCurser = brk; c.lastSupport = sup;
+        } else if (brk - c.lastCurser >= thresh * 20) {
+            c.isClusternSplit = true;
+            if (dpos - c.curStartPos > thresh * 20 && c.lastCurser - dpos > thresh * 20) {
+                push_node(chrG, c.curStartPos, dpos - c.curStartPos);
+                c.curStartPos = dpos;
+            }
+            push_node(chrG, c.curStartPos, c.lastCurser - c.curStartPos);
+            c.curStartPos = c.lastCurser; c.curEndPos = c.lastCurser;
+            st.markedStart = c.lastCurser; st.markedChr = chrG;
+            c.lastCurser = brk;
+        }
+    }
+
     // flag1/flag2 of the two walks at :536-601 for an entry (c,p0,p1); dc = first discordant block not covered yet
     SQ_HD bool walk_ok(bool first_walk, int32_t chrG, int32_t dc, int32_t c, int32_t p0, int32_t p1) const {
         const DiscBlock *D = in.D;
@@ -648,6 +830,34 @@ struct SeedMachineT {
         }
         return dc == in.nD || c < D[dc].chr || (c == D[dc].chr && p1 + RL < D[dc].pos);
     }
+    // maximum end over the ConcordantCluster entries of records [a, b) (all on one chromosome): whole tiles from the per-tile
+    // table of the classification pass, the ragged ends (and the rare tiles that hold several chromosomes) by walking
+    SQ_HD int32_t cc_end_max_walk(int64_t a, int64_t b) const {
+        int32_t m = -(1 << 30);
+        for (int64_t r = a + W::lane(); r < b; r += W::size())
+            if (isCC(r)) { const int32_t e = e_pos(r) + e_len(r); if (e > m) m = e; }
+        return m;  // lane-local
+    }
+    SQ_HD int32_t cc_end_max(int64_t a, int64_t b) const {
+        int32_t m = -(1 << 30);
+        if (b <= a) return m;
+        const int64_t T = in.cc_tile;
+        int64_t ta = T > 0 ? (a + T - 1) / T : 0, tb = T > 0 ? b / T : 0;
+        if (!in.ccmax || T <= 0 || ta >= tb) m = cc_end_max_walk(a, b);
+        else {
+            int32_t v = cc_end_max_walk(a, ta * T); if (v > m) m = v;
+            v = cc_end_max_walk(tb * T, b); if (v > m) m = v;
+            for (int64_t t = ta + W::lane(); t < tb; t += W::size()) {
+                int32_t q = in.ccmax[t];
+                if (q == 0x7fffffff) {  // several chromosomes in the tile: this lane walks it
+                    q = -(1 << 30);
+                    for (int64_t r = t * T; r < (t + 1) * T; r++) if (isCC(r)) { const int32_t e = e_pos(r) + e_len(r); if (e > q) q = e; }
+                }
+                if (q > m) m = q;
+            }
+        }
+        return W::max(m);
+    }
     // Advance st.offCC over the maximal prefix of window entries that pass walk_ok; returns the largest end consumed.
     SQ_HD int32_t consume_cc(int64_t rg, int32_t chrG, int32_t dc, bool first_walk) {
         constexpr int U = 4;
@@ -655,6 +865,34 @@ struct SeedMachineT {
         const int chunk = W::size() * U;
         int32_t mx = NEG;
         int64_t x = st.offCC;
+        if (first_walk && x < rg && in.b.ref_id[x] == chrG) {
+            // Every entry of [offCC, rg) lies on chrG (sorted stream; :529-530 skipped the earlier chromosomes).  An entry that
+            // starts left of T = min(next discordant block - ReadLen - lmax, end of the last segment) passes walk_ok whatever
+            // its length, so up to the first record at or right of T only the maximum end matters: no per-chunk reductions.
+            int64_t T = (int64_t)1 << 40;
+            const DiscBlock *D = in.D;
+            if (dc != in.nD && D[dc].chr == chrG) T = (int64_t)D[dc].pos - in.read_len - in.lmax;
+            bool any_ok = true;
+            if (st.have_back) {
+                if (st.backChr < chrG) any_ok = false;               // c > backChr for every entry
+                else if (st.backChr == chrG && st.backEnd < T) T = st.backEnd;
+            }
+            if (any_ok && T > in.b.pos[x]) {
+                int64_t xs = T >= ((int64_t)1 << 31) ? rg : lb_pos(x, rg, chrG, (int32_t)T);
+                // displaced entries start elsewhere than their record: the first one in [x, xs) that fails ends the prefix
+                for (int32_t k = lb_list(in.dp_rec, in.n_dp, x); k < in.n_dp && in.dp_rec[k] < xs; k++) {
+                    const int64_t r = in.dp_rec[k];
+                    if (!isCC(r)) continue;
+                    const int32_t p0 = e_pos(r);
+                    if (!walk_ok(true, chrG, dc, e_chr(r), p0, p0 + e_len(r))) { xs = r; break; }
+                }
+                if (xs > x) {
+                    const int32_t m = cc_end_max(x, xs);
+                    if (m > mx) mx = m;
+                    x = xs;
+                }
+            }
+        }
         while (x < rg) {
             uint8_t c[U]; uint32_t fl[U]; int32_t rc[U], ps[U];
 #pragma unroll
@@ -847,7 +1085,9 @@ struct SeedMachineT {
             int32_t lo = 0, hi = in.nP;
             while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.Pchr[m] < chrG || (in.Pchr[m] == chrG && in.Ppos[m] < v)) lo = m + 1; else hi = m; }
             ps = lo;
-            for (pe = ps; pe < in.nP && in.Pchr[pe] == chrG && in.Ppos[pe] < nextright + RL; pe++) {}
+            hi = in.nP;  // first entry from ps on that leaves (chrG, < nextright + ReadLen); the list is sorted by (chr, pos)
+            while (lo < hi) { int32_t m = (lo + hi) >> 1; if (in.Pchr[m] == chrG && in.Ppos[m] < nextright + RL) lo = m + 1; else hi = m; }
+            pe = lo;
         }
         SQ_PROF_ADD(1);
         while (ds != de) {
@@ -855,18 +1095,29 @@ struct SeedMachineT {
             isClusternSplit = false;
             int32_t nM = 0;
             int32_t dc;
-            for (dc = ds; dc != de; dc++) {
-                push_margin(nM, D[dc].pos); push_margin(nM, D[dc].pos + D[dc].len);
-                if (D[dc].pos + D[dc].len > curEndPos) curEndPos = D[dc].pos + D[dc].len;
-                if (dc + 1 != de && D[dc + 1].pos > D[dc].pos + D[dc].len) break;
-            }
-            disStartPos = curStartPos > D[ds].pos ? curStartPos : D[ds].pos;
-            disEndPos = curEndPos;
-            disCount = dc - ds;
-            if (dc != de)
-                for (dc++; dc != de && D[dc].pos < curEndPos + thresh; dc++) { push_margin(nM, D[dc].pos); push_margin(nM, D[dc].pos + D[dc].len); }
-            for (int32_t pc = ps; pc != pe && in.Ppos[pc] < curEndPos + thresh; pc++) push_margin(nM, in.Ppos[pc]);
             const int32_t m0 = D[ds].pos;  // MarginPositions.front() while still unsorted
+            {   // :400-416, the loops over the discordant blocks and PartAlignPos split across the lanes (only the multiset of
+                // margins matters).  First loop: blocks from ds up to one that the next block does not touch.
+                const int32_t dcb = find_first(ds, de - 1, [&](int32_t k) { return D[k + 1].pos > D[k].pos + D[k].len; });
+                const bool broke = dcb < de - 1;
+                int32_t mx = -(1 << 30);
+                for (int32_t k = ds + W::lane(); k <= dcb; k += W::size()) { const int32_t e = D[k].pos + D[k].len; if (e > mx) mx = e; }
+                mx = W::max(mx);
+                if (mx > curEndPos) curEndPos = mx;
+                disStartPos = curStartPos > D[ds].pos ? curStartPos : D[ds].pos;
+                disEndPos = curEndPos;
+                disCount = broke ? dcb - ds : de - ds;
+                dc = broke ? dcb : de;
+                int32_t dend = de;  // margins of the blocks [ds, dend)
+                if (broke) { const int32_t lim = curEndPos + thresh; dend = find_first(dcb + 1, de, [&](int32_t k) { return !(D[k].pos < lim); }); dc = dend; }
+                int32_t pce = ps;   // PartAlignPos entries [ps, pce): sorted by position inside the group's window
+                { int32_t lo = ps, hi = pe; const int32_t lim = curEndPos + thresh; while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (in.Ppos[m] < lim) lo = m + 1; else hi = m; } pce = lo; }
+                const int32_t n_fixed = 2 * (dend - ds) + (pce - ps);
+                if (n_fixed + 1 >= mcap()) { error = 1; return; }
+                for (int32_t k = ds + W::lane(); k < dend; k += W::size()) { margin[2 * (k - ds)] = D[k].pos; margin[2 * (k - ds) + 1] = D[k].pos + D[k].len; }
+                for (int32_t k = ps + W::lane(); k < pce; k += W::size()) margin[2 * (dend - ds) + (k - ps)] = in.Ppos[k];
+                nM = n_fixed;
+            }
             if (st.offPC < szPC) {  // :420-434; an entry contributes only if its block start lies in (m0-thresh-lmax, curEndPos+thresh)
                 const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, m0 - thresh - in.lmax), hi = lb_pc_pos(lo, szPC, chrG, curEndPos + thresh);
                 pc_margins(in.pc_rec, lo, hi, false, chrG, m0, curEndPos, nM);
@@ -874,54 +1125,63 @@ struct SeedMachineT {
                 if (in.n_dp > 0 && !error) pc_margins(in.dp_rec, lb_list(in.dp_rec, in.n_dp, wp), lb_list(in.dp_rec, in.n_dp, rg), true, chrG, m0, curEndPos, nM);
             }
             if (error) return;
+            W::sync();
             SQ_PROF_ADD(2);
-            sort_margins(nM);
-            if (error) return;
-            ms = margin;
-            if (nM <= msearch_cap) {  // the sorted margins are searched twice per window entry: keep them close
-                for (int32_t i = W::lane(); i < nM; i += W::size()) msearch[i] = margin[i];
-                W::sync();
-                ms = msearch;
+            BreakCtx bc;
+            bc.lastCurser = -1; bc.lastSupport = 0; bc.curStartPos = curStartPos; bc.curEndPos = curEndPos; bc.isClusternSplit = false;
+            bool dense = false;
+            int32_t P_lo = 0, R = 0;
+            if (use_dense && in.dense_max_r > 0) {  // position range of the margins: small enough for position-indexed tables?
+                int32_t mn = 0x7fffffff, mx = -(1 << 30);
+                for (int32_t i = W::lane(); i < nM; i += W::size()) { const int32_t v = margin[i]; if (v < mn) mn = v; if (v > mx) mx = v; }
+                mn = W::min(mn); mx = W::max(mx);
+                const int64_t r64 = (int64_t)mx - mn + 1;
+                // (a wide range with a handful of margins is cheaper through the sorted margins: the tables cost O(R))
+                if (r64 <= in.dense_max_r && r64 <= 16 * (int64_t)nM + 4096 && 5 * (r64 + 2) + 2 * (r64 < nM ? r64 : (int64_t)nM) + 2 <= 5 * (int64_t)mcap()) { dense = true; P_lo = mn; R = (int32_t)r64; }
             }
-            SQ_PROF_ADD(3);
-            tabulate_breaks(nM, ds, de, chrG, in.D[grp.ds].pos, rg, szPC);
-            SQ_PROF_ADD(4);
-            const int32_t *t_sr = margin + mcap(), *t_pl = margin + 2 * mcap(), *t_pr = margin + 3 * mcap(), *t_cov = margin + 4 * mcap(), *t_rest = margin + 5 * mcap();
-            int32_t lastCurser = -1, lastSupport = 0;
-            for (int32_t ib = 0; ib < nM;) {
-                const int32_t brk = ms[ib];
-                if (st.have_back && st.backChr == chrG && brk - st.backEnd < thresh * 20) { ib++; continue; }
-                const int32_t sr = t_sr[ib], pl = t_pl[ib], pr = t_pr[ib];
-                if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
-                    int32_t coverage = t_cov[ib];
-                    int32_t rest = coverage - sr; if (rest < 0) rest = 0;
-                    if (sr > rest + 2) {
-                        coverage += t_rest[ib];
-                        rest = coverage - sr; if (rest < 0) rest = 0;
-                    }
-                    if (sr > rest + 2) {
-                        const int32_t sup = sr + (pl > pr ? pl : pr);
-                        if (lastCurser == -1 && brk - curStartPos < thresh * 20) {
-                            st.markedStart = curStartPos; st.markedChr = chrG;
-                        } else if ((lastCurser == -1 || brk - lastCurser < thresh * 20) && sup > lastSupport) {
-                            lastCurser = brk; lastSupport = sup;
-                        } else if (brk - lastCurser >= thresh * 20) {
-                            isClusternSplit = true;
-                            if (D[ds].pos - curStartPos > thresh * 20 && lastCurser - D[ds].pos > thresh * 20) {
-                                push_node(chrG, curStartPos, D[ds].pos - curStartPos);
-                                curStartPos = D[ds].pos;
-                            }
-                            push_node(chrG, curStartPos, lastCurser - curStartPos);
-                            curStartPos = lastCurser; curEndPos = lastCurser;
-                            st.markedStart = lastCurser; st.markedChr = chrG;
-                            lastCurser = brk;
-                        }
-                    }
+            if (dense) n_dense++; else n_sparse++;
+            if (dense) {
+                int32_t *CAND = margin + mcap() + 5 * (R + 2);
+                const int32_t nC = tabulate_dense(nM, P_lo, R, ds, de, chrG, in.D[grp.ds].pos, rg, szPC, CAND);
+                SQ_PROF_ADD(4);
+                for (int32_t ic = 0; ic < nC; ic++) {
+                    const int32_t brk = CAND[2 * ic];
+                    if (st.have_back && st.backChr == chrG && brk - st.backEnd < thresh * 20) continue;
+                    accept_break(brk, CAND[2 * ic + 1], chrG, D[ds].pos, bc);
                 }
-                int32_t j = ib;
-                while (j < nM && ms[j] == brk) j++;
-                if (j < nM) ib = j; else break;
+            } else {
+                sort_margins(nM);
+                if (error) return;
+                ms = margin;
+                if (nM <= msearch_cap) {  // the sorted margins are searched twice per window entry: keep them close
+                    for (int32_t i = W::lane(); i < nM; i += W::size()) msearch[i] = margin[i];
+                    W::sync();
+                    ms = msearch;
+                }
+                SQ_PROF_ADD(3);
+                tabulate_breaks(nM, ds, de, chrG, in.D[grp.ds].pos, rg, szPC);
+                SQ_PROF_ADD(4);
+                const int32_t *t_sr = margin + mcap(), *t_pl = margin + 2 * mcap(), *t_pr = margin + 3 * mcap(), *t_cov = margin + 4 * mcap(), *t_rest = margin + 5 * mcap();
+                for (int32_t ib = 0; ib < nM;) {
+                    const int32_t brk = ms[ib];
+                    if (st.have_back && st.backChr == chrG && brk - st.backEnd < thresh * 20) { ib++; continue; }
+                    const int32_t sr = t_sr[ib], pl = t_pl[ib], pr = t_pr[ib];
+                    if (sr > 3 || sr + pl > 4 || sr + pr > 4) {
+                        int32_t coverage = t_cov[ib];
+                        int32_t rest = coverage - sr; if (rest < 0) rest = 0;
+                        if (sr > rest + 2) {
+                            coverage += t_rest[ib];
+                            rest = coverage - sr; if (rest < 0) rest = 0;
+                        }
+                        if (sr > rest + 2) accept_break(brk, sr + (pl > pr ? pl : pr), chrG, D[ds].pos, bc);
+                    }
+                    int32_t j = ib;
+                    while (j < nM && ms[j] == brk) j++;
+                    if (j < nM) ib = j; else break;
+                }
             }
+            int32_t lastCurser = bc.lastCurser;
+            curStartPos = bc.curStartPos; curEndPos = bc.curEndPos; isClusternSplit = bc.isClusternSplit;
             if (lastCurser != -1 && (!isClusternSplit || st.backEnd != lastCurser)) {  // :505-516
                 isClusternSplit = true;
                 if (D[ds].pos - curStartPos > thresh * 20 && lastCurser - D[ds].pos > thresh * 20) {
@@ -945,7 +1205,7 @@ struct SeedMachineT {
             // :529-532
             while (st.offCC < rg && e_chr(st.offCC) < chrG) st.offCC = nextCC(st.offCC + 1, rg);
             while (st.offPC < szPC && e_chr(in.pc_rec[st.offPC]) < chrG) st.offPC++;
-            for (dc = ds; dc != de && D[dc].pos + D[dc].len <= curEndPos; dc++) {}
+            { const int32_t lim = curEndPos; dc = find_first(ds, de, [&](int32_t k) { return !(D[k].pos + D[k].len <= lim); }); }
             // :536-567 walk the windows up to the end of the last inserted segment, tracking the 0-coverage position.
             // Each window gives up its maximal prefix of entries that lie left of the last segment's end and more than
             // ReadLen left of the next discordant block; the two windows do not influence each other here.

@@ -149,6 +149,7 @@ struct IsCutOp {
     __device__ bool operator()(int32_t g) const { return flag[g] != 0; }
 };
 // scratch each island needs: [2i] = op slots, [2i+1] = margin slots
+constexpr int32_t kHeavySpanDev = 1 << 14;  // islands spanning more records than this get a whole block instead of a warp
 __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n_isl, int32_t *cap_ops, int32_t *cap_mar, int32_t *span) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_isl) return;
@@ -157,9 +158,11 @@ __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n
     const int32_t ga = isl_start[i], gb = (i + 1 < n_isl) ? isl_start[i + 1] : in.g_hi;
     const int32_t thresh = kSeedThresh, RL = in.read_len;
     int32_t mmax = 0;
+    int64_t rmax = 0;  // widest position range the margins of one group can span (all lie in [group start - ReadLen, group right + thresh])
     for (int32_t g = ga; g < gb; g++) {
         const Group grp = in.G[g];
         const int32_t s0 = in.D[grp.ds].pos;
+        { const int64_t r = (int64_t)grp.right - s0 + RL + thresh + 2; if (r <= in.dense_max_r && r > rmax) rmax = r; }
         int32_t m = 2 * (grp.de - grp.ds);
         {   // PartAlignPos entries of the group (:392-393)
             int32_t lo = 0, hi = in.nP;
@@ -181,7 +184,6 @@ __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n
     cap_ops[i] = 4 * (in.G[gb - 1].de - in.G[ga].ds) + 2 * mmax + 64;
     int32_t pw = 1;
     while (pw < mmax + 2) pw <<= 1;  // sort_margins pads to a power of two; + the five per-break tables
-    cap_mar[i] = 6 * pw;
     int64_t w0 = r0;  // the windows were emptied at the last 0-coverage record before the island's first group
     if (ga > 0) {
         int32_t cc, cr;
@@ -190,13 +192,22 @@ __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n
         if (z >= 0) w0 = in.gap_rec[z];
     }
     span[i] = (int32_t)((r1 - w0) > 0x7fffffff ? 0x7fffffff : (r1 - w0));  // records the island may have to walk
+    // scratch: six regions of mcap ints (margin list + the five per-break tables) + 8 cells; islands that use position-indexed
+    // tables need 5 (R + 2) + 2 min(nM, R) ints behind the list
+    int64_t mc = pw;
+    if (in.dense_max_r > 0 && (in.dense_all || span[i] > kHeavySpanDev)) {
+        const int64_t r = rmax < 16 * (int64_t)mmax + 4096 ? rmax : 16 * (int64_t)mmax + 4096;
+        const int64_t need = (5 * (r + 2) + 2 * (r < mmax + 2 ? r : (int64_t)mmax + 2) + 2 + 4) / 5 + 1;
+        if (need > mc) mc = need;
+    }
+    cap_mar[i] = (int32_t)(6 * mc + 8);
 }
 __global__ void k_gather_i32(const int32_t *src, const int32_t *idx, int32_t n, int32_t *out) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = src[idx[i]];
 }
 constexpr int kSeedBlock = 512;        // threads per block of the seed kernels
-constexpr int kHeavySpan = 1 << 14;
+constexpr int kHeavySpan = kHeavySpanDev;
 // Islands spanning more records than this would get a thread-block cluster (k_seed_giants).  Measured on the benchmark the
 // cluster policy is correct (GPU tests force it with SQG_GIANT_SPAN) but not yet faster than one 512-thread block: 11 islands of
 // 0.4-0.9 M records took 16 ms in clusters of 8 against 11 ms in single blocks (cluster barriers inside the chunked window
@@ -216,6 +227,7 @@ __device__ __forceinline__ void seed_one_island(const SeedInputs &in, int32_t i,
     sm.out = ops + off_ops[i]; sm.out_cap = (int32_t)(off_ops[i + 1] - off_ops[i]);
     sm.margin = margin + off_mar[i]; sm.margin_cap = (int32_t)(off_mar[i + 1] - off_mar[i]);
     sm.msearch = fast; sm.msearch_cap = fast_cap;
+    sm.use_dense = in.dense_max_r > 0 && (in.dense_all || W::size() > 32);  // block- and cluster-sized islands
 #ifdef SQ_SEED_PROF
     long long t0_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0_));
 #endif
@@ -296,6 +308,9 @@ struct CoopCluster {
     static __device__ __forceinline__ void add(int32_t *p, int32_t v) { atomicAdd(p, v); }
     static __device__ __forceinline__ void add_range(int32_t *diff, int32_t ja, int32_t jb, bool on) { CoopBlock::add_range(diff, ja, jb, on); }
     static __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+    static __device__ __forceinline__ void begin_append(int32_t *cell, int32_t n) { sync(); if (lane() == 0) *cell = n; sync(); }
+    static __device__ __forceinline__ int32_t reserve(bool has, int32_t &n, int32_t *cell) { return CoopBlock::reserve(has, n, cell); }
+    static __device__ __forceinline__ void end_append(int32_t *cell, int32_t &n) { sync(); n = *(volatile int32_t *)cell; sync(); }
 };
 __global__ void __cluster_dims__(kGiantCluster, 1, 1) __launch_bounds__(kSeedBlock, 2)
 k_seed_giants(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar, SeedOp *ops, int32_t *margin, int32_t *n_out,
@@ -636,7 +651,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
-    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
+    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_ccmax.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_chain_used.release(); ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_slow.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
@@ -926,14 +941,14 @@ static int run_classify(sqg_ctx *ctx) {
     ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n; ctx->end_other = 0;
     if (n > 0) {
         const int64_t n_tiles = (n + kTile - 1) / kTile;
-        CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8));
+        CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8)); CK(ctx->d_ccmax.ensure(n_tiles + 1));
         int64_t cand_cap = std::max<int64_t>({(int64_t)ctx->d_cand_key.cap, n / 16, (int64_t)1 << 20});
         int32_t n_cand = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             cand_cap = std::min<int64_t>(cand_cap, n + 1);
             CK(ctx->d_cand_key.ensure(cand_cap));
             P1Out o;
-            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
+            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.ccmax = ctx->d_ccmax.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
             o.cand_rec = ctx->d_scratch32.p; o.cand_key = ctx->d_cand_key.p; o.cand_cap = (int32_t)cand_cap;
             // counters: [0..1] totals n_gap, n_pc, n_dp (int32) | [2] first_kept | [3] lmax | [4] n_cand, ticket (int32) | [20] validation flags
             CK(cudaMemsetAsync(ctx->d_counters.p, 0, 5 * sizeof(int64_t), ctx->stream));
@@ -1294,6 +1309,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     in.b = b; in.cls = ctx->d_cls.p; in.first_len = ctx->d_flen.p; in.gap_other = ctx->d_other.p;
     in.gap_rec = ctx->d_gap.p; in.n_gap = ctx->n_gap; in.pc_rec = ctx->d_pc.p; in.n_pc = ctx->n_pc;
     in.dp_rec = ctx->d_dp.p; in.n_dp = ctx->n_dp; in.lmax = ctx->lmax; in.n_rec = n;
+    in.ccmax = n > 0 ? ctx->d_ccmax.p : nullptr; in.cc_tile = kTile;
     in.D = ctx->d_disc.p; in.nD = nD; in.G = ctx->d_groups.p; in.nG = nG; in.trigger = ctx->d_trigger.p;
     in.Pchr = ctx->d_pchr.p; in.Ppos = ctx->d_ppos.p; in.nP = nP;
     in.rest = ctx->d_rest2.p; in.n_rest = (int32_t)n_rest; in.read_len = ctx->params.read_len; in.first_kept = ctx->first_kept;
@@ -1327,6 +1343,11 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     if (g_hi < g_lo) g_hi = g_lo;
     in.g_hi = g_hi;
     in.g_lo = g_lo; in.has_next = ctx->shard_index + 1 < ctx->shard_count; in.end_other = ctx->end_other;
+    {   // position-indexed break tables (sq_seed.cuh: tabulate_dense): SQG_SEED_DENSE = 0 off, 1 block-sized islands only, 2 every island (default)
+        static const int dense_mode = getenv("SQG_SEED_DENSE") ? atoi(getenv("SQG_SEED_DENSE")) : 2;
+        static const int dense_r = getenv("SQG_SEED_DENSE_R") ? atoi(getenv("SQG_SEED_DENSE_R")) : (1 << 16);
+        in.dense_max_r = dense_mode > 0 ? dense_r : 0; in.dense_all = dense_mode > 1;
+    }
     CK(ctx->d_cutflag.ensure(nG + 1)); CK(ctx->d_isl.ensure(nG + 2));
     LAUNCH(k_island_cuts, blocks_for(nG, 64), 64, in, ctx->d_cutflag.p);
     CK(cudaMemsetAsync(ctx->d_counters.p + 5, 0, sizeof(int64_t), ctx->stream));

@@ -71,6 +71,8 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> cls(n);
     std::vector<uint16_t> first_len(n, 0);
     std::vector<uint64_t> other_excl(n);
+    const int32_t cc_tile = getenv("SQ_EMUL_CC_TILE") ? atoi(getenv("SQ_EMUL_CC_TILE")) : 512;  // 0: no per-tile maxima (plain walks)
+    std::vector<int32_t> ccmax(cc_tile > 0 ? (size_t)((n + cc_tile - 1) / cc_tile) + 1 : 1, kNoCcEnd);
     {
         int64_t prev = -1;
         uint64_t run = 1ull << 32;
@@ -79,6 +81,12 @@ int main(int argc, char **argv) {
             cls[r] = o.cls;
             first_len[r] = (uint16_t)(o.first_len < 65535 ? o.first_len : 65535);
             other_excl[r] = run;
+            if (cc_tile > 0) {
+                int32_t &m = ccmax[(size_t)(r / cc_tile)];
+                const int64_t t0 = r / cc_tile * cc_tile, t1 = std::min<int64_t>(t0 + cc_tile, n) - 1;
+                if (b.ref_id[t0] < 0 || b.ref_id[t0] != b.ref_id[t1]) m = kCcWalkTile;
+                else if (o.cc_end > m) m = o.cc_end;
+            }
             if (o.other_key > run) run = o.other_key;
             if (o.cls & CLS_GATE) prev = r;
         }
@@ -133,9 +141,11 @@ int main(int argc, char **argv) {
     sm.in.Pchr = pre.part_chr.data(); sm.in.Ppos = pre.part_pos.data(); sm.in.nP = (int32_t)pre.part_chr.size();
     sm.in.rest = rest.data(); sm.in.n_rest = (int32_t)rest.size();
     sm.in.read_len = p.read_len;
+    if (cc_tile > 0) { sm.in.ccmax = ccmax.data(); sm.in.cc_tile = cc_tile; }
     sm.in.dp_rec = dprec.data(); sm.in.n_dp = (int32_t)dprec.size(); sm.in.lmax = lmax; sm.in.n_rec = n; sm.in.first_kept = first_kept;
-    std::vector<int32_t> margin(6 * 2 * (4 * (size_t)nD + 2 * pre.part_chr.size() + 2 * pcrec.size() + 64));
+    std::vector<int32_t> margin(6 * 2 * (4 * (size_t)nD + 2 * pre.part_chr.size() + 2 * pcrec.size() + 64) + 8 + (getenv("SQ_EMUL_DENSE") ? 6 * 2 * (size_t)atoi(getenv("SQ_EMUL_DENSE")) : 0));
     sm.margin = margin.data(); sm.margin_cap = (int32_t)margin.size();
+    if (getenv("SQ_EMUL_DENSE")) { sm.use_dense = true; sm.in.dense_max_r = atoi(getenv("SQ_EMUL_DENSE")); }  // position-indexed break tables (heavy islands on the device)
     // islands: cut before group g when the machine provably restarts there
     std::vector<int32_t> isl_start(1, 0);
     const bool one_island = getenv("SQ_EMUL_ONE_ISLAND") != nullptr;
@@ -162,7 +172,7 @@ int main(int argc, char **argv) {
         stitch_ops(ops[i].data(), (int32_t)ops[i].size(), seeds);
         if (gdone[i] < isl_start[i + 1]) { g_done = gdone[i]; break; }
     }
-    fprintf(stderr, "emul: %d groups, %d islands, %zu seeds, lmax %d, %zu displaced\n", nG, nI, seeds.size(), lmax, dprec.size());
+    fprintf(stderr, "emul: %d groups, %d islands, %zu seeds, lmax %d, %zu displaced, sub-clusters dense %d sparse %d\n", nG, nI, seeds.size(), lmax, dprec.size(), sm.n_dense, sm.n_sparse);
     {
         std::vector<int32_t> s;
         for (auto &x : seeds) { s.push_back(x.chr); s.push_back(x.pos); s.push_back(x.len); }

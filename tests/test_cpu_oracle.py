@@ -58,6 +58,9 @@ def test_restatement_matches_reference_on_fuzz(seed, n, disc, ref_len, tmp_path,
 @pytest.mark.parametrize("opts,args", [
     ((1, 25, 10, 3, 50000, 20), ["-mq", "3", "-pl", "25", "-pm", "10"]),
     ((1, 5, 4, -1, 3000, 2), ["-dp", "3000", "-di", "2", "-pl", "5"]),
+    # -pt 0 selects offset 64 (ReadRec.cpp:19-38; the README says the opposite): with -pm 10 the threshold
+    # is 'J', above every synthetic quality, so every read has a low-phred run -- with offset 33 it would be '+'
+    ((0, 10, 10, -1, 50000, 20), ["-pt", "0", "-pm", "10"]),
 ])
 def test_restatement_matches_reference_with_options(opts, args, tmp_path, ref_oracle):
     """The -mq / -pl / -pm / -dp / -di rules (Config.cpp:18-25) on both sides; the options must change the outputs."""

@@ -215,6 +215,8 @@ def test_bam_input_matches_reference(tmp_path, built_lib, ref_oracle):
 @pytest.mark.parametrize("opts,args", [
     (dict(min_mapq=3, max_lowphred_len=25, min_phred=10), ["-mq", "3", "-pl", "25", "-pm", "10"]),
     (dict(concord_dist_pos=3000, concord_dist_idx=2, max_lowphred_len=5), ["-dp", "3000", "-di", "2", "-pl", "5"]),
+    # Phred64 (-pt 0 means offset 64 in the code, ReadRec.cpp:19-38, contrary to the README): threshold 'J' > every quality
+    (dict(phred33=0, min_phred=10), ["-pt", "0", "-pm", "10"]),
 ])
 def test_non_default_parameters(tmp_path, built_lib, ref_oracle, opts, args):
     """-mq / -pl / -pm gate and classify differently, -dp moves the point at which a breakpoint stops being counted
