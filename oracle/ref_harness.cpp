@@ -188,17 +188,25 @@ int main(int argc, char **argv) {
                 dump_bpmap("support_i32.bin", Support);
                 if (write_outputs) {
                     // main.cpp:37-38, 61-62 without the GLPK ordering in between (out of scope, not installed): the component
-                    // ordering is a deterministic stand-in -- the nodes of every connected component in index order, every third
-                    // component reversed, orientations from a hash -- dumped so that the writer twin is fed the very same one.
+                    // ordering is a deterministic stand-in (below), dumped so that the writer twin is fed the very same one.
                     g.OutputGraph(outdir + "/ref_graph.txt");
                     int n_lab = 0;
                     for (size_t i = 0; i < g.Label.size(); i++) n_lab = std::max(n_lab, g.Label[i] + 1);
                     vector<vector<int> > Components(n_lab);
-                    for (size_t i = 0; i < g.vNodes.size(); i++) {
-                        const bool neg = ((uint32_t)((uint32_t)i * 2654435761u) >> 7) & 1u;
-                        Components[g.Label[i]].push_back(neg ? -(int)(i + 1) : (int)(i + 1));
+                    // orientations: every discordant edge, in vEdges order, orients its two nodes the way that makes it consistent
+                    // with index order (WriteIO.cpp:61) unless one of them is already oriented; every third component is then
+                    // reverse-complemented as a whole, which moves its edges to the mirrored test (WriteIO.cpp:63)
+                    std::vector<int> sign(g.vNodes.size(), 0);
+                    for (size_t e = 0; e < g.vEdges.size(); e++) {
+                        const Edge_t &ed = g.vEdges[e];
+                        if (!g.IsDiscordant((int)e) || sign[ed.Ind1] || sign[ed.Ind2] || ed.Ind1 == ed.Ind2) continue;
+                        sign[ed.Ind1] = ed.Head1 ? -1 : 1; sign[ed.Ind2] = ed.Head2 ? 1 : -1;
                     }
-                    for (size_t c = 0; c < Components.size(); c += 3) std::reverse(Components[c].begin(), Components[c].end());
+                    for (size_t i = 0; i < g.vNodes.size(); i++) Components[g.Label[i]].push_back(sign[i] < 0 ? -(int)(i + 1) : (int)(i + 1));
+                    for (size_t c = 0; c < Components.size(); c += 3) {
+                        std::reverse(Components[c].begin(), Components[c].end());
+                        for (size_t j = 0; j < Components[c].size(); j++) Components[c][j] = -Components[c][j];
+                    }
                     {
                         std::vector<int32_t> flat;
                         flat.push_back((int32_t)Components.size());

@@ -27,7 +27,9 @@ BWA_CASES = {
     "bwa_fourchr_6k": dict(n_pairs=6000, seed=11, disc_frac=0.03, ref_len=[3000000, 2000000, 500000, 16569], n_genes=12),
 }
 KEEP = ["nodes_i32.bin", "nodes_f64.bin", "edges_i32.bin", "chim_loaded.bin", "chim_loaded.bin.meta", "chim_after_edges.bin", "final_nodes_i32.bin",
-        "final_edges_i32.bin", "exactbp_i32.bin", "support_i32.bin", "readlen.bin"]
+        "final_edges_i32.bin", "exactbp_i32.bin", "support_i32.bin", "readlen.bin",
+        # --write-outputs: OutputGraph / WriteBEDPE of the reference (under the harness's stand-in ordering) and what they were fed
+        "final_nodes_f64.bin", "labels_i32.bin", "chim_after_exactbp.bin", "components_i32.bin", "edges_before_demultiply_i32.bin", "ref_graph.txt", "ref_sv.txt"]
 
 F1, F2, REV, MREV, PAIRED = 0x40, 0x80, 0x10, 0x20, 0x1
 
@@ -82,7 +84,7 @@ def main():
         kw = dict(kw)
         conc, chim, info = synth.make_case(kw.pop("n_pairs"), **kw)
         sqmb.write_sqmb(d + "/conc.sqmb", conc); sqmb.write_sqmb(d + "/chim.sqmb", chim)
-        pyref.run(d + "/conc.sqmb", d + "/chim.sqmb", d + "/ref")
+        pyref.run(d + "/conc.sqmb", d + "/chim.sqmb", d + "/ref", extra_args=("--write-outputs",))
         for f in os.listdir(d + "/ref"):
             if f not in KEEP:
                 os.remove(os.path.join(d, "ref", f))
