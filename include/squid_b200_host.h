@@ -29,6 +29,10 @@ int sqh_open_case(const char *concordant_sqmb, const char *chimeric_sqmb, const 
  * GetNextAlignment on the path (src/ReadRec.cpp:271-279, 340-343; src/SegmentGraph.cpp:293-296, 1570-1577, 3126-3129).
  * The file is inflated on all cores and decoded once for all three phases. */
 int sqh_open_bam_case(const char *concordant_bam, const char *chimeric_bam, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen);
+/* The concordant file alone (SQMB), for a caller that already holds Chimrecord -- the binding of INTEGRATION.md
+ * (integration/binding.cpp): chim_qnames[n_names] = the Qnames of Chimrecord, from which ChimName is built
+ * (src/SegmentGraph.cpp:196-201).  The chimeric side of the case stays empty and config.read_len 0. */
+int sqh_open_concordant(const char *concordant_sqmb, const char *const *chim_qnames, int64_t n_names, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen);
 void sqh_close_case(sqh_case *c);
 const sqg_batch *sqh_case_batch(const sqh_case *c);
 sqg_chimeric *sqh_case_chimeric(sqh_case *c);

@@ -66,7 +66,7 @@ EXPORTS = [
     "sqg_phase_ms", "sqg_launch_count", "sqg_stat", "sqg_selftest_gpu_sort",
     "sqg_plan_shards", "sqg_set_shard", "sqg_shard_seeds", "sqg_shard_build", "sqg_shard_hint_state", "sqg_shard_redo_edges",
     "sqg_shard_cov_begin", "sqg_shard_cov_chain", "sqg_shard_cov_owned_t", "sqg_shard_cov_count",
-    "sqh_default_options", "sqh_open_case", "sqh_open_bam_case", "sqh_probe_bam", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
+    "sqh_default_options", "sqh_open_case", "sqh_open_concordant", "sqh_open_bam_case", "sqh_probe_bam", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
     "sqh_case_n_ref", "sqh_case_ref_len", "sqh_case_blocks",
     "sqh_exact_breakpoint", "sqh_free", "sqh_write_graph", "sqh_write_bedpe",
 ]

@@ -72,6 +72,34 @@ int sqh_open_case(const char *conc_path, const char *chim_path, const sqh_option
 int sqh_open_bam_case(const char *conc_bam, const char *chim_bam, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen) {
     return open_case(true, conc_bam, chim_bam, opt, out, errbuf, errlen);
 }
+// The concordant BAM alone, for a caller that already holds Chimrecord (the binding of INTEGRATION.md): ChimName is built from
+// the Qnames it passes (SegmentGraph.cpp:196-201), the chimeric side of the case stays empty.
+int sqh_open_concordant(const char *conc_path, const char *const *chim_qnames, int64_t n_names, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen) {
+    auto fail = [&](int code, const std::string &m) { if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", m.c_str()); return code; };
+    if (!conc_path || !out || n_names < 0 || (n_names > 0 && !chim_qnames)) return fail(SQG_EINVAL, "null argument");
+    *out = nullptr;
+    sqh_case *c = new (std::nothrow) sqh_case();
+    if (!c) return fail(SQG_ENOMEM, "out of memory");
+    sqh_options o;
+    if (opt) o = *opt; else sqh_default_options(&o);
+    c->cfg.phred33 = o.phred33 != 0; c->cfg.max_lowphred_len = o.max_lowphred_len; c->cfg.min_phred = o.min_phred;
+    c->cfg.min_mapq = o.min_mapq < 0 ? 255 : o.min_mapq; c->cfg.concord_dist_pos = o.concord_dist_pos; c->cfg.concord_dist_idx = o.concord_dist_idx;
+    if (!c->conc.open(conc_path)) { delete c; return fail(SQG_EINVAL, std::string("cannot open ") + conc_path); }
+    c->ref_len.assign(c->conc.ref_len, c->conc.ref_len + c->conc.n_ref);
+    std::unordered_set<std::string> names;
+    names.insert("");  // ChimName is pre-sized with empty strings before the names are appended (SegmentGraph.cpp:196-198)
+    for (int64_t i = 0; i < n_names; i++) names.insert(chim_qnames[i] ? chim_qnames[i] : "");
+    std::string err;
+    const int rc = sqh::pack_concordant(sqh::source_of(c->conc), c->cfg, names, c->batch, err);
+    if (rc) { delete c; return fail(rc, err); }
+    c->pchim.from_reads(c->reads);
+    c->bview = c->batch.view();
+    c->cview = c->pchim.view();
+    c->gcfg.using_star = 1; c->gcfg.max_lowphred_len = c->cfg.max_lowphred_len; c->gcfg.min_mapq = c->cfg.min_mapq;
+    c->gcfg.concord_dist_pos = c->cfg.concord_dist_pos; c->gcfg.concord_dist_idx = c->cfg.concord_dist_idx; c->gcfg.read_len = 0;
+    *out = c;
+    return SQG_OK;
+}
 void sqh_close_case(sqh_case *c) { delete c; }
 const sqg_batch *sqh_case_batch(const sqh_case *c) { return c ? &c->bview : nullptr; }
 sqg_chimeric *sqh_case_chimeric(sqh_case *c) { return c ? &c->cview : nullptr; }
