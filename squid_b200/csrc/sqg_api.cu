@@ -107,31 +107,56 @@ __global__ void k_triggers(DevBatch b, const uint8_t *cls, const Group *G, int32
 }
 
 // ConcordRest candidates: non-first blocks of concordant records that start inside
-// [group start - ReadLen, group right + ReadLen) of some discordant group (:690-699, :387, :471-473)
-__global__ void k_rest_collect(DevBatch b, const uint8_t *cls, const Group *G, const DiscBlock *D, int32_t nG, int32_t read_len,
+// [group start - ReadLen, group right + ReadLen) of some discordant group (:690-699, :387, :471-473).
+// The groups cover a tiny part of the genome, so a bitmap over 1024-bp bins (bit set = some group's extended range touches the
+// bin) rejects almost every block with one cached load; only the survivors search the group list.
+constexpr int kRestBinShift = 10;
+struct RestBins { const uint32_t *bits; const int32_t *off; };   // off[c] = first bin of chromosome c (n_ref + 1 entries)
+__global__ void k_rest_mark(const Group *G, const DiscBlock *D, int32_t nG, int32_t read_len, const int32_t *ref_len, uint32_t *bits, const int32_t *off) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nG) return;
+    const Group grp = G[g];
+    int32_t a = D[grp.ds].pos - read_len, b = grp.right + read_len - 1;  // positions [a, b]
+    if (a < 0) a = 0;
+    const int32_t last = ref_len[grp.chr] > 0 ? ref_len[grp.chr] : 0;
+    if (b > last) b = last;
+    for (int32_t k = a >> kRestBinShift; k <= (b >> kRestBinShift); k++) { const int32_t bin = off[grp.chr] + k; atomicOr(&bits[bin >> 5], 1u << (bin & 31)); }
+}
+__global__ void k_rest_collect(DevBatch b, const uint8_t *cls, const Group *G, const DiscBlock *D, int32_t nG, int32_t read_len, RestBins rb, const int32_t *ref_len,
                                RestBlock *out, uint64_t *out_key, int64_t cap, int64_t *counter) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= b.n_rec) return;
-    if (!(cls[r] & CLS_REST)) return;  // CLS_CONC, a mate flag, >= 2 blocks
-    const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
-    const int32_t c = b.ref_id[r];
-    for (uint32_t k = o + 1; k < e; k++) {
-        const int32_t q = b.blk_ref_pos[k];
-        int32_t lo = 0, hi = nG;  // last group with (chr, start - RL) <= (c, q)
-        while (lo < hi) {
-            const int32_t m = (lo + hi) >> 1;
-            const Group g = G[m];
-            const int32_t s = D[g.ds].pos - read_len;
-            if (g.chr < c || (g.chr == c && s <= q)) lo = m + 1; else hi = m;
-        }
-        const int32_t gi = lo - 1;
-        if (gi < 0) continue;
-        const Group g = G[gi];
-        if (g.chr != c || q >= g.right + read_len) continue;
-        const int64_t slot = (int64_t)atomicAdd((unsigned long long *)counter, 1ull);
-        if (slot < cap) {
-            out[slot] = RestBlock{c, q, q + b.blk_match_ref[k], (int32_t)r};
-            out_key[slot] = ((uint64_t)(uint32_t)c << 32) | (uint32_t)q;
+    const int64_t r0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;  // four records per thread: one 32-bit load of their class bytes
+    if (r0 >= b.n_rec) return;
+    uint32_t w = 0;
+    if (r0 + 3 < b.n_rec) w = *reinterpret_cast<const uint32_t *>(cls + r0);
+    else for (int k = 0; k < 4; k++) if (r0 + k < b.n_rec) w |= (uint32_t)cls[r0 + k] << (8 * k);
+    if (!(w & (0x01010101u * CLS_REST))) return;
+    for (int j = 0; j < 4; j++) {
+        if (!((w >> (8 * j)) & CLS_REST)) continue;  // CLS_CONC, a mate flag, >= 2 blocks
+        const int64_t r = r0 + j;
+        const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
+        const int32_t c = b.ref_id[r];
+        const int32_t last = ref_len[c] > 0 ? ref_len[c] : 0;
+        for (uint32_t k = o + 1; k < e; k++) {
+            const int32_t q = b.blk_ref_pos[k];
+            if (q < 0 || q > last) continue;  // (cannot lie in any group's range, which is clipped to the chromosome)
+            const int32_t bin = rb.off[c] + (q >> kRestBinShift);
+            if (!((rb.bits[bin >> 5] >> (bin & 31)) & 1u)) continue;
+            int32_t lo = 0, hi = nG;  // last group with (chr, start - RL) <= (c, q)
+            while (lo < hi) {
+                const int32_t m = (lo + hi) >> 1;
+                const Group g = G[m];
+                const int32_t s = D[g.ds].pos - read_len;
+                if (g.chr < c || (g.chr == c && s <= q)) lo = m + 1; else hi = m;
+            }
+            const int32_t gi = lo - 1;
+            if (gi < 0) continue;
+            const Group g = G[gi];
+            if (g.chr != c || q >= g.right + read_len) continue;
+            const int64_t slot = (int64_t)atomicAdd((unsigned long long *)counter, 1ull);
+            if (slot < cap) {
+                out[slot] = RestBlock{c, q, q + b.blk_match_ref[k], (int32_t)r};
+                out_key[slot] = ((uint64_t)(uint32_t)c << 32) | (uint32_t)q;
+            }
         }
     }
 }
@@ -320,6 +345,45 @@ k_seed_giants(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int6
     seed_one_island<CoopCluster>(in, giant[gi], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr, nullptr, 0);
 }
 
+// The op lists of the islands, concatenated in island order WITHOUT their unused capacity (the scratch of an island is sized for
+// the worst case: two ops per margin).  One block: islands up to the first one that the stream ended in the middle of
+// (g_done < start of the next island; nothing later is ever processed), an exclusive scan of their op counts, the copies.
+// out_meta[0] = number of ops, out_meta[1] = first group that was not processed.
+__global__ void __launch_bounds__(1024) k_ops_dense(const int32_t *isl_start, int32_t n_isl, int32_t g_hi, const int32_t *n_out, const int32_t *g_done, const int64_t *off_ops,
+                                                    const SeedOp *ops, SeedOp *dense, int64_t *out_meta) {
+    __shared__ int32_t s_first_bad, s_warp[32], s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_first_bad = n_isl; s_carry = 0; }
+    __syncthreads();
+    int32_t fb = n_isl;
+    for (int32_t i = tid; i < n_isl; i += 1024) {
+        const int32_t nxt = i + 1 < n_isl ? isl_start[i + 1] : g_hi;
+        if (g_done[i] < nxt && i < fb) fb = i;
+    }
+    fb = __reduce_min_sync(0xffffffffu, fb);
+    if (lane == 0 && fb < n_isl) atomicMin(&s_first_bad, fb);
+    __syncthreads();
+    const int32_t first_bad = s_first_bad;
+    const int32_t n_use = first_bad < n_isl ? first_bad + 1 : n_isl;  // the island that stopped early still contributes its ops
+    for (int32_t base = 0; base < n_use; base += 1024) {
+        const int32_t i = base + tid;
+        const int32_t c = i < n_use ? n_out[i] : 0;
+        int32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int32_t wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += s_warp[w];
+        const int32_t at = s_carry + wbase + inc - c;
+        if (i < n_use) { const SeedOp *src = ops + off_ops[i]; for (int32_t k = 0; k < c; k++) dense[at + k] = src[k]; }
+        __syncthreads();
+        if (tid == 1023) s_carry = at + c;
+        __syncthreads();
+    }
+    if (tid == 0) { out_meta[0] = s_carry; out_meta[1] = first_bad < n_isl ? g_done[first_bad] : g_hi; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernels: segment table index
 // ------------------------------------------------------------------------------------------------
@@ -439,6 +503,16 @@ __global__ void k_fix_chains(DevBatch b, ChimDev c, Params p, NodeTable nt, int3
             q = q2;
         }
     }
+}
+// blocks of the chimeric reads that LocateRead trimmed (:1229-1248): (index, RefPos, ReadPos, MatchRef, MatchRead) rows -- a few
+// thousand of a million, so the caller's arrays are patched on the host instead of copying four whole arrays back
+__global__ void k_chim_diff(const int32_t *p0, const int32_t *r0, const int32_t *m0, const int32_t *q0, const int32_t *p1, const int32_t *r1, const int32_t *m1, const int32_t *q1,
+                            int64_t n, int32_t *rows5, int32_t cap, int32_t *count) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (p0[k] == p1[k] && r0[k] == r1[k] && m0[k] == m1[k] && q0[k] == q1[k]) return;
+    const int32_t at = atomicAdd(count, 1);
+    if (at < cap) { int32_t *row = rows5 + 5 * (int64_t)at; row[0] = (int32_t)k; row[1] = p1[k]; row[2] = r1[k]; row[3] = m1[k]; row[4] = q1[k]; }
 }
 __global__ void k_unpack_edges(const uint64_t *keys, const int32_t *counts, int64_t n, int32_t *ind1, int32_t *ind2, uint8_t *heads, int32_t *w) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -648,7 +722,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->dc_match_ref.release(); ctx->dc_match_read.release(); ctx->dc_res0.release(); ctx->dc_rev.release();
     ctx->dc0_ref_pos.release(); ctx->dc0_read_pos.release(); ctx->dc0_match_ref.release(); ctx->dc0_match_read.release();
     ctx->d_trigger.release(); ctx->d_rest.release(); ctx->d_rest2.release(); ctx->d_restkey.release(); ctx->d_restkey2.release();
-    ctx->d_ops.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
+    ctx->d_chimdiff.release(); ctx->h_chimdiff.release(); ctx->d_restbits.release(); ctx->d_restoff.release(); ctx->d_reflen.release(); ctx->d_ops.release(); ctx->d_ops_dense.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_ccmax.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
@@ -829,6 +903,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     // stream copies and classifies the concordant batch; it is joined in sqg_build_nodes / sqg_build_edges.
     ctx->prepass_worker.wait();
     ctx->chim_view = *c;
+    ctx->chim_undo.clear();  // fresh arrays: nothing of an earlier patch applies
     ctx->prepass_uploaded = false;
     ctx->c_n_reads = c->n_reads; ctx->c_n_blk = c->n_blk;
     const size_t nr = (size_t)c->n_reads, nb = (size_t)c->n_blk;
@@ -1282,12 +1357,25 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     CK(ctx->d_trigger.ensure(nG + 1));
     LAUNCH(k_triggers, blocks_for(nG), kThreads, b, ctx->d_cls.p, ctx->d_groups.p, nG, ctx->d_trigger.p);
     // ConcordRest candidates, sorted by (chr,pos)
+    RestBins rbins;
+    {   // bitmap of the 1024-bp bins that some group's extended range touches
+        const int32_t n_ref = ctx->params.n_ref;
+        std::vector<int32_t> off((size_t)n_ref + 1, 0);
+        for (int32_t c = 0; c < n_ref; c++) off[c + 1] = off[c] + ((ctx->ref_len[c] > 0 ? ctx->ref_len[c] : 0) >> kRestBinShift) + 1;
+        const size_t words = ((size_t)off[n_ref] + 31) / 32 + 1;
+        CK(ctx->d_restbits.ensure(words)); CK(ctx->d_restoff.ensure((size_t)n_ref + 1)); CK(ctx->d_reflen.ensure((size_t)n_ref + 1));
+        CK(cudaMemsetAsync(ctx->d_restbits.p, 0, words * 4, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_restoff.p, off.data(), ((size_t)n_ref + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));  // (pageable source: staged before the call returns)
+        CK(cudaMemcpyAsync(ctx->d_reflen.p, ctx->ref_len.data(), (size_t)n_ref * 4, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_rest_mark, blocks_for(nG), kThreads, ctx->d_groups.p, ctx->d_disc.p, nG, ctx->params.read_len, ctx->d_reflen.p, ctx->d_restbits.p, ctx->d_restoff.p);
+        rbins.bits = ctx->d_restbits.p; rbins.off = ctx->d_restoff.p;
+    }
     int64_t rest_cap = std::max<int64_t>(1024, ctx->d_rest.cap);
     int64_t n_rest = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         CK(ctx->d_rest.ensure(rest_cap)); CK(ctx->d_rest2.ensure(rest_cap)); CK(ctx->d_restkey.ensure(rest_cap)); CK(ctx->d_restkey2.ensure(rest_cap));
         CK(cudaMemsetAsync(ctx->d_counters.p + 4, 0, sizeof(int64_t), ctx->stream));
-        if (n > 0) LAUNCH(k_rest_collect, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->d_groups.p, ctx->d_disc.p, nG, ctx->params.read_len,
+        if (n > 0) LAUNCH(k_rest_collect, blocks_for((n + 3) / 4), kThreads, b, ctx->d_cls.p, ctx->d_groups.p, ctx->d_disc.p, nG, ctx->params.read_len, rbins, ctx->d_reflen.p,
                           ctx->d_rest.p, ctx->d_restkey.p, rest_cap, ctx->d_counters.p + 4);
         CK(cudaMemcpyAsync(ctx->h_counters.p + 4, ctx->d_counters.p + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1460,30 +1548,25 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
         cudaFree(d_prof);
     }
 #endif
-    // this batch's op lists in island order (host: a few hundred thousand ops at most)
-    std::vector<int32_t> h_nout(n_isl + 1), h_gdone(n_isl + 1), h_isl(n_isl + 1);
-    std::vector<int64_t> h_off(n_isl + 1);
-    if (n_isl > 0) {
-        CK(cudaMemcpyAsync(h_nout.data(), ctx->d_isl_nout.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h_gdone.data(), ctx->d_isl_gdone.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h_isl.data(), ctx->d_isl.p, n_isl * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CK(cudaMemcpyAsync(h_off.data(), ctx->d_off_ops.p, (n_isl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // this batch's op lists in island order: compacted on the device (the islands' scratch is sized for the worst case, two ops
+    // per margin -- copying that capacity cost more than the whole tiling stage), then one small copy
+    CK(ctx->d_ops_dense.ensure((size_t)(tot[0] > 0 ? tot[0] : 1)));
+    LAUNCH(k_ops_dense, 1, 1024, ctx->d_isl.p, n_isl, g_hi, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, ctx->d_off_ops.p, ctx->d_ops.p, ctx->d_ops_dense.p, ctx->d_counters.p + 24);
+    CK(cudaMemcpyAsync(ctx->h_counters.p + 24, ctx->d_counters.p + 24, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters.p + 6, ctx->d_counters.p + 6, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<int64_t> trig_last(1, n);
     if (nG > 0) CK(cudaMemcpyAsync(trig_last.data(), ctx->d_trigger.p + (nG - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx->h_ops.ensure(tot[0] + 1));
-    if (tot[0] > 0) CK(cudaMemcpyAsync(ctx->h_ops.p, ctx->d_ops.p, tot[0] * sizeof(SeedOp), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int32_t serr = *(int32_t *)(ctx->h_counters.p + 7);
     if (serr) FAIL(SQG_ENOMEM, serr == 1 ? "seed machine: margin scratch overflow" : "seed machine: output overflow");
-    h_isl[n_isl] = g_hi;
-    ctx->shard_ops.clear();
-    int32_t g_done = g_hi;  // (== nG exactly when every group was triggered by this batch)
-    for (int32_t i = 0; i < n_isl; i++) {
-        ctx->shard_ops.insert(ctx->shard_ops.end(), ctx->h_ops.p + h_off[i], ctx->h_ops.p + h_off[i] + h_nout[i]);
-        if (h_gdone[i] < h_isl[i + 1]) { g_done = h_gdone[i]; break; }  // the stream ended before this group: nothing later is ever processed
+    const int64_t n_ops_dense = ctx->h_counters.p[24];
+    const int32_t g_done = (int32_t)ctx->h_counters.p[25];  // (== nG exactly when every group was triggered by this batch)
+    CK(ctx->h_ops.ensure((size_t)n_ops_dense + 1));
+    if (n_ops_dense > 0) {
+        CK(cudaMemcpyAsync(ctx->h_ops.p, ctx->d_ops_dense.p, (size_t)n_ops_dense * sizeof(SeedOp), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
     }
+    ctx->shard_ops.assign(ctx->h_ops.p, ctx->h_ops.p + n_ops_dense);
     ctx->shard_g_done = g_done;
     ctx->shard_trig_last = trig_last[0];
     ctx->n_islands = n_isl;
@@ -1658,12 +1741,39 @@ extern "C" int sqg_build_edges(sqg_ctx *ctx, int32_t **ind1, int32_t **ind2, uin
         rc = run_assign(ctx, false, true);
         if (rc) return rc;
     }
-    if (chim_inout && ctx->c_n_blk > 0) {  // LocateRead trimmed Chimrecord in place (:1229-1248)
-        const size_t nb = (size_t)ctx->c_n_blk;
-        CK(cudaMemcpyAsync(chim_inout->blk_ref_pos, ctx->dc_ref_pos.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(chim_inout->blk_read_pos, ctx->dc_read_pos.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(chim_inout->blk_match_ref, ctx->dc_match_ref.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(chim_inout->blk_match_read, ctx->dc_match_read.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (chim_inout && ctx->c_n_blk > 0) {  // LocateRead trimmed Chimrecord in place (:1229-1248): patch the caller's arrays
+        const int64_t nb = ctx->c_n_blk;
+        // an earlier call on this context may have patched the same arrays for another segment table: back to the loaded values
+        for (const sqg_ctx::ChimPatch &u : ctx->chim_undo) {
+            chim_inout->blk_ref_pos[u.k] = u.v[0]; chim_inout->blk_read_pos[u.k] = u.v[1]; chim_inout->blk_match_ref[u.k] = u.v[2]; chim_inout->blk_match_read[u.k] = u.v[3];
+        }
+        ctx->chim_undo.clear();
+        int64_t cap = std::max<int64_t>((int64_t)ctx->d_chimdiff.cap / 5, 4096);
+        for (int attempt = 0; attempt < 2; attempt++) {
+            CK(ctx->d_chimdiff.ensure((size_t)cap * 5));
+            CK(cudaMemsetAsync(ctx->d_counters.p + 26, 0, sizeof(int64_t), ctx->stream));
+            LAUNCH(k_chim_diff, blocks_for(nb), kThreads, ctx->dc0_ref_pos.p, ctx->dc0_read_pos.p, ctx->dc0_match_ref.p, ctx->dc0_match_read.p,
+                   ctx->dc_ref_pos.p, ctx->dc_read_pos.p, ctx->dc_match_ref.p, ctx->dc_match_read.p, nb, ctx->d_chimdiff.p, (int32_t)std::min<int64_t>(cap, 0x7fffffff), (int32_t *)(ctx->d_counters.p + 26));
+            CK(cudaMemcpyAsync(ctx->h_counters.p + 26, ctx->d_counters.p + 26, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const int64_t nd = *(int32_t *)(ctx->h_counters.p + 26);
+            if (nd <= cap) {
+                CK(ctx->h_chimdiff.ensure((size_t)nd * 5 + 1));
+                if (nd > 0) {
+                    CK(cudaMemcpyAsync(ctx->h_chimdiff.p, ctx->d_chimdiff.p, (size_t)nd * 5 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                }
+                ctx->chim_undo.reserve((size_t)nd);
+                for (int64_t i = 0; i < nd; i++) {
+                    const int32_t *row = ctx->h_chimdiff.p + 5 * i;
+                    const int32_t k = row[0];
+                    ctx->chim_undo.push_back(sqg_ctx::ChimPatch{k, {chim_inout->blk_ref_pos[k], chim_inout->blk_read_pos[k], chim_inout->blk_match_ref[k], chim_inout->blk_match_read[k]}});
+                    chim_inout->blk_ref_pos[k] = row[1]; chim_inout->blk_read_pos[k] = row[2]; chim_inout->blk_match_ref[k] = row[3]; chim_inout->blk_match_read[k] = row[4];
+                }
+                break;
+            }
+            cap = nd + 16;
+        }
     }
     return export_edges(ctx, ind1, ind2, heads, weight, n_edges);
 }

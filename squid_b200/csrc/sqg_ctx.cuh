@@ -177,7 +177,12 @@ struct sqg_ctx {
     sq::DBuf<int64_t> d_trigger;
     sq::DBuf<sq::RestBlock> d_rest, d_rest2;
     sq::DBuf<uint64_t> d_restkey, d_restkey2;
+    sq::DBuf<int32_t> d_chimdiff; sq::HBuf<int32_t> h_chimdiff;  // rows (block, RefPos, ReadPos, MatchRef, MatchRead) of the trimmed chimeric blocks
+    struct ChimPatch { int32_t k; int32_t v[4]; };
+    std::vector<ChimPatch> chim_undo;  // loaded values of the blocks the last sqg_build_edges patched in the caller's arrays
+    sq::DBuf<uint32_t> d_restbits; sq::DBuf<int32_t> d_restoff, d_reflen;  // bitmap of the 1024-bp bins near discordant groups (k_rest_collect)
     sq::DBuf<sq::SeedOp> d_ops;
+    sq::DBuf<sq::SeedOp> d_ops_dense;  // the islands' op lists without their unused capacity, island order
     sq::HBuf<sq::SeedOp> h_ops;
     sq::DBuf<uint8_t> d_cutflag;
     sq::DBuf<int32_t> d_isl, d_cap_ops, d_cap_mar, d_isl_nout, d_isl_gdone, d_span, d_heavy, d_light;
