@@ -173,6 +173,7 @@ void sort_like_std(SortKey *first, SortKey *last, int threads) {
     }
 }
 }  // namespace
+void sort_keys_like_std(SortKey *first, SortKey *last, int threads) { sort_like_std(first, last, threads); }
 
 // test hook: does sort_like_std reproduce std::sort's permutation (payload included) on n keys drawn from [0,range)?
 extern "C" int sqh_selftest_sort(int64_t n, uint64_t seed, uint64_t range, int pattern, int fanout) {

@@ -25,6 +25,8 @@ struct SortKey { uint64_t key; uint32_t k; };
 // them (the keys themselves may stay where they were: nothing reads them afterwards) and return true, or return false with `a`
 // untouched (the CPU twin then sorts).
 typedef std::function<bool(SortKey *a, size_t n)> SortHook;
+// std::sort's permutation (libstdc++ introsort + final insertion sort, comparison on `key` only) on `threads` threads
+void sort_keys_like_std(SortKey *first, SortKey *last, int threads);
 // `c` = chimeric reads as passed over the C ABI.
 void chimeric_prepass(const sqg_chimeric &c, int32_t n_ref, int32_t read_len, ChimPrepass &out, const SortHook &sort_hook = SortHook());
 }  // namespace sqh

@@ -64,6 +64,8 @@ struct P2Args {
     const BatchDesc *desc; const NodeTable *nt_dev;  // device copies for the out-of-line generic path
     unsigned long long *path_counts;  // [0] records through read_edges_single, [1] through the generic read_edges (statistics)
     int32_t *slow_list; int32_t *n_slow; int32_t slow_cap;  // records left to k_edges_generic
+    // ReadsOther blocks of <= 3 bp (sq_depth_cover.cuh): per-segment start masks, the deferred short blocks (chr, start, len, node)
+    uint32_t *omask; int4 *shorts; int32_t *n_short; int32_t short_cap;
 };
 
 constexpr uint32_t kP2Fields = F_REF | F_MREF | F_MPOS | F_FLAG | F_TLEN | F_LOWQ | F_CLS | F_BLOCKS;
@@ -95,6 +97,20 @@ __device__ __noinline__ int32_t conc_edges_generic(const BatchDesc *desc, const 
     conc_load_read(b, r, rv, is_first);
     if (rv.nF + rv.nS == 0) return -2;
     return read_edges(nt, p, rv, MODE_OTHER, is_first, false, 0, node, *edges) ? node[0] : -3;
+}
+
+// ReadsOther, the two rare cases (sq_depth_cover.cuh): an entry that starts d <= 2 bp right of the start of its segment m2 goes
+// into that segment's start mask; a block of <= 3 bp is not counted here but deferred to the second pass.  Out of line.
+__device__ __noinline__ bool depth_other_rare(uint32_t *omask, int4 *shorts, int32_t *n_short, int32_t short_cap, int32_t rid, int32_t st, int32_t l, int32_t m2, int32_t d, bool on) {
+    if (l > kSeedThresh) {
+        // (every read spliced into an exon that opens a segment lands here with the same bit: look before the atomic)
+        if (m2 != kNoNode && !(__ldcg(&omask[m2]) & (1u << d))) atomicOr(&omask[m2], 1u << d);
+        return on;
+    }
+    if (m2 != kNoNode && (uint32_t)d <= 2u) { const uint32_t bit = 1u << (3 + 3 * d + ((l < 1 ? 1 : l) - 1)); if (!(__ldcg(&omask[m2]) & bit)) atomicOr(&omask[m2], bit); }
+    const int32_t q = atomicAdd(n_short, 1);
+    if (q < short_cap) shorts[q] = make_int4(rid, st, l, kNoNode);
+    return false;
 }
 
 template <bool DO_DEPTH, bool DO_EDGES>
@@ -173,8 +189,15 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
                 if (counted && k < nb) {
                     const int32_t st = staged ? tb.blk_ref_pos[o0 + k] : b.blk_ref_pos[o0 + k];
                     l = staged ? tb.blk_match_ref[o0 + k] : b.blk_match_ref[o0 + k];
-                    if (rid == wc && wq <= st && st < we && l > kSeedThresh) { m2 = ws; on = st + l <= we + kSeedThresh; }
-                    else { m2 = depth_target(nt, rid, st, l); on = m2 != kNoNode && depth_contained(nt, m2, rid, st, l); }
+                    int32_t pj;
+                    if (rid == wc && wq <= st && st < we) { m2 = ws; pj = wq; on = st + l <= we + kSeedThresh; }  // the tile's segment
+                    else {
+                        m2 = depth_target(nt, rid, st, kSeedThresh + 1);  // first segment ending right of the start
+                        pj = st - 100;
+                        if (m2 != kNoNode) { pj = nt.pos[m2]; on = nt.chr[m2] == rid && st >= pj - kSeedThresh && st + l <= nt.end[m2] + kSeedThresh; }
+                    }
+                    // rare: a block of <= 3 bp (deferred), or one that starts within 2 bp of its segment's start (start mask)
+                    if (l <= kSeedThresh || (uint32_t)(st - pj) <= 2u) on = depth_other_rare(a.omask, a.shorts, a.n_short, a.short_cap, rid, st, l, m2, st - pj, on);
                 }
                 depth_add(m2, l, on, base, s_dcnt[1], s_dsum[1], a.cnt_other, a.sum_other);
             }
@@ -374,6 +397,53 @@ __global__ void __launch_bounds__(128) k_edges_generic(P2Args a) {
         for (int h = tid; h < kEdgeSlots; h += 128)
             if (s_edges.cnt[h]) { if (at < a.sink.cap) { a.sink.keys[at] = (uint64_t)s_edges.keys[h]; a.sink.w[at] = s_edges.cnt[h]; } at++; }
     }
+}
+
+// ReadsOther blocks of <= 3 bp, second pass: the segment each one is counted in (depth_short_node), and how many of them tie
+// with an entry of the same (chr, start) that would move them (then the reference's answer is its unstable sort's tie order)
+__global__ void k_depth_short_nodes(NodeTable nt, const uint32_t *omask, int4 *shorts, const int32_t *n_short, int32_t cap, int32_t *n_unstable) {
+    const int32_t n = *n_short < cap ? *n_short : cap;
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        int4 x = shorts[q];
+        bool un = false;
+        x.w = depth_short_node(nt, omask, x.x, x.y, x.z, &un);
+        shorts[q] = x;
+        if (un) atomicAdd(n_unstable, 1);
+    }
+}
+__global__ void k_depth_short_apply(const int4 *shorts, int32_t n, int32_t *cnt_other, int32_t *sum_other) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int4 x = shorts[q];
+        if (x.w != kNoNode) { atomicAdd(&cnt_other[x.w], 1); atomicAdd(&sum_other[x.w], x.z); }
+    }
+}
+// ---- the tie order of sort(ReadsOther) (:781), only when some short block depends on it ----------------------------------
+// ReadsOther in push order: the non-first blocks of the records that feed the depth streams, keyed by (chr, start).
+struct OtherCountOp {
+    const uint32_t *blk_off; const uint8_t *cls; int64_t r_break;
+    __device__ int32_t operator()(int64_t r) const { if (r >= r_break || !(cls[r] & CLS_HASBLK)) return 0; const uint32_t nb = blk_off[r + 1] - blk_off[r]; return nb > 1 ? (int32_t)(nb - 1) : 0; }
+};
+__global__ void k_other_fill(DevBatch b, const uint8_t *cls, int64_t r_break, const int32_t *off, uint64_t *keys, uint32_t *idx, int32_t *len) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= b.n_rec || r >= r_break || !(cls[r] & CLS_HASBLK)) return;
+    const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
+    int32_t at = off[r];
+    const uint64_t c = (uint64_t)(uint32_t)b.ref_id[r] << 32;
+    for (uint32_t k = o + 1; k < e; k++, at++) { keys[at] = c | (uint32_t)b.blk_ref_pos[k]; idx[at] = (uint32_t)at; len[at] = b.blk_match_ref[k]; }
+}
+// own segment of every entry, in sorted order (long: first segment ending right of the start; short: earliest containing one)
+__global__ void k_other_own(NodeTable nt, const uint64_t *keys, const uint32_t *idx, const int32_t *len, int64_t m, int32_t *own) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < m) own[p] = depth_target(nt, (int32_t)(keys[p] >> 32), (int32_t)(uint32_t)keys[p], len[idx[p]]);
+}
+// the merge loop's cursor at entry p = running maximum of the own segments up to and including p: short entries are counted there
+__global__ void k_other_apply(NodeTable nt, const uint64_t *keys, const uint32_t *idx, const int32_t *len, const int32_t *cursor, int64_t m, int32_t *cnt_other, int32_t *sum_other) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const int32_t l = len[idx[p]];
+    if (l > kSeedThresh) return;
+    const int32_t c = cursor[p];
+    if (c != kNoNode && c < nt.n && depth_contained(nt, c, (int32_t)(keys[p] >> 32), (int32_t)(uint32_t)keys[p], l)) { atomicAdd(&cnt_other[c], 1); atomicAdd(&sum_other[c], l); }
 }
 
 // exclusive running maximum of the per-tile maximum targets (one block of 32 warps, each walking a contiguous run of tiles

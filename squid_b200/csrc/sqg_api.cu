@@ -722,7 +722,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->dc_match_ref.release(); ctx->dc_match_read.release(); ctx->dc_res0.release(); ctx->dc_rev.release();
     ctx->dc0_ref_pos.release(); ctx->dc0_read_pos.release(); ctx->dc0_match_ref.release(); ctx->dc0_match_read.release();
     ctx->d_trigger.release(); ctx->d_rest.release(); ctx->d_rest2.release(); ctx->d_restkey.release(); ctx->d_restkey2.release();
-    ctx->d_chimdiff.release(); ctx->h_chimdiff.release(); ctx->d_restbits.release(); ctx->d_restoff.release(); ctx->d_reflen.release(); ctx->d_ops.release(); ctx->d_ops_dense.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
+    ctx->d_omask.release(); ctx->d_shorts.release(); ctx->d_other_off.release(); ctx->d_other_key.release(); ctx->d_other_idx.release(); ctx->d_other_len.release(); ctx->d_other_own.release(); ctx->d_chimdiff.release(); ctx->h_chimdiff.release(); ctx->d_restbits.release(); ctx->d_restoff.release(); ctx->d_reflen.release(); ctx->d_ops.release(); ctx->d_ops_dense.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
     ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_ccmax.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
@@ -777,6 +777,9 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     if (n == "sensitive_reads") return ctx->n_sensitive;
     if (n == "raw_edges") return ctx->n_raw_edges;
     if (n == "r_break") return ctx->r_break;
+    if (n == "short_other_blocks") return ctx->n_short_other;        // ReadsOther blocks of <= 3 bp in the last depth pass
+    if (n == "unstable_depth_blocks") return ctx->n_unstable_other;  // ... whose segment depends on the tie order of sort(ReadsOther): resolved by replaying that sort
+    if (n == "other_sort_status") return ctx->other_sort_status;
     if (n == "edges_single_path") return ctx->h_counters.p ? ctx->h_counters.p[16] : -1;
     if (n == "edges_generic_path") return ctx->h_counters.p ? ctx->h_counters.p[17] : -1;
     return -1;
@@ -1201,6 +1204,67 @@ static int run_cov_compact(sqg_ctx *ctx) {
 
 static int reduce_edges(sqg_ctx *ctx, int64_t n_raw, const int32_t *d_weights_in);
 
+// ReadsOther blocks of <= 3 bp (sq_depth_cover.cuh).  Their segments are known from the start masks unless some of them tie with
+// an entry of the same (chr, start) that would move them: the reference's answer is then the order in which its unstable
+// std::sort leaves ReadsOther (SegmentGraph.cpp:781), so the sort is replayed -- std::sort's exact permutation, on the device
+// (sq_gpusort.cuh), on the CPU twin if the device declines -- and the merge loop's cursor walked as a running maximum.
+static int count_short_other(sqg_ctx *ctx, int64_t n_short, int64_t n_unstable) {
+    if (n_short <= 0) return SQG_OK;
+    const int32_t N = ctx->nt.n;
+    int32_t *cnt_other = ctx->d_cnt3.p + 2 * (size_t)N, *sum_other = ctx->d_sum3.p + 2 * (size_t)N;
+    static const bool force_sort = getenv("SQG_OTHER_SORT") && atoi(getenv("SQG_OTHER_SORT")) == 1;  // test hook: the sort path even without order-dependent ties
+    if (n_unstable == 0 && !force_sort) {
+        LAUNCH(k_depth_short_apply, 64, 128, ctx->d_shorts.p, (int32_t)n_short, cnt_other, sum_other);
+        return SQG_OK;
+    }
+    if (ctx->shard_count > 1 && n_unstable > 0)
+        FAIL(SQG_EUNSUPPORTED, "a ReadsOther block of <= 3 bp ties with another block at the same start: its segment depends on the tie order of the reference's "
+                               "std::sort over the WHOLE stream (SegmentGraph.cpp:781), which a range shard cannot replay -- run this stream on one context");
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec;
+    OtherCountOp op{b.blk_off, ctx->d_cls.p, ctx->r_break};
+    cub::CountingInputIterator<int64_t> cnt(0);
+    cub::TransformInputIterator<int32_t, OtherCountOp, cub::CountingInputIterator<int64_t>> it(cnt, op);
+    CK(ctx->d_other_off.ensure((size_t)n + 2));
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, ctx->d_other_off.p, (int)(n + 1), ctx->stream));
+    ENSURE_TEMP(tb);
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_temp.p, tb, it, ctx->d_other_off.p, (int)(n + 1), ctx->stream));
+    ctx->launches += 2;
+    int32_t m32 = 0;
+    CK(cudaMemcpyAsync(&m32, ctx->d_other_off.p + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t M = m32;
+    if (M <= 0) return SQG_OK;
+    CK(ctx->d_other_key.ensure((size_t)M + 1)); CK(ctx->d_other_idx.ensure((size_t)M + 1)); CK(ctx->d_other_len.ensure((size_t)M + 1)); CK(ctx->d_other_own.ensure((size_t)M + 1));
+    LAUNCH(k_other_fill, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->r_break, ctx->d_other_off.p, ctx->d_other_key.p, ctx->d_other_idx.p, ctx->d_other_len.p);
+    CK(ctx->d_gs_scratch.ensure(gsort::bytes_needed((size_t)M)));
+    int rc = gsort::sort_like_std_device(ctx->d_other_key.p, ctx->d_other_idx.p, (size_t)M, ctx->d_gs_scratch.p, ctx->stream, &ctx->launches);
+    if (rc < 0) { ctx->err = std::string("ReadsOther sort: ") + cudaGetErrorString((cudaError_t)(-rc)); return SQG_ECUDA; }
+    ctx->other_sort_status = rc;
+    if (rc != 0) {  // std::sort would have left the quicksort path: the CPU twin, from a fresh copy of the keys
+        LAUNCH(k_other_fill, blocks_for(n), kThreads, b, ctx->d_cls.p, ctx->r_break, ctx->d_other_off.p, ctx->d_other_key.p, ctx->d_other_idx.p, ctx->d_other_len.p);
+        std::vector<uint64_t> hk((size_t)M);
+        CK(cudaMemcpyAsync(hk.data(), ctx->d_other_key.p, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<sqh::SortKey> a((size_t)M);
+        for (int64_t i = 0; i < M; i++) a[(size_t)i] = sqh::SortKey{hk[(size_t)i], (uint32_t)i};
+        sqh::sort_keys_like_std(a.data(), a.data() + a.size(), 16);
+        std::vector<uint32_t> hi((size_t)M);
+        for (int64_t i = 0; i < M; i++) { hk[(size_t)i] = a[(size_t)i].key; hi[(size_t)i] = a[(size_t)i].k; }
+        CK(cudaMemcpyAsync(ctx->d_other_key.p, hk.data(), (size_t)M * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_other_idx.p, hi.data(), (size_t)M * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    LAUNCH(k_other_own, blocks_for(M), kThreads, ctx->nt, ctx->d_other_key.p, ctx->d_other_idx.p, ctx->d_other_len.p, M, ctx->d_other_own.p);
+    CK(cub::DeviceScan::InclusiveScan(nullptr, tb, ctx->d_other_own.p, ctx->d_other_own.p, MaxI32(), (int)M, ctx->stream));
+    ENSURE_TEMP(tb);
+    CK(cub::DeviceScan::InclusiveScan(ctx->d_temp.p, tb, ctx->d_other_own.p, ctx->d_other_own.p, MaxI32(), (int)M, ctx->stream));
+    ctx->launches += 2;
+    LAUNCH(k_other_apply, blocks_for(M), kThreads, ctx->nt, ctx->d_other_key.p, ctx->d_other_idx.p, ctx->d_other_len.p, ctx->d_other_own.p, M, cnt_other, sum_other);
+    return SQG_OK;
+}
+
 // Phase 2 (sq_phase2.cuh): one pass over the batch for the depth numerators (do_depth) and the raw edges of the chimeric
 // reads + the concordant stream (do_edges); then the hint fix-up chains and the sort + reduce of the (key, count) pairs.
 static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
@@ -1218,8 +1282,10 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
     int64_t cap = std::max<int64_t>({(int64_t)ctx->d_ekeys.cap, n / 8 + 4 * ctx->c_n_blk + 2 * ctx->c_n_reads + 4096, (int64_t)1 << 20});
     int64_t sens_cap = std::max<int64_t>({(int64_t)ctx->d_sens.cap, n / 64 + 4096, ctx->c_n_reads + 1});
     int64_t slow_cap = std::max<int64_t>({(int64_t)ctx->d_slow.cap, n / 8 + 4096});
+    int64_t short_cap = std::max<int64_t>({(int64_t)ctx->d_shorts.cap, n / 256 + 4096});
     CK(ctx->dc_res0.ensure(ctx->c_n_reads + 1)); CK(ctx->d_scratch32.ensure(n + 1));
     int64_t n_raw = 0;
+    int64_t n_short = 0, n_unstable = 0;
     if (ctx->chim_upload_pending) {  // the chimeric arrays: uploaded by the pre-pass thread behind its own work
         ctx->prepass_worker.wait();
         if (ctx->chim_upload_err) { ctx->err = std::string("upload of the chimeric reads: ") + cudaGetErrorString((cudaError_t)ctx->chim_upload_err); return SQG_ECUDA; }
@@ -1269,6 +1335,11 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             CK(cudaMemsetAsync(ctx->d_counters.p + 16, 0, 3 * sizeof(int64_t), ctx->stream));
             CK(ctx->d_slow.ensure(slow_cap));
             a.slow_list = ctx->d_slow.p; a.n_slow = (int32_t *)(ctx->d_counters.p + 18); a.slow_cap = (int32_t)std::min<int64_t>(ctx->d_slow.cap, 0x7fffffff);
+            // ReadsOther blocks of <= 3 bp: counters [27] = #short blocks, #order-dependent ones (int32 each)
+            CK(ctx->d_omask.ensure((size_t)N + 2)); CK(ctx->d_shorts.ensure((size_t)short_cap));
+            a.omask = ctx->d_omask.p; a.shorts = ctx->d_shorts.p; a.n_short = (int32_t *)(ctx->d_counters.p + 27); a.short_cap = (int32_t)std::min<int64_t>(short_cap, 0x7fffffff);
+            CK(cudaMemsetAsync(ctx->d_counters.p + 27, 0, sizeof(int64_t), ctx->stream));
+            if (do_depth) CK(cudaMemsetAsync(ctx->d_omask.p, 0, ((size_t)N + 2) * 4, ctx->stream));
             {
                 struct { BatchDesc d; NodeTable nt; } hd;
                 hd.d.b = b; hd.d.p = ctx->params; hd.nt = ctx->nt;
@@ -1302,6 +1373,7 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             if (do_depth) {
                 LAUNCH(k_depth_scan, 1, 1024, ctx->d_dtile.p, (int32_t)n_tiles);
                 LAUNCH(k_depth_fix, blocks_for(n_tiles), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_dtile.p, (int32_t)n_tiles, a.cnt_main, a.sum_main);
+                LAUNCH(k_depth_short_nodes, 64, 128, ctx->nt, ctx->d_omask.p, ctx->d_shorts.p, a.n_short, a.short_cap, a.n_short + 1);
             }
             if (do_edges) {
                 LAUNCH(k_fix_heads, 256, 128, ctx->d_scratch32.p, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, ctx->shard_init_hint, (int32_t *)(ctx->d_counters.p + 22));
@@ -1312,18 +1384,27 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
         CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_counters.p + 16, ctx->d_counters.p + 16, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_counters.p + 22, ctx->d_counters.p + 22, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_counters.p + 27, ctx->d_counters.p + 27, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        n_short = do_depth && n > 0 ? ((int32_t *)(ctx->h_counters.p + 27))[0] : 0;
+        n_unstable = do_depth && n > 0 ? ((int32_t *)(ctx->h_counters.p + 27))[1] : 0;
         ctx->shard_lead_sensitive = *(int32_t *)(ctx->h_counters.p + 22) != 0;
         ctx->shard_out_hint = (ctx->shard_count > 1 && do_edges && n > 0) ? *(int32_t *)(ctx->h_counters.p + 23) : -1;
         n_raw = ctx->h_counters.p[9];
         const int32_t ns_conc = ((int32_t *)(ctx->h_counters.p + 10))[0], ns_chim = ((int32_t *)(ctx->h_counters.p + 10))[1];
         ctx->n_sensitive = (int64_t)ns_conc + ns_chim;
         const int64_t n_slow = *(int32_t *)(ctx->h_counters.p + 18);
-        if (!do_edges || (n_raw <= cap && ns_conc <= conc_sens_cap && n_slow <= slow_cap)) break;
+        if (n_short <= short_cap && (!do_edges || (n_raw <= cap && ns_conc <= conc_sens_cap && n_slow <= slow_cap))) break;
         slow_cap = std::max(slow_cap, n_slow + 4096);
-        if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge / sensitive read buffer overflow");
+        short_cap = std::max(short_cap, n_short + 4096);
+        if (attempt == 1) FAIL(SQG_ENOMEM, "raw edge / sensitive read / short block buffer overflow");
         cap = std::max(cap, n_raw + 4096);  // rerun with room for everything (counters are reset, the chimeric blocks restored from their pristine copies)
         sens_cap = std::max<int64_t>(sens_cap, (int64_t)ns_conc + ctx->c_n_reads + 4096);
+    }
+    if (do_depth) {
+        ctx->n_short_other = n_short; ctx->n_unstable_other = n_unstable;
+        const int rc = count_short_other(ctx, n_short, n_unstable);
+        if (rc) return rc;
     }
     PHASE_END(do_depth ? "depth_edges" : "edges_only");
     if (do_edges) {

@@ -181,6 +181,9 @@ struct sqg_ctx {
     struct ChimPatch { int32_t k; int32_t v[4]; };
     std::vector<ChimPatch> chim_undo;  // loaded values of the blocks the last sqg_build_edges patched in the caller's arrays
     sq::DBuf<uint32_t> d_restbits; sq::DBuf<int32_t> d_restoff, d_reflen;  // bitmap of the 1024-bp bins near discordant groups (k_rest_collect)
+    sq::DBuf<uint32_t> d_omask; sq::DBuf<int4> d_shorts;  // ReadsOther blocks of <= 3 bp: per-segment start masks, deferred blocks
+    sq::DBuf<int32_t> d_other_off, d_other_len, d_other_own; sq::DBuf<uint64_t> d_other_key; sq::DBuf<uint32_t> d_other_idx;  // the replayed sort(ReadsOther)
+    int64_t n_short_other = 0, n_unstable_other = 0; int other_sort_status = -1;
     sq::DBuf<sq::SeedOp> d_ops;
     sq::DBuf<sq::SeedOp> d_ops_dense;  // the islands' op lists without their unused capacity, island order
     sq::HBuf<sq::SeedOp> h_ops;

@@ -235,6 +235,10 @@ int main(int argc, char **argv) {
         if (j >= c0 && d.pos >= nt.pos[j] && d.pos + d.len <= nt.end[j]) { cnt[j]++; sum[j] += d.len; }
     }
     bool other_nonempty = false;
+    std::vector<uint32_t> omask((size_t)N + 1, 0);
+    struct ShortBlk { int32_t chr, start, len; };
+    std::vector<ShortBlk> shorts;
+    int64_t n_unstable = 0;
     {
         int32_t cursor = 0;
         for (int64_t r = 0; r < r_break; r++) {
@@ -248,10 +252,44 @@ int main(int argc, char **argv) {
             }
             for (uint32_t k = o + 1; k < b.blk_off[r + 1]; k++) {
                 other_nonempty = true;
-                const int32_t m2 = depth_target(nt, c, b.blk_ref_pos[k], b.blk_match_ref[k]);
-                if (m2 != kNoNode && depth_contained(nt, m2, c, b.blk_ref_pos[k], b.blk_match_ref[k])) { cnt[2 * N + m2]++; sum[2 * N + m2] += b.blk_match_ref[k]; }
+                const int32_t st = b.blk_ref_pos[k], l = b.blk_match_ref[k];
+                uint32_t bit;
+                const int32_t jm = depth_other_mark(nt, c, st, l, &bit);
+                if (jm >= 0) omask[jm] |= bit;
+                if (l <= kSeedThresh) { shorts.push_back(ShortBlk{c, st, l}); continue; }  // second pass, once the masks are complete
+                const int32_t m2 = depth_target(nt, c, st, l);
+                if (m2 != kNoNode && depth_contained(nt, m2, c, st, l)) { cnt[2 * N + m2]++; sum[2 * N + m2] += l; }
             }
         }
+        std::vector<int32_t> short_node(shorts.size());
+        for (size_t q = 0; q < shorts.size(); q++) {
+            bool un = false;
+            short_node[q] = depth_short_node(nt, omask.data(), shorts[q].chr, shorts[q].start, shorts[q].len, &un);
+            if (un) n_unstable++;
+        }
+        if (n_unstable == 0 || getenv("SQ_EMUL_NO_OTHER_SORT")) {
+            for (size_t q = 0; q < shorts.size(); q++)
+                if (short_node[q] != kNoNode) { cnt[2 * N + short_node[q]]++; sum[2 * N + short_node[q]] += shorts[q].len; }
+        } else {
+            // Some short block ties with an entry of the same (chr, start) that would move it: the reference's answer is the order
+            // in which its unstable std::sort (:781) leaves the ties.  Same input order, same comparator, same library: sort
+            // ReadsOther for real and walk the cursor = running maximum of the entries' own segments.
+            std::vector<std::pair<int, std::pair<int, int>>> RO;
+            for (int64_t r = 0; r < r_break; r++) {
+                if (!(cls[r] & CLS_HASBLK)) continue;
+                for (uint32_t k = b.blk_off[r] + 1; k < b.blk_off[r + 1]; k++) RO.push_back(std::make_pair(b.ref_id[r], std::make_pair(b.blk_ref_pos[k], b.blk_match_ref[k])));
+            }
+            std::sort(RO.begin(), RO.end(), [](std::pair<int, std::pair<int, int>> a, std::pair<int, std::pair<int, int>> c) { if (a.first != c.first) return a.first < c.first; else return (a.second).first < (c.second).first; });
+            int32_t cursor = -1;
+            for (const auto &e : RO) {
+                const int32_t c = e.first, st = e.second.first, l = e.second.second;
+                const int32_t own = depth_target(nt, c, st, l);  // long: n(start); short: earliest containing segment, else n(start)
+                if (own == kNoNode) { cursor = kNoNode; continue; }
+                if (own > cursor) cursor = own;
+                if (l <= kSeedThresh && cursor != kNoNode && cursor < N && depth_contained(nt, cursor, c, st, l)) { cnt[2 * N + cursor]++; sum[2 * N + cursor] += l; }
+            }
+        }
+        fprintf(stderr, "emul: %zu short ReadsOther blocks, %lld order-dependent\n", shorts.size(), (long long)n_unstable);
     }
     {
         std::vector<int32_t> a;

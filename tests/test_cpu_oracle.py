@@ -72,3 +72,17 @@ def test_restatement_matches_reference_with_options(opts, args, tmp_path, ref_or
     me = pyref.run_restate(cp, hp, str(tmp_path / "me"), bps=bps, opts=opts)
     common.assert_same(r, me, ("chim_loaded", "nodes", "avgdepth", "edges", "chim_after_edges"))
     assert pyref.support_from_cov(r, bps, me["cov"]) == pyref.support_map(r)
+
+
+@pytest.mark.parametrize("n,seed,disc,kw", [
+    (30000, 37, 0.2, dict(n_genes=100, fusion_support=20)),
+    (20000, 36, 0.05, dict(n_genes=20, fusion_support=20, exon_len=(20, 170), intron_len=(60, 400))),
+])
+def test_restatement_matches_reference_with_short_blocks(n, seed, disc, kw, tmp_path, ref_oracle):
+    """min_block=1: aligned blocks of 1-3 bp are left in (the generators' default drops them)."""
+    cp, hp, *_ = common.write_case(str(tmp_path), n, seed, disc, None, min_block=1, **kw)
+    r = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    bps = pyref.breakpoints_of(r)
+    me = pyref.run_restate(cp, hp, str(tmp_path / "me"), bps=bps)
+    common.assert_same(r, me, ("chim_loaded", "nodes", "avgdepth", "edges", "chim_after_edges"))
+    assert pyref.support_from_cov(r, bps, me["cov"]) == pyref.support_map(r)

@@ -235,3 +235,30 @@ def test_non_default_parameters(tmp_path, built_lib, ref_oracle, opts, args):
            "edges": edges.table(), "chim_after_edges": case.chimeric.block_table()}
     common.assert_same(ref, got)
     assert g.ExactBPConcordantSupport(ref["final_nodes"], ref["final_edges"], pyref.exactbp_map(ref)) == pyref.support_map(ref)
+
+
+@pytest.mark.parametrize("n,seed,disc,ref_len,kw,want_unstable", [
+    # aligned blocks of 1-3 bp (STAR's alignSJDBoverhangMin is 3): short NON-first blocks feed ReadsOther, whose merge loop
+    # (SegmentGraph.cpp:806-825) counts them in the segment LEFT of the one they start in when that one still contains them
+    # within +-3 -- unless an entry sorted before them has moved the cursor on
+    (600, 303, 0.3, [3000000, 2000000], dict(n_genes=40, fusion_support=8), False),   # short blocks, no tie that matters: start masks only
+    (600, 327, 0.3, [3000000, 2000000], dict(n_genes=40, fusion_support=8), False),
+    (600, 302, 0.3, [3000000, 2000000], dict(n_genes=40, fusion_support=8), True),    # ties at a splice junction: the reference's answer
+    (30000, 37, 0.2, None, dict(n_genes=100, fusion_support=20), True),               # is its unstable sort's tie order, replayed
+    (30000, 38, 0.05, [3000000, 2000000, 500000, 16569], dict(n_genes=100, fusion_support=60), True),
+    (120000, 39, 0.05, None, dict(n_genes=300, fusion_support=20, exon_len=(20, 170), intron_len=(60, 400)), True),
+])
+def test_short_blocks_match_reference(n, seed, disc, ref_len, kw, want_unstable, tmp_path, built_lib, ref_oracle):
+    """min_block=1: nothing is filtered out of the generator.  Support / AvgDepth with 1-3 bp blocks, including the case the
+    reference's own source leaves to std::sort's tie order (sqg_stat "unstable_depth_blocks" > 0: the sort is replayed)."""
+    cp, hp, *_ = common.write_case(str(tmp_path), n, seed, disc, ref_len, min_block=1, **kw)
+    ref = ref_oracle.run(cp, hp, str(tmp_path / "ref"))
+    got = common.run_cuda(cp, hp, do_cov_with=ref)
+    common.assert_same(ref, got)
+    g = got["graph"]
+    assert g.stat("short_other_blocks") > 0
+    assert (g.stat("unstable_depth_blocks") > 0) == want_unstable
+    if want_unstable:
+        assert g.stat("other_sort_status") == 0  # std::sort's permutation came from the device
+    from oracle import pyref
+    assert got["support"] == pyref.support_map(ref)
