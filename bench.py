@@ -33,7 +33,43 @@ import numpy as np  # noqa: E402
 
 DEFAULT_PAIRS = int(os.environ.get("SQUID_BENCH_PAIRS", 100_000_000))
 DISC_FRAC = 0.005
-CPU_SAMPLE_PAIRS = int(os.environ.get("SQUID_BENCH_CPU_PAIRS", 1_000_000))
+CPU_SAMPLE_PAIRS = int(os.environ.get("SQUID_BENCH_CPU_PAIRS", 2_000_000))   # one reference run on it: ~4 s on one core
+REF_ARM_PAIRS = int(os.environ.get("SQUID_BENCH_REF_PAIRS", 4_000_000))      # --impl reference: ~8 s per step, the largest sample that keeps 25 steps within a few minutes
+# 100-bp reads, ~70 % unspliced / ~30 % spliced, K = 1.35 aligned blocks per record.  The splicing comes from
+# the transcript model (reads laid on exon chains), so K is set through the exon length range; pairs with an aligned block
+# under 4 bp are dropped by the generator (STAR's default minimum splice overhangs are 3-5 bp).
+BENCH_EXON_LEN = (60, 460)
+BENCH_MIN_BLOCK = 4
+CRC_FILE = os.path.join(ROOT, "tests", "golden", "bench_crc.json")
+
+
+def make_workload(pairs: int, seed: int, device: str):
+    from squid_b200 import synth_gpu
+    return synth_gpu.make_bench_batch(pairs, seed=seed, device=device, exon_len=BENCH_EXON_LEN, min_block=BENCH_MIN_BLOCK)
+
+
+def workload_id(pairs: int, seed: int) -> str:
+    return "grch38 pairs=%d seed=%d disc=%g exon_len=%d-%d min_block=%d genes=20000" % (pairs, seed, DISC_FRAC, BENCH_EXON_LEN[0], BENCH_EXON_LEN[1], BENCH_MIN_BLOCK)
+
+
+def output_crcs(nodes, edges, chim_blocks, cov) -> dict:
+    """CRC32 of every output of one step, in the layout of the reference harness's dumps."""
+    import zlib
+    c = lambda a: zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xffffffff
+    nd = np.stack([nodes.Chr, nodes.Position, nodes.Length, nodes.Support], axis=1).astype(np.int32)
+    return {"nodes": c(nd), "avgdepth": c(np.asarray(nodes.AvgDepth, np.float64)), "edges": c(edges.table()), "chim_after_edges": c(np.asarray(chim_blocks, np.int32)),
+            "coverage": c(np.asarray(cov, np.int32)), "n_nodes": int(nd.shape[0]), "n_edges": int(edges.Ind1.shape[0]), "n_bp": int(np.asarray(cov).shape[0])}
+
+
+def pinned_crcs(pairs: int, seed: int):
+    """Reference CRCs of this exact workload, if it has been pinned (tests/tools/pin_bench_crc.py ran the reference on it)."""
+    try:
+        for rec in json.load(open(CRC_FILE)):
+            if rec["workload"] == workload_id(pairs, seed):
+                return rec
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak_gbs():
@@ -108,9 +144,9 @@ def reference_arm(args, rank, world):
     from oracle import pyref
     from squid_b200 import sqmb, synth
     pyref.build()
-    P = CPU_SAMPLE_PAIRS
+    P = REF_ARM_PAIRS
     with tempfile.TemporaryDirectory() as d:
-        conc, chim, info = synth.make_case(P, ref_len=synth.GRCH38_LEN, seed=100, disc_frac=DISC_FRAC, n_genes=20000, adversarial=False)
+        conc, chim, info = synth.make_case(P, ref_len=synth.GRCH38_LEN, seed=100, disc_frac=DISC_FRAC, n_genes=20000, adversarial=False, exon_len=BENCH_EXON_LEN, min_block=BENCH_MIN_BLOCK)
         sqmb.write_sqmb(d + "/conc.sqmb", conc); sqmb.write_sqmb(d + "/chim.sqmb", chim)
         n_pairs = conc.n / 2.0
         times = []
@@ -125,7 +161,7 @@ def reference_arm(args, rank, world):
            "sample": "%d read pairs, GRCh38 layout, %.1f%% discordant; BuildNode_STAR+BuildEdges+ExactBPConcordantSupport of the reference's own sources (oracle/_ref), in-memory BAM shim" % (int(n_pairs), 100 * DISC_FRAC)}
     print(json.dumps({"impl": "reference", "metric": "read pairs/s through segment-graph build", "value": val, "unit": "read pairs/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                      "dtype": "int32", "data": "synthetic", "config": {"workload": "synthetic GRCh38-layout read pairs, ~0.5% discordant (bounded sample of configs[1])", "pairs_per_step": int(n_pairs)},
+                      "dtype": "int32", "data": "synthetic", "config": {"workload": "synthetic GRCh38-layout read pairs, ~0.5% discordant, K = 1.35 blocks/record (bounded sample of configs[1]: the largest that keeps the run within a few minutes on one core)", "pairs_per_step": int(n_pairs)},
                       "cpu_baseline": cpu, "e2e": {"value": val, "unit": "read pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -138,7 +174,7 @@ def cpu_baseline_leg():
             return None
         P = CPU_SAMPLE_PAIRS
         with tempfile.TemporaryDirectory() as d:
-            conc, chim, info = synth.make_case(P, ref_len=synth.GRCH38_LEN, seed=100, disc_frac=DISC_FRAC, n_genes=20000, adversarial=False)
+            conc, chim, info = synth.make_case(P, ref_len=synth.GRCH38_LEN, seed=100, disc_frac=DISC_FRAC, n_genes=20000, adversarial=False, exon_len=BENCH_EXON_LEN, min_block=BENCH_MIN_BLOCK)
             sqmb.write_sqmb(d + "/conc.sqmb", conc); sqmb.write_sqmb(d + "/chim.sqmb", chim)
             r = pyref.run(d + "/conc.sqmb", d + "/chim.sqmb", d + "/out")
         t = r["timings"]
@@ -147,6 +183,113 @@ def cpu_baseline_leg():
                 "sample": "%d read pairs of the same generator; reference's own sources (oracle/_ref), single thread, BGZF excluded; phases s: nodes %.2f edges %.2f coverage %.2f" % (conc.n // 2, t["build_nodes_s"], t["build_edges_s"], t["bp_coverage_s"])}
     except Exception as e:  # the baseline is informative; never fail the bench on it
         return {"value": None, "unit": "read pairs/s", "cores": 1, "kind": "reference", "sample": "failed: %s" % e}
+
+
+def stream_case(pairs: int, seed: int):
+    """Chimeric reads + config of the stream (pairs, seed) through the host loader, without generating its concordant records."""
+    from squid_b200 import api, sqmb, synth
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tx = synth.Transcriptome(rng, np.asarray(synth.GRCH38_LEN, dtype=np.int64), 20000, exon_len=BENCH_EXON_LEN)
+    prob = tx.g_expr / tx.g_expr.sum()
+    chim_tab, _ = synth.make_chimeric(tx, prob, pairs, seed, DISC_FRAC, adversarial=False)
+    with tempfile.TemporaryDirectory() as d:
+        sqmb.write_sqmb(d + "/chim.sqmb", chim_tab)
+        sqmb.write_sqmb(d + "/conc.sqmb", sqmb.empty(synth.GRCH38_LEN, 0))
+        case = api.HostCase(d + "/conc.sqmb", d + "/chim.sqmb")
+    return case, case.chimeric
+
+
+def one_stream_leg(args, rank, world, local, dev, batch, chim0, case, steps, warmup):
+    """N > 1, north_star's split: ONE sorted stream -- rank 0's stream, the very stream the single-GPU run measures -- cut at
+    clean cuts into N exact genomic-range shards (sqg_plan_shards), one per GPU; seed ops, depth numerators, edge tables,
+    LocateRead hints and the coverage chain cross the ranks over NCCL (squid_b200/sharded.py).  The combined outputs are
+    bit-identical to the single-GPU run, so they are held against the same pinned reference CRCs.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from squid_b200 import api, sharded, synth_gpu
+    comm = sharded.DistComm()
+    shm = "/dev/shm/sq_bench_%s" % os.environ.get("MASTER_PORT", "0")
+    t_plan = 0.0
+    if rank == 0:
+        os.makedirs(shm, exist_ok=True)
+        host = {k: v.cpu().numpy() for k, v in batch.items()}
+        hb = api.RecordBatch({k: (v.view(np.uint16) if v.dtype == np.int16 else v.view(np.uint32) if k == "blk_off" else v) for k, v in host.items()})
+        t0 = time.perf_counter()
+        cuts = api.plan_shards(hb, chim0, case.config, len(case.ref_len), world)
+        t_plan = time.perf_counter() - t0
+        ok = len(cuts) - 1 == world
+        if ok:
+            for r in range(world):
+                for k, v in hb.slice(cuts[r], cuts[r + 1]).a.items():
+                    np.save("%s/%d_%s.npy" % (shm, r, k), v)
+        json.dump({"cuts": cuts, "ok": ok}, open(shm + "/cuts.json", "w"))
+        del hb, host
+    dist.barrier()
+    meta = json.load(open(shm + "/cuts.json"))
+    if not meta["ok"]:
+        return {"unavailable": "the planner found %d clean shards for %d ranks" % (len(meta["cuts"]) - 1, world)}
+    cuts = meta["cuts"]
+    mine = {k: np.load("%s/%d_%s.npy" % (shm, rank, k)) for k in api.BATCH_DTYPES}
+    dbatch = {k: torch.from_numpy(v.view(np.int16) if v.dtype == np.uint16 else v.view(np.int32) if v.dtype == np.uint32 else v).to(dev) for k, v in mine.items()}
+    del mine
+    dist.barrier()
+    if rank == 0:
+        for f in os.listdir(shm):
+            os.unlink(os.path.join(shm, f))
+        os.rmdir(shm)
+    dstruct = synth_gpu.batch_struct(dbatch)
+    sg = sharded.ShardedSegmentGraph(case.config, case.ref_len, world, [rank], comm=comm, devices=[local])
+    g = sg.g[0]
+    st = {}
+
+    def step():
+        pool = st.setdefault("pool", [])
+        chim = pool.pop() if pool else api.ChimericReads(chim0.a)
+        st["chim"] = chim
+        g.attach_concordant_device(dstruct, keepalive=dbatch, first_record_index=cuts[rank])
+        g.load_chimeric(chim)
+        t0 = time.perf_counter()
+        nodes = sg.BuildNode_STAR()
+        t1 = time.perf_counter()
+        edges = sg.BuildEdges(gather_chimeric=False)
+        t2 = time.perf_counter()
+        if "bps" not in st:
+            st["bps"] = bps_from_graph(nodes, edges)
+        bc, bp = st["bps"]
+        cov = sg.BPCoverage(bc, bp)
+        t3 = time.perf_counter()
+        tl = st.setdefault("tl", {})
+        for k, v in (("BuildNode_STAR", t1 - t0), ("BuildEdges", t2 - t1), ("BPCoverage", t3 - t2)):
+            tl[k] = tl.get(k, 0.0) + 1e3 * v
+        return nodes, edges, cov
+
+    def barrier():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    st["pool"] = [api.ChimericReads(chim0.a) for _ in range(steps)]
+    st["tl"] = {}
+    sg.rounds = {"seeds": 0, "hints": 0, "chain": 0}
+    barrier()
+    t = time.perf_counter()
+    for _ in range(steps):
+        nodes, edges, cov = step()
+    barrier()
+    sec = (time.perf_counter() - t) / steps
+    tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt.item())
+    per_rank = comm.allgather([{"rank": rank, "records": int(cuts[rank + 1] - cuts[rank]), "host_timeline_ms": {k: round(v / steps, 2) for k, v in st["tl"].items()}}])
+    out = None
+    if rank == 0:
+        R = cuts[-1]
+        got = output_crcs(nodes, edges, st["chim"].block_table(), cov)
+        out = {"mode": "ONE stream of %d read pairs in %d exact genomic-range shards (sqg_plan_shards), NCCL exchanges between the stages" % (R // 2, world),
+               "scaling": "strong", "value": (R // 2) / sec, "unit": "read pairs/s", "ms_per_step": 1e3 * sec, "planner_s": round(t_plan, 3), "cuts": cuts,
+               "exchange_rounds_per_step": {k: v / steps for k, v in sg.rounds.items()}, "per_rank": per_rank, "crc32": got}
+    sg.close()
+    return out
 
 
 def main():
@@ -184,7 +327,7 @@ def main():
     # ---- workload: generated on the device, sorted; chimeric reads through the host loader --------------------
     t0 = time.time()
     seed0 = int(os.environ.get("SQUID_BENCH_SEED", 100))  # (rank r of a multi-GPU run uses seed0 + r: its stream on one GPU = SQUID_BENCH_SEED=100+r)
-    batch, tx, prob = synth_gpu.make_bench_batch(P, seed=seed0 + rank, device=str(dev))
+    batch, tx, prob = make_workload(P, seed0 + rank, str(dev))
     chim_tab, fusions = synth.make_chimeric(tx, prob, P, seed0 + rank, DISC_FRAC, adversarial=False)
     with tempfile.TemporaryDirectory() as d:
         sqmb.write_sqmb(d + "/chim.sqmb", chim_tab)
@@ -276,6 +419,7 @@ def main():
         cov = g.BPCoverage(bc, bp)
         lap("BPCoverage")
         state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "cov_chain_chunks", "edges_single_path", "edges_generic_path")}
+        state["last"] = (nodes, edges, cov)
         state.update(n_nodes=int(nodes.Chr.shape[0]), n_edges=int(edges.Ind1.shape[0]), n_bp=int(bc.shape[0]), cov_sum=int(cov.sum()),
                      d2h=int(nodes.Chr.nbytes * 3 + nodes.count3.nbytes * 2 + edges.Ind1.nbytes * 3 + edges.Ind1.shape[0] + cov.nbytes))
         return nodes, edges, cov
@@ -321,6 +465,15 @@ def main():
         print("[rank %d] resident step %.1f ms; host timeline %s" % (rank, 1e3 * sec, {k: round(v, 1) for k, v in timeline.items()}), file=sys.stderr, flush=True)
     sec_e2e, phases_e2e, _, _ = timed(False, max(1, min(args.steps, 3)), 1)
 
+    # ---- N > 1: the same stream as the single-GPU run, range-sharded over the N GPUs (strong scaling, north_star's split) ----
+    one_stream = None
+    if world > 1:
+        if rank != 0:
+            del batch
+            torch.cuda.empty_cache()
+        case0, chim00 = (case, chim0) if rank == 0 else stream_case(P_req, seed0)  # every rank holds ALL chimeric reads of the one stream
+        one_stream = one_stream_leg(args, rank, world, local, dev, batch if rank == 0 else None, chim00, case0, max(1, min(args.steps, 5)), 2)
+
     # ---- roofline of the dominant stream phase --------------------------------------------------------------
     K = NB / R
     # algorithmic bytes per launch of the stream kernels: phase 1 and phase 2 read the whole batch
@@ -346,6 +499,20 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg()
+    # ---- parity at full size: the outputs of the last timed step against the reference's, pinned once for this exact workload
+    #      (tests/tools/pin_bench_crc.py: the reference's own sources ran on these records; tests/golden/bench_crc.json)
+    parity = None
+    if rank == 0:
+        nodes_l, edges_l, cov_l = state["last"]
+        got = output_crcs(nodes_l, edges_l, state["chim"].block_table(), cov_l)
+        pin = pinned_crcs(P_req, seed0)
+        if pin is None:
+            parity = {"checked": False, "why": "this workload has not been pinned (tests/tools/pin_bench_crc.py)", "crc32": got}
+        else:
+            bad = [k for k, v in pin["reference_crc32"].items() if got.get(k) != v]
+            parity = {"checked": True, "ok": not bad, "against": "reference build (oracle/_ref) on the same %d records; coverage: CPU restatement" % pin["records"], "mismatch": bad}
+            if bad:
+                print(json.dumps({"error": "outputs differ from the pinned reference CRCs", "mismatch": bad, "got": got, "want": pin["reference_crc32"]}), file=sys.stderr, flush=True)
     if rank == 0:
         out = {
             "metric": "read pairs/s through segment-graph build", "value": world * P / sec, "unit": "read pairs/s", "n_gpus": world, "steps": args.steps,
@@ -360,8 +527,17 @@ def main():
             "whole_path": {"alg_bytes_per_pair": b_alg_pair, "gpu_ms_in_kernels": total_gpu_ms,
                            "frac_of_hbm_roofline_wall": (b_alg_pair * P / sec) / 1e9 / peak, "frac_of_hbm_roofline_kernels": (b_alg_pair * P / (total_gpu_ms * 1e-3)) / 1e9 / peak if total_gpu_ms else None},
             "phases_ms": phases, "host_timeline_ms": timeline, "bps_standin_ms_outside_timed_region": state.get("bps_standin_ms"), "phases_ms_e2e": phases_e2e, "stats": state.get("stats"),
-            "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches), "gen_s": t_gen,
+            "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches), "gen_s": t_gen, "parity": parity,
         }
+        if one_stream is not None:
+            pin = pinned_crcs(P_req, seed0)
+            if pin is not None and "crc32" in one_stream:
+                bad = [k for k, v in pin["reference_crc32"].items() if one_stream["crc32"].get(k) != v]
+                one_stream["parity"] = {"checked": True, "ok": not bad, "mismatch": bad, "against": "the pinned reference CRCs of the single-GPU workload"}
+                if bad:
+                    parity = dict(parity or {}, checked=True, ok=False, mismatch=(parity or {}).get("mismatch", []) + ["one_stream:" + k for k in bad])
+                    out["parity"] = parity
+            out["one_stream"] = one_stream
         if real_stdout is not None:
             sys.stdout.flush()
             os.dup2(real_stdout, 1)
@@ -369,6 +545,8 @@ def main():
     g.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity and parity.get("checked") and not parity.get("ok"):
+        raise SystemExit(3)  # a fast step with the wrong answer is not a result
 
 
 def _dev_view(ptr, n, dtype, dev):

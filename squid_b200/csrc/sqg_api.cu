@@ -26,6 +26,7 @@
 #include "sq_phase3.cuh"
 #include "sq_seed.cuh"
 #include "sq_gpusort.cuh"
+#include "sq_prepass.cuh"
 #include "sqg_ctx.cuh"
 
 using namespace sq;
@@ -772,8 +773,8 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     if (n == "partial_records") return ctx->n_pc;
     if (n == "displaced_records") return ctx->n_dp;
     if (n == "lmax") return ctx->lmax;
-    if (n == "groups") return (int64_t)ctx->pre.groups.size();
-    if (n == "disc_blocks") return (int64_t)ctx->pre.disc.size() - 1;
+    if (n == "groups") return ctx->pre_nG;
+    if (n == "disc_blocks") return ctx->pre_nD;
     if (n == "sensitive_reads") return ctx->n_sensitive;
     if (n == "raw_edges") return ctx->n_raw_edges;
     if (n == "r_break") return ctx->r_break;
@@ -895,6 +896,109 @@ extern "C" int sqg_selftest_gpu_sort(int32_t device, int64_t n, uint64_t seed, u
     return verdict;
 }
 
+// The chimeric pre-pass on the device (sq_prepass.cuh), run by the pre-pass thread on stream3 beside the classification: the
+// chimeric arrays are in HBM already (this thread uploaded them), the products never touch the host -- only their sizes do.
+#define PCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+static int device_prepass(sqg_ctx *ctx, size_t nr, size_t nb) {
+    cudaStream_t st = ctx->stream3;
+    const int32_t n_ref = ctx->params.n_ref;
+    PreChim c;
+    c.n_reads = (int64_t)nr; c.read_off = ctx->dc_read_off.p; c.n_first = ctx->dc_n_first.p; c.first_total = ctx->dc_first_total.p; c.second_total = ctx->dc_second_total.p;
+    c.first_low = ctx->dc_first_low.p; c.second_low = ctx->dc_second_low.p; c.multi = ctx->dc_multi.p;
+    c.chr = ctx->dc_ref_id.p; c.pos = ctx->dc0_ref_pos.p; c.rpos = ctx->dc0_read_pos.p; c.mref = ctx->dc0_match_ref.p; c.mread = ctx->dc0_match_read.p; c.rev = ctx->dc_rev.p;
+    PCK(ctx->d_pre_ndis.ensure(nr + 1)); PCK(ctx->d_pre_pusher.ensure(nr + 1)); PCK(ctx->d_pre_lastk.ensure(nr + 1)); PCK(ctx->d_pre_off.ensure(nr + 2));
+    PCK(ctx->d_pre_part.ensure(4 * nr + n_ref + 1)); PCK(ctx->d_pre_part2.ensure(4 * nr + n_ref + 1)); PCK(ctx->d_pre_cnt.ensure(8)); PCK(ctx->h_pre_cnt.ensure(8));
+    auto temp = [&](size_t bytes) { return ctx->d_temp3.ensure(bytes + 256); };
+    int64_t launches = 0;
+    PCK(cudaMemsetAsync(ctx->d_pre_ndis.p + nr, 0, 4, st));
+    k_pre_count<<<blocks_for((int64_t)nr), kThreads, 0, st>>>(c, ctx->d_pre_ndis.p, ctx->d_pre_pusher.p, ctx->d_pre_lastk.p);
+    size_t tb = 0, tb2 = 0;
+    PCK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_pre_ndis.p, ctx->d_pre_off.p, (int)(nr + 1), st));
+    PCK(cub::DeviceScan::ExclusiveScan(nullptr, tb2, ctx->d_pre_pusher.p, ctx->d_pre_pusher.p, MaxI32(), (int32_t)-1, (int)nr, st));
+    PCK(temp(std::max(tb, tb2)));
+    PCK(cub::DeviceScan::ExclusiveSum(ctx->d_temp3.p, tb, ctx->d_pre_ndis.p, ctx->d_pre_off.p, (int)(nr + 1), st));
+    PCK(cub::DeviceScan::ExclusiveScan(ctx->d_temp3.p, tb2, ctx->d_pre_pusher.p, ctx->d_pre_pusher.p, MaxI32(), (int32_t)-1, (int)nr, st));
+    PCK(cudaMemcpyAsync(ctx->h_pre_cnt.p, ctx->d_pre_off.p + nr, 8, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    const int64_t nD = ctx->h_pre_cnt.p[0];
+    if (nD >= 0x7fffff00ll) return (int)cudaErrorInvalidValue;
+    PCK(ctx->d_gs_keys.ensure((size_t)nD + 1)); PCK(ctx->d_gs_idx.ensure((size_t)nD + 1)); PCK(ctx->d_gs_scratch.ensure(gsort::bytes_needed((size_t)nD)));
+    PCK(ctx->d_disc.ensure((size_t)nD + 1)); PCK(ctx->d_pre_endkey.ensure((size_t)nD + 1)); PCK(ctx->d_pre_excl.ensure((size_t)nD + 1)); PCK(ctx->d_pre_incl.ensure((size_t)nD + 1));
+    PCK(ctx->d_pre_opens.ensure((size_t)nD + 1)); PCK(ctx->d_pre_open.ensure((size_t)nD + 1));
+    // PartAlignPos is resize()d to n_ref entries (0, 0) and then appended to (:203-204)
+    PCK(cudaMemsetAsync(ctx->d_pre_part.p, 0, (size_t)n_ref * 8, st));
+    const unsigned long long np0 = (unsigned long long)n_ref;
+    PCK(cudaMemcpyAsync(ctx->d_pre_cnt.p, &np0, 8, cudaMemcpyHostToDevice, st));
+    k_pre_write<<<blocks_for((int64_t)nr), kThreads, 0, st>>>(c, ctx->d_pre_off.p, ctx->d_pre_pusher.p, ctx->d_pre_lastk.p, ctx->d_gs_keys.p, ctx->d_gs_idx.p, ctx->d_pre_part.p,
+                                                                 (unsigned long long *)ctx->d_pre_cnt.p);
+    PCK(cudaMemcpyAsync(ctx->h_pre_cnt.p + 1, ctx->d_pre_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    launches += 6;
+    // std::sort's permutation of bamdiscordant (:264): tie order is observable
+    int rc = gsort::sort_like_std_device(ctx->d_gs_keys.p, ctx->d_gs_idx.p, (size_t)nD, ctx->d_gs_scratch.p, st, &launches);
+    ctx->gs_last_status = rc;
+    if (rc < 0) return -rc;
+    if (rc != 0) {  // std::sort would have left the quicksort path (never seen on alignment data): the CPU twin, from a fresh copy of the keys
+        const unsigned long long np1 = (unsigned long long)n_ref;
+        PCK(cudaMemcpyAsync(ctx->d_pre_cnt.p, &np1, 8, cudaMemcpyHostToDevice, st));
+        k_pre_write<<<blocks_for((int64_t)nr), kThreads, 0, st>>>(c, ctx->d_pre_off.p, ctx->d_pre_pusher.p, ctx->d_pre_lastk.p, ctx->d_gs_keys.p, ctx->d_gs_idx.p, ctx->d_pre_part.p,
+                                                                     (unsigned long long *)ctx->d_pre_cnt.p);
+        std::vector<uint64_t> hk((size_t)nD); std::vector<uint32_t> hi((size_t)nD);
+        PCK(cudaMemcpyAsync(hk.data(), ctx->d_gs_keys.p, (size_t)nD * 8, cudaMemcpyDeviceToHost, st));
+        PCK(cudaMemcpyAsync(hi.data(), ctx->d_gs_idx.p, (size_t)nD * 4, cudaMemcpyDeviceToHost, st));
+        PCK(cudaStreamSynchronize(st));
+        std::vector<sqh::SortKey> a((size_t)nD);
+        for (int64_t i = 0; i < nD; i++) a[(size_t)i] = sqh::SortKey{hk[(size_t)i], hi[(size_t)i]};
+        sqh::sort_keys_like_std(a.data(), a.data() + a.size(), 8);
+        for (int64_t i = 0; i < nD; i++) hi[(size_t)i] = a[(size_t)i].k;
+        PCK(cudaMemcpyAsync(ctx->d_gs_idx.p, hi.data(), (size_t)nD * 4, cudaMemcpyHostToDevice, st));
+        PCK(cudaStreamSynchronize(st));
+    }
+    PCK(cudaStreamSynchronize(st));
+    const int64_t nP = ctx->h_pre_cnt.p[1];
+    PCK(ctx->d_pchr.ensure((size_t)nP + 1)); PCK(ctx->d_ppos.ensure((size_t)nP + 1));
+    {   // sort(PartAlignPos) by (chr, pos) (:262): a total order on the values, any stable or unstable sort agrees
+        int key_bits = 33;
+        while (key_bits < 64 && (1ll << (key_bits - 32)) < (long long)n_ref) key_bits++;
+        PCK(cub::DeviceRadixSort::SortKeys(nullptr, tb, ctx->d_pre_part.p, ctx->d_pre_part2.p, (int)nP, 0, key_bits, st));
+        PCK(temp(tb));
+        PCK(cub::DeviceRadixSort::SortKeys(ctx->d_temp3.p, tb, ctx->d_pre_part.p, ctx->d_pre_part2.p, (int)nP, 0, key_bits, st));
+        k_pre_split_part<<<blocks_for(nP), kThreads, 0, st>>>(ctx->d_pre_part2.p, nP, ctx->d_pchr.p, ctx->d_ppos.p);
+        launches += 4;
+    }
+    k_pre_gather<<<blocks_for(nD + 1), kThreads, 0, st>>>(c, ctx->d_gs_idx.p, nD, ctx->d_disc.p, ctx->d_pre_endkey.p);
+    int32_t nG = 0;
+    if (nD > 0) {
+        PCK(cub::DeviceScan::ExclusiveScan(nullptr, tb, ctx->d_pre_endkey.p, ctx->d_pre_excl.p, MaxU64(), (uint64_t)0, (int)nD, st));
+        PCK(cub::DeviceScan::InclusiveScan(nullptr, tb2, ctx->d_pre_endkey.p, ctx->d_pre_incl.p, MaxU64(), (int)nD, st));
+        PCK(temp(std::max(tb, tb2)));
+        PCK(cub::DeviceScan::ExclusiveScan(ctx->d_temp3.p, tb, ctx->d_pre_endkey.p, ctx->d_pre_excl.p, MaxU64(), (uint64_t)0, (int)nD, st));
+        PCK(cub::DeviceScan::InclusiveScan(ctx->d_temp3.p, tb2, ctx->d_pre_endkey.p, ctx->d_pre_incl.p, MaxU64(), (int)nD, st));
+        k_pre_opens<<<blocks_for(nD), kThreads, 0, st>>>(ctx->d_disc.p, ctx->d_pre_excl.p, nD, ctx->params.read_len, ctx->d_pre_opens.p);
+        cub::CountingInputIterator<int32_t> cnt(0);
+        PreOpenOp op{ctx->d_pre_opens.p};
+        int32_t *d_ng = (int32_t *)(ctx->d_pre_cnt.p + 2);
+        PCK(cub::DeviceSelect::If(nullptr, tb, cnt, ctx->d_pre_open.p, d_ng, (int)nD, op, st));
+        PCK(temp(tb));
+        PCK(cub::DeviceSelect::If(ctx->d_temp3.p, tb, cnt, ctx->d_pre_open.p, d_ng, (int)nD, op, st));
+        PCK(cudaMemcpyAsync(ctx->h_pre_cnt.p + 2, ctx->d_pre_cnt.p + 2, 8, cudaMemcpyDeviceToHost, st));
+        PCK(cudaStreamSynchronize(st));
+        nG = *(int32_t *)(ctx->h_pre_cnt.p + 2);
+        PCK(ctx->d_groups.ensure((size_t)nG + 1));
+        k_pre_groups<<<blocks_for(nG), kThreads, 0, st>>>(ctx->d_disc.p, ctx->d_pre_open.p, d_ng, ctx->d_pre_excl.p, ctx->d_pre_incl.p, nD, ctx->d_groups.p);
+        launches += 9;
+    } else PCK(ctx->d_groups.ensure(1));
+    PCK(cudaGetLastError());
+    ctx->pre_nD = (int32_t)nD; ctx->pre_nG = nG; ctx->pre_nP = (int32_t)nP;
+    ctx->gs_launches += launches;
+    if (ctx->shard_count > 1) {  // a range shard looks its first group up on the host (seed_stage: g_lo)
+        ctx->pre.groups.resize((size_t)nG);
+        if (nG) PCK(cudaMemcpyAsync(ctx->pre.groups.data(), ctx->d_groups.p, (size_t)nG * sizeof(Group), cudaMemcpyDeviceToHost, st));
+        PCK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+#undef PCK
+
 extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     if (!ctx || !c || c->n_reads < 0) return SQG_EINVAL;
     CK(cudaSetDevice(ctx->device));
@@ -914,6 +1018,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     CK(ctx->dc_ref_id.ensure(nb + 1)); CK(ctx->dc_ref_pos.ensure(nb + 1)); CK(ctx->dc_read_pos.ensure(nb + 1)); CK(ctx->dc_match_ref.ensure(nb + 1));
     CK(ctx->dc_match_read.ensure(nb + 1)); CK(ctx->dc_rev.ensure(nb + 1));
     CK(ctx->dc0_ref_pos.ensure(nb + 1)); CK(ctx->dc0_read_pos.ensure(nb + 1)); CK(ctx->dc0_match_ref.ensure(nb + 1)); CK(ctx->dc0_match_read.ensure(nb + 1));
+    CK(ctx->dc_first_low.ensure(nr + 1)); CK(ctx->dc_second_low.ensure(nr + 1)); CK(ctx->dc_multi.ensure(nr + 1));
     // the previous edge pass may still read the device copies: the uploads are ordered behind everything enqueued so far
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
@@ -926,6 +1031,27 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
         if (gpu_sort) hook = [ctx](sqh::SortKey *a, size_t n) { return device_sort_hook(ctx, a, n); };
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream3);  // a previous job's DMA out of ctx->pre must be over before the vectors are rewritten
+        static const bool dev_pre = !(getenv("SQG_DEVICE_PREPASS") && atoi(getenv("SQG_DEVICE_PREPASS")) == 0);
+        if (dev_pre && nr > 0 && nb > 0) {
+            // the chimeric arrays first, then the pre-pass itself on the device (sq_prepass.cuh): nothing of it runs on the cores
+            const sqg_chimeric &c = ctx->chim_view;
+            cudaError_t e = cudaSuccess;
+#define UPW(buf, src, cnt) do { if (e == cudaSuccess && (cnt)) e = cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream3); } while (0)
+            UPW(dc_read_off, c.read_off, nr + 1); UPW(dc_n_first, c.n_first, nr);
+            UPW(dc_first_total, c.first_total_len, nr); UPW(dc_second_total, c.second_total_len, nr);
+            UPW(dc_first_low, c.first_lowphred, nr); UPW(dc_second_low, c.second_lowphred, nr); UPW(dc_multi, c.multi_filter, nr);
+            UPW(dc_ref_id, c.blk_ref_id, nb); UPW(dc0_ref_pos, c.blk_ref_pos, nb); UPW(dc0_read_pos, c.blk_read_pos, nb);
+            UPW(dc0_match_ref, c.blk_match_ref, nb); UPW(dc0_match_read, c.blk_match_read, nb); UPW(dc_rev, c.blk_is_reverse, nb);
+#undef UPW
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chim, ctx->stream3);
+            ctx->chim_upload_err = (int)e;
+            int rc = e == cudaSuccess ? device_prepass(ctx, nr, nb) : (int)e;
+            if (rc == 0) rc = (int)cudaEventRecord(ctx->ev_pre, ctx->stream3);
+            ctx->pre_upload_err = rc;
+            ctx->prepass_stage.store(1, std::memory_order_release);
+            ctx->prepass_stage.store(2, std::memory_order_release);
+            return;
+        }
         ctx->pre.before_disc_realloc = [ctx]() {  // the page-lock must go before the storage does
             sqg_ctx::Pinned &pp = ctx->pre_pinned[0];
             if (pp.p) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream3); cudaHostUnregister(const_cast<void *>(pp.p)); pp.p = nullptr; pp.bytes = 0; }
@@ -954,6 +1080,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
             }
             if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pre, ctx->stream3);
             ctx->pre_upload_err = (int)e;
+            ctx->pre_nD = (int32_t)nD1 - 1; ctx->pre_nG = (int32_t)nG; ctx->pre_nP = (int32_t)nP;
         }
         ctx->prepass_stage.store(1, std::memory_order_release);  // finish_prepass() may go on
         // then the chimeric arrays themselves (needed by the edge pass only): from this thread, so that the caller's thread
@@ -976,7 +1103,11 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
 
 // join the host pre-pass and put its products (discordant blocks, groups, PartAlignPos) into HBM
 static int finish_prepass(sqg_ctx *ctx) {
-    while (ctx->prepass_stage.load(std::memory_order_acquire) < 1) std::this_thread::yield();  // the products; the thread may still be uploading
+    // the products (the thread may still be uploading the chimeric arrays): a short spin, then sleep -- a busy-waiting thread per
+    // process is exactly what several processes on one host cannot afford
+    for (int spins = 0; ctx->prepass_stage.load(std::memory_order_acquire) < 1; spins++) {
+        if (spins < 2000) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
     if (ctx->prepass_uploaded) return SQG_OK;
     if (ctx->pre_upload_err) { ctx->err = std::string("upload of the pre-pass products: ") + cudaGetErrorString((cudaError_t)ctx->pre_upload_err); return SQG_ECUDA; }
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));
@@ -1271,7 +1402,7 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
     const int32_t N = ctx->nt.n;
-    const int32_t nD = (int32_t)ctx->pre.disc.size() - 1;
+    const int32_t nD = ctx->pre_nD;
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     ChimDev cd;
     cd.n_reads = ctx->c_n_reads; cd.read_off = ctx->dc_read_off.p; cd.n_first = ctx->dc_n_first.p;
@@ -1431,7 +1562,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     rc = finish_prepass(ctx);
     if (rc) return rc;
     lap("wait for pre-pass + upload");
-    const int32_t nD = (int32_t)ctx->pre.disc.size() - 1, nG = (int32_t)ctx->pre.groups.size(), nP = (int32_t)ctx->pre.part_chr.size();
+    const int32_t nD = ctx->pre_nD, nG = ctx->pre_nG, nP = ctx->pre_nP;
     if (nD <= 0) FAIL(SQG_EUNSUPPORTED, "no discordant block in the chimeric reads: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
 
     PHASE_BEGIN("seed");
@@ -1461,6 +1592,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
         CK(cudaMemcpyAsync(ctx->h_counters.p + 4, ctx->d_counters.p + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         n_rest = ctx->h_counters.p[4];
+        lap("  seed: triggers + rest collect");
         if (n_rest <= rest_cap) break;
         rest_cap = n_rest + 1024;
     }
@@ -1508,6 +1640,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
         CK(cudaMemcpyAsync(h_trig.data(), ctx->d_trigger.p, (size_t)nG * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         g_hi = (int32_t)(std::lower_bound(h_trig.begin(), h_trig.end(), n) - h_trig.begin());
+        lap("  seed: rest sort + triggers back");
     }
     if (g_hi < g_lo) g_hi = g_lo;
     in.g_hi = g_hi;
@@ -1532,6 +1665,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     CK(cudaMemcpyAsync(ctx->h_counters.p + 5, ctx->d_counters.p + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int32_t n_isl = *(int32_t *)(ctx->h_counters.p + 5);
+    lap("  seed: island cuts");
     CK(ctx->d_cap_ops.ensure(2 * (size_t)n_isl + 4)); CK(ctx->d_cap_mar.ensure(n_isl + 2)); CK(ctx->d_off_ops.ensure(n_isl + 2)); CK(ctx->d_off_mar.ensure(n_isl + 2));
     CK(ctx->d_isl_nout.ensure(n_isl + 1)); CK(ctx->d_isl_gdone.ensure(n_isl + 1));
     CK(cudaMemsetAsync(ctx->d_cap_ops.p, 0, (n_isl + 2) * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->d_cap_mar.p, 0, (n_isl + 2) * 4, ctx->stream));
@@ -1550,6 +1684,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     CK(cudaMemcpyAsync(&tot[0], ctx->d_off_ops.p + n_isl, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&tot[1], ctx->d_off_mar.p + n_isl, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    lap("  seed: island caps + offsets");
     CK(ctx->d_ops.ensure(tot[0] + 1)); CK(ctx->d_margin.ensure(tot[1] + 1));
     int32_t *d_err = (int32_t *)(ctx->d_counters.p + 7), *d_nprefix = (int32_t *)(ctx->d_counters.p + 6);
     CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, 2 * sizeof(int64_t), ctx->stream));
@@ -1573,6 +1708,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     CK(cudaStreamSynchronize(ctx->stream));
     const int32_t n_heavy = ((int32_t *)(ctx->h_counters.p + 13))[0], n_light = ((int32_t *)(ctx->h_counters.p + 13))[1];
     ctx->n_heavy = n_heavy;
+    lap("  seed: prefix + heavy/light split");
     if (n_heavy > 1) {  // longest islands first: the kernel's critical path is its largest island
         // d_cap_ops is free again after the offset scans: sort scratch [keys | keys2]
         int32_t *k1 = ctx->d_cap_ops.p, *k2 = ctx->d_cap_ops.p + n_heavy;
@@ -1660,7 +1796,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
 static int finish_stage(sqg_ctx *ctx, std::vector<SeedNode> &seeds, HostLap &lap, int32_t **chr, int32_t **pos, int32_t **len, int64_t *n_nodes,
                         int32_t **count3, int32_t **sumlen3, int32_t *reads_other_nonempty) {
     const int64_t n = ctx->batch.n_rec;
-    const int32_t nG = (int32_t)ctx->pre.groups.size();
+    const int32_t nG = ctx->pre_nG;
     if (seeds.empty()) FAIL(SQG_EUNSUPPORTED, "no seed segment was produced: BuildNode_STAR is undefined there (SegmentGraph.cpp:757 on an empty vector)");
     PHASE_BEGIN("tile");
     int rc = tile_genome(ctx, seeds);
