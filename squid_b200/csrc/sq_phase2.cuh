@@ -107,6 +107,23 @@ __device__ __noinline__ int32_t conc_edges_generic(const BatchDesc *desc, const 
     return conc_edges_sized<kMaxBlocks>(b, p, nt, r, edges);
 }
 
+// The same for a record of a staged tile: blocks and record fields come from shared memory (`tb` lives there too).
+__device__ __noinline__ int32_t conc_edges_tile(const TileBatch *tbp, const BatchDesc *desc, const NodeTable *ntp, int64_t r, TileEdgeTable *edges) {
+    const TileBatch &tb = *tbp;
+    const Params &p = desc->p;
+    const NodeTable nt = *ntp;
+    if (!conc_builds_edges(tb, p, r)) return -2;
+    const uint32_t nb = tb.blk_off[r + 1] - tb.blk_off[r];
+    Blk F[4], S[4];
+    int32_t node[8];
+    if (nb > 3) return -5;  // (rare: left to the out-of-tile kernel, whose frame holds 16 blocks per mate)
+    ReadView rv; rv.F = F; rv.S = S;
+    bool is_first;
+    conc_load_read(tb, r, rv, is_first);
+    if (rv.nF + rv.nS == 0) return -2;
+    return read_edges(nt, p, rv, MODE_OTHER, is_first, false, 0, node, *edges) ? node[0] : -3;
+}
+
 // ReadsOther, the two rare cases (sq_depth_cover.cuh): an entry that starts d <= 2 bp right of the start of its segment m2 goes
 // into that segment's start mask; a block of <= 3 bp is not counted here but deferred to the second pass.  Out of line.
 __device__ __noinline__ bool depth_other_rare(uint32_t *omask, int4 *shorts, int32_t *n_short, int32_t short_cap, int32_t rid, int32_t st, int32_t l, int32_t m2, int32_t d, bool on) {
@@ -121,8 +138,9 @@ __device__ __noinline__ bool depth_other_rare(uint32_t *omask, int4 *shorts, int
     return false;
 }
 
-template <bool DO_DEPTH, bool DO_EDGES>
+template <bool DO_DEPTH, bool DO_EDGES, bool SLOW_IN_TILE>
 __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2Args a, int bulk_ok) {
+    __shared__ TileBatch s_tb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileStage &s = *reinterpret_cast<TileStage *>(smem_raw);
     __shared__ TileEdgeTable s_edges;
@@ -145,6 +163,7 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
     stage_wait<kP2Fields>(s, b, a.cls, tk);
     const bool staged = ti.nb >= 0;
     const TileBatch tb = tile_view(s, ti, b);
+    if (SLOW_IN_TILE && tid == 0) s_tb = tb;
     if (tid == 0) {
         // The segment that holds the tile's first block: sorted input keeps most of the tile (usually all of it) inside this
         // one segment, so it is looked up once and every block of the tile is first tested against it.  The window of
@@ -286,16 +305,42 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
             if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
         }
     }
-    // ---- the multi-block records that left the tile's segment go to k_edges_generic (one dense kernel over all of them) ----
+    // ---- the multi-block records that left the tile's segment ----------------------------------------------------------------
+    // SLOW_IN_TILE: processed right here, from the staged tile (a third of the records at the App. C block mix: dense enough to keep
+    // the tile's lanes busy, and their edges repeat the tile's other edges in its table).  Otherwise (and for the rare tile
+    // whose blocks were too many to stage, or a record with more than three blocks) they go to k_edges_generic's list.
     if (DO_EDGES) {
-        __shared__ int32_t s_slow_base;
-        const int ns = s_nslow;
-        if (tid == 0 && ns > 0) s_slow_base = atomicAdd(a.n_slow, ns);
-        __syncthreads();
-        if (ns > 0) {
-            const int32_t base_q = s_slow_base;
-            for (int q = tid; q < ns; q += kTileThreads)
-                if (base_q + q < a.slow_cap) a.slow_list[base_q + q] = (int32_t)(rec0 + s_slow[q]);
+        __shared__ int32_t s_slow_base, s_nleft;
+        int ns = s_nslow;
+        if (SLOW_IN_TILE && staged) {
+            if (tid == 0) s_nleft = 0;
+            __syncthreads();
+#pragma unroll 1
+            for (int q = tid; q < ns; q += kTileThreads) {
+                const int i = s_slow[q];
+                const int64_t r = rec0 + i;
+                const int32_t out = conc_edges_tile(&s_tb, a.desc, a.nt_dev, r, &s_edges);
+                if (out == -5) { s_mid[atomicAdd(&s_nleft, 1)] = (uint16_t)i; continue; }  // (s_mid is free again after pass B1)
+                a.res0[r] = out;
+                if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
+            }
+            __syncthreads();
+            ns = s_nleft;
+            if (tid == 0 && ns > 0) s_slow_base = atomicAdd(a.n_slow, ns);
+            __syncthreads();
+            if (ns > 0) {
+                const int32_t base_q = s_slow_base;
+                for (int q = tid; q < ns; q += kTileThreads)
+                    if (base_q + q < a.slow_cap) a.slow_list[base_q + q] = (int32_t)(rec0 + s_mid[q]);
+            }
+        } else {
+            if (tid == 0 && ns > 0) s_slow_base = atomicAdd(a.n_slow, ns);
+            __syncthreads();
+            if (ns > 0) {
+                const int32_t base_q = s_slow_base;
+                for (int q = tid; q < ns; q += kTileThreads)
+                    if (base_q + q < a.slow_cap) a.slow_list[base_q + q] = (int32_t)(rec0 + s_slow[q]);
+            }
         }
     }
     // ---- ReadsMain with the tile-local cursor -----------------------------------------------------------------------
@@ -379,31 +424,45 @@ __global__ void __launch_bounds__(128) k_edges_generic(P2Args a) {
     if (tid == 0) s_edges.spill = a.sink;
     __syncthreads();
     const int32_t n = *a.n_slow < a.slow_cap ? *a.n_slow : a.slow_cap;
-    for (int32_t q = blockIdx.x * 128 + tid; q < n; q += gridDim.x * 128) {
-        const int64_t r = a.slow_list[q];
-        const int32_t out = conc_edges_generic(a.desc, a.nt_dev, r, &s_edges);
-        a.res0[r] = out;
-        if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
-    }
-    __syncthreads();
-    int mine = 0;
-    for (int h = tid; h < kEdgeSlots; h += 128) mine += s_edges.cnt[h] != 0;
-    int inc = mine;
+    // A block takes CONTIGUOUS runs of the list (tiles append their records in one piece, so a run is a stretch of the genome): the
+    // run's edges repeat and are counted in the table, which is written out whenever it is more than half full -- never spilled
+    // edge by edge through the one global counter.
+    constexpr int32_t kRun = 128 * 4;
+    for (int32_t base = blockIdx.x * kRun; base < n; base += gridDim.x * kRun) {
+        const int32_t end = base + kRun < n ? base + kRun : n;
+        for (int32_t q = base + tid; q < end; q += 128) {
+            const int64_t r = a.slow_list[q];
+            const int32_t out = conc_edges_generic(a.desc, a.nt_dev, r, &s_edges);
+            a.res0[r] = out;
+            if (out == -3) { const int32_t k = atomicAdd(a.n_sens, 1); if (k < a.sens_cap) a.sens[k] = (int32_t)r; }
+        }
+        __syncthreads();
+        const bool last = base + (int64_t)gridDim.x * kRun >= n;
+        int mine = 0;
+        for (int h = tid; h < kEdgeSlots; h += 128) mine += s_edges.cnt[h] != 0;
+        int inc = mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
-    if (lane == 31) s_woff[warp] = inc;
-    __syncthreads();
-    if (tid == 0) {
-        int tot = 0;
-        for (int w = 0; w < 4; w++) { const int c = s_woff[w]; s_woff[w] = tot; tot += c; }
-        s_tot = tot;
-        if (tot > 0) s_at = atomicAdd(a.sink.counter, (unsigned long long)tot);
-    }
-    __syncthreads();
-    if (s_tot > 0) {
-        long long at = (long long)s_at + s_woff[warp] + inc - mine;
-        for (int h = tid; h < kEdgeSlots; h += 128)
-            if (s_edges.cnt[h]) { if (at < a.sink.cap) { a.sink.keys[at] = (uint64_t)s_edges.keys[h]; a.sink.w[at] = s_edges.cnt[h]; } at++; }
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) s_woff[warp] = inc;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < 4; w++) { const int c = s_woff[w]; s_woff[w] = tot; tot += c; }
+            if (!last && tot <= kEdgeSlots / 2) tot = 0;  // room left: keep counting
+            s_tot = tot;
+            if (tot > 0) s_at = atomicAdd(a.sink.counter, (unsigned long long)tot);
+        }
+        __syncthreads();
+        if (s_tot > 0) {
+            long long at = (long long)s_at + s_woff[warp] + inc - mine;
+            for (int h = tid; h < kEdgeSlots; h += 128)
+                if (s_edges.cnt[h]) {
+                    if (at < a.sink.cap) { a.sink.keys[at] = (uint64_t)s_edges.keys[h]; a.sink.w[at] = s_edges.cnt[h]; }
+                    at++;
+                    s_edges.keys[h] = kEmptyKey; s_edges.cnt[h] = 0;
+                }
+        }
+        __syncthreads();
     }
 }
 

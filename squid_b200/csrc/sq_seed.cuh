@@ -42,7 +42,7 @@ struct SeedOp {    // seed-segment emission of one island
                    // 2: the current last segment gets End = pos
     int32_t chr, pos, len;
 };
-struct RestBlock {  // ConcordRest candidate: non-first block of a concordant record, sorted by (chr,pos)
+struct RestBlock {  // ConcordRest candidate: non-first block of a concordant record; the table is ordered by owning group
     int32_t chr, pos, end, rec;
 };
 constexpr int32_t kIslandSlack = 70;  // > thresh*20 + 2*thresh, see island_cut()
@@ -61,7 +61,7 @@ struct SeedInputs {
     const Group *G; int32_t nG;
     const int64_t *trigger;         // per group: first kept record past its right end, or n_rec
     const int32_t *Pchr, *Ppos; int32_t nP;  // PartAlignPos sorted
-    const RestBlock *rest; int32_t n_rest;
+    const RestBlock *rest; const uint32_t *rest_g; int32_t n_rest;  // ConcordRest candidates binned by the group they can matter to (rest_g ascending)
     int32_t read_len;
     int64_t first_kept;
     long long *prof_out = nullptr;  // SQ_SEED_PROF builds: 12 int64 per island
@@ -488,21 +488,15 @@ struct SeedMachineT {
         return W::sum(cov);
     }
 
-    // ConcordRest coverage at `brk` for the group starting at sPos on chromosome chrG, records before rg (:471-473)
-    SQ_HD int32_t rest_coverage(int32_t chrG, int32_t sPos, int32_t brk, int64_t rg) const {
-        const int32_t lo_pos = sPos - in.read_len, hi_pos = brk - kSeedThresh;
+    // The ConcordRest candidates of group g: a block that starts in [start_g - ReadLen, right_g + ReadLen) belongs to g alone (the
+    // next group starts at least ReadLen right of right_g), and nothing a break of g looks at starts outside that range.
+    SQ_HD void rest_range(int32_t g, int32_t *lo_out, int32_t *hi_out) const {
         int32_t lo = 0, hi = in.n_rest;
-        while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
+        while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (in.rest_g[m] < (uint32_t)g) lo = m + 1; else hi = m; }
         int32_t lo2 = lo, hi2 = in.n_rest;
-        while (lo2 < hi2) { int32_t m = (lo2 + hi2) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < hi_pos)) lo2 = m + 1; else hi2 = m; }
-        int32_t cnt = 0;
-        for (int32_t k = lo + W::lane(); k < lo2; k += W::size()) {
-            const RestBlock &e = in.rest[k];
-            if (e.rec < rg && e.end >= brk + kSeedThresh) cnt++;
-        }
-        return W::sum(cnt);
+        while (lo2 < hi2) { const int32_t m = (lo2 + hi2) >> 1; if (in.rest_g[m] <= (uint32_t)g) lo2 = m + 1; else hi2 = m; }
+        *lo_out = lo; *hi_out = lo2;
     }
-
     // :420-434 for one PartialAlignCluster entry: the margin position it contributes, if any
     SQ_HD bool pc_margin_value(int64_t r, int32_t chrG, int32_t m0, int32_t curEndPos, int32_t *v) const {
         const int32_t thresh = kSeedThresh;
@@ -610,7 +604,7 @@ struct SeedMachineT {
         }
         W::sync();
     }
-    SQ_HD void tabulate_breaks(int32_t nM, int32_t ds, int32_t de, int32_t chrG, int32_t sPos, int64_t rg, int32_t szPC) {
+    SQ_HD void tabulate_breaks(int32_t g, int32_t nM, int32_t ds, int32_t de, int32_t chrG, int32_t sPos, int64_t rg, int32_t szPC) {
         const int32_t thresh = kSeedThresh, RL = in.read_len, cap = mcap();
         int32_t *t_sr = margin + cap, *t_pl = margin + 2 * cap, *t_pr = margin + 3 * cap, *t_cov = margin + 4 * cap, *t_rest = margin + 5 * cap;
         const DiscBlock *D = in.D;
@@ -663,17 +657,15 @@ struct SeedMachineT {
         }
         {   // ConcordRest (:471-473): blocks of records before rg that start at/after group start - ReadLen
             const int32_t lo_pos = sPos - RL;
-            int32_t lo = 0, hi = in.n_rest;
-            while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
-            int32_t lo2 = lo, hi2 = in.n_rest;
-            while (lo2 < hi2) { int32_t m = (lo2 + hi2) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < pmax)) lo2 = m + 1; else hi2 = m; }
+            int32_t lo, lo2;
+            rest_range(g, &lo, &lo2);
             for (int32_t base = lo; base < lo2; base += W::size()) {
                 const int32_t k = base + W::lane();
                 bool on = false;
                 int32_t ja = 0, jb = 0;
                 if (k < lo2) {
                     const RestBlock e = in.rest[k];
-                    if (e.rec < rg) { on = true; ja = m_upper(nM, e.pos + kSeedThresh); jb = m_upper(nM, e.end - kSeedThresh); }
+                    if (e.rec < rg && e.pos >= lo_pos && e.pos < pmax) { on = true; ja = m_upper(nM, e.pos + kSeedThresh); jb = m_upper(nM, e.end - kSeedThresh); }
                 }
                 W::add_range(t_rest, ja, jb, on);
             }
@@ -690,7 +682,7 @@ struct SeedMachineT {
     // depends on what the break loop emits) are compacted in increasing order for the short sequential pass.
     SQ_HD int32_t didx(int32_t x, int32_t P_lo, int32_t R) const { const int32_t i = x - P_lo; return i < 0 ? 0 : (i > R ? R : i); }
     // returns the number of candidate breaks; CAND = (position, support) pairs
-    SQ_HD int32_t tabulate_dense(int32_t nM, int32_t P_lo, int32_t R, int32_t ds, int32_t de, int32_t chrG, int32_t sPos, int64_t rg, int32_t szPC, int32_t *CAND) {
+    SQ_HD int32_t tabulate_dense(int32_t g, int32_t nM, int32_t P_lo, int32_t R, int32_t ds, int32_t de, int32_t chrG, int32_t sPos, int64_t rg, int32_t szPC, int32_t *CAND) {
         const int32_t thresh = kSeedThresh, RL = in.read_len;
         int32_t *H = margin + mcap(), *PL = H + (R + 2), *PR = PL + (R + 2), *COV = PR + (R + 2), *REST = COV + (R + 2);
         const DiscBlock *D = in.D;
@@ -754,17 +746,15 @@ struct SeedMachineT {
         }
         {   // ConcordRest (:471-473): blocks of records before rg that start at/after group start - ReadLen
             const int32_t lo_pos = sPos - RL;
-            int32_t lo = 0, hi = in.n_rest;
-            while (lo < hi) { int32_t m = (lo + hi) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < lo_pos)) lo = m + 1; else hi = m; }
-            int32_t lo2 = lo, hi2 = in.n_rest;
-            while (lo2 < hi2) { int32_t m = (lo2 + hi2) >> 1; const RestBlock &e = in.rest[m]; if (e.chr < chrG || (e.chr == chrG && e.pos < pmax)) lo2 = m + 1; else hi2 = m; }
+            int32_t lo, lo2;
+            rest_range(g, &lo, &lo2);
             for (int32_t base = lo; base < lo2; base += W::size()) {
                 const int32_t k = base + W::lane();
                 bool on = false;
                 int32_t ja = 0, jb = 0;
                 if (k < lo2) {
                     const RestBlock e = in.rest[k];
-                    if (e.rec < rg) { on = true; ja = didx(e.pos + thresh + 1, P_lo, R); jb = didx(e.end - thresh + 1, P_lo, R); }
+                    if (e.rec < rg && e.pos >= lo_pos && e.pos < pmax) { on = true; ja = didx(e.pos + thresh + 1, P_lo, R); jb = didx(e.end - thresh + 1, P_lo, R); }
                 }
                 W::add_range(REST, ja, jb, on);
             }
@@ -1142,7 +1132,7 @@ struct SeedMachineT {
             if (dense) n_dense++; else n_sparse++;
             if (dense) {
                 int32_t *CAND = margin + mcap() + 5 * (R + 2);
-                const int32_t nC = tabulate_dense(nM, P_lo, R, ds, de, chrG, in.D[grp.ds].pos, rg, szPC, CAND);
+                const int32_t nC = tabulate_dense(g, nM, P_lo, R, ds, de, chrG, in.D[grp.ds].pos, rg, szPC, CAND);
                 SQ_PROF_ADD(4);
                 for (int32_t ic = 0; ic < nC; ic++) {
                     const int32_t brk = CAND[2 * ic];
@@ -1159,7 +1149,7 @@ struct SeedMachineT {
                     ms = msearch;
                 }
                 SQ_PROF_ADD(3);
-                tabulate_breaks(nM, ds, de, chrG, in.D[grp.ds].pos, rg, szPC);
+                tabulate_breaks(g, nM, ds, de, chrG, in.D[grp.ds].pos, rg, szPC);
                 SQ_PROF_ADD(4);
                 const int32_t *t_sr = margin + mcap(), *t_pl = margin + 2 * mcap(), *t_pr = margin + 3 * mcap(), *t_cov = margin + 4 * mcap(), *t_rest = margin + 5 * mcap();
                 for (int32_t ib = 0; ib < nM;) {

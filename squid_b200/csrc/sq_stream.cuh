@@ -18,7 +18,7 @@ constexpr int kTileThreads = 128;    // threads per tile (kTile / kTileThreads r
 constexpr int kTileRPT = kTile / kTileThreads;
 constexpr int kWarpsPerTile = kTileThreads / 32;
 constexpr int kTileChunks = kTile / 32;  // 32-record chunks: chunk c = records [32c, 32c+32) of the tile
-constexpr int kTileBlkCap = 768;     // staged blocks per tile (K <= 1.48 with the 8-element alignment slack); denser tiles read HBM directly
+constexpr int kTileBlkCap = 1152;    // staged blocks per tile (K <= 2.2 with the 8-element alignment slack: all but ~0.1 % of the tiles at the App. C block mix, whose K varies from gene to gene); denser tiles read HBM directly
 
 // ---- mbarrier + bulk copy ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -123,42 +123,69 @@ __global__ void k_rest_mark(const Group *G, const DiscBlock *D, int32_t nG, int3
     if (b > last) b = last;
     for (int32_t k = a >> kRestBinShift; k <= (b >> kRestBinShift); k++) { const int32_t bin = off[grp.chr] + k; atomicOr(&bits[bin >> 5], 1u << (bin & 31)); }
 }
+// group of a candidate block at (c, q): the last group whose (start - ReadLen) lies at or left of it, if the block starts left of
+// that group's right end + ReadLen; -1 otherwise
+__device__ __forceinline__ int32_t rest_group_of(const Group *G, const DiscBlock *D, int32_t nG, int32_t read_len, int32_t c, int32_t q) {
+    int32_t lo = 0, hi = nG;
+    while (lo < hi) {
+        const int32_t m = (lo + hi) >> 1;
+        const Group g = G[m];
+        const int32_t s = D[g.ds].pos - read_len;
+        if (g.chr < c || (g.chr == c && s <= q)) lo = m + 1; else hi = m;
+    }
+    const int32_t gi = lo - 1;
+    if (gi < 0) return -1;
+    const Group g = G[gi];
+    return (g.chr != c || q >= g.right + read_len) ? -1 : gi;
+}
 __global__ void k_rest_collect(DevBatch b, const uint8_t *cls, const Group *G, const DiscBlock *D, int32_t nG, int32_t read_len, RestBins rb, const int32_t *ref_len,
-                               RestBlock *out, uint64_t *out_key, int64_t cap, int64_t *counter) {
+                               RestBlock *out, uint32_t *out_key, int64_t cap, int64_t *counter) {
     const int64_t r0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;  // four records per thread: one 32-bit load of their class bytes
-    if (r0 >= b.n_rec) return;
     uint32_t w = 0;
     if (r0 + 3 < b.n_rec) w = *reinterpret_cast<const uint32_t *>(cls + r0);
     else for (int k = 0; k < 4; k++) if (r0 + k < b.n_rec) w |= (uint32_t)cls[r0 + k] << (8 * k);
-    if (!(w & (0x01010101u * CLS_REST))) return;
-    for (int j = 0; j < 4; j++) {
-        if (!((w >> (8 * j)) & CLS_REST)) continue;  // CLS_CONC, a mate flag, >= 2 blocks
-        const int64_t r = r0 + j;
-        const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
-        const int32_t c = b.ref_id[r];
-        const int32_t last = ref_len[c] > 0 ? ref_len[c] : 0;
-        for (uint32_t k = o + 1; k < e; k++) {
-            const int32_t q = b.blk_ref_pos[k];
-            if (q < 0 || q > last) continue;  // (cannot lie in any group's range, which is clipped to the chromosome)
-            const int32_t bin = rb.off[c] + (q >> kRestBinShift);
-            if (!((rb.bits[bin >> 5] >> (bin & 31)) & 1u)) continue;
-            int32_t lo = 0, hi = nG;  // last group with (chr, start - RL) <= (c, q)
-            while (lo < hi) {
-                const int32_t m = (lo + hi) >> 1;
-                const Group g = G[m];
-                const int32_t s = D[g.ds].pos - read_len;
-                if (g.chr < c || (g.chr == c && s <= q)) lo = m + 1; else hi = m;
-            }
-            const int32_t gi = lo - 1;
-            if (gi < 0) continue;
-            const Group g = G[gi];
-            if (g.chr != c || q >= g.right + read_len) continue;
-            const int64_t slot = (int64_t)atomicAdd((unsigned long long *)counter, 1ull);
-            if (slot < cap) {
-                out[slot] = RestBlock{c, q, q + b.blk_match_ref[k], (int32_t)r};
-                out_key[slot] = ((uint64_t)(uint32_t)c << 32) | (uint32_t)q;
+    const bool any = (w & (0x01010101u * CLS_REST)) != 0;
+    if (!__any_sync(0xffffffffu, any)) return;
+    // pass 1: which (record, block) pairs qualify -- a bit each (4 records x up to 15 non-first blocks); pass 2 writes them to slots
+    // reserved with ONE atomic per warp (the single list counter serialises otherwise: tens of millions of candidates)
+    uint64_t hit = 0;
+    if (any)
+        for (int j = 0; j < 4; j++) {
+            if (!((w >> (8 * j)) & CLS_REST)) continue;  // CLS_CONC, a mate flag, >= 2 blocks
+            const int64_t r = r0 + j;
+            const uint32_t o = b.blk_off[r], e = b.blk_off[r + 1];
+            const int32_t c = b.ref_id[r];
+            const int32_t last = ref_len[c] > 0 ? ref_len[c] : 0;
+            for (uint32_t k = o + 1; k < e && k - o <= 15; k++) {
+                const int32_t q = b.blk_ref_pos[k];
+                if (q < 0 || q > last) continue;  // (cannot lie in any group's range, which is clipped to the chromosome)
+                const int32_t bin = rb.off[c] + (q >> kRestBinShift);
+                if (!((rb.bits[bin >> 5] >> (bin & 31)) & 1u)) continue;
+                if (rest_group_of(G, D, nG, read_len, c, q) >= 0) hit |= 1ull << (16 * j + (k - o));
             }
         }
+    const int cnt = __popcll(hit);
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if ((int)(threadIdx.x & 31) >= d) inc += u; }
+    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+    if (tot == 0) return;
+    long long base = 0;
+    if ((threadIdx.x & 31) == 31) base = (long long)atomicAdd((unsigned long long *)counter, (unsigned long long)tot);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int64_t slot = base + inc - cnt;
+    while (hit) {
+        const int bit = __ffsll((long long)hit) - 1;
+        hit &= hit - 1;
+        const int j = bit >> 4, kk = bit & 15;
+        const int64_t r = r0 + j;
+        const uint32_t k = b.blk_off[r] + kk;
+        const int32_t c = b.ref_id[r], q = b.blk_ref_pos[k];
+        if (slot < cap) {
+            out[slot] = RestBlock{c, q, q + b.blk_match_ref[k], (int32_t)r};
+            out_key[slot] = (uint32_t)rest_group_of(G, D, nG, read_len, c, q);
+        }
+        slot++;
     }
 }
 
@@ -1480,19 +1507,24 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             }
             // two launches of the same tile kernel, one per job: each half is small enough for the instruction cache, and
             // reading the batch twice is cheap next to that
-            CK(cudaFuncSetAttribute(k_assign_tiles<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-            CK(cudaFuncSetAttribute(k_assign_tiles<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            CK(cudaFuncSetAttribute(k_assign_tiles<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            CK(cudaFuncSetAttribute(k_assign_tiles<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            CK(cudaFuncSetAttribute(k_assign_tiles<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+            // multi-block records that leave their tile's segment: in the tile kernel, from shared memory (default), or all of them in
+            // k_edges_generic (SQG_SLOW_IN_TILE=0)
+            static const bool slow_in_tile = !(getenv("SQG_SLOW_IN_TILE") && atoi(getenv("SQG_SLOW_IN_TILE")) == 0);
             PHASE_BEGIN("k_assign");
             if (do_depth) {
                 PHASE_BEGIN("k_assign_depth");
-                k_assign_tiles<true, false><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
+                k_assign_tiles<true, false, false><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
                 ctx->launches++;
                 CK(cudaGetLastError());
                 PHASE_END("k_assign_depth");
             }
             if (do_edges) {
                 PHASE_BEGIN("k_assign_edges");
-                k_assign_tiles<false, true><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
+                if (slow_in_tile) k_assign_tiles<false, true, true><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
+                else k_assign_tiles<false, true, false><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
                 ctx->launches++;
                 CK(cudaGetLastError());
                 PHASE_END("k_assign_edges");
@@ -1598,8 +1630,8 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     }
     if (n_rest > 0) {
         size_t tb = 0;
-        int key_bits = 33;  // (chr << 32 | pos): only the bits a chromosome index can set
-        while (key_bits < 64 && (1ll << (key_bits - 32)) < (long long)ctx->params.n_ref) key_bits++;
+        int key_bits = 1;  // the owning group: the table is binned by group, not ordered inside a group
+        while (key_bits < 32 && (1ll << key_bits) < (long long)nG) key_bits++;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, key_bits, ctx->stream));
         ENSURE_TEMP(tb);
         CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp.p, tb, ctx->d_restkey.p, ctx->d_restkey2.p, ctx->d_rest.p, ctx->d_rest2.p, (int)n_rest, 0, key_bits, ctx->stream));
@@ -1613,7 +1645,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     in.ccmax = n > 0 ? ctx->d_ccmax.p : nullptr; in.cc_tile = kTile;
     in.D = ctx->d_disc.p; in.nD = nD; in.G = ctx->d_groups.p; in.nG = nG; in.trigger = ctx->d_trigger.p;
     in.Pchr = ctx->d_pchr.p; in.Ppos = ctx->d_ppos.p; in.nP = nP;
-    in.rest = ctx->d_rest2.p; in.n_rest = (int32_t)n_rest; in.read_len = ctx->params.read_len; in.first_kept = ctx->first_kept;
+    in.rest = ctx->d_rest2.p; in.rest_g = ctx->d_restkey2.p; in.n_rest = (int32_t)n_rest; in.read_len = ctx->params.read_len; in.first_kept = ctx->first_kept;
     // range shard (sqg_set_shard): the groups whose right end lies left of this batch's first kept record were triggered in
     // an earlier shard; when another shard follows, the pending segment of the last island is closed at the batch end
     int32_t g_lo = 0;

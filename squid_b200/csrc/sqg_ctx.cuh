@@ -176,7 +176,7 @@ struct sqg_ctx {
     // node building
     sq::DBuf<int64_t> d_trigger;
     sq::DBuf<sq::RestBlock> d_rest, d_rest2;
-    sq::DBuf<uint64_t> d_restkey, d_restkey2;
+    sq::DBuf<uint32_t> d_restkey, d_restkey2;
     sq::DBuf<int32_t> d_chimdiff; sq::HBuf<int32_t> h_chimdiff;  // rows (block, RefPos, ReadPos, MatchRef, MatchRead) of the trimmed chimeric blocks
     struct ChimPatch { int32_t k; int32_t v[4]; };
     std::vector<ChimPatch> chim_undo;  // loaded values of the blocks the last sqg_build_edges patched in the caller's arrays

@@ -117,19 +117,29 @@ int main(int argc, char **argv) {
         while (lo < n && !(cls[lo] & CLS_KEEP)) lo++;
         trig[g] = lo;
     }
+    // ConcordRest candidates, binned by group: a non-first block of a concordant record belongs to the last group whose
+    // (start - ReadLen) lies at or left of it, if it starts left of that group's right end + ReadLen
     std::vector<RestBlock> rest;
-    for (int64_t r = 0; r < n; r++) {
-        if (!(cls[r] & CLS_CONC) || !(b.flag[r] & 0xC0)) continue;
-        for (uint32_t k = b.blk_off[r] + 1; k < b.blk_off[r + 1]; k++) {
-            // keep only blocks that can matter for some group: start in [S_g - RL, right_g + RL)
-            const int32_t c = b.ref_id[r], q = b.blk_ref_pos[k];
-            bool near = false;
-            for (int32_t g = 0; g < nG && !near; g++)
-                if (pre.groups[g].chr == c && q >= pre.disc[pre.groups[g].ds].pos - p.read_len && q < pre.groups[g].right + p.read_len) near = true;
-            if (near) rest.push_back(RestBlock{c, q, q + b.blk_match_ref[k], (int32_t)r});
+    std::vector<uint32_t> rest_g;
+    {
+        std::vector<std::pair<uint32_t, RestBlock>> tmp;
+        for (int64_t r = 0; r < n; r++) {
+            if (!(cls[r] & CLS_CONC) || !(b.flag[r] & 0xC0)) continue;
+            for (uint32_t k = b.blk_off[r] + 1; k < b.blk_off[r + 1]; k++) {
+                const int32_t c = b.ref_id[r], q = b.blk_ref_pos[k];
+                int32_t gi = -1;
+                for (int32_t g = 0; g < nG; g++) {
+                    const Group &G = pre.groups[g];
+                    const int32_t s0 = pre.disc[G.ds].pos - p.read_len;
+                    if (G.chr < c || (G.chr == c && s0 <= q)) gi = g; else break;
+                }
+                if (gi < 0 || pre.groups[gi].chr != c || q >= pre.groups[gi].right + p.read_len) continue;
+                tmp.push_back({(uint32_t)gi, RestBlock{c, q, q + b.blk_match_ref[k], (int32_t)r}});
+            }
         }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<uint32_t, RestBlock> &a, const std::pair<uint32_t, RestBlock> &c) { return a.first < c.first; });
+        for (auto &x : tmp) { rest_g.push_back(x.first); rest.push_back(x.second); }
     }
-    std::stable_sort(rest.begin(), rest.end(), [](const RestBlock &a, const RestBlock &c) { return a.chr != c.chr ? a.chr < c.chr : a.pos < c.pos; });
 
     // ---- seed machine ----
     SeedMachine sm;
@@ -139,7 +149,7 @@ int main(int argc, char **argv) {
     sm.in.D = pre.disc.data(); sm.in.nD = nD; sm.in.G = pre.groups.data(); sm.in.nG = nG;
     sm.in.trigger = trig.data();
     sm.in.Pchr = pre.part_chr.data(); sm.in.Ppos = pre.part_pos.data(); sm.in.nP = (int32_t)pre.part_chr.size();
-    sm.in.rest = rest.data(); sm.in.n_rest = (int32_t)rest.size();
+    sm.in.rest = rest.data(); sm.in.rest_g = rest_g.data(); sm.in.n_rest = (int32_t)rest.size();
     sm.in.read_len = p.read_len;
     if (cc_tile > 0) { sm.in.ccmax = ccmax.data(); sm.in.cc_tile = cc_tile; }
     sm.in.dp_rec = dprec.data(); sm.in.n_dp = (int32_t)dprec.size(); sm.in.lmax = lmax; sm.in.n_rec = n; sm.in.first_kept = first_kept;
