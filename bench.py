@@ -444,7 +444,7 @@ def main():
         phases = {}
         for _ in range(steps):
             step(resident)
-            for ph in ("h2d", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_assign_depth", "k_assign_edges", "k_edges_generic", "k_cov_compact", "k_cov_count"):
+            for ph in ("h2d", "prepass", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_assign_depth", "k_assign_edges", "k_edges_generic", "k_cov_compact", "k_cov_count"):
                 v = g.phase_ms(ph)
                 if v >= 0:
                     phases[ph] = phases.get(ph, 0.0) + v / steps

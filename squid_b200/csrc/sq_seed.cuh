@@ -686,6 +686,7 @@ struct SeedMachineT {
         const int32_t thresh = kSeedThresh, RL = in.read_len;
         int32_t *H = margin + mcap(), *PL = H + (R + 2), *PR = PL + (R + 2), *COV = PR + (R + 2), *REST = COV + (R + 2);
         const DiscBlock *D = in.D;
+        SQ_PROF_T0();  // (profile builds: [0] tables + margins + discordant blocks, [1] ConcordantCluster window, [3] other windows, [5] scans + candidates)
         W::sync();
         for (int32_t i = W::lane(); i < 5 * (R + 2); i += W::size()) H[i] = 0;
         W::sync();
@@ -698,6 +699,17 @@ struct SeedMachineT {
         }
         const int32_t bmin = P_lo, bmax = P_lo + R - 1;
         const int32_t pmin = bmin + thresh - in.lmax, pmax = bmax - thresh;  // block starts that can span some break
+        // The window walks add +1/-1 at a handful of offsets over and over (sorted stream: hundreds of records per position in an
+        // expressed gene), and atomics on one address in HBM/L2 scratch complete one after the other.  When the caller has fast
+        // (shared) memory for them, the walks accumulate there and the sums are folded into the tables afterwards.
+        int32_t *COVw = COV, *RESTw = REST;
+        if (msearch && R + 2 <= msearch_cap) {
+            COVw = msearch;
+            if (2 * (R + 2) <= msearch_cap) RESTw = msearch + (R + 2);
+            for (int32_t i = W::lane(); i < (RESTw != REST ? 2 : 1) * (R + 2); i += W::size()) msearch[i] = 0;
+            W::sync();
+        }
+        SQ_PROF_ADD(0);
         if (st.offCC < rg) {  // ConcordantCluster window (:457-461); every record of [lo,hi) lies on chrG (sorted stream, rg is the group's trigger)
             const int64_t lo = lb_pos(st.offCC, rg, chrG, pmin), hi = lb_pos(lo, rg, chrG, pmax);
             constexpr int U = 8;
@@ -714,10 +726,11 @@ struct SeedMachineT {
                     const bool ok = (c[u] & (CLS_CONC | CLS_PART | CLS_DISPL)) == CLS_CONC;
                     int32_t l = (int32_t)fl[u];
                     if (ok && fl[u] == 65535u) l = in.b.blk_match_ref[in.b.blk_off[base + (int64_t)u * W::size() + W::lane()]];
-                    W::add_range(COV, didx(ps_[u] + thresh + 1, P_lo, R), didx(ps_[u] + l - thresh + 1, P_lo, R), ok);
+                    W::add_range(COVw, didx(ps_[u] + thresh + 1, P_lo, R), didx(ps_[u] + l - thresh + 1, P_lo, R), ok);
                 }
             }
         }
+        SQ_PROF_ADD(1);
         if (st.offPC < szPC) {  // PartialAlignCluster window (:465-469)
             const int32_t lo = lb_pc_pos(st.offPC, szPC, chrG, pmin), hi = lb_pc_pos(lo, szPC, chrG, pmax);
             for (int32_t base = lo; base < hi; base += W::size()) {
@@ -728,7 +741,7 @@ struct SeedMachineT {
                     const int64_t r = in.pc_rec[i];
                     if (!isDispl(r) && in.b.ref_id[r] == chrG) { on = true; const int32_t p0 = e_pos(r); ja = didx(p0 + thresh + 1, P_lo, R); jb = didx(p0 + e_len(r) - thresh + 1, P_lo, R); }
                 }
-                W::add_range(COV, ja, jb, on);
+                W::add_range(COVw, ja, jb, on);
             }
         }
         {   // displaced entries of either window
@@ -756,9 +769,15 @@ struct SeedMachineT {
                     const RestBlock e = in.rest[k];
                     if (e.rec < rg && e.pos >= lo_pos && e.pos < pmax) { on = true; ja = didx(e.pos + thresh + 1, P_lo, R); jb = didx(e.end - thresh + 1, P_lo, R); }
                 }
-                W::add_range(REST, ja, jb, on);
+                W::add_range(RESTw, ja, jb, on);
             }
         }
+        if (COVw != COV) {  // fold the fast accumulators into the tables (the discordant blocks and displaced entries went there directly)
+            W::sync();
+            for (int32_t i = W::lane(); i <= R; i += W::size()) { COV[i] += COVw[i]; if (RESTw != REST) REST[i] += RESTw[i]; }
+            W::sync();
+        }
+        SQ_PROF_ADD(3);
         scan_inplace(PL, R); scan_inplace(PR, R); scan_inplace(COV, R); scan_inplace(REST, R);
         // candidate breaks, in increasing position
         int32_t nC = 0;
@@ -784,6 +803,7 @@ struct SeedMachineT {
             nC += tot;
         }
         W::sync();
+        SQ_PROF_ADD(5);
         return nC;
     }
 

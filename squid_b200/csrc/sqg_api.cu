@@ -202,7 +202,8 @@ struct IsCutOp {
     __device__ bool operator()(int32_t g) const { return flag[g] != 0; }
 };
 // scratch each island needs: [2i] = op slots, [2i+1] = margin slots
-constexpr int32_t kHeavySpanDev = 1 << 14;  // islands spanning more records than this get a whole block instead of a warp
+constexpr int32_t kHeavySpanDev = 1 << 14;  // islands spanning more records than this get a whole block instead of a warp (measured: 1 << 12 moves the
+                                            // tail from the warps to the blocks and lengthens the kernel, 5.5 -> 6.6 ms)
 __global__ void k_island_caps(SeedInputs in, const int32_t *isl_start, int32_t n_isl, int32_t *cap_ops, int32_t *cap_mar, int32_t *span) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_isl) return;
@@ -266,7 +267,7 @@ constexpr int kHeavySpan = kHeavySpanDev;
 // 0.4-0.9 M records took 16 ms in clusters of 8 against 11 ms in single blocks (cluster barriers inside the chunked window
 // walks, 8x redundant scalar control).  Off by default until the walks are restructured around fewer barriers.
 constexpr int kGiantSpan = 0x7fffffff;
-constexpr int32_t kSeedMarginSmem = 8192;  // ints of shared memory per block for the sorted margins (32 KB)    // islands spanning more records than this get a whole block instead of a warp
+constexpr int32_t kSeedMarginSmem = 11264;  // ints of shared memory per block: the sorted margins / the window accumulators of the position-indexed tables (44 KB)    // islands spanning more records than this get a whole block instead of a warp
 struct IsHeavyOp {
     const int32_t *span; const int32_t *n_prefix; bool want_heavy;
     __device__ bool operator()(int32_t i) const { return i >= *n_prefix && ((span[i] > kHeavySpan) == want_heavy); }
@@ -1052,6 +1053,12 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
     ctx->chim_upload_err = 0;
     ctx->chim_upload_pending = true;
     ctx->prepass_stage.store(0);
+    {   // "prepass" phase timer: created here, on the caller's thread (the map is not touched by the pre-pass thread, only its events)
+        PhaseTimer &t = ctx->timers["prepass"];
+        if (!t.a) { CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); }
+        t.done = false;
+        ctx->prepass_timer = &t;
+    }
     ctx->prepass_worker.submit([ctx, nr, nb]() {
         sqh::SortHook hook;
         static const bool gpu_sort = !(getenv("SQG_GPU_SORT") && atoi(getenv("SQG_GPU_SORT")) == 0);
@@ -1062,7 +1069,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
         if (dev_pre && nr > 0 && nb > 0) {
             // the chimeric arrays first, then the pre-pass itself on the device (sq_prepass.cuh): nothing of it runs on the cores
             const sqg_chimeric &c = ctx->chim_view;
-            cudaError_t e = cudaSuccess;
+            cudaError_t e = cudaEventRecord(ctx->prepass_timer->a, ctx->stream3);
 #define UPW(buf, src, cnt) do { if (e == cudaSuccess && (cnt)) e = cudaMemcpyAsync(ctx->buf.p, (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream3); } while (0)
             UPW(dc_read_off, c.read_off, nr + 1); UPW(dc_n_first, c.n_first, nr);
             UPW(dc_first_total, c.first_total_len, nr); UPW(dc_second_total, c.second_total_len, nr);
@@ -1074,6 +1081,7 @@ extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
             ctx->chim_upload_err = (int)e;
             int rc = e == cudaSuccess ? device_prepass(ctx, nr, nb) : (int)e;
             if (rc == 0) rc = (int)cudaEventRecord(ctx->ev_pre, ctx->stream3);
+            if (rc == 0) { rc = (int)cudaEventRecord(ctx->prepass_timer->b, ctx->stream3); ctx->prepass_timer->done = rc == 0; }
             ctx->pre_upload_err = rc;
             ctx->prepass_stage.store(1, std::memory_order_release);
             ctx->prepass_stage.store(2, std::memory_order_release);
@@ -1510,9 +1518,11 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             CK(cudaFuncSetAttribute(k_assign_tiles<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
             CK(cudaFuncSetAttribute(k_assign_tiles<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
             CK(cudaFuncSetAttribute(k_assign_tiles<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-            // multi-block records that leave their tile's segment: in the tile kernel, from shared memory (default), or all of them in
-            // k_edges_generic (SQG_SLOW_IN_TILE=0)
-            static const bool slow_in_tile = !(getenv("SQG_SLOW_IN_TILE") && atoi(getenv("SQG_SLOW_IN_TILE")) == 0);
+            // multi-block records that leave their tile's segment: all of them in k_edges_generic (default), or in the tile kernel from
+            // shared memory (SQG_SLOW_IN_TILE=1).  Measured at the App. C block mix, 100 M pairs: 4.6 + 8.3 ms against 21.3 ms -- inside
+            // the tile kernel the generic rules stall on instruction fetch (ncu: no_instruction is the top stall) and the tile's warps
+            // wait at the barrier behind the one that drew the longest records (profiles/r2_ncu_summary.txt).
+            static const bool slow_in_tile = getenv("SQG_SLOW_IN_TILE") && atoi(getenv("SQG_SLOW_IN_TILE")) == 1;
             PHASE_BEGIN("k_assign");
             if (do_depth) {
                 PHASE_BEGIN("k_assign_depth");

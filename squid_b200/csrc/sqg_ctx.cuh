@@ -187,6 +187,7 @@ struct sqg_ctx {
     // the chimeric pre-pass on the device (sq_prepass.cuh)
     sq::DBuf<int32_t> d_pre_ndis, d_pre_pusher, d_pre_lastk, d_pre_open; sq::DBuf<int64_t> d_pre_off; sq::DBuf<uint64_t> d_pre_part, d_pre_part2, d_pre_endkey, d_pre_excl, d_pre_incl;
     sq::DBuf<uint8_t> d_pre_opens, dc_first_low, dc_second_low, dc_multi, d_temp3; sq::DBuf<int64_t> d_pre_cnt; sq::HBuf<int64_t> h_pre_cnt;
+    sq::PhaseTimer *prepass_timer = nullptr;
     int32_t pre_nD = 0, pre_nG = 0, pre_nP = 0;   // sizes of the pre-pass products (either path)
     sq::DBuf<sq::SeedOp> d_ops;
     sq::DBuf<sq::SeedOp> d_ops_dense;  // the islands' op lists without their unused capacity, island order
