@@ -17,6 +17,7 @@
 #ifndef SQ_PHASE1_CUH
 #define SQ_PHASE1_CUH
 #include "sq_classify.cuh"
+#include "sq_depth_cover.cuh"
 #include "sq_stream.cuh"
 
 namespace sq {
@@ -29,6 +30,7 @@ struct P1Out {
     uint8_t *cls;
     uint16_t *first_len;      // per record: length of the first kept block of a CLS_CONC record (65535 = too long for 16 bits), else 0
     TileAgg *agg;             // n_tiles
+    uint32_t *cov_nq; uint64_t *cov_qmax;  // n_tiles: records of the tile that qualify for phase 3 (sq_phase3.cuh), their maximum start key
     int32_t *ccmax;           // n_tiles: maximum end of the ConcordantCluster entries of the tile (kNoCcEnd: none; kCcWalkTile: several chromosomes)
     uint64_t *gate_word;      // n_tiles, zeroed: one-word chain of "1 + index of the last gate-passing record"
     int32_t *cand_rec; uint64_t *cand_key; int32_t *n_cand; int32_t cand_cap;
@@ -67,12 +69,12 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     __shared__ int32_t s_cmax[kTileChunks];   // per chunk: max key end, then the exclusive maximum before the chunk
     __shared__ int32_t s_pc[kWarpsPerTile], s_dp[kWarpsPerTile];
     __shared__ long long s_prev_carry;
-    __shared__ int32_t s_bad, s_lmax, s_minkeep, s_ccmax;
+    __shared__ int32_t s_bad, s_lmax, s_minkeep, s_ccmax, s_nq, s_qmax;
     int32_t *s_end = s.end_pos;               // per record: end of the first block if the record updates otherrightmost, else 0
     uint16_t *s_flen = s.total_len;           // per record: first_len (a record's total_len is only read by its own thread, before)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
-    if (tid == 0) { s_tile = atomicAdd(o.ticket, 1); s_bad = 0; s_lmax = 0; s_minkeep = kTile; s_ccmax = kNoCcEnd; }
+    if (tid == 0) { s_tile = atomicAdd(o.ticket, 1); s_bad = 0; s_lmax = 0; s_minkeep = kTile; s_ccmax = kNoCcEnd; s_nq = 0; s_qmax = -1; }
     __syncthreads();
     const int tile = s_tile;
     const StageTicket tk = stage_issue<kP1Fields>(s, b, nullptr, tile, bulk_ok != 0);
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     // single-chromosome tiles (all but a handful) compare 32-bit block ends; the others are finished by one thread below
     const int32_t chr_tile = s.ref_id[0];
     const bool single_chr = chr_tile >= 0 && s.ref_id[n - 1] == chr_tile;
-    int32_t flen_max = 0, npc = 0, ndp = 0, cc_max = kNoCcEnd;
+    int32_t flen_max = 0, npc = 0, ndp = 0, cc_max = kNoCcEnd, nq = 0, q_max = -1;
 #pragma unroll 1
     for (int j = 0; j < kTileRPT; j++) {
         const int i = j * kTileThreads + tid;
@@ -157,6 +159,16 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
             if (co.first_len > flen_max) flen_max = co.first_len;
             if (co.cc_end > cc_max) cc_max = co.cc_end;
         }
+        // phase 3 (ExactBPConcordantSupport's pass) keeps the gate-passing right-hand mates: counted here, per tile, so that its
+        // compaction kernel knows every tile's rank offset without a look-back chain
+        int32_t qs = -1;
+        if (i < n && (c & CLS_GATE)) {
+            const uint16_t f = s.flag[i];
+            const int32_t rid = s.ref_id[i], ps = s.pos[i], mr = s.mate_ref_id[i], mp = s.mate_pos[i];
+            if (cover_qualifies(c, f, rid, ps, mr, mp)) { qs = cover_start(f, rid, ps, mr, mp); if (qs < 0) qs = 0; }
+        }
+        nq += __popc(__ballot_sync(full, qs >= 0));
+        { const int32_t m = __reduce_max_sync(full, qs); if (m > q_max) q_max = m; }
         if (i < n) { s.cls[i] = c; s_end[i] = key_end; s_flen[i] = (uint16_t)(co_len < 65535 ? co_len : 65535); }
         const int chunk = j * kWarpsPerTile + warp;
         npc += __popc(__ballot_sync(full, (c & CLS_PART) != 0));
@@ -167,7 +179,8 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     }
     flen_max = __reduce_max_sync(full, flen_max);
     cc_max = __reduce_max_sync(full, cc_max);
-    if (lane == 0) { s_pc[warp] = npc; s_dp[warp] = ndp; if (flen_max > 0) atomicMax(&s_lmax, flen_max); if (cc_max > kNoCcEnd) atomicMax(&s_ccmax, cc_max); }
+    if (lane == 0) { s_pc[warp] = npc; s_dp[warp] = ndp; if (flen_max > 0) atomicMax(&s_lmax, flen_max); if (cc_max > kNoCcEnd) atomicMax(&s_ccmax, cc_max);
+                     if (nq) atomicAdd(&s_nq, nq); if (q_max >= 0) atomicMax(&s_qmax, q_max); }
     __syncthreads();
     if (warp == 0) {  // chunk maxima -> exclusive maximum before each chunk; the tile's aggregate
         int32_t inc = lane < kTileChunks ? s_cmax[lane] : 0;
@@ -236,6 +249,15 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     } else for (int i = 4 * tid; i < n; i++) { o.cls[rec0 + i] = s.cls[i]; o.first_len[rec0 + i] = s_flen[i]; }
     __syncthreads();
     if (tid == 0) {
+        o.cov_nq[tile] = (uint32_t)s_nq;
+        uint64_t qk = 0;
+        if (single_chr) { if (s_qmax >= 0) qk = chrpos_key(chr_tile, s_qmax); }
+        else for (int i = 0; i < n; i++)  // a tile that crosses a chromosome boundary: literally
+            if ((s.cls[i] & CLS_GATE) && cover_qualifies(s.cls[i], s.flag[i], s.ref_id[i], s.pos[i], s.mate_ref_id[i], s.mate_pos[i])) {
+                const uint64_t k = chrpos_key(s.ref_id[i], cover_start(s.flag[i], s.ref_id[i], s.pos[i], s.mate_ref_id[i], s.mate_pos[i]));
+                if (k > qk) qk = k;
+            }
+        o.cov_qmax[tile] = qk;
         o.ccmax[tile] = single_chr ? s_ccmax : kCcWalkTile;
         if (s_lmax > 0) atomicMax(o.lmax, s_lmax);
         if (s_minkeep < kTile) atomicMin(o.first_kept, (long long)(rec0 + s_minkeep));

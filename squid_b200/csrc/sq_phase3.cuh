@@ -20,20 +20,17 @@ struct CovTile {
 };
 
 constexpr int kCovTile = 2048, kCovThreads = 256, kCovRPT = kCovTile / kCovThreads, kCovWarps = kCovThreads / 32, kCovChunks = kCovTile / 32;
-__global__ void __launch_bounds__(kCovThreads) k_cov_compact(DevBatch b, const uint8_t *cls, Chain chain, int32_t *ticket, int32_t n_tiles,
-                                                              uint64_t *qkey, int32_t *qend, CovTile *tiles, int64_t *nq_out) {
-    __shared__ int s_tile;
+static_assert(kCovTile % kTile == 0, "a coverage tile is a whole number of classification tiles");
+// rank0[t] / incmax[t]: qualifying records before classification tile t / maximum start key up to and including it (scans of the
+// per-tile counts the classification pass left behind): every block knows where its records go, no tile waits for another.
+__global__ void __launch_bounds__(kCovThreads) k_cov_compact(DevBatch b, const uint8_t *cls, const int64_t *rank0, const uint64_t *incmax, int32_t n_ctiles, int32_t n_tiles,
+                                                              uint64_t *qkey, int32_t *qend, CovTile *tiles) {
     __shared__ int32_t s_cnt[kCovChunks];
-    __shared__ unsigned long long s_max[kCovWarps];
-    __shared__ long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int tile = s_tile;
+    const int tile = blockIdx.x;
     const int64_t rec0 = (int64_t)tile * kCovTile;
     uint64_t key[kCovRPT]; int32_t endp[kCovRPT]; unsigned qm[kCovRPT];
-    uint64_t mx = 0;
 #pragma unroll
     for (int j = 0; j < kCovRPT; j++) {
         const int64_t r = rec0 + j * kCovThreads + tid;
@@ -43,13 +40,11 @@ __global__ void __launch_bounds__(kCovThreads) k_cov_compact(DevBatch b, const u
             const uint16_t f = b.flag[r];
             const int32_t rid = b.ref_id[r], pos = b.pos[r], mrid = b.mate_ref_id[r], mpos = b.mate_pos[r];
             q = cover_qualifies(cls[r], f, rid, pos, mrid, mpos);
-            if (q) { key[j] = chrpos_key(rid, cover_start(f, rid, pos, mrid, mpos)); endp[j] = b.end_pos[r]; if (key[j] > mx) mx = key[j]; }
+            if (q) { key[j] = chrpos_key(rid, cover_start(f, rid, pos, mrid, mpos)); endp[j] = b.end_pos[r]; }
         }
         qm[j] = __ballot_sync(full, q);
         if (lane == 0) s_cnt[j * kCovWarps + warp] = __popc(qm[j]);
     }
-    mx = warp_max_u64(mx);
-    if (lane == 0) s_max[warp] = mx;
     __syncthreads();
     if (warp == 0) {
         // exclusive scan of the kCovChunks (= 64) chunk counts: two consecutive chunks per lane
@@ -57,22 +52,17 @@ __global__ void __launch_bounds__(kCovThreads) k_cov_compact(DevBatch b, const u
         int32_t inc = v0 + v1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(full, inc, d); if (lane >= d) inc += u; }
-        const int32_t tot = __shfl_sync(full, inc, 31);
         s_cnt[2 * lane] = inc - v0 - v1; s_cnt[2 * lane + 1] = inc - v1;
-        uint64_t tm = 0;
-#pragma unroll
-        for (int k = 0; k < kCovWarps; k++) if (s_max[k] > tm) tm = s_max[k];
-        uint64_t xa, xb;
-        chain_scan(chain, tile, tm, (uint64_t)(uint32_t)tot, &xa, &xb);
         if (lane == 0) {
-            s_base = (long long)xb;
-            CovTile t; t.rank0 = (int64_t)xb; t.incmax = xa > tm ? xa : tm;
+            const int ct0 = tile * (kCovTile / kTile);
+            int ct1 = ct0 + (kCovTile / kTile) - 1;
+            if (ct1 > n_ctiles - 1) ct1 = n_ctiles - 1;
+            CovTile t; t.rank0 = rank0[ct0]; t.incmax = incmax[ct1];
             tiles[tile] = t;
-            if (tile == n_tiles - 1) *nq_out = (int64_t)xb + tot;
         }
     }
     __syncthreads();
-    const int64_t base = s_base;
+    const int64_t base = rank0[tile * (kCovTile / kTile)];
 #pragma unroll
     for (int j = 0; j < kCovRPT; j++)
         if (qm[j] & (1u << lane)) {

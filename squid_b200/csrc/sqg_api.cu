@@ -714,9 +714,9 @@ int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int
     sqg_ctx *ctx = new (std::nothrow) sqg_ctx();
     if (!ctx) return SQG_ENOMEM;
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
     int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the cluster kernel must get its SMs before the block kernel fills them
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // (numerically lower = more urgent)
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SQG_ECUDA; }
     if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream_cov, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_cov_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -754,7 +754,7 @@ void sqg_destroy(sqg_ctx *ctx) {
     ctx->d_omask.release(); ctx->d_shorts.release(); ctx->d_other_off.release(); ctx->d_other_key.release(); ctx->d_other_idx.release(); ctx->d_other_len.release(); ctx->d_other_own.release(); ctx->d_chimdiff.release(); ctx->h_chimdiff.release(); ctx->d_restbits.release(); ctx->d_restoff.release(); ctx->d_reflen.release(); ctx->d_ops.release(); ctx->d_ops_dense.release(); ctx->h_ops.release(); ctx->d_cutflag.release(); ctx->d_isl.release(); ctx->d_cap_ops.release(); ctx->d_cap_mar.release();
     ctx->d_isl_nout.release(); ctx->d_isl_gdone.release(); ctx->d_span.release(); ctx->d_heavy.release(); ctx->d_light.release(); ctx->d_off_ops.release(); ctx->d_off_mar.release(); ctx->d_dp.release();
     ctx->d_margin.release(); ctx->d_seedstate.release();
-    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_ccmax.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
+    ctx->d_bin_off.release(); ctx->d_bin_seg.release(); ctx->d_flen.release(); ctx->d_tileagg.release(); ctx->d_ccmax.release(); ctx->d_cov_nq.release(); ctx->d_cov_qmax.release(); ctx->d_cov_rank0.release(); ctx->d_cov_incmax.release(); ctx->d_temp_cov.release(); ctx->d_desc.release(); ctx->d_cand_key.release(); ctx->d_chain64.release(); ctx->d_chain32.release(); ctx->d_nchr.release(); ctx->d_npos.release(); ctx->d_nend.release(); ctx->d_chr_first.release(); ctx->d_cnt3.release(); ctx->d_sum3.release();
     ctx->d_chain_used.release(); ctx->d_qend.release(); ctx->d_covtile.release(); ctx->d_slow.release(); ctx->d_head.release(); ctx->d_ew.release(); ctx->d_dtile.release(); ctx->d_ekeys.release(); ctx->d_ekeys2.release(); ctx->d_ukeys.release(); ctx->d_ecount.release(); ctx->d_sens.release();
     ctx->d_e_ind1.release(); ctx->d_e_ind2.release(); ctx->d_e_w.release(); ctx->d_e_heads.release();
     ctx->d_bpkey.release(); ctx->d_covM.release(); ctx->d_qkey.release(); ctx->d_chunks.release(); ctx->d_r0.release(); ctx->d_t.release(); ctx->d_cov.release(); ctx->d_bpchr.release(); ctx->d_bppos.release();
@@ -1185,14 +1185,14 @@ static int run_classify(sqg_ctx *ctx) {
     ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n; ctx->end_other = 0;
     if (n > 0) {
         const int64_t n_tiles = (n + kTile - 1) / kTile;
-        CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8)); CK(ctx->d_ccmax.ensure(n_tiles + 1));
+        CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8)); CK(ctx->d_ccmax.ensure(n_tiles + 1)); CK(ctx->d_cov_nq.ensure(n_tiles + 2)); CK(ctx->d_cov_qmax.ensure(n_tiles + 2));
         int64_t cand_cap = std::max<int64_t>({(int64_t)ctx->d_cand_key.cap, n / 16, (int64_t)1 << 20});
         int32_t n_cand = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             cand_cap = std::min<int64_t>(cand_cap, n + 1);
             CK(ctx->d_cand_key.ensure(cand_cap));
             P1Out o;
-            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.ccmax = ctx->d_ccmax.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
+            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.ccmax = ctx->d_ccmax.p; o.cov_nq = ctx->d_cov_nq.p; o.cov_qmax = ctx->d_cov_qmax.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
             o.cand_rec = ctx->d_scratch32.p; o.cand_key = ctx->d_cand_key.p; o.cand_cap = (int32_t)cand_cap;
             // counters: [0..1] totals n_gap, n_pc, n_dp (int32) | [2] first_kept | [3] lmax | [4] n_cand, ticket (int32) | [20] validation flags
             CK(cudaMemsetAsync(ctx->d_counters.p, 0, 5 * sizeof(int64_t), ctx->stream));
@@ -1347,19 +1347,26 @@ static int run_cov_compact(sqg_ctx *ctx) {
         cudaStream_t st = ctx->stream_cov;
         CK(cudaEventRecord(ctx->ev_cov_fork, ctx->stream));
         CK(cudaStreamWaitEvent(st, ctx->ev_cov_fork, 0));
-        Chain ch[1];
-        int32_t *ticket = nullptr;
         CK(ctx->d_qkey.ensure(n + 1)); CK(ctx->d_qend.ensure(n + 1)); CK(ctx->d_covtile.ensure(n_tiles + 1));  // (allocation synchronises: before the launches)
-        int rc = prepare_chains(ctx, 1, n_tiles, ch, &ticket, st);
+        // rank offsets and running maxima of the classification tiles: scans of the per-tile counts phase 1 left (no look-back chain)
+        const int64_t n_ct = (n + kTile - 1) / kTile;
+        CK(ctx->d_cov_rank0.ensure(n_ct + 2)); CK(ctx->d_cov_incmax.ensure(n_ct + 2));
+        size_t tb1 = 0, tb2 = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb1, ctx->d_cov_nq.p, ctx->d_cov_rank0.p, (int)(n_ct + 1), st));
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tb2, ctx->d_cov_qmax.p, ctx->d_cov_incmax.p, MaxU64(), (int)n_ct, st));
+        CK(ctx->d_temp_cov.ensure(std::max(tb1, tb2) + 256));
+        CK(cudaMemsetAsync(ctx->d_cov_nq.p + n_ct, 0, 4, st));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_temp_cov.p, tb1, ctx->d_cov_nq.p, ctx->d_cov_rank0.p, (int)(n_ct + 1), st));
+        CK(cub::DeviceScan::InclusiveScan(ctx->d_temp_cov.p, tb2, ctx->d_cov_qmax.p, ctx->d_cov_incmax.p, MaxU64(), (int)n_ct, st));
+        ctx->launches += 4;
+        int rc = phase_begin(ctx, "k_cov_compact", st);
         if (rc) return rc;
-        CK(cudaMemsetAsync(ctx->d_counters.p + 15, 0, sizeof(int64_t), st));
-        rc = phase_begin(ctx, "k_cov_compact", st);
-        if (rc) return rc;
-        k_cov_compact<<<(unsigned)n_tiles, kCovThreads, 0, st>>>(b, ctx->d_cls.p, ch[0], ticket, (int32_t)n_tiles, ctx->d_qkey.p, ctx->d_qend.p, ctx->d_covtile.p, ctx->d_counters.p + 15);
+        k_cov_compact<<<(unsigned)n_tiles, kCovThreads, 0, st>>>(b, ctx->d_cls.p, ctx->d_cov_rank0.p, ctx->d_cov_incmax.p, (int32_t)n_ct, (int32_t)n_tiles, ctx->d_qkey.p, ctx->d_qend.p, ctx->d_covtile.p);
         ctx->launches++;
         CK(cudaGetLastError());
         rc = phase_end(ctx, "k_cov_compact", st);
         if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->d_counters.p + 15, ctx->d_cov_rank0.p + n_ct, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(ctx->h_counters.p + 15, ctx->d_counters.p + 15, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ctx->ev_cov_done, st));
         ctx->cov_pending = true;
@@ -1599,8 +1606,6 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     int rc = run_classify(ctx);
     if (rc) return rc;
     lap("classify");
-    rc = run_cov_compact(ctx);  // independent of the segment table: overlaps the wait for the chimeric pre-pass
-    if (rc) return rc;
     rc = finish_prepass(ctx);
     if (rc) return rc;
     lap("wait for pre-pass + upload");
@@ -1766,6 +1771,11 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     long long *d_prof = nullptr;
     if (getenv("SQG_SEED_PROF_OUT")) { cudaMalloc(&d_prof, (size_t)n_isl * 12 * 8); cudaMemset(d_prof, 0, (size_t)n_isl * 12 * 8); cudaDeviceSynchronize(); in.prof_out = d_prof; }
 #endif
+    // Phase 3's compaction pass only needs the class bytes.  It is forked HERE, behind the short kernels of this stage and beside the
+    // island machine (latency-bound, a few resident warps per SM): enqueued right after the classification, its 10^5 blocks sat in
+    // front of the ConcordRest collection, which is on the critical path (5.7 ms instead of 1.4 ms).
+    rc = run_cov_compact(ctx);
+    if (rc) return rc;
     // the longest islands (sorted first) go to thread-block clusters on a second stream, concurrently with the rest
     int32_t n_giant = 0;
     if (n_heavy > 0) {
