@@ -5,15 +5,19 @@ segment-graph build, with % of HBM roofline).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
 
 One "step" = one pass of the hot path over one batch: BuildNode_STAR + BuildEdges + breakpoint coverage on
-synthetic sorted alignment records of the configs[1] shape (GRCh38 layout, ~0.5 % discordant).
+synthetic sorted alignment records of the configs[1] shape (GRCh38 layout, ~0.5 % discordant, SURVEY App. C block mix K = 1.35).
   value : whole-job pairs/s with the record batch already resident in HBM when the timed region starts
   e2e   : the same through the C ABI with HOST (pinned) buffers: H2D of the batch inside the timed region
-  roofline : dominant stream phase, algorithmic bytes (SURVEY.md §8d / DESIGN.md) / CUDA-event time / measured HBM peak
+  roofline : the kernel with the longest live CUDA-event time in the step: algorithmic bytes (SURVEY.md §8d / DESIGN.md §3) / that
+             time / measured HBM peak; every timed kernel is listed under roofline.kernels, the whole path under roofline.whole_path
+  parity   : CRC32 of every output of the step against the reference build's on the same stream (tests/golden/bench_crc.json);
+             a mismatch makes the run exit 3
   cpu_baseline : the reference's own BuildNode_STAR/BuildEdges/ExactBPConcordantSupport (oracle/_ref, single thread)
                  on a bounded sample of the same generator
 N > 1: weak scaling over N independent streams of that shape, one per rank (a cohort of N samples): every rank runs the whole
-path on its own stream, the per-rank edge tables are exchanged with NCCL all_gather and merge-reduced on the device.  (ONE
-stream cut into exact range shards -- bit-identical results for every N -- is measured by bench_sharded.py)
+path on its own stream, the per-rank edge tables are exchanged with NCCL all_gather and merge-reduced on the device.  The same
+run also times ONE stream (rank 0's) cut into N exact genomic-range shards -- bit-identical results for every N, checked against
+the pinned CRCs -- and reports it as `one_stream` (strong scaling).
 """
 from __future__ import annotations
 
@@ -418,7 +422,7 @@ def main():
         lap("edge exchange + breakpoints (cached host stand-in)" if world > 1 else "breakpoints (cached host stand-in)")
         cov = g.BPCoverage(bc, bp)
         lap("BPCoverage")
-        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "cov_chain_chunks", "edges_single_path", "edges_generic_path")}
+        state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "cov_chain_chunks", "edges_single_path", "edges_generic_path", "slow_records", "qualifying_records", "short_other_blocks", "unstable_depth_blocks", "device_sort_status")}
         state["last"] = (nodes, edges, cov)
         state.update(n_nodes=int(nodes.Chr.shape[0]), n_edges=int(edges.Ind1.shape[0]), n_bp=int(bc.shape[0]), cov_sum=int(cov.sum()),
                      d2h=int(nodes.Chr.nbytes * 3 + nodes.count3.nbytes * 2 + edges.Ind1.nbytes * 3 + edges.Ind1.shape[0] + cov.nbytes))
@@ -444,7 +448,7 @@ def main():
         phases = {}
         for _ in range(steps):
             step(resident)
-            for ph in ("h2d", "prepass", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_assign", "k_assign_depth", "k_assign_edges", "k_edges_generic", "k_cov_compact", "k_cov_count"):
+            for ph in ("h2d", "prepass", "classify", "seed", "tile", "depth_edges", "edge_sort", "coverage", "k_classify", "k_seed_islands", "k_assign", "k_assign_depth", "k_assign_edges", "k_edges_generic", "k_cov_compact", "k_cov_count"):
                 v = g.phase_ms(ph)
                 if v >= 0:
                     phases[ph] = phases.get(ph, 0.0) + v / steps
@@ -474,28 +478,44 @@ def main():
         case0, chim00 = (case, chim0) if rank == 0 else stream_case(P_req, seed0)  # every rank holds ALL chimeric reads of the one stream
         one_stream = one_stream_leg(args, rank, world, local, dev, batch if rank == 0 else None, chim00, case0, max(1, min(args.steps, 5)), 2)
 
-    # ---- roofline of the dominant stream phase --------------------------------------------------------------
+    # ---- roofline ------------------------------------------------------------------------------------------------------
+    # Every timed kernel with its algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md §3): the stream kernels read the whole
+    # batch (32 B per record + 12 B per aligned block), phase 3 its 24-byte subset, then 12 B per qualifying record; the generic
+    # edge kernel the records it is handed (32 B + 12 B per block of each).  The seed machine has no streaming figure: it walks
+    # the window records of its islands (7 B each, several times) and is bound by dependent-load latency, not by bytes.
     K = NB / R
-    # algorithmic bytes per launch of the stream kernels: phase 1 and phase 2 read the whole batch
-    # (32 B/record + 12 B/block), phase 3 the 24-byte subset of the qualifying half
-    # (k_assign_depth and k_assign_edges are two launches of the tile kernel, each over the whole batch; phase 3 is the compaction
-    # pass over the 24-byte subset plus the 12-byte pass over the compacted pairs)
-    alg = {"k_classify": 32 * R + 12 * NB, "k_assign_depth": 32 * R + 12 * NB, "k_assign_edges": 32 * R + 12 * NB, "k_cov_compact": 24 * R}
-    # dram__bytes_read + dram__bytes_write per record from the ncu --set full capture (profiles/r1_ncu_summary_20Mpairs.txt)
-    traffic = {"k_classify": 42.8, "k_assign_depth": 36.2, "k_assign_edges": 44.3, "k_cov_compact": 28.4}
+    st_ = state.get("stats", {})
+    n_slow = max(0, st_.get("slow_records", 0)); nq = max(0, st_.get("qualifying_records", 0))
+    alg = {"k_classify": 32 * R + 12 * NB, "k_assign_depth": 32 * R + 12 * NB, "k_assign_edges": 32 * R + 12 * NB, "k_cov_compact": 24 * R,
+           "k_edges_generic": int(n_slow * (32 + 12 * max(2.0, K))), "k_cov_count": 12 * nq, "k_seed_islands": None}
+    # DRAM bytes per record of each kernel from this round's `ncu --set full` capture (profiles/r2_traffic.json, written by
+    # tests/tools/ncu_summary.py from the committed capture; dram__bytes_read.sum + dram__bytes_write.sum over the records of that run)
+    traffic_pr = {}
+    try:
+        traffic_pr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["dram_bytes_per_record"]
+    except Exception:
+        pass
     peak, peak_src = measured_peak_gbs()
-    stream = {k: v for k, v in phases.items() if k in alg}
-    top = max(stream, key=stream.get) if stream else None
+    timed = {k: v for k, v in phases.items() if k in alg}
+    top = max(timed, key=timed.get) if timed else None
+    per_kernel = {}
+    for k, v in timed.items():
+        gb = alg[k] / (v * 1e-3) / 1e9 if alg[k] else None
+        per_kernel[k] = {"ms": v, "alg_bytes": alg[k], "GBps": gb, "frac": gb / peak if gb else None,
+                         "dram_traffic_bytes": traffic_pr[k] * R if k in traffic_pr else None}
+    b_alg_pair = (2 * (32 * R + 12 * NB) + 24 * R) / P
+    # phases are disjoint intervals of the main stream; the coverage compaction runs beside the island machine on its own stream
+    total_gpu_ms = sum(v for k, v in phases.items() if not k.startswith("k_") and k not in ("prepass", "h2d"))
+    whole = (b_alg_pair * P / sec) / 1e9
     roof = None
     if top:
-        ach = alg[top] / (stream[top] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic[top] * R if traffic.get(top) else None,
-                "peak_source": peak_src, "alg_bytes_per_launch": alg[top], "ms": stream[top],
-                "note": "dominant STREAM kernel of the step, timed live with CUDA events; k_classify shares the SMs with the chimeric pre-pass sort (own stream, highest priority), which costs it ~0.6 ms against its stand-alone 5.05 ms (profiles/r1_launches_100M_final.csv); the latency-bound seed machine is listed in phases_ms",
-                "all_stream_kernels": {k: {"ms": v, "GBps": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak} for k, v in stream.items()}}
-    b_alg_pair = (2 * (32 * R + 12 * NB) + 24 * R) / P
-    # phases are disjoint stream intervals; the eager coverage compaction runs between "classify" and "seed"
-    total_gpu_ms = sum(v for k, v in phases.items() if not k.startswith("k_")) + phases.get("k_cov_compact", 0.0)
+        pk = per_kernel[top]
+        roof = {"bound": "hbm", "kernel": top, "achieved": pk["GBps"], "peak": peak, "unit": "GB/s", "frac": pk["frac"], "traffic": pk["dram_traffic_bytes"],
+                "peak_source": peak_src, "alg_bytes_per_launch": pk["alg_bytes"], "ms": pk["ms"],
+                "note": "the kernel with the longest live CUDA-event time in the step (all timed kernels are in `kernels`); traffic = DRAM bytes per record of this round's ncu capture x records of this run",
+                "whole_path": {"alg_bytes_per_pair": b_alg_pair, "achieved": whole, "frac": whole / peak, "ms_per_step": 1e3 * sec,
+                               "what": "B_alg = 2 (32 R + 12 B) + 24 R over the whole step, wall clock (SURVEY.md 8d)"},
+                "kernels": per_kernel}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg()
@@ -519,13 +539,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
             "config": {"workload": "synthetic GRCh38-layout sorted alignment records, %d read pairs per GPU, ~0.5%% discordant (configs[1])" % P,
-                       "pairs_per_gpu": P, "pairs_requested": P_req, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": "one independent stream per GPU x%d (exact range shards of one stream: bench_sharded.py)" % world,
+                       "pairs_per_gpu": P, "pairs_requested": P_req, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": ("one GPU" if world == 1 else "weak scaling: one independent stream (sample) per GPU x%d, edge tables all-gathered over NCCL and merge-reduced on the device; `one_stream` = rank 0's stream in %d exact genomic-range shards (strong scaling)" % (world, world)),
+                       "block_mix": "SURVEY App. C: K = %.3f aligned blocks per record (exon lengths %d-%d)" % (K, BENCH_EXON_LEN[0], BENCH_EXON_LEN[1]),
                        "l2": "inputs (%.1f GB) larger than L2" % (n_bytes / 1e9), "segments": state.get("n_nodes"), "edges": state.get("n_edges"), "breakpoints": state.get("n_bp"),
                        "breakpoint_source": "host stand-in for the out-of-scope stages between BuildEdges and ExactBPConcordantSupport, computed in the warm-up steps"},
             "e2e": {"value": world * P / sec_e2e, "unit": "read pairs/s", "h2d_bytes_per_step": n_bytes + sum(v.nbytes for v in chim0.a.values()), "d2h_bytes_per_step": state.get("d2h", 0), "ms_per_step": 1e3 * sec_e2e, "host_memory": host_kind},
             "roofline": roof,
-            "whole_path": {"alg_bytes_per_pair": b_alg_pair, "gpu_ms_in_kernels": total_gpu_ms,
-                           "frac_of_hbm_roofline_wall": (b_alg_pair * P / sec) / 1e9 / peak, "frac_of_hbm_roofline_kernels": (b_alg_pair * P / (total_gpu_ms * 1e-3)) / 1e9 / peak if total_gpu_ms else None},
+            "whole_path": {"alg_bytes_per_pair": b_alg_pair, "gpu_ms_in_phases": total_gpu_ms,
+                           "frac_of_hbm_roofline_wall": (b_alg_pair * P / sec) / 1e9 / peak, "frac_of_hbm_roofline_phases": (b_alg_pair * P / (total_gpu_ms * 1e-3)) / 1e9 / peak if total_gpu_ms else None},
             "phases_ms": phases, "host_timeline_ms": timeline, "bps_standin_ms_outside_timed_region": state.get("bps_standin_ms"), "phases_ms_e2e": phases_e2e, "stats": state.get("stats"),
             "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches), "gen_s": t_gen, "parity": parity,
         }

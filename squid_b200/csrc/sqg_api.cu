@@ -806,6 +806,8 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     if (n == "sensitive_reads") return ctx->n_sensitive;
     if (n == "raw_edges") return ctx->n_raw_edges;
     if (n == "r_break") return ctx->r_break;
+    if (n == "slow_records") return ctx->h_counters.p ? (int64_t)*(int32_t *)(ctx->h_counters.p + 18) : -1;  // records handled by k_edges_generic
+    if (n == "qualifying_records") return ctx->cov_nq;
     if (n == "short_other_blocks") return ctx->n_short_other;        // ReadsOther blocks of <= 3 bp in the last depth pass
     if (n == "unstable_depth_blocks") return ctx->n_unstable_other;  // ... whose segment depends on the tie order of sort(ReadsOther): resolved by replaying that sort
     if (n == "other_sort_status") return ctx->other_sort_status;
@@ -1799,10 +1801,12 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
         CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     }
     if (n_heavy - n_giant + n_light > 0) {
+        PHASE_BEGIN("k_seed_islands");
         k_seed_islands<<<(unsigned)(n_heavy - n_giant + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, 0, ctx->stream>>>(in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
                ctx->d_ops.p, ctx->d_margin.p, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, ctx->d_heavy.p + n_giant, n_heavy - n_giant, ctx->d_light.p, n_light);
         ctx->launches++;
         CK(cudaGetLastError());
+        PHASE_END("k_seed_islands");
     }
     if (n_giant > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     PHASE_END("seed");
