@@ -43,6 +43,13 @@ const int32_t *sqh_case_ref_len(const sqh_case *c);
  * (ref_pos, match_ref, read_pos, match_read) rows; returns the block count. */
 int32_t sqh_case_blocks(const sqh_case *c, int64_t r, int32_t *out4, int32_t max_blocks, int32_t *total_len, int32_t *lowphred_run);
 
+/* Packs an sqg_batch into its wire form (squid_b200.h: sqg_wire) on all cores.  pinned != 0: the arrays are page-locked
+ * (cudaHostAlloc) so that sqg_load_concordant_wire() copies them asynchronously.  SQG_EINVAL: aux >= 16, a record with more
+ * than 65535 blocks or a decreasing blk_off.  Release with sqh_free_wire(). */
+int sqh_pack_wire(const sqg_batch *batch, int32_t pinned, sqg_wire **out);
+void sqh_free_wire(sqg_wire *w);
+int64_t sqh_wire_bytes(const sqg_wire *w);
+
 /*
  * Replaces SegmentGraph_t::ExactBreakpoint + CountTop (src/SegmentGraph.cpp:3019-3081, 51-102; SURVEY.md §8 row a17, host side).
  * The chimeric reads -- as sqg_build_edges left them, i.e. already trimmed once -- are located on the FINAL graph

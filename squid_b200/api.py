@@ -44,6 +44,16 @@ class sqg_chimeric(C.Structure):
         "blk_ref_id", "blk_ref_pos", "blk_read_pos", "blk_match_ref", "blk_match_read", "blk_is_reverse")]
 
 
+class sqg_wire(C.Structure):  # include/squid_b200.h
+    _fields_ = [(k, C.c_int64) for k in ("n_rec", "n_blk", "n_tiles", "n_rec_exc", "n_blk_exc")] + [(k, C.c_void_p) for k in (
+        "tile_ref_id", "tile_pos", "tile_blk_off", "tile_rec_exc_off", "tile_blk_exc_off", "dpos", "span", "dmate", "flag", "total_len", "lowphred_run", "mapq", "aux_nblk",
+        "blk_dref", "blk_match_ref", "blk_read_pos", "blk_match_read", "rec_exc", "blk_exc")]
+
+
+WIRE_REC_EXC = np.dtype([("idx", "<u4"), ("ref_id", "<i4"), ("pos", "<i4"), ("mate_ref_id", "<i4"), ("mate_pos", "<i4"), ("end_pos", "<i4"), ("lowphred_run", "<u2"), ("n_blk", "<u2")])
+WIRE_BLK_EXC = np.dtype([("idx", "<u4"), ("ref_pos", "<i4"), ("match_ref", "<i4")])
+
+
 class sqh_options(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("phred33", "max_lowphred_len", "min_phred", "min_mapq", "concord_dist_pos", "concord_dist_idx")]
 
@@ -61,14 +71,14 @@ CHIM_DTYPES = {
 }
 
 EXPORTS = [
-    "sqg_create", "sqg_destroy", "sqg_last_error", "sqg_load_concordant", "sqg_attach_concordant_device", "sqg_load_chimeric",
+    "sqg_create", "sqg_destroy", "sqg_last_error", "sqg_load_concordant", "sqg_load_concordant_wire", "sqg_download_concordant", "sqg_attach_concordant_device", "sqg_load_chimeric",
     "sqg_build_nodes", "sqg_set_nodes", "sqg_build_edges", "sqg_bp_coverage", "sqg_edges_device_table", "sqg_merge_edge_tables",
     "sqg_phase_ms", "sqg_launch_count", "sqg_stat", "sqg_selftest_gpu_sort",
     "sqg_plan_shards", "sqg_set_shard", "sqg_shard_seeds", "sqg_shard_build", "sqg_shard_hint_state", "sqg_shard_redo_edges",
     "sqg_shard_cov_begin", "sqg_shard_cov_chain", "sqg_shard_cov_owned_t", "sqg_shard_cov_count",
     "sqh_default_options", "sqh_open_case", "sqh_open_concordant", "sqh_open_bam_case", "sqh_probe_bam", "sqh_close_case", "sqh_case_batch", "sqh_case_chimeric", "sqh_case_config",
     "sqh_case_n_ref", "sqh_case_ref_len", "sqh_case_blocks",
-    "sqh_exact_breakpoint", "sqh_free", "sqh_write_graph", "sqh_write_bedpe",
+    "sqh_exact_breakpoint", "sqh_free", "sqh_write_graph", "sqh_write_bedpe", "sqh_pack_wire", "sqh_free_wire", "sqh_wire_bytes",
 ]
 
 _lib = None
@@ -91,6 +101,11 @@ def lib() -> C.CDLL:
     L.sqg_last_error.argtypes = [_P]; L.sqg_last_error.restype = C.c_char_p
     L.sqg_load_concordant.argtypes = [_P, pp(sqg_batch), C.c_int64]
     L.sqg_attach_concordant_device.argtypes = [_P, pp(sqg_batch), C.c_int64]
+    L.sqg_load_concordant_wire.argtypes = [_P, pp(sqg_wire), C.c_int64]
+    L.sqg_download_concordant.argtypes = [_P, pp(sqg_batch)]
+    L.sqh_pack_wire.argtypes = [pp(sqg_batch), C.c_int32, pp(pp(sqg_wire))]
+    L.sqh_free_wire.argtypes = [pp(sqg_wire)]; L.sqh_free_wire.restype = None
+    L.sqh_wire_bytes.argtypes = [pp(sqg_wire)]; L.sqh_wire_bytes.restype = C.c_int64
     L.sqg_load_chimeric.argtypes = [_P, pp(sqg_chimeric)]
     L.sqg_build_nodes.argtypes = [_P, pp(_P), pp(_P), pp(_P), pp(C.c_int64), pp(_P), pp(_P), pp(C.c_int32)]
     L.sqg_set_nodes.argtypes = [_P, _P, _P, _P, C.c_int64]
@@ -191,6 +206,47 @@ class RecordBatch:
             else:
                 d[k] = self.a[k][lo:hi]
         return RecordBatch(d)
+
+
+class WireBatch:
+    """Wire form of a RecordBatch (include/squid_b200.h: sqg_wire), packed by the host library (sqh_pack_wire)."""
+
+    def __init__(self, batch: "RecordBatch", pinned: bool = False):
+        L = lib()
+        self._keep = batch
+        bs = batch.as_struct()
+        h = C.POINTER(sqg_wire)()
+        rc = L.sqh_pack_wire(C.byref(bs), 1 if pinned else 0, C.byref(h))
+        if rc != 0:
+            raise SquidB200Error(rc, "sqh_pack_wire failed")
+        self._h = h
+        self.nbytes = int(L.sqh_wire_bytes(h))
+
+    @property
+    def struct(self) -> sqg_wire:
+        return self._h.contents
+
+    def arrays(self) -> dict:
+        """numpy views of every wire array (tests decode them independently)."""
+        w = self.struct
+        nt = w.n_tiles
+        spec = {"tile_ref_id": (nt, np.int32), "tile_pos": (nt, np.int32), "tile_blk_off": (nt + 1, np.uint32), "tile_rec_exc_off": (nt + 1, np.uint32),
+                "tile_blk_exc_off": (nt + 1, np.uint32), "dpos": (w.n_rec, np.uint16), "span": (w.n_rec, np.uint16), "dmate": (w.n_rec, np.int16),
+                "flag": (w.n_rec, np.uint16), "total_len": (w.n_rec, np.uint16), "lowphred_run": (w.n_rec, np.uint8), "mapq": (w.n_rec, np.uint8),
+                "aux_nblk": (w.n_rec, np.uint8), "blk_dref": (w.n_blk, np.uint16), "blk_match_ref": (w.n_blk, np.uint16), "blk_read_pos": (w.n_blk, np.uint16),
+                "blk_match_read": (w.n_blk, np.uint16), "rec_exc": (w.n_rec_exc, WIRE_REC_EXC), "blk_exc": (w.n_blk_exc, WIRE_BLK_EXC)}
+        return {k: _np_from(getattr(w, k) or 0, n, dt) for k, (n, dt) in spec.items()}
+
+    def close(self):
+        if self._h:
+            lib().sqh_free_wire(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ChimericReads:
@@ -339,6 +395,22 @@ class SegmentGraph:
         self._batch = batch  # keep the host arrays alive for the duration of the copy
         s = batch.as_struct()
         self._ck(self.L.sqg_load_concordant(self._h, C.byref(s), first_record_index))
+
+    def load_concordant_wire(self, wire: "WireBatch", first_record_index: int = 0):
+        self._wire = wire
+        self._ck(self.L.sqg_load_concordant_wire(self._h, wire._h, int(first_record_index)))
+
+    def download_concordant(self) -> "RecordBatch":
+        """The resident batch copied back (check of the wire upload)."""
+        n, nb = int(self.stat("n_rec")), int(self.stat("n_blk"))
+        a = {"ref_id": np.empty(n, np.int32), "pos": np.empty(n, np.int32), "mate_ref_id": np.empty(n, np.int32), "mate_pos": np.empty(n, np.int32),
+             "end_pos": np.empty(n, np.int32), "flag": np.empty(n, np.uint16), "total_len": np.empty(n, np.uint16), "lowphred_run": np.empty(n, np.uint16),
+             "mapq": np.empty(n, np.uint8), "aux": np.empty(n, np.uint8), "blk_off": np.empty(n + 1, np.uint32), "blk_ref_pos": np.empty(nb, np.int32),
+             "blk_match_ref": np.empty(nb, np.int32), "blk_read_pos": np.empty(nb, np.uint16), "blk_match_read": np.empty(nb, np.uint16)}
+        out = RecordBatch(a)
+        s = out.as_struct()
+        self._ck(self.L.sqg_download_concordant(self._h, C.byref(s)))
+        return out
 
     def attach_concordant_device(self, dev_struct: sqg_batch, keepalive=None, first_record_index: int = 0):
         self._batch = keepalive

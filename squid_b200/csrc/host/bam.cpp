@@ -72,22 +72,22 @@ bool bgzf_inflate_all(const uint8_t *d, size_t len, RawBuf<uint8_t> &out, std::s
         member_off->push_back(total);
     }
     const int T = threads > 0 ? threads : omp_get_num_procs();
-    int bad = 0;
-#pragma omp parallel for num_threads(T) schedule(dynamic, 16)
+    int bad = 0;  // bit 0: corrupt deflate stream, bit 1: CRC mismatch
+#pragma omp parallel for num_threads(T) schedule(dynamic, 16) reduction(| : bad)
     for (long long i = 0; i < (long long)mem.size(); i++) {
         const Member &m = mem[(size_t)i];
         if (m.isize == 0) continue;  // the EOF marker
         z_stream z;
         memset(&z, 0, sizeof(z));
-        if (inflateInit2(&z, -15) != Z_OK) { bad = 1; continue; }
+        if (inflateInit2(&z, -15) != Z_OK) { bad |= 1; continue; }
         z.next_in = const_cast<Bytef *>(d + m.cdata); z.avail_in = (uInt)m.clen;
         z.next_out = out.data() + m.off; z.avail_out = m.isize;
         const int rc = inflate(&z, Z_FINISH);
-        if (rc != Z_STREAM_END || z.avail_out != 0) bad = 1;
-        else if (crc32(crc32(0L, Z_NULL, 0), out.data() + m.off, m.isize) != rd32(d + m.cdata + m.clen)) bad = 2;
+        if (rc != Z_STREAM_END || z.avail_out != 0) bad |= 1;
+        else if (crc32(crc32(0L, Z_NULL, 0), out.data() + m.off, m.isize) != rd32(d + m.cdata + m.clen)) bad |= 2;
         inflateEnd(&z);
     }
-    if (bad) { err = bad == 2 ? "BGZF block fails its CRC32" : "corrupt deflate stream in a BGZF block"; return false; }
+    if (bad) { err = !(bad & 1) ? "BGZF block fails its CRC32" : "corrupt deflate stream in a BGZF block"; return false; }
     return true;
 }
 
@@ -153,6 +153,8 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
                 if (bs < 32 || p + 4 + (size_t)bs > e) return false;
                 const uint8_t *q = b + p + 4;
                 const uint32_t l_name = q[8], n_cig = rd16(q + 12), l_seq = rd32(q + 16);
+                // the variable-length fields have to fit the record before their sizes enter the totals that size the allocations
+                if (32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 + l_seq > (uint64_t)bs) return false;
                 if (rec_out) { rec_out[t.rec] = p + 4; no[t.rec] = t.name; co[t.rec] = t.cig; so[t.rec] = t.seq; }
                 t.rec++; t.name += l_name ? l_name - 1 : 0; t.cig += n_cig; t.seq += l_seq;
                 p += 4 + (size_t)bs;
@@ -162,15 +164,15 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
         bool members_ok = S > 1;
         if (members_ok) {
             int fail = 0;
-#pragma omp parallel for num_threads(T) schedule(dynamic, 8)
-            for (long long k = 0; k < (long long)S; k++) { Tot t{0, 0, 0, 0}; if (!walk(seg[(size_t)k], seg[(size_t)k + 1], t, nullptr, nullptr, nullptr, nullptr)) fail = 1; tot[(size_t)k + 1] = t; }
+#pragma omp parallel for num_threads(T) schedule(dynamic, 8) reduction(| : fail)
+            for (long long k = 0; k < (long long)S; k++) { Tot t{0, 0, 0, 0}; if (!walk(seg[(size_t)k], seg[(size_t)k + 1], t, nullptr, nullptr, nullptr, nullptr)) fail |= 1; tot[(size_t)k + 1] = t; }
             members_ok = !fail;
         }
         if (!members_ok) {  // one sequential walk over the whole stream
             seg.assign({o, n}); S = 1;
             tot.assign(2, Tot{0, 0, 0, 0});
             Tot t{0, 0, 0, 0};
-            if (!walk(o, n, t, nullptr, nullptr, nullptr, nullptr)) { err = "truncated BAM alignment record"; break; }
+            if (!walk(o, n, t, nullptr, nullptr, nullptr, nullptr)) { err = "truncated or malformed BAM alignment record"; break; }
             tot[1] = t;
         }
         for (size_t k = 1; k <= S; k++) { tot[k].rec += tot[k - 1].rec; tot[k].name += tot[k - 1].name; tot[k].cig += tot[k - 1].cig; tot[k].seq += tot[k - 1].seq; }
@@ -191,7 +193,7 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
         if (!names.resize(name_off[R]) || !cigar.resize(cigar_off[R]) || !seq.resize(seq_off[R]) || !qual.resize(seq_off[R])) { err = "out of memory"; break; }
         int bad = 0;
         lap("offsets + allocation");
-#pragma omp parallel for num_threads(T) schedule(static)
+#pragma omp parallel for num_threads(T) schedule(static) reduction(| : bad)
         for (long long rr = 0; rr < (long long)R; rr++) {
             const size_t r = (size_t)rr;
             const uint8_t *p = b + rec[r];
@@ -205,7 +207,7 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
             const uint32_t l_seq = rd32(p + 16);
             mate_ref_id[r] = rdi32(p + 20); mate_pos[r] = rdi32(p + 24);
             const uint8_t *q = p + 32;
-            if (q + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > end) { bad = 1; continue; }
+            if (q + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > end) { bad |= 1; continue; }
             if (l_name) memcpy(names.data() + name_off[r], q, l_name - 1);
             q += l_name;
             memcpy(cigar.data() + cigar_off[r], q, 4ull * n_cig);
@@ -225,19 +227,18 @@ bool BamTable::open(const std::string &path, std::string &err, int threads) {
             while (q + 3 <= end) {  // aux: tag[2] type value
                 const char t0 = (char)q[0], t1 = (char)q[1], ty = (char)q[2];
                 const size_t sz = aux_size(ty, q + 3, end);
-                if (sz == 0 || q + 3 + sz > end) { bad = 1; break; }
+                if (sz == 0 || q + 3 + sz > end) { bad |= 1; break; }
                 if (t0 == 'X' && t1 == 'A') tags[r] |= 1;
                 else if (t0 == 'I' && t1 == 'H') {
                     tags[r] |= 2;
                     const uint8_t *v = q + 3;
+                    // BamTools' GetTag<int>: the destination is zeroed and the 1, 2 or 4 value bytes are copied over its low end --
+                    // no sign extension of the narrow signed types; 'A' (one character) converts as well
                     switch (ty) {
-                        case 'c': ih[r] = (int8_t)v[0]; break;
-                        case 'C': ih[r] = v[0]; break;
-                        case 's': ih[r] = (int16_t)rd16(v); break;
-                        case 'S': ih[r] = rd16(v); break;
-                        case 'i': ih[r] = rdi32(v); break;
-                        case 'I': ih[r] = (int32_t)rd32(v); break;
-                        default: break;  // GetTag<int> fails on a non-integer tag: the value stays 0
+                        case 'A': case 'c': case 'C': ih[r] = v[0]; break;
+                        case 's': case 'S': ih[r] = rd16(v); break;
+                        case 'i': case 'I': ih[r] = (int32_t)rd32(v); break;
+                        default: break;  // GetTag<int> fails on any other type: the value stays 0
                     }
                 }
                 q += 3 + sz;

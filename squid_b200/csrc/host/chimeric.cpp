@@ -128,8 +128,10 @@ int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::uno
             decode_alignment(a, cfg, d);
             if (d.blocks.size() > 16) { terr[t] = "record " + std::to_string(r) + " has more than 16 aligned blocks"; return; }
             out.end_pos[r] = a.end_pos();
-            out.total_len[r] = (uint16_t)std::min(d.total_len, 65535);
-            out.lowphred_run[r] = (uint16_t)std::min(d.lowphred_run, 65535);
+            // the batch keeps read coordinates in 16 bits (include/squid_b200.h): a longer read is refused, never wrapped
+            if (d.total_len > 65535) { terr[t] = "record " + std::to_string(r) + " is longer than 65535 bases (TotalLen " + std::to_string(d.total_len) + ")"; return; }
+            out.total_len[r] = (uint16_t)d.total_len;
+            out.lowphred_run[r] = (uint16_t)std::min(d.lowphred_run, 65535);  // <= total_len
             uint8_t aux = 0;
             if (a.tag_xa) aux |= SQG_AUX_XA;
             if (a.tag_ih && a.ih_value > 1) aux |= SQG_AUX_IH_GT1;
@@ -143,6 +145,9 @@ int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::uno
     for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
     for (auto &x : th) x.join();
     for (unsigned t = 0; t < nt; t++) if (!terr[t].empty()) { err = terr[t]; return SQG_EUNSUPPORTED; }
+    uint64_t total_blocks = 0;
+    for (uint64_t r = 0; r < n; r++) total_blocks += out.blk_off[r + 1];
+    if (total_blocks > 0xFFFFFFFFull) { err = "more than 2^32 - 1 aligned blocks in one batch: shard the stream"; return SQG_EUNSUPPORTED; }
     for (uint64_t r = 0; r < n; r++) out.blk_off[r + 1] += out.blk_off[r];
     const size_t nb = out.blk_off[n];
     out.blk_ref_pos.resize(nb); out.blk_match_ref.resize(nb); out.blk_read_pos.resize(nb); out.blk_match_read.resize(nb);

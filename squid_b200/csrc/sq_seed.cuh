@@ -65,6 +65,7 @@ struct SeedInputs {
     int32_t read_len;
     int64_t first_kept;
     long long *prof_out = nullptr;  // SQ_SEED_PROF builds: 12 int64 per island
+    unsigned long long *win_count = nullptr;  // (device) total number of window records the groups looked at: the machine's algorithmic input
     // range shard of one genome: groups before g_lo belong to earlier shards; when a later shard follows, the record right
     // after this batch is a 0-coverage record for the pending group (the shard planner guarantees it, sqg_plan_shards)
     int32_t g_lo = 0;
@@ -1074,6 +1075,9 @@ struct SeedMachineT {
             const int64_t lb = in.pc_rec[szPC - 1];
             if (D[ds].pos > e_pos(lb) + e_len(lb) + RL) st.offPC = szPC;
         }
+#ifdef __CUDA_ARCH__
+        if (in.win_count && W::lane() == 0 && rg > st.offCC) atomicAdd(in.win_count, (unsigned long long)(rg - st.offCC));
+#endif
         // :375-385
         curStartPos = D[ds].pos;
         {

@@ -27,6 +27,7 @@
 #include "sq_seed.cuh"
 #include "sq_gpusort.cuh"
 #include "sq_prepass.cuh"
+#include "sq_wire.cuh"
 #include "sqg_ctx.cuh"
 
 using namespace sq;
@@ -769,6 +770,8 @@ void sqg_destroy(sqg_ctx *ctx) {
     if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
     for (auto &pp : ctx->pre_pinned) if (pp.p) cudaHostUnregister(const_cast<void *>(pp.p));
     if (ctx->stream_cov) cudaStreamDestroy(ctx->stream_cov);
+    if (ctx->stream_up) cudaStreamDestroy(ctx->stream_up);
+    for (cudaEvent_t e : ctx->ev_up) cudaEventDestroy(e);
     if (ctx->ev_cov_fork) cudaEventDestroy(ctx->ev_cov_fork);
     if (ctx->ev_cov_done) cudaEventDestroy(ctx->ev_cov_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -806,6 +809,9 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
     if (n == "sensitive_reads") return ctx->n_sensitive;
     if (n == "raw_edges") return ctx->n_raw_edges;
     if (n == "r_break") return ctx->r_break;
+    if (n == "seed_window_records") return ctx->h_counters.p ? ctx->h_counters.p[29] : -1;  // concordant-cluster window sizes summed over the groups
+    if (n == "n_rec") return ctx->have_batch ? ctx->batch.n_rec : -1;
+    if (n == "n_blk") return ctx->have_batch ? ctx->batch.n_blk : -1;
     if (n == "slow_records") return ctx->h_counters.p ? (int64_t)*(int32_t *)(ctx->h_counters.p + 18) : -1;  // records handled by k_edges_generic
     if (n == "qualifying_records") return ctx->cov_nq;
     if (n == "short_other_blocks") return ctx->n_short_other;        // ReadsOther blocks of <= 3 bp in the last depth pass
@@ -821,6 +827,10 @@ int64_t sqg_stat(const sqg_ctx *ctx, const char *name) {
 extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t first_record_index) {
     if (!ctx || !hb || hb->n_rec < 0 || hb->n_blk < 0) return SQG_EINVAL;
     if (hb->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
+    // end points of the offset array (host memory: checked before anything is indexed with it; monotonicity and the 16-block limit
+    // are checked on the device, where an offset is compared with n_blk before it is used)
+    if (hb->n_rec > 0 && (hb->blk_off[0] != 0 || (int64_t)hb->blk_off[hb->n_rec] != hb->n_blk)) FAIL(SQG_EINVAL, "batch: blk_off does not span [0, n_blk]");
+    if (hb->n_rec == 0 && hb->n_blk != 0) FAIL(SQG_EINVAL, "batch: blocks without records");
     CK(cudaSetDevice(ctx->device));
     { const int rcj = cov_join(ctx); if (rcj) return rcj; }
     PHASE_BEGIN("h2d");
@@ -843,11 +853,111 @@ extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t fi
     b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
     PHASE_END("h2d");
     ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
+    ctx->wire_loaded = false;
+    return SQG_OK;
+}
+
+// Wire-form upload: the chunks go down a copy stream; the main stream waits for each chunk's event and widens it
+// (sq_wire.cuh) while the following chunks are on the bus.
+extern "C" int sqg_load_concordant_wire(sqg_ctx *ctx, const sqg_wire *w, int64_t first_record_index) {
+    if (!ctx || !w || w->n_rec < 0 || w->n_blk < 0 || w->n_rec_exc < 0 || w->n_blk_exc < 0) return SQG_EINVAL;
+    if (w->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
+    const int64_t n = w->n_rec, nb = w->n_blk, nt = w->n_tiles;
+    if (nt != (n + kWireTile - 1) / kWireTile || nb > 0xFFFFFFFFll) return SQG_EINVAL;
+    if (nt > 0) {  // the tile tables drive the copies and index the exception lists: checked here, everything else on the device
+        if (w->tile_blk_off[0] != 0 || (int64_t)w->tile_blk_off[nt] != nb || w->tile_rec_exc_off[0] != 0 || (int64_t)w->tile_rec_exc_off[nt] != w->n_rec_exc ||
+            w->tile_blk_exc_off[0] != 0 || (int64_t)w->tile_blk_exc_off[nt] != w->n_blk_exc) FAIL(SQG_EINVAL, "wire batch: tile tables do not match the counts");
+        bool mono = true;
+#pragma omp parallel for schedule(static) reduction(&& : mono)
+        for (long long t = 0; t < (long long)nt; t++)
+            mono = mono && w->tile_blk_off[t] <= w->tile_blk_off[t + 1] && w->tile_rec_exc_off[t] <= w->tile_rec_exc_off[t + 1] && w->tile_blk_exc_off[t] <= w->tile_blk_exc_off[t + 1];
+        if (!mono) FAIL(SQG_EINVAL, "wire batch: tile tables are not monotone");
+    } else if (nb != 0) return SQG_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    { const int rcj = cov_join(ctx); if (rcj) return rcj; }
+    if (!ctx->stream_up) CK(cudaStreamCreateWithFlags(&ctx->stream_up, cudaStreamNonBlocking));
+    PHASE_BEGIN("h2d");
+    const size_t n1 = n ? (size_t)n : 1, nb1 = nb ? (size_t)nb : 1, nt1 = (size_t)nt + 1;
+    CK(ctx->o_ref_id.ensure(n1)); CK(ctx->o_pos.ensure(n1)); CK(ctx->o_mate_ref_id.ensure(n1)); CK(ctx->o_mate_pos.ensure(n1)); CK(ctx->o_end_pos.ensure(n1));
+    CK(ctx->o_flag.ensure(n1)); CK(ctx->o_total_len.ensure(n1)); CK(ctx->o_lowphred_run.ensure(n1)); CK(ctx->o_mapq.ensure(n1)); CK(ctx->o_aux.ensure(n1));
+    CK(ctx->o_blk_off.ensure(n1 + 1));
+    CK(ctx->o_blk_ref_pos.ensure(nb1)); CK(ctx->o_blk_match_ref.ensure(nb1)); CK(ctx->o_blk_read_pos.ensure(nb1)); CK(ctx->o_blk_match_read.ensure(nb1));
+    CK(ctx->w_dpos.ensure(n1)); CK(ctx->w_span.ensure(n1)); CK(ctx->w_dmate.ensure(n1)); CK(ctx->w_lp.ensure(n1)); CK(ctx->w_an.ensure(n1));
+    CK(ctx->w_bdref.ensure(nb1)); CK(ctx->w_bmref.ensure(nb1));
+    CK(ctx->w_tile_ref.ensure(nt1)); CK(ctx->w_tile_pos.ensure(nt1)); CK(ctx->w_tile_blk.ensure(nt1)); CK(ctx->w_tile_rexc.ensure(nt1)); CK(ctx->w_tile_bexc.ensure(nt1));
+    CK(ctx->w_rec_exc.ensure(w->n_rec_exc ? (size_t)w->n_rec_exc : 1)); CK(ctx->w_blk_exc.ensure(w->n_blk_exc ? (size_t)w->n_blk_exc : 1));
+    CK(ctx->d_counters.ensure(32)); CK(ctx->h_counters.ensure(32));
+    cudaStream_t up = ctx->stream_up;
+    // the copy stream starts after everything the main stream still has queued on the previous batch
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(up, ctx->ev_fork, 0));
+    CK(cudaMemsetAsync(ctx->d_counters.p + 28, 0, sizeof(int64_t), ctx->stream));
+#define UPW(dst, src, off, cnt) do { if ((cnt) > 0) CK(cudaMemcpyAsync((dst) + (off), (src) + (off), (size_t)(cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, up)); } while (0)
+    if (nt > 0) {
+        UPW(ctx->w_tile_ref.p, w->tile_ref_id, 0, nt); UPW(ctx->w_tile_pos.p, w->tile_pos, 0, nt);
+        UPW(ctx->w_tile_blk.p, w->tile_blk_off, 0, nt + 1); UPW(ctx->w_tile_rexc.p, w->tile_rec_exc_off, 0, nt + 1); UPW(ctx->w_tile_bexc.p, w->tile_blk_exc_off, 0, nt + 1);
+        UPW(ctx->w_rec_exc.p, w->rec_exc, 0, w->n_rec_exc); UPW(ctx->w_blk_exc.p, w->blk_exc, 0, w->n_blk_exc);
+    }
+    WireDev wd;
+    wd.n_rec = n; wd.n_blk = nb; wd.n_tiles = nt;
+    wd.tile_ref_id = ctx->w_tile_ref.p; wd.tile_pos = ctx->w_tile_pos.p; wd.tile_blk_off = ctx->w_tile_blk.p; wd.tile_rec_exc_off = ctx->w_tile_rexc.p; wd.tile_blk_exc_off = ctx->w_tile_bexc.p;
+    wd.dpos = ctx->w_dpos.p; wd.span = ctx->w_span.p; wd.dmate = ctx->w_dmate.p; wd.lowphred_run = ctx->w_lp.p; wd.aux_nblk = ctx->w_an.p;
+    wd.blk_dref = ctx->w_bdref.p; wd.blk_match_ref16 = ctx->w_bmref.p; wd.rec_exc = ctx->w_rec_exc.p; wd.blk_exc = ctx->w_blk_exc.p;
+    WireOut wo;
+    wo.ref_id = ctx->o_ref_id.p; wo.pos = ctx->o_pos.p; wo.mate_ref_id = ctx->o_mate_ref_id.p; wo.mate_pos = ctx->o_mate_pos.p; wo.end_pos = ctx->o_end_pos.p;
+    wo.lowphred_run = ctx->o_lowphred_run.p; wo.aux = ctx->o_aux.p; wo.blk_off = ctx->o_blk_off.p; wo.blk_ref_pos = ctx->o_blk_ref_pos.p; wo.blk_match_ref = ctx->o_blk_match_ref.p;
+    wo.bad = (int32_t *)(ctx->d_counters.p + 28);
+    static const int n_chunks_env = getenv("SQG_WIRE_CHUNKS") ? atoi(getenv("SQG_WIRE_CHUNKS")) : 16;
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks_env, nt));
+    while ((int64_t)ctx->ev_up.size() < n_chunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
+    for (int64_t c = 0; c < n_chunks && nt > 0; c++) {
+        const int64_t t0 = nt * c / n_chunks, t1 = nt * (c + 1) / n_chunks;
+        if (t1 <= t0) continue;
+        const int64_t r0 = t0 * kWireTile, r1 = std::min<int64_t>(n, t1 * kWireTile), k0 = w->tile_blk_off[t0], k1 = w->tile_blk_off[t1];
+        UPW(ctx->w_dpos.p, w->dpos, r0, r1 - r0); UPW(ctx->w_span.p, w->span, r0, r1 - r0); UPW(ctx->w_dmate.p, w->dmate, r0, r1 - r0);
+        UPW(ctx->w_lp.p, w->lowphred_run, r0, r1 - r0); UPW(ctx->w_an.p, w->aux_nblk, r0, r1 - r0);
+        UPW(ctx->o_flag.p, w->flag, r0, r1 - r0); UPW(ctx->o_total_len.p, w->total_len, r0, r1 - r0); UPW(ctx->o_mapq.p, w->mapq, r0, r1 - r0);
+        UPW(ctx->w_bdref.p, w->blk_dref, k0, k1 - k0); UPW(ctx->w_bmref.p, w->blk_match_ref, k0, k1 - k0);
+        UPW(ctx->o_blk_read_pos.p, w->blk_read_pos, k0, k1 - k0); UPW(ctx->o_blk_match_read.p, w->blk_match_read, k0, k1 - k0);
+        CK(cudaEventRecord(ctx->ev_up[(size_t)c], up));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[(size_t)c], 0));
+        k_wire_decode<<<(unsigned)(t1 - t0), kWireTile, 0, ctx->stream>>>(wd, wo, t0);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+#undef UPW
+    if (n == 0) CK(cudaMemsetAsync(ctx->o_blk_off.p, 0, sizeof(uint32_t), ctx->stream));
+    DevBatch &b = ctx->batch;
+    b.n_rec = n; b.n_blk = nb;
+    b.ref_id = ctx->o_ref_id.p; b.pos = ctx->o_pos.p; b.mate_ref_id = ctx->o_mate_ref_id.p; b.mate_pos = ctx->o_mate_pos.p; b.end_pos = ctx->o_end_pos.p;
+    b.flag = ctx->o_flag.p; b.total_len = ctx->o_total_len.p; b.lowphred_run = ctx->o_lowphred_run.p; b.mapq = ctx->o_mapq.p; b.aux = ctx->o_aux.p;
+    b.blk_off = ctx->o_blk_off.p; b.blk_ref_pos = ctx->o_blk_ref_pos.p; b.blk_match_ref = ctx->o_blk_match_ref.p;
+    b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
+    PHASE_END("h2d");
+    ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
+    ctx->wire_loaded = true;
+    return SQG_OK;
+}
+
+// (test / diagnostic) the resident batch back into host arrays
+extern "C" int sqg_download_concordant(sqg_ctx *ctx, sqg_batch *out) {
+    if (!ctx || !out) return SQG_EINVAL;
+    if (!ctx->have_batch) FAIL(SQG_ESTATE, "no concordant batch loaded");
+    const DevBatch &b = ctx->batch;
+    if (out->n_rec != b.n_rec || out->n_blk != b.n_blk) FAIL(SQG_EINVAL, "sqg_download_concordant: n_rec / n_blk do not match the resident batch");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)b.n_rec, nb = (size_t)b.n_blk;
+#define DN(field, cnt) do { if ((cnt) > 0) CK(cudaMemcpyAsync((void *)out->field, b.field, (cnt) * sizeof(*b.field), cudaMemcpyDeviceToHost, ctx->stream)); } while (0)
+    DN(ref_id, n); DN(pos, n); DN(mate_ref_id, n); DN(mate_pos, n); DN(end_pos, n); DN(flag, n); DN(total_len, n); DN(lowphred_run, n); DN(mapq, n); DN(aux, n);
+    DN(blk_off, n + 1); DN(blk_ref_pos, nb); DN(blk_match_ref, nb); DN(blk_read_pos, nb); DN(blk_match_read, nb);
+#undef DN
+    CK(cudaMemcpyAsync(ctx->h_counters.p + 28, ctx->d_counters.p + 28, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->wire_loaded && *(int32_t *)(ctx->h_counters.p + 28)) FAIL(SQG_EINVAL, "wire batch is inconsistent (escape without an exception entry, or block counts that contradict the tile table)");
     return SQG_OK;
 }
 
 extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, int64_t first_record_index) {
-    if (!ctx || !db || db->n_rec < 0) return SQG_EINVAL;
+    if (!ctx || !db || db->n_rec < 0 || db->n_blk < 0) return SQG_EINVAL;
     if (db->n_rec >= 0x7fffff00ll) FAIL(SQG_EUNSUPPORTED, "more than 2^31 records per context: shard the stream");
     CK(cudaSetDevice(ctx->device));
     if (ctx->cov_pending) { CK(cudaStreamSynchronize(ctx->stream_cov)); ctx->cov_pending = false; }  // the previous batch's arrays belong to the caller again
@@ -857,6 +967,7 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     b.flag = db->flag; b.total_len = db->total_len; b.lowphred_run = db->lowphred_run; b.mapq = db->mapq; b.aux = db->aux;
     b.blk_off = db->blk_off; b.blk_ref_pos = db->blk_ref_pos; b.blk_match_ref = db->blk_match_ref; b.blk_read_pos = db->blk_read_pos; b.blk_match_read = db->blk_match_read;
     ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
+    ctx->wire_loaded = false;
     return SQG_OK;
 }
 
@@ -1030,9 +1141,13 @@ static int device_prepass(sqg_ctx *ctx, size_t nr, size_t nb) {
 #undef PCK
 
 extern "C" int sqg_load_chimeric(sqg_ctx *ctx, const sqg_chimeric *c) {
-    if (!ctx || !c || c->n_reads < 0) return SQG_EINVAL;
+    if (!ctx || !c || c->n_reads < 0 || c->n_blk < 0) return SQG_EINVAL;
     CK(cudaSetDevice(ctx->device));
+    // the pre-pass and the uploads index the block arrays through read_off: it has to start at 0, never decrease and end at n_blk
+    if (c->n_reads > 0 && (c->read_off[0] != 0 || (int64_t)c->read_off[c->n_reads] != c->n_blk)) FAIL(SQG_EINVAL, "chimeric reads: read_off does not span [0, n_blk]");
+    if (c->n_reads == 0 && c->n_blk != 0) FAIL(SQG_EINVAL, "chimeric reads: blocks without reads");
     for (int64_t i = 0; i < c->n_reads; i++) {
+        if (c->read_off[i + 1] < c->read_off[i]) FAIL(SQG_EINVAL, "chimeric reads: read_off decreases");
         const uint32_t nb = c->read_off[i + 1] - c->read_off[i], nf = c->n_first[i];
         if (nf > nb || nf > (uint32_t)kMaxBlocks || nb - nf > (uint32_t)kMaxBlocks) FAIL(SQG_EUNSUPPORTED, "chimeric read with more than 16 blocks in one mate");
     }
@@ -1220,7 +1335,9 @@ static int run_classify(sqg_ctx *ctx) {
             LAUNCH(k_tile_scan, 1, 1024, ctx->d_tileagg.p, (int32_t)n_tiles, totals, (uint64_t *)(ctx->d_counters.p + 21));
             CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(ctx->h_counters.p + 20, ctx->d_counters.p + 20, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (ctx->wire_loaded) CK(cudaMemcpyAsync(ctx->h_counters.p + 28, ctx->d_counters.p + 28, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->wire_loaded && *(int32_t *)(ctx->h_counters.p + 28)) FAIL(SQG_EINVAL, "wire batch is inconsistent (escape without an exception entry, or block counts that contradict the tile table)");
             const int32_t flags = *(int32_t *)(ctx->h_counters.p + 20);
             if (flags & 1) FAIL(SQG_EINVAL, "record with ref_id outside [-1, n_ref)");
             if (flags & 2) FAIL(SQG_EUNSUPPORTED, "mapped record with ref_id -1");
@@ -1737,6 +1854,8 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     CK(ctx->d_ops.ensure(tot[0] + 1)); CK(ctx->d_margin.ensure(tot[1] + 1));
     int32_t *d_err = (int32_t *)(ctx->d_counters.p + 7), *d_nprefix = (int32_t *)(ctx->d_counters.p + 6);
     CK(cudaMemsetAsync(ctx->d_counters.p + 6, 0, 2 * sizeof(int64_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p + 29, 0, sizeof(int64_t), ctx->stream));
+    in.win_count = (unsigned long long *)(ctx->d_counters.p + 29);
     // (a shard that follows one with an emitted segment starts with an inherited last segment: no sequential prefix)
     if (!(ctx->shard_index > 0 && ctx->shard_prior_emission) && n_isl > 0)
         LAUNCH(k_seed_prefix, 1, kSeedBlock, in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p, ctx->d_ops.p, ctx->d_margin.p,
@@ -1827,6 +1946,7 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     LAUNCH(k_ops_dense, 1, 1024, ctx->d_isl.p, n_isl, g_hi, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, ctx->d_off_ops.p, ctx->d_ops.p, ctx->d_ops_dense.p, ctx->d_counters.p + 24);
     CK(cudaMemcpyAsync(ctx->h_counters.p + 24, ctx->d_counters.p + 24, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters.p + 6, ctx->d_counters.p + 6, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters.p + 29, ctx->d_counters.p + 29, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<int64_t> trig_last(1, n);
     if (nG > 0) CK(cudaMemcpyAsync(trig_last.data(), ctx->d_trigger.p + (nG - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

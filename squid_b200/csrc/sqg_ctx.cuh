@@ -115,6 +115,17 @@ struct sqg_ctx {
     sq::DBuf<uint16_t> o_flag, o_total_len, o_lowphred_run, o_blk_read_pos, o_blk_match_read;
     sq::DBuf<uint8_t> o_mapq, o_aux;
     sq::DBuf<uint32_t> o_blk_off;
+    // wire-form upload (sqg_load_concordant_wire): staging of the delta-coded arrays, the copy stream and one event per chunk
+    sq::DBuf<uint16_t> w_dpos, w_span, w_bdref, w_bmref;
+    sq::DBuf<int16_t> w_dmate;
+    sq::DBuf<uint8_t> w_lp, w_an;
+    sq::DBuf<int32_t> w_tile_ref, w_tile_pos;
+    sq::DBuf<uint32_t> w_tile_blk, w_tile_rexc, w_tile_bexc;
+    sq::DBuf<sqg_wire_rec_exc> w_rec_exc;
+    sq::DBuf<sqg_wire_blk_exc> w_blk_exc;
+    cudaStream_t stream_up = nullptr;
+    std::vector<cudaEvent_t> ev_up;
+    bool wire_loaded = false;
 
     // classify products
     sq::DBuf<uint8_t> d_cls;
