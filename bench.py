@@ -90,12 +90,18 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -103,11 +109,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.time()])
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        # nvidia-smi takes a while to start, so it is started before the warm-up steps; only the samples that arrived between
+        # mark_begin() and mark_end() -- the timed region -- are used (all samples under load if that window caught none)
+        window = "timed region"
+        if self.t0 is not None and self.t1 is not None:
+            inside = [r for r in self.rows if self.t0 <= r[-1] <= self.t1]
+            if inside:
+                self.rows = inside
+            else:
+                window = "warm-up + timed steps (no sample fell inside the timed region)"
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -124,7 +139,7 @@ class ClockSampler:
                 sm, mx = [a], [b]
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def bps_from_graph(nodes, edges, min_weight=5):
@@ -324,6 +339,7 @@ def one_stream_leg(args, rank, world, local, dev, batch, chim0, case, steps, war
     st["pool"] = [api.ChimericReads(chim0.a) for _ in range(steps)]
     st["tl"] = {}
     sg.rounds = {"seeds": 0, "hints": 0, "chain": 0}
+    sg.detail_ms = {}
     barrier()
     t = time.perf_counter()
     for _ in range(steps):
@@ -333,7 +349,8 @@ def one_stream_leg(args, rank, world, local, dev, batch, chim0, case, steps, war
     tt = torch.tensor([sec], dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     sec = float(tt.item())
-    per_rank = comm.allgather([{"rank": rank, "records": int(cuts[rank + 1] - cuts[rank]), "host_timeline_ms": {k: round(v / steps, 2) for k, v in st["tl"].items()}}])
+    per_rank = comm.allgather([{"rank": rank, "records": int(cuts[rank + 1] - cuts[rank]), "host_timeline_ms": {k: round(v / steps, 2) for k, v in st["tl"].items()},
+                                "detail_ms": {k: round(v / steps, 2) for k, v in sg.detail_ms.items()}}])
     out = None
     if rank == 0:
         R = cuts[-1]
@@ -394,25 +411,37 @@ def main():
     P_req, P = P, R // 2  # the generator drops pairs with <4-bp blocks: count what is really there
     n_bytes = synth_gpu.batch_bytes(batch)
     dstruct = synth_gpu.batch_struct(batch)
+    # Host copies for the end-to-end legs.  One GPU: the batch in page-locked memory in both forms (wire = the headline, SoA = the
+    # resident layout shipped as it is).  N GPUs on one host: only the wire form is page-locked (N x 14 GB of pinned memory is more
+    # than a host should be asked for); it is packed from a pageable copy that is dropped afterwards, and e2e_soa is not measured.
+    want_soa = world == 1
     host_kind = "pinned"
-    try:
-        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in batch.items()}
-    except RuntimeError as e:  # N ranks x 9 GB of page-locked memory can exceed what the host allows: measure from pageable memory, and say so
-        print("[rank %d] pinning the host batch failed (%s): e2e is measured from pageable memory" % (rank, str(e).splitlines()[0]), file=sys.stderr, flush=True)
+    host = None
+    if want_soa:
+        try:
+            host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in batch.items()}
+        except RuntimeError as e:
+            print("[rank %d] pinning the host batch failed (%s): e2e_soa is measured from pageable memory" % (rank, str(e).splitlines()[0]), file=sys.stderr, flush=True)
+            host_kind = "wire pinned; SoA pageable (pinning failed)"
+    if host is None:
         host = {k: torch.empty(v.shape, dtype=v.dtype) for k, v in batch.items()}
-        host_kind = "pageable (pinning failed)"
     for k in batch:
         host[k].copy_(batch[k])
     torch.cuda.synchronize()
     hstruct = synth_gpu.batch_struct(host)
     t_pack = time.perf_counter()
+    host_rb = api.RecordBatch({k: v.numpy().view(api.BATCH_DTYPES[k]) for k, v in host.items()})  # views: no copy
     try:
-        host_rb = api.RecordBatch({k: v.numpy().view(api.BATCH_DTYPES[k]) for k, v in host.items()})  # views: no copy
-        wire = api.WireBatch(host_rb, pinned=(host_kind == "pinned"))
-    except api.SquidB200Error:
+        wire = api.WireBatch(host_rb, pinned=True)
+    except api.SquidB200Error as e:
+        print("[rank %d] page-locking the wire batch failed (%s): e2e is measured from pageable memory" % (rank, e), file=sys.stderr, flush=True)
         wire = api.WireBatch(host_rb, pinned=False)
-        host_kind += "; wire pageable"
+        host_kind = "pageable (pinning failed)"
     t_pack = time.perf_counter() - t_pack
+    wire._keep = None
+    if not want_soa:
+        del host_rb, host, hstruct
+        host = hstruct = None
 
     g = api.SegmentGraph(cfg, case.ref_len, device=local)
     state = {}
@@ -494,6 +523,8 @@ def main():
         torch.cuda.synchronize()
 
     def timed(mode: str, steps: int, warmup: int):
+        sampler = ClockSampler(local)
+        sampler.start()
         for _ in range(warmup):
             step(mode)
         state["chim_pool"] = [api.ChimericReads(chim0.a) for _ in range(steps)]  # pristine inputs of the timed steps
@@ -501,8 +532,7 @@ def main():
         state["timeline"] = {}
         state["timed"] = True
         l0 = g.launch_count()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler.mark_begin()
         t = time.perf_counter()
         phases = {}
         for _ in range(steps):
@@ -513,6 +543,7 @@ def main():
                     phases[ph] = phases.get(ph, 0.0) + v / steps
         barrier()
         sec = (time.perf_counter() - t) / steps
+        sampler.mark_end()
         clocks = sampler.stop()
         if world > 1:
             tt = torch.tensor([sec], dtype=torch.float64, device=dev)
@@ -532,7 +563,9 @@ def main():
     # end to end from host memory: the wire form (13 + 8 B, what a front end hands over; packed once, outside the timed region, its
     # cost reported as pack_wire_s) is the headline; the resident 32 + 12 B layout shipped as it is stays as `e2e_soa`
     sec_e2e, phases_e2e, _, _ = timed("wire", max(1, min(args.steps, 5)), 2)
-    sec_soa, phases_soa, _, _ = timed("soa", max(1, min(args.steps, 2)), 1)
+    sec_soa, phases_soa = None, None
+    if want_soa:
+        sec_soa, phases_soa, _, _ = timed("soa", max(1, min(args.steps, 2)), 1)
 
     # ---- N > 1: the same stream as the single-GPU run, range-sharded over the N GPUs (strong scaling, north_star's split) ----
     one_stream = None
@@ -613,8 +646,8 @@ def main():
             "e2e": {"value": world * P / sec_e2e, "unit": "read pairs/s", "h2d_bytes_per_step": wire.nbytes + sum(v.nbytes for v in chim0.a.values()), "d2h_bytes_per_step": state.get("d2h", 0), "ms_per_step": 1e3 * sec_e2e, "host_memory": host_kind,
                     "input": "sqg_wire (include/squid_b200.h): delta-coded records, 13 B + 8 B per block, %d record and %d block exceptions; uploaded in chunks, widened on the device while the next chunks are on the bus" % (wire.struct.n_rec_exc, wire.struct.n_blk_exc),
                     "pack_wire_s_outside_timed_region": t_pack, "pack_threads": os.cpu_count()},
-            "e2e_soa": {"value": world * P / sec_soa, "unit": "read pairs/s", "h2d_bytes_per_step": n_bytes + sum(v.nbytes for v in chim0.a.values()), "ms_per_step": 1e3 * sec_soa,
-                        "input": "sqg_batch (the resident 32 B + 12 B layout) copied as it is", "phases_ms": phases_soa},
+            "e2e_soa": ({"value": world * P / sec_soa, "unit": "read pairs/s", "h2d_bytes_per_step": n_bytes + sum(v.nbytes for v in chim0.a.values()), "ms_per_step": 1e3 * sec_soa,
+                         "input": "sqg_batch (the resident 32 B + 12 B layout) copied as it is", "phases_ms": phases_soa} if sec_soa else None),
             "roofline": roof,
             "whole_path": {"alg_bytes_per_pair": b_alg_pair, "gpu_ms_in_phases": total_gpu_ms,
                            "frac_of_hbm_roofline_wall": (b_alg_pair * P / sec) / 1e9 / peak, "frac_of_hbm_roofline_phases": (b_alg_pair * P / (total_gpu_ms * 1e-3)) / 1e9 / peak if total_gpu_ms else None},

@@ -236,122 +236,6 @@ SQ_HD void conc_load_read(const B &b, int64_t r, ReadView &rv, bool &is_first) {
     else { rv.nS = no; rv.nF = nm; rv.second_total = b.total_len[r]; rv.first_total = 0; }
 }
 
-// read_edges(MODE_OTHER, hint unknown) for a read of at most N blocks in all -- FirstRead followed by SecondMate in ONE array of
-// compile-time size.  Every loop is unrolled with constant indices and guarded by the list lengths, so the lists and
-// tmpRead_Node stay in registers (read_edges indexes its lists dynamically, which puts them in local memory).  Same rules, same
-// order of emission.  Returns -3 when the read is hint-sensitive (nothing emitted), else tmpRead_Node[0].  nF + nS must be > 0.
-template <int N, class Emit>
-SQ_HD int32_t read_edges_small(const NodeTable &nt, const Params &p, Blk (&A)[N], int nF, int nS, int32_t first_total, int32_t second_total,
-                               bool record_is_first, Emit &emit) {
-    const int n = nF + nS;
-    int32_t node[N], span[N];
-    uint32_t spanning = 0;
-    bool sensitive = false;
-    Cursor cur;
-    cur.idx = 0; cur.known = false;
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        node[k] = -1; span[k] = 0;
-        if (k < n) {
-            const int32_t j = locate_block(nt, A[k], cur, false, 0, &sensitive);
-            if (sensitive) return -3;
-            node[k] = j;
-            if (j >= 0) trim_block(nt, j, A[k]);
-        }
-    }
-    const bool ffi_known = node[0] != -1;  // firstfrontindex after this read (:1608-1609)
-    const int32_t ffi = node[0];
-#pragma unroll
-    for (int k = 0; k < N; k++)  // the -1 fallbacks, all decided before anything is emitted
-        if (k < n && node[k] == -1 && A[k].ref_id >= 0 && A[k].ref_id < nt.n_ref) {
-            span[k] = spanning_node(nt, A[k], ffi_known, ffi, &sensitive);
-            if (sensitive) return -3;
-            spanning |= 1u << k;
-        }
-#pragma unroll
-    for (int k = 0; k < N; k++)
-        if ((spanning >> k) & 1u) { const int32_t i = span[k]; if (i + 1 < nt.n) emit(edge_key(i, false, i + 1, true)); }
-#pragma unroll
-    for (int k = 0; k + 1 < N; k++)
-        if (k + 1 < n && k + 1 != nF) {  // k and k+1 belong to the same mate: split junction
-            const int32_t i = node[k], j = node[k + 1];
-            if (i != j && i != -1 && j != -1) emit(edge_key(i, A[k].rev, j, !A[k + 1].rev));
-        }
-    if (record_is_first && nF > 0 && nS > 0) {  // pair edge between the last block of each mate
-        bool end_disc = false;  // IsEndDiscordant of either list (ReadRec.cpp:178-209)
-#pragma unroll
-        for (int k = 0; k + 1 < N; k++)
-            if (k + 1 < n && k + 1 != nF) {
-                const Blk &x = A[k], &y = A[k + 1];
-                const bool a = x.ref_pos < y.ref_pos, r = x.read_pos < y.read_pos;
-                if (x.ref_id != y.ref_id || x.rev != y.rev || (!x.rev && a != r) || (x.rev && a == r)) end_disc = true;
-            }
-        if (!end_disc) {
-            Blk fb = A[0], sf = A[0], sb = A[0];  // FirstRead.back(), SecondMate.front(), SecondMate.back()
-            int32_t i = -1, j = -1;
-#pragma unroll
-            for (int k = 0; k < N; k++) {
-                if (k == nF - 1) { fb = A[k]; i = node[k]; }
-                if (k == nF) sf = A[k];
-                if (k == n - 1) { sb = A[k]; j = node[k]; }
-            }
-            bool overlap = false;
-#pragma unroll
-            for (int k = 0; k < N; k++)
-                if (k < n && (k < nF ? j == node[k] : i == node[k])) overlap = true;
-            const int32_t d = i > j ? i - j : j - i;
-            if ((nF > 1 || nS > 1) && d < 3) overlap = true;
-            if (i != j && i != -1 && j != -1 && !overlap) {
-                const uint64_t key = edge_key(i, fb.rev, j, sb.rev);
-                const bool disc = edge_is_discordant(nt, p, key);
-                const Blk &ff = A[0];
-                bool pd = false;  // IsPairDiscordant(false), ReadRec.cpp:211-228
-                if (ff.ref_id != sb.ref_id || ff.rev == sb.rev) pd = true;
-                else if (!ff.rev && ff.ref_pos - ff.read_pos > sb.ref_pos - (second_total - sb.read_pos - sb.match_read)) pd = true;
-                else if (!sf.rev && sf.ref_pos - sf.read_pos > fb.ref_pos - (first_total - fb.read_pos - fb.match_read)) pd = true;
-                if (pd == disc) emit(key);
-            }
-        }
-    }
-    return node[0];
-}
-
-// RawEdgesOther for record r with at most three own blocks: the own blocks are put in read order by a three-element insertion
-// network (SortbyReadPos: stable), the synthetic mate block takes its place in front of or behind them, and read_edges_small runs
-// on registers only.  Returns the res0 code (-2: no block at all).
-template <class B, class Emit>
-SQ_HD int32_t conc_edges_small(const B &b, const Params &p, const NodeTable &nt, int64_t r, Emit &emit) {
-    const uint32_t o = b.blk_off[r];
-    const int no = (int)(b.blk_off[r + 1] - o);
-    const uint16_t f = b.flag[r];
-    const int32_t rid = b.ref_id[r];
-    const bool rev = flag_rev(f);
-    Blk own[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        own[k].ref_id = rid; own[k].rev = rev; own[k].ref_pos = 0; own[k].match_ref = 0; own[k].read_pos = 0; own[k].match_read = 0;
-        if (k < no) { own[k].ref_pos = b.blk_ref_pos[o + k]; own[k].match_ref = b.blk_match_ref[o + k]; own[k].read_pos = b.blk_read_pos[o + k]; own[k].match_read = b.blk_match_read[o + k]; }
-    }
-    if (no > 1 && own[1].read_pos < own[0].read_pos) { const Blk t = own[0]; own[0] = own[1]; own[1] = t; }
-    if (no > 2 && own[2].read_pos < own[1].read_pos) {
-        { const Blk t = own[1]; own[1] = own[2]; own[2] = t; }
-        if (own[1].read_pos < own[0].read_pos) { const Blk t = own[0]; own[0] = own[1]; own[1] = t; }
-    }
-    const bool is_first = flag_first(f), hm = has_mate_block(f, b.mate_ref_id[r]);
-    const Blk mate = mate_block_of(f, b.mate_ref_id[r], b.mate_pos[r]);
-    Blk A[4];
-    if (hm && !is_first) { A[0] = mate; A[1] = own[0]; A[2] = own[1]; A[3] = own[2]; }  // FirstRead = [mate], SecondMate = own blocks
-    else { A[0] = own[0]; A[1] = own[1]; A[2] = own[2]; A[3] = mate; }
-    if (hm && is_first) {  // FirstRead = own blocks, SecondMate = [mate]: the mate block follows the last own block
-        if (no == 0) A[0] = mate; else if (no == 1) A[1] = mate; else if (no == 2) A[2] = mate;
-    }
-    const int nm = hm ? 1 : 0;
-    const int nF = is_first ? no : nm, nS = is_first ? nm : no;
-    if (nF + nS == 0) return -2;
-    const int32_t tl = b.total_len[r];
-    return read_edges_small<4>(nt, p, A, nF, nS, is_first ? tl : 0, is_first ? 0 : tl, is_first, emit);
-}
-
 // read_edges(MODE_OTHER, hint unknown) for a record with at most ONE own block -- nine records out of ten -- with
 // everything in registers: the lists are [own] and [mate], so there are no split junctions and at most one pair edge.
 // Returns -3 when the read is hint-sensitive (nothing emitted), else tmpRead_Node[0] (>= -1).  n = #blocks must be > 0.

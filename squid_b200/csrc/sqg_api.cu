@@ -41,12 +41,13 @@ using namespace sq;
         }                                                                                          \
     } while (0)
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
-#define LAUNCH(kernel, grid, block, ...)                                                           \
+#define LAUNCH_ON(st, kernel, grid, block, ...)                                                    \
     do {                                                                                           \
-        kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                                  \
+        kernel<<<(grid), (block), 0, (st)>>>(__VA_ARGS__);                                         \
         ctx->launches++;                                                                           \
         CK(cudaGetLastError());                                                                    \
     } while (0)
+#define LAUNCH(kernel, grid, block, ...) LAUNCH_ON(ctx->stream, kernel, grid, block, __VA_ARGS__)
 
 struct HostLap {  // SQG_TIMING=1: wall-clock laps of the host side of a call, to stderr
     bool on; std::chrono::steady_clock::time_point t0;
@@ -1649,14 +1650,24 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
             // the tile kernel the generic rules stall on instruction fetch (ncu: no_instruction is the top stall) and the tile's warps
             // wait at the barrier behind the one that drew the longest records (profiles/r2_ncu_summary.txt).
             static const bool slow_in_tile = getenv("SQG_SLOW_IN_TILE") && atoi(getenv("SQG_SLOW_IN_TILE")) == 1;
-            PHASE_BEGIN("k_assign");
-            if (do_depth) {
-                PHASE_BEGIN("k_assign_depth");
-                k_assign_tiles<true, false, false><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
+            // The depth pass and the edge pass are independent: SQG_DEPTH_OVERLAP=1 runs the depth tile kernel on the second stream
+            // beside k_edges_generic instead of in front of it.  Measured (100 M pairs): no gain, 21.6 ms against 20.2 ms for the two
+            // passes together -- the two kernels compete for the same issue slots and L2 -- so the default keeps them in sequence.
+            static const bool overlap_env = getenv("SQG_DEPTH_OVERLAP") && atoi(getenv("SQG_DEPTH_OVERLAP")) == 1;
+            const bool overlap = do_depth && do_edges && overlap_env;
+            auto depth_pass = [&](cudaStream_t st) -> int {
+                { const int rc_ = phase_begin(ctx, "k_assign_depth", st); if (rc_) return rc_; }
+                k_assign_tiles<true, false, false><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, st>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
                 ctx->launches++;
                 CK(cudaGetLastError());
-                PHASE_END("k_assign_depth");
-            }
+                { const int rc_ = phase_end(ctx, "k_assign_depth", st); if (rc_) return rc_; }
+                LAUNCH_ON(st, k_depth_scan, 1, 1024, ctx->d_dtile.p, (int32_t)n_tiles);
+                LAUNCH_ON(st, k_depth_fix, blocks_for(n_tiles), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_dtile.p, (int32_t)n_tiles, a.cnt_main, a.sum_main);
+                LAUNCH_ON(st, k_depth_short_nodes, 64, 128, ctx->nt, ctx->d_omask.p, ctx->d_shorts.p, a.n_short, a.short_cap, a.n_short + 1);
+                return SQG_OK;
+            };
+            PHASE_BEGIN("k_assign");
+            if (do_depth && !overlap) { const int rc_ = depth_pass(ctx->stream); if (rc_) return rc_; }
             if (do_edges) {
                 PHASE_BEGIN("k_assign_edges");
                 if (slow_in_tile) k_assign_tiles<false, true, true><<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, a, batch_bulk_ok(b) ? 1 : 0);
@@ -1664,21 +1675,22 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
                 ctx->launches++;
                 CK(cudaGetLastError());
                 PHASE_END("k_assign_edges");
+                if (overlap) {
+                    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                    const int rc_ = depth_pass(ctx->stream2);
+                    if (rc_) return rc_;
+                    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                }
                 PHASE_BEGIN("k_edges_generic");
                 LAUNCH(k_edges_generic, 148 * 16, 128, a);
                 PHASE_END("k_edges_generic");
-            }
-            PHASE_END("k_assign");
-            if (do_depth) {
-                LAUNCH(k_depth_scan, 1, 1024, ctx->d_dtile.p, (int32_t)n_tiles);
-                LAUNCH(k_depth_fix, blocks_for(n_tiles), kThreads, b, ctx->d_cls.p, ctx->nt, ctx->r_break, ctx->d_dtile.p, (int32_t)n_tiles, a.cnt_main, a.sum_main);
-                LAUNCH(k_depth_short_nodes, 64, 128, ctx->nt, ctx->d_omask.p, ctx->d_shorts.p, a.n_short, a.short_cap, a.n_short + 1);
-            }
-            if (do_edges) {
                 LAUNCH(k_fix_heads, 256, 128, ctx->d_scratch32.p, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, ctx->shard_init_hint, (int32_t *)(ctx->d_counters.p + 22));
                 LAUNCH(k_fix_chains<false>, 256, 128, b, cd, ctx->params, ctx->nt, ctx->d_scratch32.p, n, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, sink);
                 if (ctx->shard_count > 1) LAUNCH(k_last_located, 1, 1, ctx->d_scratch32.p, n, (int32_t *)(ctx->d_counters.p + 23));
+                if (overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
             }
+            PHASE_END("k_assign");
         }
         CK(cudaMemcpyAsync(ctx->h_counters.p + 9, ctx->d_counters.p + 9, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_counters.p + 16, ctx->d_counters.p + 16, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -148,6 +148,15 @@ class ShardedSegmentGraph:
         self.vEdges = None
         self.Chimrecord = None
         self.rounds = {"seeds": 0, "hints": 0, "chain": 0}
+        self.detail_ms = {}  # host wall clock per sub-stage (exchanges included), accumulated over the calls
+        self._t = None
+
+    def _lap(self, name=None):
+        import time
+        now = time.perf_counter()
+        if name is not None and self._t is not None:
+            self.detail_ms[name] = self.detail_ms.get(name, 0.0) + 1e3 * (now - self._t)
+        self._t = now
 
     def close(self):
         for g in self.g:
@@ -163,7 +172,9 @@ class ShardedSegmentGraph:
     def BuildNode_STAR(self) -> Nodes:
         N = self.n_shards
         assumed = [s > 0 for s in range(N)]
+        self._lap()
         ops = [g.shard_seeds(assumed[sid]) for g, sid in zip(self.g, self.ids)]
+        self._lap("nodes: shard_seeds")
         while True:
             self.rounds["seeds"] += 1
             all_ops = [o.reshape(-1, 4) for o in self.comm.allgather_arrays(ops)]
@@ -176,16 +187,20 @@ class ShardedSegmentGraph:
                 i = self.ids.index(s)
                 ops[i] = self.g[i].shard_seeds(truth)
         cat = np.concatenate(all_ops, axis=0) if all_ops else np.zeros((0, 4), np.int32)
+        self._lap("nodes: seed-op exchange")
         parts, node = [], None
         for g in self.g:
             c, p, l, c3, s3, other = g.shard_build(cat)
             node = (c, p, l)
             parts.append((c3, s3, other))
+        self._lap("nodes: shard_build")
         count3, sum3, other = merge_depth(parts)  # the local shards; then across the processes, in one int32 vector
         tot = self.comm.allreduce(np.concatenate([count3.ravel(), sum3.ravel(), np.array([other], np.int32)]).astype(np.int32), "sum")
         nn = count3.size
         count3, sum3, other = tot[:nn].reshape(count3.shape), tot[nn:2 * nn].reshape(sum3.shape), int(tot[2 * nn] != 0)
+        self._lap("nodes: depth all-reduce")
         self._fix_hints()
+        self._lap("nodes: hint exchange")
         length = node[2]
         support = count3[0] + count3[1] + (count3[2] if other else 0)  # as api.SegmentGraph.BuildNode_STAR
         depth = sum3[0].astype(np.float64) + sum3[1].astype(np.float64)
@@ -214,15 +229,19 @@ class ShardedSegmentGraph:
     def BuildEdges(self, gather_chimeric: bool = True) -> Edges:
         """gather_chimeric=False: the trimmed chimeric blocks stay with the process that holds shard 0."""
         keys, ws, chim = [], [], None
+        self._lap()
         for g, sid in zip(self.g, self.ids):
             e = g.BuildEdges()
             keys.append(_shard.pack_edge_keys(e.Ind1, e.Ind2, e.Head1, e.Head2)); ws.append(e.Weight)
             if sid == 0:
                 chim = g.Chimrecord  # trimmed in place by shard 0 (it owns the chimeric reads' LocateRead pass)
+        self._lap("edges: local tables")
         all_k, all_w = self.comm.allgather_arrays(keys), self.comm.allgather_arrays(ws)
+        self._lap("edges: all-gather")
         mk, mw = _shard.merge_edge_tables(list(zip(all_k, all_w)))
         i1, i2, h1, h2 = _shard.unpack_edge_keys(mk)
         self.vEdges = Edges(i1, i2, h1, h2, mw)
+        self._lap("edges: merge")
         if gather_chimeric and self.comm.world > 1:
             got = self.comm.allgather([chim.a if (chim is not None and sid == 0) else None for sid in self.ids])
             ca = next((a for a in got if a is not None), None)
@@ -235,12 +254,17 @@ class ShardedSegmentGraph:
         K = int(np.asarray(bp_chr).shape[0])
         if K == 0:
             return np.zeros(0, np.int32)
-        info = self.comm.allgather_arrays([np.array(g.shard_cov_begin(bp_chr, bp_pos), np.int64) for g in self.g])
+        self._lap()
+        begun = [np.array(g.shard_cov_begin(bp_chr, bp_pos), np.int64) for g in self.g]
+        self._lap("coverage: begin")
+        info = self.comm.allgather_arrays(begun)
+        self._lap("coverage: begin exchange")
         nq = [int(x[0]) for x in info]
         off = np.concatenate([[0], np.cumsum(nq)]).astype(np.int64)
         k_in = chain_k_in_guess([int(x[1]) for x in info])
         k_in[0] = 0
         k_out = {sid: g.shard_cov_chain(k_in[sid]) for g, sid in zip(self.g, self.ids)}
+        self._lap("coverage: chain")
         while True:
             self.rounds["chain"] += 1
             outs = [int(x[0]) for x in self.comm.allgather_arrays([np.array([k_out[sid]], np.int64) for sid in self.ids])]
@@ -251,12 +275,18 @@ class ShardedSegmentGraph:
             k_in[s] = outs[s - 1]
             if s in self.ids:
                 k_out[s] = self.g[self.ids.index(s)].shard_cov_chain(k_in[s])
+        self._lap("coverage: chain exchange")
         t = np.full(K, -1, np.int64)
         for g, sid in zip(self.g, self.ids):
             g.shard_cov_owned_t(int(off[sid]), k_in[sid], k_out[sid], t)
+        self._lap("coverage: owned t")
         t = self.comm.allreduce(t, "max")  # every process filled the entries its shards own
         t[t < 0] = int(off[-1])  # never passed: every qualifying record is tested against the breakpoint
+        self._lap("coverage: t all-reduce")
         cov = np.zeros(K, np.int32)
         for g, sid in zip(self.g, self.ids):
             cov += g.shard_cov_count(int(off[sid]), t)
-        return self.comm.allreduce(cov, "sum")
+        self._lap("coverage: count")
+        out = self.comm.allreduce(cov, "sum")
+        self._lap("coverage: count all-reduce")
+        return out

@@ -345,12 +345,6 @@ int main(int argc, char **argv) {
                 else sens[i] = 1;
                 continue;
             }
-            if (mode == MODE_OTHER && n_own <= 3 && !getenv("SQ_EMUL_NO_SMALL_EDGES")) {  // the register path of k_edges_generic (conc_edges_small)
-                const int32_t r0 = conc_edges_small(b, p, nt, i, e2);
-                if (r0 != -3) { keys.insert(keys.end(), tmp.begin(), tmp.end()); res0[i] = r0; }
-                else sens[i] = 1;
-                continue;
-            }
             if (read_edges(nt, p, rv, mode, is_first, false, 0, node, e2)) {
                 keys.insert(keys.end(), tmp.begin(), tmp.end());
                 res0[i] = node[0];
