@@ -282,7 +282,10 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
                     s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)i;
                 }
             }
-            if (in && out != -4) {
+            if (in) {
+                // (-4 = deferred to pass B1 / B2 / k_edges_generic, which overwrite it.  Written here all the same: when the deferred
+                // list overflows, the records past its capacity are never processed in this attempt, and the hint fix-up, which
+                // runs before the host notices and repeats the pass, must not find stale values of an earlier batch in their place)
                 a.res0[r] = out;
                 if (out == -3) { const int32_t q = atomicAdd(a.n_sens, 1); if (q < a.sens_cap) a.sens[q] = (int32_t)r; }
             }
@@ -308,9 +311,10 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
         }
     }
     // ---- the multi-block records that left the tile's segment ----------------------------------------------------------------
-    // SLOW_IN_TILE: processed right here, from the staged tile (a third of the records at the App. C block mix: dense enough to keep
-    // the tile's lanes busy, and their edges repeat the tile's other edges in its table).  Otherwise (and for the rare tile
-    // whose blocks were too many to stage, or a record with more than three blocks) they go to k_edges_generic's list.
+    // They go to k_edges_generic's list.  (SLOW_IN_TILE, an experiment kept for measurements: processed right here with the generic
+    // rules, from the staged tile -- slower, see sqg_api.cu.  Also measured and dropped: a register-only rule set for the plain
+    // ones among them -- every block well inside one segment, nine in ten -- run here as a "pass B2": 43 M of the 53 M records of
+    // the benchmark leave the list, k_edges_generic 5.4 -> 1.5 ms, this kernel 5.5 -> 9.3 ms: the same cost per record either way.)
     if (DO_EDGES) {
         __shared__ int32_t s_slow_base, s_nleft;
         int ns = s_nslow;
@@ -417,7 +421,8 @@ __global__ void __launch_bounds__(kTileThreads, 7) k_assign_tiles(DevBatch b, P2
 
 // The records k_assign_tiles left over (several aligned blocks, not all inside one segment): the generic rules, one record
 // per thread, every lane busy.  Edges are counted in a per-block table like in the tile kernel.
-__global__ void __launch_bounds__(128) k_edges_generic(P2Args a) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_edges_generic(P2Args a) {
     __shared__ TileEdgeTable s_edges;
     __shared__ int32_t s_tot, s_woff[4];
     __shared__ unsigned long long s_at;

@@ -515,7 +515,7 @@ __global__ void k_fix_chains(DevBatch b, ChimDev c, Params p, NodeTable nt, int3
     const int32_t n = *n_sens < cap ? *n_sens : cap;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int32_t hint = head_hint[i];
-        if (hint < 0) continue;
+        if (hint < 0 || hint >= nt.n) continue;  // (>= nt.n: only in an attempt whose lists overflowed and that is repeated anyway)
         int64_t q = sens[i];
         for (;;) {
             Blk F[kMaxBlocks + 1], S[kMaxBlocks + 1];
@@ -1683,7 +1683,13 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
                     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
                 }
                 PHASE_BEGIN("k_edges_generic");
-                LAUNCH(k_edges_generic, 148 * 16, 128, a);
+                // resident blocks per SM the generic kernel is compiled for (it is bound by the latency of dependent loads: more warps,
+                // fewer registers each -- 64 at 8 blocks -- beat fewer warps without local-memory traffic: 5.4 ms against 6.7 ms at 7)
+                static const int gen_occ = getenv("SQG_GENERIC_OCC") ? atoi(getenv("SQG_GENERIC_OCC")) : 8;
+                if (gen_occ >= 12) LAUNCH(k_edges_generic<12>, 148 * 16, 128, a);
+                else if (gen_occ >= 10) LAUNCH(k_edges_generic<10>, 148 * 16, 128, a);
+                else if (gen_occ >= 8) LAUNCH(k_edges_generic<8>, 148 * 16, 128, a);
+                else LAUNCH(k_edges_generic<7>, 148 * 16, 128, a);
                 PHASE_END("k_edges_generic");
                 LAUNCH(k_fix_heads, 256, 128, ctx->d_scratch32.p, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, ctx->shard_init_hint, (int32_t *)(ctx->d_counters.p + 22));
                 LAUNCH(k_fix_chains<false>, 256, 128, b, cd, ctx->params, ctx->nt, ctx->d_scratch32.p, n, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, sink);
