@@ -2235,8 +2235,8 @@ static int cov_prepare(sqg_ctx *ctx, const int32_t *bp_chr, const int32_t *bp_po
 
 // t[k] for k in [k_begin, K) from this batch's qualifying ranks alone, the chain starting fresh at breakpoint k_begin.
 // Values >= nq mean "not passed by any record of this batch" (everything from the first such breakpoint on is unresolved).
-static int cov_chain(sqg_ctx *ctx, int64_t k_begin) {
-    const int64_t n = ctx->batch.n_rec, nq = ctx->cov_nq, K = ctx->cov_K - k_begin;
+static int cov_chain(sqg_ctx *ctx, int64_t k_begin, int64_t k_end) {  // resolves t for the breakpoints [k_begin, k_end)
+    const int64_t n = ctx->batch.n_rec, nq = ctx->cov_nq, K = k_end - k_begin;
     if (K <= 0) return SQG_OK;
     const int64_t n_tiles = (n + kCovTile - 1) / kCovTile;
     const int32_t *bpchr = ctx->d_bpchr.p + k_begin, *bppos = ctx->d_bppos.p + k_begin;
@@ -2312,7 +2312,7 @@ extern "C" int sqg_bp_coverage(sqg_ctx *ctx, const int32_t *bp_chr, const int32_
     int rc = cov_prepare(ctx, bp_chr, bp_pos, K);
     if (rc) return rc;
     PHASE_BEGIN("coverage");
-    rc = cov_chain(ctx, 0);
+    rc = cov_chain(ctx, 0, K);
     if (rc) return rc;
     rc = cov_count(ctx, cov_out);
     if (rc) return rc;
@@ -2341,21 +2341,25 @@ extern "C" int sqg_shard_cov_begin(sqg_ctx *ctx, const int32_t *bp_chr, const in
     int64_t lo = 0, hi = K;  // r0 is non-decreasing in k: first breakpoint no record of this shard passes
     while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (ctx->h_t.p[m] < ctx->cov_nq) lo = m + 1; else hi = m; }
     *n_pass = lo;
+    ctx->cov_n_pass = lo;
     return SQG_OK;
 }
 extern "C" int sqg_shard_cov_chain(sqg_ctx *ctx, int64_t k_in, int64_t *k_out) {
     if (!ctx || !k_out || k_in < 0 || k_in > ctx->cov_K) return SQG_EINVAL;
     CK(cudaSetDevice(ctx->device));
-    const int64_t K = ctx->cov_K;
+    // No record of this shard passes a breakpoint from cov_n_pass on (r0 is non-decreasing along the sorted list), so the chain
+    // cannot resolve any of them here: only [k_in, cov_n_pass) is walked.  (Walking the unresolvable tail as well made the
+    // verification fail on it and sent the whole list through the literal replay: 9 ms on the first of two shards.)
+    const int64_t k_end = ctx->cov_n_pass < ctx->cov_K ? ctx->cov_n_pass : ctx->cov_K;
     *k_out = k_in;
-    if (k_in == K) return SQG_OK;
-    int rc = cov_chain(ctx, k_in);
+    if (k_in >= k_end) return SQG_OK;
+    int rc = cov_chain(ctx, k_in, k_end);
     if (rc) return rc;
-    CK(ctx->h_t.ensure(K + 1));
-    CK(cudaMemcpyAsync(ctx->h_t.p + k_in, ctx->d_t.p + k_in, (K - k_in) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx->h_t.ensure(ctx->cov_K + 1));
+    CK(cudaMemcpyAsync(ctx->h_t.p + k_in, ctx->d_t.p + k_in, (k_end - k_in) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int64_t k = k_in;
-    while (k < K && ctx->h_t.p[k] < ctx->cov_nq) k++;
+    while (k < k_end && ctx->h_t.p[k] < ctx->cov_nq) k++;
     *k_out = k;
     return SQG_OK;
 }

@@ -225,6 +225,7 @@ struct sqg_ctx {
     int32_t shard_g_done = 0;
     int64_t shard_trig_last = 0;
     int64_t cov_K = 0, cov_nq = 0;       // staged coverage (sqg_shard_cov_*)
+    int64_t cov_n_pass = 0;              // range shard: breakpoints [cov_n_pass, cov_K) are passed by no record of this shard
     sq::HBuf<int64_t> h_t;
 
     // segment table

@@ -90,6 +90,17 @@ class DistComm(LocalComm):
         return t.cpu().numpy().view(a.dtype).reshape(a.shape)
 
 
+def dev_view(ptr, n, dtype, dev):
+    """torch view of library-owned device memory (no copy)."""
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (int(n),), "typestr": {torch.int64: "<i8", torch.int32: "<i4"}[dtype], "data": (int(ptr), False), "version": 2, "strides": None}
+    return torch.as_tensor(a, device=dev)
+
+
 # ---- the exchange logic, free of any device call (tested on CPU with gloo) --------------------------------------------------
 def first_wrong_prior(assumed, op_counts):
     """Shards run stage 1 assuming `assumed[s]` = "an earlier shard has emitted a seed op".  Returns (s, truth) for the first
@@ -226,8 +237,52 @@ class ShardedSegmentGraph:
                     self.g[self.ids.index(s)].shard_redo_edges(inc[s])
 
     # -- BuildEdges ----------------------------------------------------------------------------------------------------
+    def _merge_edges_on_device(self):
+        """One shard per process over NCCL: the per-shard (key, weight) tables never leave HBM -- one all_gather of
+        [count | keys | weights] per rank, then sort + reduce-by-key on the device (sqg_merge_edge_tables)."""
+        import ctypes as C
+        comm, g = self.comm, self.g[0]
+        torch, dist, dev = comm.torch, comm.dist, comm.dev
+        dk, dw, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        g._ck(g.L.sqg_edges_device_table(g._h, C.byref(dk), C.byref(dw), C.byref(n)))
+        m = n.value
+        mx_t = torch.tensor([m], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx_t, op=dist.ReduceOp.MAX, group=comm.group)
+        mx = int(mx_t.item())
+        buf = torch.zeros(1 + 2 * mx, dtype=torch.int64, device=dev)
+        buf[0] = m
+        if m:
+            buf[1:1 + m] = dev_view(dk.value, m, torch.int64, dev)
+            buf[1 + mx:1 + mx + m] = dev_view(dw.value, m, torch.int32, dev).to(torch.int64)
+        allb = torch.empty(comm.world * (1 + 2 * mx), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allb, buf, group=comm.group)
+        allb = allb.view(comm.world, 1 + 2 * mx)
+        cnts = allb[:, 0].tolist()
+        allk = torch.cat([allb[r, 1:1 + int(cnts[r])] for r in range(comm.world)])
+        allw = torch.cat([allb[r, 1 + mx:1 + mx + int(cnts[r])] for r in range(comm.world)]).to(torch.int32)
+        torch.cuda.current_stream().synchronize()  # the library works on its own stream
+        i1, i2, hd, w, ne = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        g._ck(g.L.sqg_merge_edge_tables(g._h, allk.data_ptr(), allw.data_ptr(), int(allk.shape[0]), C.byref(i1), C.byref(i2), C.byref(hd), C.byref(w), C.byref(ne)))
+        k = ne.value
+        from .api import _np_from
+        heads = _np_from(hd, k, np.uint8)
+        return Edges(_np_from(i1, k, np.int32), _np_from(i2, k, np.int32), (heads & 1).astype(bool), ((heads >> 1) & 1).astype(bool), _np_from(w, k, np.int32))
+
     def BuildEdges(self, gather_chimeric: bool = True) -> Edges:
         """gather_chimeric=False: the trimmed chimeric blocks stay with the process that holds shard 0."""
+        if isinstance(self.comm, DistComm) and self.comm.dev.type == "cuda" and len(self.g) == 1:
+            self._lap()
+            self.g[0].BuildEdges()  # this shard's table (and, on shard 0, the in-place trim of the chimeric blocks)
+            chim = self.g[0].Chimrecord if self.ids[0] == 0 else None
+            self._lap("edges: local tables")
+            self.vEdges = self._merge_edges_on_device()
+            self._lap("edges: all-gather + merge on the device")
+            if gather_chimeric and self.comm.world > 1:
+                got = self.comm.allgather([chim.a if chim is not None else None])
+                ca = next((a for a in got if a is not None), None)
+                chim = ChimericReads(ca) if ca is not None else None
+            self.Chimrecord = chim
+            return self.vEdges
         keys, ws, chim = [], [], None
         self._lap()
         for g, sid in zip(self.g, self.ids):
