@@ -15,7 +15,8 @@ synthetic sorted alignment records of the configs[1] shape (GRCh38 layout, ~0.5 
   cpu_baseline : the reference's own BuildNode_STAR/BuildEdges/ExactBPConcordantSupport (oracle/_ref, single thread)
                  on a bounded sample of the same generator
 N > 1: weak scaling over N independent streams of that shape, one per rank (a cohort of N samples): every rank runs the whole
-path on its own stream, the per-rank edge tables are exchanged with NCCL all_gather and merge-reduced on the device.  The same
+path on its own stream; independent samples have nothing to exchange, so there is no data-path collective (round 1 merged the
+per-rank edge tables anyway: 10 ms of an 8-GPU step spent on a table that means nothing across samples).  The same
 run also times ONE stream (rank 0's) cut into N exact genomic-range shards -- bit-identical results for every N, checked against
 the pinned CRCs -- and reports it as `one_stream` (strong scaling).
 """
@@ -475,30 +476,6 @@ def main():
         lap("BuildNode_STAR")
         edges = g.BuildEdges()
         lap("BuildEdges")
-        if world > 1:  # exchange per-shard sparse edge tables, merge-reduce on the device
-            import ctypes as C
-            dk, dw, n = C.c_void_p(), C.c_void_p(), C.c_int64()
-            g._ck(g.L.sqg_edges_device_table(g._h, C.byref(dk), C.byref(dw), C.byref(n)))
-            m = n.value
-            # one tiny all_reduce for the padded size, one all_gather of [count | keys | weights] per rank
-            mx_t = torch.tensor([m], dtype=torch.int64, device=dev)
-            dist.all_reduce(mx_t, op=dist.ReduceOp.MAX)
-            mx = int(mx_t.item())
-            buf = torch.zeros(1 + 2 * mx, dtype=torch.int64, device=dev)
-            buf[0] = m
-            if m:
-                buf[1:1 + m] = _dev_view(dk.value, m, torch.int64, dev)
-                buf[1 + mx:1 + mx + m] = _dev_view(dw.value, m, torch.int32, dev).to(torch.int64)
-            allb = torch.empty(world * (1 + 2 * mx), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allb, buf)
-            allb = allb.view(world, 1 + 2 * mx)
-            cnts = allb[:, 0].tolist()
-            # node indices are shard-local in this weak-scaling run; the merge-reduce cost is what is exercised
-            allk = torch.cat([allb[r, 1:1 + int(cnts[r])] for r in range(world)]); allw = torch.cat([allb[r, 1 + mx:1 + mx + int(cnts[r])] for r in range(world)]).to(torch.int32)
-            torch.cuda.current_stream().synchronize()  # the library works on its own stream
-            i1, i2, hd, w, ne = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
-            g._ck(g.L.sqg_merge_edge_tables(g._h, allk.data_ptr(), allw.data_ptr(), int(allk.shape[0]), C.byref(i1), C.byref(i2), C.byref(hd), C.byref(w), C.byref(ne)))
-            state["merged_edges"] = ne.value
         # The host stages between BuildEdges and ExactBPConcordantSupport (filters, ordering, ExactBreakpoint) are out of scope;
         # their stand-in only has to produce the sorted breakpoint list, which is the same every step: computed in the warm-up
         # steps, reused (and its cost reported separately) in the timed ones.
@@ -507,7 +484,7 @@ def main():
             state["bps"] = bps_from_graph(nodes, edges)
             state["bps_standin_ms"] = 1e3 * (time.perf_counter() - t_b)
         bc, bp = state["bps"]
-        lap("edge exchange + breakpoints (cached host stand-in)" if world > 1 else "breakpoints (cached host stand-in)")
+        lap("breakpoints (cached host stand-in)")
         cov = g.BPCoverage(bc, bp)
         lap("BPCoverage")
         state["stats"] = {k: g.stat(k) for k in ("groups", "islands", "heavy_islands", "giant_islands", "gap_records", "partial_records", "displaced_records", "lmax", "sensitive_reads", "raw_edges", "cov_chain_fallback", "cov_chain_chunks", "edges_single_path", "edges_generic_path", "slow_records", "qualifying_records", "seed_window_records", "short_other_blocks", "unstable_depth_blocks", "device_sort_status")}
@@ -639,7 +616,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
             "config": {"workload": "synthetic GRCh38-layout sorted alignment records, %d read pairs per GPU, ~0.5%% discordant (configs[1])" % P,
-                       "pairs_per_gpu": P, "pairs_requested": P_req, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": ("one GPU" if world == 1 else "weak scaling: one independent stream (sample) per GPU x%d, edge tables all-gathered over NCCL and merge-reduced on the device; `one_stream` = rank 0's stream in %d exact genomic-range shards (strong scaling)" % (world, world)),
+                       "pairs_per_gpu": P, "pairs_requested": P_req, "records": R, "blocks_per_record": K, "chimeric_reads": int(chim0.n_reads), "parallelism": ("one GPU" if world == 1 else "weak scaling: one independent stream (a sample of a cohort) per GPU x%d, no data-path collective (independent samples have nothing to exchange); `one_stream` = rank 0's stream in %d exact genomic-range shards with the NCCL exchanges of the sharded protocol (strong scaling)" % (world, world)),
                        "block_mix": "SURVEY App. C: K = %.3f aligned blocks per record (exon lengths %d-%d)" % (K, BENCH_EXON_LEN[0], BENCH_EXON_LEN[1]),
                        "l2": "inputs (%.1f GB) larger than L2" % (n_bytes / 1e9), "segments": state.get("n_nodes"), "edges": state.get("n_edges"), "breakpoints": state.get("n_bp"),
                        "breakpoint_source": "host stand-in for the out-of-scope stages between BuildEdges and ExactBPConcordantSupport, computed in the warm-up steps"},
@@ -672,18 +649,6 @@ def main():
         dist.destroy_process_group()
     if rank == 0 and parity and parity.get("checked") and not parity.get("ok"):
         raise SystemExit(3)  # a fast step with the wrong answer is not a result
-
-
-def _dev_view(ptr, n, dtype, dev):
-    """torch view of library-owned device memory (no copy)."""
-    import torch
-
-    class _Arr:
-        pass
-    a = _Arr()
-    itemsize = torch.empty(0, dtype=dtype).element_size()
-    a.__cuda_array_interface__ = {"shape": (int(n),), "typestr": {torch.int64: "<i8", torch.int32: "<i4"}[dtype], "data": (int(ptr), False), "version": 2, "strides": None}
-    return torch.as_tensor(a, device=dev)
 
 
 if __name__ == "__main__":
