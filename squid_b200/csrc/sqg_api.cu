@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(kSeedBlock) k_seed_prefix(SeedInputs in, const
 }
 // All other islands in parallel, each starting from an inherited (far-left) last segment: blocks [0, n_heavy) take one
 // heavy island each (SeedMachineT<CoopBlock>), the remaining blocks take one light island per warp (SeedMachineT<CoopWarp>).
-__global__ void __launch_bounds__(kSeedBlock, 2) k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar,
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_seed_islands(SeedInputs in, const int32_t *isl_start, int32_t n_isl, const int64_t *off_ops, const int64_t *off_mar,
                                                            SeedOp *ops, int32_t *margin, int32_t *n_out, int32_t *g_done, int32_t *err,
                                                            const int32_t *heavy, int32_t n_heavy, const int32_t *light, int32_t n_light) {
     __shared__ int32_t s_margins[kSeedMarginSmem];  // sorted margins of the island being processed (whole block, or one slice per warp)
@@ -321,9 +322,9 @@ __global__ void __launch_bounds__(kSeedBlock, 2) k_seed_islands(SeedInputs in, c
         seed_one_island<CoopBlock>(in, heavy[blockIdx.x], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr, s_margins, kSeedMarginSmem);
         return;
     }
-    const int32_t k = ((int32_t)blockIdx.x - n_heavy) * (kSeedBlock / 32) + (threadIdx.x >> 5);
+    const int32_t k = ((int32_t)blockIdx.x - n_heavy) * (BLOCK / 32) + (threadIdx.x >> 5);
     if (k >= n_light) return;
-    constexpr int32_t per_warp = kSeedMarginSmem / (kSeedBlock / 32);
+    constexpr int32_t per_warp = kSeedMarginSmem / (BLOCK / 32);
     seed_one_island<CoopWarp>(in, light[k], true, isl_start, n_isl, off_ops, off_mar, ops, margin, n_out, g_done, err, nullptr, s_margins + (threadIdx.x >> 5) * per_warp, per_warp);
 }
 
@@ -1939,7 +1940,9 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     }
     if (n_heavy - n_giant + n_light > 0) {
         PHASE_BEGIN("k_seed_islands");
-        k_seed_islands<<<(unsigned)(n_heavy - n_giant + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, 0, ctx->stream>>>(in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
+        // (block size measured at 100 M pairs: 256 threads 9.6 ms, 512 threads 7.5 ms, 1024 threads 8.9 ms -- the kernel needs both
+        // many islands in flight and many lanes on the few long ones)
+        k_seed_islands<kSeedBlock><<<(unsigned)(n_heavy - n_giant + (n_light + kSeedBlock / 32 - 1) / (kSeedBlock / 32)), kSeedBlock, 0, ctx->stream>>>(in, ctx->d_isl.p, n_isl, ctx->d_off_ops.p, ctx->d_off_mar.p,
                ctx->d_ops.p, ctx->d_margin.p, ctx->d_isl_nout.p, ctx->d_isl_gdone.p, d_err, ctx->d_heavy.p + n_giant, n_heavy - n_giant, ctx->d_light.p, n_light);
         ctx->launches++;
         CK(cudaGetLastError());
