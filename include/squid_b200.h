@@ -87,6 +87,14 @@ typedef struct sqg_chimeric {
     uint8_t *blk_is_reverse;
 } sqg_chimeric;
 
+/*
+ * Replaces SegmentGraph_t::ConnectedComponent (SegmentGraph.cpp:2986-3003 with DFS :2911-2935) on any graph
+ * given as edge end points: label[i] = index of node i's connected component, components numbered in the order of their smallest
+ * node -- what the reference's repeated scan + DFS produces.  Union-find on the device (links to the smaller index) + a prefix
+ * count of the roots.  Host arrays in, host array out; *n_components may be NULL.  Needs no context.
+ */
+int sqg_connected_components(int32_t device, int64_t n_nodes, const int32_t *ind1, const int32_t *ind2, int64_t n_edges, int32_t *label_out, int32_t *n_components);
+
 /* Creates a context on CUDA device `device`.  ref_len[n_ref] = RefLength (ReadRec.cpp:274-279). */
 int sqg_create(sqg_ctx **out, const sqg_config *cfg, const int32_t *ref_len, int32_t n_ref, int32_t device);
 void sqg_destroy(sqg_ctx *ctx);

@@ -1,4 +1,5 @@
-// The binding INTEGRATION.md describes, compiled for real: the four seams of SegmentGraph_t that make up the hot path,
+// The binding INTEGRATION.md describes, compiled for real: the four seams of SegmentGraph_t that make up the hot path (and one
+// of the next rows),
 // redefined on top of libsquid_b200.so (include/squid_b200.h, include/squid_b200_host.h).  This file is compiled against the
 // reference's OWN headers and linked with the reference's OWN, unmodified objects (ReadRec.cpp, SegmentGraph.cpp, WriteIO.cpp,
 // Config.cpp, built in place from /root/reference by integration/Makefile); the reference's definitions of these four member
@@ -9,6 +10,7 @@
 //   SegmentGraph_t::BuildEdges                src/SegmentGraph.cpp:1932  -> sqg_build_edges (+ UpdateNodeLink, the reference's own)
 //   SegmentGraph_t::ExactBreakpoint           src/SegmentGraph.cpp:3019  -> sqh_exact_breakpoint (host twin)
 //   SegmentGraph_t::ExactBPConcordantSupport  src/SegmentGraph.cpp:3083  -> sqg_bp_coverage between the reference's own glue
+//   SegmentGraph_t::ConnectedComponent        src/SegmentGraph.cpp:2986  -> sqg_connected_components
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -164,4 +166,13 @@ void SegmentGraph_t::ExactBPConcordantSupport(string Input_BAM, SBamrecord_t &Ch
         }
         ExactBP_concord_support[e] = supports;
     }
+}
+
+void SegmentGraph_t::ConnectedComponent() {
+    std::vector<int32_t> a(vEdges.size()), b(vEdges.size()), lab(vNodes.size());
+    for (size_t k = 0; k < vEdges.size(); k++) { a[k] = vEdges[k].Ind1; b[k] = vEdges[k].Ind2; }
+    const int dev = getenv("SQUID_B200_DEVICE") ? atoi(getenv("SQUID_B200_DEVICE")) : 0;
+    int32_t nc = 0;
+    if (sqg_connected_components(dev, (int64_t)vNodes.size(), a.data(), b.data(), (int64_t)a.size(), lab.data(), &nc)) fail("sqg_connected_components", "");
+    Label.assign(lab.begin(), lab.end());
 }

@@ -71,7 +71,7 @@ CHIM_DTYPES = {
 }
 
 EXPORTS = [
-    "sqg_create", "sqg_destroy", "sqg_last_error", "sqg_load_concordant", "sqg_load_concordant_wire", "sqg_download_concordant", "sqg_attach_concordant_device", "sqg_load_chimeric",
+    "sqg_create", "sqg_destroy", "sqg_last_error", "sqg_load_concordant", "sqg_load_concordant_wire", "sqg_download_concordant", "sqg_connected_components", "sqg_attach_concordant_device", "sqg_load_chimeric",
     "sqg_build_nodes", "sqg_set_nodes", "sqg_build_edges", "sqg_bp_coverage", "sqg_edges_device_table", "sqg_merge_edge_tables",
     "sqg_phase_ms", "sqg_launch_count", "sqg_stat", "sqg_selftest_gpu_sort",
     "sqg_plan_shards", "sqg_set_shard", "sqg_shard_seeds", "sqg_shard_build", "sqg_shard_hint_state", "sqg_shard_redo_edges",
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
     L.sqg_attach_concordant_device.argtypes = [_P, pp(sqg_batch), C.c_int64]
     L.sqg_load_concordant_wire.argtypes = [_P, pp(sqg_wire), C.c_int64]
     L.sqg_download_concordant.argtypes = [_P, pp(sqg_batch)]
+    L.sqg_connected_components.argtypes = [C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, pp(C.c_int32)]
     L.sqh_pack_wire.argtypes = [pp(sqg_batch), C.c_int32, pp(pp(sqg_wire))]
     L.sqh_free_wire.argtypes = [pp(sqg_wire)]; L.sqh_free_wire.restype = None
     L.sqh_wire_bytes.argtypes = [pp(sqg_wire)]; L.sqh_wire_bytes.restype = C.c_int64
@@ -573,6 +574,19 @@ def ExactBreakpoint(final_nodes: np.ndarray, Chimrecord: "ChimericReads", Concor
         raise SquidB200Error(rc, "sqh_exact_breakpoint failed")
     out = _np_from(rows, 6 * n.value, np.int32).reshape(-1, 6)
     L.sqh_free(rows)
+    return out
+
+
+def ConnectedComponent(n_nodes: int, Ind1, Ind2, device: int = 0) -> np.ndarray:
+    """Twin of SegmentGraph_t::ConnectedComponent (SegmentGraph.cpp:2986-3003) on the device: Label per node, components numbered
+    in the order of their smallest node."""
+    a = np.ascontiguousarray(Ind1, np.int32); b = np.ascontiguousarray(Ind2, np.int32)
+    assert a.shape == b.shape
+    out = np.empty(int(n_nodes), np.int32)
+    nc = C.c_int32()
+    rc = lib().sqg_connected_components(int(device), int(n_nodes), a.ctypes.data, b.ctypes.data, int(a.shape[0]), out.ctypes.data, C.byref(nc))
+    if rc != 0:
+        raise SquidB200Error(rc, "sqg_connected_components failed")
     return out
 
 

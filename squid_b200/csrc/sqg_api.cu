@@ -28,6 +28,7 @@
 #include "sq_gpusort.cuh"
 #include "sq_prepass.cuh"
 #include "sq_wire.cuh"
+#include "sq_cc.cuh"
 #include "sqg_ctx.cuh"
 
 using namespace sq;
@@ -938,6 +939,47 @@ extern "C" int sqg_load_concordant_wire(sqg_ctx *ctx, const sqg_wire *w, int64_t
     ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
     ctx->wire_loaded = true;
     return SQG_OK;
+}
+
+// SegmentGraph_t::ConnectedComponent on the device (sq_cc.cuh)
+extern "C" int sqg_connected_components(int32_t device, int64_t n_nodes, const int32_t *ind1, const int32_t *ind2, int64_t n_edges, int32_t *label_out, int32_t *n_components) {
+    if (n_nodes < 0 || n_edges < 0 || n_nodes >= 0x7fffff00ll || (n_edges > 0 && (!ind1 || !ind2)) || (n_nodes > 0 && !label_out)) return SQG_EINVAL;
+    if (n_components) *n_components = 0;
+    if (n_nodes == 0) return n_edges == 0 ? SQG_OK : SQG_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) return SQG_ENODEVICE;
+    DBuf<int32_t> parent, flag, rank, e1, e2, bad;
+    DBuf<uint8_t> temp;
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return SQG_ECUDA;
+    int rc = SQG_OK;
+    do {
+#define CC_CK(x) if ((x) != cudaSuccess) { cudaGetLastError(); rc = SQG_ECUDA; break; }
+        CC_CK(parent.ensure((size_t)n_nodes)); CC_CK(flag.ensure((size_t)n_nodes)); CC_CK(rank.ensure((size_t)n_nodes)); CC_CK(bad.ensure(1));
+        CC_CK(e1.ensure((size_t)(n_edges ? n_edges : 1))); CC_CK(e2.ensure((size_t)(n_edges ? n_edges : 1)));
+        CC_CK(cudaMemsetAsync(bad.p, 0, 4, st));
+        if (n_edges) { CC_CK(cudaMemcpyAsync(e1.p, ind1, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st)); CC_CK(cudaMemcpyAsync(e2.p, ind2, (size_t)n_edges * 4, cudaMemcpyHostToDevice, st)); }
+        k_cc_init<<<blocks_for(n_nodes), kThreads, 0, st>>>(parent.p, n_nodes);
+        if (n_edges) k_cc_hook<<<blocks_for(n_edges), kThreads, 0, st>>>(parent.p, e1.p, e2.p, n_edges, n_nodes, bad.p);
+        k_cc_flatten<<<blocks_for(n_nodes), kThreads, 0, st>>>(parent.p, n_nodes, flag.p);
+        size_t tb = 0;
+        CC_CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, rank.p, (int)n_nodes, st));
+        CC_CK(temp.ensure(tb ? tb : 1));
+        CC_CK(cub::DeviceScan::ExclusiveSum(temp.p, tb, flag.p, rank.p, (int)n_nodes, st));
+        k_cc_label<<<blocks_for(n_nodes), kThreads, 0, st>>>(parent.p, rank.p, n_nodes, flag.p);  // (flag is free again: the labels)
+        CC_CK(cudaGetLastError());
+        int32_t hbad = 0, last_rank = 0, last_root = 0;
+        CC_CK(cudaMemcpyAsync(label_out, flag.p, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost, st));
+        CC_CK(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, st));
+        CC_CK(cudaMemcpyAsync(&last_rank, rank.p + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
+        CC_CK(cudaMemcpyAsync(&last_root, parent.p + (n_nodes - 1), 4, cudaMemcpyDeviceToHost, st));
+        CC_CK(cudaStreamSynchronize(st));
+#undef CC_CK
+        if (hbad) { rc = SQG_EINVAL; break; }
+        if (n_components) *n_components = last_rank + (last_root == (int32_t)(n_nodes - 1) ? 1 : 0);
+    } while (false);
+    cudaStreamDestroy(st);
+    return rc;
 }
 
 // (test / diagnostic) the resident batch back into host arrays
