@@ -1954,8 +1954,10 @@ static int seed_stage(sqg_ctx *ctx, HostLap &lap) {
     if (getenv("SQG_SEED_PROF_OUT")) { cudaMalloc(&d_prof, (size_t)n_isl * 12 * 8); cudaMemset(d_prof, 0, (size_t)n_isl * 12 * 8); cudaDeviceSynchronize(); in.prof_out = d_prof; }
 #endif
     // Phase 3's compaction pass only needs the class bytes.  It is forked HERE, behind the short kernels of this stage and beside the
-    // island machine (latency-bound, a few resident warps per SM): enqueued right after the classification, its 10^5 blocks sat in
-    // front of the ConcordRest collection, which is on the critical path (5.7 ms instead of 1.4 ms).
+    // island machine: enqueued right after the classification, its 10^5 blocks sat in front of the ConcordRest collection, which is
+    // on the critical path (5.7 ms instead of 1.4 ms).  (The two share the SMs without gaining from it: alone the island kernel
+    // takes 5.4 ms and the compaction 2.3, together 7.6; forking the compaction beside the depth tile kernel instead moves the
+    // same 2 ms there.  The step is bound by the sum of the work, not by a critical path.)
     rc = run_cov_compact(ctx);
     if (rc) return rc;
     // the longest islands (sorted first) go to thread-block clusters on a second stream, concurrently with the rest
