@@ -31,6 +31,8 @@ struct P1Out {
     uint16_t *first_len;      // per record: length of the first kept block of a CLS_CONC record (65535 = too long for 16 bits), else 0
     TileAgg *agg;             // n_tiles
     uint32_t *cov_nq; uint64_t *cov_qmax;  // n_tiles: records of the tile that qualify for phase 3 (sq_phase3.cuh), their maximum start key
+    uint64_t *qstage_key; int32_t *qstage_end;  // n_rec: the (start key, fragment end) pairs of those records, compacted inside each tile:
+                                                // tile t owns [t * kTile, t * kTile + cov_nq[t]) (k_cov_gather closes the gaps)
     int32_t *ccmax;           // n_tiles: maximum end of the ConcordantCluster entries of the tile (kNoCcEnd: none; kCcWalkTile: several chromosomes)
     uint64_t *gate_word;      // n_tiles, zeroed: one-word chain of "1 + index of the last gate-passing record"
     int32_t *cand_rec; uint64_t *cand_key; int32_t *n_cand; int32_t cand_cap;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
     __shared__ int s_tile;
     __shared__ uint32_t s_gate[kTileChunks];
     __shared__ int32_t s_cmax[kTileChunks];   // per chunk: max key end, then the exclusive maximum before the chunk
-    __shared__ int32_t s_pc[kWarpsPerTile], s_dp[kWarpsPerTile];
+    __shared__ int32_t s_pc[kWarpsPerTile], s_dp[kWarpsPerTile], s_qcnt[kTileChunks];
     __shared__ long long s_prev_carry;
     __shared__ int32_t s_bad, s_lmax, s_minkeep, s_ccmax, s_nq, s_qmax;
     int32_t *s_end = s.end_pos;               // per record: end of the first block if the record updates otherrightmost, else 0
@@ -167,10 +169,10 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
             const int32_t rid = s.ref_id[i], ps = s.pos[i], mr = s.mate_ref_id[i], mp = s.mate_pos[i];
             if (cover_qualifies(c, f, rid, ps, mr, mp)) { qs = cover_start(f, rid, ps, mr, mp); if (qs < 0) qs = 0; }
         }
-        nq += __popc(__ballot_sync(full, qs >= 0));
+        const int chunk = j * kWarpsPerTile + warp;
+        { const int32_t cq = __popc(__ballot_sync(full, qs >= 0)); nq += cq; if (lane == 0) s_qcnt[chunk] = cq; }
         { const int32_t m = __reduce_max_sync(full, qs); if (m > q_max) q_max = m; }
         if (i < n) { s.cls[i] = c; s_end[i] = key_end; s_flen[i] = (uint16_t)(co_len < 65535 ? co_len : 65535); }
-        const int chunk = j * kWarpsPerTile + warp;
         npc += __popc(__ballot_sync(full, (c & CLS_PART) != 0));
         ndp += __popc(__ballot_sync(full, (c & (CLS_CONC | CLS_DISPL)) == (CLS_CONC | CLS_DISPL)));
         const unsigned km = __ballot_sync(full, (c & CLS_KEEP) != 0);
@@ -247,6 +249,33 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_classify_tiles(DevBatch b, 
         *reinterpret_cast<uint32_t *>(o.cls + rec0 + 4 * tid) = *reinterpret_cast<const uint32_t *>(&s.cls[4 * tid]);
         *reinterpret_cast<uint2 *>(o.first_len + rec0 + 4 * tid) = *reinterpret_cast<const uint2 *>(&s_flen[4 * tid]);
     } else for (int i = 4 * tid; i < n; i++) { o.cls[rec0 + i] = s.cls[i]; o.first_len[rec0 + i] = s_flen[i]; }
+    {   // phase 3's (fragment start key, fragment end) pairs of the tile, in record order, compacted inside the tile: the record
+        // fields are still staged, so the separate compaction pass over the whole batch (23 B per record) is gone
+        const int32_t cq = lane < kTileChunks ? s_qcnt[lane] : 0;
+        int32_t inc = cq;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(full, inc, d); if (lane >= d) inc += u; }
+        const int32_t exc = inc - cq;  // qualifying records of the tile before chunk `lane`
+#pragma unroll 1
+        for (int j = 0; j < kTileRPT; j++) {
+            const int i = j * kTileThreads + tid;
+            bool q = false;
+            uint64_t key = 0;
+            if (i < n) {
+                const uint8_t c = s.cls[i];
+                const uint16_t f = s.flag[i];
+                const int32_t rid = s.ref_id[i], ps = s.pos[i], mr = s.mate_ref_id[i], mp = s.mate_pos[i];
+                q = cover_qualifies(c, f, rid, ps, mr, mp);
+                if (q) key = chrpos_key(rid, cover_start(f, rid, ps, mr, mp));
+            }
+            const unsigned qm = __ballot_sync(full, q);
+            const int32_t before = __shfl_sync(full, exc, j * kWarpsPerTile + warp);
+            if (q) {
+                const int64_t at = (int64_t)tile * kTile + before + __popc(qm & ((1u << lane) - 1u));
+                o.qstage_key[at] = key; o.qstage_end[at] = b.end_pos[rec0 + i];
+            }
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         o.cov_nq[tile] = (uint32_t)s_nq;

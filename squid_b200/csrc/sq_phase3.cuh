@@ -1,9 +1,9 @@
 // Phase 3 of the path: concordant fragments covering each breakpoint (the BAM pass of ExactBPConcordantSupport,
 // SegmentGraph.cpp:3124-3166), two passes:
-//   k_cov_compact : ONE pass over the record fields the rule needs (23 B/record): the qualifying records -- right-hand
-//                   mates that pass the gate (:3136-3142) -- are compacted in stream order into (fragment start key,
-//                   fragment end) pairs.  Rank offsets and the running maximum of the start keys cross tiles through one
-//                   decoupled look-back chain; both are kept per tile, which is all the indBP threshold search needs.
+//   k_cov_gather  : the qualifying records -- right-hand mates that pass the gate (:3136-3142) -- as (fragment start key,
+//                   fragment end) pairs in stream order.  The classification kernel (sq_phase1.cuh) writes them per tile;
+//                   this pass closes the gaps at offsets that come from a scan of the per-tile counts.  Rank offsets and the
+//                   running maximum of the start keys are kept per tile, which is all the indBP threshold search needs.
 //   k_cov_count   : one pass over the compacted pairs (12 B each).  A block first intersects the position range of its
 //                   fragments with the sorted breakpoint list; most blocks see no breakpoint at all and stop there, the
 //                   others count against the few breakpoints in range from shared memory.
@@ -21,54 +21,24 @@ struct CovTile {
 
 constexpr int kCovTile = 2048, kCovThreads = 256, kCovRPT = kCovTile / kCovThreads, kCovWarps = kCovThreads / 32, kCovChunks = kCovTile / 32;
 static_assert(kCovTile % kTile == 0, "a coverage tile is a whole number of classification tiles");
-// rank0[t] / incmax[t]: qualifying records before classification tile t / maximum start key up to and including it (scans of the
-// per-tile counts the classification pass left behind): every block knows where its records go, no tile waits for another.
-__global__ void __launch_bounds__(kCovThreads) k_cov_compact(DevBatch b, const uint8_t *cls, const int64_t *rank0, const uint64_t *incmax, int32_t n_ctiles, int32_t n_tiles,
-                                                              uint64_t *qkey, int32_t *qend, CovTile *tiles) {
-    __shared__ int32_t s_cnt[kCovChunks];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned full = 0xffffffffu;
+// The qualifying records -- right-hand mates that pass the gate (:3136-3142) -- leave the classification kernel as (fragment start
+// key, fragment end) pairs compacted inside each 512-record tile (P1Out::qstage_*), together with the tile's count and maximum key.
+// rank0[t] / incmax[t] = qualifying records before classification tile t / maximum start key up to and including it (scans of
+// those per-tile values): this kernel only closes the gaps between the tiles -- 12 B read and written per qualifying record where
+// a separate compaction pass read 23 B of every record -- and no tile waits for another.
+__global__ void __launch_bounds__(kCovThreads) k_cov_gather(const uint64_t *stage_key, const int32_t *stage_end, const uint32_t *nq_tile, const int64_t *rank0, const uint64_t *incmax,
+                                                             int32_t n_ctiles, int32_t n_tiles, uint64_t *qkey, int32_t *qend, CovTile *tiles) {
     const int tile = blockIdx.x;
-    const int64_t rec0 = (int64_t)tile * kCovTile;
-    uint64_t key[kCovRPT]; int32_t endp[kCovRPT]; unsigned qm[kCovRPT];
-#pragma unroll
-    for (int j = 0; j < kCovRPT; j++) {
-        const int64_t r = rec0 + j * kCovThreads + tid;
-        bool q = false;
-        key[j] = 0; endp[j] = 0;
-        if (r < b.n_rec) {
-            const uint16_t f = b.flag[r];
-            const int32_t rid = b.ref_id[r], pos = b.pos[r], mrid = b.mate_ref_id[r], mpos = b.mate_pos[r];
-            q = cover_qualifies(cls[r], f, rid, pos, mrid, mpos);
-            if (q) { key[j] = chrpos_key(rid, cover_start(f, rid, pos, mrid, mpos)); endp[j] = b.end_pos[r]; }
-        }
-        qm[j] = __ballot_sync(full, q);
-        if (lane == 0) s_cnt[j * kCovWarps + warp] = __popc(qm[j]);
+    constexpr int kPer = kCovTile / kTile;
+    const int ct0 = tile * kPer;
+    int ct1 = ct0 + kPer - 1;
+    if (ct1 > n_ctiles - 1) ct1 = n_ctiles - 1;
+    for (int ct = ct0; ct <= ct1; ct++) {
+        const int32_t cnt = (int32_t)nq_tile[ct];
+        const int64_t base = rank0[ct], src = (int64_t)ct * kTile;
+        for (int k = threadIdx.x; k < cnt; k += kCovThreads) { qkey[base + k] = stage_key[src + k]; qend[base + k] = stage_end[src + k]; }
     }
-    __syncthreads();
-    if (warp == 0) {
-        // exclusive scan of the kCovChunks (= 64) chunk counts: two consecutive chunks per lane
-        const int32_t v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1];
-        int32_t inc = v0 + v1;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int32_t u = __shfl_up_sync(full, inc, d); if (lane >= d) inc += u; }
-        s_cnt[2 * lane] = inc - v0 - v1; s_cnt[2 * lane + 1] = inc - v1;
-        if (lane == 0) {
-            const int ct0 = tile * (kCovTile / kTile);
-            int ct1 = ct0 + (kCovTile / kTile) - 1;
-            if (ct1 > n_ctiles - 1) ct1 = n_ctiles - 1;
-            CovTile t; t.rank0 = rank0[ct0]; t.incmax = incmax[ct1];
-            tiles[tile] = t;
-        }
-    }
-    __syncthreads();
-    const int64_t base = rank0[tile * (kCovTile / kTile)];
-#pragma unroll
-    for (int j = 0; j < kCovRPT; j++)
-        if (qm[j] & (1u << lane)) {
-            const int64_t at = base + s_cnt[j * kCovWarps + warp] + __popc(qm[j] & ((1u << lane) - 1u));
-            qkey[at] = key[j]; qend[at] = endp[j];
-        }
+    if (threadIdx.x == 0) { CovTile t; t.rank0 = rank0[ct0]; t.incmax = incmax[ct1]; tiles[tile] = t; }
 }
 
 // r0[k] = first qualifying rank whose running-maximum start key exceeds (chr, pos + dist) of breakpoint k (nq if none);

@@ -1346,6 +1346,7 @@ static int run_classify(sqg_ctx *ctx) {
     ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n; ctx->end_other = 0;
     if (n > 0) {
         const int64_t n_tiles = (n + kTile - 1) / kTile;
+        CK(ctx->d_qstage_key.ensure((size_t)n + 1)); CK(ctx->d_qstage_end.ensure((size_t)n + 1));
         CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8)); CK(ctx->d_ccmax.ensure(n_tiles + 1)); CK(ctx->d_cov_nq.ensure(n_tiles + 2)); CK(ctx->d_cov_qmax.ensure(n_tiles + 2));
         int64_t cand_cap = std::max<int64_t>({(int64_t)ctx->d_cand_key.cap, n / 16, (int64_t)1 << 20});
         int32_t n_cand = 0;
@@ -1353,7 +1354,7 @@ static int run_classify(sqg_ctx *ctx) {
             cand_cap = std::min<int64_t>(cand_cap, n + 1);
             CK(ctx->d_cand_key.ensure(cand_cap));
             P1Out o;
-            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.ccmax = ctx->d_ccmax.p; o.cov_nq = ctx->d_cov_nq.p; o.cov_qmax = ctx->d_cov_qmax.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
+            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.ccmax = ctx->d_ccmax.p; o.cov_nq = ctx->d_cov_nq.p; o.cov_qmax = ctx->d_cov_qmax.p; o.qstage_key = ctx->d_qstage_key.p; o.qstage_end = ctx->d_qstage_end.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
             o.cand_rec = ctx->d_scratch32.p; o.cand_key = ctx->d_cand_key.p; o.cand_cap = (int32_t)cand_cap;
             // counters: [0..1] totals n_gap, n_pc, n_dp (int32) | [2] first_kept | [3] lmax | [4] n_cand, ticket (int32) | [20] validation flags
             CK(cudaMemsetAsync(ctx->d_counters.p, 0, 5 * sizeof(int64_t), ctx->stream));
@@ -1524,7 +1525,8 @@ static int run_cov_compact(sqg_ctx *ctx) {
         ctx->launches += 4;
         int rc = phase_begin(ctx, "k_cov_compact", st);
         if (rc) return rc;
-        k_cov_compact<<<(unsigned)n_tiles, kCovThreads, 0, st>>>(b, ctx->d_cls.p, ctx->d_cov_rank0.p, ctx->d_cov_incmax.p, (int32_t)n_ct, (int32_t)n_tiles, ctx->d_qkey.p, ctx->d_qend.p, ctx->d_covtile.p);
+        k_cov_gather<<<(unsigned)n_tiles, kCovThreads, 0, st>>>(ctx->d_qstage_key.p, ctx->d_qstage_end.p, ctx->d_cov_nq.p, ctx->d_cov_rank0.p, ctx->d_cov_incmax.p, (int32_t)n_ct, (int32_t)n_tiles,
+                                                                ctx->d_qkey.p, ctx->d_qend.p, ctx->d_covtile.p);
         ctx->launches++;
         CK(cudaGetLastError());
         rc = phase_end(ctx, "k_cov_compact", st);

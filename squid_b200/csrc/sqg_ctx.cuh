@@ -135,6 +135,7 @@ struct sqg_ctx {
     sq::DBuf<uint32_t> d_chain32;
     sq::DBuf<sq::TileAgg> d_tileagg;  // per-tile aggregates / exclusive prefixes of phase 1
     sq::DBuf<uint32_t> d_cov_nq; sq::DBuf<uint64_t> d_cov_qmax, d_cov_incmax; sq::DBuf<int64_t> d_cov_rank0; sq::DBuf<uint8_t> d_temp_cov;  // phase 3: per classification tile
+    sq::DBuf<uint64_t> d_qstage_key; sq::DBuf<int32_t> d_qstage_end;  // phase 3's pairs as the classification kernel leaves them (per tile)
     sq::DBuf<int32_t> d_ccmax;        // per tile: maximum end of its ConcordantCluster entries (consume_cc of the seed machine)
     sq::DBuf<unsigned char> d_desc;   // device copy of the batch descriptor
     sq::DBuf<uint64_t> d_cand_key;    // coverage-gap candidates (their record indices live in d_scratch32)
