@@ -555,7 +555,8 @@ def main():
 
     # ---- roofline ------------------------------------------------------------------------------------------------------
     # Every timed kernel with its algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md §3): the stream kernels read the whole
-    # batch (32 B per record + 12 B per aligned block); phase 3's pairs leave the classification kernel per tile and are gathered (12 B
+    # batch (32 B per record + 12 B per aligned block); phase 3's pairs leave the classification kernel per tile (12 B written per
+    # qualifying record on top of its read of the batch) and are gathered (12 B
     # read + 12 B written per qualifying record), then counted (12 B per qualifying record); the generic
     # edge kernel the records it is handed (32 B + 12 B per block of each).  The seed machine's input is the window of concordant
     # records in front of each discordant group (7 B each: pos, first-block length, class), counted by the kernel itself; it
@@ -563,7 +564,7 @@ def main():
     K = NB / R
     st_ = state.get("stats", {})
     n_slow = max(0, st_.get("slow_records", 0)); nq = max(0, st_.get("qualifying_records", 0))
-    alg = {"k_classify": 32 * R + 12 * NB, "k_assign_depth": 32 * R + 12 * NB, "k_assign_edges": 32 * R + 12 * NB, "k_cov_compact": 24 * nq,
+    alg = {"k_classify": 32 * R + 12 * NB + 12 * nq, "k_assign_depth": 32 * R + 12 * NB, "k_assign_edges": 32 * R + 12 * NB, "k_cov_compact": 24 * nq,
            "k_edges_generic": int(n_slow * (32 + 12 * max(2.0, K))), "k_cov_count": 12 * nq, "k_seed_islands": 7 * max(0, st_.get("seed_window_records", 0))}
     # DRAM bytes per record of each kernel from this round's `ncu --set full` capture (profiles/r2_traffic.json, written by
     # tests/tools/ncu_summary.py from the committed capture; dram__bytes_read.sum + dram__bytes_write.sum over the records of that run)
