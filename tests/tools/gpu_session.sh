@@ -9,7 +9,7 @@ timeout 2400 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_pytest_gpu.
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -2 gpurun_out/${TAG}_bench.err
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'sq::|cub::|^k_|gsort' -c 1800 --csv --log-file gpurun_out/${TAG}_launches_100M.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
-timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_classify_tiles|k_assign_tiles|k_edges_generic|k_seed_islands|k_cov_compact|k_cov_count_tiles' -c 10 -o gpurun_out/${TAG}_prof_20M python bench.py --pairs 20000000 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_classify_tiles|k_assign_tiles|k_edges_generic|k_seed_islands|k_cov_gather|k_cov_count_tiles' -c 11 -o gpurun_out/${TAG}_prof_20M python bench.py --pairs 20000000 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_wire_decode' -c 2 -o gpurun_out/${TAG}_prof_wire_20M python bench.py --pairs 20000000 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_wire.log 2>&1
 REC=$(grep -o '"records": [0-9]*' gpurun_out/${TAG}_ncu_full.log | head -1 | grep -o '[0-9]*$')
 python tests/tools/ncu_summary.py gpurun_out/${TAG}_prof_20M.ncu-rep --records $REC --traffic-json gpurun_out/${TAG}_traffic.json > gpurun_out/${TAG}_ncu_summary.txt
