@@ -1728,13 +1728,10 @@ static int run_assign(sqg_ctx *ctx, bool do_depth, bool do_edges) {
                     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
                 }
                 PHASE_BEGIN("k_edges_generic");
-                // resident blocks per SM the generic kernel is compiled for (it is bound by the latency of dependent loads: more warps,
-                // fewer registers each -- 64 at 8 blocks -- beat fewer warps without local-memory traffic: 5.4 ms against 6.7 ms at 7)
-                static const int gen_occ = getenv("SQG_GENERIC_OCC") ? atoi(getenv("SQG_GENERIC_OCC")) : 8;
-                if (gen_occ >= 12) LAUNCH(k_edges_generic<12>, 148 * 16, 128, a);
-                else if (gen_occ >= 10) LAUNCH(k_edges_generic<10>, 148 * 16, 128, a);
-                else if (gen_occ >= 8) LAUNCH(k_edges_generic<8>, 148 * 16, 128, a);
-                else LAUNCH(k_edges_generic<7>, 148 * 16, 128, a);
+                // the generic kernel is compiled for 8 resident blocks per SM (64 registers): it is bound by the latency of dependent
+                // loads, and more warps with fewer registers each beat fewer warps without local-memory traffic -- measured at 100 M
+                // pairs: 7 blocks (72 registers) 6.7 ms, 8 blocks 5.4 ms, 10 and 12 blocks (48 / 40 registers) 5.5 ms
+                LAUNCH(k_edges_generic<8>, 148 * 16, 128, a);
                 PHASE_END("k_edges_generic");
                 LAUNCH(k_fix_heads, 256, 128, ctx->d_scratch32.p, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, ctx->shard_init_hint, (int32_t *)(ctx->d_counters.p + 22));
                 LAUNCH(k_fix_chains<false>, 256, 128, b, cd, ctx->params, ctx->nt, ctx->d_scratch32.p, n, ctx->d_sens.p, d_nsens, conc_sens_cap, ctx->d_head.p, sink);
