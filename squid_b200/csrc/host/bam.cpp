@@ -279,6 +279,7 @@ AlnSource BamTable::source() const {
         return a;
     };
     s.name = [t](uint64_t r) { return std::string(t->names.data() + t->name_off[r], (size_t)(t->name_off[r + 1] - t->name_off[r])); };
+    s.name_into = [t](uint64_t r, char *buf) { const size_t len = (size_t)(t->name_off[r + 1] - t->name_off[r]); memcpy(buf, t->names.data() + t->name_off[r], len); return len; };
     return s;
 }
 

@@ -2,6 +2,9 @@
 #include "chimeric.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 namespace sqh {
@@ -29,11 +32,27 @@ std::string name_at(const SqmbView &v, uint64_t r) {
     return s;
 }
 
+// name_at() into a buffer: 'q' + decimal name_id (+ "/1" or "/2")
+static size_t name_into_at(const SqmbView &v, uint64_t r, char *buf) {
+    char tmp[24];
+    int k = 0;
+    long long x = (long long)v.name_id[r];
+    const bool neg = x < 0;
+    unsigned long long u = neg ? 0ull - (unsigned long long)x : (unsigned long long)x;
+    do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+    size_t n = 0;
+    buf[n++] = 'q';
+    if (neg) buf[n++] = '-';
+    while (k) buf[n++] = tmp[--k];
+    if (v.aux[r] & 4) { buf[n++] = '/'; buf[n++] = (v.flag[r] & 0x80) ? '2' : '1'; }
+    return n;
+}
 AlnSource source_of(const SqmbView &v) {
     AlnSource s;
     s.n_rec = v.n_rec;
     s.at = [&v](uint64_t r) { return alignment_at(v, r); };
     s.name = [&v](uint64_t r) { return name_at(v, r); };
+    s.name_into = [&v](uint64_t r, char *buf) { return name_into_at(v, r, buf); };
     return s;
 }
 void load_chimeric(const SqmbView &chim, HostConfig &cfg, std::vector<Read> &out) { load_chimeric(source_of(chim), cfg, out); }
@@ -110,9 +129,25 @@ sqg_batch PackedBatch::view() const {
 
 int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::unordered_set<std::string> &chim_names, PackedBatch &out, std::string &err) {
     const uint64_t n = conc.n_rec;
+    const bool timing = getenv("SQH_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (!timing) return; const auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[sqh]   pack: %-20s %8.3f ms\n", what, 1e3 * std::chrono::duration<double>(t - t_last).count()); t_last = t; };
     out.ref_id.resize(n); out.pos.resize(n); out.mate_ref_id.resize(n); out.mate_pos.resize(n); out.flag.resize(n); out.mapq.resize(n);
     out.end_pos.resize(n); out.total_len.resize(n); out.lowphred_run.resize(n); out.aux.resize(n);
     out.blk_off.assign(n + 1, 0);
+    lap("allocate");
+    // ChimName probe (SegmentGraph.cpp:302, a binary search over strings in the reference): nearly every record misses, so a
+    // two-probe Bloom filter over a 64-bit hash of the name answers first and only a hit goes to the exact set
+    auto fnv = [](const char *p, size_t len) { uint64_t h = 1469598103934665603ull; for (size_t i = 0; i < len; i++) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } return h; };
+    size_t bloom_bits = 1024;
+    while (bloom_bits < 16 * chim_names.size()) bloom_bits <<= 1;
+    std::vector<uint64_t> bloom(bloom_bits / 64, 0);
+    for (const std::string &nm : chim_names) {
+        const uint64_t h = fnv(nm.data(), nm.size());
+        const uint64_t a = h & (bloom_bits - 1), b2 = (h >> 32) & (bloom_bits - 1);
+        bloom[a >> 6] |= 1ull << (a & 63); bloom[b2 >> 6] |= 1ull << (b2 & 63);
+    }
+    const bool probe_names = !chim_names.empty();
     // pass 1 (parallel over record ranges): per-record summaries and block counts
     const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     std::vector<std::vector<Block>> tblocks(nt);
@@ -121,6 +156,8 @@ int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::uno
         const uint64_t lo = n * t / nt, hi = n * (t + 1) / nt;
         Decoded d;
         std::vector<Block> &acc = tblocks[t];
+        acc.reserve((size_t)((hi - lo) + (hi - lo) / 2 + 16));
+        char nbuf[320];
         for (uint64_t r = lo; r < hi; r++) {
             Alignment a = conc.at(r);
             out.ref_id[r] = a.ref_id; out.pos[r] = a.pos; out.mate_ref_id[r] = a.mate_ref_id; out.mate_pos[r] = a.mate_pos;
@@ -135,7 +172,16 @@ int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::uno
             uint8_t aux = 0;
             if (a.tag_xa) aux |= SQG_AUX_XA;
             if (a.tag_ih && a.ih_value > 1) aux |= SQG_AUX_IH_GT1;
-            if (!chim_names.empty() && chim_names.count(conc.name(r))) aux |= SQG_AUX_CHIMNAME;
+            if (probe_names) {
+                bool maybe = true;
+                if (conc.name_into) {
+                    const size_t len = conc.name_into(r, nbuf);
+                    const uint64_t h = fnv(nbuf, len);
+                    const uint64_t x = h & (bloom_bits - 1), y = (h >> 32) & (bloom_bits - 1);
+                    maybe = ((bloom[x >> 6] >> (x & 63)) & 1ull) && ((bloom[y >> 6] >> (y & 63)) & 1ull);
+                    if (maybe && chim_names.count(std::string(nbuf, len))) aux |= SQG_AUX_CHIMNAME;
+                } else if (chim_names.count(conc.name(r))) aux |= SQG_AUX_CHIMNAME;
+            }
             out.aux[r] = aux;
             out.blk_off[r + 1] = (uint32_t)d.blocks.size();
             acc.insert(acc.end(), d.blocks.begin(), d.blocks.end());
@@ -144,20 +190,29 @@ int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::uno
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
     for (auto &x : th) x.join();
+    lap("decode (parallel)");
     for (unsigned t = 0; t < nt; t++) if (!terr[t].empty()) { err = terr[t]; return SQG_EUNSUPPORTED; }
-    uint64_t total_blocks = 0;
-    for (uint64_t r = 0; r < n; r++) total_blocks += out.blk_off[r + 1];
-    if (total_blocks > 0xFFFFFFFFull) { err = "more than 2^32 - 1 aligned blocks in one batch: shard the stream"; return SQG_EUNSUPPORTED; }
-    for (uint64_t r = 0; r < n; r++) out.blk_off[r + 1] += out.blk_off[r];
-    const size_t nb = out.blk_off[n];
+    // block offsets: every thread's range starts where the blocks of the ranges before it end
+    std::vector<uint64_t> tbase(nt + 1, 0);
+    for (unsigned t = 0; t < nt; t++) tbase[t + 1] = tbase[t] + tblocks[t].size();
+    if (tbase[nt] > 0xFFFFFFFFull) { err = "more than 2^32 - 1 aligned blocks in one batch: shard the stream"; return SQG_EUNSUPPORTED; }
+    const size_t nb = (size_t)tbase[nt];
     out.blk_ref_pos.resize(nb); out.blk_match_ref.resize(nb); out.blk_read_pos.resize(nb); out.blk_match_read.resize(nb);
-    size_t o = 0;
-    for (unsigned t = 0; t < nt; t++)
+    auto tail = [&](unsigned t) {
+        const uint64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        uint32_t run = (uint32_t)tbase[t];
+        for (uint64_t r = lo; r < hi; r++) { const uint32_t c = out.blk_off[r + 1]; out.blk_off[r + 1] = run + c; run += c; }  // blk_off[r + 1] = blocks up to and including r
+        size_t o = (size_t)tbase[t];
         for (const Block &b : tblocks[t]) {
             out.blk_ref_pos[o] = b.ref_pos; out.blk_match_ref[o] = b.match_ref;
             out.blk_read_pos[o] = (uint16_t)b.read_pos; out.blk_match_read[o] = (uint16_t)b.match_read;
             o++;
         }
+    };
+    th.clear();
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(tail, t);
+    for (auto &x : th) x.join();
+    lap("offsets + block copy");
     return SQG_OK;
 }
 

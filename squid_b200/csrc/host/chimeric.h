@@ -22,6 +22,7 @@ struct AlnSource {
     uint64_t n_rec = 0;
     std::function<Alignment(uint64_t)> at;
     std::function<std::string(uint64_t)> name;   // BamAlignment::Name, raw
+    std::function<size_t(uint64_t, char *)> name_into;  // the same into a caller buffer of >= 256 bytes (no allocation); returns the length
 };
 AlnSource source_of(const SqmbView &v);
 void load_chimeric(const AlnSource &chim, HostConfig &cfg, std::vector<Read> &out);

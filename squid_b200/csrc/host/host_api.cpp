@@ -2,6 +2,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <unordered_set>
 
@@ -28,6 +31,18 @@ void sqh_default_options(sqh_options *o) {
     o->phred33 = 1; o->max_lowphred_len = 10; o->min_phred = 4; o->min_mapq = -1; o->concord_dist_pos = 50000; o->concord_dist_idx = 20;
 }
 
+namespace {
+struct HostLaps {  // SQH_TIMING=1: wall-clock laps of the host front end, to stderr
+    bool on; std::chrono::steady_clock::time_point t0;
+    HostLaps() : on(getenv("SQH_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void operator()(const char *what) {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sqh] %-28s %8.3f ms\n", what, 1e3 * std::chrono::duration<double>(t - t0).count());
+        t0 = t;
+    }
+};
+}  // namespace
 static int open_case(bool bam, const char *conc_path, const char *chim_path, const sqh_options *opt, sqh_case **out, char *errbuf, int errlen) {
     auto fail = [&](int code, const std::string &m) { if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", m.c_str()); return code; };
     if (!conc_path || !chim_path || !out) return fail(SQG_EINVAL, "null argument");
@@ -51,14 +66,20 @@ static int open_case(bool bam, const char *conc_path, const char *chim_path, con
         c->ref_len.assign(c->conc.ref_len, c->conc.ref_len + c->conc.n_ref);
         sconc = sqh::source_of(c->conc); schim = sqh::source_of(c->chim);
     }
+    HostLaps lap;
+    lap("open files");
     sqh::load_chimeric(schim, c->cfg, c->reads);
+    lap("chimeric loader");
     std::unordered_set<std::string> names;
     names.insert("");  // ChimName is pre-sized with empty strings before the names are appended (SegmentGraph.cpp:196-198)
     for (const sqh::Read &r : c->reads) names.insert(r.qname);
+    lap("ChimName set");
     std::string err;
     int rc = sqh::pack_concordant(sconc, c->cfg, names, c->batch, err);
     if (rc) { delete c; return fail(rc, err); }
+    lap("decode + pack concordant");
     c->pchim.from_reads(c->reads);
+    lap("pack chimeric");
     c->bview = c->batch.view();
     c->cview = c->pchim.view();
     c->gcfg.using_star = 1; c->gcfg.max_lowphred_len = c->cfg.max_lowphred_len; c->gcfg.min_mapq = c->cfg.min_mapq;

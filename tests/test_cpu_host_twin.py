@@ -124,3 +124,34 @@ def test_parallel_sort_reproduces_std_sort(built_lib):
                     if n > 500000 and (fan != 8 or rng not in (3, 1 << 40)):
                         continue  # the largest size only on the fully parallel path
                     assert L.sqh_selftest_sort(n, n * 31 + rng + pat, rng, pat, fan) == 1, (n, rng, pat, fan)
+
+
+def test_chimname_gate_bits_match_brute_force(tmp_path):
+    """SQG_AUX_CHIMNAME of the packed batch (SegmentGraph.cpp:302: the RAW record name looked up in the suffix-stripped Qnames of
+    Chimrecord, plus the empty strings ChimName is pre-sized with) against a plain Python set -- the packer answers through a Bloom
+    filter first, so every bit is checked, hits and misses."""
+    from squid_b200 import api, sqmb, synth
+    conc, chim, info = synth.make_case(30000, ref_len=synth.CHR17_LEN, seed=77, disc_frac=0.05)
+    # give some concordant records the name of a chimeric read (with and without the /1 /2 suffix)
+    rng = np.random.default_rng(3)
+    take = rng.choice(conc.n, size=400, replace=False)
+    conc.name_id[take] = rng.choice(chim.name_id, size=400)
+    cp, hp = str(tmp_path / "c.sqmb"), str(tmp_path / "h.sqmb")
+    sqmb.write_sqmb(cp, conc); sqmb.write_sqmb(hp, chim)
+
+    def raw_name(t, r):
+        s = "q%d" % t.name_id[r]
+        if t.aux[r] & sqmb.AUX_NAME_SUFFIX:
+            s += "/2" if t.flag[r] & 0x80 else "/1"
+        return s
+    names = {""}
+    for r in range(chim.n):
+        if (chim.flag[r] & 0x4) or (chim.flag[r] & 0x400):
+            continue
+        s = raw_name(chim, r)
+        names.add(s[:-2] if s.endswith(("/1", "/2")) else s)
+    want = np.array([raw_name(conc, r) in names for r in range(conc.n)])
+    case = api.HostCase(cp, hp)
+    got = (case.batch.a["aux"] & 8) != 0
+    assert want.sum() > 50 and (~want).sum() > 1000
+    assert np.array_equal(got, want)
