@@ -147,12 +147,17 @@ def lib() -> C.CDLL:
     return L
 
 
-def _np_from(ptr, n, dtype) -> np.ndarray:
+def _np_from(ptr, n, dtype, owner=None) -> np.ndarray:
+    """Array over library memory.  owner=None: a copy.  Else a VIEW (no copy) that keeps `owner` -- the object whose close()
+    releases the memory -- alive for as long as the array (or anything sliced from it) lives."""
     n = int(n)
     if n == 0:
         return np.zeros(0, dtype=dtype)
     buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr if isinstance(ptr, int) else ptr.value)
-    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+    if owner is None:
+        return np.frombuffer(buf, dtype=dtype, count=n).copy()
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dtype, count=n)
 
 
 @dataclass
@@ -188,11 +193,12 @@ class RecordBatch:
         return s
 
     @staticmethod
-    def from_struct(s: sqg_batch) -> "RecordBatch":
+    def from_struct(s: sqg_batch, owner=None) -> "RecordBatch":
+        """owner: the object that owns the arrays of `s` (they are then viewed, not copied: a 100 M-pair batch is 9 GB)."""
         d = {}
         for k, dt in BATCH_DTYPES.items():
             n = s.n_blk if k.startswith("blk_") and k != "blk_off" else (s.n_rec + 1 if k == "blk_off" else s.n_rec)
-            d[k] = _np_from(getattr(s, k), n, dt)
+            d[k] = _np_from(getattr(s, k), n, dt, owner)
         return RecordBatch(d)
 
     def slice(self, lo: int, hi: int) -> "RecordBatch":
@@ -300,7 +306,7 @@ class HostCase:
         if rc != 0:
             raise SquidB200Error(rc, err.value.decode())
         self._h = h
-        self.batch = RecordBatch.from_struct(L.sqh_case_batch(h).contents)
+        self.batch = RecordBatch.from_struct(L.sqh_case_batch(h).contents, owner=self)  # views into the case (valid until close())
         self.chimeric = ChimericReads.from_struct(L.sqh_case_chimeric(h).contents)
         g = L.sqh_case_config(h).contents
         self.config = Config(True, o.phred33, g.max_lowphred_len, o.min_phred, g.min_mapq, g.concord_dist_pos, g.concord_dist_idx, g.read_len)
