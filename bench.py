@@ -629,7 +629,7 @@ def main():
                        "l2": "inputs (%.1f GB) larger than L2" % (n_bytes / 1e9), "segments": state.get("n_nodes"), "edges": state.get("n_edges"), "breakpoints": state.get("n_bp"),
                        "breakpoint_source": "host stand-in for the out-of-scope stages between BuildEdges and ExactBPConcordantSupport, computed in the warm-up steps"},
             "e2e": {"value": world * P / sec_e2e, "unit": "read pairs/s", "h2d_bytes_per_step": wire.nbytes + sum(v.nbytes for v in chim0.a.values()), "d2h_bytes_per_step": state.get("d2h", 0), "ms_per_step": 1e3 * sec_e2e, "host_memory": host_kind,
-                    "input": "sqg_wire (include/squid_b200.h): delta-coded records, 13 B + 8 B per block, %d record and %d block exceptions; uploaded in chunks, widened on the device while the next chunks are on the bus" % (wire.struct.n_rec_exc, wire.struct.n_blk_exc),
+                    "input": "sqg_wire (include/squid_b200.h): delta-coded records, 13 B + 8 B per explicit block (%d of %d blocks are implied by their record: plain unclipped reads), %d record and %d block exceptions; uploaded in chunks, widened on the device while the next chunks are on the bus" % (wire.struct.n_blk - wire.struct.n_wblk, wire.struct.n_blk, wire.struct.n_rec_exc, wire.struct.n_blk_exc),
                     "pack_wire_s_outside_timed_region": t_pack, "pack_threads": os.cpu_count()},
             "e2e_soa": ({"value": world * P / sec_soa, "unit": "read pairs/s", "h2d_bytes_per_step": n_bytes + sum(v.nbytes for v in chim0.a.values()), "ms_per_step": 1e3 * sec_soa,
                          "input": "sqg_batch (the resident 32 B + 12 B layout) copied as it is", "phases_ms": phases_soa} if sec_soa else None),

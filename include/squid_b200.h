@@ -108,15 +108,18 @@ const char *sqg_last_error(const sqg_ctx *ctx);
  */
 int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *batch, int64_t first_record_index);
 /*
- * Compact wire form of an sqg_batch for the host -> HBM transfer (13 B per record + 8 B per block instead of 32 + 12): the
+ * Compact wire form of an sqg_batch for the host -> HBM transfer (13 B per record + 8 B per explicit block instead of 32 + 12): the
  * transfer over PCIe is what an end-to-end call waits for, so the stream is shipped delta-coded and widened on the device.
- * Records are cut into tiles of SQG_WIRE_TILE consecutive records; tile t carries the (ref_id, pos) of its first record and the
- * index of its first block.  Per record: dpos = pos - pos of the previous record (0 for the first record of a tile; same ref_id as
- * that record), span = end_pos - pos, dmate = mate_pos - pos (mate on the same ref_id), lowphred_run as one byte, aux (low 4 bits) | block count (high 4 bits); flag,
- * total_len, mapq and the blocks' read_pos / match_read are shipped as they are.  Per block: dref = ref_pos - pos of its record
- * and match_ref as 16 bits.  A value that does not fit is stored as the escape (0xFFFF; dmate -32768; lowphred_run 255; block
- * count 15) and its record / block is listed in full in rec_exc / blk_exc (sorted by index; tile t owns entries
- * [tile_rec_exc_off[t], tile_rec_exc_off[t+1]) resp. tile_blk_exc_off).  Lossless for every valid sqg_batch whose aux < 16.
+ * Records are cut into tiles of SQG_WIRE_TILE consecutive records; tile t carries the (ref_id, pos) of its first record, the
+ * index of its first block in the batch (tile_blk_off) and in the wire block arrays (tile_wblk_off).  Per record: dpos = pos - pos
+ * of the previous record (0 for the first record of a tile; same ref_id as that record), span = end_pos - pos, dmate = mate_pos -
+ * pos (mate on the same ref_id), lowphred_run as one byte, aux (low 4 bits) | block code (high 4 bits); flag, total_len and mapq
+ * are shipped as they are.  Block code 0..13 = that many explicit blocks; 14 = ONE block that the record implies (ref_pos = pos,
+ * match_ref = match_read = span, read_pos = 0: an unclipped, unspliced read -- two records in three) and that is not shipped at
+ * all; 15 = escape.  Per explicit block: dref = ref_pos - pos of its record and match_ref as 16 bits, read_pos, match_read.  A
+ * value that does not fit is stored as the escape (0xFFFF; dmate -32768; lowphred_run 255; block code 15) and its record / block
+ * is listed in full in rec_exc / blk_exc (sorted by index -- record index resp. index into the WIRE block arrays; tile t owns
+ * entries [tile_rec_exc_off[t], tile_rec_exc_off[t+1]) resp. tile_blk_exc_off).  Lossless for every valid sqg_batch whose aux < 16.
  * sqh_pack_wire (squid_b200_host.h) builds it from an sqg_batch.
  */
 #define SQG_WIRE_TILE 512
@@ -124,11 +127,13 @@ typedef struct sqg_wire_rec_exc { uint32_t idx; int32_t ref_id, pos, mate_ref_id
 typedef struct sqg_wire_blk_exc { uint32_t idx; int32_t ref_pos, match_ref; } sqg_wire_blk_exc;                                                        /* 12 B */
 typedef struct sqg_wire {
     int64_t n_rec, n_blk, n_tiles, n_rec_exc, n_blk_exc;
+    int64_t n_wblk;                                                         /* explicit blocks = length of the wire block arrays */
     const int32_t *tile_ref_id, *tile_pos;                                  /* n_tiles */
     const uint32_t *tile_blk_off, *tile_rec_exc_off, *tile_blk_exc_off;     /* n_tiles + 1 each */
+    const uint32_t *tile_wblk_off;                                          /* n_tiles + 1 */
     const uint16_t *dpos, *span; const int16_t *dmate;                      /* n_rec */
     const uint16_t *flag, *total_len; const uint8_t *lowphred_run, *mapq, *aux_nblk;
-    const uint16_t *blk_dref, *blk_match_ref, *blk_read_pos, *blk_match_read; /* n_blk */
+    const uint16_t *blk_dref, *blk_match_ref, *blk_read_pos, *blk_match_read; /* n_wblk */
     const sqg_wire_rec_exc *rec_exc; const sqg_wire_blk_exc *blk_exc;
 } sqg_wire;
 /* sqg_load_concordant() from the wire form: uploaded in record-range chunks on a copy stream, each chunk widened into the

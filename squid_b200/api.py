@@ -45,8 +45,8 @@ class sqg_chimeric(C.Structure):
 
 
 class sqg_wire(C.Structure):  # include/squid_b200.h
-    _fields_ = [(k, C.c_int64) for k in ("n_rec", "n_blk", "n_tiles", "n_rec_exc", "n_blk_exc")] + [(k, C.c_void_p) for k in (
-        "tile_ref_id", "tile_pos", "tile_blk_off", "tile_rec_exc_off", "tile_blk_exc_off", "dpos", "span", "dmate", "flag", "total_len", "lowphred_run", "mapq", "aux_nblk",
+    _fields_ = [(k, C.c_int64) for k in ("n_rec", "n_blk", "n_tiles", "n_rec_exc", "n_blk_exc", "n_wblk")] + [(k, C.c_void_p) for k in (
+        "tile_ref_id", "tile_pos", "tile_blk_off", "tile_rec_exc_off", "tile_blk_exc_off", "tile_wblk_off", "dpos", "span", "dmate", "flag", "total_len", "lowphred_run", "mapq", "aux_nblk",
         "blk_dref", "blk_match_ref", "blk_read_pos", "blk_match_read", "rec_exc", "blk_exc")]
 
 
@@ -238,10 +238,10 @@ class WireBatch:
         w = self.struct
         nt = w.n_tiles
         spec = {"tile_ref_id": (nt, np.int32), "tile_pos": (nt, np.int32), "tile_blk_off": (nt + 1, np.uint32), "tile_rec_exc_off": (nt + 1, np.uint32),
-                "tile_blk_exc_off": (nt + 1, np.uint32), "dpos": (w.n_rec, np.uint16), "span": (w.n_rec, np.uint16), "dmate": (w.n_rec, np.int16),
+                "tile_blk_exc_off": (nt + 1, np.uint32), "tile_wblk_off": (nt + 1, np.uint32), "dpos": (w.n_rec, np.uint16), "span": (w.n_rec, np.uint16), "dmate": (w.n_rec, np.int16),
                 "flag": (w.n_rec, np.uint16), "total_len": (w.n_rec, np.uint16), "lowphred_run": (w.n_rec, np.uint8), "mapq": (w.n_rec, np.uint8),
-                "aux_nblk": (w.n_rec, np.uint8), "blk_dref": (w.n_blk, np.uint16), "blk_match_ref": (w.n_blk, np.uint16), "blk_read_pos": (w.n_blk, np.uint16),
-                "blk_match_read": (w.n_blk, np.uint16), "rec_exc": (w.n_rec_exc, WIRE_REC_EXC), "blk_exc": (w.n_blk_exc, WIRE_BLK_EXC)}
+                "aux_nblk": (w.n_rec, np.uint8), "blk_dref": (w.n_wblk, np.uint16), "blk_match_ref": (w.n_wblk, np.uint16), "blk_read_pos": (w.n_wblk, np.uint16),
+                "blk_match_read": (w.n_wblk, np.uint16), "rec_exc": (w.n_rec_exc, WIRE_REC_EXC), "blk_exc": (w.n_blk_exc, WIRE_BLK_EXC)}
         return {k: _np_from(getattr(w, k) or 0, n, dt) for k, (n, dt) in spec.items()}
 
     def close(self):

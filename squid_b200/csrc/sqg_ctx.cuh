@@ -116,11 +116,11 @@ struct sqg_ctx {
     sq::DBuf<uint8_t> o_mapq, o_aux;
     sq::DBuf<uint32_t> o_blk_off;
     // wire-form upload (sqg_load_concordant_wire): staging of the delta-coded arrays, the copy stream and one event per chunk
-    sq::DBuf<uint16_t> w_dpos, w_span, w_bdref, w_bmref;
+    sq::DBuf<uint16_t> w_dpos, w_span, w_bdref, w_bmref, w_brpos, w_bmread;
     sq::DBuf<int16_t> w_dmate;
     sq::DBuf<uint8_t> w_lp, w_an;
     sq::DBuf<int32_t> w_tile_ref, w_tile_pos;
-    sq::DBuf<uint32_t> w_tile_blk, w_tile_rexc, w_tile_bexc;
+    sq::DBuf<uint32_t> w_tile_blk, w_tile_rexc, w_tile_bexc, w_tile_wblk;
     sq::DBuf<sqg_wire_rec_exc> w_rec_exc;
     sq::DBuf<sqg_wire_blk_exc> w_blk_exc;
     cudaStream_t stream_up = nullptr;

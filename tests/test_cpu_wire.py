@@ -15,11 +15,14 @@ T = 512
 def decode_wire(a: dict, n_rec: int, n_blk: int) -> dict:
     """Numpy restatement of the format's definition."""
     lp = a["lowphred_run"].astype(np.uint16)
-    nb = (a["aux_nblk"] >> 4).astype(np.int64)
+    code = (a["aux_nblk"] >> 4).astype(np.int64)
+    implied = code == 14
+    nb = np.where(implied, 1, code)
     aux = (a["aux_nblk"] & 15).astype(np.uint8)
-    esc = (a["dpos"] == 0xFFFF) | (a["span"] == 0xFFFF) | (a["dmate"] == -32768) | (a["lowphred_run"] == 255) | (nb == 15)
+    esc = (a["dpos"] == 0xFFFF) | (a["span"] == 0xFFFF) | (a["dmate"] == -32768) | (a["lowphred_run"] == 255) | (code == 15)
     e = a["rec_exc"]
     assert np.array_equal(np.flatnonzero(esc), e["idx"].astype(np.int64)), "every escaped record, and only those, is in rec_exc (sorted)"
+    assert not (esc & implied).any(), "a record with an implied block needs no exception entry"
     i = e["idx"].astype(np.int64)
     # positions: the running sum of dpos restarts at every tile head (tile_pos) and at every listed record (its own pos)
     ref = np.zeros(n_rec, np.int32); pos = np.zeros(n_rec, np.int64)
@@ -38,20 +41,35 @@ def decode_wire(a: dict, n_rec: int, n_blk: int) -> dict:
     off = np.zeros(n_rec + 1, np.int64)
     np.cumsum(nb, out=off[1:])
     assert off[-1] == n_blk
-    assert np.array_equal(off[::T][: len(a["tile_blk_off"]) - 1], a["tile_blk_off"][:-1].astype(np.int64)) and a["tile_blk_off"][-1] == n_blk
-    assert np.array_equal(np.searchsorted(e["idx"], np.arange(len(a["tile_rec_exc_off"])) * T), a["tile_rec_exc_off"])
-    rec_of = np.repeat(np.arange(n_rec), nb)
-    rp = pos[rec_of] + a["blk_dref"]
-    ml = a["blk_match_ref"].astype(np.int64)
+    nw = np.where(implied, 0, nb)  # blocks on the wire
+    woff = np.zeros(n_rec + 1, np.int64)
+    np.cumsum(nw, out=woff[1:])
+    n_wblk = int(woff[-1])
+    assert n_wblk == a["blk_dref"].shape[0]
+    nt = len(a["tile_blk_off"]) - 1
+    assert np.array_equal(off[::T][:nt], a["tile_blk_off"][:-1].astype(np.int64)) and a["tile_blk_off"][-1] == n_blk
+    assert np.array_equal(woff[::T][:nt], a["tile_wblk_off"][:-1].astype(np.int64)) and a["tile_wblk_off"][-1] == n_wblk
+    assert np.array_equal(np.searchsorted(e["idx"], np.arange(nt + 1) * T), a["tile_rec_exc_off"])
+    # explicit blocks
+    wrec = np.repeat(np.arange(n_rec), nw)
+    wrp = pos[wrec] + a["blk_dref"]
+    wml = a["blk_match_ref"].astype(np.int64)
     besc = (a["blk_dref"] == 0xFFFF) | (a["blk_match_ref"] == 0xFFFF)
     be = a["blk_exc"]
     assert np.array_equal(np.flatnonzero(besc), be["idx"].astype(np.int64))
-    assert np.array_equal(np.searchsorted(be["idx"], a["tile_blk_off"]), a["tile_blk_exc_off"])
+    assert np.array_equal(np.searchsorted(be["idx"], a["tile_wblk_off"]), a["tile_blk_exc_off"])
     k = be["idx"].astype(np.int64)
-    rp[k], ml[k] = be["ref_pos"], be["match_ref"]
+    wrp[k], wml[k] = be["ref_pos"], be["match_ref"]
+    # blocks of the batch: explicit ones from the wire, implied ones from their record
+    rp = np.zeros(n_blk, np.int64); ml = np.zeros(n_blk, np.int64); rpos = np.zeros(n_blk, np.uint16); mread = np.zeros(n_blk, np.uint16)
+    exp_rec = np.flatnonzero(~implied)
+    dst = np.concatenate([np.arange(off[r], off[r + 1]) for r in exp_rec]) if n_wblk else np.zeros(0, np.int64)
+    rp[dst], ml[dst], rpos[dst], mread[dst] = wrp, wml, a["blk_read_pos"], a["blk_match_read"]
+    imp = np.flatnonzero(implied)
+    rp[off[imp]] = pos[imp]; ml[off[imp]] = a["span"][imp]; rpos[off[imp]] = 0; mread[off[imp]] = a["span"][imp]
     return {"ref_id": ref, "pos": pos.astype(np.int32), "mate_ref_id": mref, "mate_pos": mpos.astype(np.int32), "end_pos": end.astype(np.int32), "flag": a["flag"],
             "total_len": a["total_len"], "lowphred_run": lp, "mapq": a["mapq"], "aux": aux, "blk_off": off.astype(np.uint32), "blk_ref_pos": rp.astype(np.int32),
-            "blk_match_ref": ml.astype(np.int32), "blk_read_pos": a["blk_read_pos"], "blk_match_read": a["blk_match_read"]}
+            "blk_match_ref": ml.astype(np.int32), "blk_read_pos": rpos, "blk_match_read": mread}
 
 
 def adversarial_batch(seed: int, n: int = 3000):
@@ -77,6 +95,18 @@ def adversarial_batch(seed: int, n: int = 3000):
          "blk_ref_pos": (pos[rec_of] + rng.choice([0, 5, 65534, 65535, 70000], size=nblk, p=[.4, .5, .04, .03, .03])).astype(np.int32),
          "blk_match_ref": rng.choice([1, 3, 100, 65534, 65535, 90000], size=nblk, p=[.1, .1, .7, .04, .03, .03]).astype(np.int32),
          "blk_read_pos": rng.integers(0, 65535, nblk).astype(np.uint16), "blk_match_read": rng.integers(0, 65535, nblk).astype(np.uint16)}
+    # a share of the single-block records as plain unclipped reads (the implied block of the format), some of them off by one field
+    one = np.flatnonzero(nb == 1)
+    plain = one[rng.random(one.shape[0]) < 0.6]
+    k = off[plain]
+    sp = np.minimum(span[plain], 60000)
+    a["end_pos"][plain] = (pos[plain] + sp).astype(np.int32)
+    a["blk_ref_pos"][k] = pos[plain].astype(np.int32); a["blk_match_ref"][k] = sp.astype(np.int32)
+    a["blk_read_pos"][k] = 0; a["blk_match_read"][k] = sp.astype(np.uint16)
+    near = plain[rng.random(plain.shape[0]) < 0.15]
+    kn = off[near]
+    which = rng.integers(0, 4, near.shape[0])
+    a["blk_ref_pos"][kn[which == 0]] += 1; a["blk_match_ref"][kn[which == 1]] -= 1; a["blk_read_pos"][kn[which == 2]] = 5; a["blk_match_read"][kn[which == 3]] += 1
     return api.RecordBatch(a)
 
 
@@ -93,6 +123,7 @@ def test_wire_roundtrip_escape_boundaries(seed):
     b = adversarial_batch(seed)
     w = roundtrip(b)
     assert w.struct.n_rec_exc > 0 and w.struct.n_blk_exc > 0
+    assert 0 < w.struct.n_wblk < w.struct.n_blk  # some blocks are implied, some are not
 
 
 def test_wire_roundtrip_synthetic_case(tmp_path):
