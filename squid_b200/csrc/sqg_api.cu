@@ -856,10 +856,13 @@ extern "C" int sqg_load_concordant(sqg_ctx *ctx, const sqg_batch *hb, int64_t fi
     b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
     PHASE_END("h2d");
     ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
-    ctx->wire_loaded = false;
+    ctx->wire_loaded = false; ctx->classify_prelaunched = false;
     return SQG_OK;
 }
 
+static int classify_setup(sqg_ctx *ctx, int64_t cand_cap, P1Out &o);
+static int classify_launch(sqg_ctx *ctx, const P1Out &o, int64_t tiles);
+static_assert(kWireTile == kTile, "a wire tile is a classification tile");
 // Wire-form upload: the chunks go down a copy stream; the main stream waits for each chunk's event and widens it
 // (sq_wire.cuh) while the following chunks are on the bus.
 extern "C" int sqg_load_concordant_wire(sqg_ctx *ctx, const sqg_wire *w, int64_t first_record_index) {
@@ -914,6 +917,25 @@ extern "C" int sqg_load_concordant_wire(sqg_ctx *ctx, const sqg_wire *w, int64_t
     wo.lowphred_run = ctx->o_lowphred_run.p; wo.aux = ctx->o_aux.p; wo.blk_off = ctx->o_blk_off.p; wo.blk_ref_pos = ctx->o_blk_ref_pos.p; wo.blk_match_ref = ctx->o_blk_match_ref.p;
     wo.blk_read_pos = ctx->o_blk_read_pos.p; wo.blk_match_read = ctx->o_blk_match_read.p;
     wo.bad = (int32_t *)(ctx->d_counters.p + 28);
+    DevBatch &b = ctx->batch;
+    b.n_rec = n; b.n_blk = nb;
+    b.ref_id = ctx->o_ref_id.p; b.pos = ctx->o_pos.p; b.mate_ref_id = ctx->o_mate_ref_id.p; b.mate_pos = ctx->o_mate_pos.p; b.end_pos = ctx->o_end_pos.p;
+    b.flag = ctx->o_flag.p; b.total_len = ctx->o_total_len.p; b.lowphred_run = ctx->o_lowphred_run.p; b.mapq = ctx->o_mapq.p; b.aux = ctx->o_aux.p;
+    b.blk_off = ctx->o_blk_off.p; b.blk_ref_pos = ctx->o_blk_ref_pos.p; b.blk_match_ref = ctx->o_blk_match_ref.p;
+    b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
+    // The classification tile kernel needs nothing but the batch: it follows every chunk's widening kernel on the main stream, so
+    // that it, too, runs while the later chunks are on the bus (run_classify then only finishes: scans, lists).  A tile looks at
+    // the first record of the NEXT tile (sortedness), so the last tile of a chunk waits for the next chunk.
+    static const bool pre_classify = !(getenv("SQG_WIRE_CLASSIFY") && atoi(getenv("SQG_WIRE_CLASSIFY")) == 0);
+    P1Out pre_o;
+    ctx->classify_prelaunched = false;
+    if (pre_classify && nt > 0) {
+        ctx->pre_cand_cap = std::min<int64_t>(std::max<int64_t>({(int64_t)ctx->d_cand_key.cap, n / 16, (int64_t)1 << 20}), n + 1);
+        const int rc_ = classify_setup(ctx, ctx->pre_cand_cap, pre_o);
+        if (rc_) return rc_;
+        ctx->classify_prelaunched = true;
+    }
+    int64_t tiles_classified = 0;
     static const int n_chunks_env = getenv("SQG_WIRE_CHUNKS") ? atoi(getenv("SQG_WIRE_CHUNKS")) : 16;
     const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks_env, nt));
     while ((int64_t)ctx->ev_up.size() < n_chunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up.push_back(e); }
@@ -931,15 +953,15 @@ extern "C" int sqg_load_concordant_wire(sqg_ctx *ctx, const sqg_wire *w, int64_t
         k_wire_decode<<<(unsigned)(t1 - t0), kWireTile, 0, ctx->stream>>>(wd, wo, t0);
         ctx->launches++;
         CK(cudaGetLastError());
+        if (ctx->classify_prelaunched) {
+            const int64_t upto = t1 == nt ? nt : t1 - 1;
+            const int rc_ = classify_launch(ctx, pre_o, upto - tiles_classified);
+            if (rc_) return rc_;
+            if (upto > tiles_classified) tiles_classified = upto;
+        }
     }
 #undef UPW
     if (n == 0) CK(cudaMemsetAsync(ctx->o_blk_off.p, 0, sizeof(uint32_t), ctx->stream));
-    DevBatch &b = ctx->batch;
-    b.n_rec = n; b.n_blk = nb;
-    b.ref_id = ctx->o_ref_id.p; b.pos = ctx->o_pos.p; b.mate_ref_id = ctx->o_mate_ref_id.p; b.mate_pos = ctx->o_mate_pos.p; b.end_pos = ctx->o_end_pos.p;
-    b.flag = ctx->o_flag.p; b.total_len = ctx->o_total_len.p; b.lowphred_run = ctx->o_lowphred_run.p; b.mapq = ctx->o_mapq.p; b.aux = ctx->o_aux.p;
-    b.blk_off = ctx->o_blk_off.p; b.blk_ref_pos = ctx->o_blk_ref_pos.p; b.blk_match_ref = ctx->o_blk_match_ref.p;
-    b.blk_read_pos = ctx->o_blk_read_pos.p; b.blk_match_read = ctx->o_blk_match_read.p;
     PHASE_END("h2d");
     ctx->have_batch = true; ctx->batch_owned = true; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
     ctx->wire_loaded = true;
@@ -1016,7 +1038,7 @@ extern "C" int sqg_attach_concordant_device(sqg_ctx *ctx, const sqg_batch *db, i
     b.flag = db->flag; b.total_len = db->total_len; b.lowphred_run = db->lowphred_run; b.mapq = db->mapq; b.aux = db->aux;
     b.blk_off = db->blk_off; b.blk_ref_pos = db->blk_ref_pos; b.blk_match_ref = db->blk_match_ref; b.blk_read_pos = db->blk_read_pos; b.blk_match_read = db->blk_match_read;
     ctx->have_batch = true; ctx->batch_owned = false; ctx->classified = false; ctx->cov_compacted = false; ctx->have_edge_table = false; ctx->first_record_index = first_record_index;
-    ctx->wire_loaded = false;
+    ctx->wire_loaded = false; ctx->classify_prelaunched = false;
     return SQG_OK;
 }
 
@@ -1340,48 +1362,70 @@ static bool batch_bulk_ok(const DevBatch &b) {  // TMA bulk copies need 16-byte 
 static constexpr size_t kTileSmemBytes = sizeof(TileStage) + 128;
 
 // classify stage (phase 1): class bytes, gap / partial / displaced lists, first kept record, lmax; validates the batch
+// Classification, part 1: buffers, counters and the kernel's argument block for a batch of n records (cand_cap candidates).
+static int classify_setup(sqg_ctx *ctx, int64_t cand_cap, P1Out &o) {
+    const DevBatch &b = ctx->batch;
+    const int64_t n = b.n_rec, n_tiles = (n + kTile - 1) / kTile;
+    CK(ctx->d_cls.ensure(n + 4)); CK(ctx->d_flen.ensure(n + 4)); CK(ctx->d_scratch32.ensure(n + 1));
+    CK(ctx->d_counters.ensure(32)); CK(ctx->h_counters.ensure(32));
+    CK(ctx->d_qstage_key.ensure((size_t)n + 1)); CK(ctx->d_qstage_end.ensure((size_t)n + 1));
+    CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8)); CK(ctx->d_ccmax.ensure(n_tiles + 1)); CK(ctx->d_cov_nq.ensure(n_tiles + 2)); CK(ctx->d_cov_qmax.ensure(n_tiles + 2));
+    CK(ctx->d_cand_key.ensure(cand_cap));
+    o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.ccmax = ctx->d_ccmax.p; o.cov_nq = ctx->d_cov_nq.p; o.cov_qmax = ctx->d_cov_qmax.p; o.qstage_key = ctx->d_qstage_key.p; o.qstage_end = ctx->d_qstage_end.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
+    o.cand_rec = ctx->d_scratch32.p; o.cand_key = ctx->d_cand_key.p; o.cand_cap = (int32_t)cand_cap;
+    // counters: [0..1] totals n_gap, n_pc, n_dp (int32) | [2] first_kept | [3] lmax | [4] n_cand, ticket (int32) | [20] validation flags
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 5 * sizeof(int64_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p + 20, 0, sizeof(int64_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_chain64.p, 0, n_tiles * sizeof(uint64_t), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_counters.p + 2, &n, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    o.first_kept = (long long *)(ctx->d_counters.p + 2); o.lmax = (int32_t *)(ctx->d_counters.p + 3);
+    o.n_cand = (int32_t *)(ctx->d_counters.p + 4); o.ticket = o.n_cand + 1;
+    o.bad_flags = (int32_t *)(ctx->d_counters.p + 20);
+    {
+        BatchDesc hd; hd.b = b; hd.p = ctx->params;
+        CK(ctx->d_desc.ensure(sizeof(BatchDesc)));
+        CK(cudaMemcpyAsync(ctx->d_desc.p, &hd, sizeof(BatchDesc), cudaMemcpyHostToDevice, ctx->stream));  // pageable source: staged before the call returns
+        o.desc = (const BatchDesc *)ctx->d_desc.p;
+    }
+    CK(cudaFuncSetAttribute(k_classify_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+    return SQG_OK;
+}
+// part 2: the next `tiles` tiles of the batch (a tile takes its index from a ticket, so consecutive launches continue each other)
+static int classify_launch(sqg_ctx *ctx, const P1Out &o, int64_t tiles) {
+    if (tiles <= 0) return SQG_OK;
+    const DevBatch &b = ctx->batch;
+    k_classify_tiles<<<(unsigned)tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, ctx->params, o, batch_bulk_ok(b) ? 1 : 0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SQG_OK;
+}
+
 static int run_classify(sqg_ctx *ctx) {
     if (ctx->classified) return SQG_OK;
     { const int rcj = cov_join(ctx); if (rcj) return rcj; }
     const DevBatch &b = ctx->batch;
     const int64_t n = b.n_rec;
     PHASE_BEGIN("classify");
-    CK(ctx->d_cls.ensure(n + 4)); CK(ctx->d_flen.ensure(n + 4)); CK(ctx->d_scratch32.ensure(n + 1));
     CK(ctx->d_counters.ensure(32)); CK(ctx->h_counters.ensure(32));
     ctx->n_gap = 0; ctx->n_pc = 0; ctx->n_dp = 0; ctx->lmax = 0; ctx->first_kept = n; ctx->end_other = 0;
     if (n > 0) {
         const int64_t n_tiles = (n + kTile - 1) / kTile;
-        CK(ctx->d_qstage_key.ensure((size_t)n + 1)); CK(ctx->d_qstage_end.ensure((size_t)n + 1));
-        CK(ctx->d_tileagg.ensure(n_tiles + 1)); CK(ctx->d_chain64.ensure(n_tiles + 8)); CK(ctx->d_ccmax.ensure(n_tiles + 1)); CK(ctx->d_cov_nq.ensure(n_tiles + 2)); CK(ctx->d_cov_qmax.ensure(n_tiles + 2));
         int64_t cand_cap = std::max<int64_t>({(int64_t)ctx->d_cand_key.cap, n / 16, (int64_t)1 << 20});
         int32_t n_cand = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             cand_cap = std::min<int64_t>(cand_cap, n + 1);
-            CK(ctx->d_cand_key.ensure(cand_cap));
-            P1Out o;
-            o.cls = ctx->d_cls.p; o.first_len = ctx->d_flen.p; o.agg = ctx->d_tileagg.p; o.ccmax = ctx->d_ccmax.p; o.cov_nq = ctx->d_cov_nq.p; o.cov_qmax = ctx->d_cov_qmax.p; o.qstage_key = ctx->d_qstage_key.p; o.qstage_end = ctx->d_qstage_end.p; o.gate_word = ctx->d_chain64.p; o.n_tiles = (int32_t)n_tiles;
-            o.cand_rec = ctx->d_scratch32.p; o.cand_key = ctx->d_cand_key.p; o.cand_cap = (int32_t)cand_cap;
-            // counters: [0..1] totals n_gap, n_pc, n_dp (int32) | [2] first_kept | [3] lmax | [4] n_cand, ticket (int32) | [20] validation flags
-            CK(cudaMemsetAsync(ctx->d_counters.p, 0, 5 * sizeof(int64_t), ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_counters.p + 20, 0, sizeof(int64_t), ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_chain64.p, 0, n_tiles * sizeof(uint64_t), ctx->stream));
-            CK(cudaMemcpyAsync(ctx->d_counters.p + 2, &n, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
             int32_t *totals = (int32_t *)ctx->d_counters.p;
-            o.first_kept = (long long *)(ctx->d_counters.p + 2); o.lmax = (int32_t *)(ctx->d_counters.p + 3);
-            o.n_cand = (int32_t *)(ctx->d_counters.p + 4); o.ticket = o.n_cand + 1;
-            o.bad_flags = (int32_t *)(ctx->d_counters.p + 20);
-            {
-                BatchDesc hd; hd.b = b; hd.p = ctx->params;
-                CK(ctx->d_desc.ensure(sizeof(BatchDesc)));
-                CK(cudaMemcpyAsync(ctx->d_desc.p, &hd, sizeof(BatchDesc), cudaMemcpyHostToDevice, ctx->stream));  // pageable source: staged before the call returns
-                o.desc = (const BatchDesc *)ctx->d_desc.p;
+            if (attempt == 0 && ctx->classify_prelaunched) {
+                // the tile kernel already ran, chunk by chunk, behind the widening kernels of the wire upload
+                cand_cap = ctx->pre_cand_cap;
+                ctx->classify_prelaunched = false;
+            } else {
+                P1Out o;
+                { const int rc_ = classify_setup(ctx, cand_cap, o); if (rc_) return rc_; }
+                PHASE_BEGIN("k_classify");
+                { const int rc_ = classify_launch(ctx, o, n_tiles); if (rc_) return rc_; }
+                PHASE_END("k_classify");
             }
-            CK(cudaFuncSetAttribute(k_classify_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-            PHASE_BEGIN("k_classify");
-            k_classify_tiles<<<(unsigned)n_tiles, kTileThreads, kTileSmemBytes, ctx->stream>>>(b, ctx->params, o, batch_bulk_ok(b) ? 1 : 0);
-            ctx->launches++;
-            CK(cudaGetLastError());
-            PHASE_END("k_classify");
             LAUNCH(k_tile_scan, 1, 1024, ctx->d_tileagg.p, (int32_t)n_tiles, totals, (uint64_t *)(ctx->d_counters.p + 21));
             CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(ctx->h_counters.p + 20, ctx->d_counters.p + 20, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -126,6 +126,9 @@ struct sqg_ctx {
     cudaStream_t stream_up = nullptr;
     std::vector<cudaEvent_t> ev_up;
     bool wire_loaded = false;
+    // classification launched chunk by chunk behind the widening kernels of a wire upload (run_classify then only finishes it)
+    bool classify_prelaunched = false;
+    int64_t pre_cand_cap = 0;
 
     // classify products
     sq::DBuf<uint8_t> d_cls;
