@@ -223,7 +223,7 @@ def same_input_leg(cp, hp, ref, n_pairs, device):
     from oracle import pyref
     from squid_b200 import api
     best = None
-    for it in range(3):  # the first pass pays the allocations of a fresh context
+    for it in range(5):  # the first pass pays the allocations of a fresh context
         t0 = time.perf_counter()
         case = api.HostCase(cp, hp)
         t1 = time.perf_counter()
@@ -244,7 +244,7 @@ def same_input_leg(cp, hp, ref, n_pairs, device):
         if not ok:
             break
     best.update({"pairs": int(n_pairs), "value": n_pairs / best["seconds"], "unit": "read pairs/s", "outputs_equal_reference": bool(ok), "host_threads": os.cpu_count(),
-                 "what": "same two input tables as the reference run; timed from opening them to the support map: host decode/pack on all cores + upload + CUDA path (best of 3)"})
+                 "what": "same two input tables as the reference run; timed from opening them to the support map: host decode/pack on all cores + upload + CUDA path (best of 5)"})
     return best
 
 
