@@ -137,7 +137,7 @@ typedef struct sqg_wire {
     const sqg_wire_rec_exc *rec_exc; const sqg_wire_blk_exc *blk_exc;
 } sqg_wire;
 /* sqg_load_concordant() from the wire form: uploaded in record-range chunks on a copy stream, each chunk widened into the
- * resident sqg_batch layout by k_wire_decode while the next ones are still in flight.  Page-locked arrays make the copies
+ * resident sqg_batch layout by k_wire_decode -- and classified -- while the next ones are still in flight.  Page-locked arrays make the copies
  * asynchronous.  An inconsistent wire batch is reported (SQG_EINVAL) by the next sqg_build_nodes/sqg_build_edges/sqg_bp_coverage. */
 int sqg_load_concordant_wire(sqg_ctx *ctx, const sqg_wire *wire, int64_t first_record_index);
 /* Copies the resident batch back into caller-allocated host arrays of `out` (n_rec / n_blk must match): the check that a wire
