@@ -164,7 +164,7 @@ int pack_concordant(const AlnSource &conc, const HostConfig &cfg, const std::uno
             out.flag[r] = a.flag; out.mapq[r] = a.mapq;
             decode_alignment(a, cfg, d);
             if (d.blocks.size() > 16) { terr[t] = "record " + std::to_string(r) + " has more than 16 aligned blocks"; return; }
-            out.end_pos[r] = a.end_pos();
+            out.end_pos[r] = d.end_pos;
             // the batch keeps read coordinates in 16 bits (include/squid_b200.h): a longer read is refused, never wrapped
             if (d.total_len > 65535) { terr[t] = "record " + std::to_string(r) + " is longer than 65535 bases (TotalLen " + std::to_string(d.total_len) + ")"; return; }
             out.total_len[r] = (uint16_t)d.total_len;

@@ -31,11 +31,14 @@ int32_t Alignment::end_pos() const {
 void decode_alignment(const Alignment &a, const HostConfig &cfg, Decoded &out) {
     out.blocks.clear();
     int total = 0;
+    int32_t end = a.pos;
     for (uint32_t i = 0; i < a.n_cigar; i++) {
         uint32_t op = op_of(a.cigar[i]);
         if (op == OP_M || op == OP_S || op == OP_H || op == OP_I || op == OP_EQ || op == OP_X) total += len_of(a.cigar[i]);
+        if (op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X) end += len_of(a.cigar[i]);
     }
     out.total_len = total;
+    out.end_pos = end;
 
     const int thr = (cfg.phred33 ? 33 : 64) + cfg.min_phred;
     int best = 0;
